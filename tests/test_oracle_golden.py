@@ -1,0 +1,119 @@
+"""Pins the CPU oracle (oracle/ref_path.py) against fixtures produced by the
+unmodified reference (tests/golden/make_golden.py) and the reference's one KAT."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_path as rp
+import det_weights as dw
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def L(name):
+    d = np.load(os.path.join(G, name))
+    return {k: torch.from_numpy(np.asarray(d[k])) for k in d.files}
+
+
+def test_kat_parametrizer():
+    # ops/parametrizers.py:52-58 -- values the reference prints
+    k = json.load(open(os.path.join(G, "kat_parametrizer.json")))
+    gi = rp.nonneg_init(0.1 * torch.eye(5))
+    gf = rp.nonneg_forward(gi)
+    assert torch.equal(gi, torch.tensor(k["init"]))
+    assert torch.equal(gf, torch.tensor(k["forward"]))
+    assert abs(gi[0, 0].item() - 3.1623e-01) < 5e-6 and abs(gi[0, 1].item() - 3.8147e-06) < 5e-11
+    assert abs(gf[0, 0].item() - 0.1) < 1e-7 and gf[0, 1].item() == 0.0
+
+
+def test_leaf_ops_bit_exact():
+    d = L("leaf_ops.npz")
+    assert torch.equal(rp.lower_bound(d["lb_x"], 0.11), d["lb_out"])
+    assert torch.equal(rp.lower_bound_grad(d["lb_x"], torch.tensor(0.11), d["lb_gout"]), d["lb_grad"])
+    assert torch.equal(rp.lower_bound(d["lb_x"], 0.05), d["mlb_out"])
+    assert torch.equal(rp.lower_bound_grad(d["lb_x"], torch.tensor(0.05), d["lb_gout"]), d["mlb_grad"])
+    assert torch.equal(rp.ste_round(d["rnd_in"]), d["ste_round"])
+    assert torch.equal(rp.bypass_round(d["rnd_in"]), d["bypass_round"])
+    assert torch.equal(rp.nonneg_forward(d["nn_p"]), d["nn_fwd_min0"])
+    assert torch.equal(rp.nonneg_forward(d["nn_p"], minimum=1e-6), d["nn_fwd_beta"])
+    assert torch.equal(rp.nonneg_init(d["nn_p"]), d["nn_init"])
+    bb, gb, ped = rp.model_gdn_constants()
+    assert [bb, gb, ped] == d["model_gdn_consts"].tolist()
+    b2, p2 = rp.parametrizer_constants(1e-6)
+    g2, _ = rp.parametrizer_constants(0.0)
+    assert [b2, g2, p2] == d["layers_gdn_consts"].tolist()
+
+
+def test_gdn_variants_bit_exact():
+    d = L("leaf_ops.npz")
+    x, bp, gp = d["x"], d["beta_p"], d["gamma_p"]
+    assert torch.equal(rp.gdn_model(x, bp, gp, False), d["model_gdn"])
+    assert torch.equal(rp.gdn_model(x, bp, gp, True), d["model_igdn"])
+    assert torch.equal(rp.gdn_layers(x, bp, gp, False), d["layers_gdn_inv0"])
+    assert torch.equal(rp.gdn_layers(x, bp, gp, True), d["layers_gdn_inv1"])
+    # model/ops.py:106-136 is the same arithmetic as model/gdn.py
+    assert torch.equal(rp.gdn_model(x, bp, gp, False), d["model_ops_gdn_inv0"])
+    assert torch.equal(rp.gdn_model(x, bp, gp, True), d["model_ops_gdn_inv1"])
+
+
+def test_gaussian_model_bit_exact():
+    d = L("gaussian_model.npz")
+    assert torch.equal(rp.bypass_round(d["v"]), d["v_rounded"])
+    lik = rp.gaussian_model_likelihood(d["v_rounded"], d["sigma"], d["mu"])
+    # NaN where sigma == 0 (reference quirk H2) must match position-wise
+    assert torch.equal(torch.isnan(lik), torch.isnan(d["lik"]))
+    m = ~torch.isnan(lik)
+    assert torch.equal(lik[m], d["lik"][m])
+    zl = rp.gaussian_model_likelihood(d["z_rounded"], d["z_sigma"], torch.zeros_like(d["z_sigma"]))
+    assert torch.equal(zl, d["z_lik"])
+
+
+def test_block_sample_gather_equals_onehot():
+    r = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 6, 7, generator=r)
+    for masked in (True, False):
+        assert torch.equal(rp.block_sample_gather(x, masked), rp.block_sample_onehot(x, masked))
+
+
+@pytest.mark.parametrize("name", ["net_64x64_b1.npz", "net_64x128_b2.npz", "net_evalpad_60x50.npz"])
+def test_net_forward_full(name):
+    d = L(name)
+    B, H, W, th, tw = (int(d[k]) for k in ("B", "H", "W", "th", "tw"))
+    sd = dw.make_state_dict(int(d["seed"]), boost=bool(int(d["boost"])))
+    x = rp.eval_pad(d["img"]) if "img" in d else dw.make_input(int(d["seed"]), B, H, W)
+    with torch.no_grad():
+        o = rp.net_forward_test(sd, x, (B, th, tw, 3))
+    for k in ("z3", "z2", "h2", "mu", "sigma", "z2_lik", "y_lik", "syn_lik", "x_tilde16", "z3_syntax", "conv_weights"):
+        assert torch.equal(o[k], d[k]), k
+    # reference binds prediction_model_syntax's (mu, sigma) as (sigma, mu): model/net.py:789 vs :413
+    assert torch.equal(o["syn_sigma"], d["syn_first"]) and torch.equal(o["syn_mu"], d["syn_second"])
+    for k in ("bpp", "v_mse", "v_psnr"):
+        assert torch.equal(o[k], d[k]), k
+
+
+def test_net_forward_faithful_sampler_matches():
+    d = L("net_64x64_b1.npz")
+    sd = dw.make_state_dict(0)
+    x = dw.make_input(0, 1, 64, 64)
+    with torch.no_grad():
+        o = rp.net_forward_test(sd, x, (1, 64, 64, 3), faithful_sampler=True)
+    assert torch.equal(o["bpp"], d["bpp"]) and torch.equal(o["y_lik"], d["y_lik"])
+
+
+def test_net_default_gain_and_config1():
+    d = L("net_64x64_default_gain.npz")
+    with torch.no_grad():
+        o = rp.net_forward_test(dw.make_state_dict(0, boost=False), dw.make_input(0, 1, 64, 64), (1, 64, 64, 3))
+    for k in ("bpp", "v_mse", "v_psnr", "z3", "z2"):
+        assert torch.equal(o[k], d[k]), k
+    d = L("net_256x256_b1.npz")
+    with torch.no_grad():
+        o = rp.net_forward_test(dw.make_state_dict(0), dw.make_input(0, 1, 256, 256), (1, 256, 256, 3))
+    assert torch.equal(o["z3"], d["z3"]) and torch.equal(o["z2"], d["z2"])
+    assert torch.equal(o["x_tilde16"][:, :, ::8, ::8], d["x_tilde16_sub"])
+    # thread-count dependent summation order in torch.sum: compare scalars to 1e-6
+    for k in ("bpp", "v_mse", "v_psnr", "bits"):
+        assert torch.allclose(o[k], d[k], rtol=2e-6, atol=0), k
