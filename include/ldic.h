@@ -1,0 +1,193 @@
+/*
+ * ldic.h -- C ABI of libldic_b200.so: the B200 (sm_100a) rate-distortion forward
+ * path of xiaobucc/learning-driven-image-compression-algorithm.
+ *
+ * The reference has no FFI of its own (it is 100% Python/PyTorch);
+ * the boundary is its nn.Module surface.  Each entry point below names the
+ * reference code it replaces (file:line relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *    name ends in _host;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    never synchronises, never uses the default stream implicitly, and
+ *    allocates no device memory: outputs and workspaces are caller-owned;
+ *  - returns 0 on success, a negative LDIC_E* code otherwise; the message is
+ *    available from ldic_last_error() (thread local);
+ *  - activations inside the transforms are NHWC ("channels-last") bf16 unless
+ *    stated; module-surface tensors are NCHW fp32 like the reference's.
+ */
+#ifndef LDIC_H_
+#define LDIC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LDIC_API __attribute__((visibility("default")))
+#else
+#define LDIC_API
+#endif
+
+#define LDIC_OK 0
+#define LDIC_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define LDIC_ECUDA (-2)    /* a CUDA runtime / driver call failed         */
+#define LDIC_ENOTSUP (-3)  /* device is not sm_100                        */
+
+LDIC_API int ldic_version(void);
+LDIC_API const char* ldic_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's
+ * gpu_launches).  */
+LDIC_API long long ldic_launch_count(void);
+/* 0 when device `dev` is compute capability 10.x, LDIC_ENOTSUP otherwise. */
+LDIC_API int ldic_check_device(int dev);
+
+/* ---- a3: LowerBound + NonNegativeParametrizer ---------------------------------
+ * y = max(x, bound)                                   ops/bound_ops.py:21-22
+ * dx = (x >= bound || g < 0) ? g : 0                  ops/bound_ops.py:25-27, model/gdn.py:19-26 */
+LDIC_API int ldic_lower_bound(const float* x, float bound, float* y, size_t n, void* stream);
+LDIC_API int ldic_lower_bound_bwd(const float* x, float bound, const float* grad_out, float* grad_in, size_t n, void* stream);
+/* out = max(p, bound)^2 - pedestal                    ops/parametrizers.py:46-49, model/gdn.py:75-81 */
+LDIC_API int ldic_nonneg_reparam(const float* p, float bound, float pedestal, float* out, size_t n, void* stream);
+
+/* beta_eff[C], gamma_eff[C*C] (fp32) from the stored (reparametrised) parameters;
+ * optionally also the bf16 operand image of gamma used by the tensor-core GDN
+ * epilogue: gamma_bf16 is [Np][Kp] row-major (row i = output channel), built as
+ * `groups` block-diagonal copies of the CxC matrix, zero elsewhere; beta_tiled is
+ * [Np] fp32 (beta repeated per group, 1.0 in the padding).  Pass NULL to skip.
+ * model/gdn.py:75-81,140-146; layers/gdn.py:65-67.                               */
+LDIC_API int ldic_gdn_prepare(const float* beta_p, const float* gamma_p, int C,
+                     float beta_bound, float gamma_bound, float pedestal,
+                     float* beta_eff, float* gamma_eff,
+                     void* gamma_bf16, float* beta_tiled, int groups, int Np, int Kp,
+                     void* stream);
+
+/* ---- a2: stand-alone GDN / IGDN on the module surface (NCHW fp32) -------------
+ * y = x * rsqrt(beta + gamma . x^2)   (inverse=0)   or   x * sqrt(...) (inverse=1)
+ * layers/gdn.py:62-75, model/gdn.py:69-92,134-156, model/ops.py:106-136.
+ * fp32 CUDA-core kernel (bit-faithful op order except the summation order).     */
+LDIC_API int ldic_gdn_nchw_f32(const float* x, const float* beta_eff, const float* gamma_eff, float* y,
+                      int B, int C, int H, int W, int inverse, int use_rsqrt, void* stream);
+
+/* ---- a6+a7+a8+a9: quantise, Gaussian likelihood, sum(ln L) --------------------
+ * One pass over a logical [rows x cols] problem.  Tensor t is addressed as
+ *   t[row * t_rs + t_off + col]            (t_rs = row stride in elements)
+ * so NHWC channel slices need no copies.  mu / sigma can be per element (mode 2),
+ * per column i.e. per channel (mode 1, pointer to `cols` floats) or absent
+ * (mode 0: mu = 0).  NCHW tensors with per-channel sigma use rows = B*C, cols = H*W
+ * and mode 3 (per row, index row % sigma_period).
+ *
+ * quant: 0 = v already quantised; 1 = round(v) half-to-even (BypassRound,
+ *        model/net.py:416-426); 2 = round(v - mu) + mu (CompressAI "dequantize",
+ *        model/net_unet_ha_hs.py:937); 3 = (round(v) - v) + v (ste_round,
+ *        ops/ops.py:34).
+ * form:  0 = GaussianModel  Phi((v-mu+.5)/s) - Phi((v-mu-.5)/s), Phi via erf,
+ *            clamp(min=lik_bound), NO sigma bound (model/net.py:272-286);
+ *        1 = GaussianConditional: |v-mu|, s = max(s, scale_bound), erfc form,
+ *            max(L, lik_bound) (model/Net_unet.py:1057).
+ * sigma_is_log: sigma tensor holds log-sigma; exp() is applied first
+ *            (model/net.py:316).
+ * Outputs (any may be NULL): v_hat (fp32, same addressing as v_hat_rs/off),
+ * v_hat_bf16 (bf16 copy for the synthesis transform), lik (fp32, dense
+ * [rows x cols]).  sum_ln_out[0] receives sum(ln L) over the whole problem
+ * (deterministic two-level reduction; NaNs propagate like the reference).
+ * `workspace` must hold ldic_likelihood_workspace_bytes() bytes and be zeroed
+ * once before the first use (the kernel leaves it zeroed).                      */
+typedef struct {
+  const float* v;      long long v_rs;      long long v_off;
+  const float* mu;     long long mu_rs;     long long mu_off;     int mu_mode;
+  const float* sigma;  long long sigma_rs;  long long sigma_off;  int sigma_mode;
+  int sigma_period;    /* mode 3: sigma index = row % sigma_period */
+  long long rows, cols;
+  int quant, form, sigma_is_log;
+  float lik_bound, scale_bound;
+  float* v_hat;        long long v_hat_rs;  long long v_hat_off;
+  void* v_hat_bf16;    long long vb_rs;     long long vb_off;
+  float* lik;
+  float* sum_ln_out;
+  void* workspace;
+} LdicLikelihoodArgs;
+LDIC_API size_t ldic_likelihood_workspace_bytes(void);
+LDIC_API int ldic_round_likelihood_bpp(const LdicLikelihoodArgs* args, void* stream);
+
+/* ---- a11: MSE / PSNR on 8-bit levels --------------------------------------------
+ * gt = round((x+1)*127.5); xh = round(clamp((xt+1)*127.5, 0, 255));
+ * sq_err[b] = sum((xh-gt)^2) as an exact 64-bit integer; the caller divides by
+ * C*H*W and forms 20*log10(255/sqrt(mse)).  model/net.py:864-869;
+ * clamp_pm1 != 0 adds clamp(xt,-1,1) first (model/net_unet_ha_hs.py:1006).
+ * sq_err must be zeroed by the caller (it is accumulated into).                */
+LDIC_API int ldic_mse_sum(const float* x, const float* x_tilde, int B, long long chw, int clamp_pm1,
+                 unsigned long long* sq_err, void* stream);
+/* Fused tail of Net.forward: per-image 1x1 conv (batch_conv, model/net.py:527-537)
+ * of the 16-channel NHWC fp32 synthesis output with weights w[B][3][M], then the
+ * a11 arithmetic against the NCHW fp32 input x.  x_tilde_nchw (optional) receives
+ * the reconstruction.                                                           */
+LDIC_API int ldic_syntax_conv_mse(const float* x_nchw, const float* xt_nhwc, const float* w, int B, int M,
+                         int H, int W, float* x_tilde_nchw, unsigned long long* sq_err, void* stream);
+
+/* ---- layout / dtype glue ------------------------------------------------------------ */
+/* NCHW fp32 -> NHWC bf16 (channels padded to Cp with zeros) and back.            */
+LDIC_API int ldic_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, int Cp, int apply_abs, void* stream);
+LDIC_API int ldic_nhwc_to_nchw_f32(const void* x, int x_is_bf16, float* y, int B, int C, int H, int W, int Cp, void* stream);
+/* y (NHWC fp32, C channels) -> optional outputs: round(y) bf16, |y| bf16, round(y) fp32.
+ * model/net.py:197 (abs), :676/:741 (round).                                     */
+LDIC_API int ldic_latent_prep(const float* y, size_t n, void* y_round_bf16, void* y_abs_bf16, float* y_round_f32, void* stream);
+/* First-layer patch matrix: x NCHW fp32 (B,3,H,W) -> A[B*Ho*Wo][Kp] bf16 with
+ * A[p][(ky*5+kx)*Cin+ci] = x[ci, 2oy+ky-1, 2ox+kx-1] (zero outside), zero for
+ * k >= 25*Cin.  model/net.py:97-98 (ZeroPad2d((1,2,1,2)) + Conv2d k5 s2).       */
+LDIC_API int ldic_im2col_5x5s2(const float* x, void* a, int B, int Cin, int H, int W, int Kp, void* stream);
+
+/* ---- a1/a4/a5/a10: tensor-core implicit-GEMM convolutions ---------------------------- */
+enum {
+  LDIC_CONV_S2_5x5_P12 = 0,   /* ZeroPad2d((1,2,1,2)) + Conv2d(k5,s2,p0)      model/net.py:97-112   */
+  LDIC_CONV_S2_5x5_P2 = 1,    /* Conv2d(k5,s2,p2)                             model/net.py:191-193  */
+  LDIC_CONV_S1_3x3_P1 = 2,    /* Conv2d(k3,s1,p1)                             model/net.py:189      */
+  LDIC_CONV_1x1 = 3,          /* GEMM over pixels (first layer after im2col)                        */
+  LDIC_DECONV_GS_5x5 = 4,     /* ZeroPad2d((1,0,1,0)) + ConvTranspose2d(k5,s2,p3,op1) model/net.py:128-142 */
+  LDIC_DECONV_HS_5x5 = 5,     /* ConvTranspose2d(k5,s2,p2,op1)                model/net.py:207-209  */
+  LDIC_DECONV_S1_3x3 = 6,     /* ConvTranspose2d(k3,s1,p1)                    model/net.py:211      */
+  LDIC_DECONV_GS_5x5_MERGED = 7 /* same as 4 with the 4 sub-pixel phases merged into N (small Cout) */
+};
+enum { LDIC_ACT_NONE = 0, LDIC_ACT_RELU = 1, LDIC_ACT_LEAKY02 = 2, LDIC_ACT_GDN = 3, LDIC_ACT_IGDN = 4 };
+
+typedef struct {
+  int kind;           /* LDIC_CONV_* */
+  int B, H, W;        /* input (NHWC) batch and spatial size                     */
+  int Cin, Cout;      /* logical channel counts of the layer                     */
+  int Cin_pad;        /* channels of the input tensor in memory (multiple of 64) */
+  int Cout_pad;       /* channels of the output tensor in memory                 */
+  int act;            /* LDIC_ACT_*                                              */
+  int out_f32;        /* 0: bf16 NHWC output, 1: fp32 NHWC output                */
+} LdicConvDesc;
+
+/* Elements (bf16) of the packed weight image for this layer, and the packer:
+ * w is the state-dict tensor, (Cout,Cin,k,k) for Conv2d or (Cin,Cout,k,k) for
+ * ConvTranspose2d; cin_offset places the Cin logical channels inside Cin_pad
+ * (used to feed the full 192-channel latent to the 176-channel g_s input,
+ * model/net.py:726).  bias_packed is [Np] fp32.                                */
+LDIC_API long long ldic_conv_weight_elems(const LdicConvDesc* d);
+LDIC_API int ldic_conv_n_cols(const LdicConvDesc* d);  /* Np: accumulator columns          */
+LDIC_API int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, const float* bias, int cin_offset,
+                           void* w_packed, float* bias_packed, void* stream);
+LDIC_API void ldic_conv_out_shape(const LdicConvDesc* d, int* Ho, int* Wo);
+/* y = act(conv(x) + bias); for LDIC_ACT_GDN / IGDN the normalisation
+ * x * rsqrt|sqrt(beta + gamma . x^2) runs in the epilogue on the tensor cores
+ * (gamma_bf16 / beta_tiled from ldic_gdn_prepare).                              */
+LDIC_API int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                      const void* gamma_bf16, const float* beta_tiled, void* y, void* stream);
+/* Plain CUDA-core fp32 direct convolution of the same layer kinds on NHWC fp32
+ * tensors (validation aid for the tensor-core path at sizes the CPU oracle
+ * cannot reach; not used by the product forward).                               */
+LDIC_API int ldic_conv_forward_f32_reference_kernel(const LdicConvDesc* d, const float* x_nhwc, const float* w,
+                                           const float* bias, float* y_nhwc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDIC_H_ */

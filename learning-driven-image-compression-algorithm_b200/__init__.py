@@ -1,0 +1,17 @@
+"""ldic_b200 -- B200 (sm_100a) rate-distortion forward path of
+xiaobucc/learning-driven-image-compression-algorithm behind the reference's nn.Module surface.
+
+The directory name carries the reference's (hyphenated) name; import it as ``ldic_b200``
+(repo-root shim ``ldic_b200.py``).
+"""
+from . import _lib, ops                                     # noqa: F401
+from ._lib import LdicError, EXPORTED_SYMBOLS, lib_path     # noqa: F401
+from .layers import (GDN, GaussianConditional, GaussianModel, LowerBound, ModelGDN, ModelIGDN,   # noqa: F401
+                     NonNegativeParametrizer, bypass_round, ste_round, psnr_from_sq_err)
+from .transforms import (analysisTransformModel, synthesisTransformModel, h_analysisTransformModel,  # noqa: F401
+                         h_synthesisTransformModel)
+from .net import Net                                        # noqa: F401
+
+__all__ = ["GDN", "ModelGDN", "ModelIGDN", "LowerBound", "NonNegativeParametrizer", "GaussianModel",
+           "GaussianConditional", "bypass_round", "ste_round", "analysisTransformModel", "synthesisTransformModel",
+           "h_analysisTransformModel", "h_synthesisTransformModel", "Net", "ops", "LdicError"]

@@ -1,0 +1,117 @@
+"""ctypes binding of libldic_b200.so (the C ABI declared in include/ldic.h).
+
+There is deliberately NO fallback: if the library is missing or the device is
+not sm_100, every op raises.  Nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+_LIB = None
+
+LDIC_CONV_S2_5x5_P12 = 0
+LDIC_CONV_S2_5x5_P2 = 1
+LDIC_CONV_S1_3x3_P1 = 2
+LDIC_CONV_1x1 = 3
+LDIC_DECONV_GS_5x5 = 4
+LDIC_DECONV_HS_5x5 = 5
+LDIC_DECONV_S1_3x3 = 6
+LDIC_DECONV_GS_5x5_MERGED = 7
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_GDN, ACT_IGDN = 0, 1, 2, 3, 4
+
+
+class LdicError(RuntimeError):
+    pass
+
+
+class LikelihoodArgs(C.Structure):
+    _fields_ = [
+        ("v", C.c_void_p), ("v_rs", C.c_longlong), ("v_off", C.c_longlong),
+        ("mu", C.c_void_p), ("mu_rs", C.c_longlong), ("mu_off", C.c_longlong), ("mu_mode", C.c_int),
+        ("sigma", C.c_void_p), ("sigma_rs", C.c_longlong), ("sigma_off", C.c_longlong), ("sigma_mode", C.c_int),
+        ("sigma_period", C.c_int),
+        ("rows", C.c_longlong), ("cols", C.c_longlong),
+        ("quant", C.c_int), ("form", C.c_int), ("sigma_is_log", C.c_int),
+        ("lik_bound", C.c_float), ("scale_bound", C.c_float),
+        ("v_hat", C.c_void_p), ("v_hat_rs", C.c_longlong), ("v_hat_off", C.c_longlong),
+        ("v_hat_bf16", C.c_void_p), ("vb_rs", C.c_longlong), ("vb_off", C.c_longlong),
+        ("lik", C.c_void_p), ("sum_ln_out", C.c_void_p), ("workspace", C.c_void_p),
+    ]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int),
+                ("Cout", C.c_int), ("Cin_pad", C.c_int), ("Cout_pad", C.c_int), ("act", C.c_int),
+                ("out_f32", C.c_int)]
+
+
+_SIGS = {
+    "ldic_version": (C.c_int, []),
+    "ldic_last_error": (C.c_char_p, []),
+    "ldic_launch_count": (C.c_longlong, []),
+    "ldic_check_device": (C.c_int, [C.c_int]),
+    "ldic_lower_bound": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ldic_lower_bound_bwd": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ldic_nonneg_reparam": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ldic_gdn_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ldic_gdn_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p]),
+    "ldic_likelihood_workspace_bytes": (C.c_size_t, []),
+    "ldic_round_likelihood_bpp": (C.c_int, [C.POINTER(LikelihoodArgs), C.c_void_p]),
+    "ldic_mse_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    "ldic_syntax_conv_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p]),
+    "ldic_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p]),
+    "ldic_latent_prep": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_im2col_5x5s2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ldic_conv_weight_elems": (C.c_longlong, [C.POINTER(ConvDesc)]),
+    "ldic_conv_n_cols": (C.c_int, [C.POINTER(ConvDesc)]),
+    "ldic_conv_pack_weights": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
+    "ldic_conv_out_shape": (None, [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ldic_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "ldic_conv_forward_f32_reference_kernel": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS.keys())
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = False):
+    """Loads (once) and returns the ctypes handle.  Raises LdicError when the
+    shared library is absent -- the product path never falls back to torch/CPU."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        if build_if_missing:
+            _build.build()
+        else:
+            raise LdicError(f"{path} not found: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                            "There is no CPU/torch fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ldic_last_error()
+        raise LdicError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,812 @@
+// Implicit-GEMM convolution / transposed convolution on the 5th-gen tensor cores
+// (tcgen05.mma, accumulators in TMEM), operands staged by TMA, with the GDN / IGDN
+// normalisation fused into the epilogue as a second tensor-core contraction.
+//
+// One persistent CTA per SM, 320 threads:
+//   warp 0      TMA producer   (one lane)
+//   warp 1      MMA issuer     (one lane) + TMEM allocator
+//   warps 2..9  epilogue       (TMEM -> registers -> global), 2 warps per TMEM lane quadrant
+//
+// GEMM view: M = 128 output (or, for transposed convs, input-grid) pixels per tile,
+// N = Np accumulator columns (= output channels, or 4 sub-pixel phases x channels for the
+// merged small-Cout deconv), K = taps x Cin_pad walked in 64-channel blocks.
+// A tile  : 128 pixels x 64 channels bf16, gathered by TMA from the NHWC activation
+//           (zero fill outside the image = the reference's ZeroPad2d / conv padding);
+//           stride-2 convs address the input through an (x-parity, x/2) split view.
+// B tile  : Np x 64 slice of the packed weights [tap][Np][Cin_pad].
+// GDN     : acc(+bias) -> x (registers) ; x^2 -> bf16 -> smem A-slot of the SAME pipeline
+//           ring whose B-slot receives a 64-wide K block of gamma; norm = x^2 . gamma^T is
+//           accumulated in a second TMEM region; out = x * rsqrt|sqrt(norm + beta).
+//
+// Reference semantics: model/net.py:96-114 (g_a), :126-144 (g_s), :188-216 (h_a/h_s),
+// model/gdn.py:69-92,134-156 (GDN/IGDN).
+#include <cuda.h>
+#include "common.cuh"
+
+using namespace ldic;
+
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // bf16 elements = 128 B = one swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kMaxTaps = 36;
+constexpr int kMaxJobs = 4;
+constexpr int kTmemCols = 512;
+constexpr int kNormCol = 256;
+
+struct Tap { int dx, dy, px; };
+struct Job { int ntaps, tap_begin, oy_off, ox_off; };
+
+struct ConvParams {
+  int mode;                 // 0: stride-1 gather (4-D map), 1: stride-2 gather (5-D parity map)
+  int TW, TH, TN;
+  int tiles_x, tiles_y, tiles_n, tiles_per_job, njobs, total_tiles;
+  int Wg, Hg, B;            // pixel grid the M tiles walk over
+  int kc_per_tap;           // Cin_pad / 64
+  int gdn_kblocks;          // Np / 64 when act is GDN/IGDN, else 0
+  int act, out_f32;
+  int stages;
+  int ngroups, Cg;          // accumulator columns = ngroups x Cg
+  int sy, sx;               // output pixel = grid pixel * (sy,sx) + job offset + group offset
+  int gy[4], gx[4];
+  long long out_sN, out_sY, out_sX;  // output strides in elements
+  Job jobs[kMaxJobs];
+  Tap taps[kMaxTaps];
+  const float* bias;
+  const float* beta;
+  void* out;
+};
+
+// ---------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("ldic conv_tc: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------
+struct TileCoord { int job, n0, y0, x0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, int t) {
+  TileCoord c;
+  c.job = t / P.tiles_per_job;
+  int r = t - c.job * P.tiles_per_job;
+  int per_n = P.tiles_y * P.tiles_x;
+  int tn = r / per_n;
+  r -= tn * per_n;
+  int ty = r / P.tiles_x;
+  int tx = r - ty * P.tiles_x;
+  c.n0 = tn * P.TN;
+  c.y0 = ty * P.TH;
+  c.x0 = tx * P.TW;
+  return c;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
+  constexpr int CPT = NP / 2;                       // accumulator columns per epilogue thread
+  constexpr int kBTileBytes = NP * kBlockK * 2;
+  constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024 B alignment
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = P.stages;
+  uint8_t* aux = smem_al + (size_t)stages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [kMaxStages]
+  uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages]
+  uint64_t* acc_full = empty_bar + kMaxStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint64_t* x2_ready = acc_empty + 1;
+  uint64_t* norm_full = x2_ready + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);              // [NP]
+  float* s_beta = s_bias + NP;                                         // [NP]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kEpiThreads);
+    mbar_init(x2_ready, kEpiThreads);
+    mbar_init(norm_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    if (gdn) prefetch_tmap(&tmG);
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  for (int i = threadIdx.x; i < NP; i += kThreads) {
+    s_bias[i] = P.bias ? P.bias[i] : 0.f;
+    s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int kcpt = P.kc_per_tap;
+  const int gk = gdn ? P.gdn_kblocks : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t kcount = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(P, t);
+        const Job jb = P.jobs[tc.job];
+        for (int tp = 0; tp < jb.ntaps; ++tp) {
+          const Tap tap = P.taps[jb.tap_begin + tp];
+          for (int kc = 0; kc < kcpt; ++kc, ++kcount) {
+            const uint32_t slot = kcount % stages, use = kcount / stages;
+            mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
+            const uint32_t a_dst = smem_base + slot * kStageBytes;
+            const uint32_t b_dst = a_dst + kATileBytes;
+            mbar_expect_tx(&full_bar[slot], kStageBytes);
+            if (P.mode == 1) {
+              for (int j = 0; j < P.TH; ++j)
+                tma_load_5d(a_dst + j * P.TW * 128, &tmA, &full_bar[slot], kc * kBlockK, tap.px, tc.x0 + tap.dx,
+                            2 * (tc.y0 + j) + tap.dy, tc.n0);
+            } else {
+              tma_load_4d(a_dst, &tmA, &full_bar[slot], kc * kBlockK, tc.x0 + tap.dx, tc.y0 + tap.dy, tc.n0);
+            }
+            tma_load_2d(b_dst, &tmW, &full_bar[slot], kc * kBlockK, (jb.tap_begin + tp) * NP);
+          }
+        }
+        for (int kb = 0; kb < gk; ++kb, ++kcount) {       // gamma K-blocks ride the same ring
+          const uint32_t slot = kcount % stages, use = kcount / stages;
+          mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
+          mbar_expect_tx(&full_bar[slot], kBTileBytes);
+          tma_load_2d(smem_base + slot * kStageBytes + kATileBytes, &tmG, &full_bar[slot], kb * kBlockK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t kcount = 0, it = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(P, t);
+        const int nkb = P.jobs[tc.job].ntaps * kcpt;
+        mbar_wait(acc_empty, (it & 1) ^ 1);                 // epilogue has drained the accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+          const uint32_t slot = kcount % stages, use = kcount / stages;
+          mbar_wait(&full_bar[slot], use & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + slot * kStageBytes;
+          const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(tmem_base, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), kIdesc,
+                      (kb | k) != 0);
+          tc_commit(&empty_bar[slot]);                       // frees the smem slot when these MMAs retire
+        }
+        tc_commit(acc_full);
+        if (gk) {
+          mbar_wait(x2_ready, it & 1);                        // x^2 tiles written by the epilogue warps
+          tc_fence_after();
+          for (int kb = 0; kb < gk; ++kb, ++kcount) {
+            const uint32_t slot = kcount % stages, use = kcount / stages;
+            mbar_wait(&full_bar[slot], use & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + slot * kStageBytes;
+            const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16(tmem_base + kNormCol, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32),
+                        kIdesc, (kb | k) != 0);
+            tc_commit(&empty_bar[slot]);
+          }
+          tc_commit(norm_full);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int h = (warp - 2) >> 2;          // column half
+    const int r = q * 32 + lane;            // tile row = TMEM lane
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int col0 = h * CPT;
+    uint32_t kcount = 0, it = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(P, t);
+      const Job jb = P.jobs[tc.job];
+      const int nkb = jb.ntaps * kcpt;
+      // row -> pixel of the M grid
+      const int xi = r % P.TW, yi = (r / P.TW) % P.TH, ni = r / (P.TW * P.TH);
+      const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
+      const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B);
+      const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
+                                 (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX;
+
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after();
+      kcount += nkb;
+
+      float xr[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; c += 32) {
+        uint32_t tr[32];
+        tmem_ld32(tmem_base + lane_sel + col0 + c, tr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) xr[c + k] = __uint_as_float(tr[k]) + s_bias[col0 + c + k];
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);               // accumulator may be overwritten by the next tile
+
+      if (gk) {
+        // x^2 -> bf16 -> A slots (K-major, 128B swizzle: 16-byte chunk index XOR (row & 7))
+        for (int kb = 0; kb < gk; ++kb) {
+          const uint32_t kc2 = kcount + kb;
+          mbar_wait(&empty_bar[kc2 % stages], ((kc2 / stages) & 1) ^ 1);
+        }
+#pragma unroll
+        for (int j = 0; j < CPT / 8; ++j) {
+          const int col = col0 + j * 8;
+          const uint32_t kc2 = kcount + (col >> 6);
+          const uint32_t a_addr = smem_base + (kc2 % stages) * kStageBytes;
+          const uint32_t chunk = (uint32_t)((col & 63) >> 3);
+          const uint32_t addr = a_addr + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4);
+          const float* x8 = &xr[j * 8];
+          st_shared_v4(addr, pack_bf16x2(x8[0] * x8[0], x8[1] * x8[1]), pack_bf16x2(x8[2] * x8[2], x8[3] * x8[3]),
+                       pack_bf16x2(x8[4] * x8[4], x8[5] * x8[5]), pack_bf16x2(x8[6] * x8[6], x8[7] * x8[7]));
+        }
+        fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(x2_ready);
+        kcount += gk;
+        mbar_wait(norm_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < CPT; c += 32) {
+          uint32_t tr[32];
+          tmem_ld32(tmem_base + kNormCol + lane_sel + col0 + c, tr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float nrm = __uint_as_float(tr[k]) + s_beta[col0 + c + k];
+            xr[c + k] *= (P.act == LDIC_ACT_IGDN) ? sqrtf(nrm) : rsqrtf(nrm);
+          }
+        }
+        tc_fence_before();
+      } else if (P.act == LDIC_ACT_RELU) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) xr[c] = fmaxf(xr[c], 0.f);
+      } else if (P.act == LDIC_ACT_LEAKY02) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) xr[c] = xr[c] > 0.f ? xr[c] : 0.2f * xr[c];
+      }
+
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < CPT / 8; ++j) {
+          const int col = col0 + j * 8;
+          const int g = col / P.Cg, cc = col - g * P.Cg;
+          const long long off = pix_base + (long long)P.gy[g] * P.out_sY + (long long)P.gx[g] * P.out_sX + cc;
+          const float* x8 = &xr[j * 8];
+          if (P.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off);
+            dst[0] = make_float4(x8[0], x8[1], x8[2], x8[3]);
+            dst[1] = make_float4(x8[4], x8[5], x8[6], x8[7]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off);
+            *dst = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
+                              pack_bf16x2(x8[6], x8[7]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Host side: tap tables, tiling, tensor maps
+// ---------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(LDIC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(LDIC_ECUDA, "cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                box[0], box[1], rank > 2 ? box[2] : 0);
+  return LDIC_OK;
+}
+
+struct Layer {          // everything derived from an LdicConvDesc
+  int mode, k, transposed, merged;
+  int Np, ngroups, Cg;
+  int njobs, ntaps_total;
+  Job jobs[kMaxJobs];
+  Tap taps[kMaxTaps];
+  int tap_ky[kMaxTaps][4], tap_kx[kMaxTaps][4];   // per (tap, group): kernel cell or -1
+  int Wg, Hg;           // M-grid
+  int Ho, Wo, sy, sx;
+  int gy[4], gx[4];
+};
+
+// rows/cols of the 5x5 transposed kernels hit by output parity p at input offset d (-1,0,+1); -1 = none
+inline int gs_k(int p, int d) {   // o = 2i - 1 + k   (ZeroPad2d((1,0,1,0)) + k5 s2 p3 op1)
+  if (p == 0) return d == 0 ? 1 : (d == -1 ? 3 : -1);
+  return d == 1 ? 0 : (d == 0 ? 2 : 4);
+}
+inline int hs_k(int p, int d) {   // o = 2i - 2 + k   (k5 s2 p2 op1)
+  if (p == 0) return d == 1 ? 0 : (d == 0 ? 2 : 4);
+  return d == 1 ? 1 : (d == 0 ? 3 : -1);
+}
+
+int build_layer(const LdicConvDesc* d, Layer* L) {
+  memset(L, 0, sizeof(*L));
+  if (!d) return fail(LDIC_EINVAL, "conv: null desc");
+  if (d->B < 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0) return fail(LDIC_EINVAL, "conv: bad shape");
+  if (d->Cin_pad % 64 || d->Cin_pad < d->Cin) return fail(LDIC_EINVAL, "conv: Cin_pad must be a multiple of 64 >= Cin");
+  for (int t = 0; t < kMaxTaps; ++t) for (int g = 0; g < 4; ++g) L->tap_ky[t][g] = L->tap_kx[t][g] = -1;
+  L->ngroups = 1; L->Cg = d->Cout_pad; L->sy = L->sx = 1; L->njobs = 1;
+  L->Wg = d->W; L->Hg = d->H; L->Ho = d->H; L->Wo = d->W;
+  auto add_tap = [&](int dx, int dy, int px) { Tap t{dx, dy, px}; L->taps[L->ntaps_total] = t; return L->ntaps_total++; };
+  switch (d->kind) {
+    case LDIC_CONV_S2_5x5_P12:
+    case LDIC_CONV_S2_5x5_P2: {
+      if ((d->H & 1) || (d->W & 1)) return fail(LDIC_EINVAL, "conv s2: H and W must be even");
+      const int pad = d->kind == LDIC_CONV_S2_5x5_P12 ? 1 : 2;
+      L->mode = 1; L->k = 5;
+      L->Ho = d->H / 2; L->Wo = d->W / 2; L->Wg = L->Wo; L->Hg = L->Ho;
+      for (int ky = 0; ky < 5; ++ky) for (int kx = 0; kx < 5; ++kx) {
+        int off = kx - pad;
+        int t = add_tap(off >> 1, ky - pad, off & 1);
+        L->tap_ky[t][0] = ky; L->tap_kx[t][0] = kx;
+      }
+      L->jobs[0] = Job{25, 0, 0, 0};
+      break;
+    }
+    case LDIC_CONV_S1_3x3_P1: {
+      L->mode = 0; L->k = 3;
+      for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) {
+        int t = add_tap(kx - 1, ky - 1, 0);
+        L->tap_ky[t][0] = ky; L->tap_kx[t][0] = kx;
+      }
+      L->jobs[0] = Job{9, 0, 0, 0};
+      break;
+    }
+    case LDIC_CONV_1x1: {
+      L->mode = 0; L->k = 1;
+      int t = add_tap(0, 0, 0);
+      L->tap_ky[t][0] = 0; L->tap_kx[t][0] = 0;
+      L->jobs[0] = Job{1, 0, 0, 0};
+      break;
+    }
+    case LDIC_DECONV_GS_5x5:
+    case LDIC_DECONV_HS_5x5: {
+      L->mode = 0; L->k = 5; L->transposed = 1;
+      L->Ho = 2 * d->H; L->Wo = 2 * d->W; L->sy = L->sx = 2; L->njobs = 4;
+      auto kk = d->kind == LDIC_DECONV_GS_5x5 ? gs_k : hs_k;
+      for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
+        Job jb{0, L->ntaps_total, py, px};
+        for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+          int ky = kk(py, dy), kx = kk(px, dx);
+          if (ky < 0 || kx < 0) continue;
+          int t = add_tap(dx, dy, 0);
+          L->tap_ky[t][0] = ky; L->tap_kx[t][0] = kx;
+          jb.ntaps++;
+        }
+        L->jobs[py * 2 + px] = jb;
+      }
+      break;
+    }
+    case LDIC_DECONV_S1_3x3: {   // o = i - 1 + k  ->  input offset d = 1 - k
+      L->mode = 0; L->k = 3; L->transposed = 1;
+      for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+        int t = add_tap(dx, dy, 0);
+        L->tap_ky[t][0] = 1 - dy; L->tap_kx[t][0] = 1 - dx;
+      }
+      L->jobs[0] = Job{9, 0, 0, 0};
+      break;
+    }
+    case LDIC_DECONV_GS_5x5_MERGED: {
+      L->mode = 0; L->k = 5; L->transposed = 1; L->merged = 1;
+      L->Ho = 2 * d->H; L->Wo = 2 * d->W; L->sy = L->sx = 2;
+      L->ngroups = 4;
+      for (int g = 0; g < 4; ++g) { L->gy[g] = g >> 1; L->gx[g] = g & 1; }
+      for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+        int t = add_tap(dx, dy, 0);
+        for (int g = 0; g < 4; ++g) {
+          int ky = gs_k(g >> 1, dy), kx = gs_k(g & 1, dx);
+          if (ky >= 0 && kx >= 0) { L->tap_ky[t][g] = ky; L->tap_kx[t][g] = kx; }
+        }
+      }
+      L->jobs[0] = Job{9, 0, 0, 0};
+      break;
+    }
+    default:
+      return fail(LDIC_EINVAL, "conv: unknown kind %d", d->kind);
+  }
+  if (d->Cout_pad < d->Cout || d->Cout_pad % 8) return fail(LDIC_EINVAL, "conv: Cout_pad must be >= Cout and a multiple of 8");
+  L->Np = L->ngroups * L->Cg;
+  if (L->Np != 64 && L->Np != 128 && L->Np != 192 && L->Np != 256)
+    return fail(LDIC_EINVAL, "conv: accumulator width %d (groups %d x Cout_pad %d) must be 64/128/192/256", L->Np,
+                L->ngroups, L->Cg);
+  return LDIC_OK;
+}
+
+void choose_tile(int mode, int Wg, int Hg, int B, int* TW, int* TH, int* TN) {
+  double best = 1e30;
+  int bw = 128, bh = 1, bn = 1;
+  for (int tw = 128; tw >= (mode == 1 ? 8 : 1); tw >>= 1) {
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      int tn = 128 / (tw * th);
+      if (mode == 1 && tn != 1) continue;
+      long long tiles = (long long)((Wg + tw - 1) / tw) * ((Hg + th - 1) / th) * ((B + tn - 1) / tn);
+      double cost = (double)tiles * (1.0 + (mode == 1 ? 0.02 * th : 0.0));   // stride-2 tiles issue TH loads per stage
+      if (cost < best - 1e-9) { best = cost; bw = tw; bh = th; bn = tn; }
+    }
+  }
+  *TW = bw; *TH = bh; *TN = bn;
+}
+
+template <int NP>
+int launch_conv(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
+  const int stage_bytes = kATileBytes + NP * kBlockK * 2;
+  const size_t smem = (size_t)P.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * NP * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  conv_tc_kernel<NP><<<grid, kThreads, smem, st>>>(a, w, g, P);
+  return check_launch("conv_tc_kernel");
+}
+
+// generic weight packer: Wp[t][n][k]
+struct PackTable {
+  int ntaps, Np, Cg, ngroups, Cin, Cout, Cin_pad, cin_offset, k, transposed;
+  signed char ky[kMaxTaps][4], kx[kMaxTaps][4];
+};
+__global__ void k_pack_weights(const float* __restrict__ w, const float* __restrict__ bias, PackTable T,
+                               __nv_bfloat16* __restrict__ wp, float* __restrict__ bp) {
+  const long long total = (long long)T.ntaps * T.Np * T.Cin_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int kc = (int)(i % T.Cin_pad);
+    long long r = i / T.Cin_pad;
+    int n = (int)(r % T.Np);
+    int t = (int)(r / T.Np);
+    int g = n / T.Cg, co = n - g * T.Cg;
+    int ci = kc - T.cin_offset;
+    float v = 0.f;
+    int ky = T.ky[t][g], kx = T.kx[t][g];
+    if (ky >= 0 && co < T.Cout && ci >= 0 && ci < T.Cin) {
+      long long idx = T.transposed ? ((((long long)ci * T.Cout + co) * T.k + ky) * T.k + kx)
+                                   : ((((long long)co * T.Cin + ci) * T.k + ky) * T.k + kx);
+      v = w[idx];
+    }
+    wp[i] = __float2bfloat16_rn(v);
+  }
+  if (bp) {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < T.Np; n += gridDim.x * blockDim.x) {
+      int co = n % T.Cg;
+      bp[n] = (bias && co < T.Cout) ? bias[co] : 0.f;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ldic_conv_n_cols(const LdicConvDesc* d) {
+  Layer L;
+  if (build_layer(d, &L) != LDIC_OK) return -1;
+  return L.Np;
+}
+extern "C" long long ldic_conv_weight_elems(const LdicConvDesc* d) {
+  Layer L;
+  if (build_layer(d, &L) != LDIC_OK) return -1;
+  return (long long)L.ntaps_total * L.Np * d->Cin_pad;
+}
+extern "C" void ldic_conv_out_shape(const LdicConvDesc* d, int* Ho, int* Wo) {
+  Layer L;
+  if (build_layer(d, &L) != LDIC_OK) { *Ho = *Wo = -1; return; }
+  *Ho = L.Ho; *Wo = L.Wo;
+}
+
+extern "C" int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, const float* bias, int cin_offset,
+                                      void* w_packed, float* bias_packed, void* stream) {
+  Layer L;
+  int rc = build_layer(d, &L);
+  if (rc) return rc;
+  if (cin_offset < 0 || cin_offset + d->Cin > d->Cin_pad) return fail(LDIC_EINVAL, "pack: cin_offset out of range");
+  PackTable T;
+  T.ntaps = L.ntaps_total; T.Np = L.Np; T.Cg = L.Cg; T.ngroups = L.ngroups; T.Cin = d->Cin; T.Cout = d->Cout;
+  T.Cin_pad = d->Cin_pad; T.cin_offset = cin_offset; T.k = L.k; T.transposed = L.transposed;
+  for (int t = 0; t < kMaxTaps; ++t) for (int g = 0; g < 4; ++g) { T.ky[t][g] = (signed char)L.tap_ky[t][g]; T.kx[t][g] = (signed char)L.tap_kx[t][g]; }
+  long long total = (long long)T.ntaps * T.Np * T.Cin_pad;
+  int grid = (int)((total + 255) / 256 > kNumSMs * 8 ? kNumSMs * 8 : (total + 255) / 256);
+  k_pack_weights<<<grid, 256, 0, (cudaStream_t)stream>>>(w, bias, T, (__nv_bfloat16*)w_packed, bias_packed);
+  return check_launch("k_pack_weights");
+}
+
+extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                                 const void* gamma_bf16, const float* beta_tiled, void* y, void* stream) {
+  Layer L;
+  int rc = build_layer(d, &L);
+  if (rc) return rc;
+  if (d->B == 0) return LDIC_OK;
+  if (!x || !w_packed || !y) return fail(LDIC_EINVAL, "conv: null tensor");
+  const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
+  if (gdn && (!gamma_bf16 || !beta_tiled)) return fail(LDIC_EINVAL, "conv: GDN epilogue needs gamma_bf16 and beta_tiled");
+  if ((((uintptr_t)x) & 15) || (((uintptr_t)w_packed) & 15) || (((uintptr_t)y) & 15)) return fail(LDIC_EINVAL, "conv: tensors must be 16-byte aligned");
+
+  ConvParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = L.mode;
+  choose_tile(L.mode, L.Wg, L.Hg, d->B, &P.TW, &P.TH, &P.TN);
+  P.tiles_x = (L.Wg + P.TW - 1) / P.TW;
+  P.tiles_y = (L.Hg + P.TH - 1) / P.TH;
+  P.tiles_n = (d->B + P.TN - 1) / P.TN;
+  P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
+  P.njobs = L.njobs;
+  P.total_tiles = P.tiles_per_job * P.njobs;
+  P.Wg = L.Wg; P.Hg = L.Hg; P.B = d->B;
+  P.kc_per_tap = d->Cin_pad / 64;
+  P.gdn_kblocks = gdn ? L.Np / 64 : 0;
+  P.act = d->act; P.out_f32 = d->out_f32;
+  P.ngroups = L.ngroups; P.Cg = L.Cg; P.sy = L.sy; P.sx = L.sx;
+  for (int g = 0; g < 4; ++g) { P.gy[g] = L.gy[g]; P.gx[g] = L.gx[g]; }
+  P.out_sX = L.Cg; P.out_sY = (long long)L.Wo * L.Cg; P.out_sN = (long long)L.Ho * L.Wo * L.Cg;
+  for (int j = 0; j < kMaxJobs; ++j) P.jobs[j] = L.jobs[j];
+  for (int t = 0; t < kMaxTaps; ++t) P.taps[t] = L.taps[t];
+  P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
+  const int stage_bytes = kATileBytes + L.Np * kBlockK * 2;
+  int stages = (227 * 1024 - 2048 - 2 * L.Np * 4) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  P.stages = stages;
+  if (gdn && stages < P.gdn_kblocks + 1) return fail(LDIC_EINVAL, "conv: not enough pipeline stages for the GDN epilogue");
+
+  CUtensorMap tmA, tmW, tmG;
+  const cuuint64_t C = (cuuint64_t)d->Cin_pad;
+  if (L.mode == 1) {
+    cuuint64_t dims[5] = {C, 2, (cuuint64_t)d->W / 2, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t str[4] = {C * 2, 2 * C * 2, (cuuint64_t)d->W * C * 2, (cuuint64_t)d->H * d->W * C * 2};
+    cuuint32_t box[5] = {64, 1, (cuuint32_t)P.TW, 1, 1};
+    if ((rc = encode_map(&tmA, x, 5, dims, str, box))) return rc;
+  } else {
+    cuuint64_t dims[4] = {C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t str[3] = {C * 2, (cuuint64_t)d->W * C * 2, (cuuint64_t)d->H * d->W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+    if ((rc = encode_map(&tmA, x, 4, dims, str, box))) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {C, (cuuint64_t)L.ntaps_total * L.Np};
+    cuuint64_t str[1] = {C * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
+    if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
+  }
+  if (gdn) {
+    cuuint64_t dims[2] = {(cuuint64_t)L.Np, (cuuint64_t)L.Np};
+    cuuint64_t str[1] = {(cuuint64_t)L.Np * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
+    if ((rc = encode_map(&tmG, gamma_bf16, 2, dims, str, box))) return rc;
+  } else {
+    tmG = tmW;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (L.Np) {
+    case 64: return launch_conv<64>(tmA, tmW, tmG, P, st);
+    case 128: return launch_conv<128>(tmA, tmW, tmG, P, st);
+    case 192: return launch_conv<192>(tmA, tmW, tmG, P, st);
+    case 256: return launch_conv<256>(tmA, tmW, tmG, P, st);
+  }
+  return fail(LDIC_EINVAL, "conv: unsupported Np %d", L.Np);
+}
+
+// ---------------------------------------------------------------------------------
+// CUDA-core fp32 direct convolution of the same layer kinds (validation aid).
+// x NHWC fp32 [B,H,W,Cin], w = state-dict layout, y NHWC fp32 [B,Ho,Wo,Cout].
+// ---------------------------------------------------------------------------------
+namespace {
+struct RefTable {
+  int njobs, Cin, Cout, k, transposed, mode, H, W, Ho, Wo, sy, sx, Hg, Wg, B;
+  Job jobs[kMaxJobs];
+  Tap taps[kMaxTaps];
+  signed char ky[kMaxTaps], kx[kMaxTaps];
+};
+__global__ void k_conv_ref(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                           float* __restrict__ y, RefTable T) {
+  const long long total = (long long)T.njobs * T.B * T.Hg * T.Wg * T.Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(i % T.Cout);
+    long long r = i / T.Cout;
+    int gx = (int)(r % T.Wg); r /= T.Wg;
+    int gy = (int)(r % T.Hg); r /= T.Hg;
+    int n = (int)(r % T.B);
+    int j = (int)(r / T.B);
+    const Job jb = T.jobs[j];
+    float acc = bias ? bias[co] : 0.f;
+    for (int tp = 0; tp < jb.ntaps; ++tp) {
+      const Tap tap = T.taps[jb.tap_begin + tp];
+      int ix, iy;
+      if (T.mode == 1) { ix = 2 * (gx + tap.dx) + tap.px; iy = 2 * gy + tap.dy; }
+      else { ix = gx + tap.dx; iy = gy + tap.dy; }
+      if (ix < 0 || ix >= T.W || iy < 0 || iy >= T.H) continue;
+      const float* xp = x + (((long long)n * T.H + iy) * T.W + ix) * T.Cin;
+      const int ky = T.ky[jb.tap_begin + tp], kx = T.kx[jb.tap_begin + tp];
+      for (int ci = 0; ci < T.Cin; ++ci) {
+        long long widx = T.transposed ? ((((long long)ci * T.Cout + co) * T.k + ky) * T.k + kx)
+                                      : ((((long long)co * T.Cin + ci) * T.k + ky) * T.k + kx);
+        acc = fmaf(xp[ci], __ldg(w + widx), acc);
+      }
+    }
+    int oy = gy * T.sy + jb.oy_off, ox = gx * T.sx + jb.ox_off;
+    y[(((long long)n * T.Ho + oy) * T.Wo + ox) * T.Cout + co] = acc;
+  }
+}
+}  // namespace
+
+extern "C" int ldic_conv_forward_f32_reference_kernel(const LdicConvDesc* d, const float* x_nhwc, const float* w,
+                                                      const float* bias, float* y_nhwc, void* stream) {
+  LdicConvDesc dd = *d;
+  if (dd.kind == LDIC_DECONV_GS_5x5_MERGED) dd.kind = LDIC_DECONV_GS_5x5;
+  dd.Cout = 8; dd.Cout_pad = 64; dd.Cin_pad = ((dd.Cin + 63) / 64) * 64;   // only the tap tables are used here
+  Layer L;
+  int rc = build_layer(&dd, &L);
+  if (rc) return rc;
+  if (d->B == 0) return LDIC_OK;
+  RefTable T;
+  memset(&T, 0, sizeof(T));
+  T.njobs = L.njobs; T.Cin = d->Cin; T.Cout = d->Cout; T.k = L.k; T.transposed = L.transposed; T.mode = L.mode;
+  T.H = d->H; T.W = d->W; T.Ho = L.Ho; T.Wo = L.Wo; T.sy = L.sy; T.sx = L.sx; T.Hg = L.Hg; T.Wg = L.Wg; T.B = d->B;
+  for (int j = 0; j < kMaxJobs; ++j) T.jobs[j] = L.jobs[j];
+  for (int t = 0; t < kMaxTaps; ++t) { T.taps[t] = L.taps[t]; T.ky[t] = (signed char)L.tap_ky[t][0]; T.kx[t] = (signed char)L.tap_kx[t][0]; }
+  long long total = (long long)T.njobs * T.B * T.Hg * T.Wg * T.Cout;
+  int grid = (int)((total + 255) / 256 > kNumSMs * 16 ? kNumSMs * 16 : (total + 255) / 256);
+  k_conv_ref<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nhwc, w, bias, y_nhwc, T);
+  return check_launch("k_conv_ref");
+}

@@ -1,0 +1,613 @@
+// Memory-bound kernels of the rate-distortion path: LowerBound / reparametrisation,
+// quantise + Gaussian likelihood + sum(ln L), MSE on 8-bit levels, layout glue.
+// sm_100a; every kernel is a coalesced, vectorised streaming pass.
+#include "common.cuh"
+
+namespace ldic {
+thread_local char g_err[512] = {0};
+std::atomic<long long> g_launches{0};
+}  // namespace ldic
+
+using namespace ldic;
+
+extern "C" int ldic_version(void) { return 100; }
+extern "C" const char* ldic_last_error(void) { return g_err; }
+extern "C" long long ldic_launch_count(void) { return g_launches.load(); }
+extern "C" int ldic_check_device(int dev) {
+  cudaDeviceProp p;
+  LDIC_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (p.major != 10) return fail(LDIC_ENOTSUP, "device %d is sm_%d%d, libldic_b200 needs sm_100", dev, p.major, p.minor);
+  return LDIC_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// a3: LowerBound, NonNegativeParametrizer
+// ------------------------------------------------------------------------------------
+// torch.max propagates NaN; (x < b ? b : x) keeps a NaN x, unlike fmaxf.
+__device__ __forceinline__ float lower_bound_f(float x, float b) { return (x < b) ? b : x; }
+
+__global__ void k_lower_bound(const float* __restrict__ x, float bound, float* __restrict__ y, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) y[i] = lower_bound_f(x[i], bound);
+}
+__global__ void k_lower_bound_bwd(const float* __restrict__ x, float bound, const float* __restrict__ g,
+                                  float* __restrict__ gi, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) gi[i] = ((x[i] >= bound) || (g[i] < 0.f)) ? g[i] : 0.f * g[i];
+}
+__global__ void k_nonneg(const float* __restrict__ p, float bound, float pedestal, float* __restrict__ o, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) {
+    float t = lower_bound_f(p[i], bound);
+    o[i] = __fsub_rn(__fmul_rn(t, t), pedestal);
+  }
+}
+static inline int grid_for(size_t n, int threads = 256, int max_blocks = kNumSMs * 8) {
+  size_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b > (size_t)max_blocks ? max_blocks : b);
+}
+
+extern "C" int ldic_lower_bound(const float* x, float bound, float* y, size_t n, void* stream) {
+  if (n == 0) return LDIC_OK;
+  k_lower_bound<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, bound, y, n);
+  return check_launch("k_lower_bound");
+}
+extern "C" int ldic_lower_bound_bwd(const float* x, float bound, const float* g, float* gi, size_t n, void* stream) {
+  if (n == 0) return LDIC_OK;
+  k_lower_bound_bwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, bound, g, gi, n);
+  return check_launch("k_lower_bound_bwd");
+}
+extern "C" int ldic_nonneg_reparam(const float* p, float bound, float pedestal, float* out, size_t n, void* stream) {
+  if (n == 0) return LDIC_OK;
+  k_nonneg<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, bound, pedestal, out, n);
+  return check_launch("k_nonneg");
+}
+
+// beta_eff / gamma_eff + the bf16 block-diagonal operand image for the tensor-core epilogue.
+__global__ void k_gdn_prepare(const float* __restrict__ beta_p, const float* __restrict__ gamma_p, int C,
+                              float bb, float gb, float ped, float* __restrict__ beta_eff,
+                              float* __restrict__ gamma_eff, __nv_bfloat16* __restrict__ gamma_bf16,
+                              float* __restrict__ beta_tiled, int groups, int Np, int Kp) {
+  int tid = blockIdx.x * blockDim.x + threadIdx.x, st = gridDim.x * blockDim.x;
+  for (int i = tid; i < C; i += st) {
+    float t = lower_bound_f(beta_p[i], bb);
+    float b = __fsub_rn(__fmul_rn(t, t), ped);
+    if (beta_eff) beta_eff[i] = b;
+  }
+  for (int i = tid; i < C * C; i += st) {
+    float t = lower_bound_f(gamma_p[i], gb);
+    float g = __fsub_rn(__fmul_rn(t, t), ped);
+    if (gamma_eff) gamma_eff[i] = g;
+  }
+  if (gamma_bf16) {
+    for (int i = tid; i < Np * Kp; i += st) {
+      int r = i / Kp, k = i % Kp;
+      float g = 0.f;
+      if (r < groups * C && k < groups * C && (r / C) == (k / C)) {
+        float t = lower_bound_f(gamma_p[(r % C) * C + (k % C)], gb);
+        g = __fsub_rn(__fmul_rn(t, t), ped);
+      }
+      gamma_bf16[i] = __float2bfloat16_rn(g);
+    }
+  }
+  if (beta_tiled) {
+    for (int i = tid; i < Np; i += st) {
+      float b = 1.f;
+      if (i < groups * C) {
+        float t = lower_bound_f(beta_p[i % C], bb);
+        b = __fsub_rn(__fmul_rn(t, t), ped);
+      }
+      beta_tiled[i] = b;
+    }
+  }
+}
+extern "C" int ldic_gdn_prepare(const float* beta_p, const float* gamma_p, int C, float beta_bound, float gamma_bound,
+                                float pedestal, float* beta_eff, float* gamma_eff, void* gamma_bf16,
+                                float* beta_tiled, int groups, int Np, int Kp, void* stream) {
+  if (C <= 0) return fail(LDIC_EINVAL, "gdn_prepare: C=%d", C);
+  if (gamma_bf16 && (groups * C > Np || groups * C > Kp)) return fail(LDIC_EINVAL, "gdn_prepare: groups*C exceeds Np/Kp");
+  size_t n = (size_t)C * C;
+  if (gamma_bf16 && (size_t)Np * Kp > n) n = (size_t)Np * Kp;
+  k_gdn_prepare<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(beta_p, gamma_p, C, beta_bound, gamma_bound, pedestal,
+                                                                beta_eff, gamma_eff, (__nv_bfloat16*)gamma_bf16,
+                                                                beta_tiled, groups, Np, Kp);
+  return check_launch("k_gdn_prepare");
+}
+
+// ------------------------------------------------------------------------------------
+// a2: stand-alone GDN / IGDN, NCHW fp32 (module surface).  CUDA-core fp32: the
+// fused tensor-core version lives in conv_tc.cu.  One block = 64 pixels x all C.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gdn_nchw(const float* __restrict__ x, const float* __restrict__ beta,
+                                                  const float* __restrict__ gamma, float* __restrict__ y, int C,
+                                                  long long HW, int inverse, int use_rsqrt) {
+  extern __shared__ float xs[];  // [C][64] squares
+  const int b = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * 64;
+  const float* xb = x + (long long)b * C * HW;
+  float* yb = y + (long long)b * C * HW;
+  for (int i = threadIdx.x; i < C * 64; i += 256) {
+    int c = i >> 6, p = i & 63;
+    float v = (p0 + p < HW) ? xb[(long long)c * HW + p0 + p] : 0.f;
+    xs[i] = v * v;
+  }
+  __syncthreads();
+  const int p = threadIdx.x & 63, g = threadIdx.x >> 6;
+  if (p0 + p >= HW) return;
+  for (int i = g; i < C; i += 4) {
+    const float* gr = gamma + (long long)i * C;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = 0;
+    for (; j + 3 < C; j += 4) {
+      a0 = fmaf(__ldg(gr + j), xs[(j << 6) + p], a0);
+      a1 = fmaf(__ldg(gr + j + 1), xs[((j + 1) << 6) + p], a1);
+      a2 = fmaf(__ldg(gr + j + 2), xs[((j + 2) << 6) + p], a2);
+      a3 = fmaf(__ldg(gr + j + 3), xs[((j + 3) << 6) + p], a3);
+    }
+    for (; j < C; ++j) a0 = fmaf(__ldg(gr + j), xs[(j << 6) + p], a0);
+    float norm = ((a0 + a1) + (a2 + a3)) + __ldg(beta + i);
+    float xv = xb[(long long)i * HW + p0 + p];
+    float o;
+    if (inverse) o = xv * __fsqrt_rn(norm);
+    else if (use_rsqrt) o = xv * __fdiv_rn(1.0f, __fsqrt_rn(norm));
+    else o = __fdiv_rn(xv, __fsqrt_rn(norm));
+    yb[(long long)i * HW + p0 + p] = o;
+  }
+}
+extern "C" int ldic_gdn_nchw_f32(const float* x, const float* beta_eff, const float* gamma_eff, float* y, int B, int C,
+                                 int H, int W, int inverse, int use_rsqrt, void* stream) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return (B == 0 || H == 0 || W == 0) ? LDIC_OK : fail(LDIC_EINVAL, "gdn: bad shape");
+  size_t smem = (size_t)C * 64 * sizeof(float);
+  if (smem > 200 * 1024) return fail(LDIC_EINVAL, "gdn: C=%d too large", C);
+  if (smem > 48 * 1024) LDIC_CUDA(cudaFuncSetAttribute(k_gdn_nchw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 63) / 64), B);
+  k_gdn_nchw<<<grid, 256, smem, (cudaStream_t)stream>>>(x, beta_eff, gamma_eff, y, C, HW, inverse, use_rsqrt);
+  return check_launch("k_gdn_nchw");
+}
+
+// ------------------------------------------------------------------------------------
+// a6+a7+a8+a9: quantise + Gaussian likelihood + sum(ln L), one streaming pass.
+// ------------------------------------------------------------------------------------
+constexpr int kLikThreads = 256;
+constexpr int kLikMaxBlocks = kNumSMs * 8;
+
+struct LikWs {
+  unsigned int ticket;
+  unsigned int pad[15];
+  double partial[kLikMaxBlocks];
+};
+extern "C" size_t ldic_likelihood_workspace_bytes(void) { return sizeof(LikWs); }
+
+__device__ __forceinline__ float quantise(float v, float mu, int quant) {
+  switch (quant) {
+    case 1: return rintf(v);
+    case 2: return __fadd_rn(rintf(__fsub_rn(v, mu)), mu);
+    case 3: return __fadd_rn(__fsub_rn(rintf(v), v), v);
+    default: return v;
+  }
+}
+
+// form 0: model/net.py:272-286.  cdf(t) = 0.5*(1+erf(t/sqrt2)), difference, clamp(min).
+// form 1: CompressAI GaussianConditional (erfc form on |v-mu|, sigma lower bound).
+template <int FORM>
+__device__ __forceinline__ float likelihood(float vhat, float mu, float sigma, float lik_bound, float scale_bound) {
+  float d = __fsub_rn(vhat, mu);
+  float l;
+  if (FORM == 0) {
+    float r = __frcp_rn(sigma);
+    float tu = __fmul_rn(__fadd_rn(d, 0.5f), r);
+    float tl = __fmul_rn(__fsub_rn(d, 0.5f), r);
+    const float inv_sqrt2 = 0.70710678118654752440f;
+    float cu = __fmul_rn(0.5f, __fadd_rn(1.0f, erff(__fmul_rn(tu, inv_sqrt2))));
+    float cl = __fmul_rn(0.5f, __fadd_rn(1.0f, erff(__fmul_rn(tl, inv_sqrt2))));
+    l = __fsub_rn(cu, cl);
+  } else {
+    float a = fabsf(d);
+    float s = lower_bound_f(sigma, scale_bound);
+    float r = __frcp_rn(s);
+    const float c = -0.70710678118654752440f;
+    float tu = __fmul_rn(__fsub_rn(0.5f, a), r);
+    float tl = __fmul_rn(__fsub_rn(-0.5f, a), r);
+    float cu = __fmul_rn(0.5f, erfcf(__fmul_rn(c, tu)));
+    float cl = __fmul_rn(0.5f, erfcf(__fmul_rn(c, tl)));
+    l = __fsub_rn(cu, cl);
+  }
+  return lower_bound_f(l, lik_bound);  // NaN stays NaN, like torch.clamp / torch.max
+}
+
+struct LikParams {
+  const float* v; long long v_rs, v_off;
+  const float* mu; long long mu_rs, mu_off; int mu_mode;
+  const float* sigma; long long sg_rs, sg_off; int sg_mode; int sg_period;
+  long long rows, cols;
+  int quant, sigma_is_log;
+  float lik_bound, scale_bound;
+  float* v_hat; long long vh_rs, vh_off;
+  __nv_bfloat16* v_hat_bf16; long long vb_rs, vb_off;
+  float* lik;
+  float* sum_out;
+  LikWs* ws;
+};
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using T = float4; };
+template <> struct VecT<1> { using T = float; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&o)[VEC]) {
+  if (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = t.x; o[1 % VEC] = t.y; o[2 % VEC] = t.z; o[3 % VEC] = t.w;
+  } else {
+    o[0] = __ldg(p);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&o)[VEC]) {
+  if (VEC == 4) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
+  } else {
+    p[0] = o[0];
+  }
+}
+
+template <int VEC, int FORM>
+__global__ void __launch_bounds__(kLikThreads) k_likelihood(LikParams P) {
+  const long long colsv = P.cols / VEC;
+  const long long total = P.rows * colsv;
+  const long long stride = (long long)gridDim.x * kLikThreads;
+  long long i = (long long)blockIdx.x * kLikThreads + threadIdx.x;
+  long long row = i / colsv, cv = i - row * colsv;
+  const long long step_r = stride / colsv, step_c = stride - step_r * colsv;
+  float acc = 0.f;  // sum of log2(L) for this thread
+  for (; i < total; i += stride) {
+    const long long col = cv * VEC;
+    float v[VEC], mu[VEC], sg[VEC], vh[VEC], lk[VEC];
+    load_vec<VEC>(P.v + row * P.v_rs + P.v_off + col, v);
+    if (P.mu_mode == 2) load_vec<VEC>(P.mu + row * P.mu_rs + P.mu_off + col, mu);
+    else if (P.mu_mode == 1) load_vec<VEC>(P.mu + col, mu);
+    else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) mu[k] = 0.f;
+    }
+    if (P.sg_mode == 2) load_vec<VEC>(P.sigma + row * P.sg_rs + P.sg_off + col, sg);
+    else if (P.sg_mode == 1) load_vec<VEC>(P.sigma + col, sg);
+    else {
+      float s = __ldg(P.sigma + (row % P.sg_period));
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) sg[k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float s = P.sigma_is_log ? expf(sg[k]) : sg[k];
+      vh[k] = quantise(v[k], mu[k], P.quant);
+      lk[k] = likelihood<FORM>(vh[k], mu[k], s, P.lik_bound, P.scale_bound);
+      acc += __log2f(lk[k]);
+    }
+    if (P.v_hat) store_vec<VEC>(P.v_hat + row * P.vh_rs + P.vh_off + col, vh);
+    if (P.v_hat_bf16) {
+      __nv_bfloat16* q = P.v_hat_bf16 + row * P.vb_rs + P.vb_off + col;
+      if (VEC == 4) {
+        uint2 t = make_uint2(pack_bf16x2(vh[0], vh[1 % VEC]), pack_bf16x2(vh[2 % VEC], vh[3 % VEC]));
+        *reinterpret_cast<uint2*>(q) = t;
+      } else {
+        q[0] = __float2bfloat16_rn(vh[0]);
+      }
+    }
+    if (P.lik) store_vec<VEC>(P.lik + row * P.cols + col, lk);
+    cv += step_c; row += step_r;
+    if (cv >= colsv) { cv -= colsv; ++row; }
+  }
+  // block reduction (warp shuffle -> smem -> double), then a deterministic last-block pass
+  __shared__ float wsum[kLikThreads / 32];
+  __shared__ bool is_last;
+  float w = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kLikThreads / 32; ++k) s += (double)wsum[k];
+    P.ws->partial[blockIdx.x] = s;
+    __threadfence();
+    unsigned int t = atomicAdd(&P.ws->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    __threadfence();
+    double s = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) s += *((volatile double*)&P.ws->partial[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) {
+      P.sum_out[0] = (float)(s * 0.69314718055994530942);  // sum ln L
+      P.ws->ticket = 0;                                      // leave the workspace reusable
+    }
+  }
+}
+
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+extern "C" int ldic_round_likelihood_bpp(const LdicLikelihoodArgs* a, void* stream) {
+  if (!a || !a->v || !a->sigma || !a->sum_ln_out || !a->workspace) return fail(LDIC_EINVAL, "likelihood: null argument");
+  if (a->rows < 0 || a->cols < 0) return fail(LDIC_EINVAL, "likelihood: negative shape");
+  if (a->mu_mode < 0 || a->mu_mode > 2 || a->sigma_mode < 1 || a->sigma_mode > 3) return fail(LDIC_EINVAL, "likelihood: bad broadcast mode");
+  if (a->mu_mode != 0 && !a->mu) return fail(LDIC_EINVAL, "likelihood: mu is null");
+  if (a->sigma_mode == 3 && a->sigma_period <= 0) return fail(LDIC_EINVAL, "likelihood: sigma_period");
+  if (a->form < 0 || a->form > 1 || a->quant < 0 || a->quant > 3) return fail(LDIC_EINVAL, "likelihood: bad form/quant");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->rows == 0 || a->cols == 0) {  // empty input: sum over nothing = 0 (torch.sum of empty)
+    LDIC_CUDA(cudaMemsetAsync(a->sum_ln_out, 0, sizeof(float), st));
+    return LDIC_OK;
+  }
+  LikParams P;
+  P.v = a->v; P.v_rs = a->v_rs; P.v_off = a->v_off;
+  P.mu = a->mu; P.mu_rs = a->mu_rs; P.mu_off = a->mu_off; P.mu_mode = a->mu_mode;
+  P.sigma = a->sigma; P.sg_rs = a->sigma_rs; P.sg_off = a->sigma_off; P.sg_mode = a->sigma_mode;
+  P.sg_period = a->sigma_period > 0 ? a->sigma_period : 1;
+  P.rows = a->rows; P.cols = a->cols; P.quant = a->quant; P.sigma_is_log = a->sigma_is_log;
+  P.lik_bound = a->lik_bound; P.scale_bound = a->scale_bound;
+  P.v_hat = a->v_hat; P.vh_rs = a->v_hat_rs; P.vh_off = a->v_hat_off;
+  P.v_hat_bf16 = (__nv_bfloat16*)a->v_hat_bf16; P.vb_rs = a->vb_rs; P.vb_off = a->vb_off;
+  P.lik = a->lik; P.sum_out = a->sum_ln_out; P.ws = (LikWs*)a->workspace;
+  // dense per-element problems collapse to a single row (no per-row index math)
+  bool dense = (P.v_rs == P.cols && P.v_off == 0) &&
+               (P.mu_mode == 0 || (P.mu_mode == 2 && P.mu_rs == P.cols && P.mu_off == 0)) &&
+               (P.sg_mode == 2 && P.sg_rs == P.cols && P.sg_off == 0) &&
+               (!P.v_hat || (P.vh_rs == P.cols && P.vh_off == 0)) &&
+               (!P.v_hat_bf16 || (P.vb_rs == P.cols && P.vb_off == 0));
+  if (dense) {
+    P.cols = P.rows * P.cols; P.rows = 1;
+    P.v_rs = P.mu_rs = P.sg_rs = P.vh_rs = P.vb_rs = P.cols;
+  }
+  auto ok4 = [](long long x) { return (x & 3) == 0; };
+  bool vec4 = ok4(P.cols) && ok4(P.v_rs) && ok4(P.v_off) && aligned16(P.v) &&
+              (P.mu_mode == 0 || (ok4(P.mu_rs) && ok4(P.mu_off) && aligned16(P.mu))) &&
+              (P.sg_mode == 3 || (ok4(P.sg_rs) && ok4(P.sg_off) && aligned16(P.sigma))) &&
+              (!P.v_hat || (ok4(P.vh_rs) && ok4(P.vh_off) && aligned16(P.v_hat))) &&
+              (!P.v_hat_bf16 || (ok4(P.vb_rs) && ok4(P.vb_off) && ((((uintptr_t)P.v_hat_bf16) & 7) == 0))) &&
+              (!P.lik || aligned16(P.lik));
+  long long items = P.rows * (P.cols / (vec4 ? 4 : 1));
+  int grid = (int)((items + kLikThreads - 1) / kLikThreads);
+  if (grid > kLikMaxBlocks) grid = kLikMaxBlocks;
+  if (grid < 1) grid = 1;
+  if (vec4) {
+    if (a->form == 0) k_likelihood<4, 0><<<grid, kLikThreads, 0, st>>>(P);
+    else k_likelihood<4, 1><<<grid, kLikThreads, 0, st>>>(P);
+  } else {
+    if (a->form == 0) k_likelihood<1, 0><<<grid, kLikThreads, 0, st>>>(P);
+    else k_likelihood<1, 1><<<grid, kLikThreads, 0, st>>>(P);
+  }
+  return check_launch("k_likelihood");
+}
+
+// ------------------------------------------------------------------------------------
+// a11: MSE on 8-bit levels (exact integer accumulation)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int sq_level_err(float x, float xt, int clamp_pm1) {
+  if (clamp_pm1) xt = fminf(fmaxf(xt, -1.f), 1.f);
+  float gt = rintf(__fmul_rn(__fadd_rn(x, 1.f), 127.5f));
+  float xh = __fmul_rn(__fadd_rn(xt, 1.f), 127.5f);
+  xh = rintf(fminf(fmaxf(xh, 0.f), 255.f));
+  float d = xh - gt;   // integers: exact
+  return (unsigned int)(d * d);
+}
+
+__global__ void __launch_bounds__(256) k_mse_sum(const float* __restrict__ x, const float* __restrict__ xt,
+                                                 long long chw, int clamp_pm1, unsigned long long* __restrict__ out) {
+  const int b = blockIdx.y;
+  const float* xb = x + (long long)b * chw;
+  const float* tb = xt + (long long)b * chw;
+  unsigned long long acc = 0;
+  long long n4 = ((((uintptr_t)xb | (uintptr_t)tb) & 15) == 0) ? chw / 4 : 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(xb) + i);
+    float4 t = __ldg(reinterpret_cast<const float4*>(tb) + i);
+    acc += sq_level_err(a.x, t.x, clamp_pm1) + sq_level_err(a.y, t.y, clamp_pm1) +
+           sq_level_err(a.z, t.z, clamp_pm1) + sq_level_err(a.w, t.w, clamp_pm1);
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < chw; i += (long long)gridDim.x * 256)
+    acc += sq_level_err(xb[i], tb[i], clamp_pm1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ unsigned long long ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int k = 0; k < 8; ++k) s += ws[k];
+    atomicAdd(out + b, s);
+  }
+}
+extern "C" int ldic_mse_sum(const float* x, const float* x_tilde, int B, long long chw, int clamp_pm1,
+                            unsigned long long* sq_err, void* stream) {
+  if (B < 0 || chw < 0) return fail(LDIC_EINVAL, "mse: bad shape");
+  if (B == 0 || chw == 0) return LDIC_OK;
+  long long blocks = (chw / 4 + 255) / 256;
+  int per_img = (int)(blocks < 1 ? 1 : (blocks > kNumSMs * 4 ? kNumSMs * 4 : blocks));
+  k_mse_sum<<<dim3(per_img, B), 256, 0, (cudaStream_t)stream>>>(x, x_tilde, chw, clamp_pm1, sq_err);
+  return check_launch("k_mse_sum");
+}
+
+// batch_conv (per-image 1x1, M -> 3) + the a11 arithmetic.  One thread per pixel.
+template <int M>
+__global__ void __launch_bounds__(256) k_syntax_conv_mse(const float* __restrict__ x, const float* __restrict__ xt,
+                                                         const float* __restrict__ w, long long HW,
+                                                         float* __restrict__ xo, unsigned long long* __restrict__ out) {
+  const int b = blockIdx.y;
+  __shared__ float ws[3 * M];
+  __shared__ unsigned long long red[8];
+  for (int i = threadIdx.x; i < 3 * M; i += 256) ws[i] = w[(long long)b * 3 * M + i];
+  __syncthreads();
+  unsigned long long acc = 0;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < HW; p += (long long)gridDim.x * 256) {
+    const float4* src = reinterpret_cast<const float4*>(xt + ((long long)b * HW + p) * M);
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < M / 4; ++q) {
+      float4 t = __ldg(src + q);
+      float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o0 = fmaf(tv[k], ws[q * 4 + k], o0);
+        o1 = fmaf(tv[k], ws[M + q * 4 + k], o1);
+        o2 = fmaf(tv[k], ws[2 * M + q * 4 + k], o2);
+      }
+    }
+    const float o[3] = {o0, o1, o2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      long long idx = ((long long)b * 3 + c) * HW + p;
+      if (xo) xo[idx] = o[c];
+      acc += sq_level_err(__ldg(x + idx), o[c], 0);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int k = 0; k < 8; ++k) s += red[k];
+    atomicAdd(out + b, s);
+  }
+}
+extern "C" int ldic_syntax_conv_mse(const float* x_nchw, const float* xt_nhwc, const float* w, int B, int M, int H, int W,
+                                    float* x_tilde_nchw, unsigned long long* sq_err, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return (B == 0 || H == 0 || W == 0) ? LDIC_OK : fail(LDIC_EINVAL, "syntax_conv_mse: bad shape");
+  long long HW = (long long)H * W;
+  long long blocks = (HW + 255) / 256;
+  int per_img = (int)(blocks > kNumSMs * 4 ? kNumSMs * 4 : blocks);
+  dim3 grid(per_img, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 16) k_syntax_conv_mse<16><<<grid, 256, 0, st>>>(x_nchw, xt_nhwc, w, HW, x_tilde_nchw, sq_err);
+  else if (M == 32) k_syntax_conv_mse<32><<<grid, 256, 0, st>>>(x_nchw, xt_nhwc, w, HW, x_tilde_nchw, sq_err);
+  else return fail(LDIC_EINVAL, "syntax_conv_mse: M=%d unsupported (16 or 32)", M);
+  return check_launch("k_syntax_conv_mse");
+}
+
+// ------------------------------------------------------------------------------------
+// layout / dtype glue
+// ------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC bf16 through a 32-pixel x 32-channel smem tile.
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                           int C, long long HW, int Cp, int apply_abs) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
+  for (int r = ty; r < 32; r += 8) {
+    int c = c0 + r;
+    long long p = p0 + tx;
+    float v = (c < C && p < HW) ? x[((long long)b * C + c) * HW + p] : 0.f;
+    t[r][tx] = apply_abs ? fabsf(v) : v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    long long p = p0 + r;
+    int c = c0 + tx;
+    if (p < HW && c < Cp) y[((long long)b * HW + p) * Cp + c] = __float2bfloat16_rn(t[tx][r]);
+  }
+}
+extern "C" int ldic_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, int Cp, int apply_abs,
+                                          void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return LDIC_OK;
+  if (Cp < C) return fail(LDIC_EINVAL, "nchw_to_nhwc: Cp < C");
+  long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (Cp + 31) / 32, B);
+  k_nchw_to_nhwc_bf16<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, C, HW, Cp, apply_abs);
+  return check_launch("k_nchw_to_nhwc_bf16");
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const TIn* __restrict__ x, float* __restrict__ y, int C,
+                                                      long long HW, int Cp) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    long long p = p0 + r;
+    int c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < Cp) v = (float)x[((long long)b * HW + p) * Cp + c];
+    t[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int c = c0 + r;
+    long long p = p0 + tx;
+    if (c < C && p < HW) y[((long long)b * C + c) * HW + p] = t[tx][r];
+  }
+}
+extern "C" int ldic_nhwc_to_nchw_f32(const void* x, int x_is_bf16, float* y, int B, int C, int H, int W, int Cp,
+                                     void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return LDIC_OK;
+  long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, B);
+  if (x_is_bf16) k_nhwc_to_nchw<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, HW, Cp);
+  else k_nhwc_to_nchw<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, C, HW, Cp);
+  return check_launch("k_nhwc_to_nchw");
+}
+
+__global__ void k_latent_prep(const float* __restrict__ y, size_t n, __nv_bfloat16* __restrict__ yr,
+                              __nv_bfloat16* __restrict__ ya, float* __restrict__ yrf) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) {
+    float v = y[i];
+    float r = rintf(v);
+    if (yr) yr[i] = __float2bfloat16_rn(r);
+    if (ya) ya[i] = __float2bfloat16_rn(fabsf(v));
+    if (yrf) yrf[i] = r;
+  }
+}
+extern "C" int ldic_latent_prep(const float* y, size_t n, void* y_round_bf16, void* y_abs_bf16, float* y_round_f32,
+                                void* stream) {
+  if (n == 0) return LDIC_OK;
+  k_latent_prep<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(y, n, (__nv_bfloat16*)y_round_bf16,
+                                                                (__nv_bfloat16*)y_abs_bf16, y_round_f32);
+  return check_launch("k_latent_prep");
+}
+
+// First-layer patch matrix.  One thread per (pixel, 8-wide k chunk) -> one 16 B store.
+__global__ void __launch_bounds__(256) k_im2col_5x5s2(const float* __restrict__ x, __nv_bfloat16* __restrict__ a,
+                                                      int Cin, int H, int W, int Ho, int Wo, int Kp, long long total) {
+  const int chunks = Kp / 8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int q = (int)(i % chunks);
+    long long p = i / chunks;
+    const int ox = (int)(p % Wo);
+    long long t = p / Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int k = q * 8 + e;
+      float val = 0.f;
+      if (k < 25 * Cin) {
+        int tap = k / Cin, ci = k - tap * Cin;
+        int ky = tap / 5, kx = tap - ky * 5;
+        int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(x + (((long long)b * Cin + ci) * H + iy) * W + ix);
+      }
+      v[e] = val;
+    }
+    uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(a + p * Kp + q * 8) = o;
+  }
+}
+extern "C" int ldic_im2col_5x5s2(const float* x, void* a, int B, int Cin, int H, int W, int Kp, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return LDIC_OK;
+  if ((H & 1) || (W & 1) || Kp % 8 || Kp < 25 * Cin) return fail(LDIC_EINVAL, "im2col: H,W must be even and Kp>=25*Cin, Kp%%8==0");
+  int Ho = H / 2, Wo = W / 2;
+  long long total = (long long)B * Ho * Wo * (Kp / 8);
+  int grid = (int)((total + 255) / 256 > kNumSMs * 16 ? kNumSMs * 16 : (total + 255) / 256);
+  k_im2col_5x5s2<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)a, Cin, H, W, Ho, Wo, Kp, total);
+  return check_launch("k_im2col_5x5s2");
+}

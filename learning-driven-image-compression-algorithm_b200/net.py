@@ -1,0 +1,271 @@
+"""Drop-in ``Net`` of the reference's model/net.py (429-871) on the B200 kernels.
+
+Same constructor, same ``forward(inputs, mode, num)`` contract in test mode
+(returns ``(bpp, v_mse[B], v_psnr)``), same parameter / buffer names, so a
+reference checkpoint loads with ``strict=True`` (the four one-hot
+``*_sampler.sample_filter`` buffers and the HAN post-processing head are
+accepted and discarded: the sampler is a gather here, post-processing is out of
+scope of this path).
+
+Kernel coverage: g_a + GDN (a1,a2,a3), h_a (a4), h_s (a5), rounding
+(a6), GaussianModel likelihoods (a7), bpp reduction (a9), g_s + IGDN (a10),
+batch_conv + MSE/PSNR (a11) run on libldic_b200.  The context / syntax
+branches run as stock torch ops on the GPU.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .layers import GaussianModel, psnr_from_sq_err
+from .transforms import (analysisTransformModel, h_analysisTransformModel, h_synthesisTransformModel,
+                         synthesisTransformModel)
+
+_DISCARDED_PREFIXES = ("HAN.", "conv_weights_gen_HAN.", "add_mean.")
+
+
+class conv_generator(nn.Module):
+    """model/net.py:322-343."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.transform = nn.Sequential(nn.Linear(in_dim, 128), nn.LeakyReLU(0.2), nn.Linear(128, 256),
+                                       nn.LeakyReLU(0.2), nn.Linear(256, out_dim * 3))
+
+    def forward(self, x):
+        b = x.shape[0]
+        return self.transform(x.reshape(b, -1)).view(b, 3, self.out_dim, 1, 1)
+
+
+class Syntax_Model(nn.Module):
+    """model/net.py:349-375."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.down0 = nn.Conv2d(in_dim, 32, 3, 2, 1)
+        self.down1 = nn.Conv2d(32, 64, 3, 2, 1)
+        self.conv = nn.Conv2d(in_dim + 32 + 64, out_dim, 1, 1, 0)
+        self.pooling = nn.AdaptiveAvgPool2d(1)
+
+    def forward(self, syntax):
+        out1 = self.pooling(syntax)
+        ds1 = F.relu(self.down0(syntax))
+        out2 = self.pooling(ds1)
+        ds2 = F.relu(self.down1(ds1))
+        out3 = self.pooling(ds2)
+        return self.conv(torch.cat((out1, out2, out3), 1))
+
+
+class PredictionModel_Syntax(nn.Module):
+    """model/net.py:378-413.  Returns (mu, sigma); Net binds them swapped like the reference (:789)."""
+
+    def __init__(self, in_dim, dim=192, trainable=True, outdim=None):
+        super().__init__()
+        outdim = dim if outdim is None else outdim
+        self.down0 = nn.Conv2d(in_dim, dim, 3, 2, 1)
+        self.down1 = nn.Conv2d(dim, dim, 3, 2, 1)
+        self.pooling = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(dim * 2 + in_dim, outdim)
+        self.flatten = nn.Flatten()
+
+    def forward(self, y_rounded, h_tilde, h_sampler=None):
+        b, c, h, w = y_rounded.size()
+        ds0 = F.relu(self.down0(h_tilde))
+        ds1 = F.relu(self.down1(ds0))
+        ctx = self.flatten(torch.cat((self.pooling(h_tilde), self.pooling(ds0), self.pooling(ds1)), 1))
+        t = self.fc(ctx)
+        mu = t[:, :c].view(b, h, w, c).permute(0, 3, 1, 2)
+        sigma = torch.exp(t[:, c:]).contiguous().view(b, h, w, c).permute(0, 3, 1, 2)
+        return mu, sigma
+
+
+class PredictionModel_Context(nn.Module):
+    """model/net.py:289-319.  The reference's BlockSample (one-hot 7x7 conv2d, :219-242) is
+    replaced by the equivalent pad + unfold gather: patch cell (i,j) of latent position (y,x) is
+    input[y+i-3, x+j-2]; the y sampler zeroes cells (3,2) and (3,3) (causal mask)."""
+
+    def __init__(self, in_dim, dim=192, trainable=True, outdim=None):
+        super().__init__()
+        outdim = dim if outdim is None else outdim
+        self.transform = nn.Sequential(nn.Conv2d(in_dim, dim, 3, 1, 1), nn.LeakyReLU(0.2),
+                                       nn.Conv2d(dim, dim, 3, 2, 1), nn.LeakyReLU(0.2),
+                                       nn.Conv2d(dim, dim, 3, 1, 1), nn.LeakyReLU(0.2))
+        self.fc = nn.Linear(dim * 2 * 2, outdim)
+        self.flatten = nn.Flatten()
+        self.max_patches_per_chunk = 32768
+
+    @staticmethod
+    def sample(x, masked):
+        b, c, h, w = x.shape
+        t = F.unfold(F.pad(x, (2, 1, 3, 0)), kernel_size=4)             # (b, c*16, h*w)
+        t = t.view(b, c, 4, 4, h * w).permute(0, 4, 1, 2, 3).reshape(b * h * w, c, 4, 4)
+        if masked:
+            t[:, :, 3, 2:] = 0
+        return t
+
+    def raw(self, y_rounded, h_tilde):
+        """fc output (b*h*w, 2c): [:, :c] = mu, [:, c:] = log sigma, rows in (b,h,w) order."""
+        b, c, h, w = y_rounded.shape
+        outs = []
+        rows_per_img = h * w
+        imgs_per_chunk = max(1, self.max_patches_per_chunk // rows_per_img)
+        for i0 in range(0, b, imgs_per_chunk):
+            ys = self.sample(y_rounded[i0:i0 + imgs_per_chunk], True)
+            hs = self.sample(h_tilde[i0:i0 + imgs_per_chunk], False)
+            t = self.transform(torch.cat([ys, hs], 1))
+            outs.append(self.fc(self.flatten(t)))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    def forward(self, y_rounded, h_tilde, y_sampler=None, h_sampler=None):
+        b, c, h, w = y_rounded.shape
+        t = self.raw(y_rounded, h_tilde)
+        mu = t[:, :c].view(b, h, w, c).permute(0, 3, 1, 2)
+        sigma = torch.exp(t[:, c:]).contiguous().view(b, h, w, c).permute(0, 3, 1, 2)
+        return mu, sigma
+
+
+class Net(nn.Module):
+    def __init__(self, train_size, test_size, is_high, post_processing):
+        super().__init__()
+        if post_processing:
+            raise NotImplementedError("HAN post-processing (model/han.py) is outside the rate-distortion forward path")
+        self.train_size = train_size
+        self.test_size = test_size
+        self.post_processing = post_processing
+        self.is_high = is_high
+        N, M = (384, 32) if is_high else (192, 16)
+        if N > 256:
+            raise NotImplementedError("is_high (N=384): fused GDN epilogue supports up to 256 channels in this round")
+        self.M, self.N = M, N
+        self.a_model = analysisTransformModel(3, [N, N, N, N])
+        self.s_model = synthesisTransformModel(N - M, [N, N, N, M])
+        self.s_model.cin_offset = M          # g_s reads the full N-channel rounded latent; syntax rows get zero weights
+        self.s_model.cin_pad = ops._pad64(N)
+        self.syntax_model = Syntax_Model(M, M)
+        self.conv_weights_gen = conv_generator(in_dim=M, out_dim=M)
+        self.ha_model = h_analysisTransformModel(N, [N, N, N], [1, 2, 2])
+        self.hs_model = h_synthesisTransformModel(N, [N, N, N], [2, 2, 1])
+        self.entropy_bottleneck_z2 = GaussianModel()
+        self.entropy_bottleneck_z3 = GaussianModel()
+        self.entropy_bottleneck_z3_syntax = GaussianModel()
+        self.v_z2_sigma = nn.Parameter(torch.ones((1, N, 1, 1), dtype=torch.float32, requires_grad=True))
+        self.register_parameter('z2_sigma', self.v_z2_sigma)       # same tensor under two names (model/net.py:482-488)
+        self.prediction_model = PredictionModel_Context(in_dim=2 * N - M, dim=N, outdim=(N - M) * 2)
+        self.prediction_model_syntax = PredictionModel_Syntax(in_dim=N, dim=M, outdim=M * 2)
+        self.context_tf32 = True
+
+    # -- checkpoint compatibility ---------------------------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        kept = {k: v for k, v in state_dict.items()
+                if not (k.endswith("_sampler.sample_filter") or k.startswith(_DISCARDED_PREFIXES))}
+        return super().load_state_dict(kept, strict=strict, assign=assign)
+
+    def base_params(self):
+        mods = [self.a_model, self.s_model, self.ha_model, self.hs_model, self.syntax_model, self.conv_weights_gen,
+                self.prediction_model, self.prediction_model_syntax]
+        params = [p for m in mods for p in m.parameters()]
+        params.append(self.v_z2_sigma)
+        return params
+
+    def post_processing_params(self):
+        return []
+
+    def batch_conv(self, weights, inputs):
+        """model/net.py:527-537 (kept for API parity; the forward uses the fused kernel)."""
+        b, ch, _, _ = inputs.shape
+        _, ch_out, _, k, _ = weights.shape
+        weights = weights.reshape(b * ch_out, ch, k, k)
+        inputs = torch.cat(torch.split(inputs, 1, dim=0), dim=1)
+        out = F.conv2d(inputs, weights, stride=1, padding=0, groups=b)
+        return torch.cat(torch.split(out, ch_out, dim=1), dim=0)
+
+    # -- the hot path -----------------------------------------------------------------------
+    @torch.no_grad()
+    def rd_forward(self, inputs: torch.Tensor, want_x_hat: bool = False, want_likelihoods: bool = False
+                   ) -> Dict[str, torch.Tensor]:
+        """Rate-distortion forward of Net.forward(mode='test') (model/net.py:539-871).
+        Returns the per-stream sum(ln L) (`bits` = [z, y, syntax]), the exact per-image
+        squared-error sums and, on request, x_hat / likelihood tensors."""
+        if not inputs.is_cuda:
+            raise ops.LdicError("Net runs on CUDA only (no CPU fallback)")
+        x = inputs.contiguous().float()
+        B, _, H, W = x.shape
+        N, M = self.N, self.M
+        if H % 64 or W % 64:
+            raise ops.LdicError("H and W must be multiples of 64 (eval_net.py:68-81 pads to 64)")
+        h, w = H // 16, W // 16
+        P = B * h * w
+
+        y = self.a_model.forward_nhwc(x)                                            # :627   (B,h,w,N) fp32 NHWC
+        y_round_bf16, y_abs_bf16, _ = ops.latent_prep(y)                            # :197 abs, :741 round
+        z = self.ha_model.forward_nhwc(y_abs_bf16)                                  # :666   (B,h/4,w/4,N) fp32
+        Pz = z.shape[0] * z.shape[1] * z.shape[2]
+        z_hat_bf16 = torch.empty(z.shape, dtype=torch.bfloat16, device=x.device)
+        sigma_z = self.z2_sigma.detach().reshape(N).contiguous()
+        lik_z = torch.empty_like(z) if want_likelihoods else None
+        sum_z = ops.likelihood_rows(z, Pz, N, v_rs=N, sigma=sigma_z, sigma_mode=1, quant=ops.QUANT_ROUND,     # :676,:781
+                                    lik_bound=self.entropy_bottleneck_z2.likelihood_bound,
+                                    v_hat_bf16=z_hat_bf16, vb_rs=N, lik=lik_z)
+        h2 = self.hs_model.forward_nhwc(z_hat_bf16)                                 # :681   (B,h,w,N) fp32 NHWC
+
+        y_nchw = y.permute(0, 3, 1, 2)                                              # channels-last view, no copy
+        h2_nchw = h2.permute(0, 3, 1, 2)
+        prev_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(self.context_tf32)
+        try:
+            z3_syntax = self.syntax_model(y_nchw[:, :M])                            # :712-719
+            z3_syntax_rounded = torch.round(z3_syntax)                              # :753
+            y_content_rounded = torch.round(y_nchw[:, M:])                          # :741
+            ctx = self.prediction_model.raw(y_content_rounded, h2_nchw)             # :784  (P, 2(N-M))
+            syn_first, syn_second = self.prediction_model_syntax(z3_syntax_rounded, h2_nchw)   # :789 (mu, sigma) bound swapped
+            conv_w = self.conv_weights_gen(z3_syntax_rounded)                       # :805
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+        Cc = N - M
+        lik_y = torch.empty(B, h, w, Cc, dtype=torch.float32, device=x.device) if want_likelihoods else None
+        sum_y = ops.likelihood_rows(y, P, Cc, v_rs=N, v_off=M, mu=ctx, mu_mode=2, mu_rs=2 * Cc, mu_off=0,      # :786
+                                    sigma=ctx, sigma_mode=2, sigma_rs=2 * Cc, sigma_off=Cc, sigma_is_log=True,
+                                    quant=ops.QUANT_ROUND, lik_bound=self.entropy_bottleneck_z3.likelihood_bound,
+                                    lik=lik_y)
+        # syntax stream: "sigma" <- first return (mu), "mu" <- second (sigma): reference quirk H2
+        _, lik_syn, sum_syn = ops.gaussian_likelihood(z3_syntax_rounded.contiguous(), syn_first.contiguous(),
+                                                      syn_second.contiguous(),
+                                                      lik_bound=self.entropy_bottleneck_z3_syntax.likelihood_bound)
+
+        xt16 = self.s_model.forward_nhwc(y_round_bf16)                              # :800   (B,H,W,M) fp32 NHWC
+        sq_err, x_hat = ops.syntax_conv_mse(x, xt16, conv_w.reshape(B, 3, M), want_x_tilde=want_x_hat)   # :811,:864-868
+
+        out = {"bits": torch.cat([sum_z, sum_y, sum_syn]), "sq_err": sq_err}
+        if want_x_hat:
+            out["x_hat"] = x_hat
+        if want_likelihoods:
+            out["likelihoods"] = {"y": lik_y.permute(0, 3, 1, 2), "z": lik_z.permute(0, 3, 1, 2), "syntax": lik_syn}
+        out["latents"] = {"y": y, "z": z, "h2": h2, "ctx": ctx, "z3_syntax": z3_syntax, "conv_w": conv_w, "xt16": xt16}
+        return out
+
+    def metrics(self, out: Dict[str, torch.Tensor], batch: int, H: int, W: int):
+        """bpp / v_mse / v_psnr exactly as model/net.py:856-869 forms them."""
+        tb, th, tw, tc = self.test_size
+        num_pixels = batch * th * tw
+        bpp = out["bits"].sum() / (-math.log(2) * num_pixels)
+        v_mse, v_psnr = psnr_from_sq_err(out["sq_err"], 3 * H * W)
+        return bpp, v_mse, v_psnr
+
+    def forward(self, inputs, mode='train', num=1):
+        if mode != 'test':
+            raise NotImplementedError("only the rate-distortion forward (mode='test') is implemented; training is out of scope")
+        out = self.rd_forward(inputs)
+        return self.metrics(out, inputs.shape[0], inputs.shape[2], inputs.shape[3])
+
+    def forward_dict(self, inputs):
+        """CompressAI-style view ({'x_hat', 'likelihoods': {'y','z'}}) that RateDistortionLoss
+        (train_net_unet.py:62-87) consumes."""
+        out = self.rd_forward(inputs, want_x_hat=True, want_likelihoods=True)
+        return {"x_hat": out["x_hat"], "likelihoods": {"y": out["likelihoods"]["y"], "z": out["likelihoods"]["z"]}}

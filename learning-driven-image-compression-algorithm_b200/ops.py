@@ -1,0 +1,381 @@
+"""Thin torch-facing wrappers over the C ABI (include/ldic.h).
+
+torch is used for device memory, streams and autograd plumbing only; every op
+launches hand-written sm_100a kernels from libldic_b200.so through ctypes with
+raw device pointers and the current CUDA stream.  No op has a CPU or
+torch-eager fallback: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, LikelihoodArgs, LdicError, check
+
+_ws_cache = {}
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype=None, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise LdicError(f"{name} must be a CUDA tensor (ldic_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise LdicError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(_L().ldic_launch_count())
+
+
+def _workspace(device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _ws_cache.get(key)
+    if ws is None:
+        n = int(_L().ldic_likelihood_workspace_bytes())
+        ws = torch.zeros((n + 7) // 8, dtype=torch.int64, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+# --------------------------------------------------------------------------------------
+# a3
+# --------------------------------------------------------------------------------------
+def lower_bound_fwd(x: torch.Tensor, bound: float) -> torch.Tensor:
+    x = _req(x, torch.float32, "x").contiguous()
+    y = torch.empty_like(x)
+    check(_L().ldic_lower_bound(_ptr(x), float(bound), _ptr(y), x.numel(), _stream()), "ldic_lower_bound")
+    return y
+
+
+def lower_bound_bwd(x: torch.Tensor, bound: float, grad_out: torch.Tensor) -> torch.Tensor:
+    x = _req(x, torch.float32, "x").contiguous()
+    g = _req(grad_out, torch.float32, "grad").contiguous()
+    gi = torch.empty_like(g)
+    check(_L().ldic_lower_bound_bwd(_ptr(x), float(bound), _ptr(g), _ptr(gi), x.numel(), _stream()), "ldic_lower_bound_bwd")
+    return gi
+
+
+class _LowerBoundFn(torch.autograd.Function):
+    """ops/bound_ops.py:30-41 / model/gdn.py:11-26 with both passes on our kernels."""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        ctx.save_for_backward(x)
+        ctx.bound = float(bound)
+        return lower_bound_fwd(x, bound)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (x,) = ctx.saved_tensors
+        return lower_bound_bwd(x, ctx.bound, grad_output), None
+
+
+def lower_bound(x: torch.Tensor, bound: float) -> torch.Tensor:
+    return _LowerBoundFn.apply(x, float(bound))
+
+
+def nonneg_reparam(p: torch.Tensor, bound: float, pedestal: float) -> torch.Tensor:
+    p = _req(p, torch.float32, "p").contiguous()
+    out = torch.empty_like(p)
+    check(_L().ldic_nonneg_reparam(_ptr(p), float(bound), float(pedestal), _ptr(out), p.numel(), _stream()),
+          "ldic_nonneg_reparam")
+    return out
+
+
+def gdn_prepare(beta_p: torch.Tensor, gamma_p: torch.Tensor, beta_bound: float, gamma_bound: float, pedestal: float,
+                tc_groups: int = 0, tc_np: int = 0):
+    """-> (beta_eff[C], gamma_eff[C,C]) and, when tc_np>0, (gamma_bf16[Np,Np], beta_tiled[Np])."""
+    beta_p = _req(beta_p, torch.float32, "beta").contiguous()
+    gamma_p = _req(gamma_p, torch.float32, "gamma").contiguous()
+    Cc = beta_p.numel()
+    if gamma_p.numel() != Cc * Cc:
+        raise LdicError("gamma must be CxC")
+    dev = beta_p.device
+    beta_eff = torch.empty(Cc, dtype=torch.float32, device=dev)
+    gamma_eff = torch.empty(Cc, Cc, dtype=torch.float32, device=dev)
+    g16 = bt = None
+    if tc_np:
+        g16 = torch.empty(tc_np, tc_np, dtype=torch.bfloat16, device=dev)
+        bt = torch.empty(tc_np, dtype=torch.float32, device=dev)
+    check(_L().ldic_gdn_prepare(_ptr(beta_p), _ptr(gamma_p), Cc, float(beta_bound), float(gamma_bound), float(pedestal),
+                                _ptr(beta_eff), _ptr(gamma_eff), _ptr(g16), _ptr(bt), int(tc_groups or 1), int(tc_np),
+                                int(tc_np), _stream()), "ldic_gdn_prepare")
+    return beta_eff, gamma_eff, g16, bt
+
+
+def gdn_nchw(x: torch.Tensor, beta_eff: torch.Tensor, gamma_eff: torch.Tensor, inverse: bool, use_rsqrt: bool) -> torch.Tensor:
+    x = _req(x, torch.float32, "x").contiguous()
+    if x.dim() != 4:
+        raise LdicError("GDN expects (B,C,H,W)")
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    check(_L().ldic_gdn_nchw_f32(_ptr(x), _ptr(beta_eff), _ptr(gamma_eff), _ptr(y), B, Cc, H, W, int(bool(inverse)),
+                                 int(bool(use_rsqrt)), _stream()), "ldic_gdn_nchw_f32")
+    return y
+
+
+# --------------------------------------------------------------------------------------
+# a6-a9
+# --------------------------------------------------------------------------------------
+QUANT_NONE, QUANT_ROUND, QUANT_DEQUANT, QUANT_STE = 0, 1, 2, 3
+FORM_GAUSSIAN_MODEL, FORM_GAUSSIAN_CONDITIONAL = 0, 1
+
+
+def likelihood_rows(v, rows, cols, *, v_rs, v_off=0, mu=None, mu_mode=0, mu_rs=0, mu_off=0,
+                    sigma=None, sigma_mode=2, sigma_rs=0, sigma_off=0, sigma_period=1,
+                    quant=QUANT_NONE, form=FORM_GAUSSIAN_MODEL, sigma_is_log=False,
+                    lik_bound=1e-8, scale_bound=0.11,
+                    v_hat=None, v_hat_rs=0, v_hat_off=0, v_hat_bf16=None, vb_rs=0, vb_off=0,
+                    lik=None, sum_out=None) -> torch.Tensor:
+    """Raw strided form of ldic_round_likelihood_bpp; returns the 1-element sum(ln L) tensor."""
+    _req(v, torch.float32, "v")
+    _req(sigma, torch.float32, "sigma")
+    if sum_out is None:
+        sum_out = torch.empty(1, dtype=torch.float32, device=v.device)
+    a = LikelihoodArgs()
+    a.v, a.v_rs, a.v_off = _ptr(v), v_rs, v_off
+    a.mu, a.mu_rs, a.mu_off, a.mu_mode = _ptr(mu), mu_rs, mu_off, mu_mode
+    a.sigma, a.sigma_rs, a.sigma_off, a.sigma_mode, a.sigma_period = _ptr(sigma), sigma_rs, sigma_off, sigma_mode, sigma_period
+    a.rows, a.cols = rows, cols
+    a.quant, a.form, a.sigma_is_log = quant, form, int(bool(sigma_is_log))
+    a.lik_bound, a.scale_bound = float(lik_bound), float(scale_bound)
+    a.v_hat, a.v_hat_rs, a.v_hat_off = _ptr(v_hat), v_hat_rs, v_hat_off
+    a.v_hat_bf16, a.vb_rs, a.vb_off = _ptr(v_hat_bf16), vb_rs, vb_off
+    a.lik = _ptr(lik)
+    a.sum_ln_out = _ptr(sum_out)
+    a.workspace = _ptr(_workspace(v.device))
+    check(_L().ldic_round_likelihood_bpp(C.byref(a), _stream()), "ldic_round_likelihood_bpp")
+    return sum_out
+
+
+def gaussian_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch.Tensor] = None, *,
+                        quant: int = QUANT_NONE, form: int = FORM_GAUSSIAN_MODEL, lik_bound: float = 1e-8,
+                        scale_bound: float = 0.11, want_lik: bool = True, want_vhat: bool = False
+                        ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], torch.Tensor]:
+    """Module-surface form on (B,C,H,W) tensors with torch broadcasting rules limited to the
+    reference's two cases: same-shape sigma/mu, or (1,C,1,1) sigma with mu == 0 / (1,C,1,1).
+    Returns (v_hat or None, likelihood or None, sum_ln[1])."""
+    _req(v, torch.float32, "v")
+    if v.dim() != 4:
+        raise LdicError("expected (B,C,H,W)")
+    B, Cc, H, W = v.shape
+    per_channel = sigma.numel() == Cc and sigma.numel() != v.numel()
+    if per_channel:
+        if mu is not None and torch.count_nonzero(mu).item() != 0:
+            # general per-channel mean: fold it in by expanding (rare; not on the reference path)
+            return gaussian_likelihood(v, sigma.expand_as(v).contiguous(), mu.expand_as(v).contiguous(), quant=quant,
+                                       form=form, lik_bound=lik_bound, scale_bound=scale_bound, want_lik=want_lik,
+                                       want_vhat=want_vhat)
+        vc = v.contiguous()
+        sg = sigma.reshape(Cc).contiguous()
+        lik = torch.empty_like(vc) if want_lik else None
+        vh = torch.empty_like(vc) if want_vhat else None
+        s = likelihood_rows(vc, B * Cc, H * W, v_rs=H * W, sigma=sg, sigma_mode=3, sigma_period=Cc, quant=quant,
+                            form=form, lik_bound=lik_bound, scale_bound=scale_bound, v_hat=vh, v_hat_rs=H * W, lik=lik)
+        return vh, lik, s
+    if sigma.shape != v.shape or (mu is not None and mu.shape != v.shape):
+        sigma = sigma.expand_as(v)
+        mu = None if mu is None else mu.expand_as(v)
+    # the reference hands us NCHW *views* of (b,h,w,c) storage (model/net.py:314-317): keep whatever
+    # memory format v has and bring the others to it.
+    if v.is_contiguous():
+        fmt = torch.contiguous_format
+    elif v.is_contiguous(memory_format=torch.channels_last):
+        fmt = torch.channels_last
+    else:
+        v = v.contiguous()
+        fmt = torch.contiguous_format
+    sg = sigma.contiguous(memory_format=fmt)
+    m = None if mu is None else mu.contiguous(memory_format=fmt)
+    n = v.numel()
+    lik = torch.empty_like(v) if want_lik else None      # preserves v's memory format
+    vh = torch.empty_like(v) if want_vhat else None
+    s = likelihood_rows(v, 1, n, v_rs=n, mu=m, mu_mode=2 if m is not None else 0, mu_rs=n, sigma=sg, sigma_mode=2,
+                        sigma_rs=n, quant=quant, form=form, lik_bound=lik_bound, scale_bound=scale_bound, v_hat=vh,
+                        v_hat_rs=n, lik=lik)
+    return vh, lik, s
+
+
+# --------------------------------------------------------------------------------------
+# a11
+# --------------------------------------------------------------------------------------
+def mse_sum(x: torch.Tensor, x_tilde: torch.Tensor, clamp_pm1: bool = False) -> torch.Tensor:
+    """Exact per-image sum of squared 8-bit-level errors (int64[B])."""
+    x = _req(x, torch.float32, "x").contiguous()
+    xt = _req(x_tilde, torch.float32, "x_tilde").contiguous()
+    if x.shape != xt.shape:
+        raise LdicError("x and x_tilde must have the same shape")
+    B = x.shape[0] if x.dim() > 0 else 1
+    chw = x.numel() // max(B, 1)
+    out = torch.zeros(B, dtype=torch.int64, device=x.device)
+    check(_L().ldic_mse_sum(_ptr(x), _ptr(xt), B, chw, int(bool(clamp_pm1)), _ptr(out), _stream()), "ldic_mse_sum")
+    return out
+
+
+def syntax_conv_mse(x_nchw, xt_nhwc, w, want_x_tilde=False):
+    x = _req(x_nchw, torch.float32, "x").contiguous()
+    xt = _req(xt_nhwc, torch.float32, "x_tilde16").contiguous()
+    w = _req(w, torch.float32, "w").contiguous()
+    B, _, H, W = x.shape
+    M = xt.shape[-1]
+    out = torch.zeros(B, dtype=torch.int64, device=x.device)
+    xo = torch.empty_like(x) if want_x_tilde else None
+    check(_L().ldic_syntax_conv_mse(_ptr(x), _ptr(xt), _ptr(w), B, M, H, W, _ptr(xo), _ptr(out), _stream()),
+          "ldic_syntax_conv_mse")
+    return out, xo
+
+
+# --------------------------------------------------------------------------------------
+# glue
+# --------------------------------------------------------------------------------------
+def nchw_to_nhwc_bf16(x: torch.Tensor, Cp: Optional[int] = None, apply_abs: bool = False) -> torch.Tensor:
+    x = _req(x, torch.float32, "x").contiguous()
+    B, Cc, H, W = x.shape
+    Cp = Cp or Cc
+    y = torch.empty(B, H, W, Cp, dtype=torch.bfloat16, device=x.device)
+    check(_L().ldic_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(y), B, Cc, H, W, Cp, int(apply_abs), _stream()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor, Cc: Optional[int] = None) -> torch.Tensor:
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise LdicError("nhwc_to_nchw: bf16 or fp32 input")
+    _req(x, None, "x")
+    x = x.contiguous()
+    B, H, W, Cp = x.shape
+    Cc = Cc or Cp
+    y = torch.empty(B, Cc, H, W, dtype=torch.float32, device=x.device)
+    check(_L().ldic_nhwc_to_nchw_f32(_ptr(x), int(x.dtype == torch.bfloat16), _ptr(y), B, Cc, H, W, Cp, _stream()),
+          "nhwc_to_nchw")
+    return y
+
+
+def latent_prep(y: torch.Tensor, want_round_bf16=True, want_abs_bf16=True, want_round_f32=False):
+    y = _req(y, torch.float32, "y").contiguous()
+    mk = lambda dt: torch.empty(y.shape, dtype=dt, device=y.device)
+    yr = mk(torch.bfloat16) if want_round_bf16 else None
+    ya = mk(torch.bfloat16) if want_abs_bf16 else None
+    yf = mk(torch.float32) if want_round_f32 else None
+    check(_L().ldic_latent_prep(_ptr(y), y.numel(), _ptr(yr), _ptr(ya), _ptr(yf), _stream()), "ldic_latent_prep")
+    return yr, ya, yf
+
+
+def im2col_5x5s2(x: torch.Tensor, Kp: int = 128) -> torch.Tensor:
+    x = _req(x, torch.float32, "x").contiguous()
+    B, Cin, H, W = x.shape
+    a = torch.empty(B, H // 2, W // 2, Kp, dtype=torch.bfloat16, device=x.device)
+    check(_L().ldic_im2col_5x5s2(_ptr(x), _ptr(a), B, Cin, H, W, Kp, _stream()), "ldic_im2col_5x5s2")
+    return a
+
+
+# --------------------------------------------------------------------------------------
+# a1 / a4 / a5 / a10: tensor-core conv layers
+# --------------------------------------------------------------------------------------
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+class ConvTC:
+    """One conv / transposed-conv layer of the transforms, weights pre-packed for the
+    tcgen05 kernel.  Input and output are NHWC tensors (bf16 in; bf16 or fp32 out)."""
+
+    def __init__(self, kind: int, weight: torch.Tensor, bias: Optional[torch.Tensor], *, act: int = _lib.ACT_NONE,
+                 out_f32: bool = False, cin_pad: Optional[int] = None, cin_offset: int = 0,
+                 cout_pad: Optional[int] = None, gdn: Optional[tuple] = None):
+        w = _req(weight, torch.float32, "weight").contiguous()
+        transposed = kind in (_lib.LDIC_DECONV_GS_5x5, _lib.LDIC_DECONV_HS_5x5, _lib.LDIC_DECONV_S1_3x3,
+                              _lib.LDIC_DECONV_GS_5x5_MERGED)
+        if kind == _lib.LDIC_CONV_1x1:
+            w = w.reshape(w.shape[0], -1).contiguous()
+            cout, cin = w.shape
+        elif transposed:
+            cin, cout = w.shape[0], w.shape[1]
+        else:
+            cout, cin = w.shape[0], w.shape[1]
+        self.kind, self.act, self.out_f32 = kind, act, bool(out_f32)
+        self.cin, self.cout = cin, cout
+        self.cin_pad = cin_pad or _pad64(cin + cin_offset)
+        self.cout_pad = cout_pad or cout
+        self.device = w.device
+        d = self._desc(1, 16, 16)
+        L = _L()
+        self.np_cols = L.ldic_conv_n_cols(C.byref(d))
+        n = L.ldic_conv_weight_elems(C.byref(d))
+        if n < 0 or self.np_cols < 0:
+            check(-1, "ldic_conv_weight_elems")
+        self.w_packed = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+        self.bias_packed = torch.empty(self.np_cols, dtype=torch.float32, device=w.device)
+        b = None if bias is None else _req(bias, torch.float32, "bias").contiguous()
+        check(L.ldic_conv_pack_weights(C.byref(d), _ptr(w), _ptr(b), int(cin_offset), _ptr(self.w_packed),
+                                       _ptr(self.bias_packed), _stream()), "ldic_conv_pack_weights")
+        self.gamma_bf16 = self.beta_tiled = None
+        if act in (_lib.ACT_GDN, _lib.ACT_IGDN):
+            if gdn is None:
+                raise LdicError("GDN epilogue needs (beta_p, gamma_p, beta_bound, gamma_bound, pedestal)")
+            beta_p, gamma_p, bb, gb, ped = gdn
+            groups = self.np_cols // self.cout_pad
+            _, _, self.gamma_bf16, self.beta_tiled = gdn_prepare(beta_p, gamma_p, bb, gb, ped, tc_groups=groups,
+                                                                 tc_np=self.np_cols)
+
+    def _desc(self, B, H, W) -> ConvDesc:
+        return ConvDesc(self.kind, B, H, W, self.cin, self.cout, self.cin_pad, self.cout_pad, self.act, int(self.out_f32))
+
+    def out_hw(self, H, W):
+        d = self._desc(1, H, W)
+        ho, wo = C.c_int(), C.c_int()
+        _L().ldic_conv_out_shape(C.byref(d), C.byref(ho), C.byref(wo))
+        return ho.value, wo.value
+
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _req(x, torch.bfloat16, "x")
+        if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
+            raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
+        B, H, W, _ = x.shape
+        ho, wo = self.out_hw(H, W)
+        if out is None:
+            out = torch.empty(B, ho, wo, self.cout_pad, dtype=torch.float32 if self.out_f32 else torch.bfloat16,
+                              device=x.device)
+        d = self._desc(B, H, W)
+        check(_L().ldic_conv_forward(C.byref(d), _ptr(x), _ptr(self.w_packed), _ptr(self.bias_packed),
+                                     _ptr(self.gamma_bf16), _ptr(self.beta_tiled), _ptr(out), _stream()),
+              "ldic_conv_forward")
+        return out
+
+
+def conv_reference_f32(kind: int, x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """CUDA-core fp32 direct convolution (validation aid, ldic_conv_forward_f32_reference_kernel)."""
+    x = _req(x_nhwc, torch.float32, "x").contiguous()
+    w = _req(weight, torch.float32, "w").contiguous()
+    transposed = kind in (_lib.LDIC_DECONV_GS_5x5, _lib.LDIC_DECONV_HS_5x5, _lib.LDIC_DECONV_S1_3x3,
+                          _lib.LDIC_DECONV_GS_5x5_MERGED)
+    if kind == _lib.LDIC_CONV_1x1:
+        w = w.reshape(w.shape[0], -1).contiguous()
+        cout, cin = w.shape
+    elif transposed:
+        cin, cout = w.shape[0], w.shape[1]
+    else:
+        cout, cin = w.shape[0], w.shape[1]
+    B, H, W, _ = x.shape
+    dq = ConvDesc(kind, B, H, W, cin, 8, _pad64(cin), 64, 0, 1)    # shape query only
+    d = ConvDesc(kind, B, H, W, cin, cout, _pad64(cin), 64, 0, 1)
+    ho, wo = C.c_int(), C.c_int()
+    _L().ldic_conv_out_shape(C.byref(dq), C.byref(ho), C.byref(wo))
+    y = torch.empty(B, ho.value, wo.value, cout, dtype=torch.float32, device=x.device)
+    check(_L().ldic_conv_forward_f32_reference_kernel(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(y), _stream()),
+          "conv_reference_f32")
+    return y

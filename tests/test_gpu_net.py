@@ -1,0 +1,98 @@
+"""End-to-end parity of the drop-in Net against golden fixtures produced by the unmodified
+reference (gates of BASELINE.json: bpp within 0.5 %, PSNR within 0.01 dB)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import det_weights as dw
+from oracle import ref_path as rp
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+BPP_RTOL, PSNR_ATOL_DB = 5e-3, 1e-2
+
+
+def L(name):
+    d = np.load(os.path.join(G, name))
+    return {k: torch.from_numpy(np.asarray(d[k])) for k in d.files}
+
+
+@pytest.fixture(scope="module")
+def ldic():
+    import ldic_b200
+    ldic_b200._lib.check(ldic_b200._lib.load().ldic_check_device(0), "device")
+    return ldic_b200
+
+
+def build(ldic, d):
+    B, th, tw = int(d["B"]), int(d["th"]), int(d["tw"])
+    net = ldic.Net((B, th, tw, 3), (B, th, tw, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(int(d["seed"]), boost=bool(int(d["boost"]))), strict=True)
+    return net
+
+
+@pytest.mark.parametrize("name", ["net_64x64_b1.npz", "net_64x128_b2.npz", "net_evalpad_60x50.npz",
+                                  "net_64x64_default_gain.npz", "net_256x256_b1.npz"])
+def test_net_forward_vs_reference_golden(ldic, name):
+    d = L(name)
+    B, H, W = int(d["B"]), int(d["H"]), int(d["W"])
+    net = build(ldic, d)
+    x = rp.eval_pad(d["img"]) if "img" in d else dw.make_input(int(d["seed"]), B, H, W)
+    bpp, v_mse, v_psnr = net(x.cuda(), "test", 1)
+    assert v_mse.shape == (B,)
+    assert abs(bpp.item() / d["bpp"].item() - 1) < BPP_RTOL, (bpp.item(), d["bpp"].item())
+    assert abs(v_psnr.item() - d["v_psnr"].item()) < PSNR_ATOL_DB, (v_psnr.item(), d["v_psnr"].item())
+    # intermediates: bf16-operand budget on the latents
+    out = net.rd_forward(x.cuda())
+    y = out["latents"]["y"].permute(0, 3, 1, 2).cpu()
+    rel = ((y - d["z3"]).pow(2).mean().sqrt() / d["z3"].pow(2).mean().sqrt()).item()
+    assert rel < 1e-2, rel
+    flips = (torch.round(y) != torch.round(d["z3"])).float().mean().item()
+    assert flips < 0.02, flips
+
+
+def test_net_512x768_scalars(ldic):
+    k = json.load(open(os.path.join(G, "net_512x768_b1.json")))
+    net = ldic.Net((1, 512, 768, 3), (1, 512, 768, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(k["seed"]), strict=True)
+    x = dw.make_input(k["seed"], 1, 512, 768)
+    bpp, v_mse, v_psnr = net(x.cuda(), "test", 1)
+    assert abs(bpp.item() / k["bpp"] - 1) < BPP_RTOL
+    assert abs(v_psnr.item() - k["v_psnr"]) < PSNR_ATOL_DB
+    # batch independence at full size: image 0 of a batch of 2 gives the same per-image numbers
+    x2 = torch.cat([x, dw.make_input(1, 1, 512, 768)], 0).cuda()
+    out2 = net.rd_forward(x2)
+    out1 = net.rd_forward(x.cuda())
+    assert out2["sq_err"][0].item() == out1["sq_err"][0].item()
+
+
+def test_state_dict_contract(ldic):
+    net = ldic.Net((1, 64, 64, 3), (1, 64, 64, 3), False, False)
+    sd = dw.make_state_dict(0)
+    # a reference checkpoint also carries sampler buffers and the HAN head: accepted under strict=True
+    sd["test_y_sampler.sample_filter"] = torch.zeros(1)
+    sd["HAN.head.0.weight"] = torch.zeros(1)
+    net.load_state_dict(sd, strict=True)
+    keys = set(net.state_dict().keys())
+    assert {"v_z2_sigma", "z2_sigma", "a_model.transform.1.weight", "a_model.transform.2.beta", "a_model.transform.2.gamma",
+            "a_model.transform.2.reparam_offset", "a_model.transform.2.pedestal", "s_model.transform.11.gamma",
+            "ha_model.transform.4.bias", "hs_model.transform.4.weight", "prediction_model.fc.weight",
+            "prediction_model_syntax.fc.bias", "syntax_model.conv.weight", "conv_weights_gen.transform.4.weight"} <= keys
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 64, 64), "train")
+
+
+def test_forward_dict_view(ldic):
+    d = L("net_64x64_b1.npz")
+    net = build(ldic, d)
+    x = dw.make_input(0, 1, 64, 64).cuda()
+    o = net.forward_dict(x)
+    assert o["x_hat"].shape == (1, 3, 64, 64)
+    assert o["likelihoods"]["y"].shape == (1, 176, 4, 4) and o["likelihoods"]["z"].shape == (1, 192, 1, 1)
+    # RateDistortionLoss-style bpp (train_net_unet.py:76-79) agrees with the forward's y+z bits
+    bits = sum(torch.log(l).sum() for l in o["likelihoods"].values())
+    out = net.rd_forward(x)
+    assert abs(bits.item() - out["bits"][:2].sum().item()) < 1e-3 * abs(bits.item())
