@@ -217,14 +217,16 @@ class Net(nn.Module):
         y_nchw = y.permute(0, 3, 1, 2)                                              # channels-last view, no copy
         h2_nchw = h2.permute(0, 3, 1, 2)
         prev_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(self.context_tf32)
         try:
+            # the tiny syntax branch stays in full fp32; only the heavy context transform may use TF32
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
             z3_syntax = self.syntax_model(y_nchw[:, :M])                            # :712-719
             z3_syntax_rounded = torch.round(z3_syntax)                              # :753
             y_content_rounded = torch.round(y_nchw[:, M:])                          # :741
-            ctx = self.prediction_model.raw(y_content_rounded, h2_nchw)             # :784  (P, 2(N-M))
             syn_first, syn_second = self.prediction_model_syntax(z3_syntax_rounded, h2_nchw)   # :789 (mu, sigma) bound swapped
             conv_w = self.conv_weights_gen(z3_syntax_rounded)                       # :805
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(self.context_tf32)
+            ctx = self.prediction_model.raw(y_content_rounded, h2_nchw)             # :784  (P, 2(N-M))
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 

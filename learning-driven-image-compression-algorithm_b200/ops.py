@@ -16,6 +16,8 @@ from . import _lib
 from ._lib import ConvDesc, LikelihoodArgs, LdicError, check
 
 _ws_cache = {}
+# bench.py sets this to a list to get (layer, (B,H,W), start_event, end_event) per conv launch
+PROFILE = None
 
 
 def _L():
@@ -341,6 +343,20 @@ class ConvTC:
         _L().ldic_conv_out_shape(C.byref(d), C.byref(ho), C.byref(wo))
         return ho.value, wo.value
 
+    def flops(self, B: int, H: int, W: int) -> float:
+        """Algorithmic FLOPs (2 x MACs on logical channels, no zero-insertion / padding waste):
+        conv: k*k*Cin*Cout per OUTPUT pixel; transposed conv: k*k*Cin*Cout per INPUT pixel;
+        GDN/IGDN: C*C per output pixel."""
+        ho, wo = self.out_hw(H, W)
+        k = {_lib.LDIC_CONV_1x1: 1, _lib.LDIC_CONV_S1_3x3_P1: 3, _lib.LDIC_DECONV_S1_3x3: 3}.get(self.kind, 5)
+        transposed = self.kind in (_lib.LDIC_DECONV_GS_5x5, _lib.LDIC_DECONV_HS_5x5, _lib.LDIC_DECONV_S1_3x3,
+                                   _lib.LDIC_DECONV_GS_5x5_MERGED)
+        pix = B * (H * W if transposed else ho * wo)
+        f = 2.0 * k * k * self.cin * self.cout * pix
+        if self.act in (_lib.ACT_GDN, _lib.ACT_IGDN):
+            f += 2.0 * self.cout * self.cout * B * ho * wo
+        return f
+
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         _req(x, torch.bfloat16, "x")
         if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
@@ -351,9 +367,16 @@ class ConvTC:
             out = torch.empty(B, ho, wo, self.cout_pad, dtype=torch.float32 if self.out_f32 else torch.bfloat16,
                               device=x.device)
         d = self._desc(B, H, W)
+        prof = PROFILE
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(_L().ldic_conv_forward(C.byref(d), _ptr(x), _ptr(self.w_packed), _ptr(self.bias_packed),
                                      _ptr(self.gamma_bf16), _ptr(self.beta_tiled), _ptr(out), _stream()),
               "ldic_conv_forward")
+        if prof is not None:
+            e1.record()
+            prof.append((self, (B, H, W), e0, e1))
         return out
 
 
