@@ -2,10 +2,11 @@
 // (tcgen05.mma, accumulators in TMEM), operands staged by TMA, with the GDN / IGDN
 // normalisation fused into the epilogue as a second tensor-core contraction.
 //
-// One persistent CTA per SM, 320 threads:
-//   warp 0      TMA producer   (one lane)
-//   warp 1      MMA issuer     (one lane) + TMEM allocator
-//   warps 2..9  epilogue       (TMEM -> registers -> global), 2 warps per TMEM lane quadrant
+// One persistent CTA per SM, 384 threads:
+//   warp 0       TMA producer   (one lane)
+//   warp 1       MMA issuer     (one lane) + TMEM allocator
+//   warps 4..11  epilogue       (TMEM -> registers -> global), 2 warps per TMEM lane quadrant
+// (setmaxnreg moves registers from warpgroup 0 to the two epilogue warpgroups)
 //
 // GEMM view: M = 128 output (or, for transposed convs, input-grid) pixels per tile,
 // N = Np accumulator columns (= output channels, or 4 sub-pixel phases x channels for the
@@ -27,7 +28,7 @@ using namespace ldic;
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;          // warpgroup 0: producer, MMA, 2 spare; warpgroups 1-2: epilogue
 constexpr int kEpiThreads = 256;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = 128 B = one swizzle row
@@ -44,6 +45,7 @@ struct Job { int ntaps, tap_begin, oy_off, ox_off; };
 struct ConvParams {
   int mode;                 // 0: stride-1 gather (4-D map), 1: stride-2 gather (5-D parity map)
   int TW, TH, TN;
+  int tw_shift, th_shift, cg_shift;
   int tiles_x, tiles_y, tiles_n, tiles_per_job, njobs, total_tiles;
   int Wg, Hg, B;            // pixel grid the M tiles walk over
   int kc_per_tap;           // Cin_pad / 64
@@ -174,6 +176,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -219,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* x2_ready = acc_empty + 1;
   uint64_t* norm_full = x2_ready + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 2);              // [NP]
+  float* s_bias = reinterpret_cast<float*>(aux + 256);                 // [NP], 16-byte aligned
   float* s_beta = s_bias + NP;                                         // [NP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,6 +257,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kcpt = P.kc_per_tap;
   const int gk = gdn ? P.gdn_kblocks : 0;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // warpgroup 0 hands registers to the epilogue
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -323,20 +333,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  }
   } else {
     // ===================== epilogue warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int h = (warp - 2) >> 2;          // column half
+    const int h = (warp - 4) >> 2;          // column half
     const int r = q * 32 + lane;            // tile row = TMEM lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const int col0 = h * CPT;
+    // row -> pixel of the M grid (TW, TH are powers of two)
+    const int xi = r & (P.TW - 1), yi = (r >> P.tw_shift) & (P.TH - 1), ni = r >> (P.tw_shift + P.th_shift);
+    const bool igdn = (P.act == LDIC_ACT_IGDN);
     uint32_t kcount = 0, it = 0;
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(P, t);
       const Job jb = P.jobs[tc.job];
       const int nkb = jb.ntaps * kcpt;
-      // row -> pixel of the M grid
-      const int xi = r % P.TW, yi = (r / P.TW) % P.TH, ni = r / (P.TW * P.TH);
       const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
       const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B);
       const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
@@ -346,17 +359,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       kcount += nkb;
 
+      // ---- pass 1: accumulator -> registers (+bias); release the accumulator ----
       float xr[CPT];
+      {
+        uint32_t(&xu)[CPT] = reinterpret_cast<uint32_t(&)[CPT]>(xr);
 #pragma unroll
-      for (int c = 0; c < CPT; c += 32) {
-        uint32_t tr[32];
-        tmem_ld32(tmem_base + lane_sel + col0 + c, tr);
+        for (int c = 0; c < CPT; c += 32) tmem_ld32(tmem_base + lane_sel + col0 + c, reinterpret_cast<uint32_t(&)[32]>(xu[c]));
         tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 32; ++k) xr[c + k] = __uint_as_float(tr[k]) + s_bias[col0 + c + k];
       }
       tc_fence_before();
       mbar_arrive(acc_empty);               // accumulator may be overwritten by the next tile
+#pragma unroll
+      for (int c = 0; c < CPT; c += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[col0 + c]);
+        xr[c] += b4.x; xr[c + 1] += b4.y; xr[c + 2] += b4.z; xr[c + 3] += b4.w;
+      }
 
       if (gk) {
         // x^2 -> bf16 -> A slots (K-major, 128B swizzle: 16-byte chunk index XOR (row & 7))
@@ -364,31 +381,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t kc2 = kcount + kb;
           mbar_wait(&empty_bar[kc2 % stages], ((kc2 / stages) & 1) ^ 1);
         }
+        const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
 #pragma unroll
         for (int j = 0; j < CPT / 8; ++j) {
           const int col = col0 + j * 8;
           const uint32_t kc2 = kcount + (col >> 6);
           const uint32_t a_addr = smem_base + (kc2 % stages) * kStageBytes;
           const uint32_t chunk = (uint32_t)((col & 63) >> 3);
-          const uint32_t addr = a_addr + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4);
           const float* x8 = &xr[j * 8];
-          st_shared_v4(addr, pack_bf16x2(x8[0] * x8[0], x8[1] * x8[1]), pack_bf16x2(x8[2] * x8[2], x8[3] * x8[3]),
-                       pack_bf16x2(x8[4] * x8[4], x8[5] * x8[5]), pack_bf16x2(x8[6] * x8[6], x8[7] * x8[7]));
+          st_shared_v4(a_addr + row_off + ((chunk ^ rx) << 4), pack_bf16x2(x8[0] * x8[0], x8[1] * x8[1]),
+                       pack_bf16x2(x8[2] * x8[2], x8[3] * x8[3]), pack_bf16x2(x8[4] * x8[4], x8[5] * x8[5]),
+                       pack_bf16x2(x8[6] * x8[6], x8[7] * x8[7]));
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
         mbar_arrive(x2_ready);
         kcount += gk;
         mbar_wait(norm_full, it & 1);
         tc_fence_after();
+        // ---- pass 2: out = x * rsqrt(norm + beta)   (IGDN: x * sqrt = x * n * rsqrt(n)) ----
 #pragma unroll
         for (int c = 0; c < CPT; c += 32) {
           uint32_t tr[32];
           tmem_ld32(tmem_base + kNormCol + lane_sel + col0 + c, tr);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const float nrm = __uint_as_float(tr[k]) + s_beta[col0 + c + k];
-            xr[c + k] *= (P.act == LDIC_ACT_IGDN) ? sqrtf(nrm) : rsqrtf(nrm);
+          for (int k = 0; k < 32; k += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_beta[col0 + c + k]);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float nrm = __uint_as_float(tr[k + e]) + bb[e];
+              const float rs = rsqrt_approx(nrm);
+              xr[c + k + e] *= igdn ? nrm * rs : rs;
+            }
           }
         }
         tc_fence_before();
@@ -401,20 +426,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 
       if (valid) {
-#pragma unroll
-        for (int j = 0; j < CPT / 8; ++j) {
-          const int col = col0 + j * 8;
-          const int g = col / P.Cg, cc = col - g * P.Cg;
-          const long long off = pix_base + (long long)P.gy[g] * P.out_sY + (long long)P.gx[g] * P.out_sX + cc;
-          const float* x8 = &xr[j * 8];
+        if (P.ngroups == 1) {
+          // this thread's CPT columns are contiguous channels of one output pixel
           if (P.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off);
-            dst[0] = make_float4(x8[0], x8[1], x8[2], x8[3]);
-            dst[1] = make_float4(x8[4], x8[5], x8[6], x8[7]);
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix_base + col0);
+#pragma unroll
+            for (int j = 0; j < CPT / 4; ++j) dst[j] = make_float4(xr[4 * j], xr[4 * j + 1], xr[4 * j + 2], xr[4 * j + 3]);
           } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off);
-            *dst = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
-                              pack_bf16x2(x8[6], x8[7]));
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix_base + col0);
+#pragma unroll
+            for (int j = 0; j < CPT / 8; ++j) {
+              const float* x8 = &xr[j * 8];
+              dst[j] = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
+                                  pack_bf16x2(x8[6], x8[7]));
+            }
+          }
+        } else {
+          // merged sub-pixel phases: Cg (a power of two >= 8) channels per output pixel, group g = col / Cg
+#pragma unroll
+          for (int j = 0; j < CPT / 8; ++j) {
+            const int col = col0 + j * 8;
+            const int g = col >> P.cg_shift, cc = col & (P.Cg - 1);
+            const long long off = pix_base + (long long)(g >> 1) * P.out_sY + (long long)(g & 1) * P.out_sX + cc;
+            const float* x8 = &xr[j * 8];
+            if (P.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off);
+              dst[0] = make_float4(x8[0], x8[1], x8[2], x8[3]);
+              dst[1] = make_float4(x8[4], x8[5], x8[6], x8[7]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off);
+              *dst = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
+                                pack_bf16x2(x8[6], x8[7]));
+            }
           }
         }
       }
@@ -688,6 +731,9 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   memset(&P, 0, sizeof(P));
   P.mode = L.mode;
   choose_tile(L.mode, L.Wg, L.Hg, d->B, &P.TW, &P.TH, &P.TN);
+  auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
+  P.tw_shift = ilog2(P.TW); P.th_shift = ilog2(P.TH); P.cg_shift = ilog2(L.Cg);
+  if (L.ngroups > 1 && ((1 << P.cg_shift) != L.Cg || L.Cg < 8)) return fail(LDIC_EINVAL, "conv: merged deconv needs a power-of-two Cout_pad >= 8");
   P.tiles_x = (L.Wg + P.TW - 1) / P.TW;
   P.tiles_y = (L.Hg + P.TH - 1) / P.TH;
   P.tiles_n = (d->B + P.TN - 1) / P.TN;

@@ -332,8 +332,13 @@ __global__ void __launch_bounds__(kLikThreads) k_likelihood(LikParams P) {
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 extern "C" int ldic_round_likelihood_bpp(const LdicLikelihoodArgs* a, void* stream) {
-  if (!a || !a->v || !a->sigma || !a->sum_ln_out || !a->workspace) return fail(LDIC_EINVAL, "likelihood: null argument");
+  if (!a || !a->sum_ln_out) return fail(LDIC_EINVAL, "likelihood: null argument");
   if (a->rows < 0 || a->cols < 0) return fail(LDIC_EINVAL, "likelihood: negative shape");
+  if (a->rows == 0 || a->cols == 0) {  // empty input: sum over nothing = 0 (torch.sum of an empty tensor)
+    LDIC_CUDA(cudaMemsetAsync(a->sum_ln_out, 0, sizeof(float), (cudaStream_t)stream));
+    return LDIC_OK;
+  }
+  if (!a->v || !a->sigma || !a->workspace) return fail(LDIC_EINVAL, "likelihood: null argument");
   if (a->mu_mode < 0 || a->mu_mode > 2 || a->sigma_mode < 1 || a->sigma_mode > 3) return fail(LDIC_EINVAL, "likelihood: bad broadcast mode");
   if (a->mu_mode != 0 && !a->mu) return fail(LDIC_EINVAL, "likelihood: mu is null");
   if (a->sigma_mode == 3 && a->sigma_period <= 0) return fail(LDIC_EINVAL, "likelihood: sigma_period");
