@@ -254,7 +254,7 @@ def run_ours(args):
                                "(BASELINE configs[1])", "global_batch": world * B, "height": H, "width": W,
                    "weights": "random init (tests/det_weights.py seed 0, gain-boosted)",
                    "l2": f"{NBUF} rotating input batches ({NBUF * in_bytes >> 20} MiB) and ~3 GB of activations per step, both > 126 MB L2",
-                   "context_model": "torch ops (TF32 cuDNN) -- SURVEY 8 f1, not yet on ldic kernels",
+                   "context_model": "PredictionModel_Context on conv_tc_kernel (TMA patch gather, SURVEY 8 f1); syntax branch (<0.1% FLOPs) torch ops",
                    "parallelism": f"batch sharded over {world} GPU(s), 1 all-reduce of 5 scalars per step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": float(tt.item()) / args.steps, "wall_ms_per_step": wall_ms / args.steps},

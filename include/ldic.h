@@ -138,6 +138,9 @@ LDIC_API int ldic_nhwc_to_nchw_f32(const void* x, int x_is_bf16, float* y, int B
 /* y (NHWC fp32, C channels) -> optional outputs: round(y) bf16, |y| bf16, round(y) fp32.
  * model/net.py:197 (abs), :676/:741 (round).                                     */
 LDIC_API int ldic_latent_prep(const float* y, size_t n, void* y_round_bf16, void* y_abs_bf16, float* y_round_f32, void* stream);
+/* Context-model input image [P][2N] bf16 = round(y) (bf16, N ch) | bf16(h2) (fp32 in, N ch)
+ * model/net.py:307-309.                                                          */
+LDIC_API int ldic_ctx_pack_input(const void* y_round_bf16, const float* h2, void* x, long long P, int N, void* stream);
 /* First-layer patch matrix: x NCHW fp32 (B,3,H,W) -> A[B*Ho*Wo][Kp] bf16 with
  * A[p][(ky*5+kx)*Cin+ci] = x[ci, 2oy+ky-1, 2ox+kx-1] (zero outside), zero for
  * k >= 25*Cin.  model/net.py:97-98 (ZeroPad2d((1,2,1,2)) + Conv2d k5 s2).       */
@@ -152,7 +155,14 @@ enum {
   LDIC_DECONV_GS_5x5 = 4,     /* ZeroPad2d((1,0,1,0)) + ConvTranspose2d(k5,s2,p3,op1) model/net.py:128-142 */
   LDIC_DECONV_HS_5x5 = 5,     /* ConvTranspose2d(k5,s2,p2,op1)                model/net.py:207-209  */
   LDIC_DECONV_S1_3x3 = 6,     /* ConvTranspose2d(k3,s1,p1)                    model/net.py:211      */
-  LDIC_DECONV_GS_5x5_MERGED = 7 /* same as 4 with the 4 sub-pixel phases merged into N (small Cout) */
+  LDIC_DECONV_GS_5x5_MERGED = 7, /* same as 4 with the 4 sub-pixel phases merged into N (small Cout) */
+  /* Context model PredictionModel_Context (model/net.py:289-319).  The reference materialises one
+   * 4x4 patch per latent position with a one-hot 7x7 conv (BlockSample, :219-242); here the first
+   * conv gathers the patch cells straight from the latent images by TMA, 16 jobs = 16 patch cells. */
+  LDIC_CTX_CONV1 = 8,  /* x [B,h,w, round(y)(N) | h2(N)] bf16 -> [B*h*w,4,4,N]; aux0=N, aux1=M; Conv2d(2N-M,N,3,1,1) :295 */
+  LDIC_CTX_CONV2 = 9,  /* [P,4,4,N] -> [P,2,2,N]   Conv2d(N,N,3,2,1)  :297                                           */
+  LDIC_CTX_CONV3 = 10, /* [P,2,2,N] -> [P,2,2,N]   Conv2d(N,N,3,1,1)  :299                                           */
+  LDIC_CTX_FC = 11     /* [P,2,2,N] -> [P,1,2,Cout_pad] fp32 (mu | log sigma), Linear(4N, 2*Cout) :302; Cout = N-M   */
 };
 enum { LDIC_ACT_NONE = 0, LDIC_ACT_RELU = 1, LDIC_ACT_LEAKY02 = 2, LDIC_ACT_GDN = 3, LDIC_ACT_IGDN = 4 };
 
@@ -164,6 +174,7 @@ typedef struct {
   int Cout_pad;       /* channels of the output tensor in memory                 */
   int act;            /* LDIC_ACT_*                                              */
   int out_f32;        /* 0: bf16 NHWC output, 1: fp32 NHWC output                */
+  int aux0, aux1;     /* kind specific (LDIC_CTX_CONV1: N, M), else 0            */
 } LdicConvDesc;
 
 /* Elements (bf16) of the packed weight image for this layer, and the packer:
@@ -173,6 +184,9 @@ typedef struct {
  * model/net.py:726).  bias_packed is [Np] fp32.                                */
 LDIC_API long long ldic_conv_weight_elems(const LdicConvDesc* d);
 LDIC_API int ldic_conv_n_cols(const LdicConvDesc* d);  /* Np: accumulator columns          */
+LDIC_API int ldic_conv_bias_elems(const LdicConvDesc* d);  /* floats in bias_packed        */
+/* output tensor dims [B', Ho, Wo, C] (NHWC) */
+LDIC_API int ldic_conv_out_dims(const LdicConvDesc* d, int* dims4);
 LDIC_API int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, const float* bias, int cin_offset,
                            void* w_packed, float* bias_packed, void* stream);
 LDIC_API void ldic_conv_out_shape(const LdicConvDesc* d, int* Ho, int* Wo);

@@ -20,6 +20,10 @@ LDIC_DECONV_GS_5x5 = 4
 LDIC_DECONV_HS_5x5 = 5
 LDIC_DECONV_S1_3x3 = 6
 LDIC_DECONV_GS_5x5_MERGED = 7
+LDIC_CTX_CONV1 = 8
+LDIC_CTX_CONV2 = 9
+LDIC_CTX_CONV3 = 10
+LDIC_CTX_FC = 11
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_GDN, ACT_IGDN = 0, 1, 2, 3, 4
 
 
@@ -45,7 +49,7 @@ class LikelihoodArgs(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int),
                 ("Cout", C.c_int), ("Cin_pad", C.c_int), ("Cout_pad", C.c_int), ("act", C.c_int),
-                ("out_f32", C.c_int)]
+                ("out_f32", C.c_int), ("aux0", C.c_int), ("aux1", C.c_int)]
 
 
 _SIGS = {
@@ -70,9 +74,12 @@ _SIGS = {
     "ldic_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p]),
     "ldic_latent_prep": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_ctx_pack_input": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "ldic_im2col_5x5s2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldic_conv_weight_elems": (C.c_longlong, [C.POINTER(ConvDesc)]),
     "ldic_conv_n_cols": (C.c_int, [C.POINTER(ConvDesc)]),
+    "ldic_conv_bias_elems": (C.c_int, [C.POINTER(ConvDesc)]),
+    "ldic_conv_out_dims": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int)]),
     "ldic_conv_pack_weights": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
     "ldic_conv_out_shape": (None, [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -34,13 +34,15 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = 128 B = one swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
-constexpr int kMaxTaps = 36;
-constexpr int kMaxJobs = 4;
+constexpr int kMaxTaps = 112;
+constexpr int kMaxJobs = 16;
 constexpr int kTmemCols = 512;
 constexpr int kNormCol = 256;
 
-struct Tap { int dx, dy, px; };
-struct Job { int ntaps, tap_begin, oy_off, ox_off; };
+// one filter tap = one spatial offset of the gather + a K range: nkc 64-wide blocks starting at
+// channel a_c0 of the activation and column b_c0 of the tap's packed weight block
+struct Tap { short dx, dy, px, nkc; int a_c0, b_c0; };
+struct Job { int ntaps, tap_begin, nkb, oy_off, ox_off, out_off; };
 
 struct ConvParams {
   int mode;                 // 0: stride-1 gather (4-D map), 1: stride-2 gather (5-D parity map)
@@ -48,13 +50,12 @@ struct ConvParams {
   int tw_shift, th_shift, cg_shift;
   int tiles_x, tiles_y, tiles_n, tiles_per_job, njobs, total_tiles;
   int Wg, Hg, B;            // pixel grid the M tiles walk over
-  int kc_per_tap;           // Cin_pad / 64
   int gdn_kblocks;          // Np / 64 when act is GDN/IGDN, else 0
   int act, out_f32;
   int stages;
   int ngroups, Cg;          // accumulator columns = ngroups x Cg
-  int sy, sx;               // output pixel = grid pixel * (sy,sx) + job offset + group offset
-  int gy[4], gx[4];
+  int sy, sx;               // output pixel = grid pixel * (sy,sx) + job offset (+ sub-pixel group offset)
+  int nbias;                // 1, or njobs when every job has its own bias vector
   long long out_sN, out_sY, out_sX;  // output strides in elements
   Job jobs[kMaxJobs];
   Tap taps[kMaxTaps];
@@ -228,7 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* norm_full = x2_ready + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 1);
   float* s_bias = reinterpret_cast<float*>(aux + 256);                 // [NP], 16-byte aligned
-  float* s_beta = s_bias + NP;                                         // [NP]
+  float* s_beta = s_bias + NP * P.nbias;                               // [NP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
@@ -245,16 +246,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (gdn) prefetch_tmap(&tmG);
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
-  for (int i = threadIdx.x; i < NP; i += kThreads) {
-    s_bias[i] = P.bias ? P.bias[i] : 0.f;
-    s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
-  }
+  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int kcpt = P.kc_per_tap;
   const int gk = gdn ? P.gdn_kblocks : 0;
 
   if (warp < 4) {
@@ -268,7 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const Job jb = P.jobs[tc.job];
         for (int tp = 0; tp < jb.ntaps; ++tp) {
           const Tap tap = P.taps[jb.tap_begin + tp];
-          for (int kc = 0; kc < kcpt; ++kc, ++kcount) {
+          for (int kc = 0; kc < tap.nkc; ++kc, ++kcount) {
             const uint32_t slot = kcount % stages, use = kcount / stages;
             mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
             const uint32_t a_dst = smem_base + slot * kStageBytes;
@@ -276,12 +274,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(&full_bar[slot], kStageBytes);
             if (P.mode == 1) {
               for (int j = 0; j < P.TH; ++j)
-                tma_load_5d(a_dst + j * P.TW * 128, &tmA, &full_bar[slot], kc * kBlockK, tap.px, tc.x0 + tap.dx,
-                            2 * (tc.y0 + j) + tap.dy, tc.n0);
+                tma_load_5d(a_dst + j * P.TW * 128, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tap.px,
+                            tc.x0 + tap.dx, 2 * (tc.y0 + j) + tap.dy, tc.n0);
             } else {
-              tma_load_4d(a_dst, &tmA, &full_bar[slot], kc * kBlockK, tc.x0 + tap.dx, tc.y0 + tap.dy, tc.n0);
+              tma_load_4d(a_dst, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tc.x0 + tap.dx, tc.y0 + tap.dy, tc.n0);
             }
-            tma_load_2d(b_dst, &tmW, &full_bar[slot], kc * kBlockK, (jb.tap_begin + tp) * NP);
+            tma_load_2d(b_dst, &tmW, &full_bar[slot], tap.b_c0 + kc * kBlockK, (jb.tap_begin + tp) * NP);
           }
         }
         for (int kb = 0; kb < gk; ++kb, ++kcount) {       // gamma K-blocks ride the same ring
@@ -298,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t kcount = 0, it = 0;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
         const TileCoord tc = decode_tile(P, t);
-        const int nkb = P.jobs[tc.job].ntaps * kcpt;
+        const int nkb = P.jobs[tc.job].nkb;
         mbar_wait(acc_empty, (it & 1) ^ 1);                 // epilogue has drained the accumulator
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb, ++kcount) {
@@ -349,17 +347,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(P, t);
       const Job jb = P.jobs[tc.job];
-      const int nkb = jb.ntaps * kcpt;
+      const int nkb = jb.nkb;
       const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
       const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B);
       const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
-                                 (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX;
+                                 (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
 
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
       kcount += nkb;
 
       // ---- pass 1: accumulator -> registers (+bias); release the accumulator ----
+      const float* sb = s_bias + (P.nbias > 1 ? tc.job * NP : 0);
       float xr[CPT];
       {
         uint32_t(&xu)[CPT] = reinterpret_cast<uint32_t(&)[CPT]>(xr);
@@ -371,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_arrive(acc_empty);               // accumulator may be overwritten by the next tile
 #pragma unroll
       for (int c = 0; c < CPT; c += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[col0 + c]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&sb[col0 + c]);
         xr[c] += b4.x; xr[c + 1] += b4.y; xr[c + 2] += b4.z; xr[c + 3] += b4.w;
       }
 
@@ -507,15 +506,20 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
 }
 
 struct Layer {          // everything derived from an LdicConvDesc
-  int mode, k, transposed, merged;
+  int mode, k, transposed;
   int Np, ngroups, Cg;
-  int njobs, ntaps_total;
+  int njobs, ntaps_total, nbias;
   Job jobs[kMaxJobs];
   Tap taps[kMaxTaps];
-  int tap_ky[kMaxTaps][4], tap_kx[kMaxTaps][4];   // per (tap, group): kernel cell or -1
-  int Wg, Hg;           // M-grid
-  int Ho, Wo, sy, sx;
-  int gy[4], gx[4];
+  signed char tap_ky[kMaxTaps][4], tap_kx[kMaxTaps][4];   // per (tap, group): kernel cell or -1
+  short tap_co_base[kMaxTaps];                            // first logical output channel of the tap's job
+  int cin_map, map_N, map_M;   // 0: ci = k - cin_offset;  1: context conv1 (y | h2 channel segments)
+  int Kw;                      // K extent (columns) of one packed weight block
+  long long vC, vW, vH, vN;    // activation view behind the TMA map (mode 1 splits vW into parity x vW/2)
+  int Wg, Hg, Bg;              // pixel grid the M tiles walk over
+  int oB, Ho, Wo, Cs;          // output tensor [oB, Ho, Wo, Cs]
+  long long out_sN, out_sY, out_sX;
+  int sy, sx;
 };
 
 // rows/cols of the 5x5 transposed kernels hit by output parity p at input offset d (-1,0,+1); -1 = none
@@ -533,10 +537,22 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
   if (!d) return fail(LDIC_EINVAL, "conv: null desc");
   if (d->B < 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0) return fail(LDIC_EINVAL, "conv: bad shape");
   if (d->Cin_pad % 64 || d->Cin_pad < d->Cin) return fail(LDIC_EINVAL, "conv: Cin_pad must be a multiple of 64 >= Cin");
+  if (d->Cout_pad < d->Cout || d->Cout_pad % 8) return fail(LDIC_EINVAL, "conv: Cout_pad must be >= Cout and a multiple of 8");
   for (int t = 0; t < kMaxTaps; ++t) for (int g = 0; g < 4; ++g) L->tap_ky[t][g] = L->tap_kx[t][g] = -1;
-  L->ngroups = 1; L->Cg = d->Cout_pad; L->sy = L->sx = 1; L->njobs = 1;
-  L->Wg = d->W; L->Hg = d->H; L->Ho = d->H; L->Wo = d->W;
-  auto add_tap = [&](int dx, int dy, int px) { Tap t{dx, dy, px}; L->taps[L->ntaps_total] = t; return L->ntaps_total++; };
+  L->ngroups = 1; L->Cg = d->Cout_pad; L->sy = L->sx = 1; L->njobs = 1; L->nbias = 1;
+  L->Wg = d->W; L->Hg = d->H; L->Bg = d->B; L->Ho = d->H; L->Wo = d->W; L->oB = d->B;
+  L->vC = d->Cin_pad; L->vW = d->W; L->vH = d->H; L->vN = d->B;
+  L->Kw = d->Cin_pad;
+  const int nkc_full = d->Cin_pad / 64;
+  auto add_tap = [&](int dx, int dy, int px, int a_c0 = 0, int b_c0 = 0, int nkc = -1) {
+    Tap t;
+    t.dx = (short)dx; t.dy = (short)dy; t.px = (short)px; t.nkc = (short)(nkc < 0 ? nkc_full : nkc);
+    t.a_c0 = a_c0; t.b_c0 = b_c0;
+    L->taps[L->ntaps_total] = t;
+    return L->ntaps_total++;
+  };
+  auto job = [](int ntaps, int tap_begin, int oy, int ox, int out_off) { Job j{ntaps, tap_begin, 0, oy, ox, out_off}; return j; };
+  bool custom_out = false;
   switch (d->kind) {
     case LDIC_CONV_S2_5x5_P12:
     case LDIC_CONV_S2_5x5_P2: {
@@ -549,7 +565,7 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
         int t = add_tap(off >> 1, ky - pad, off & 1);
         L->tap_ky[t][0] = ky; L->tap_kx[t][0] = kx;
       }
-      L->jobs[0] = Job{25, 0, 0, 0};
+      L->jobs[0] = job(25, 0, 0, 0, 0);
       break;
     }
     case LDIC_CONV_S1_3x3_P1: {
@@ -558,14 +574,14 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
         int t = add_tap(kx - 1, ky - 1, 0);
         L->tap_ky[t][0] = ky; L->tap_kx[t][0] = kx;
       }
-      L->jobs[0] = Job{9, 0, 0, 0};
+      L->jobs[0] = job(9, 0, 0, 0, 0);
       break;
     }
     case LDIC_CONV_1x1: {
       L->mode = 0; L->k = 1;
       int t = add_tap(0, 0, 0);
       L->tap_ky[t][0] = 0; L->tap_kx[t][0] = 0;
-      L->jobs[0] = Job{1, 0, 0, 0};
+      L->jobs[0] = job(1, 0, 0, 0, 0);
       break;
     }
     case LDIC_DECONV_GS_5x5:
@@ -574,7 +590,7 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
       L->Ho = 2 * d->H; L->Wo = 2 * d->W; L->sy = L->sx = 2; L->njobs = 4;
       auto kk = d->kind == LDIC_DECONV_GS_5x5 ? gs_k : hs_k;
       for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
-        Job jb{0, L->ntaps_total, py, px};
+        Job jb = job(0, L->ntaps_total, py, px, 0);
         for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
           int ky = kk(py, dy), kx = kk(px, dx);
           if (ky < 0 || kx < 0) continue;
@@ -592,14 +608,13 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
         int t = add_tap(dx, dy, 0);
         L->tap_ky[t][0] = 1 - dy; L->tap_kx[t][0] = 1 - dx;
       }
-      L->jobs[0] = Job{9, 0, 0, 0};
+      L->jobs[0] = job(9, 0, 0, 0, 0);
       break;
     }
     case LDIC_DECONV_GS_5x5_MERGED: {
-      L->mode = 0; L->k = 5; L->transposed = 1; L->merged = 1;
+      L->mode = 0; L->k = 5; L->transposed = 1;
       L->Ho = 2 * d->H; L->Wo = 2 * d->W; L->sy = L->sx = 2;
       L->ngroups = 4;
-      for (int g = 0; g < 4; ++g) { L->gy[g] = g >> 1; L->gx[g] = g & 1; }
       for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
         int t = add_tap(dx, dy, 0);
         for (int g = 0; g < 4; ++g) {
@@ -607,17 +622,96 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
           if (ky >= 0 && kx >= 0) { L->tap_ky[t][g] = ky; L->tap_kx[t][g] = kx; }
         }
       }
-      L->jobs[0] = Job{9, 0, 0, 0};
+      L->jobs[0] = job(9, 0, 0, 0, 0);
+      break;
+    }
+    // ---- context model (model/net.py:289-319), one latent position = one 4x4 patch -------------
+    case LDIC_CTX_CONV1: {
+      // x = [B,h,w, y_round(N) | h2(N)] ; output cell (i,j) of the patch at (y,x) is a 3x3 conv over
+      // patch cells (i+di, j+dj) in [0,3]^2 = image pixels (y+i+di-3, x+j+dj-2) (zero outside the
+      // image: BlockSample pads with zeros, model/net.py:238); the y sampler masks cells (3,2),(3,3)
+      // (:227-230) -> those taps contract over the h2 channels only.
+      const int N = d->aux0, M = d->aux1;
+      if (N <= 0 || N % 64 || M < 0 || M >= N || d->Cin != 2 * N - M || d->Cin_pad != 2 * N || d->Cout != N || d->Cout_pad != N)
+        return fail(LDIC_EINVAL, "ctx conv1: need aux0=N (multiple of 64), aux1=M, Cin=2N-M, Cin_pad=2N, Cout=Cout_pad=N");
+      L->mode = 0; L->k = 3; L->cin_map = 1; L->map_N = N; L->map_M = M; L->njobs = 16;
+      for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+        Job jb = job(0, L->ntaps_total, 0, 0, (i * 4 + j) * N);
+        for (int di = -1; di <= 1; ++di) for (int dj = -1; dj <= 1; ++dj) {
+          const int ci = i + di, cj = j + dj;
+          if (ci < 0 || ci > 3 || cj < 0 || cj > 3) continue;
+          const bool masked = (ci == 3 && cj >= 2);
+          int t = masked ? add_tap(cj - 2, ci - 3, 0, N, N, N / 64) : add_tap(cj - 2, ci - 3, 0, 0, 0, 2 * N / 64);
+          L->tap_ky[t][0] = di + 1; L->tap_kx[t][0] = dj + 1;
+          jb.ntaps++;
+        }
+        L->jobs[i * 4 + j] = jb;
+      }
+      L->oB = d->B * d->H * d->W; L->Ho = 4; L->Wo = 4;
+      L->out_sX = 16LL * N; L->out_sY = (long long)d->W * 16 * N; L->out_sN = (long long)d->H * d->W * 16 * N;
+      custom_out = true;
+      break;
+    }
+    case LDIC_CTX_CONV2:     // Conv2d(3, s2, p1) on the 4x4 patch -> 2x2          (model/net.py:297)
+    case LDIC_CTX_CONV3:     // Conv2d(3, s1, p1) on the 2x2 patch                 (model/net.py:299)
+    case LDIC_CTX_FC: {      // Linear over the (c,h,w)-flattened 2x2 patch         (model/net.py:302,311-312)
+      const int N = d->Cin;
+      const int cells_in = d->kind == LDIC_CTX_CONV2 ? 16 : 4;
+      const int side = d->kind == LDIC_CTX_CONV2 ? 4 : 2;
+      if (N % 64 || d->Cin_pad != N || d->H != side || d->W != side)
+        return fail(LDIC_EINVAL, "ctx conv2/conv3/fc: Cin=Cin_pad multiple of 64, H=W=%d", side);
+      L->mode = 0; L->k = d->kind == LDIC_CTX_FC ? 2 : 3;
+      L->vC = (long long)cells_in * N; L->vW = d->B; L->vH = 1; L->vN = 1;
+      L->Wg = d->B; L->Hg = 1; L->Bg = 1; L->Kw = N;
+      L->oB = d->B;
+      if (d->kind == LDIC_CTX_FC) {
+        L->njobs = 2; L->nbias = 2; L->Ho = 1; L->Wo = 2;
+        for (int g = 0; g < 2; ++g) {
+          Job jb = job(4, L->ntaps_total, 0, 0, g * d->Cout_pad);
+          for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+            int t = add_tap(0, 0, 0, (a * 2 + b) * N, 0, N / 64);
+            L->tap_ky[t][0] = a; L->tap_kx[t][0] = b; L->tap_co_base[t] = (short)(g * d->Cout);
+          }
+          L->jobs[g] = jb;
+        }
+        L->out_sX = 2LL * d->Cout_pad;
+      } else {
+        L->njobs = 4; L->Ho = 2; L->Wo = 2;
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+          Job jb = job(0, L->ntaps_total, 0, 0, (a * 2 + b) * d->Cout_pad);
+          for (int di = -1; di <= 1; ++di) for (int dj = -1; dj <= 1; ++dj) {
+            int ci, cj;
+            if (d->kind == LDIC_CTX_CONV2) { ci = 2 * a + di; cj = 2 * b + dj; }      // stride 2, pad 1
+            else { ci = a + di; cj = b + dj; }                                           // stride 1, pad 1
+            if (ci < 0 || ci >= side || cj < 0 || cj >= side) continue;
+            int t = add_tap(0, 0, 0, (ci * side + cj) * N, 0, N / 64);
+            L->tap_ky[t][0] = di + 1; L->tap_kx[t][0] = dj + 1;
+            jb.ntaps++;
+          }
+          L->jobs[a * 2 + b] = jb;
+        }
+        L->out_sX = 4LL * d->Cout_pad;
+      }
+      L->out_sY = L->out_sN = 0;
+      custom_out = true;
       break;
     }
     default:
       return fail(LDIC_EINVAL, "conv: unknown kind %d", d->kind);
   }
-  if (d->Cout_pad < d->Cout || d->Cout_pad % 8) return fail(LDIC_EINVAL, "conv: Cout_pad must be >= Cout and a multiple of 8");
   L->Np = L->ngroups * L->Cg;
+  L->Cs = L->Cg;
   if (L->Np != 64 && L->Np != 128 && L->Np != 192 && L->Np != 256)
     return fail(LDIC_EINVAL, "conv: accumulator width %d (groups %d x Cout_pad %d) must be 64/128/192/256", L->Np,
                 L->ngroups, L->Cg);
+  if (!custom_out) {
+    L->out_sX = L->Cg; L->out_sY = (long long)L->Wo * L->Cg; L->out_sN = (long long)L->Ho * L->Wo * L->Cg;
+  }
+  for (int j = 0; j < L->njobs; ++j) {
+    int n = 0;
+    for (int t = 0; t < L->jobs[j].ntaps; ++t) n += L->taps[L->jobs[j].tap_begin + t].nkc;
+    L->jobs[j].nkb = n;
+  }
   return LDIC_OK;
 }
 
@@ -639,7 +733,7 @@ void choose_tile(int mode, int Wg, int Hg, int B, int* TW, int* TH, int* TN) {
 template <int NP>
 int launch_conv(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
   const int stage_bytes = kATileBytes + NP * kBlockK * 2;
-  const size_t smem = (size_t)P.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * NP * sizeof(float);
+  const size_t smem = (size_t)P.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + (size_t)(P.nbias + 1) * NP * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     LDIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -652,32 +746,37 @@ int launch_conv(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g
 
 // generic weight packer: Wp[t][n][k]
 struct PackTable {
-  int ntaps, Np, Cg, ngroups, Cin, Cout, Cin_pad, cin_offset, k, transposed;
+  int ntaps, Np, Cg, ngroups, Cin, Cout, Kw, cin_offset, k, transposed, cin_map, map_N, map_M, nbias;
   signed char ky[kMaxTaps][4], kx[kMaxTaps][4];
+  short co_base[kMaxTaps];
 };
 __global__ void k_pack_weights(const float* __restrict__ w, const float* __restrict__ bias, PackTable T,
                                __nv_bfloat16* __restrict__ wp, float* __restrict__ bp) {
-  const long long total = (long long)T.ntaps * T.Np * T.Cin_pad;
+  const long long total = (long long)T.ntaps * T.Np * T.Kw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int kc = (int)(i % T.Cin_pad);
-    long long r = i / T.Cin_pad;
+    int kc = (int)(i % T.Kw);
+    long long r = i / T.Kw;
     int n = (int)(r % T.Np);
     int t = (int)(r / T.Np);
     int g = n / T.Cg, co = n - g * T.Cg;
-    int ci = kc - T.cin_offset;
+    int ci;
+    if (T.cin_map == 1) ci = kc < T.map_N ? (kc >= T.map_M ? kc - T.map_M : -1) : (T.map_N - T.map_M) + (kc - T.map_N);
+    else ci = kc - T.cin_offset;
     float v = 0.f;
     int ky = T.ky[t][g], kx = T.kx[t][g];
     if (ky >= 0 && co < T.Cout && ci >= 0 && ci < T.Cin) {
-      long long idx = T.transposed ? ((((long long)ci * T.Cout + co) * T.k + ky) * T.k + kx)
-                                   : ((((long long)co * T.Cin + ci) * T.k + ky) * T.k + kx);
+      const int cot = co + T.co_base[t];
+      const int Ctot = T.Cout * T.nbias;     // total logical output channels of the weight tensor
+      long long idx = T.transposed ? ((((long long)ci * Ctot + cot) * T.k + ky) * T.k + kx)
+                                   : ((((long long)cot * T.Cin + ci) * T.k + ky) * T.k + kx);
       v = w[idx];
     }
     wp[i] = __float2bfloat16_rn(v);
   }
   if (bp) {
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < T.Np; n += gridDim.x * blockDim.x) {
-      int co = n % T.Cg;
-      bp[n] = (bias && co < T.Cout) ? bias[co] : 0.f;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < T.Np * T.nbias; n += gridDim.x * blockDim.x) {
+      int jb = n / T.Np, co = (n % T.Np) % T.Cg;
+      bp[n] = (bias && co < T.Cout) ? bias[jb * T.Cout + co] : 0.f;
     }
   }
 }
@@ -689,15 +788,27 @@ extern "C" int ldic_conv_n_cols(const LdicConvDesc* d) {
   if (build_layer(d, &L) != LDIC_OK) return -1;
   return L.Np;
 }
+extern "C" int ldic_conv_bias_elems(const LdicConvDesc* d) {
+  Layer L;
+  if (build_layer(d, &L) != LDIC_OK) return -1;
+  return L.Np * L.nbias;
+}
 extern "C" long long ldic_conv_weight_elems(const LdicConvDesc* d) {
   Layer L;
   if (build_layer(d, &L) != LDIC_OK) return -1;
-  return (long long)L.ntaps_total * L.Np * d->Cin_pad;
+  return (long long)L.ntaps_total * L.Np * L.Kw;
 }
 extern "C" void ldic_conv_out_shape(const LdicConvDesc* d, int* Ho, int* Wo) {
   Layer L;
   if (build_layer(d, &L) != LDIC_OK) { *Ho = *Wo = -1; return; }
   *Ho = L.Ho; *Wo = L.Wo;
+}
+extern "C" int ldic_conv_out_dims(const LdicConvDesc* d, int* dims4) {
+  Layer L;
+  int rc = build_layer(d, &L);
+  if (rc) return rc;
+  dims4[0] = L.oB; dims4[1] = L.Ho; dims4[2] = L.Wo; dims4[3] = L.Cs;
+  return LDIC_OK;
 }
 
 extern "C" int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, const float* bias, int cin_offset,
@@ -705,12 +816,18 @@ extern "C" int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, con
   Layer L;
   int rc = build_layer(d, &L);
   if (rc) return rc;
-  if (cin_offset < 0 || cin_offset + d->Cin > d->Cin_pad) return fail(LDIC_EINVAL, "pack: cin_offset out of range");
+  if (cin_offset < 0 || (L.cin_map == 0 && L.Kw == d->Cin_pad && cin_offset + d->Cin > d->Cin_pad))
+    return fail(LDIC_EINVAL, "pack: cin_offset out of range");
   PackTable T;
+  memset(&T, 0, sizeof(T));
   T.ntaps = L.ntaps_total; T.Np = L.Np; T.Cg = L.Cg; T.ngroups = L.ngroups; T.Cin = d->Cin; T.Cout = d->Cout;
-  T.Cin_pad = d->Cin_pad; T.cin_offset = cin_offset; T.k = L.k; T.transposed = L.transposed;
-  for (int t = 0; t < kMaxTaps; ++t) for (int g = 0; g < 4; ++g) { T.ky[t][g] = (signed char)L.tap_ky[t][g]; T.kx[t][g] = (signed char)L.tap_kx[t][g]; }
-  long long total = (long long)T.ntaps * T.Np * T.Cin_pad;
+  T.Kw = L.Kw; T.cin_offset = cin_offset; T.k = L.k; T.transposed = L.transposed;
+  T.cin_map = L.cin_map; T.map_N = L.map_N; T.map_M = L.map_M; T.nbias = L.nbias;
+  for (int t = 0; t < kMaxTaps; ++t) {
+    T.co_base[t] = L.tap_co_base[t];
+    for (int g = 0; g < 4; ++g) { T.ky[t][g] = L.tap_ky[t][g]; T.kx[t][g] = L.tap_kx[t][g]; }
+  }
+  long long total = (long long)T.ntaps * T.Np * T.Kw;
   int grid = (int)((total + 255) / 256 > kNumSMs * 8 ? kNumSMs * 8 : (total + 255) / 256);
   k_pack_weights<<<grid, 256, 0, (cudaStream_t)stream>>>(w, bias, T, (__nv_bfloat16*)w_packed, bias_packed);
   return check_launch("k_pack_weights");
@@ -725,53 +842,52 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   if (!x || !w_packed || !y) return fail(LDIC_EINVAL, "conv: null tensor");
   const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
   if (gdn && (!gamma_bf16 || !beta_tiled)) return fail(LDIC_EINVAL, "conv: GDN epilogue needs gamma_bf16 and beta_tiled");
+  if (gdn && L.njobs > 4) return fail(LDIC_EINVAL, "conv: GDN epilogue is not available for the context layers");
   if ((((uintptr_t)x) & 15) || (((uintptr_t)w_packed) & 15) || (((uintptr_t)y) & 15)) return fail(LDIC_EINVAL, "conv: tensors must be 16-byte aligned");
 
   ConvParams P;
   memset(&P, 0, sizeof(P));
   P.mode = L.mode;
-  choose_tile(L.mode, L.Wg, L.Hg, d->B, &P.TW, &P.TH, &P.TN);
+  choose_tile(L.mode, L.Wg, L.Hg, L.Bg, &P.TW, &P.TH, &P.TN);
   auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
   P.tw_shift = ilog2(P.TW); P.th_shift = ilog2(P.TH); P.cg_shift = ilog2(L.Cg);
   if (L.ngroups > 1 && ((1 << P.cg_shift) != L.Cg || L.Cg < 8)) return fail(LDIC_EINVAL, "conv: merged deconv needs a power-of-two Cout_pad >= 8");
   P.tiles_x = (L.Wg + P.TW - 1) / P.TW;
   P.tiles_y = (L.Hg + P.TH - 1) / P.TH;
-  P.tiles_n = (d->B + P.TN - 1) / P.TN;
+  P.tiles_n = (L.Bg + P.TN - 1) / P.TN;
   P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
   P.njobs = L.njobs;
   P.total_tiles = P.tiles_per_job * P.njobs;
-  P.Wg = L.Wg; P.Hg = L.Hg; P.B = d->B;
-  P.kc_per_tap = d->Cin_pad / 64;
+  P.Wg = L.Wg; P.Hg = L.Hg; P.B = L.Bg;
   P.gdn_kblocks = gdn ? L.Np / 64 : 0;
   P.act = d->act; P.out_f32 = d->out_f32;
-  P.ngroups = L.ngroups; P.Cg = L.Cg; P.sy = L.sy; P.sx = L.sx;
-  for (int g = 0; g < 4; ++g) { P.gy[g] = L.gy[g]; P.gx[g] = L.gx[g]; }
-  P.out_sX = L.Cg; P.out_sY = (long long)L.Wo * L.Cg; P.out_sN = (long long)L.Ho * L.Wo * L.Cg;
+  P.ngroups = L.ngroups; P.Cg = L.Cg; P.sy = L.sy; P.sx = L.sx; P.nbias = L.nbias;
+  P.out_sX = L.out_sX; P.out_sY = L.out_sY; P.out_sN = L.out_sN;
   for (int j = 0; j < kMaxJobs; ++j) P.jobs[j] = L.jobs[j];
   for (int t = 0; t < kMaxTaps; ++t) P.taps[t] = L.taps[t];
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
   const int stage_bytes = kATileBytes + L.Np * kBlockK * 2;
-  int stages = (227 * 1024 - 2048 - 2 * L.Np * 4) / stage_bytes;
+  int stages = (227 * 1024 - 2048 - (L.nbias + 1) * L.Np * 4) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   P.stages = stages;
   if (gdn && stages < P.gdn_kblocks + 1) return fail(LDIC_EINVAL, "conv: not enough pipeline stages for the GDN epilogue");
 
   CUtensorMap tmA, tmW, tmG;
-  const cuuint64_t C = (cuuint64_t)d->Cin_pad;
+  const cuuint64_t C = (cuuint64_t)L.vC;
   if (L.mode == 1) {
-    cuuint64_t dims[5] = {C, 2, (cuuint64_t)d->W / 2, (cuuint64_t)d->H, (cuuint64_t)d->B};
-    cuuint64_t str[4] = {C * 2, 2 * C * 2, (cuuint64_t)d->W * C * 2, (cuuint64_t)d->H * d->W * C * 2};
+    cuuint64_t dims[5] = {C, 2, (cuuint64_t)L.vW / 2, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
+    cuuint64_t str[4] = {C * 2, 2 * C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
     cuuint32_t box[5] = {64, 1, (cuuint32_t)P.TW, 1, 1};
     if ((rc = encode_map(&tmA, x, 5, dims, str, box))) return rc;
   } else {
-    cuuint64_t dims[4] = {C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
-    cuuint64_t str[3] = {C * 2, (cuuint64_t)d->W * C * 2, (cuuint64_t)d->H * d->W * C * 2};
+    cuuint64_t dims[4] = {C, (cuuint64_t)L.vW, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
+    cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
     if ((rc = encode_map(&tmA, x, 4, dims, str, box))) return rc;
   }
   {
-    cuuint64_t dims[2] = {C, (cuuint64_t)L.ntaps_total * L.Np};
-    cuuint64_t str[1] = {C * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.ntaps_total * L.Np};
+    cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
     if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
   }

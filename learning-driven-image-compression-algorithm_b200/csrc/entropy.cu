@@ -616,3 +616,31 @@ extern "C" int ldic_im2col_5x5s2(const float* x, void* a, int B, int Cin, int H,
   k_im2col_5x5s2<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)a, Cin, H, W, Ho, Wo, Kp, total);
   return check_launch("k_im2col_5x5s2");
 }
+
+// Context-model input image: x[p][0:N] = round(y) (bf16, already rounded), x[p][N:2N] = bf16(h2).
+// (model/net.py:307-309 concatenates the sampled y and h patches; here the concat happens once on
+// the latent images and the patches are gathered by TMA inside the first context conv.)
+__global__ void k_ctx_pack_input(const uint4* __restrict__ yr, const float4* __restrict__ h2, uint4* __restrict__ x,
+                                 long long P, int N8) {
+  const long long total = P * N8 * 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / (2 * N8);
+    const int c8 = (int)(i - p * 2 * N8);
+    uint4 o;
+    if (c8 < N8) {
+      o = __ldg(yr + p * N8 + c8);
+    } else {
+      const float4 a = __ldg(h2 + (p * N8 + (c8 - N8)) * 2), b = __ldg(h2 + (p * N8 + (c8 - N8)) * 2 + 1);
+      o = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    x[i] = o;
+  }
+}
+extern "C" int ldic_ctx_pack_input(const void* y_round_bf16, const float* h2, void* x, long long P, int N, void* stream) {
+  if (P <= 0) return LDIC_OK;
+  if (N <= 0 || N % 8) return fail(LDIC_EINVAL, "ctx_pack_input: N must be a multiple of 8");
+  long long total = P * (N / 8) * 2;
+  int grid = (int)((total + 255) / 256 > kNumSMs * 16 ? kNumSMs * 16 : (total + 255) / 256);
+  k_ctx_pack_input<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)y_round_bf16, (const float4*)h2, (uint4*)x, P, N / 8);
+  return check_launch("k_ctx_pack_input");
+}

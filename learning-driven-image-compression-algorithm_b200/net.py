@@ -9,8 +9,10 @@ scope of this path).
 
 Kernel coverage: g_a + GDN (a1,a2,a3), h_a (a4), h_s (a5), rounding
 (a6), GaussianModel likelihoods (a7), bpp reduction (a9), g_s + IGDN (a10),
-batch_conv + MSE/PSNR (a11) run on libldic_b200.  The context / syntax
-branches run as stock torch ops on the GPU.
+batch_conv + MSE/PSNR (a11) and the context model PredictionModel_Context
+(TMA patch gather + 3 convs + fc on the tcgen05 kernel) run on
+libldic_b200.  The tiny syntax branch (Syntax_Model, PredictionModel_Syntax,
+conv_generator: < 0.1 % of the FLOPs) runs as stock torch ops on the GPU.
 """
 from __future__ import annotations
 
@@ -109,8 +111,41 @@ class PredictionModel_Context(nn.Module):
             t[:, :, 3, 2:] = 0
         return t
 
+    # -- tensor-core path ----------------------------------------------------------
+    _plan = None
+    _plan_key = None
+
+    def plan(self, N: int, M: int):
+        from . import _lib
+        key = tuple((p._version, p.data_ptr()) for p in self.parameters()) + (N, M)
+        if self._plan is None or self._plan_key != key:
+            t = self.transform
+            with torch.no_grad():
+                self._plan = [
+                    ops.ConvTC(_lib.LDIC_CTX_CONV1, t[0].weight.detach(), t[0].bias.detach(), act=_lib.ACT_LEAKY02, aux=(N, M)),
+                    ops.ConvTC(_lib.LDIC_CTX_CONV2, t[2].weight.detach(), t[2].bias.detach(), act=_lib.ACT_LEAKY02),
+                    ops.ConvTC(_lib.LDIC_CTX_CONV3, t[4].weight.detach(), t[4].bias.detach(), act=_lib.ACT_LEAKY02),
+                    ops.ConvTC(_lib.LDIC_CTX_FC, self.fc.weight.detach(), self.fc.bias.detach(), out_f32=True),
+                ]
+            self._plan_key = key
+        return self._plan
+
+    def raw_tc(self, y_round_bf16: torch.Tensor, h2: torch.Tensor, M: int) -> torch.Tensor:
+        """(B,h,w,N) bf16 rounded latent (all N channels; the first M are the syntax channels and
+        get zero weights) + (B,h,w,N) fp32 h_s output -> (B*h*w, 1, 2, Cp) fp32: [..,0,:c] = mu,
+        [..,1,:c] = log sigma.  The 4x4 patches of BlockSample (model/net.py:219-242) are gathered by
+        TMA inside the first conv instead of being materialised."""
+        N = h2.shape[-1]
+        L = self.plan(N, M)
+        x = ops.ctx_pack_input(y_round_bf16, h2)
+        t = L[0](x)            # (P,4,4,N)
+        t = L[1](t)            # (P,2,2,N)
+        t = L[2](t)            # (P,2,2,N)
+        return L[3](t)         # (P,1,2,Cp) fp32
+
     def raw(self, y_rounded, h_tilde):
-        """fc output (b*h*w, 2c): [:, :c] = mu, [:, c:] = log sigma, rows in (b,h,w) order."""
+        """torch-op formulation (unfold gather + cuDNN), kept as the GPU cross-check of raw_tc.
+        fc output (b*h*w, 2c): [:, :c] = mu, [:, c:] = log sigma, rows in (b,h,w) order."""
         b, c, h, w = y_rounded.shape
         outs = []
         rows_per_img = h * w
@@ -123,10 +158,17 @@ class PredictionModel_Context(nn.Module):
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def forward(self, y_rounded, h_tilde, y_sampler=None, h_sampler=None):
+        """Module surface of the reference: (B,c,h,w) rounded content latent + (B,N,h,w) h_s output
+        -> (mu, sigma) as NCHW views of (b,h,w,c) storage (model/net.py:313-319)."""
         b, c, h, w = y_rounded.shape
-        t = self.raw(y_rounded, h_tilde)
-        mu = t[:, :c].view(b, h, w, c).permute(0, 3, 1, 2)
-        sigma = torch.exp(t[:, c:]).contiguous().view(b, h, w, c).permute(0, 3, 1, 2)
+        N = h_tilde.shape[1]
+        M = N - c
+        y_full = torch.zeros(b, h, w, N, dtype=torch.bfloat16, device=y_rounded.device)
+        y_full[..., M:] = y_rounded.permute(0, 2, 3, 1)
+        h2 = h_tilde.permute(0, 2, 3, 1).contiguous().float()
+        t = self.raw_tc(y_full, h2, M)                       # (P,1,2,Cp)
+        mu = t[:, 0, 0, :c].view(b, h, w, c).permute(0, 3, 1, 2)
+        sigma = torch.exp(t[:, 0, 1, :c]).contiguous().view(b, h, w, c).permute(0, 3, 1, 2)
         return mu, sigma
 
 
@@ -159,6 +201,7 @@ class Net(nn.Module):
         self.prediction_model = PredictionModel_Context(in_dim=2 * N - M, dim=N, outdim=(N - M) * 2)
         self.prediction_model_syntax = PredictionModel_Syntax(in_dim=N, dim=M, outdim=M * 2)
         self.context_tf32 = True
+        self.context_on_torch = False     # True: run the context transform with torch ops (cross-check in tests)
 
     # -- checkpoint compatibility ---------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -225,15 +268,20 @@ class Net(nn.Module):
             y_content_rounded = torch.round(y_nchw[:, M:])                          # :741
             syn_first, syn_second = self.prediction_model_syntax(z3_syntax_rounded, h2_nchw)   # :789 (mu, sigma) bound swapped
             conv_w = self.conv_weights_gen(z3_syntax_rounded)                       # :805
-            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(self.context_tf32)
-            ctx = self.prediction_model.raw(y_content_rounded, h2_nchw)             # :784  (P, 2(N-M))
+            if self.context_on_torch:      # cross-check path only (tests); the product path is raw_tc
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(self.context_tf32)
+                ctx = self.prediction_model.raw(y_content_rounded, h2_nchw)         # :784  (P, 2(N-M))
+                ctx_rs, ctx_sig_off = ctx.shape[1], N - M
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 
         Cc = N - M
+        if not self.context_on_torch:
+            ctx = self.prediction_model.raw_tc(y_round_bf16, h2, M)                 # :784  (P,1,2,Cp): mu | log sigma
+            ctx_rs, ctx_sig_off = 2 * ctx.shape[-1], ctx.shape[-1]
         lik_y = torch.empty(B, h, w, Cc, dtype=torch.float32, device=x.device) if want_likelihoods else None
-        sum_y = ops.likelihood_rows(y, P, Cc, v_rs=N, v_off=M, mu=ctx, mu_mode=2, mu_rs=2 * Cc, mu_off=0,      # :786
-                                    sigma=ctx, sigma_mode=2, sigma_rs=2 * Cc, sigma_off=Cc, sigma_is_log=True,
+        sum_y = ops.likelihood_rows(y, P, Cc, v_rs=N, v_off=M, mu=ctx, mu_mode=2, mu_rs=ctx_rs, mu_off=0,      # :786
+                                    sigma=ctx, sigma_mode=2, sigma_rs=ctx_rs, sigma_off=ctx_sig_off, sigma_is_log=True,
                                     quant=ops.QUANT_ROUND, lik_bound=self.entropy_bottleneck_z3.likelihood_bound,
                                     lik=lik_y)
         # syntax stream: "sigma" <- first return (mu), "mu" <- second (sigma): reference quirk H2

@@ -298,13 +298,26 @@ class ConvTC:
 
     def __init__(self, kind: int, weight: torch.Tensor, bias: Optional[torch.Tensor], *, act: int = _lib.ACT_NONE,
                  out_f32: bool = False, cin_pad: Optional[int] = None, cin_offset: int = 0,
-                 cout_pad: Optional[int] = None, gdn: Optional[tuple] = None):
+                 cout_pad: Optional[int] = None, gdn: Optional[tuple] = None, aux=(0, 0)):
         w = _req(weight, torch.float32, "weight").contiguous()
         transposed = kind in (_lib.LDIC_DECONV_GS_5x5, _lib.LDIC_DECONV_HS_5x5, _lib.LDIC_DECONV_S1_3x3,
                               _lib.LDIC_DECONV_GS_5x5_MERGED)
+        self.aux = tuple(aux)
+        probe_hw = (16, 16)
         if kind == _lib.LDIC_CONV_1x1:
             w = w.reshape(w.shape[0], -1).contiguous()
             cout, cin = w.shape
+        elif kind == _lib.LDIC_CTX_CONV1:            # (N, 2N-M, 3, 3); aux = (N, M)
+            cout, cin = w.shape[0], w.shape[1]
+            cin_pad = 2 * self.aux[0]
+        elif kind in (_lib.LDIC_CTX_CONV2, _lib.LDIC_CTX_CONV3):
+            cout, cin = w.shape[0], w.shape[1]
+            probe_hw = (4, 4) if kind == _lib.LDIC_CTX_CONV2 else (2, 2)
+        elif kind == _lib.LDIC_CTX_FC:               # Linear(4N, 2*Cout): rows [mu | log sigma], cols (c,h,w)
+            cin = w.shape[1] // 4
+            cout = w.shape[0] // 2
+            cout_pad = cout_pad or _pad64(cout)
+            probe_hw = (2, 2)
         elif transposed:
             cin, cout = w.shape[0], w.shape[1]
         else:
@@ -314,14 +327,16 @@ class ConvTC:
         self.cin_pad = cin_pad or _pad64(cin + cin_offset)
         self.cout_pad = cout_pad or cout
         self.device = w.device
-        d = self._desc(1, 16, 16)
+        self._probe_hw = probe_hw
+        d = self._desc(1, *probe_hw)
         L = _L()
         self.np_cols = L.ldic_conv_n_cols(C.byref(d))
         n = L.ldic_conv_weight_elems(C.byref(d))
-        if n < 0 or self.np_cols < 0:
+        nb = L.ldic_conv_bias_elems(C.byref(d))
+        if n < 0 or self.np_cols < 0 or nb < 0:
             check(-1, "ldic_conv_weight_elems")
         self.w_packed = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-        self.bias_packed = torch.empty(self.np_cols, dtype=torch.float32, device=w.device)
+        self.bias_packed = torch.empty(nb, dtype=torch.float32, device=w.device)
         b = None if bias is None else _req(bias, torch.float32, "bias").contiguous()
         check(L.ldic_conv_pack_weights(C.byref(d), _ptr(w), _ptr(b), int(cin_offset), _ptr(self.w_packed),
                                        _ptr(self.bias_packed), _stream()), "ldic_conv_pack_weights")
@@ -335,25 +350,39 @@ class ConvTC:
                                                                  tc_np=self.np_cols)
 
     def _desc(self, B, H, W) -> ConvDesc:
-        return ConvDesc(self.kind, B, H, W, self.cin, self.cout, self.cin_pad, self.cout_pad, self.act, int(self.out_f32))
+        return ConvDesc(self.kind, B, H, W, self.cin, self.cout, self.cin_pad, self.cout_pad, self.act,
+                        int(self.out_f32), int(self.aux[0]), int(self.aux[1]))
+
+    def out_dims(self, B, H, W):
+        d = self._desc(B, H, W)
+        dims = (C.c_int * 4)()
+        check(_L().ldic_conv_out_dims(C.byref(d), dims), "ldic_conv_out_dims")
+        return tuple(dims)
 
     def out_hw(self, H, W):
-        d = self._desc(1, H, W)
-        ho, wo = C.c_int(), C.c_int()
-        _L().ldic_conv_out_shape(C.byref(d), C.byref(ho), C.byref(wo))
-        return ho.value, wo.value
+        return self.out_dims(1, H, W)[1:3]
 
     def flops(self, B: int, H: int, W: int) -> float:
         """Algorithmic FLOPs (2 x MACs on logical channels, no zero-insertion / padding waste):
         conv: k*k*Cin*Cout per OUTPUT pixel; transposed conv: k*k*Cin*Cout per INPUT pixel;
-        GDN/IGDN: C*C per output pixel."""
+        GDN/IGDN: C*C per output pixel; context layers: the taps that fall inside the patch."""
+        K = _lib
+        if self.kind == K.LDIC_CTX_CONV1:      # 100 in-patch taps per position, 10 of them without the masked y part
+            N, M = self.aux
+            return 2.0 * B * H * W * self.cout * (100 * self.cin - 10 * (N - M))
+        if self.kind == K.LDIC_CTX_CONV2:
+            return 2.0 * B * 25 * self.cin * self.cout
+        if self.kind == K.LDIC_CTX_CONV3:
+            return 2.0 * B * 16 * self.cin * self.cout
+        if self.kind == K.LDIC_CTX_FC:
+            return 2.0 * B * 4 * self.cin * 2 * self.cout
         ho, wo = self.out_hw(H, W)
-        k = {_lib.LDIC_CONV_1x1: 1, _lib.LDIC_CONV_S1_3x3_P1: 3, _lib.LDIC_DECONV_S1_3x3: 3}.get(self.kind, 5)
-        transposed = self.kind in (_lib.LDIC_DECONV_GS_5x5, _lib.LDIC_DECONV_HS_5x5, _lib.LDIC_DECONV_S1_3x3,
-                                   _lib.LDIC_DECONV_GS_5x5_MERGED)
+        k = {K.LDIC_CONV_1x1: 1, K.LDIC_CONV_S1_3x3_P1: 3, K.LDIC_DECONV_S1_3x3: 3}.get(self.kind, 5)
+        transposed = self.kind in (K.LDIC_DECONV_GS_5x5, K.LDIC_DECONV_HS_5x5, K.LDIC_DECONV_S1_3x3,
+                                   K.LDIC_DECONV_GS_5x5_MERGED)
         pix = B * (H * W if transposed else ho * wo)
         f = 2.0 * k * k * self.cin * self.cout * pix
-        if self.act in (_lib.ACT_GDN, _lib.ACT_IGDN):
+        if self.act in (K.ACT_GDN, K.ACT_IGDN):
             f += 2.0 * self.cout * self.cout * B * ho * wo
         return f
 
@@ -362,9 +391,8 @@ class ConvTC:
         if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
             raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
         B, H, W, _ = x.shape
-        ho, wo = self.out_hw(H, W)
         if out is None:
-            out = torch.empty(B, ho, wo, self.cout_pad, dtype=torch.float32 if self.out_f32 else torch.bfloat16,
+            out = torch.empty(self.out_dims(B, H, W), dtype=torch.float32 if self.out_f32 else torch.bfloat16,
                               device=x.device)
         d = self._desc(B, H, W)
         prof = PROFILE
@@ -378,6 +406,18 @@ class ConvTC:
             e1.record()
             prof.append((self, (B, H, W), e0, e1))
         return out
+
+
+def ctx_pack_input(y_round_bf16: torch.Tensor, h2: torch.Tensor) -> torch.Tensor:
+    """[B,h,w,N] bf16 (rounded latent) and [B,h,w,N] fp32 (h_s output) -> [B,h,w,2N] bf16."""
+    _req(y_round_bf16, torch.bfloat16, "y_round")
+    _req(h2, torch.float32, "h2")
+    if y_round_bf16.shape != h2.shape or not y_round_bf16.is_contiguous() or not h2.is_contiguous():
+        raise LdicError("ctx_pack_input: y_round and h2 must be contiguous NHWC tensors of the same shape")
+    B, h, w, N = h2.shape
+    x = torch.empty(B, h, w, 2 * N, dtype=torch.bfloat16, device=h2.device)
+    check(_L().ldic_ctx_pack_input(_ptr(y_round_bf16), _ptr(h2), _ptr(x), B * h * w, N, _stream()), "ldic_ctx_pack_input")
+    return x
 
 
 def conv_reference_f32(kind: int, x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
@@ -394,8 +434,8 @@ def conv_reference_f32(kind: int, x_nhwc: torch.Tensor, weight: torch.Tensor, bi
     else:
         cout, cin = w.shape[0], w.shape[1]
     B, H, W, _ = x.shape
-    dq = ConvDesc(kind, B, H, W, cin, 8, _pad64(cin), 64, 0, 1)    # shape query only
-    d = ConvDesc(kind, B, H, W, cin, cout, _pad64(cin), 64, 0, 1)
+    dq = ConvDesc(kind, B, H, W, cin, 8, _pad64(cin), 64, 0, 1, 0, 0)    # shape query only
+    d = ConvDesc(kind, B, H, W, cin, cout, _pad64(cin), 64, 0, 1, 0, 0)
     ho, wo = C.c_int(), C.c_int()
     _L().ldic_conv_out_shape(C.byref(dq), C.byref(ho), C.byref(wo))
     y = torch.empty(B, ho.value, wo.value, cout, dtype=torch.float32, device=x.device)

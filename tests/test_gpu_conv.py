@@ -177,3 +177,26 @@ def test_transform_modules_vs_oracle(ldic):
         h_ref = rp.h_synthesis_transform(sd, torch.round(z_ref))
         hh = net.hs_model(torch.round(z_ref).cuda()).cpu()
         assert hh.shape == h_ref.shape and rel(hh, h_ref) < 1e-2
+
+
+def test_context_model_tc_vs_oracle(ldic):
+    """PredictionModel_Context on the tcgen05 kernels (TMA patch gather) against the
+    oracle's BlockSample + convs + fc (model/net.py:219-242, 289-319)."""
+    sd = dw.make_state_dict(0)
+    net = ldic.Net((1, 64, 64, 3), (1, 64, 64, 3), False, False).cuda()
+    net.load_state_dict(sd, strict=True)
+    B, h, w, N, M = 2, 6, 9, 192, 16
+    yr = torch.round(rnd((B, N - M, h, w), 31, 2.0))
+    h2 = bf(rnd((B, N, h, w), 32, 0.8))                      # bf16-exact input isolates the kernel error
+    with torch.no_grad():
+        mu_ref, sg_ref = rp.prediction_context(sd, yr, h2)
+        mu, sg = net.prediction_model(yr.cuda(), h2.cuda())
+    assert mu.shape == mu_ref.shape and sg.shape == sg_ref.shape
+    rel = lambda a, b: ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+    assert rel(mu.cpu(), mu_ref) < 1e-2, rel(mu.cpu(), mu_ref)
+    assert rel(torch.log(sg.cpu()), torch.log(sg_ref)) < 1e-2
+    # weights rounded to bf16 on the oracle side as well: only summation order / bf16 activations remain
+    sdb = {k: (bf(v) if k.startswith("prediction_model.") and k.endswith("weight") else v) for k, v in sd.items()}
+    with torch.no_grad():
+        mu_b, _ = rp.prediction_context(sdb, yr, h2)
+    assert rel(mu.cpu(), mu_b) < 6e-3
