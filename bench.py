@@ -211,9 +211,9 @@ def run_ours(args):
         res = torch.cat([bpp_i.reshape(1), psnr_i.reshape(1), v_mse]).cpu()   # D2H read of the step's result
     e1.record()
     sync_all()
+    wall_ms = (time.perf_counter() - w0) * 1e3
     clocks = sampler.stop()
     e2e_ms = e0.elapsed_time(e1)
-    wall_ms = (time.perf_counter() - w0) * 1e3
     tt = torch.tensor([max(e2e_ms, 0.0)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

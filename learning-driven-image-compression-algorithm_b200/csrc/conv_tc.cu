@@ -177,6 +177,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+template <typename T>
+__device__ __forceinline__ void st_global_v8(void* p, const T* v) {   // 32-byte store, p 32-byte aligned
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]),
+               "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
+
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -425,19 +433,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 
       if (valid) {
+        // 256-bit stores: every lane writes whole 32-byte sectors of its own pixel row
         if (P.ngroups == 1) {
           // this thread's CPT columns are contiguous channels of one output pixel
           if (P.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix_base + col0);
+            float* dst = reinterpret_cast<float*>(P.out) + pix_base + col0;
 #pragma unroll
-            for (int j = 0; j < CPT / 4; ++j) dst[j] = make_float4(xr[4 * j], xr[4 * j + 1], xr[4 * j + 2], xr[4 * j + 3]);
+            for (int j = 0; j < CPT / 8; ++j) st_global_v8(dst + 8 * j, &xr[8 * j]);
           } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix_base + col0);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + pix_base + col0;
 #pragma unroll
-            for (int j = 0; j < CPT / 8; ++j) {
-              const float* x8 = &xr[j * 8];
-              dst[j] = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
-                                  pack_bf16x2(x8[6], x8[7]));
+            for (int j = 0; j < CPT / 16; ++j) {
+              const float* x16 = &xr[j * 16];
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(x16[2 * e], x16[2 * e + 1]);
+              st_global_v8(dst + 16 * j, pk);
             }
           }
         } else {
@@ -449,9 +460,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long off = pix_base + (long long)(g >> 1) * P.out_sY + (long long)(g & 1) * P.out_sX + cc;
             const float* x8 = &xr[j * 8];
             if (P.out_f32) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + off);
-              dst[0] = make_float4(x8[0], x8[1], x8[2], x8[3]);
-              dst[1] = make_float4(x8[4], x8[5], x8[6], x8[7]);
+              st_global_v8(reinterpret_cast<float*>(P.out) + off, x8);
             } else {
               uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off);
               *dst = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
@@ -843,7 +852,8 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
   if (gdn && (!gamma_bf16 || !beta_tiled)) return fail(LDIC_EINVAL, "conv: GDN epilogue needs gamma_bf16 and beta_tiled");
   if (gdn && L.njobs > 4) return fail(LDIC_EINVAL, "conv: GDN epilogue is not available for the context layers");
-  if ((((uintptr_t)x) & 15) || (((uintptr_t)w_packed) & 15) || (((uintptr_t)y) & 15)) return fail(LDIC_EINVAL, "conv: tensors must be 16-byte aligned");
+  if ((((uintptr_t)x) & 15) || (((uintptr_t)w_packed) & 15) || (((uintptr_t)y) & 31)) return fail(LDIC_EINVAL, "conv: x / weights must be 16-byte and y 32-byte aligned");
+  if (L.Cs % 16) return fail(LDIC_EINVAL, "conv: output channel count must be a multiple of 16");
 
   ConvParams P;
   memset(&P, 0, sizeof(P));

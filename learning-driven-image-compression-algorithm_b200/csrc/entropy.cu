@@ -579,41 +579,61 @@ extern "C" int ldic_latent_prep(const float* y, size_t n, void* y_round_bf16, vo
   return check_launch("k_latent_prep");
 }
 
-// First-layer patch matrix.  One thread per (pixel, 8-wide k chunk) -> one 16 B store.
+// First-layer patch matrix.  One CTA = 64 output pixels of one output row: the 5 input rows x Cin
+// channels it needs are staged in shared memory with coalesced loads, then every thread assembles
+// 16-byte (8 x bf16) chunks of A[p][k], k = (ky*5+kx)*Cin + ci, so the stores are fully coalesced.
+constexpr int kI2cPix = 64;
+constexpr int kI2cSpan = 2 * kI2cPix + 4;      // input columns 2*ox0-1 .. 2*ox0+2*63+3 (+1 pad)
 __global__ void __launch_bounds__(256) k_im2col_5x5s2(const float* __restrict__ x, __nv_bfloat16* __restrict__ a,
-                                                      int Cin, int H, int W, int Ho, int Wo, int Kp, long long total) {
+                                                      int Cin, int H, int W, int Ho, int Wo, int Kp) {
+  extern __shared__ float sx[];                 // [5*Cin][kI2cSpan]
+  const int ox0 = blockIdx.x * kI2cPix, oy = blockIdx.y, b = blockIdx.z;
+  const int rows = 5 * Cin;
+  for (int i = threadIdx.x; i < rows * kI2cSpan; i += 256) {
+    const int r = i / kI2cSpan, c = i - r * kI2cSpan;
+    const int ky = r / Cin, ci = r - ky * Cin;
+    const int iy = 2 * oy + ky - 1, ix = 2 * ox0 - 1 + c;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((long long)b * Cin + ci) * H + iy) * W + ix);
+    sx[i] = v;
+  }
+  // k -> staged offset (ky*Cin+ci)*span + kx, or -1 for the K padding (no per-element divisions below)
+  __shared__ int lut[256];
+  for (int k = threadIdx.x; k < Kp && k < 256; k += 256) {
+    int off = -1;
+    if (k < 25 * Cin) {
+      const int tap = k / Cin, ci = k - tap * Cin;
+      const int ky = tap / 5, kx = tap - ky * 5;
+      off = (ky * Cin + ci) * kI2cSpan + kx;
+    }
+    lut[k] = off;
+  }
+  __syncthreads();
   const int chunks = Kp / 8;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int q = (int)(i % chunks);
-    long long p = i / chunks;
-    const int ox = (int)(p % Wo);
-    long long t = p / Wo;
-    const int oy = (int)(t % Ho);
-    const int b = (int)(t / Ho);
+  const int cshift = 31 - __clz(chunks);                       // chunks is a power of two (checked on the host)
+  const long long p_row = ((long long)b * Ho + oy) * Wo;
+  for (int i = threadIdx.x; i < kI2cPix * chunks; i += 256) {
+    const int px = i >> cshift, q = i & (chunks - 1);
+    if (ox0 + px >= Wo) continue;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      int k = q * 8 + e;
-      float val = 0.f;
-      if (k < 25 * Cin) {
-        int tap = k / Cin, ci = k - tap * Cin;
-        int ky = tap / 5, kx = tap - ky * 5;
-        int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(x + (((long long)b * Cin + ci) * H + iy) * W + ix);
-      }
-      v[e] = val;
+      const int off = lut[q * 8 + e];
+      v[e] = off >= 0 ? sx[off + 2 * px] : 0.f;
     }
     uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(a + p * Kp + q * 8) = o;
+    *reinterpret_cast<uint4*>(a + (p_row + ox0 + px) * Kp + q * 8) = o;
   }
 }
 extern "C" int ldic_im2col_5x5s2(const float* x, void* a, int B, int Cin, int H, int W, int Kp, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0) return LDIC_OK;
   if ((H & 1) || (W & 1) || Kp % 8 || Kp < 25 * Cin) return fail(LDIC_EINVAL, "im2col: H,W must be even and Kp>=25*Cin, Kp%%8==0");
+  if (Cin > 8 || B > 65535 || H / 2 > 65535) return fail(LDIC_EINVAL, "im2col: Cin <= 8 and B, H/2 <= 65535");
+  if (Kp > 256 || ((Kp / 8) & (Kp / 8 - 1))) return fail(LDIC_EINVAL, "im2col: Kp must be 64, 128 or 256");
   int Ho = H / 2, Wo = W / 2;
-  long long total = (long long)B * Ho * Wo * (Kp / 8);
-  int grid = (int)((total + 255) / 256 > kNumSMs * 16 ? kNumSMs * 16 : (total + 255) / 256);
-  k_im2col_5x5s2<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)a, Cin, H, W, Ho, Wo, Kp, total);
+  dim3 grid((Wo + kI2cPix - 1) / kI2cPix, Ho, B);
+  size_t smem = (size_t)5 * Cin * kI2cSpan * sizeof(float);
+  k_im2col_5x5s2<<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)a, Cin, H, W, Ho, Wo, Kp);
   return check_launch("k_im2col_5x5s2");
 }
 
