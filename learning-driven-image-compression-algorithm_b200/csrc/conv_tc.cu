@@ -37,7 +37,8 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxTaps = 112;
 constexpr int kMaxJobs = 16;
 constexpr int kTmemCols = 512;
-constexpr int kNormCol = 256;
+constexpr int kBufCols = 256;           // two TMEM accumulator buffers at columns 0 and 256
+constexpr int kGdnInsert = 4;            // conv stages of the next tile issued before the previous tile's GDN stages
 
 // one filter tap = one spatial offset of the gather + a K range: nkc 64-wide blocks starting at
 // channel a_c0 of the activation and column b_c0 of the tap's packed weight block
@@ -231,11 +232,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* aux = smem_al + (size_t)stages * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages]
-  uint64_t* acc_full = empty_bar + kMaxStages;
-  uint64_t* acc_empty = acc_full + 1;
-  uint64_t* x2_ready = acc_empty + 1;
-  uint64_t* norm_full = x2_ready + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 1);
+  uint64_t* acc_full = empty_bar + kMaxStages;                         // [2] MMA -> epilogue: accumulator complete
+  uint64_t* buf_free = acc_full + 2;                                   // [2] epilogue -> MMA: TMEM buffer drained
+  uint64_t* x2_ready = buf_free + 2;                                   // [2] epilogue -> MMA: x^2 operand written
+  uint64_t* norm_full = x2_ready + 2;                                  // [2] MMA -> epilogue: GDN norm complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
   float* s_bias = reinterpret_cast<float*>(aux + 256);                 // [NP], 16-byte aligned
   float* s_beta = s_bias + NP * P.nbias;                               // [NP]
 
@@ -244,10 +245,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kEpiThreads);
-    mbar_init(x2_ready, kEpiThreads);
-    mbar_init(norm_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&buf_free[i], kEpiThreads);
+      mbar_init(&x2_ready[i], kEpiThreads);
+      mbar_init(&norm_full[i], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
@@ -261,83 +264,101 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Schedule (identical in all roles).  The CTA walks its tiles it = 0,1,..; tile `it` accumulates into
+  // TMEM buffer it&1 (columns 0 / 256).  With the GDN epilogue, the gamma contraction of tile it-1
+  // (gk ring stages whose A half is written by the epilogue warps) is issued after the first
+  // min(kGdnInsert, nkb) conv stages of tile `it`, into the buffer tile it-1 has just been drained from
+  // (the norm overwrites the accumulator in place), so the tensor pipe never waits for the epilogue.
   const int gk = gdn ? P.gdn_kblocks : 0;
+  const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // warpgroup 0 hands registers to the epilogue
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t kcount = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(P, t);
+    // ===================== TMA producer (whole warp: lanes issue the copies of a stage in parallel) ====
+    {
+      uint32_t slot = 0, ph = 0;                              // ring position and pass parity
+      auto advance = [&]() { if (++slot == (uint32_t)stages) { slot = 0; ph ^= 1; } };
+      auto load_gamma = [&]() {
+        for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring
+          if (lane == 0) {
+            mbar_wait(&empty_bar[slot], ph ^ 1);
+            mbar_expect_tx(&full_bar[slot], kBTileBytes);
+            tma_load_2d(smem_base + slot * kStageBytes + kATileBytes, &tmG, &full_bar[slot], kb * kBlockK, 0);
+          }
+          advance();
+        }
+      };
+      const int th = P.TH, tw128 = P.TW * 128;
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
         const Job jb = P.jobs[tc.job];
+        const int jins = (gk && it > 0) ? (jb.nkb < kGdnInsert ? jb.nkb : kGdnInsert) : -1;
+        int cb = 0;
         for (int tp = 0; tp < jb.ntaps; ++tp) {
           const Tap tap = P.taps[jb.tap_begin + tp];
-          for (int kc = 0; kc < tap.nkc; ++kc, ++kcount) {
-            const uint32_t slot = kcount % stages, use = kcount / stages;
-            mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
+          const int brow = (jb.tap_begin + tp) * NP;
+          for (int kc = 0; kc < tap.nkc; ++kc, ++cb) {
+            if (cb == jins) load_gamma();
             const uint32_t a_dst = smem_base + slot * kStageBytes;
-            const uint32_t b_dst = a_dst + kATileBytes;
-            mbar_expect_tx(&full_bar[slot], kStageBytes);
+            if (lane == 0) {
+              mbar_wait(&empty_bar[slot], ph ^ 1);
+              mbar_expect_tx(&full_bar[slot], kStageBytes);
+            }
+            __syncwarp();
             if (P.mode == 1) {
-              for (int j = 0; j < P.TH; ++j)
-                tma_load_5d(a_dst + j * P.TW * 128, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tap.px,
-                            tc.x0 + tap.dx, 2 * (tc.y0 + j) + tap.dy, tc.n0);
-            } else {
+              if (lane < th)
+                tma_load_5d(a_dst + lane * tw128, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tap.px,
+                            tc.x0 + tap.dx, 2 * (tc.y0 + lane) + tap.dy, tc.n0);
+            } else if (lane == 0) {
               tma_load_4d(a_dst, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tc.x0 + tap.dx, tc.y0 + tap.dy, tc.n0);
             }
-            tma_load_2d(b_dst, &tmW, &full_bar[slot], tap.b_c0 + kc * kBlockK, (jb.tap_begin + tp) * NP);
+            if (lane == 31) tma_load_2d(a_dst + kATileBytes, &tmW, &full_bar[slot], tap.b_c0 + kc * kBlockK, brow);
+            advance();
           }
         }
-        for (int kb = 0; kb < gk; ++kb, ++kcount) {       // gamma K-blocks ride the same ring
-          const uint32_t slot = kcount % stages, use = kcount / stages;
-          mbar_wait(&empty_bar[slot], (use & 1) ^ 1);
-          mbar_expect_tx(&full_bar[slot], kBTileBytes);
-          tma_load_2d(smem_base + slot * kStageBytes + kATileBytes, &tmG, &full_bar[slot], kb * kBlockK, 0);
-        }
+        if (cb == jins) load_gamma();
       }
+      if (gk) load_gamma();                                   // contraction of the last tile
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t kcount = 0, it = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
-        const TileCoord tc = decode_tile(P, t);
-        const int nkb = P.jobs[tc.job].nkb;
-        mbar_wait(acc_empty, (it & 1) ^ 1);                 // epilogue has drained the accumulator
+      uint32_t slot = 0, ph = 0;
+      auto mma_stage = [&](uint32_t d_tmem, bool first) {
+        mbar_wait(&full_bar[slot], ph);
         tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb, ++kcount) {
-          const uint32_t slot = kcount % stages, use = kcount / stages;
-          mbar_wait(&full_bar[slot], use & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + slot * kStageBytes;
-          const uint32_t b_addr = a_addr + kATileBytes;
+        const uint32_t a_addr = smem_base + slot * kStageBytes;
+        const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(tmem_base, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), kIdesc,
-                      (kb | k) != 0);
-          tc_commit(&empty_bar[slot]);                       // frees the smem slot when these MMAs retire
+        for (int k = 0; k < kBlockK / 16; ++k)
+          umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), kIdesc,
+                    !(first && k == 0));
+        tc_commit(&empty_bar[slot]);                         // frees the smem slot when these MMAs retire
+        if (++slot == (uint32_t)stages) { slot = 0; ph ^= 1; }
+      };
+      auto gdn_of = [&](int j) {                             // norm(j) = x^2 . gamma^T, in place over acc(j)
+        const int bsel = j & 1;
+        mbar_wait(&x2_ready[bsel], (j >> 1) & 1);            // x^2 tiles written by the epilogue warps
+        tc_fence_after();
+        for (int kb = 0; kb < gk; ++kb) mma_stage(tmem_base + bsel * kBufCols, kb == 0);
+        tc_commit(&norm_full[bsel]);
+      };
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+        const int nkb = P.jobs[tc.job].nkb;
+        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int bsel = it & 1;
+        mbar_wait(&buf_free[bsel], ((it >> 1) & 1) ^ 1);     // epilogue has drained this TMEM buffer
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (kb == jins) gdn_of(it - 1);
+          mma_stage(tmem_base + bsel * kBufCols, kb == 0);
         }
-        tc_commit(acc_full);
-        if (gk) {
-          mbar_wait(x2_ready, it & 1);                        // x^2 tiles written by the epilogue warps
-          tc_fence_after();
-          for (int kb = 0; kb < gk; ++kb, ++kcount) {
-            const uint32_t slot = kcount % stages, use = kcount / stages;
-            mbar_wait(&full_bar[slot], use & 1);
-            tc_fence_after();
-            const uint32_t a_addr = smem_base + slot * kStageBytes;
-            const uint32_t b_addr = a_addr + kATileBytes;
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16(tmem_base + kNormCol, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32),
-                        kIdesc, (kb | k) != 0);
-            tc_commit(&empty_bar[slot]);
-          }
-          tc_commit(norm_full);
-        }
+        tc_commit(&acc_full[bsel]);
+        if (nkb == jins) gdn_of(it - 1);
       }
+      if (gk) gdn_of(ntiles_cta - 1);
     }
   }
   } else {
@@ -351,31 +372,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // row -> pixel of the M grid (TW, TH are powers of two)
     const int xi = r & (P.TW - 1), yi = (r >> P.tw_shift) & (P.TH - 1), ni = r >> (P.tw_shift + P.th_shift);
     const bool igdn = (P.act == LDIC_ACT_IGDN);
-    uint32_t kcount = 0, it = 0;
-    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
-      const TileCoord tc = decode_tile(P, t);
+    uint32_t sbase = 0;                     // ring position of the first stage of tile `it`'s stream
+    for (int it = 0; it < ntiles_cta; ++it) {
+      const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
       const Job jb = P.jobs[tc.job];
-      const int nkb = jb.nkb;
+      const int bsel = it & 1;
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      const uint32_t tbuf = tmem_base + bsel * kBufCols + lane_sel + col0;
       const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
       const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B);
       const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
                                  (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
+      // ring position of this tile's gamma stages: after the first min(kGdnInsert, nkb) conv stages of
+      // the NEXT tile's stream, or right after this tile's stream when it is the CTA's last tile
+      sbase += (uint32_t)jb.nkb + ((gk && it > 0) ? (uint32_t)gk : 0u);
+      uint32_t gpos = sbase;
+      if (gk && it + 1 < ntiles_cta) {
+        const int nkb_next = P.jobs[decode_tile(P, blockIdx.x + (it + 1) * gridDim.x).job].nkb;
+        gpos += (uint32_t)(nkb_next < kGdnInsert ? nkb_next : kGdnInsert);
+      }
 
-      mbar_wait(acc_full, it & 1);
+      mbar_wait(&acc_full[bsel], par);
       tc_fence_after();
-      kcount += nkb;
 
-      // ---- pass 1: accumulator -> registers (+bias); release the accumulator ----
+      // ---- pass 1: accumulator -> registers (+bias) ----
       const float* sb = s_bias + (P.nbias > 1 ? tc.job * NP : 0);
       float xr[CPT];
       {
         uint32_t(&xu)[CPT] = reinterpret_cast<uint32_t(&)[CPT]>(xr);
 #pragma unroll
-        for (int c = 0; c < CPT; c += 32) tmem_ld32(tmem_base + lane_sel + col0 + c, reinterpret_cast<uint32_t(&)[32]>(xu[c]));
+        for (int c = 0; c < CPT; c += 32) tmem_ld32(tbuf + c, reinterpret_cast<uint32_t(&)[32]>(xu[c]));
         tmem_ld_wait();
       }
       tc_fence_before();
-      mbar_arrive(acc_empty);               // accumulator may be overwritten by the next tile
+      if (!gk) mbar_arrive(&buf_free[bsel]);   // no GDN: the buffer can take the tile after next right away
 #pragma unroll
       for (int c = 0; c < CPT; c += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(&sb[col0 + c]);
@@ -385,14 +415,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (gk) {
         // x^2 -> bf16 -> A slots (K-major, 128B swizzle: 16-byte chunk index XOR (row & 7))
         for (int kb = 0; kb < gk; ++kb) {
-          const uint32_t kc2 = kcount + kb;
+          const uint32_t kc2 = gpos + kb;
           mbar_wait(&empty_bar[kc2 % stages], ((kc2 / stages) & 1) ^ 1);
         }
         const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
 #pragma unroll
         for (int j = 0; j < CPT / 8; ++j) {
           const int col = col0 + j * 8;
-          const uint32_t kc2 = kcount + (col >> 6);
+          const uint32_t kc2 = gpos + (col >> 6);
           const uint32_t a_addr = smem_base + (kc2 % stages) * kStageBytes;
           const uint32_t chunk = (uint32_t)((col & 63) >> 3);
           const float* x8 = &xr[j * 8];
@@ -401,15 +431,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                        pack_bf16x2(x8[6] * x8[6], x8[7] * x8[7]));
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(x2_ready);
-        kcount += gk;
-        mbar_wait(norm_full, it & 1);
+        mbar_arrive(&x2_ready[bsel]);
+        mbar_wait(&norm_full[bsel], par);
         tc_fence_after();
         // ---- pass 2: out = x * rsqrt(norm + beta)   (IGDN: x * sqrt = x * n * rsqrt(n)) ----
 #pragma unroll
         for (int c = 0; c < CPT; c += 32) {
           uint32_t tr[32];
-          tmem_ld32(tmem_base + kNormCol + lane_sel + col0 + c, tr);
+          tmem_ld32(tbuf + c, tr);
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
@@ -424,6 +453,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc_fence_before();
+        mbar_arrive(&buf_free[bsel]);        // norm drained: the buffer is free for tile it+2
       } else if (P.act == LDIC_ACT_RELU) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) xr[c] = fmaxf(xr[c], 0.f);
