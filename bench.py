@@ -268,7 +268,7 @@ def run_ours(args):
                      "conv_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / t_ms if t_ms else None,
                      "per_layer_tflops": {k: round(d[1] / (d[0] * 1e-3) / 1e12, 1) for k, d in per_layer.items() if d[0] > 0}},
-        "roofline_likelihood": {"bound": "hbm", "kernel": "k_likelihood<4,0> (round + Gaussian likelihood + sum ln L)",
+        "roofline_likelihood": {"bound": "hbm", "kernel": "k_likelihood_fast<1,false> (round + Gaussian likelihood + sum ln L)",
                                 "achieved": lik_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": lik_gbs / hbm_peak,
                                 "traffic": None, "bytes_per_elem": 20, "elems": n_el, "ms": lik_ms,
                                 "peak_source": f"{peak_src} hbm_gbs", "workload": "C5-size 16x192x128x128, per-element mu/sigma"},

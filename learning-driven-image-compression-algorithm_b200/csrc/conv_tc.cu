@@ -22,6 +22,7 @@
 // Reference semantics: model/net.py:96-114 (g_a), :126-144 (g_s), :188-216 (h_a/h_s),
 // model/gdn.py:69-92,134-156 (GDN/IGDN).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 using namespace ldic;
@@ -909,6 +910,7 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   const int stage_bytes = kATileBytes + L.Np * kBlockK * 2;
   int stages = (227 * 1024 - 2048 - (L.nbias + 1) * L.Np * 4) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = getenv("LDIC_STAGES")) { int v = atoi(e); if (v >= 2 && v < stages) stages = v; }   // tuning aid
   P.stages = stages;
   if (gdn && stages < P.gdn_kblocks + 1) return fail(LDIC_EINVAL, "conv: not enough pipeline stages for the GDN epilogue");
 
