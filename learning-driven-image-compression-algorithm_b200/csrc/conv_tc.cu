@@ -3,10 +3,11 @@
 // normalisation fused into the epilogue as a second tensor-core contraction.
 //
 // One persistent CTA per SM, 384 threads:
-//   warp 0       TMA producer   (one lane)
-//   warp 1       MMA issuer     (one lane) + TMEM allocator
-//   warps 4..11  epilogue       (TMEM -> registers -> global), 2 warps per TMEM lane quadrant
-// (setmaxnreg moves registers from warpgroup 0 to the two epilogue warpgroups)
+//   warps 0..7   epilogue       (TMEM -> registers -> global), 2 warps per TMEM lane quadrant
+//   warp 8       TMA producer   (A tiles; all lanes issue copies)
+//   warp 9       MMA issuer     (one lane) + TMEM allocator
+//   warp 10      halo kernel only: weight-tile producer
+// (setmaxnreg moves registers from warpgroup 2 to the two epilogue warpgroups)
 //
 // GEMM view: M = 128 output (or, for transposed convs, input-grid) pixels per tile,
 // N = Np accumulator columns (= output channels, or 4 sub-pixel phases x channels for the
@@ -30,7 +31,11 @@ using namespace ldic;
 namespace {
 
 constexpr int kThreads = 384;          // warpgroup 0: producer, MMA, 2 spare; warpgroups 1-2: epilogue
-constexpr int kEpiThreads = 256;
+constexpr int kEpiThreads = 256;          // warps 0..7
+constexpr int kProdWarp = 8;              // TMA producer (A tiles / A regions)
+constexpr int kMmaWarp = 9;               // tcgen05.mma issuer; the HIGHEST warp id on its scheduler, so it wins
+                                          // issue arbitration against the two epilogue warps that share it
+constexpr int kProdBWarp = 10;            // halo kernel: weight / gamma tile producer
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = 128 B = one swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
@@ -43,8 +48,8 @@ constexpr int kGdnInsert = 4;            // conv stages of the next tile issued 
 
 // one filter tap = one spatial offset of the gather + a K range: nkc 64-wide blocks starting at
 // channel a_c0 of the activation and column b_c0 of the tap's packed weight block
-struct Tap { short dx, dy, px, nkc; int a_c0, b_c0; };
-struct Job { int ntaps, tap_begin, nkb, oy_off, ox_off, out_off; };
+struct Tap { short dx, dy, px, nkc; int a_c0, b_c0; int halo_off; };
+struct Job { int ntaps, tap_begin, nkb, oy_off, ox_off, out_off; int kc0, nchunks; };
 
 struct ConvParams {
   int mode;                 // 0: stride-1 gather (4-D map), 1: stride-2 gather (5-D parity map)
@@ -55,6 +60,8 @@ struct ConvParams {
   int gdn_kblocks;          // Np / 64 when act is GDN/IGDN, else 0
   int act, out_f32;
   int stages;
+  // halo variant: one (TH+dy range) x (TW+dx range) activation region per 64-channel chunk serves all taps
+  int halo, SA, SB, a_slot_bytes, RW, RH, dxmin, dymin;
   int ngroups, Cg;          // accumulator columns = ngroups x Cg
   int sy, sx;               // output pixel = grid pixel * (sy,sx) + job offset (+ sub-pixel group offset)
   int nbias;                // 1, or njobs when every job has its own bias vector
@@ -64,6 +71,7 @@ struct ConvParams {
   const float* bias;
   const float* beta;
   void* out;
+  unsigned long long* dbg;   // optional cycle counters of CTA 0 (LDIC_DEBUG_TIMING=1), else null
 };
 
 // ---------------------------------------------------------------------------------
@@ -125,6 +133,11 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {     // true on exactly one lane of a converged warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -153,13 +166,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// Same, with the two smem descriptors given as 32-bit halves (lo = start address >> 4 | LBO, hi = SBO, version,
+// swizzle mode): the issuing thread only does one 32-bit add per operand per K step.
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
 
 // K-major, 128-byte swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
   d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;          // stride byte offset between 8-row groups (1024 when dense)
   d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
@@ -217,156 +245,26 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, int t) {
   return c;
 }
 
+// ---------------------------------------------------------------------------------
+// Epilogue role (shared by the streaming and the halo kernels): warps 4..11.
+// ---------------------------------------------------------------------------------
+struct EpiRing {
+  uint32_t ring_base;       // smem address of slot 0 of the ring that carries the x^2 operand tiles
+  uint32_t slot_bytes;
+  uint32_t nslots;
+  uint64_t* empty_bar;      // [nslots] "slot free" barriers of that ring
+  uint64_t *acc_full, *buf_free, *x2_ready, *norm_full;   // [2] each
+  const float *s_bias, *s_beta;
+  int use_chunks;           // stream length of a tile: jobs[].nchunks (halo) or jobs[].nkb (streaming)
+  int insert_after;         // GDN items of tile it-1 ride after this many stream items of tile it
+};
+
 template <int NP>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
-  constexpr int CPT = NP / 2;                       // accumulator columns per epilogue thread
-  constexpr int kBTileBytes = NP * kBlockK * 2;
-  constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024 B alignment
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int stages = P.stages;
-  uint8_t* aux = smem_al + (size_t)stages * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [kMaxStages]
-  uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages]
-  uint64_t* acc_full = empty_bar + kMaxStages;                         // [2] MMA -> epilogue: accumulator complete
-  uint64_t* buf_free = acc_full + 2;                                   // [2] epilogue -> MMA: TMEM buffer drained
-  uint64_t* x2_ready = buf_free + 2;                                   // [2] epilogue -> MMA: x^2 operand written
-  uint64_t* norm_full = x2_ready + 2;                                  // [2] MMA -> epilogue: GDN norm complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
-  float* s_bias = reinterpret_cast<float*>(aux + 256);                 // [NP], 16-byte aligned
-  float* s_beta = s_bias + NP * P.nbias;                               // [NP]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&buf_free[i], kEpiThreads);
-      mbar_init(&x2_ready[i], kEpiThreads);
-      mbar_init(&norm_full[i], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmW);
-    if (gdn) prefetch_tmap(&tmG);
-  }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
-  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
-  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // Schedule (identical in all roles).  The CTA walks its tiles it = 0,1,..; tile `it` accumulates into
-  // TMEM buffer it&1 (columns 0 / 256).  With the GDN epilogue, the gamma contraction of tile it-1
-  // (gk ring stages whose A half is written by the epilogue warps) is issued after the first
-  // min(kGdnInsert, nkb) conv stages of tile `it`, into the buffer tile it-1 has just been drained from
-  // (the norm overwrites the accumulator in place), so the tensor pipe never waits for the epilogue.
-  const int gk = gdn ? P.gdn_kblocks : 0;
-  const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // warpgroup 0 hands registers to the epilogue
-  if (warp == 0) {
-    // ===================== TMA producer (whole warp: lanes issue the copies of a stage in parallel) ====
-    {
-      uint32_t slot = 0, ph = 0;                              // ring position and pass parity
-      auto advance = [&]() { if (++slot == (uint32_t)stages) { slot = 0; ph ^= 1; } };
-      auto load_gamma = [&]() {
-        for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring
-          if (lane == 0) {
-            mbar_wait(&empty_bar[slot], ph ^ 1);
-            mbar_expect_tx(&full_bar[slot], kBTileBytes);
-            tma_load_2d(smem_base + slot * kStageBytes + kATileBytes, &tmG, &full_bar[slot], kb * kBlockK, 0);
-          }
-          advance();
-        }
-      };
-      const int th = P.TH, tw128 = P.TW * 128;
-      for (int it = 0; it < ntiles_cta; ++it) {
-        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        const Job jb = P.jobs[tc.job];
-        const int jins = (gk && it > 0) ? (jb.nkb < kGdnInsert ? jb.nkb : kGdnInsert) : -1;
-        int cb = 0;
-        for (int tp = 0; tp < jb.ntaps; ++tp) {
-          const Tap tap = P.taps[jb.tap_begin + tp];
-          const int brow = (jb.tap_begin + tp) * NP;
-          for (int kc = 0; kc < tap.nkc; ++kc, ++cb) {
-            if (cb == jins) load_gamma();
-            const uint32_t a_dst = smem_base + slot * kStageBytes;
-            if (lane == 0) {
-              mbar_wait(&empty_bar[slot], ph ^ 1);
-              mbar_expect_tx(&full_bar[slot], kStageBytes);
-            }
-            __syncwarp();
-            if (P.mode == 1) {
-              if (lane < th)
-                tma_load_5d(a_dst + lane * tw128, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tap.px,
-                            tc.x0 + tap.dx, 2 * (tc.y0 + lane) + tap.dy, tc.n0);
-            } else if (lane == 0) {
-              tma_load_4d(a_dst, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tc.x0 + tap.dx, tc.y0 + tap.dy, tc.n0);
-            }
-            if (lane == 31) tma_load_2d(a_dst + kATileBytes, &tmW, &full_bar[slot], tap.b_c0 + kc * kBlockK, brow);
-            advance();
-          }
-        }
-        if (cb == jins) load_gamma();
-      }
-      if (gk) load_gamma();                                   // contraction of the last tile
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t slot = 0, ph = 0;
-      auto mma_stage = [&](uint32_t d_tmem, bool first) {
-        mbar_wait(&full_bar[slot], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + slot * kStageBytes;
-        const uint32_t b_addr = a_addr + kATileBytes;
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), kIdesc,
-                    !(first && k == 0));
-        tc_commit(&empty_bar[slot]);                         // frees the smem slot when these MMAs retire
-        if (++slot == (uint32_t)stages) { slot = 0; ph ^= 1; }
-      };
-      auto gdn_of = [&](int j) {                             // norm(j) = x^2 . gamma^T, in place over acc(j)
-        const int bsel = j & 1;
-        mbar_wait(&x2_ready[bsel], (j >> 1) & 1);            // x^2 tiles written by the epilogue warps
-        tc_fence_after();
-        for (int kb = 0; kb < gk; ++kb) mma_stage(tmem_base + bsel * kBufCols, kb == 0);
-        tc_commit(&norm_full[bsel]);
-      };
-      for (int it = 0; it < ntiles_cta; ++it) {
-        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        const int nkb = P.jobs[tc.job].nkb;
-        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
-        const int bsel = it & 1;
-        mbar_wait(&buf_free[bsel], ((it >> 1) & 1) ^ 1);     // epilogue has drained this TMEM buffer
-        tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          if (kb == jins) gdn_of(it - 1);
-          mma_stage(tmem_base + bsel * kBufCols, kb == 0);
-        }
-        tc_commit(&acc_full[bsel]);
-        if (nkb == jins) gdn_of(it - 1);
-      }
-      if (gk) gdn_of(ntiles_cta - 1);
-    }
-  }
-  } else {
-    // ===================== epilogue warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+__device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing& R, uint32_t tmem_base, int gk,
+                                              int ntiles_cta, int warp, int lane) {
+  constexpr int CPT = NP / 2;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int h = (warp - 4) >> 2;          // column half
+    const int h = warp >> 2;                // column half (epilogue warps are 0..7)
     const int r = q * 32 + lane;            // tile row = TMEM lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const int col0 = h * CPT;
@@ -384,20 +282,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B);
       const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
                                  (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
-      // ring position of this tile's gamma stages: after the first min(kGdnInsert, nkb) conv stages of
-      // the NEXT tile's stream, or right after this tile's stream when it is the CTA's last tile
-      sbase += (uint32_t)jb.nkb + ((gk && it > 0) ? (uint32_t)gk : 0u);
+      // ring position of this tile's gamma items: after the first min(insert_after, len) items of the
+      // NEXT tile's stream, or right after this tile's stream when it is the CTA's last tile
+      const int len_this = R.use_chunks ? jb.nchunks : jb.nkb;
+      sbase += (uint32_t)len_this + ((gk && it > 0) ? (uint32_t)gk : 0u);
       uint32_t gpos = sbase;
       if (gk && it + 1 < ntiles_cta) {
-        const int nkb_next = P.jobs[decode_tile(P, blockIdx.x + (it + 1) * gridDim.x).job].nkb;
-        gpos += (uint32_t)(nkb_next < kGdnInsert ? nkb_next : kGdnInsert);
+        const Job jn = P.jobs[decode_tile(P, blockIdx.x + (it + 1) * gridDim.x).job];
+        const int len_next = R.use_chunks ? jn.nchunks : jn.nkb;
+        gpos += (uint32_t)(len_next < R.insert_after ? len_next : R.insert_after);
       }
 
-      mbar_wait(&acc_full[bsel], par);
+      mbar_wait(&R.acc_full[bsel], par);
       tc_fence_after();
 
       // ---- pass 1: accumulator -> registers (+bias) ----
-      const float* sb = s_bias + (P.nbias > 1 ? tc.job * NP : 0);
+      const float* sb = R.s_bias + (P.nbias > 1 ? tc.job * NP : 0);
       float xr[CPT];
       {
         uint32_t(&xu)[CPT] = reinterpret_cast<uint32_t(&)[CPT]>(xr);
@@ -406,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
       }
       tc_fence_before();
-      if (!gk) mbar_arrive(&buf_free[bsel]);   // no GDN: the buffer can take the tile after next right away
+      if (!gk) mbar_arrive(&R.buf_free[bsel]);   // no GDN: the buffer can take the tile after next right away
 #pragma unroll
       for (int c = 0; c < CPT; c += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(&sb[col0 + c]);
@@ -417,14 +317,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // x^2 -> bf16 -> A slots (K-major, 128B swizzle: 16-byte chunk index XOR (row & 7))
         for (int kb = 0; kb < gk; ++kb) {
           const uint32_t kc2 = gpos + kb;
-          mbar_wait(&empty_bar[kc2 % stages], ((kc2 / stages) & 1) ^ 1);
+          mbar_wait(&R.empty_bar[kc2 % R.nslots], ((kc2 / R.nslots) & 1) ^ 1);
         }
         const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
 #pragma unroll
         for (int j = 0; j < CPT / 8; ++j) {
           const int col = col0 + j * 8;
           const uint32_t kc2 = gpos + (col >> 6);
-          const uint32_t a_addr = smem_base + (kc2 % stages) * kStageBytes;
+          const uint32_t a_addr = R.ring_base + (kc2 % R.nslots) * R.slot_bytes;
           const uint32_t chunk = (uint32_t)((col & 63) >> 3);
           const float* x8 = &xr[j * 8];
           st_shared_v4(a_addr + row_off + ((chunk ^ rx) << 4), pack_bf16x2(x8[0] * x8[0], x8[1] * x8[1]),
@@ -432,8 +332,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                        pack_bf16x2(x8[6] * x8[6], x8[7] * x8[7]));
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(&x2_ready[bsel]);
-        mbar_wait(&norm_full[bsel], par);
+        mbar_arrive(&R.x2_ready[bsel]);
+        mbar_wait(&R.norm_full[bsel], par);
         tc_fence_after();
         // ---- pass 2: out = x * rsqrt(norm + beta)   (IGDN: x * sqrt = x * n * rsqrt(n)) ----
 #pragma unroll
@@ -443,7 +343,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(&s_beta[col0 + c + k]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&R.s_beta[col0 + c + k]);
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -454,7 +354,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc_fence_before();
-        mbar_arrive(&buf_free[bsel]);        // norm drained: the buffer is free for tile it+2
+        mbar_arrive(&R.buf_free[bsel]);        // norm drained: the buffer is free for tile it+2
       } else if (P.act == LDIC_ACT_RELU) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) xr[c] = fmaxf(xr[c], 0.f);
@@ -501,11 +401,423 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
+  constexpr int kBTileBytes = NP * kBlockK * 2;
+  constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024 B alignment
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = P.stages;
+  uint8_t* aux = smem_al + (size_t)stages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [kMaxStages]
+  uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages]
+  uint64_t* acc_full = empty_bar + kMaxStages;                         // [2] MMA -> epilogue: accumulator complete
+  uint64_t* buf_free = acc_full + 2;                                   // [2] epilogue -> MMA: TMEM buffer drained
+  uint64_t* x2_ready = buf_free + 2;                                   // [2] epilogue -> MMA: x^2 operand written
+  uint64_t* norm_full = x2_ready + 2;                                  // [2] MMA -> epilogue: GDN norm complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
+  float* s_bias = reinterpret_cast<float*>(aux + 256);                 // [NP], 16-byte aligned
+  float* s_beta = s_bias + NP * P.nbias;                               // [NP]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&buf_free[i], kEpiThreads);
+      mbar_init(&x2_ready[i], kEpiThreads);
+      mbar_init(&norm_full[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    if (gdn) prefetch_tmap(&tmG);
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
+  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // Schedule (identical in all roles).  The CTA walks its tiles it = 0,1,..; tile `it` accumulates into
+  // TMEM buffer it&1 (columns 0 / 256).  With the GDN epilogue, the gamma contraction of tile it-1
+  // (gk ring stages whose A half is written by the epilogue warps) is issued after the first
+  // min(kGdnInsert, nkb) conv stages of tile `it`, into the buffer tile it-1 has just been drained from
+  // (the norm overwrites the accumulator in place), so the tensor pipe never waits for the epilogue.
+  const int gk = gdn ? P.gdn_kblocks : 0;
+  const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // warpgroup 2 hands registers to the epilogue
+  if (warp == kProdWarp) {
+    // ===================== TMA producer =====================
+    // The whole warp runs the loop with warp-uniform values (so addresses / coordinates live in
+    // uniform registers and the TMA instructions issue without per-lane serialisation); one elected
+    // lane arms the barrier and issues the copies.
+    {
+      uint32_t slot = 0, ph = 0;                              // ring position and pass parity
+      const bool pdbg = P.dbg != nullptr && blockIdx.x == 0;
+      long long t_empty = 0;
+      const long long tp_begin = clock64();
+      auto advance = [&]() { if (++slot == (uint32_t)stages) { slot = 0; ph ^= 1; } };
+      auto load_gamma = [&]() {
+        for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring
+          mbar_wait(&empty_bar[slot], ph ^ 1);
+          __syncwarp();
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[slot], kBTileBytes);
+            tma_load_2d(smem_base + slot * kStageBytes + kATileBytes, &tmG, &full_bar[slot], kb * kBlockK, 0);
+          }
+          advance();
+        }
+      };
+      const int th = P.TH, tw128 = P.TW * 128;
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+        const Job jb = P.jobs[tc.job];
+        const int jins = (gk && it > 0) ? (jb.nkb < kGdnInsert ? jb.nkb : kGdnInsert) : -1;
+        int cb = 0;
+        for (int tp = 0; tp < jb.ntaps; ++tp) {
+          const Tap tap = P.taps[jb.tap_begin + tp];
+          const int brow = (jb.tap_begin + tp) * NP;
+          for (int kc = 0; kc < tap.nkc; ++kc, ++cb) {
+            if (cb == jins) load_gamma();
+            const uint32_t a_dst = smem_base + slot * kStageBytes;
+            long long t0 = 0;
+            if (pdbg) t0 = clock64();
+            mbar_wait(&empty_bar[slot], ph ^ 1);
+            if (pdbg) t_empty += clock64() - t0;
+            __syncwarp();
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[slot], kStageBytes);
+              if (P.mode == 1) {
+                for (int j = 0; j < th; ++j)
+                  tma_load_5d(a_dst + j * tw128, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tap.px,
+                              tc.x0 + tap.dx, 2 * (tc.y0 + j) + tap.dy, tc.n0);
+              } else {
+                tma_load_4d(a_dst, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tc.x0 + tap.dx, tc.y0 + tap.dy, tc.n0);
+              }
+              tma_load_2d(a_dst + kATileBytes, &tmW, &full_bar[slot], tap.b_c0 + kc * kBlockK, brow);
+            }
+            advance();
+          }
+        }
+        if (cb == jins) load_gamma();
+      }
+      if (gk) load_gamma();                                   // contraction of the last tile
+      if (pdbg && lane == 0) { P.dbg[8] = (unsigned long long)(clock64() - tp_begin); P.dbg[9] = (unsigned long long)t_empty; }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
+      uint32_t slot = 0, ph = 0;
+      const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
+      long long t_full = 0, t_buf = 0, t_x2 = 0, n_st = 0;
+      const long long t_begin = clock64();
+      const uint32_t hi = desc_hi(1024);
+      auto mma_stage = [&](uint32_t d_tmem, bool first) {
+        long long t0 = 0;
+        if (dbg) t0 = clock64();
+        mbar_wait(&full_bar[slot], ph);
+        if (dbg) { t_full += clock64() - t0; ++n_st; }
+        tc_fence_after();
+        __syncwarp();
+        const uint32_t a_addr = smem_base + slot * kStageBytes;
+        const uint32_t alo = desc_lo(a_addr), blo = desc_lo(a_addr + kATileBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_lh(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, kIdesc, !(first && k == 0));
+          tc_commit(&empty_bar[slot]);                       // frees the smem slot when these MMAs retire
+        }
+        if (++slot == (uint32_t)stages) { slot = 0; ph ^= 1; }
+      };
+      auto gdn_of = [&](int j) {                             // norm(j) = x^2 . gamma^T, in place over acc(j)
+        const int bsel = j & 1;
+        long long t0 = 0;
+        if (dbg) t0 = clock64();
+        mbar_wait(&x2_ready[bsel], (j >> 1) & 1);            // x^2 tiles written by the epilogue warps
+        if (dbg) t_x2 += clock64() - t0;
+        tc_fence_after();
+        for (int kb = 0; kb < gk; ++kb) mma_stage(tmem_base + bsel * kBufCols, kb == 0);
+        __syncwarp();
+        if (elect_one()) tc_commit(&norm_full[bsel]);
+      };
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+        const int nkb = P.jobs[tc.job].nkb;
+        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int bsel = it & 1;
+        long long t0 = 0;
+        if (dbg) t0 = clock64();
+        mbar_wait(&buf_free[bsel], ((it >> 1) & 1) ^ 1);     // epilogue has drained this TMEM buffer
+        if (dbg) t_buf += clock64() - t0;
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (kb == jins) gdn_of(it - 1);
+          mma_stage(tmem_base + bsel * kBufCols, kb == 0);
+        }
+        __syncwarp();
+        if (elect_one()) tc_commit(&acc_full[bsel]);
+        if (nkb == jins) gdn_of(it - 1);
+      }
+      if (gk) gdn_of(ntiles_cta - 1);
+      if (dbg && lane == 0) {
+        P.dbg[0] = (unsigned long long)(clock64() - t_begin); P.dbg[1] = (unsigned long long)t_full;
+        P.dbg[2] = (unsigned long long)t_buf; P.dbg[3] = (unsigned long long)t_x2; P.dbg[4] = (unsigned long long)n_st;
+        P.dbg[5] = (unsigned long long)ntiles_cta;
+      }
+    }
+  }
+  } else {
+    // ===================== epilogue warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    EpiRing R;
+    R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
+    R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = kGdnInsert;
+    epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Halo variant for stride-1 gathers (transposed-conv phases, 3x3 convs, context conv1).
+// The streaming kernel above re-fetches a 128-pixel A tile for every filter tap, so every input pixel
+// crosses the L2->SM fabric once per tap (~6 TB/s of unique traffic is the measured ceiling).  Here a
+// tile is 16 rows x 8 pixels and ONE (16+dy range) x (8+dx range) pixel region per 64-channel chunk is
+// brought in by a single TMA box; every tap's A operand is that same region addressed through a UMMA
+// descriptor whose start is shifted by whole 128-byte pixel rows and whose 8-row-group stride is the
+// region row pitch (SWIZZLE_128B is applied on absolute address bits, so shifted starts read exactly
+// what TMA wrote: tools/umma_shift_probe.cu).  Two rings: A regions (warp 0) and B weight tiles (warp 2).
+// ---------------------------------------------------------------------------------
+constexpr int kHaloInsert = 1;          // conv chunks of the next tile issued before the previous tile's GDN items
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
+  constexpr int kBTileBytes = NP * kBlockK * 2;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int SA = P.SA, SB = P.SB;
+  const uint32_t a_slot = (uint32_t)P.a_slot_bytes;
+  const uint32_t b_base = smem_base + (uint32_t)SA * a_slot;
+  uint8_t* aux = smem_al + (size_t)SA * a_slot + (size_t)SB * kBTileBytes;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(aux);                  // [kMaxStages]
+  uint64_t* aempty = afull + kMaxStages;
+  uint64_t* bfull = aempty + kMaxStages;
+  uint64_t* bempty = bfull + kMaxStages;
+  uint64_t* acc_full = bempty + kMaxStages;                            // [2]
+  uint64_t* buf_free = acc_full + 2;
+  uint64_t* x2_ready = buf_free + 2;
+  uint64_t* norm_full = x2_ready + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
+  float* s_bias = reinterpret_cast<float*>(aux + 512);                 // 16-byte aligned
+  float* s_beta = s_bias + NP * P.nbias;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SA; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&buf_free[i], kEpiThreads);
+      mbar_init(&x2_ready[i], kEpiThreads);
+      mbar_init(&norm_full[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    if (gdn) prefetch_tmap(&tmG);
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
+  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int gk = gdn ? P.gdn_kblocks : 0;
+  const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t region_bytes = (uint32_t)(P.RW * P.RH * 128);
+  const uint32_t sbo = (uint32_t)P.RW * 128u;
+  // a tap contributes to channel chunk kc iff its K range covers it
+  auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == kProdWarp) {
+      // ===================== A-region producer (warp-uniform loop, elected lane issues) =====================
+      uint32_t sa = 0, pa = 0;
+      auto adv = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
+      auto reserve_gdn = [&]() {            // hand gk A slots to the epilogue warps (x^2 operand tiles)
+        for (int kb = 0; kb < gk; ++kb) {
+          mbar_wait(&aempty[sa], pa ^ 1);
+          __syncwarp();
+          if (elect_one()) mbar_arrive(&afull[sa]);
+          adv();
+        }
+      };
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+        const Job jb = P.jobs[tc.job];
+        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
+        for (int ci = 0; ci < jb.nchunks; ++ci) {
+          if (ci == jins) reserve_gdn();
+          mbar_wait(&aempty[sa], pa ^ 1);
+          __syncwarp();
+          if (elect_one()) {
+            mbar_expect_tx(&afull[sa], region_bytes);
+            tma_load_4d(smem_base + sa * a_slot, &tmA, &afull[sa], (jb.kc0 + ci) * kBlockK, tc.x0 + P.dxmin,
+                        tc.y0 + P.dymin, tc.n0);
+          }
+          adv();
+        }
+        if (jb.nchunks == jins) reserve_gdn();
+      }
+      if (gk) reserve_gdn();
+    } else if (warp == kProdBWarp) {
+      // ===================== B (weights / gamma) producer =====================
+      uint32_t sb = 0, pb = 0;
+      auto adv = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
+      auto load_gamma = [&]() {
+        for (int kb = 0; kb < gk; ++kb) {
+          mbar_wait(&bempty[sb], pb ^ 1);
+          __syncwarp();
+          if (elect_one()) {
+            mbar_expect_tx(&bfull[sb], kBTileBytes);
+            tma_load_2d(b_base + sb * kBTileBytes, &tmG, &bfull[sb], kb * kBlockK, 0);
+          }
+          adv();
+        }
+      };
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+        const Job jb = P.jobs[tc.job];
+        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
+        for (int ci = 0; ci < jb.nchunks; ++ci) {
+          if (ci == jins) load_gamma();
+          const int kc = jb.kc0 + ci;
+          for (int tp = 0; tp < jb.ntaps; ++tp) {
+            const Tap tap = P.taps[jb.tap_begin + tp];
+            if (!tap_active(tap, kc)) continue;
+            mbar_wait(&bempty[sb], pb ^ 1);
+            __syncwarp();
+            if (elect_one()) {
+              mbar_expect_tx(&bfull[sb], kBTileBytes);
+              tma_load_2d(b_base + sb * kBTileBytes, &tmW, &bfull[sb], tap.b_c0 + kc * kBlockK - tap.a_c0,
+                          (jb.tap_begin + tp) * NP);
+            }
+            adv();
+          }
+        }
+        if (jb.nchunks == jins) load_gamma();
+      }
+      if (gk) load_gamma();
+    } else if (warp == kMmaWarp) {
+      // ===================== MMA issuer =====================
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      const uint32_t hi_a = desc_hi(sbo), hi_b = desc_hi(1024);
+      auto adv_a = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
+      auto adv_b = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
+      auto gdn_of = [&](int j) {            // norm(j) = x^2 . gamma^T, in place over acc(j)
+        const int bsel = j & 1;
+        mbar_wait(&x2_ready[bsel], (j >> 1) & 1);
+        tc_fence_after();
+        for (int kb = 0; kb < gk; ++kb) {
+          mbar_wait(&afull[sa], pa);
+          mbar_wait(&bfull[sb], pb);
+          tc_fence_after();
+          __syncwarp();
+          const uint32_t alo = desc_lo(smem_base + sa * a_slot), blo = desc_lo(b_base + sb * kBTileBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16_lh(tmem_base + bsel * kBufCols, alo + 2 * k, hi_b, blo + 2 * k, hi_b, kIdesc, (kb | k) != 0);
+            tc_commit(&bempty[sb]);
+            tc_commit(&aempty[sa]);
+          }
+          adv_a(); adv_b();
+        }
+        __syncwarp();
+        if (elect_one()) tc_commit(&norm_full[bsel]);
+      };
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+        const Job jb = P.jobs[tc.job];
+        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
+        const int bsel = it & 1;
+        mbar_wait(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        bool first = true;
+        for (int ci = 0; ci < jb.nchunks; ++ci) {
+          if (ci == jins) gdn_of(it - 1);
+          const int kc = jb.kc0 + ci;
+          mbar_wait(&afull[sa], pa);
+          const uint32_t a_addr = smem_base + sa * a_slot;
+          for (int tp = 0; tp < jb.ntaps; ++tp) {
+            const Tap tap = P.taps[jb.tap_begin + tp];
+            if (!tap_active(tap, kc)) continue;
+            mbar_wait(&bfull[sb], pb);
+            tc_fence_after();
+            __syncwarp();
+            const uint32_t alo = desc_lo(a_addr + tap.halo_off), blo = desc_lo(b_base + sb * kBTileBytes);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16_lh(tmem_base + bsel * kBufCols, alo + 2 * k, hi_a, blo + 2 * k, hi_b, kIdesc, !(first && k == 0));
+              tc_commit(&bempty[sb]);
+            }
+            first = false;
+            adv_b();
+          }
+          __syncwarp();
+          if (elect_one()) tc_commit(&aempty[sa]);            // region consumed by all of its taps
+          adv_a();
+        }
+        __syncwarp();
+        if (elect_one()) tc_commit(&acc_full[bsel]);
+        if (jb.nchunks == jins) gdn_of(it - 1);
+      }
+      if (gk) gdn_of(ntiles_cta - 1);
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    EpiRing R;
+    R.ring_base = smem_base; R.slot_bytes = a_slot; R.nslots = (uint32_t)SA; R.empty_bar = aempty;
+    R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 1; R.insert_after = kHaloInsert;
+    epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -784,6 +1096,21 @@ int launch_conv(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g
   return check_launch("conv_tc_kernel");
 }
 
+template <int NP>
+int launch_halo(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
+  const size_t smem = (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * NP * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
+                      (size_t)(P.nbias + 1) * NP * sizeof(float) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (smem > 227 * 1024) return fail(LDIC_EINVAL, "conv halo: shared memory budget exceeded (%zu)", smem);
+  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  conv_halo_kernel<NP><<<grid, kThreads, smem, st>>>(a, w, g, P);
+  return check_launch("conv_halo_kernel");
+}
+
 // generic weight packer: Wp[t][n][k]
 struct PackTable {
   int ntaps, Np, Cg, ngroups, Cin, Cout, Kw, cin_offset, k, transposed, cin_map, map_N, map_M, nbias;
@@ -907,6 +1234,11 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   for (int j = 0; j < kMaxJobs; ++j) P.jobs[j] = L.jobs[j];
   for (int t = 0; t < kMaxTaps; ++t) P.taps[t] = L.taps[t];
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
+  static unsigned long long* dbg_buf = nullptr;
+  const bool want_dbg = getenv("LDIC_DEBUG_TIMING") != nullptr;
+  if (want_dbg && !dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
+  if (want_dbg) cudaMemset(dbg_buf, 0, 16 * sizeof(unsigned long long));
+  P.dbg = want_dbg ? dbg_buf : nullptr;
   const int stage_bytes = kATileBytes + L.Np * kBlockK * 2;
   int stages = (227 * 1024 - 2048 - (L.nbias + 1) * L.Np * 4) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -914,9 +1246,59 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   P.stages = stages;
   if (gdn && stages < P.gdn_kblocks + 1) return fail(LDIC_EINVAL, "conv: not enough pipeline stages for the GDN epilogue");
 
+  // ---- halo variant (stride-1 gathers with spatial taps): one region load per 64-channel chunk ----
+  bool halo = false;
+  if (L.mode == 0) {
+    int dxmin = 0, dxmax = 0, dymin = 0, dymax = 0;
+    for (int t = 0; t < L.ntaps_total; ++t) {
+      dxmin = L.taps[t].dx < dxmin ? L.taps[t].dx : dxmin; dxmax = L.taps[t].dx > dxmax ? L.taps[t].dx : dxmax;
+      dymin = L.taps[t].dy < dymin ? L.taps[t].dy : dymin; dymax = L.taps[t].dy > dymax ? L.taps[t].dy : dymax;
+    }
+    const long long halo_tiles = (long long)((L.Wg + 7) / 8) * ((L.Hg + 15) / 16) * L.Bg;
+    halo = (dxmax > dxmin || dymax > dymin) && halo_tiles * 10 <= (long long)P.tiles_per_job * 13;
+    if (const char* e = getenv("LDIC_HALO")) halo = halo && atoi(e) != 0;          // tuning aid: LDIC_HALO=0 disables
+    if (halo) {
+      P.halo = 1; P.dxmin = dxmin; P.dymin = dymin;
+      P.RW = 8 + dxmax - dxmin; P.RH = 16 + dymax - dymin;
+      P.a_slot_bytes = (P.RW * P.RH * 128 + 1023) / 1024 * 1024;
+      const int bbytes = L.Np * kBlockK * 2;
+      const int budget = 227 * 1024 - 1024 - 512 - (L.nbias + 1) * L.Np * 4 - 64;
+      int SA = P.gdn_kblocks + 2; if (SA < 3) SA = 3; if (SA > kMaxStages) SA = kMaxStages;
+      int SB = (budget - SA * P.a_slot_bytes) / bbytes;
+      while (SB < 3 && SA > P.gdn_kblocks + 1 && SA > 2) { --SA; SB = (budget - SA * P.a_slot_bytes) / bbytes; }
+      if (SB > kMaxStages) SB = kMaxStages;
+      if (SB < 2 || SA < P.gdn_kblocks + 1) halo = false;
+      P.SA = SA; P.SB = SB;
+    }
+    if (halo) {
+      P.TW = 8; P.TH = 16; P.TN = 1; P.tw_shift = 3; P.th_shift = 4;
+      P.tiles_x = (L.Wg + 7) / 8; P.tiles_y = (L.Hg + 15) / 16; P.tiles_n = L.Bg;
+      P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
+      P.total_tiles = P.tiles_per_job * P.njobs;
+      for (int t = 0; t < L.ntaps_total; ++t)
+        P.taps[t].halo_off = ((P.taps[t].dy - dymin) * P.RW + (P.taps[t].dx - dxmin)) * 128;
+      for (int j = 0; j < L.njobs; ++j) {
+        int lo = 1 << 30, hi = 0;
+        for (int t = 0; t < P.jobs[j].ntaps; ++t) {
+          const Tap& tp = P.taps[P.jobs[j].tap_begin + t];
+          const int c0 = tp.a_c0 / kBlockK;
+          lo = c0 < lo ? c0 : lo; hi = c0 + tp.nkc > hi ? c0 + tp.nkc : hi;
+        }
+        P.jobs[j].kc0 = lo; P.jobs[j].nchunks = hi - lo;
+      }
+    } else {
+      P.halo = 0;
+    }
+  }
+
   CUtensorMap tmA, tmW, tmG;
   const cuuint64_t C = (cuuint64_t)L.vC;
-  if (L.mode == 1) {
+  if (halo) {
+    cuuint64_t dims[4] = {C, (cuuint64_t)L.vW, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
+    cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)P.RW, (cuuint32_t)P.RH, 1};
+    if ((rc = encode_map(&tmA, x, 4, dims, str, box))) return rc;
+  } else if (L.mode == 1) {
     cuuint64_t dims[5] = {C, 2, (cuuint64_t)L.vW / 2, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
     cuuint64_t str[4] = {C * 2, 2 * C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
     cuuint32_t box[5] = {64, 1, (cuuint32_t)P.TW, 1, 1};
@@ -942,13 +1324,30 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
     tmG = tmW;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  switch (L.Np) {
-    case 64: return launch_conv<64>(tmA, tmW, tmG, P, st);
-    case 128: return launch_conv<128>(tmA, tmW, tmG, P, st);
-    case 192: return launch_conv<192>(tmA, tmW, tmG, P, st);
-    case 256: return launch_conv<256>(tmA, tmW, tmG, P, st);
+  if (halo) {
+    switch (L.Np) {
+      case 64: return launch_halo<64>(tmA, tmW, tmG, P, st);
+      case 128: return launch_halo<128>(tmA, tmW, tmG, P, st);
+      case 192: return launch_halo<192>(tmA, tmW, tmG, P, st);
+      case 256: return launch_halo<256>(tmA, tmW, tmG, P, st);
+    }
   }
-  return fail(LDIC_EINVAL, "conv: unsupported Np %d", L.Np);
+  switch (L.Np) {
+    case 64: rc = launch_conv<64>(tmA, tmW, tmG, P, st); break;
+    case 128: rc = launch_conv<128>(tmA, tmW, tmG, P, st); break;
+    case 192: rc = launch_conv<192>(tmA, tmW, tmG, P, st); break;
+    case 256: rc = launch_conv<256>(tmA, tmW, tmG, P, st); break;
+    default: return fail(LDIC_EINVAL, "conv: unsupported Np %d", L.Np);
+  }
+  if (want_dbg && rc == LDIC_OK) {     // debugging aid only: synchronises
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[ldic timing] kind %d Np %d tiles/cta %llu stages %llu | mma total %llu cyc: wait_full %llu wait_buf %llu wait_x2 %llu "
+            "(per stage: total %.0f wait_full %.0f) | producer total %llu wait_empty %llu\n", d->kind, L.Np, h[5], h[4], h[0], h[1], h[2], h[3],
+            h[4] ? (double)h[0] / h[4] : 0.0, h[4] ? (double)h[1] / h[4] : 0.0, h[8], h[9]);
+  }
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------
