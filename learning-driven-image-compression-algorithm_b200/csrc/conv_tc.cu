@@ -62,6 +62,7 @@ struct ConvParams {
   int stages;
   // halo variant: one (TH+dy range) x (TW+dx range) activation region per 64-channel chunk serves all taps
   int halo, SA, SB, a_slot_bytes, RW, RH, dxmin, dymin;
+  int G;                    // halo: filter taps per B-ring slot (one TMA box of G*Np weight rows)
   int ngroups, Cg;          // accumulator columns = ngroups x Cg
   int sy, sx;               // output pixel = grid pixel * (sy,sx) + job offset (+ sub-pixel group offset)
   int nbias;                // 1, or njobs when every job has its own bias vector
@@ -622,8 +623,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const int SA = P.SA, SB = P.SB;
   const uint32_t a_slot = (uint32_t)P.a_slot_bytes;
+  const int G = P.G;
+  const uint32_t b_slot = (uint32_t)G * kBTileBytes;                  // G taps of weights per slot
   const uint32_t b_base = smem_base + (uint32_t)SA * a_slot;
-  uint8_t* aux = smem_al + (size_t)SA * a_slot + (size_t)SB * kBTileBytes;
+  uint8_t* aux = smem_al + (size_t)SA * a_slot + (size_t)SB * b_slot;
   uint64_t* afull = reinterpret_cast<uint64_t*>(aux);                  // [kMaxStages]
   uint64_t* aempty = afull + kMaxStages;
   uint64_t* bfull = aempty + kMaxStages;
@@ -710,7 +713,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (elect_one()) {
             mbar_expect_tx(&bfull[sb], kBTileBytes);
-            tma_load_2d(b_base + sb * kBTileBytes, &tmG, &bfull[sb], kb * kBlockK, 0);
+            tma_load_2d(b_base + sb * b_slot, &tmG, &bfull[sb], kb * kBlockK, 0);
           }
           adv();
         }
@@ -722,14 +725,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int ci = 0; ci < jb.nchunks; ++ci) {
           if (ci == jins) load_gamma();
           const int kc = jb.kc0 + ci;
-          for (int tp = 0; tp < jb.ntaps; ++tp) {
+          for (int tp = 0; tp < jb.ntaps; tp += G) {          // G == 1 unless every tap covers every chunk
             const Tap tap = P.taps[jb.tap_begin + tp];
             if (!tap_active(tap, kc)) continue;
             mbar_wait(&bempty[sb], pb ^ 1);
             __syncwarp();
             if (elect_one()) {
-              mbar_expect_tx(&bfull[sb], kBTileBytes);
-              tma_load_2d(b_base + sb * kBTileBytes, &tmW, &bfull[sb], tap.b_c0 + kc * kBlockK - tap.a_c0,
+              mbar_expect_tx(&bfull[sb], b_slot);               // the box always spans G*Np rows (zero fill past the end)
+              tma_load_2d(b_base + sb * b_slot, &tmW, &bfull[sb], tap.b_c0 + kc * kBlockK - tap.a_c0,
                           (jb.tap_begin + tp) * NP);
             }
             adv();
@@ -753,7 +756,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&bfull[sb], pb);
           tc_fence_after();
           __syncwarp();
-          const uint32_t alo = desc_lo(smem_base + sa * a_slot), blo = desc_lo(b_base + sb * kBTileBytes);
+          const uint32_t alo = desc_lo(smem_base + sa * a_slot), blo = desc_lo(b_base + sb * b_slot);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
@@ -779,17 +782,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int kc = jb.kc0 + ci;
           mbar_wait(&afull[sa], pa);
           const uint32_t a_addr = smem_base + sa * a_slot;
-          for (int tp = 0; tp < jb.ntaps; ++tp) {
-            const Tap tap = P.taps[jb.tap_begin + tp];
-            if (!tap_active(tap, kc)) continue;
+          for (int tp = 0; tp < jb.ntaps; tp += G) {
+            if (!tap_active(P.taps[jb.tap_begin + tp], kc)) continue;
             mbar_wait(&bfull[sb], pb);
             tc_fence_after();
             __syncwarp();
-            const uint32_t alo = desc_lo(a_addr + tap.halo_off), blo = desc_lo(b_base + sb * kBTileBytes);
+            const int ng = (jb.ntaps - tp < G) ? jb.ntaps - tp : G;
+            const uint32_t bslot_lo = desc_lo(b_base + sb * b_slot);
+            uint32_t alo[4];                                   // computed warp-uniformly, outside the elected branch
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              alo[g] = (g < ng) ? desc_lo(a_addr + P.taps[jb.tap_begin + tp + g].halo_off) : 0u;
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_bf16_lh(tmem_base + bsel * kBufCols, alo + 2 * k, hi_a, blo + 2 * k, hi_b, kIdesc, !(first && k == 0));
+              for (int g = 0; g < 4; ++g) {
+                if (g < ng) {
+                  const uint32_t blo = bslot_lo + (uint32_t)g * (kBTileBytes >> 4);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16_lh(tmem_base + bsel * kBufCols, alo[g] + 2 * k, hi_a, blo + 2 * k, hi_b, kIdesc,
+                                 !(first && g == 0 && k == 0));
+                }
+              }
               tc_commit(&bempty[sb]);
             }
             first = false;
@@ -1098,7 +1112,7 @@ int launch_conv(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g
 
 template <int NP>
 int launch_halo(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
-  const size_t smem = (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * NP * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
+  const size_t smem = (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * NP * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
                       (size_t)(P.nbias + 1) * NP * sizeof(float) + 64;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1261,7 +1275,14 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
       P.halo = 1; P.dxmin = dxmin; P.dymin = dymin;
       P.RW = 8 + dxmax - dxmin; P.RH = 16 + dymax - dymin;
       P.a_slot_bytes = (P.RW * P.RH * 128 + 1023) / 1024 * 1024;
-      const int bbytes = L.Np * kBlockK * 2;
+      // taps per B slot: one TMA box holds up to 256 weight rows; only when every tap covers every chunk
+      bool uniform = true;
+      for (int t = 0; t < L.ntaps_total; ++t) uniform = uniform && L.taps[t].a_c0 == 0 && L.taps[t].nkc == L.taps[0].nkc;
+      P.G = uniform ? 256 / L.Np : 1;
+      if (P.G > 4) P.G = 4;
+      if (P.G < 1) P.G = 1;
+      if (const char* e = getenv("LDIC_HALO_G")) { int g = atoi(e); if (g >= 1 && g <= P.G) P.G = g; }     // tuning aid
+      const int bbytes = P.G * L.Np * kBlockK * 2;
       const int budget = 227 * 1024 - 1024 - 512 - (L.nbias + 1) * L.Np * 4 - 64;
       int SA = P.gdn_kblocks + 2; if (SA < 3) SA = 3; if (SA > kMaxStages) SA = kMaxStages;
       int SB = (budget - SA * P.a_slot_bytes) / bbytes;
@@ -1312,7 +1333,7 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.ntaps_total * L.Np};
     cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
+    cuuint32_t box[2] = {64, (cuuint32_t)(L.Np * (halo ? P.G : 1))};
     if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
   }
   if (gdn) {
