@@ -162,7 +162,11 @@ enum {
   LDIC_CTX_CONV1 = 8,  /* x [B,h,w, round(y)(N) | h2(N)] bf16 -> [B*h*w,4,4,N]; aux0=N, aux1=M; Conv2d(2N-M,N,3,1,1) :295 */
   LDIC_CTX_CONV2 = 9,  /* [P,4,4,N] -> [P,2,2,N]   Conv2d(N,N,3,2,1)  :297                                           */
   LDIC_CTX_CONV3 = 10, /* [P,2,2,N] -> [P,2,2,N]   Conv2d(N,N,3,1,1)  :299                                           */
-  LDIC_CTX_FC = 11     /* [P,2,2,N] -> [P,1,2,Cout_pad] fp32 (mu | log sigma), Linear(4N, 2*Cout) :302; Cout = N-M   */
+  LDIC_CTX_FC = 11,    /* [P,2,2,N] -> [P,1,2,Cout_pad] fp32 (mu | log sigma), Linear(4N, 2*Cout) :302; Cout = N-M   */
+  /* First analysis layer fused with its GDN: x is the NCHW fp32 IMAGE (B,3,H,W) itself (not NHWC bf16);
+   * ZeroPad2d((1,2,1,2)) + Conv2d(3,Cout,5,2) (+GDN) -> NHWC bf16, no patch matrix in HBM.  Cin = 3,
+   * Cin_pad = 128 (K = 75 padded), Cout_pad <= 192.  model/net.py:97-99.                          */
+  LDIC_CONV_FIRST_5x5S2 = 12
 };
 enum { LDIC_ACT_NONE = 0, LDIC_ACT_RELU = 1, LDIC_ACT_LEAKY02 = 2, LDIC_ACT_GDN = 3, LDIC_ACT_IGDN = 4 };
 
@@ -200,6 +204,12 @@ LDIC_API int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void*
  * cannot reach; not used by the product forward).                               */
 LDIC_API int ldic_conv_forward_f32_reference_kernel(const LdicConvDesc* d, const float* x_nhwc, const float* w,
                                            const float* bias, float* y_nhwc, void* stream);
+
+/* Diagnostics: every in-kernel barrier wait of the conv kernels is bounded; a starved wait records
+ * {flag, block, thread, barrier byte offset in dynamic shared memory, parity} in host-mapped memory and
+ * traps.  Returns 1 and fills out5 when a timeout has been recorded in this process, else 0 (host call,
+ * valid even after the CUDA context reported the error).                                           */
+LDIC_API int ldic_debug_last_timeout(unsigned long long* out5);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,7 @@ LDIC_CTX_CONV1 = 8
 LDIC_CTX_CONV2 = 9
 LDIC_CTX_CONV3 = 10
 LDIC_CTX_FC = 11
+LDIC_CONV_FIRST_5x5S2 = 12
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_GDN, ACT_IGDN = 0, 1, 2, 3, 4
 
 
@@ -85,6 +86,7 @@ _SIGS = {
     "ldic_conv_out_shape": (None, [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ldic_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "ldic_debug_last_timeout": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "ldic_conv_forward_f32_reference_kernel": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                                          C.c_void_p, C.c_void_p]),
 }
@@ -93,7 +95,8 @@ EXPORTED_SYMBOLS = tuple(_SIGS.keys())
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # LDIC_LIB_PATH: A/B aid (load another build of the same C ABI); the default is the in-tree library
+    return os.environ.get("LDIC_LIB_PATH") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = False):
@@ -111,6 +114,8 @@ def load(build_if_missing: bool = False):
                             "There is no CPU/torch fallback.")
     lib = C.CDLL(path)
     for name, (res, args) in _SIGS.items():
+        if not hasattr(lib, name) and os.environ.get("LDIC_LIB_PATH"):
+            continue                                  # older A/B build without the newest entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -100,17 +100,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.  Before trapping, the waiter
+// records {block, thread, barrier offset in dynamic smem, parity} in host-mapped memory so that the host can
+// still read which barrier starved after the context is lost (ldic_debug_last_timeout).
+__device__ unsigned long long* g_timeout_report = nullptr;
+__device__ __forceinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+  extern __shared__ uint8_t smem_raw[];
+  unsigned long long* r = g_timeout_report;
+  if (r && atomicCAS(r, 0ull, 1ull) == 0ull) {
+    r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = bar_addr - smem_u32(smem_raw); r[4] = parity;
+    __threadfence_system();
+  }
+  printf("ldic conv_tc: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar_addr, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("ldic conv_tc: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
-    }
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(smem_u32(bar), parity);
   }
 }
 
@@ -463,19 +472,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // warpgroup 2 hands registers to the epilogue
   if (warp == kProdWarp) {
     // ===================== TMA producer =====================
-    // The whole warp runs the loop with warp-uniform values (so addresses / coordinates live in
-    // uniform registers and the TMA instructions issue without per-lane serialisation); one elected
-    // lane arms the barrier and issues the copies.
+    // Warp-uniform loop, lane 0 arms the barrier and issues the copies.  The filter taps of the tile's
+    // job live in registers (lane t holds tap t) and are broadcast with shuffles, so the loop body has
+    // no constant-bank loads with computed indices.
     {
       uint32_t slot = 0, ph = 0;                              // ring position and pass parity
-      const bool pdbg = P.dbg != nullptr && blockIdx.x == 0;
-      long long t_empty = 0;
-      const long long tp_begin = clock64();
-      auto advance = [&]() { if (++slot == (uint32_t)stages) { slot = 0; ph ^= 1; } };
+      int stages_r = stages;
+      asm volatile("" : "+r"(stages_r));                      // keep the ring size in a register
+      auto advance = [&]() { if (++slot == (uint32_t)stages_r) { slot = 0; ph ^= 1; } };
       auto load_gamma = [&]() {
         for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring
           mbar_wait(&empty_bar[slot], ph ^ 1);
-          __syncwarp();
           if (elect_one()) {
             mbar_expect_tx(&full_bar[slot], kBTileBytes);
             tma_load_2d(smem_base + slot * kStageBytes + kATileBytes, &tmG, &full_bar[slot], kb * kBlockK, 0);
@@ -483,33 +490,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           advance();
         }
       };
-      const int th = P.TH, tw128 = P.TW * 128;
+      const int th = P.TH, tw128 = P.TW * 128, mode = P.mode;
+      const int cs = mode == 2 ? 2 : 1;                       // input pixels per tile pixel (strided TMA box)
+      int cur_job = -1, ntaps = 0, tap_begin = 0, nkb = 0;
+      uint32_t my_w0 = 0, my_w1 = 0;                          // lane t: tap t of the current job, packed
       for (int it = 0; it < ntiles_cta; ++it) {
         const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        const Job jb = P.jobs[tc.job];
-        const int jins = (gk && it > 0) ? (jb.nkb < kGdnInsert ? jb.nkb : kGdnInsert) : -1;
+        if (tc.job != cur_job) {
+          cur_job = tc.job;
+          ntaps = P.jobs[cur_job].ntaps; tap_begin = P.jobs[cur_job].tap_begin; nkb = P.jobs[cur_job].nkb;
+          if (lane < ntaps) {
+            const Tap t = P.taps[tap_begin + lane];
+            my_w0 = (uint32_t)(uint8_t)t.dx | ((uint32_t)(uint8_t)t.dy << 8) | ((uint32_t)t.px << 16) | ((uint32_t)t.nkc << 24);
+            my_w1 = (uint32_t)t.a_c0 | ((uint32_t)t.b_c0 << 16);
+          }
+        }
+        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int x0 = tc.x0 * cs, y0 = tc.y0 * cs;
         int cb = 0;
-        for (int tp = 0; tp < jb.ntaps; ++tp) {
-          const Tap tap = P.taps[jb.tap_begin + tp];
-          const int brow = (jb.tap_begin + tp) * NP;
-          for (int kc = 0; kc < tap.nkc; ++kc, ++cb) {
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const uint32_t w0 = __shfl_sync(0xffffffffu, my_w0, tp), w1 = __shfl_sync(0xffffffffu, my_w1, tp);
+          const int dx = (int)(int8_t)(w0 & 0xff), dy = (int)(int8_t)((w0 >> 8) & 0xff), px = (int)((w0 >> 16) & 0xff);
+          const int nkc = (int)(w0 >> 24), a_c0 = (int)(w1 & 0xffff), b_c0 = (int)(w1 >> 16);
+          const int brow = (tap_begin + tp) * NP;
+          for (int kc = 0; kc < nkc; ++kc, ++cb) {
             if (cb == jins) load_gamma();
             const uint32_t a_dst = smem_base + slot * kStageBytes;
-            long long t0 = 0;
-            if (pdbg) t0 = clock64();
             mbar_wait(&empty_bar[slot], ph ^ 1);
-            if (pdbg) t_empty += clock64() - t0;
-            __syncwarp();
             if (elect_one()) {
               mbar_expect_tx(&full_bar[slot], kStageBytes);
-              if (P.mode == 1) {
+              if (mode == 1) {
                 for (int j = 0; j < th; ++j)
-                  tma_load_5d(a_dst + j * tw128, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tap.px,
-                              tc.x0 + tap.dx, 2 * (tc.y0 + j) + tap.dy, tc.n0);
+                  tma_load_5d(a_dst + j * tw128, &tmA, &full_bar[slot], a_c0 + kc * kBlockK, px,
+                              tc.x0 + dx, 2 * (tc.y0 + j) + dy, tc.n0);
               } else {
-                tma_load_4d(a_dst, &tmA, &full_bar[slot], tap.a_c0 + kc * kBlockK, tc.x0 + tap.dx, tc.y0 + tap.dy, tc.n0);
+                tma_load_4d(a_dst, &tmA, &full_bar[slot], a_c0 + kc * kBlockK, x0 + dx, y0 + dy, tc.n0);
               }
-              tma_load_2d(a_dst + kATileBytes, &tmW, &full_bar[slot], tap.b_c0 + kc * kBlockK, brow);
+              tma_load_2d(a_dst + kATileBytes, &tmW, &full_bar[slot], b_c0 + kc * kBlockK, brow);
             }
             advance();
           }
@@ -517,32 +534,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (cb == jins) load_gamma();
       }
       if (gk) load_gamma();                                   // contraction of the last tile
-      if (pdbg && lane == 0) { P.dbg[8] = (unsigned long long)(clock64() - tp_begin); P.dbg[9] = (unsigned long long)t_empty; }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    // ===================== MMA issuer (warp-uniform loop, lane 0 issues) =====================
     {
       uint32_t slot = 0, ph = 0;
+      int stages_r = stages;
+      asm volatile("" : "+r"(stages_r));
       const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
       long long t_full = 0, t_buf = 0, t_x2 = 0, n_st = 0;
       const long long t_begin = clock64();
       const uint32_t hi = desc_hi(1024);
+      const uint32_t a_lo0 = desc_lo(smem_base), b_lo0 = desc_lo(smem_base + kATileBytes);
+      uint32_t slot_lo = 0;                                  // slot * (kStageBytes >> 4)
       auto mma_stage = [&](uint32_t d_tmem, bool first) {
         long long t0 = 0;
         if (dbg) t0 = clock64();
         mbar_wait(&full_bar[slot], ph);
         if (dbg) { t_full += clock64() - t0; ++n_st; }
         tc_fence_after();
-        __syncwarp();
-        const uint32_t a_addr = smem_base + slot * kStageBytes;
-        const uint32_t alo = desc_lo(a_addr), blo = desc_lo(a_addr + kATileBytes);
         if (elect_one()) {
+          const uint32_t alo = a_lo0 + slot_lo, blo = b_lo0 + slot_lo;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_bf16_lh(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, kIdesc, !(first && k == 0));
           tc_commit(&empty_bar[slot]);                       // frees the smem slot when these MMAs retire
         }
-        if (++slot == (uint32_t)stages) { slot = 0; ph ^= 1; }
+        ++slot; slot_lo += (uint32_t)(kStageBytes >> 4);
+        if (slot == (uint32_t)stages_r) { slot = 0; slot_lo = 0; ph ^= 1; }
       };
       auto gdn_of = [&](int j) {                             // norm(j) = x^2 . gamma^T, in place over acc(j)
         const int bsel = j & 1;
@@ -552,12 +571,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (dbg) t_x2 += clock64() - t0;
         tc_fence_after();
         for (int kb = 0; kb < gk; ++kb) mma_stage(tmem_base + bsel * kBufCols, kb == 0);
-        __syncwarp();
         if (elect_one()) tc_commit(&norm_full[bsel]);
       };
+      int cur_job = -1, nkb = 0;
       for (int it = 0; it < ntiles_cta; ++it) {
         const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        const int nkb = P.jobs[tc.job].nkb;
+        if (tc.job != cur_job) { cur_job = tc.job; nkb = P.jobs[cur_job].nkb; }
         const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
         const int bsel = it & 1;
         long long t0 = 0;
@@ -569,7 +588,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (kb == jins) gdn_of(it - 1);
           mma_stage(tmem_base + bsel * kBufCols, kb == 0);
         }
-        __syncwarp();
         if (elect_one()) tc_commit(&acc_full[bsel]);
         if (nkb == jins) gdn_of(it - 1);
       }
@@ -670,6 +688,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sbo = (uint32_t)P.RW * 128u;
   // a tap contributes to channel chunk kc iff its K range covers it
   auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
+  // a tap contributes to channel chunk kc iff its K range covers it
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -838,6 +857,228 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------
+// First analysis layer (Cin = 3): ZeroPad2d((1,2,1,2)) + Conv2d(3, NP, 5, 2) + GDN straight from the
+// NCHW fp32 image (model/net.py:97-99).  No patch matrix in HBM: per tile of 64 x 2 output pixels
+//   warp 8        TMA: one (136 x 7 x 3) fp32 box of the image into a 2-deep raw ring (out-of-image
+//                 reads are zero-filled = the ZeroPad2d); once per CTA: both K blocks of the packed
+//                 weights and the whole gamma matrix, which stay RESIDENT in shared memory
+//   warps 10,11   patch builders: each thread turns two pixels' 5x5x3 windows into bf16 rows of the
+//                 K-major, 128B-swizzled A operand (K = 75 padded to 80: one 64-wide block + one
+//                 16-wide MMA step of a second block)
+//   warp 9        MMA issuer: 5 K steps of conv, then the GDN contraction of the previous tile
+//   warps 0..7    the common epilogue (x^2 operand tiles go into the same 16 KB ring as the A tiles)
+// Ring order (identical in all roles): [A0 A1](tile 0) [A0 A1](1) [x^2 x gk](0) [A0 A1](2) [x^2 x gk](1) ...
+// ---------------------------------------------------------------------------------
+constexpr int kFirstTW = 64, kFirstTH = 2;
+constexpr int kRawX0 = 4;                           // the box starts 4 columns left of the tile (TMA needs a 16-byte
+                                                    // aligned start in the innermost dimension; only 1 column is padding)
+constexpr int kRawW = 2 * kFirstTW + 4 + kRawX0;    // 136 input columns per box (131 used), 544-byte rows
+constexpr int kRawH = 2 * kFirstTH + 3;             // 7 input rows
+constexpr int kRawBytes = 3 * kRawH * kRawW * 4;    // 11088
+constexpr int kRawSlot = (kRawBytes + 127) / 128 * 128;
+constexpr int kFirstK = 75;
+constexpr int kBuildThreads = 64;                   // warps 10 and 11
+
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
+  constexpr int kBTileBytes = NP * kBlockK * 2;
+  constexpr int GK = NP / 64;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int S = P.stages;                                              // 16 KB ring slots
+  const uint32_t w_base = smem_base;                                   // 2 K blocks of weights
+  const uint32_t g_base = w_base + 2 * kBTileBytes;                    // GK K blocks of gamma
+  const uint32_t ring_base = g_base + GK * kBTileBytes;
+  const uint32_t raw_base = ring_base + (uint32_t)S * kATileBytes;
+  uint8_t* aux = smem_al + (size_t)(2 + GK) * kBTileBytes + (size_t)S * kATileBytes + 2 * kRawSlot;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);               // [kMaxStages] builders -> MMA
+  uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages] MMA -> builders / epilogue
+  uint64_t* acc_full = empty_bar + kMaxStages;                         // [2]
+  uint64_t* buf_free = acc_full + 2;
+  uint64_t* x2_ready = buf_free + 2;
+  uint64_t* norm_full = x2_ready + 2;
+  uint64_t* rfull = norm_full + 2;                                     // [2] TMA -> builders
+  uint64_t* rempty = rfull + 2;                                        // [2] builders -> TMA
+  uint64_t* wfull = rempty + 2;                                        // [1] resident weights + gamma landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* s_bias = reinterpret_cast<float*>(aux + 256);
+  float* s_beta = s_bias + NP;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
+  const int gk = gdn ? GK : 0;
+  const int per_tile = 2 + gk;                                         // ring slots per tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kBuildThreads); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&buf_free[i], kEpiThreads);
+      mbar_init(&x2_ready[i], kEpiThreads);
+      mbar_init(&norm_full[i], 1);
+      mbar_init(&rfull[i], 1);
+      mbar_init(&rempty[i], kBuildThreads);
+    }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW);
+    if (gdn) prefetch_tmap(&tmG);
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
+  for (int i = threadIdx.x; i < NP; i += kThreads) {
+    s_bias[i] = P.bias ? P.bias[i] : 0.f;
+    s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // ring position of tile it's first A slot
+  auto base_pos = [&](int it) -> uint32_t { return it == 0 ? 0u : (uint32_t)(2 + per_tile * (it - 1)); };
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == kProdWarp) {
+      // ===================== TMA: resident operands once, then the raw image boxes =====================
+      if (elect_one()) {
+        mbar_expect_tx(wfull, (uint32_t)(2 + gk) * kBTileBytes);
+        tma_load_2d(w_base, &tmW, wfull, 0, 0);
+        tma_load_2d(w_base + kBTileBytes, &tmW, wfull, kBlockK, 0);
+        for (int kb = 0; kb < gk; ++kb) tma_load_2d(g_base + kb * kBTileBytes, &tmG, wfull, kb * kBlockK, 0);
+      }
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+        const int rs = it & 1;
+        mbar_wait(&rempty[rs], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&rfull[rs], kRawBytes);
+          // x start 4 columns left of the tile: TMA needs a 16-byte aligned start in the innermost dimension
+          tma_load_4d(raw_base + rs * kRawSlot, &tmX, &rfull[rs], 2 * tc.x0 - kRawX0, 2 * tc.y0 - 1, 0, tc.n0);
+        }
+      }
+    } else if (warp == kMmaWarp) {
+      // ===================== MMA issuer =====================
+      const uint32_t hi = desc_hi(1024);
+      const uint32_t ring_lo = desc_lo(ring_base), w_lo = desc_lo(w_base), g_lo = desc_lo(g_base);
+      uint32_t slot = 0, ph = 0;
+      auto adv = [&]() { if (++slot == (uint32_t)S) { slot = 0; ph ^= 1; } };
+      auto gdn_of = [&](int j) {
+        const int bsel = j & 1;
+        mbar_wait(&x2_ready[bsel], (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        for (int kb = 0; kb < gk; ++kb) {
+          if (elect_one()) {
+            const uint32_t alo = ring_lo + slot * (kATileBytes >> 4), blo = g_lo + kb * (kBTileBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16_lh(tmem_base + bsel * kBufCols, alo + 2 * k, hi, blo + 2 * k, hi, kIdesc, (kb | k) != 0);
+            tc_commit(&empty_bar[slot]);
+          }
+          adv();
+        }
+        if (elect_one()) tc_commit(&norm_full[bsel]);
+      };
+      mbar_wait(wfull, 0);
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const int bsel = it & 1;
+        const uint32_t d_tmem = tmem_base + bsel * kBufCols;
+        mbar_wait(&buf_free[bsel], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        // K block 0: 64 patch values, K block 1: 16 (11 real + zero padding) -> one K step
+        mbar_wait(&full_bar[slot], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t alo = ring_lo + slot * (kATileBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) umma_bf16_lh(d_tmem, alo + 2 * k, hi, w_lo + 2 * k, hi, kIdesc, k != 0);
+          tc_commit(&empty_bar[slot]);
+        }
+        adv();
+        mbar_wait(&full_bar[slot], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t alo = ring_lo + slot * (kATileBytes >> 4);
+          umma_bf16_lh(d_tmem, alo, hi, w_lo + (kBTileBytes >> 4), hi, kIdesc, 1u);
+          tc_commit(&empty_bar[slot]);
+          tc_commit(&acc_full[bsel]);
+        }
+        adv();
+        if (gk && it > 0) gdn_of(it - 1);
+      }
+      if (gk) gdn_of(ntiles_cta - 1);
+    } else {
+      // ===================== patch builders (warps 10, 11) =====================
+      const int tb = (int)threadIdx.x - 32 * kProdBWarp;                // 0..63 = pixel x inside the tile
+      for (int it = 0; it < ntiles_cta; ++it) {
+        const int rs = it & 1;
+        const uint32_t p0 = base_pos(it);
+        const uint32_t s0 = p0 % (uint32_t)S, s1 = (p0 + 1) % (uint32_t)S;
+        mbar_wait(&rfull[rs], (uint32_t)(it >> 1) & 1u);
+        mbar_wait(&empty_bar[s0], ((p0 / (uint32_t)S) & 1u) ^ 1u);
+        mbar_wait(&empty_bar[s1], (((p0 + 1) / (uint32_t)S) & 1u) ^ 1u);
+        const uint32_t a0 = ring_base + s0 * kATileBytes, a1 = ring_base + s1 * kATileBytes;
+        const uint32_t raw = raw_base + rs * kRawSlot;
+#pragma unroll
+        for (int ly = 0; ly < kFirstTH; ++ly) {
+          const int r = ly * kFirstTW + tb;                             // tile row = TMEM lane
+          const uint32_t src = raw + (uint32_t)((2 * ly) * kRawW + 2 * tb + (kRawX0 - 1)) * 4u;
+          const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
+#pragma unroll
+          for (int j = 0; j < 10; ++j) {                                // 16-byte chunks: k = 8j .. 8j+7
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float v[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int k = 8 * j + 2 * e + u;                        // k = (ky*5 + kx)*3 + c
+                v[u] = 0.f;
+                if (k < kFirstK) v[u] = ld_shared_f32(src + (uint32_t)(((k % 3) * kRawH + k / 15) * kRawW + (k / 3) % 5) * 4u);
+              }
+              pk[e] = pack_bf16x2(v[0], v[1]);
+            }
+            const uint32_t dst = (j < 8 ? a0 : a1) + row_off + ((((uint32_t)(j & 7)) ^ rx) << 4);
+            st_shared_v4(dst, pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(&full_bar[s0]);
+        mbar_arrive(&full_bar[s1]);
+        mbar_arrive(&rempty[rs]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    EpiRing R;
+    R.ring_base = ring_base; R.slot_bytes = kATileBytes; R.nslots = (uint32_t)S; R.empty_bar = empty_bar;
+    R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = kGdnInsert;
+    epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // Host side: tap tables, tiling, tensor maps
 // ---------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -857,12 +1098,14 @@ PFN_encodeTiled get_encode() {
 }
 
 int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box) {
+               const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr, bool f32_linear = false) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(LDIC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  if (elem_strides) for (int i = 0; i < rank; ++i) es[i] = elem_strides[i];
+  CUresult r = enc(m, f32_linear ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                   const_cast<void*>(base), dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f32_linear ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(LDIC_ECUDA, "cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,
@@ -946,6 +1189,16 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
     case LDIC_CONV_1x1: {
       L->mode = 0; L->k = 1;
       int t = add_tap(0, 0, 0);
+      L->tap_ky[t][0] = 0; L->tap_kx[t][0] = 0;
+      L->jobs[0] = job(1, 0, 0, 0, 0);
+      break;
+    }
+    case LDIC_CONV_FIRST_5x5S2: {   // x is the NCHW fp32 image; K = (ky*5+kx)*3 + c, 75 padded to 128 in the packed weights
+      if (d->Cin != 3 || d->Cin_pad != 128) return fail(LDIC_EINVAL, "first conv: Cin must be 3 and Cin_pad 128");
+      if ((d->H & 1) || (d->W & 3)) return fail(LDIC_EINVAL, "first conv: H must be even and W a multiple of 4");
+      L->mode = 0; L->k = 5; L->cin_map = 2;
+      L->Ho = d->H / 2; L->Wo = d->W / 2; L->Wg = L->Wo; L->Hg = L->Ho;
+      int t = add_tap(0, 0, 0, 0, 0, 2);
       L->tap_ky[t][0] = 0; L->tap_kx[t][0] = 0;
       L->jobs[0] = job(1, 0, 0, 0, 0);
       break;
@@ -1145,6 +1398,11 @@ __global__ void k_pack_weights(const float* __restrict__ w, const float* __restr
     else ci = kc - T.cin_offset;
     float v = 0.f;
     int ky = T.ky[t][g], kx = T.kx[t][g];
+    if (T.cin_map == 2) {                    // first layer: k = (ky*5 + kx)*Cin + ci
+      const int tap = kc / T.Cin;
+      ci = kc < 25 * T.Cin ? kc - tap * T.Cin : -1;
+      ky = tap / 5; kx = tap - ky * 5;
+    }
     if (ky >= 0 && co < T.Cout && ci >= 0 && ci < T.Cin) {
       const int cot = co + T.co_base[t];
       const int Ctot = T.Cout * T.nbias;     // total logical output channels of the weight tensor
@@ -1162,7 +1420,98 @@ __global__ void k_pack_weights(const float* __restrict__ w, const float* __restr
   }
 }
 
+template <int NP>
+int launch_first(const CUtensorMap& x, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
+  const size_t smem = (size_t)(2 + NP / 64) * NP * kBlockK * 2 + (size_t)P.stages * kATileBytes + 2 * kRawSlot + 256 +
+                      2 * NP * sizeof(float) + 1024 /*align*/;
+  if (smem > 227 * 1024) return fail(LDIC_EINVAL, "first conv: shared memory budget exceeded (%zu)", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDIC_CUDA(cudaFuncSetAttribute(conv_first_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  conv_first_kernel<NP><<<grid, kThreads, smem, st>>>(x, w, g, P);
+  return check_launch("conv_first_kernel");
+}
+
+int forward_first(const LdicConvDesc* d, const Layer& L, const void* x, const void* w_packed, const float* bias_packed,
+                  const void* gamma_bf16, const float* beta_tiled, void* y, cudaStream_t st) {
+  const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
+  if (L.Np > 192) return fail(LDIC_EINVAL, "first conv: at most 192 output channels (weights and gamma stay resident in shared memory)");
+  ConvParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = 0; P.TW = kFirstTW; P.TH = kFirstTH; P.TN = 1; P.tw_shift = 6; P.th_shift = 1;
+  P.tiles_x = (L.Wg + P.TW - 1) / P.TW; P.tiles_y = (L.Hg + P.TH - 1) / P.TH; P.tiles_n = L.Bg;
+  P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n; P.njobs = 1; P.total_tiles = P.tiles_per_job;
+  P.Wg = L.Wg; P.Hg = L.Hg; P.B = L.Bg;
+  P.gdn_kblocks = gdn ? L.Np / 64 : 0;
+  P.act = d->act; P.out_f32 = d->out_f32;
+  P.ngroups = 1; P.Cg = L.Cg; P.sy = P.sx = 1; P.nbias = 1;
+  P.out_sX = L.out_sX; P.out_sY = L.out_sY; P.out_sN = L.out_sN;
+  P.jobs[0] = L.jobs[0];
+  P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
+  const int fixed = (2 + L.Np / 64) * L.Np * kBlockK * 2 + 2 * kRawSlot + 256 + 2 * L.Np * 4 + 1024;
+  int S = (227 * 1024 - fixed) / kATileBytes;
+  if (S > kMaxStages) S = kMaxStages;
+  if (S < P.gdn_kblocks + 2) return fail(LDIC_EINVAL, "first conv: not enough shared memory for the operand ring");
+  P.stages = S;
+  CUtensorMap tmX, tmW, tmG;
+  int rc;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->W, (cuuint64_t)d->H, 3, (cuuint64_t)d->B};
+    cuuint64_t str[3] = {(cuuint64_t)d->W * 4, (cuuint64_t)d->H * d->W * 4, (cuuint64_t)3 * d->H * d->W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kRawW, (cuuint32_t)kRawH, 3, 1};
+    if ((rc = encode_map(&tmX, x, 4, dims, str, box, nullptr, true))) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.Np};
+    cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
+    if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
+  }
+  if (gdn) {
+    cuuint64_t dims[2] = {(cuuint64_t)L.Np, (cuuint64_t)L.Np};
+    cuuint64_t str[1] = {(cuuint64_t)L.Np * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
+    if ((rc = encode_map(&tmG, gamma_bf16, 2, dims, str, box))) return rc;
+  } else {
+    tmG = tmW;
+  }
+  switch (L.Np) {
+    case 64: return launch_first<64>(tmX, tmW, tmG, P, st);
+    case 128: return launch_first<128>(tmX, tmW, tmG, P, st);
+    case 192: return launch_first<192>(tmX, tmW, tmG, P, st);
+  }
+  return fail(LDIC_EINVAL, "first conv: unsupported Np %d", L.Np);
+}
+
+unsigned long long* g_timeout_host = nullptr;
+int ensure_timeout_report() {
+  static bool done = false;
+  if (done) return LDIC_OK;
+  unsigned long long* h = nullptr;
+  unsigned long long* dptr = nullptr;
+  if (cudaHostAlloc((void**)&h, 8 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&dptr, h, 0) != cudaSuccess) {
+    cudaGetLastError();
+    done = true;                      // diagnostics only: run without the report buffer
+    return LDIC_OK;
+  }
+  memset(h, 0, 8 * sizeof(unsigned long long));
+  LDIC_CUDA(cudaMemcpyToSymbol(g_timeout_report, &dptr, sizeof(dptr)));
+  g_timeout_host = h;
+  done = true;
+  return LDIC_OK;
+}
+
 }  // namespace
+
+extern "C" int ldic_debug_last_timeout(unsigned long long* out5) {
+  if (!g_timeout_host || !out5) return 0;
+  for (int i = 0; i < 5; ++i) out5[i] = g_timeout_host[i];
+  return g_timeout_host[0] != 0;
+}
 
 extern "C" int ldic_conv_n_cols(const LdicConvDesc* d) {
   Layer L;
@@ -1221,16 +1570,24 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   if (rc) return rc;
   if (d->B == 0) return LDIC_OK;
   if (!x || !w_packed || !y) return fail(LDIC_EINVAL, "conv: null tensor");
+  if ((rc = ensure_timeout_report())) return rc;
   const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
   if (gdn && (!gamma_bf16 || !beta_tiled)) return fail(LDIC_EINVAL, "conv: GDN epilogue needs gamma_bf16 and beta_tiled");
   if (gdn && L.njobs > 4) return fail(LDIC_EINVAL, "conv: GDN epilogue is not available for the context layers");
   if ((((uintptr_t)x) & 15) || (((uintptr_t)w_packed) & 15) || (((uintptr_t)y) & 31)) return fail(LDIC_EINVAL, "conv: x / weights must be 16-byte and y 32-byte aligned");
   if (L.Cs % 16) return fail(LDIC_EINVAL, "conv: output channel count must be a multiple of 16");
+  if (d->kind == LDIC_CONV_FIRST_5x5S2)
+    return forward_first(d, L, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, (cudaStream_t)stream);
 
   ConvParams P;
   memset(&P, 0, sizeof(P));
   P.mode = L.mode;
-  choose_tile(L.mode, L.Wg, L.Hg, L.Bg, &P.TW, &P.TH, &P.TN);
+  // stride-2 gathers: one TMA box with element strides (2,2) over (W,H) per stage (mode 2) instead of TH boxes of the
+  // x-parity view (mode 1, kept as a tuning fallback: LDIC_S2_STRIDED=0)
+  bool strided = L.mode == 1;
+  if (const char* e = getenv("LDIC_S2_STRIDED")) strided = strided && atoi(e) != 0;
+  if (strided) P.mode = 2;
+  choose_tile(strided ? 0 : L.mode, L.Wg, L.Hg, L.Bg, &P.TW, &P.TH, &P.TN);
   auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
   P.tw_shift = ilog2(P.TW); P.th_shift = ilog2(P.TH); P.cg_shift = ilog2(L.Cg);
   if (L.ngroups > 1 && ((1 << P.cg_shift) != L.Cg || L.Cg < 8)) return fail(LDIC_EINVAL, "conv: merged deconv needs a power-of-two Cout_pad >= 8");
@@ -1247,6 +1604,7 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   P.out_sX = L.out_sX; P.out_sY = L.out_sY; P.out_sN = L.out_sN;
   for (int j = 0; j < kMaxJobs; ++j) P.jobs[j] = L.jobs[j];
   for (int t = 0; t < kMaxTaps; ++t) P.taps[t] = L.taps[t];
+  if (strided) for (int t = 0; t < L.ntaps_total; ++t) { P.taps[t].dx = (short)(2 * L.taps[t].dx + L.taps[t].px); P.taps[t].px = 0; }
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
   static unsigned long long* dbg_buf = nullptr;
   const bool want_dbg = getenv("LDIC_DEBUG_TIMING") != nullptr;
@@ -1319,6 +1677,12 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
     cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)P.RW, (cuuint32_t)P.RH, 1};
     if ((rc = encode_map(&tmA, x, 4, dims, str, box))) return rc;
+  } else if (strided) {
+    cuuint64_t dims[4] = {C, (cuuint64_t)L.vW, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
+    cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(2 * P.TW), (cuuint32_t)(2 * P.TH), (cuuint32_t)P.TN};
+    cuuint32_t es[4] = {1, 2, 2, 1};
+    if ((rc = encode_map(&tmA, x, 4, dims, str, box, es))) return rc;
   } else if (L.mode == 1) {
     cuuint64_t dims[5] = {C, 2, (cuuint64_t)L.vW / 2, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
     cuuint64_t str[4] = {C * 2, 2 * C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};

@@ -307,6 +307,9 @@ class ConvTC:
         if kind == _lib.LDIC_CONV_1x1:
             w = w.reshape(w.shape[0], -1).contiguous()
             cout, cin = w.shape
+        elif kind == _lib.LDIC_CONV_FIRST_5x5S2:     # (Cout, 3, 5, 5); input is the NCHW fp32 image
+            cout, cin = w.shape[0], w.shape[1]
+            cin_pad = 128
         elif kind == _lib.LDIC_CTX_CONV1:            # (N, 2N-M, 3, 3); aux = (N, M)
             cout, cin = w.shape[0], w.shape[1]
             cin_pad = 2 * self.aux[0]
@@ -387,10 +390,16 @@ class ConvTC:
         return f
 
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _req(x, torch.bfloat16, "x")
-        if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
-            raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
-        B, H, W, _ = x.shape
+        if self.kind == _lib.LDIC_CONV_FIRST_5x5S2:
+            _req(x, torch.float32, "x")
+            if x.dim() != 4 or x.shape[1] != self.cin or not x.is_contiguous():
+                raise LdicError(f"first conv input must be a contiguous NCHW fp32 image with {self.cin} channels, got {tuple(x.shape)}")
+            B, _, H, W = x.shape
+        else:
+            _req(x, torch.bfloat16, "x")
+            if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
+                raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
+            B, H, W, _ = x.shape
         if out is None:
             out = torch.empty(self.out_dims(B, H, W), dtype=torch.float32 if self.out_f32 else torch.bfloat16,
                               device=x.device)

@@ -11,6 +11,8 @@ weight version) on NHWC bf16 activations.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -57,7 +59,15 @@ class analysisTransformModel(_PlannedTransform):
         layers = []
         c1 = t[1]
         self._kp1 = ops._pad64(25 * c1.in_channels)
-        if c1.in_channels * 25 <= 128:
+        self._first_fused = False
+        if (c1.in_channels == 3 and c1.out_channels in (64, 128, 192)
+                and os.environ.get("LDIC_FIRST_FUSED", "1") != "0"):
+            # first layer + GDN straight from the NCHW fp32 image (no patch matrix in HBM)
+            layers.append(ops.ConvTC(_lib.LDIC_CONV_FIRST_5x5S2, c1.weight.detach(), c1.bias.detach(),
+                                     act=_lib.ACT_GDN, gdn=self._gdn_args(t[2])))
+            self._first_im2col = False
+            self._first_fused = True
+        elif c1.in_channels * 25 <= 128:
             # first layer: patch matrix (im2col kernel) + 1x1 GEMM; k = (ky*5+kx)*Cin + ci
             w1 = c1.weight.detach().permute(0, 2, 3, 1).reshape(c1.out_channels, -1).contiguous()
             layers.append(ops.ConvTC(_lib.LDIC_CONV_1x1, w1, c1.bias.detach(), act=_lib.ACT_GDN,
@@ -81,7 +91,9 @@ class analysisTransformModel(_PlannedTransform):
         B, _, H, W = x_nchw.shape
         if H % 16 or W % 16:
             raise ops.LdicError("analysis transform needs H and W to be multiples of 16")
-        if self._first_im2col:
+        if self._first_fused:
+            t = L[0](x_nchw.contiguous())                                    # (B,H/2,W/2,C) bf16 NHWC
+        elif self._first_im2col:
             a = ops.im2col_5x5s2(x_nchw, Kp=self._kp1)                       # (B,H/2,W/2,Kp)
             t = L[0](a.view(1, 1, B * (H // 2) * (W // 2), self._kp1)).view(B, H // 2, W // 2, -1)
         else:

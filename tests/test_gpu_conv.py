@@ -91,6 +91,28 @@ def test_conv_s2_p12(ldic, B, H, W, act):
     close(y16, ref, 1e-2, 1e-3)
 
 
+@pytest.mark.parametrize("B,H,W,C,act", [(2, 16, 24, 192, "gdn"), (1, 64, 200, 192, "gdn"), (3, 6, 8, 128, "none"),
+                                         (1, 130, 132, 64, "gdn")])
+def test_first_layer_fused_from_nchw_image(ldic, B, H, W, C, act):
+    """model/net.py:97-99: ZeroPad2d((1,2,1,2)) + Conv2d(3,C,5,2) + GDN read straight from the NCHW fp32 image
+    (ragged widths: W/2 not a multiple of the 64-pixel tile; H/2 odd)."""
+    L = ldic._lib
+    x, w, b = rnd((B, 3, H, W), 40), rnd((C, 3, 5, 5), 41, 0.2), rnd((C,), 42, 0.1)
+    ref = F.conv2d(F.pad(bf(x), (1, 2, 1, 2)), bf(w), b, stride=2)
+    kw = {}
+    if act == "gdn":
+        bp, gp = gdn_params(C, 43)
+        ref = gdn_oracle_bf16(ref, bp, gp, False)
+        kw = dict(act=L.ACT_GDN, gdn=(bp.cuda(), gp.cuda()) + rp.model_gdn_constants())
+    layer = ldic.ops.ConvTC(L.LDIC_CONV_FIRST_5x5S2, w.cuda(), b.cuda(), out_f32=True, **kw)
+    y = layer(x.cuda()).cpu().permute(0, 3, 1, 2)
+    assert y.shape == ref.shape
+    close(y, ref, 2e-3 if act == "gdn" else 1e-4, 2e-4)
+    layer16 = ldic.ops.ConvTC(L.LDIC_CONV_FIRST_5x5S2, w.cuda(), b.cuda(), out_f32=False, **kw)
+    y16 = layer16(x.cuda()).float().cpu().permute(0, 3, 1, 2)
+    close(y16, ref, 1e-2, 1e-3)
+
+
 def test_conv_s2_p2_and_s1_3x3(ldic):
     L = ldic._lib
     C = 192
