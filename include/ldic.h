@@ -205,6 +205,29 @@ LDIC_API int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void*
 LDIC_API int ldic_conv_forward_f32_reference_kernel(const LdicConvDesc* d, const float* x_nhwc, const float* w,
                                            const float* bias, float* y_nhwc, void* stream);
 
+/* ---- the syntax side branch (SURVEY 8 "items on the forward", f4) -----------------------------------
+ * Syntax_Model (model/net.py:349-375), PredictionModel_Syntax (:378-413) and conv_generator
+ * (:322-343) in five fp32 launches.  Inputs are the NHWC fp32 latent y [B,h,w,N] (the first M
+ * channels are the syntax channels, :712) and the NHWC fp32 h_s output h2 [B,h,w,N].  Weights are the
+ * state-dict tensors as they are (Conv2d: [Cout][Cin][3][3], Linear / 1x1 conv: [out][in]).
+ * Scratch (caller-owned, fp32): sm_ds1 [B,h1,w1,32], sm_ds2 [B,h2,w2,64], ps_ds0 [B,h1,w1,M],
+ * ps_ds1 [B,h2,w2,M] with h1 = (h-1)/2+1, h2 = (h1-1)/2+1 (same for w); pool_part
+ * [ldic_syntax_workspace_elems(B,h,w,N,M)] (partial sums of the six mean pools + re-packed 3x3 weights).
+ * Outputs: z3 [B,M] (Syntax_Model output), z3_round = round(z3) (:753), mu / sigma [B,M] (the two
+ * returns of PredictionModel_Syntax, sigma = exp(.)), conv_w [B,3,M] (per-image 1x1 filters, :805). */
+typedef struct {
+  int B, h, w, N, M;
+  const float* y;
+  const float* h2;
+  const float *sm_down0_w, *sm_down0_b, *sm_down1_w, *sm_down1_b, *sm_conv_w, *sm_conv_b;
+  const float *ps_down0_w, *ps_down0_b, *ps_down1_w, *ps_down1_b, *ps_fc_w, *ps_fc_b;
+  const float *cg_w0, *cg_b0, *cg_w1, *cg_b1, *cg_w2, *cg_b2;
+  float *sm_ds1, *sm_ds2, *ps_ds0, *ps_ds1, *pool_part;
+  float *z3, *z3_round, *mu, *sigma, *conv_w;
+} LdicSyntaxArgs;
+LDIC_API long long ldic_syntax_workspace_elems(int B, int h, int w, int N, int M);
+LDIC_API int ldic_syntax_branch(const LdicSyntaxArgs* args, void* stream);
+
 /* Diagnostics: every in-kernel barrier wait of the conv kernels is bounded; a starved wait records
  * {flag, block, thread, barrier byte offset in dynamic shared memory, parity} in host-mapped memory and
  * traps.  Returns 1 and fills out5 when a timeout has been recorded in this process, else 0 (host call,

@@ -53,6 +53,17 @@ class ConvDesc(C.Structure):
                 ("out_f32", C.c_int), ("aux0", C.c_int), ("aux1", C.c_int)]
 
 
+class SyntaxArgs(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("B", "h", "w", "N", "M")] +
+                [(n, C.c_void_p) for n in (
+                    "y", "h2",
+                    "sm_down0_w", "sm_down0_b", "sm_down1_w", "sm_down1_b", "sm_conv_w", "sm_conv_b",
+                    "ps_down0_w", "ps_down0_b", "ps_down1_w", "ps_down1_b", "ps_fc_w", "ps_fc_b",
+                    "cg_w0", "cg_b0", "cg_w1", "cg_b1", "cg_w2", "cg_b2",
+                    "sm_ds1", "sm_ds2", "ps_ds0", "ps_ds1", "pool_part",
+                    "z3", "z3_round", "mu", "sigma", "conv_w")])
+
+
 _SIGS = {
     "ldic_version": (C.c_int, []),
     "ldic_last_error": (C.c_char_p, []),
@@ -86,6 +97,8 @@ _SIGS = {
     "ldic_conv_out_shape": (None, [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ldic_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "ldic_syntax_workspace_elems": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ldic_syntax_branch": (C.c_int, [C.POINTER(SyntaxArgs), C.c_void_p]),
     "ldic_debug_last_timeout": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "ldic_conv_forward_f32_reference_kernel": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                                          C.c_void_p, C.c_void_p]),

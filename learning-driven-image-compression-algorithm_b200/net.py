@@ -17,6 +17,7 @@ conv_generator: < 0.1 % of the FLOPs) runs as stock torch ops on the GPU.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -202,6 +203,7 @@ class Net(nn.Module):
         self.prediction_model_syntax = PredictionModel_Syntax(in_dim=N, dim=M, outdim=M * 2)
         self.context_tf32 = True
         self.context_on_torch = False     # True: run the context transform with torch ops (cross-check in tests)
+        self.syntax_on_torch = os.environ.get("LDIC_SYNTAX_FUSED", "1") == "0"   # True: syntax branch as stock torch ops
 
     # -- checkpoint compatibility ---------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -259,21 +261,29 @@ class Net(nn.Module):
 
         y_nchw = y.permute(0, 3, 1, 2)                                              # channels-last view, no copy
         h2_nchw = h2.permute(0, 3, 1, 2)
-        prev_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-        try:
-            # the tiny syntax branch stays in full fp32; only the heavy context transform may use TF32
-            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
-            z3_syntax = self.syntax_model(y_nchw[:, :M])                            # :712-719
-            z3_syntax_rounded = torch.round(z3_syntax)                              # :753
-            y_content_rounded = torch.round(y_nchw[:, M:])                          # :741
-            syn_first, syn_second = self.prediction_model_syntax(z3_syntax_rounded, h2_nchw)   # :789 (mu, sigma) bound swapped
-            conv_w = self.conv_weights_gen(z3_syntax_rounded)                       # :805
-            if self.context_on_torch:      # cross-check path only (tests); the product path is raw_tc
+        if self.syntax_on_torch:
+            # stock torch ops (cross-check path of tests): Syntax_Model, PredictionModel_Syntax, conv_generator
+            prev_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+            try:
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+                z3_syntax = self.syntax_model(y_nchw[:, :M])                        # :712-719
+                z3_syntax_rounded = torch.round(z3_syntax)                          # :753
+                syn_first, syn_second = self.prediction_model_syntax(z3_syntax_rounded, h2_nchw)   # :789 (mu, sigma) bound swapped
+                conv_w = self.conv_weights_gen(z3_syntax_rounded)                   # :805
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        else:
+            z3_syntax, z3_syntax_rounded, syn_first, syn_second, conv_w = ops.syntax_branch(
+                y, h2, M, self.syntax_model, self.prediction_model_syntax, self.conv_weights_gen)       # :712-719,:753,:789,:805
+        if self.context_on_torch:          # cross-check path only (tests); the product path is raw_tc
+            prev_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+            try:
                 torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(self.context_tf32)
+                y_content_rounded = torch.round(y_nchw[:, M:])                      # :741
                 ctx = self.prediction_model.raw(y_content_rounded, h2_nchw)         # :784  (P, 2(N-M))
                 ctx_rs, ctx_sig_off = ctx.shape[1], N - M
-        finally:
-            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 
         Cc = N - M
         if not self.context_on_torch:

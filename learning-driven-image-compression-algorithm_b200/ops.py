@@ -417,6 +417,46 @@ class ConvTC:
         return out
 
 
+def syntax_branch(y: torch.Tensor, h2: torch.Tensor, M: int, syntax_model, prediction_model_syntax, conv_weights_gen):
+    """The syntax side branch on libldic_b200 (ldic_syntax_branch): y, h2 are NHWC fp32 [B,h,w,N].
+    Returns (z3 [B,M,1,1], z3_round, mu, sigma [B,M,1,1], conv_w [B,3,M,1,1])."""
+    _req(y, torch.float32, "y"); _req(h2, torch.float32, "h2")
+    if y.shape != h2.shape or not y.is_contiguous() or not h2.is_contiguous():
+        raise LdicError("syntax_branch: y and h2 must be contiguous NHWC fp32 tensors of the same shape")
+    B, h, w, N = y.shape
+    h1, w1 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    h2s, w2s = (h1 - 1) // 2 + 1, (w1 - 1) // 2 + 1
+    dev = y.device
+    f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+    a = _lib.SyntaxArgs()
+    a.B, a.h, a.w, a.N, a.M = B, h, w, N, M
+    a.y, a.h2 = _ptr(y), _ptr(h2)
+    keep = []
+
+    def P(t):
+        t = _req(t.detach(), torch.float32, "weight").contiguous()
+        keep.append(t)
+        return t.data_ptr()
+    sm, ps, cg = syntax_model, prediction_model_syntax, conv_weights_gen.transform
+    a.sm_down0_w, a.sm_down0_b, a.sm_down1_w, a.sm_down1_b = P(sm.down0.weight), P(sm.down0.bias), P(sm.down1.weight), P(sm.down1.bias)
+    a.sm_conv_w, a.sm_conv_b = P(sm.conv.weight), P(sm.conv.bias)
+    a.ps_down0_w, a.ps_down0_b, a.ps_down1_w, a.ps_down1_b = P(ps.down0.weight), P(ps.down0.bias), P(ps.down1.weight), P(ps.down1.bias)
+    a.ps_fc_w, a.ps_fc_b = P(ps.fc.weight), P(ps.fc.bias)
+    a.cg_w0, a.cg_b0, a.cg_w1, a.cg_b1, a.cg_w2, a.cg_b2 = (P(cg[0].weight), P(cg[0].bias), P(cg[2].weight), P(cg[2].bias),
+                                                            P(cg[4].weight), P(cg[4].bias))
+    if (tuple(sm.down0.weight.shape) != (32, M, 3, 3) or tuple(sm.down1.weight.shape) != (64, 32, 3, 3)
+            or tuple(ps.down0.weight.shape) != (M, N, 3, 3) or tuple(ps.down1.weight.shape) != (M, M, 3, 3)
+            or tuple(ps.fc.weight.shape) != (2 * M, N + 2 * M) or tuple(cg[4].weight.shape) != (3 * M, 256)):
+        raise LdicError("syntax_branch: unexpected module shapes")
+    ds1, ds2, p0, p1 = f(B, h1, w1, 32), f(B, h2s, w2s, 64), f(B, h1, w1, M), f(B, h2s, w2s, M)
+    part = f(int(_L().ldic_syntax_workspace_elems(B, h, w, N, M)))
+    a.sm_ds1, a.sm_ds2, a.ps_ds0, a.ps_ds1, a.pool_part = _ptr(ds1), _ptr(ds2), _ptr(p0), _ptr(p1), _ptr(part)
+    z3, z3r, mu, sg, cw = f(B, M, 1, 1), f(B, M, 1, 1), f(B, M, 1, 1), f(B, M, 1, 1), f(B, 3, M, 1, 1)
+    a.z3, a.z3_round, a.mu, a.sigma, a.conv_w = _ptr(z3), _ptr(z3r), _ptr(mu), _ptr(sg), _ptr(cw)
+    check(_L().ldic_syntax_branch(C.byref(a), _stream()), "ldic_syntax_branch")
+    return z3, z3r, mu, sg, cw
+
+
 def ctx_pack_input(y_round_bf16: torch.Tensor, h2: torch.Tensor) -> torch.Tensor:
     """[B,h,w,N] bf16 (rounded latent) and [B,h,w,N] fp32 (h_s output) -> [B,h,w,2N] bf16."""
     _req(y_round_bf16, torch.bfloat16, "y_round")

@@ -74,6 +74,40 @@ def test_net_512x768_scalars(ldic):
     assert abs(out2["sq_err"][0].item() / out1["sq_err"][0].item() - 1) < 1e-3
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 512, 768), (3, 192, 64)])
+def test_syntax_branch_kernels_vs_torch_modules(ldic, B, H, W):
+    """Syntax_Model / PredictionModel_Syntax / conv_generator (model/net.py:322-413) on ldic_syntax_branch
+    against the same nn.Modules run as stock fp32 torch ops on identical inputs."""
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    g = torch.Generator().manual_seed(5)
+    h, w, N, M = H // 16, W // 16, net.N, net.M
+    y = (torch.randn(B, h, w, N, generator=g) * 1.5).cuda()
+    h2 = (torch.randn(B, h, w, N, generator=g) * 0.8).cuda()
+    z3, z3r, mu, sg, cw = ldic.ops.syntax_branch(y, h2, M, net.syntax_model, net.prediction_model_syntax, net.conv_weights_gen)
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            z3_t = net.syntax_model(y.permute(0, 3, 1, 2)[:, :M])
+            mu_t, sg_t = net.prediction_model_syntax(torch.round(z3_t), h2.permute(0, 3, 1, 2))
+            cw_t = net.conv_weights_gen(z3r)          # same rounded symbols on both sides
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    tol = dict(rtol=2e-5, atol=2e-5)
+    assert z3.shape == z3_t.shape and torch.allclose(z3, z3_t, **tol), (z3 - z3_t).abs().max()
+    assert torch.equal(z3r, torch.round(z3))
+    assert torch.allclose(mu, mu_t.reshape(mu.shape), **tol) and torch.allclose(sg, sg_t.reshape(sg.shape), **tol)
+    assert cw.shape == cw_t.shape and torch.allclose(cw, cw_t, **tol), (cw - cw_t).abs().max()
+    # whole forward: torch-op syntax branch and the kernel branch agree
+    x = dw.make_input(3, B, H, W).cuda()
+    o1 = net.rd_forward(x)
+    net.syntax_on_torch = True
+    o2 = net.rd_forward(x)
+    assert torch.allclose(o1["bits"], o2["bits"], rtol=1e-5)
+    assert (o1["sq_err"] - o2["sq_err"]).abs().max().item() <= 1e-4 * o2["sq_err"].max().item()
+
+
 def test_state_dict_contract(ldic):
     net = ldic.Net((1, 64, 64, 3), (1, 64, 64, 3), False, False)
     sd = dw.make_state_dict(0)
