@@ -31,6 +31,16 @@ UNIT = "images/s"
 H, W = 512, 768
 
 
+def measured_traffic():
+    """dram__bytes_read+write of the roofline kernels from the committed ncu --set full capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["conv_kernels"]["dram_bytes_per_step"]), float(t["likelihood_c5"]["dram_bytes_per_launch"])
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -273,6 +283,7 @@ def run_ours(args):
     lik_gbs = 20.0 * n_el / (lik_ms * 1e-3) / 1e9
     del v, mu, sg, vh, lk
 
+    conv_traffic, lik_traffic = measured_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -281,15 +292,16 @@ def run_ours(args):
                                "(BASELINE configs[1])", "global_batch": world * B, "height": H, "width": W,
                    "weights": "random init (tests/det_weights.py seed 0, gain-boosted)",
                    "l2": f"{NBUF} rotating input batches ({NBUF * in_bytes >> 20} MiB) and ~3 GB of activations per step, both > 126 MB L2",
-                   "context_model": "PredictionModel_Context on conv_tc_kernel (TMA patch gather, SURVEY 8 f1); syntax branch (<0.1% FLOPs) torch ops",
+                   "context_model": "PredictionModel_Context on conv_tc_kernel (TMA patch gather, SURVEY 8 f1); syntax branch on ldic_syntax_branch (fp32 CUDA-core kernels)",
                    "parallelism": f"batch sharded over {world} GPU(s), 1 all-reduce of 5 scalars per step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": float(tt.item()) / args.steps, "wall_ms_per_step": wall_ms / args.steps},
         "gpu_launches": int(n1 - n0),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (g_a/g_s/h_a/h_s convs + fused GDN/IGDN)",
+        "roofline": {"bound": "tensor", "kernel": "conv_first / conv_tc / conv_halo kernels (g_a, g_s, h_a, h_s, context convs + fused GDN/IGDN)",
                      "achieved": achieved_tf, "peak": tc_peak_sus, "unit": "TFLOP/s",
-                     "frac": achieved_tf / tc_peak_sus if tc_peak_sus else None, "traffic": None,
+                     "frac": achieved_tf / tc_peak_sus if tc_peak_sus else None,
+                     "traffic": conv_traffic, "traffic_note": "DRAM bytes of all conv launches of one step (ncu --set full, profiles/r01_traffic.json)",
                      "peak_source": f"{peak_src} bf16_tflops_sustained",
                      "algorithmic_gflop_per_image": conv_flops / 1e9 / (B * args.steps),
                      "conv_ms_per_step": conv_ms / args.steps,
@@ -298,7 +310,7 @@ def run_ours(args):
                      "per_layer_ms_per_step": {k: round(d[0] / args.steps, 4) for k, d in per_layer.items()}},
         "roofline_likelihood": {"bound": "hbm", "kernel": "k_likelihood_fast<1,false> (round + Gaussian likelihood + sum ln L)",
                                 "achieved": lik_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": lik_gbs / hbm_peak,
-                                "traffic": None, "bytes_per_elem": 20, "elems": n_el, "ms": lik_ms,
+                                "traffic": lik_traffic, "bytes_per_elem": 20, "elems": n_el, "ms": lik_ms,
                                 "peak_source": f"{peak_src} hbm_gbs", "workload": "C5-size 16x192x128x128, per-element mu/sigma"},
         "parity": {"bpp": float(bpp.item()), "psnr_db": float(psnr.item())},
     }

@@ -63,6 +63,7 @@ struct ConvParams {
   // halo variant: one (TH+dy range) x (TW+dx range) activation region per 64-channel chunk serves all taps
   int halo, SA, SB, a_slot_bytes, RW, RH, dxmin, dymin;
   int G;                    // halo: filter taps per B-ring slot (one TMA box of G*Np weight rows)
+  int super_per_job;        // CTA-pair kernel: (tiles_per_job + 1) / 2 pairs of adjacent tiles per job
   int ngroups, Cg;          // accumulator columns = ngroups x Cg
   int sy, sx;               // output pixel = grid pixel * (sy,sx) + job offset (+ sub-pixel group offset)
   int nbias;                // 1, or njobs when every job has its own bias vector
@@ -235,6 +236,82 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+
+// ---- thread-block cluster / CTA-pair (cta_group::2) wrappers -----------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {      // arrive on a barrier of any CTA of the cluster
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cl(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cl(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(smem_u32(bar), parity);
+  }
+}
+// TMA loads of a CTA pair: the data lands in the executing CTA, the completion may be signalled on a barrier of
+// either CTA of the pair (mbar = shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t mbar_cl, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(mbar_cl), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t mbar_cl, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(mbar_cl), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 MMA of a CTA pair: each CTA contributes 128 rows of A and half of the B rows; issued by the leader only
+__device__ __forceinline__ void umma_bf16_lh_cg2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------
@@ -255,6 +332,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, int t) {
   return c;
 }
 
+// CTA-pair kernels walk "super tiles": super tile s of a job = tiles 2r and 2r+1 of that job, one per CTA of the pair.
+// A tile index past the end of the job (odd tile count) decodes to image index B: every TMA read of it is
+// zero-filled and every store masked.
+__device__ __forceinline__ TileCoord decode_tile2(const ConvParams& P, int s, int rank) {
+  const int job = s / P.super_per_job;
+  const int t = 2 * (s - job * P.super_per_job) + rank;
+  if (t >= P.tiles_per_job) { TileCoord c; c.job = job; c.n0 = P.B; c.y0 = 0; c.x0 = 0; return c; }
+  return decode_tile(P, job * P.tiles_per_job + t);
+}
+
 // ---------------------------------------------------------------------------------
 // Epilogue role (shared by the streaming and the halo kernels): warps 4..11.
 // ---------------------------------------------------------------------------------
@@ -267,9 +354,13 @@ struct EpiRing {
   const float *s_bias, *s_beta;
   int use_chunks;           // stream length of a tile: jobs[].nchunks (halo) or jobs[].nkb (streaming)
   int insert_after;         // GDN items of tile it-1 ride after this many stream items of tile it
+  // CTA-pair kernels: tiles are super tiles t_first + it * t_stride decoded for `rank`; buf_free / x2_ready live in
+  // the leader CTA and are reached through their shared::cluster addresses
+  int t_first, t_stride, rank;
+  uint32_t buf_free_cl, x2_ready_cl;
 };
 
-template <int NP>
+template <int NP, bool CL = false>
 __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing& R, uint32_t tmem_base, int gk,
                                               int ntiles_cta, int warp, int lane) {
   constexpr int CPT = NP / 2;
@@ -283,7 +374,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
     const bool igdn = (P.act == LDIC_ACT_IGDN);
     uint32_t sbase = 0;                     // ring position of the first stage of tile `it`'s stream
     for (int it = 0; it < ntiles_cta; ++it) {
-      const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+      const TileCoord tc = CL ? decode_tile2(P, R.t_first + it * R.t_stride, R.rank) : decode_tile(P, blockIdx.x + it * gridDim.x);
       const Job jb = P.jobs[tc.job];
       const int bsel = it & 1;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
@@ -298,7 +389,8 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       sbase += (uint32_t)len_this + ((gk && it > 0) ? (uint32_t)gk : 0u);
       uint32_t gpos = sbase;
       if (gk && it + 1 < ntiles_cta) {
-        const Job jn = P.jobs[decode_tile(P, blockIdx.x + (it + 1) * gridDim.x).job];
+        const Job jn = P.jobs[CL ? (R.t_first + (it + 1) * R.t_stride) / P.super_per_job
+                                 : decode_tile(P, blockIdx.x + (it + 1) * gridDim.x).job];
         const int len_next = R.use_chunks ? jn.nchunks : jn.nkb;
         gpos += (uint32_t)(len_next < R.insert_after ? len_next : R.insert_after);
       }
@@ -316,7 +408,9 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         tmem_ld_wait();
       }
       tc_fence_before();
-      if (!gk) mbar_arrive(&R.buf_free[bsel]);   // no GDN: the buffer can take the tile after next right away
+      if (!gk) {                                 // no GDN: the buffer can take the tile after next right away
+        if (CL) mbar_arrive_cluster(R.buf_free_cl + 8u * bsel); else mbar_arrive(&R.buf_free[bsel]);
+      }
 #pragma unroll
       for (int c = 0; c < CPT; c += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(&sb[col0 + c]);
@@ -342,7 +436,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
                        pack_bf16x2(x8[6] * x8[6], x8[7] * x8[7]));
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(&R.x2_ready[bsel]);
+        if (CL) mbar_arrive_cluster(R.x2_ready_cl + 8u * bsel); else mbar_arrive(&R.x2_ready[bsel]);
         mbar_wait(&R.norm_full[bsel], par);
         tc_fence_after();
         // ---- pass 2: out = x * rsqrt(norm + beta)   (IGDN: x * sqrt = x * n * rsqrt(n)) ----
@@ -364,7 +458,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
           }
         }
         tc_fence_before();
-        mbar_arrive(&R.buf_free[bsel]);        // norm drained: the buffer is free for tile it+2
+        if (CL) mbar_arrive_cluster(R.buf_free_cl + 8u * bsel); else mbar_arrive(&R.buf_free[bsel]);   // norm drained: free for tile it+2
       } else if (P.act == LDIC_ACT_RELU) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) xr[c] = fmaxf(xr[c], 0.f);
@@ -853,6 +947,252 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// CTA-pair variant of the halo kernel: two CTAs of a cluster (one SM pair) work on two adjacent tiles with
+// tcgen05.mma.cta_group::2 (M = 256).  Each CTA loads its own activation region but only HALF of every
+// weight / gamma tile (rows rank*Np/2 ..), so the L2 -> SM weight traffic and the shared memory a weight stage
+// occupies are halved (twice the stages in flight for the same bytes).  The leader CTA (rank 0) issues all MMAs;
+// TMA completions of both CTAs land on the leader's "full" barriers, tcgen05.commit multicasts the "empty" /
+// "accumulator ready" arrivals to both CTAs, and the epilogue warps of the peer reach the leader's x2_ready /
+// buf_free barriers through shared::cluster addresses.
+// ---------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
+  constexpr int kBHalfBytes = (NP / 2) * kBlockK * 2;
+  constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int SA = P.SA, SB = P.SB;
+  const uint32_t a_slot = (uint32_t)P.a_slot_bytes;
+  const int G = P.G;
+  const uint32_t b_slot = (uint32_t)G * kBHalfBytes;                  // G taps x half of the weight rows per slot
+  const uint32_t b_base = smem_base + (uint32_t)SA * a_slot;
+  uint8_t* aux = smem_al + (size_t)SA * a_slot + (size_t)SB * b_slot;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(aux);                  // [kMaxStages]  (leader's are the live ones)
+  uint64_t* aempty = afull + kMaxStages;
+  uint64_t* bfull = aempty + kMaxStages;
+  uint64_t* bempty = bfull + kMaxStages;
+  uint64_t* acc_full = bempty + kMaxStages;                            // [2]
+  uint64_t* buf_free = acc_full + 2;                                   // leader only
+  uint64_t* x2_ready = buf_free + 2;                                   // leader only
+  uint64_t* norm_full = x2_ready + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
+  float* s_bias = reinterpret_cast<float*>(aux + 512);
+  float* s_beta = s_bias + NP * P.nbias;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SA; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&buf_free[i], 2 * kEpiThreads);                        // epilogue threads of both CTAs
+      mbar_init(&x2_ready[i], 2 * kEpiThreads);
+      mbar_init(&norm_full[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    if (gdn) prefetch_tmap(&tmG);
+  }
+  if (warp == kMmaWarp) tmem_alloc_cg2(tmem_ptr, kTmemCols);
+  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                                  // both CTAs' barriers are initialised
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int gk = gdn ? P.gdn_kblocks : 0;
+  const int npairs = (int)gridDim.x >> 1, pi = (int)blockIdx.x >> 1;
+  const int total_super = P.super_per_job * P.njobs;
+  const int nt = (total_super - pi + npairs - 1) / npairs;             // super tiles of this pair
+  const uint32_t region_bytes = (uint32_t)(P.RW * P.RH * 128);
+  const uint32_t sbo = (uint32_t)P.RW * 128u;
+  const uint32_t afull_L = mapa_shared(smem_u32(afull), 0), bfull_L = mapa_shared(smem_u32(bfull), 0);
+  auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == kProdWarp) {
+      // ===================== A-region producer (both CTAs: own tile, completion on the leader's barrier) ==========
+      uint32_t sa = 0, pa = 0;
+      auto adv = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
+      auto reserve_gdn = [&]() {            // gk A slots become the x^2 operand tiles of the epilogue warps
+        for (int kb = 0; kb < gk; ++kb) {
+          mbar_wait(&aempty[sa], pa ^ 1);
+          __syncwarp();
+          if (leader && elect_one()) mbar_arrive(&afull[sa]);
+          adv();
+        }
+      };
+      for (int it = 0; it < nt; ++it) {
+        const TileCoord tc = decode_tile2(P, pi + it * npairs, (int)rank);
+        const Job jb = P.jobs[tc.job];
+        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
+        for (int ci = 0; ci < jb.nchunks; ++ci) {
+          if (ci == jins) reserve_gdn();
+          mbar_wait(&aempty[sa], pa ^ 1);
+          __syncwarp();
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&afull[sa], 2 * region_bytes);
+            tma_load_4d_cg2(smem_base + sa * a_slot, &tmA, afull_L + 8u * sa, (jb.kc0 + ci) * kBlockK, tc.x0 + P.dxmin,
+                            tc.y0 + P.dymin, tc.n0);
+          }
+          adv();
+        }
+        if (jb.nchunks == jins) reserve_gdn();
+      }
+      if (gk) reserve_gdn();
+    } else if (warp == kProdBWarp) {
+      // ===================== B producer (both CTAs: half of the weight / gamma rows each) =====================
+      uint32_t sb = 0, pb = 0;
+      const int row_half = (int)rank * (NP / 2);
+      auto adv = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
+      auto load_gamma = [&]() {
+        for (int kb = 0; kb < gk; ++kb) {
+          mbar_wait(&bempty[sb], pb ^ 1);
+          __syncwarp();
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&bfull[sb], 2 * kBHalfBytes);
+            tma_load_2d_cg2(b_base + sb * b_slot, &tmG, bfull_L + 8u * sb, kb * kBlockK, row_half);
+          }
+          adv();
+        }
+      };
+      for (int it = 0; it < nt; ++it) {
+        const int job = (pi + it * npairs) / P.super_per_job;
+        const Job jb = P.jobs[job];
+        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
+        for (int ci = 0; ci < jb.nchunks; ++ci) {
+          if (ci == jins) load_gamma();
+          const int kc = jb.kc0 + ci;
+          for (int tp = 0; tp < jb.ntaps; tp += G) {          // G == 1 unless every tap covers every chunk
+            const Tap tap = P.taps[jb.tap_begin + tp];
+            if (!tap_active(tap, kc)) continue;
+            const int ng = (jb.ntaps - tp < G) ? jb.ntaps - tp : G;
+            mbar_wait(&bempty[sb], pb ^ 1);
+            __syncwarp();
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&bfull[sb], (uint32_t)(2 * ng) * kBHalfBytes);
+              for (int g = 0; g < ng; ++g)
+                tma_load_2d_cg2(b_base + sb * b_slot + (uint32_t)g * kBHalfBytes, &tmW, bfull_L + 8u * sb,
+                                tap.b_c0 + kc * kBlockK - tap.a_c0, (jb.tap_begin + tp + g) * NP + row_half);
+            }
+            adv();
+          }
+        }
+        if (jb.nchunks == jins) load_gamma();
+      }
+      if (gk) load_gamma();
+    } else if (warp == kMmaWarp && leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      const uint32_t hi_a = desc_hi(sbo), hi_b = desc_hi(1024);
+      auto adv_a = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
+      auto adv_b = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
+      auto gdn_of = [&](int j) {            // norm(j) = x^2 . gamma^T, in place over acc(j), both tiles of the pair
+        const int bsel = j & 1;
+        mbar_wait_cl(&x2_ready[bsel], (j >> 1) & 1);
+        tc_fence_after();
+        for (int kb = 0; kb < gk; ++kb) {
+          mbar_wait_cl(&afull[sa], pa);
+          mbar_wait_cl(&bfull[sb], pb);
+          tc_fence_after();
+          __syncwarp();
+          const uint32_t alo = desc_lo(smem_base + sa * a_slot), blo = desc_lo(b_base + sb * b_slot);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16_lh_cg2(tmem_base + bsel * kBufCols, alo + 2 * k, hi_b, blo + 2 * k, hi_b, kIdesc2, (kb | k) != 0);
+            tc_commit_mc(&bempty[sb]);
+            tc_commit_mc(&aempty[sa]);
+          }
+          adv_a(); adv_b();
+        }
+        __syncwarp();
+        if (elect_one()) tc_commit_mc(&norm_full[bsel]);
+      };
+      for (int it = 0; it < nt; ++it) {
+        const int job = (pi + it * npairs) / P.super_per_job;
+        const Job jb = P.jobs[job];
+        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
+        const int bsel = it & 1;
+        mbar_wait_cl(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        bool first = true;
+        for (int ci = 0; ci < jb.nchunks; ++ci) {
+          if (ci == jins) gdn_of(it - 1);
+          const int kc = jb.kc0 + ci;
+          mbar_wait_cl(&afull[sa], pa);
+          const uint32_t a_addr = smem_base + sa * a_slot;
+          for (int tp = 0; tp < jb.ntaps; tp += G) {
+            if (!tap_active(P.taps[jb.tap_begin + tp], kc)) continue;
+            mbar_wait_cl(&bfull[sb], pb);
+            tc_fence_after();
+            __syncwarp();
+            const int ng = (jb.ntaps - tp < G) ? jb.ntaps - tp : G;
+            const uint32_t bslot_lo = desc_lo(b_base + sb * b_slot);
+            uint32_t alo[4];                                   // computed warp-uniformly, outside the elected branch
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              alo[g] = (g < ng) ? desc_lo(a_addr + P.taps[jb.tap_begin + tp + g].halo_off) : 0u;
+            if (elect_one()) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (g < ng) {
+                  const uint32_t blo = bslot_lo + (uint32_t)g * (kBHalfBytes >> 4);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16_lh_cg2(tmem_base + bsel * kBufCols, alo[g] + 2 * k, hi_a, blo + 2 * k, hi_b, kIdesc2,
+                                     !(first && g == 0 && k == 0));
+                }
+              }
+              tc_commit_mc(&bempty[sb]);
+            }
+            first = false;
+            adv_b();
+          }
+          __syncwarp();
+          if (elect_one()) tc_commit_mc(&aempty[sa]);         // both regions consumed by all of their taps
+          adv_a();
+        }
+        __syncwarp();
+        if (elect_one()) tc_commit_mc(&acc_full[bsel]);
+        if (jb.nchunks == jins) gdn_of(it - 1);
+      }
+      if (gk) gdn_of(nt - 1);
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own tile) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    EpiRing R;
+    R.ring_base = smem_base; R.slot_bytes = a_slot; R.nslots = (uint32_t)SA; R.empty_bar = aempty;
+    R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 1; R.insert_after = kHaloInsert;
+    R.t_first = pi; R.t_stride = npairs; R.rank = (int)rank;
+    R.buf_free_cl = mapa_shared(smem_u32(buf_free), 0); R.x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0);
+    epilogue_role<NP, true>(P, R, tmem_base, gk, nt, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // the peer's shared memory and barriers stay alive until both CTAs are done
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
   }
 }
 
@@ -1378,6 +1718,37 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g
   return check_launch("conv_halo_kernel");
 }
 
+template <int NP>
+int launch_halo2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
+  const size_t smem = (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * (NP / 2) * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
+                      (size_t)(P.nbias + 1) * NP * sizeof(float) + 64;
+  static bool attr_set = false;
+  static int max_clusters = 0;
+  if (smem > 227 * 1024) return fail(LDIC_EINVAL, "conv halo2: shared memory budget exceeded (%zu)", smem);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+  if (!attr_set) {
+    LDIC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg.gridDim = dim3(kNumSMs);
+    cfg.dynamicSmemBytes = 227 * 1024 - 1024;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_halo2_kernel<NP>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / 2 - 4; }
+    cfg.dynamicSmemBytes = smem;
+    max_clusters = n < kNumSMs / 2 ? n : kNumSMs / 2;
+    attr_set = true;
+  }
+  const int total_super = P.super_per_job * P.njobs;
+  const int npairs = total_super < max_clusters ? total_super : max_clusters;
+  cfg.gridDim = dim3(2 * npairs);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo2_kernel<NP>, a, w, g, P);
+  if (e != cudaSuccess) return fail(LDIC_ECUDA, "conv_halo2_kernel launch: %s", cudaGetErrorString(e));
+  return check_launch("conv_halo2_kernel");
+}
+
 // generic weight packer: Wp[t][n][k]
 struct PackTable {
   int ntaps, Np, Cg, ngroups, Cin, Cout, Kw, cin_offset, k, transposed, cin_map, map_N, map_M, nbias;
@@ -1619,7 +1990,7 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   if (gdn && stages < P.gdn_kblocks + 1) return fail(LDIC_EINVAL, "conv: not enough pipeline stages for the GDN epilogue");
 
   // ---- halo variant (stride-1 gathers with spatial taps): one region load per 64-channel chunk ----
-  bool halo = false;
+  bool halo = false, pair = false;
   if (L.mode == 0) {
     int dxmin = 0, dxmax = 0, dymin = 0, dymax = 0;
     for (int t = 0; t < L.ntaps_total; ++t) {
@@ -1640,7 +2011,10 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
       if (P.G > 4) P.G = 4;
       if (P.G < 1) P.G = 1;
       if (const char* e = getenv("LDIC_HALO_G")) { int g = atoi(e); if (g >= 1 && g <= P.G) P.G = g; }     // tuning aid
-      const int bbytes = P.G * L.Np * kBlockK * 2;
+      // CTA pairs (cta_group::2): each CTA stages half of the weight rows -> half the bytes per weight stage
+      pair = true;
+      if (const char* e = getenv("LDIC_HALO2")) pair = atoi(e) != 0;                      // tuning aid: LDIC_HALO2=0 = one CTA per tile
+      const int bbytes = P.G * (pair ? L.Np / 2 : L.Np) * kBlockK * 2;
       const int budget = 227 * 1024 - 1024 - 512 - (L.nbias + 1) * L.Np * 4 - 64;
       int SA = P.gdn_kblocks + 2; if (SA < 3) SA = 3; if (SA > kMaxStages) SA = kMaxStages;
       int SB = (budget - SA * P.a_slot_bytes) / bbytes;
@@ -1654,6 +2028,7 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
       P.tiles_x = (L.Wg + 7) / 8; P.tiles_y = (L.Hg + 15) / 16; P.tiles_n = L.Bg;
       P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
       P.total_tiles = P.tiles_per_job * P.njobs;
+      P.super_per_job = (P.tiles_per_job + 1) / 2;
       for (int t = 0; t < L.ntaps_total; ++t)
         P.taps[t].halo_off = ((P.taps[t].dy - dymin) * P.RW + (P.taps[t].dx - dxmin)) * 128;
       for (int j = 0; j < L.njobs; ++j) {
@@ -1697,18 +2072,26 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.ntaps_total * L.Np};
     cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(L.Np * (halo ? P.G : 1))};
+    cuuint32_t box[2] = {64, (cuuint32_t)(halo && pair ? L.Np / 2 : L.Np * (halo ? P.G : 1))};
     if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
   }
   if (gdn) {
     cuuint64_t dims[2] = {(cuuint64_t)L.Np, (cuuint64_t)L.Np};
     cuuint64_t str[1] = {(cuuint64_t)L.Np * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
+    cuuint32_t box[2] = {64, (cuuint32_t)(halo && pair ? L.Np / 2 : L.Np)};
     if ((rc = encode_map(&tmG, gamma_bf16, 2, dims, str, box))) return rc;
   } else {
     tmG = tmW;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (halo && pair) {
+    switch (L.Np) {
+      case 64: return launch_halo2<64>(tmA, tmW, tmG, P, st);
+      case 128: return launch_halo2<128>(tmA, tmW, tmG, P, st);
+      case 192: return launch_halo2<192>(tmA, tmW, tmG, P, st);
+      case 256: return launch_halo2<256>(tmA, tmW, tmG, P, st);
+    }
+  }
   if (halo) {
     switch (L.Np) {
       case 64: return launch_halo<64>(tmA, tmW, tmG, P, st);
