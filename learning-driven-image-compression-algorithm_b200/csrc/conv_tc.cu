@@ -373,6 +373,9 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
     const int xi = r & (P.TW - 1), yi = (r >> P.tw_shift) & (P.TH - 1), ni = r >> (P.tw_shift + P.th_shift);
     const bool igdn = (P.act == LDIC_ACT_IGDN);
     uint32_t sbase = 0;                     // ring position of the first stage of tile `it`'s stream
+    const bool edbg = P.dbg != nullptr && blockIdx.x == 0 && warp == 0;
+    long long e_acc = 0, e_norm = 0, e_slot = 0, e_t0 = 0;
+    const long long e_begin = edbg ? clock64() : 0;
     for (int it = 0; it < ntiles_cta; ++it) {
       const TileCoord tc = CL ? decode_tile2(P, R.t_first + it * R.t_stride, R.rank) : decode_tile(P, blockIdx.x + it * gridDim.x);
       const Job jb = P.jobs[tc.job];
@@ -395,7 +398,9 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         gpos += (uint32_t)(len_next < R.insert_after ? len_next : R.insert_after);
       }
 
+      if (edbg) e_t0 = clock64();
       mbar_wait(&R.acc_full[bsel], par);
+      if (edbg) e_acc += clock64() - e_t0;
       tc_fence_after();
 
       // ---- pass 1: accumulator -> registers (+bias) ----
@@ -419,10 +424,12 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
 
       if (gk) {
         // x^2 -> bf16 -> A slots (K-major, 128B swizzle: 16-byte chunk index XOR (row & 7))
+        if (edbg) e_t0 = clock64();
         for (int kb = 0; kb < gk; ++kb) {
           const uint32_t kc2 = gpos + kb;
           mbar_wait(&R.empty_bar[kc2 % R.nslots], ((kc2 / R.nslots) & 1) ^ 1);
         }
+        if (edbg) e_slot += clock64() - e_t0;
         const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
 #pragma unroll
         for (int j = 0; j < CPT / 8; ++j) {
@@ -437,7 +444,9 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
         if (CL) mbar_arrive_cluster(R.x2_ready_cl + 8u * bsel); else mbar_arrive(&R.x2_ready[bsel]);
+        if (edbg) e_t0 = clock64();
         mbar_wait(&R.norm_full[bsel], par);
+        if (edbg) e_norm += clock64() - e_t0;
         tc_fence_after();
         // ---- pass 2: out = x * rsqrt(norm + beta)   (IGDN: x * sqrt = x * n * rsqrt(n)) ----
 #pragma unroll
@@ -504,6 +513,10 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
           }
         }
       }
+    }
+    if (edbg && lane == 0) {
+      P.dbg[16] = (unsigned long long)(clock64() - e_begin); P.dbg[17] = (unsigned long long)e_acc;
+      P.dbg[18] = (unsigned long long)e_norm; P.dbg[19] = (unsigned long long)e_slot; P.dbg[20] = (unsigned long long)ntiles_cta;
     }
 }
 
@@ -712,6 +725,212 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------
+// CTA-pair variant of the streaming kernel (tcgen05.mma.cta_group::2, M = 256): the two CTAs of a cluster work
+// on two adjacent tiles; each stage holds the CTA's own 128-pixel A tile and HALF of the weight rows, so a stage
+// is 16 KB + Np*64 B instead of 16 KB + Np*128 B (more stages in flight, 30 % less L2 -> SM traffic, half the
+// B-operand shared-memory reads per SM).  Barrier protocol as in conv_halo2_kernel below: TMA completions of
+// both CTAs land on the leader's full barriers, tcgen05.commit multicasts to both CTAs, the peer's epilogue
+// reaches the leader's x2_ready / buf_free barriers through shared::cluster addresses.
+// ---------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
+  constexpr int kBHalfBytes = (NP / 2) * kBlockK * 2;
+  constexpr int kStageBytes = kATileBytes + kBHalfBytes;
+  constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int stages = P.stages;
+  uint8_t* aux = smem_al + (size_t)stages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [kMaxStages]  (leader's are the live ones)
+  uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages]
+  uint64_t* acc_full = empty_bar + kMaxStages;                         // [2]
+  uint64_t* buf_free = acc_full + 2;                                   // leader only
+  uint64_t* x2_ready = buf_free + 2;                                   // leader only
+  uint64_t* norm_full = x2_ready + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
+  float* s_bias = reinterpret_cast<float*>(aux + 256);
+  float* s_beta = s_bias + NP * P.nbias;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&buf_free[i], 2 * kEpiThreads);
+      mbar_init(&x2_ready[i], 2 * kEpiThreads);
+      mbar_init(&norm_full[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    if (gdn) prefetch_tmap(&tmG);
+  }
+  if (warp == kMmaWarp) tmem_alloc_cg2(tmem_ptr, kTmemCols);
+  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int gk = gdn ? P.gdn_kblocks : 0;
+  const int npairs = (int)gridDim.x >> 1, pi = (int)blockIdx.x >> 1;
+  const int total_super = P.super_per_job * P.njobs;
+  const int nt = (total_super - pi + npairs - 1) / npairs;             // super tiles of this pair
+  const uint32_t full_L = mapa_shared(smem_u32(full_bar), 0);
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == kProdWarp) {
+      // ===================== TMA producer (both CTAs) =====================
+      uint32_t slot = 0, ph = 0;
+      int stages_r = stages;
+      asm volatile("" : "+r"(stages_r));
+      const bool pdbg = P.dbg != nullptr && blockIdx.x == 0;
+      long long t_empty = 0, tp0 = 0;
+      const long long tp_begin = clock64();
+      const int row_half = (int)rank * (NP / 2);
+      auto advance = [&]() { if (++slot == (uint32_t)stages_r) { slot = 0; ph ^= 1; } };
+      auto load_gamma = [&]() {
+        for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring (B half only)
+          mbar_wait(&empty_bar[slot], ph ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&full_bar[slot], 2 * kBHalfBytes);
+            tma_load_2d_cg2(smem_base + slot * kStageBytes + kATileBytes, &tmG, full_L + 8u * slot, kb * kBlockK, row_half);
+          }
+          advance();
+        }
+      };
+      const int cs = P.mode == 2 ? 2 : 1;                     // input pixels per tile pixel (strided TMA box)
+      int cur_job = -1, ntaps = 0, tap_begin = 0, nkb = 0;
+      uint32_t my_w0 = 0, my_w1 = 0;                          // lane t: tap t of the current job, packed
+      for (int it = 0; it < nt; ++it) {
+        const TileCoord tc = decode_tile2(P, pi + it * npairs, (int)rank);
+        if (tc.job != cur_job) {
+          cur_job = tc.job;
+          ntaps = P.jobs[cur_job].ntaps; tap_begin = P.jobs[cur_job].tap_begin; nkb = P.jobs[cur_job].nkb;
+          if (lane < ntaps) {
+            const Tap t = P.taps[tap_begin + lane];
+            my_w0 = (uint32_t)(uint8_t)t.dx | ((uint32_t)(uint8_t)t.dy << 8) | ((uint32_t)t.nkc << 24);
+            my_w1 = (uint32_t)t.a_c0 | ((uint32_t)t.b_c0 << 16);
+          }
+        }
+        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int x0 = tc.x0 * cs, y0 = tc.y0 * cs;
+        int cb = 0;
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const uint32_t w0 = __shfl_sync(0xffffffffu, my_w0, tp), w1 = __shfl_sync(0xffffffffu, my_w1, tp);
+          const int dx = (int)(int8_t)(w0 & 0xff), dy = (int)(int8_t)((w0 >> 8) & 0xff);
+          const int nkc = (int)(w0 >> 24), a_c0 = (int)(w1 & 0xffff), b_c0 = (int)(w1 >> 16);
+          const int brow = (tap_begin + tp) * NP + row_half;
+          for (int kc = 0; kc < nkc; ++kc, ++cb) {
+            if (cb == jins) load_gamma();
+            const uint32_t a_dst = smem_base + slot * kStageBytes;
+            if (pdbg) tp0 = clock64();
+            mbar_wait(&empty_bar[slot], ph ^ 1);
+            if (pdbg) t_empty += clock64() - tp0;
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&full_bar[slot], 2 * kStageBytes);
+              tma_load_4d_cg2(a_dst, &tmA, full_L + 8u * slot, a_c0 + kc * kBlockK, x0 + dx, y0 + dy, tc.n0);
+              tma_load_2d_cg2(a_dst + kATileBytes, &tmW, full_L + 8u * slot, b_c0 + kc * kBlockK, brow);
+            }
+            advance();
+          }
+        }
+        if (cb == jins) load_gamma();
+      }
+      if (gk) load_gamma();                                   // contraction of the last tile
+      if (pdbg && lane == 0) { P.dbg[8] = (unsigned long long)(clock64() - tp_begin); P.dbg[9] = (unsigned long long)t_empty; }
+    } else if (warp == kMmaWarp && leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      uint32_t slot = 0, ph = 0;
+      int stages_r = stages;
+      asm volatile("" : "+r"(stages_r));
+      const uint32_t hi = desc_hi(1024);
+      const uint32_t a_lo0 = desc_lo(smem_base), b_lo0 = desc_lo(smem_base + kATileBytes);
+      uint32_t slot_lo = 0;
+      const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
+      long long t_full = 0, t_buf = 0, t_x2 = 0, n_st = 0, t0 = 0;
+      const long long t_begin = clock64();
+      auto mma_stage = [&](uint32_t d_tmem, bool first) {
+        if (dbg) t0 = clock64();
+        mbar_wait_cl(&full_bar[slot], ph);
+        if (dbg) { t_full += clock64() - t0; ++n_st; }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t alo = a_lo0 + slot_lo, blo = b_lo0 + slot_lo;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_lh_cg2(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, kIdesc2, !(first && k == 0));
+          tc_commit_mc(&empty_bar[slot]);                    // frees the slot in both CTAs when these MMAs retire
+        }
+        ++slot; slot_lo += (uint32_t)(kStageBytes >> 4);
+        if (slot == (uint32_t)stages_r) { slot = 0; slot_lo = 0; ph ^= 1; }
+      };
+      auto gdn_of = [&](int j) {                             // norm(j) = x^2 . gamma^T, in place over acc(j)
+        const int bsel = j & 1;
+        if (dbg) t0 = clock64();
+        mbar_wait_cl(&x2_ready[bsel], (j >> 1) & 1);          // x^2 tiles written by the epilogue warps of both CTAs
+        if (dbg) t_x2 += clock64() - t0;
+        tc_fence_after();
+        for (int kb = 0; kb < gk; ++kb) mma_stage(tmem_base + bsel * kBufCols, kb == 0);
+        if (elect_one()) tc_commit_mc(&norm_full[bsel]);
+      };
+      int cur_job = -1, nkb = 0;
+      for (int it = 0; it < nt; ++it) {
+        const int job = (pi + it * npairs) / P.super_per_job;
+        if (job != cur_job) { cur_job = job; nkb = P.jobs[cur_job].nkb; }
+        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int bsel = it & 1;
+        if (dbg) t0 = clock64();
+        mbar_wait_cl(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
+        if (dbg) t_buf += clock64() - t0;
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (kb == jins) gdn_of(it - 1);
+          mma_stage(tmem_base + bsel * kBufCols, kb == 0);
+        }
+        if (elect_one()) tc_commit_mc(&acc_full[bsel]);
+        if (nkb == jins) gdn_of(it - 1);
+      }
+      if (gk) gdn_of(nt - 1);
+      if (dbg && lane == 0) {
+        P.dbg[0] = (unsigned long long)(clock64() - t_begin); P.dbg[1] = (unsigned long long)t_full;
+        P.dbg[2] = (unsigned long long)t_buf; P.dbg[3] = (unsigned long long)t_x2; P.dbg[4] = (unsigned long long)n_st;
+        P.dbg[5] = (unsigned long long)nt;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own tile) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    EpiRing R;
+    R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
+    R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = kGdnInsert;
+    R.t_first = pi; R.t_stride = npairs; R.rank = (int)rank;
+    R.buf_free_cl = mapa_shared(smem_u32(buf_free), 0); R.x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0);
+    epilogue_role<NP, true>(P, R, tmem_base, gk, nt, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // Halo variant for stride-1 gathers (transposed-conv phases, 3x3 convs, context conv1).
 // The streaming kernel above re-fetches a 128-pixel A tile for every filter tap, so every input pixel
 // crosses the L2->SM fabric once per tap (~6 TB/s of unique traffic is the measured ceiling).  Here a
@@ -857,12 +1076,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == kMmaWarp) {
       // ===================== MMA issuer =====================
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
+      long long t_a = 0, t_b = 0, t_buf = 0, t_x2 = 0, t0 = 0, n_it = 0;
+      const long long t_begin = clock64();
       const uint32_t hi_a = desc_hi(sbo), hi_b = desc_hi(1024);
       auto adv_a = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
       auto adv_b = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
       auto gdn_of = [&](int j) {            // norm(j) = x^2 . gamma^T, in place over acc(j)
         const int bsel = j & 1;
+        if (dbg) t0 = clock64();
         mbar_wait(&x2_ready[bsel], (j >> 1) & 1);
+        if (dbg) t_x2 += clock64() - t0;
         tc_fence_after();
         for (int kb = 0; kb < gk; ++kb) {
           mbar_wait(&afull[sa], pa);
@@ -887,17 +1111,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const Job jb = P.jobs[tc.job];
         const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
         const int bsel = it & 1;
+        if (dbg) t0 = clock64();
         mbar_wait(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
+        if (dbg) t_buf += clock64() - t0;
         tc_fence_after();
         bool first = true;
         for (int ci = 0; ci < jb.nchunks; ++ci) {
           if (ci == jins) gdn_of(it - 1);
           const int kc = jb.kc0 + ci;
+          if (dbg) t0 = clock64();
           mbar_wait(&afull[sa], pa);
+          if (dbg) t_a += clock64() - t0;
           const uint32_t a_addr = smem_base + sa * a_slot;
           for (int tp = 0; tp < jb.ntaps; tp += G) {
             if (!tap_active(P.taps[jb.tap_begin + tp], kc)) continue;
+            if (dbg) t0 = clock64();
             mbar_wait(&bfull[sb], pb);
+            if (dbg) { t_b += clock64() - t0; ++n_it; }
             tc_fence_after();
             __syncwarp();
             const int ng = (jb.ntaps - tp < G) ? jb.ntaps - tp : G;
@@ -931,6 +1161,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (jb.nchunks == jins) gdn_of(it - 1);
       }
       if (gk) gdn_of(ntiles_cta - 1);
+      if (dbg && lane == 0) {
+        P.dbg[0] = (unsigned long long)(clock64() - t_begin); P.dbg[1] = (unsigned long long)t_b;
+        P.dbg[2] = (unsigned long long)t_buf; P.dbg[3] = (unsigned long long)t_x2; P.dbg[4] = (unsigned long long)n_it;
+        P.dbg[5] = (unsigned long long)ntiles_cta; P.dbg[6] = (unsigned long long)t_a;
+      }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -1099,10 +1334,20 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (gk) load_gamma();
     } else if (warp == kMmaWarp && leader) {
       // ===================== MMA issuer (leader CTA only) =====================
+      // Lane t keeps tap t of the current job in registers (A-descriptor offset of its shifted start and its K
+      // range); the loop body has no constant-bank loads with computed indices.
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      int SA_r = SA, SB_r = SB, G_r = G;
+      asm volatile("" : "+r"(SA_r), "+r"(SB_r), "+r"(G_r));
       const uint32_t hi_a = desc_hi(sbo), hi_b = desc_hi(1024);
-      auto adv_a = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
-      auto adv_b = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
+      const uint32_t a_lo0 = desc_lo(smem_base), b_lo0 = desc_lo(b_base);
+      const uint32_t a_slot_lo = a_slot >> 4, b_slot_lo = b_slot >> 4;
+      uint32_t sa_lo = 0, sb_lo = 0;                           // slot index * slot size (16-byte units)
+      auto adv_a = [&]() { ++sa; sa_lo += a_slot_lo; if (sa == (uint32_t)SA_r) { sa = 0; sa_lo = 0; pa ^= 1; } };
+      auto adv_b = [&]() { ++sb; sb_lo += b_slot_lo; if (sb == (uint32_t)SB_r) { sb = 0; sb_lo = 0; pb ^= 1; } };
+      int cur_job = -1, ntaps = 0, nchunks = 0, kc0 = 0;
+      int my_a_c0 = 1 << 30, my_a_c1 = 0;
+      uint32_t my_lo = 0;
       auto gdn_of = [&](int j) {            // norm(j) = x^2 . gamma^T, in place over acc(j), both tiles of the pair
         const int bsel = j & 1;
         mbar_wait_cl(&x2_ready[bsel], (j >> 1) & 1);
@@ -1111,9 +1356,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait_cl(&afull[sa], pa);
           mbar_wait_cl(&bfull[sb], pb);
           tc_fence_after();
-          __syncwarp();
-          const uint32_t alo = desc_lo(smem_base + sa * a_slot), blo = desc_lo(b_base + sb * b_slot);
           if (elect_one()) {
+            const uint32_t alo = a_lo0 + sa_lo, blo = b_lo0 + sb_lo;
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
               umma_bf16_lh_cg2(tmem_base + bsel * kBufCols, alo + 2 * k, hi_b, blo + 2 * k, hi_b, kIdesc2, (kb | k) != 0);
@@ -1122,42 +1366,51 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           adv_a(); adv_b();
         }
-        __syncwarp();
         if (elect_one()) tc_commit_mc(&norm_full[bsel]);
       };
       for (int it = 0; it < nt; ++it) {
         const int job = (pi + it * npairs) / P.super_per_job;
-        const Job jb = P.jobs[job];
-        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
+        if (job != cur_job) {
+          cur_job = job;
+          ntaps = P.jobs[job].ntaps; nchunks = P.jobs[job].nchunks; kc0 = P.jobs[job].kc0;
+          my_a_c0 = 1 << 30; my_a_c1 = 0;
+          if (lane < ntaps) {
+            const Tap t = P.taps[P.jobs[job].tap_begin + lane];
+            my_a_c0 = t.a_c0; my_a_c1 = t.a_c0 + t.nkc * kBlockK; my_lo = (uint32_t)t.halo_off >> 4;
+          }
+        }
+        const int jins = (gk && it > 0) ? (nchunks < kHaloInsert ? nchunks : kHaloInsert) : -1;
         const int bsel = it & 1;
+        const uint32_t d_tmem = tmem_base + bsel * kBufCols;
         mbar_wait_cl(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         bool first = true;
-        for (int ci = 0; ci < jb.nchunks; ++ci) {
+        for (int ci = 0; ci < nchunks; ++ci) {
           if (ci == jins) gdn_of(it - 1);
-          const int kc = jb.kc0 + ci;
+          const int c = (kc0 + ci) * kBlockK;
+          const uint32_t mask = __ballot_sync(0xffffffffu, c >= my_a_c0 && c < my_a_c1);   // taps covering this chunk
           mbar_wait_cl(&afull[sa], pa);
-          const uint32_t a_addr = smem_base + sa * a_slot;
-          for (int tp = 0; tp < jb.ntaps; tp += G) {
-            if (!tap_active(P.taps[jb.tap_begin + tp], kc)) continue;
+          const uint32_t a_reg_lo = a_lo0 + sa_lo;
+          for (int tp = 0; tp < ntaps; tp += G_r) {
+            if (!((mask >> tp) & 1u)) continue;
+            uint32_t alo[4];                                   // A descriptors of the (up to 4) taps of this slot
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              alo[g] = 0;
+              if (g < G_r) alo[g] = a_reg_lo + __shfl_sync(0xffffffffu, my_lo, (tp + g) & 31);
+            }
+            const int ng = (ntaps - tp < G_r) ? ntaps - tp : G_r;
             mbar_wait_cl(&bfull[sb], pb);
             tc_fence_after();
-            __syncwarp();
-            const int ng = (jb.ntaps - tp < G) ? jb.ntaps - tp : G;
-            const uint32_t bslot_lo = desc_lo(b_base + sb * b_slot);
-            uint32_t alo[4];                                   // computed warp-uniformly, outside the elected branch
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              alo[g] = (g < ng) ? desc_lo(a_addr + P.taps[jb.tap_begin + tp + g].halo_off) : 0u;
             if (elect_one()) {
+              const uint32_t bslot_lo = b_lo0 + sb_lo;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (g < ng) {
                   const uint32_t blo = bslot_lo + (uint32_t)g * (kBHalfBytes >> 4);
 #pragma unroll
                   for (int k = 0; k < kBlockK / 16; ++k)
-                    umma_bf16_lh_cg2(tmem_base + bsel * kBufCols, alo[g] + 2 * k, hi_a, blo + 2 * k, hi_b, kIdesc2,
-                                     !(first && g == 0 && k == 0));
+                    umma_bf16_lh_cg2(d_tmem, alo[g] + 2 * k, hi_a, blo + 2 * k, hi_b, kIdesc2, !(first && g == 0 && k == 0));
                 }
               }
               tc_commit_mc(&bempty[sb]);
@@ -1165,13 +1418,11 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             first = false;
             adv_b();
           }
-          __syncwarp();
           if (elect_one()) tc_commit_mc(&aempty[sa]);         // both regions consumed by all of their taps
           adv_a();
         }
-        __syncwarp();
         if (elect_one()) tc_commit_mc(&acc_full[bsel]);
-        if (jb.nchunks == jins) gdn_of(it - 1);
+        if (nchunks == jins) gdn_of(it - 1);
       }
       if (gk) gdn_of(nt - 1);
     }
@@ -1718,13 +1969,15 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g
   return check_launch("conv_halo_kernel");
 }
 
-template <int NP>
-int launch_halo2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
-  const size_t smem = (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * (NP / 2) * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
-                      (size_t)(P.nbias + 1) * NP * sizeof(float) + 64;
+template <int NP, int HALO>
+int launch_pair(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
+  auto kern = HALO ? conv_halo2_kernel<NP> : conv_tc2_kernel<NP>;
+  const size_t smem = HALO ? (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * (NP / 2) * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
+                                 (size_t)(P.nbias + 1) * NP * sizeof(float) + 64
+                           : (size_t)P.stages * (kATileBytes + (NP / 2) * kBlockK * 2) + 1024 + 256 + (size_t)(P.nbias + 1) * NP * sizeof(float);
   static bool attr_set = false;
   static int max_clusters = 0;
-  if (smem > 227 * 1024) return fail(LDIC_EINVAL, "conv halo2: shared memory budget exceeded (%zu)", smem);
+  if (smem > 227 * 1024) return fail(LDIC_EINVAL, "conv pair kernel: shared memory budget exceeded (%zu)", smem);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -1732,11 +1985,11 @@ int launch_halo2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& 
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
   if (!attr_set) {
-    LDIC_CUDA(cudaFuncSetAttribute(conv_halo2_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cfg.gridDim = dim3(kNumSMs);
     cfg.dynamicSmemBytes = 227 * 1024 - 1024;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv_halo2_kernel<NP>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / 2 - 4; }
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / 2 - 4; }
     cfg.dynamicSmemBytes = smem;
     max_clusters = n < kNumSMs / 2 ? n : kNumSMs / 2;
     attr_set = true;
@@ -1744,9 +1997,9 @@ int launch_halo2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& 
   const int total_super = P.super_per_job * P.njobs;
   const int npairs = total_super < max_clusters ? total_super : max_clusters;
   cfg.gridDim = dim3(2 * npairs);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_halo2_kernel<NP>, a, w, g, P);
-  if (e != cudaSuccess) return fail(LDIC_ECUDA, "conv_halo2_kernel launch: %s", cudaGetErrorString(e));
-  return check_launch("conv_halo2_kernel");
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, w, g, P);
+  if (e != cudaSuccess) return fail(LDIC_ECUDA, "conv pair kernel launch: %s", cudaGetErrorString(e));
+  return check_launch(HALO ? "conv_halo2_kernel" : "conv_tc2_kernel");
 }
 
 // generic weight packer: Wp[t][n][k]
@@ -1979,8 +2232,8 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
   static unsigned long long* dbg_buf = nullptr;
   const bool want_dbg = getenv("LDIC_DEBUG_TIMING") != nullptr;
-  if (want_dbg && !dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
-  if (want_dbg) cudaMemset(dbg_buf, 0, 16 * sizeof(unsigned long long));
+  if (want_dbg && !dbg_buf) cudaMalloc(&dbg_buf, 32 * sizeof(unsigned long long));
+  if (want_dbg) cudaMemset(dbg_buf, 0, 32 * sizeof(unsigned long long));
   P.dbg = want_dbg ? dbg_buf : nullptr;
   const int stage_bytes = kATileBytes + L.Np * kBlockK * 2;
   int stages = (227 * 1024 - 2048 - (L.nbias + 1) * L.Np * 4) / stage_bytes;
@@ -1999,7 +2252,11 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
     }
     const long long halo_tiles = (long long)((L.Wg + 7) / 8) * ((L.Hg + 15) / 16) * L.Bg;
     halo = (dxmax > dxmin || dymax > dymin) && halo_tiles * 10 <= (long long)P.tiles_per_job * 13;
-    if (const char* e = getenv("LDIC_HALO")) halo = halo && atoi(e) != 0;          // tuning aid: LDIC_HALO=0 disables
+    // UMMA reads of the shifted (not 1024-byte aligned) halo descriptors run at about half rate, which only pays
+    // when the weight tiles are small and several taps share a stage: narrow accumulators (merged last deconv)
+    int halo_mode = 1;                                                             // 0 never, 1 Np <= 64, 2 whenever possible
+    if (const char* e = getenv("LDIC_HALO")) halo_mode = atoi(e);                  // tuning aid
+    halo = halo && (halo_mode == 2 || (halo_mode == 1 && L.Np <= 64));
     if (halo) {
       P.halo = 1; P.dxmin = dxmin; P.dymin = dymin;
       P.RW = 8 + dxmax - dxmin; P.RH = 16 + dymax - dymin;
@@ -2016,7 +2273,9 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
       if (const char* e = getenv("LDIC_HALO2")) pair = atoi(e) != 0;                      // tuning aid: LDIC_HALO2=0 = one CTA per tile
       const int bbytes = P.G * (pair ? L.Np / 2 : L.Np) * kBlockK * 2;
       const int budget = 227 * 1024 - 1024 - 512 - (L.nbias + 1) * L.Np * 4 - 64;
-      int SA = P.gdn_kblocks + 2; if (SA < 3) SA = 3; if (SA > kMaxStages) SA = kMaxStages;
+      int SA = P.gdn_kblocks + 2; if (SA < 3) SA = 3;
+      if (const char* e = getenv("LDIC_HALO_SA")) SA = P.gdn_kblocks + atoi(e);            // tuning aid: region slots beyond the x^2 tiles
+      if (SA > kMaxStages) SA = kMaxStages;
       int SB = (budget - SA * P.a_slot_bytes) / bbytes;
       while (SB < 3 && SA > P.gdn_kblocks + 1 && SA > 2) { --SA; SB = (budget - SA * P.a_slot_bytes) / bbytes; }
       if (SB > kMaxStages) SB = kMaxStages;
@@ -2045,6 +2304,20 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
     }
   }
 
+  if (!halo) pair = false;
+  // CTA pairs for the streaming kernel (cta_group::2): not for the x-parity fallback view
+  bool pair_stream = !halo && P.mode != 1;
+  if (const char* e = getenv("LDIC_PAIR")) pair_stream = pair_stream && atoi(e) != 0;      // tuning aid: LDIC_PAIR=0
+  if (pair_stream) {
+    P.super_per_job = (P.tiles_per_job + 1) / 2;
+    const int stage2 = kATileBytes + (L.Np / 2) * kBlockK * 2;
+    int st2 = (227 * 1024 - 2048 - (L.nbias + 1) * L.Np * 4) / stage2;
+    if (st2 > kMaxStages) st2 = kMaxStages;
+    if (const char* e = getenv("LDIC_STAGES")) { int v = atoi(e); if (v >= 2 && v < st2) st2 = v; }
+    P.stages = st2;
+    if (gdn && st2 < P.gdn_kblocks + 1) pair_stream = false;
+    else pair = true;                          // weight / gamma maps load half of the rows per CTA
+  }
   CUtensorMap tmA, tmW, tmG;
   const cuuint64_t C = (cuuint64_t)L.vC;
   if (halo) {
@@ -2072,13 +2345,13 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.ntaps_total * L.Np};
     cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(halo && pair ? L.Np / 2 : L.Np * (halo ? P.G : 1))};
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? L.Np / 2 : L.Np * (halo ? P.G : 1))};
     if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
   }
   if (gdn) {
     cuuint64_t dims[2] = {(cuuint64_t)L.Np, (cuuint64_t)L.Np};
     cuuint64_t str[1] = {(cuuint64_t)L.Np * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(halo && pair ? L.Np / 2 : L.Np)};
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? L.Np / 2 : L.Np)};
     if ((rc = encode_map(&tmG, gamma_bf16, 2, dims, str, box))) return rc;
   } else {
     tmG = tmW;
@@ -2086,20 +2359,26 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   cudaStream_t st = (cudaStream_t)stream;
   if (halo && pair) {
     switch (L.Np) {
-      case 64: return launch_halo2<64>(tmA, tmW, tmG, P, st);
-      case 128: return launch_halo2<128>(tmA, tmW, tmG, P, st);
-      case 192: return launch_halo2<192>(tmA, tmW, tmG, P, st);
-      case 256: return launch_halo2<256>(tmA, tmW, tmG, P, st);
+      case 64: rc = launch_pair<64, 1>(tmA, tmW, tmG, P, st); break;
+      case 128: rc = launch_pair<128, 1>(tmA, tmW, tmG, P, st); break;
+      case 192: rc = launch_pair<192, 1>(tmA, tmW, tmG, P, st); break;
+      case 256: rc = launch_pair<256, 1>(tmA, tmW, tmG, P, st); break;
     }
-  }
-  if (halo) {
+  } else if (halo) {
     switch (L.Np) {
-      case 64: return launch_halo<64>(tmA, tmW, tmG, P, st);
-      case 128: return launch_halo<128>(tmA, tmW, tmG, P, st);
-      case 192: return launch_halo<192>(tmA, tmW, tmG, P, st);
-      case 256: return launch_halo<256>(tmA, tmW, tmG, P, st);
+      case 64: rc = launch_halo<64>(tmA, tmW, tmG, P, st); break;
+      case 128: rc = launch_halo<128>(tmA, tmW, tmG, P, st); break;
+      case 192: rc = launch_halo<192>(tmA, tmW, tmG, P, st); break;
+      case 256: rc = launch_halo<256>(tmA, tmW, tmG, P, st); break;
     }
-  }
+  } else if (pair_stream) {
+    switch (L.Np) {
+      case 64: rc = launch_pair<64, 0>(tmA, tmW, tmG, P, st); break;
+      case 128: rc = launch_pair<128, 0>(tmA, tmW, tmG, P, st); break;
+      case 192: rc = launch_pair<192, 0>(tmA, tmW, tmG, P, st); break;
+      case 256: rc = launch_pair<256, 0>(tmA, tmW, tmG, P, st); break;
+    }
+  } else
   switch (L.Np) {
     case 64: rc = launch_conv<64>(tmA, tmW, tmG, P, st); break;
     case 128: rc = launch_conv<128>(tmA, tmW, tmG, P, st); break;
@@ -2108,12 +2387,14 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
     default: return fail(LDIC_EINVAL, "conv: unsupported Np %d", L.Np);
   }
   if (want_dbg && rc == LDIC_OK) {     // debugging aid only: synchronises
-    unsigned long long h[16];
+    unsigned long long h[32];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[ldic timing] kind %d Np %d tiles/cta %llu stages %llu | mma total %llu cyc: wait_full %llu wait_buf %llu wait_x2 %llu "
             "(per stage: total %.0f wait_full %.0f) | producer total %llu wait_empty %llu\n", d->kind, L.Np, h[5], h[4], h[0], h[1], h[2], h[3],
             h[4] ? (double)h[0] / h[4] : 0.0, h[4] ? (double)h[1] / h[4] : 0.0, h[8], h[9]);
+    fprintf(stderr, "[ldic timing]   epilogue total %llu cyc over %llu tiles: wait_acc %llu wait_norm %llu wait_slots %llu; mma wait_afull %llu\n",
+            h[16], h[20], h[17], h[18], h[19], h[6]);
   }
   return rc;
 }
