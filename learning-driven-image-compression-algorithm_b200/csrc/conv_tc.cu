@@ -30,12 +30,16 @@ using namespace ldic;
 
 namespace {
 
-constexpr int kThreads = 384;          // warpgroup 0: producer, MMA, 2 spare; warpgroups 1-2: epilogue
-constexpr int kEpiThreads = 256;          // warps 0..7
-constexpr int kProdWarp = 8;              // TMA producer (A tiles / A regions)
-constexpr int kMmaWarp = 9;               // tcgen05.mma issuer; the HIGHEST warp id on its scheduler, so it wins
-                                          // issue arbitration against the two epilogue warps that share it
-constexpr int kProdBWarp = 10;            // halo kernel: weight / gamma tile producer
+#ifndef LDIC_EPI_WARPS
+#define LDIC_EPI_WARPS 8                  // 8: two warps per TMEM lane quadrant (96 columns each at Np=192); 16: four (48 columns)
+#endif
+constexpr int kEpiWarps = LDIC_EPI_WARPS; // warps 0..kEpiWarps-1: epilogue (TMEM -> registers -> global)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiThreads + 128;   // + one warpgroup: TMA producer, MMA issuer, B producer / patch builders
+constexpr int kProdWarp = kEpiWarps;      // TMA producer (A tiles / A regions)
+constexpr int kMmaWarp = kEpiWarps + 1;   // tcgen05.mma issuer + TMEM allocator
+constexpr int kProdBWarp = kEpiWarps + 2; // halo kernels: weight / gamma tile producer; first layer: patch builders (+3)
+constexpr int kEpiRegs = kEpiWarps == 8 ? 216 : 104;   // setmaxnreg of the epilogue warpgroups (the last warpgroup drops to 64)
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = 128 B = one swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
@@ -74,6 +78,7 @@ struct ConvParams {
   const float* beta;
   void* out;
   unsigned long long* dbg;   // optional cycle counters of CTA 0 (LDIC_DEBUG_TIMING=1), else null
+  int dbg_nostore;           // experiment: skip the epilogue's global stores (LDIC_DEBUG_NOSTORE=1)
 };
 
 // ---------------------------------------------------------------------------------
@@ -215,6 +220,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -363,9 +381,10 @@ struct EpiRing {
 template <int NP, bool CL = false>
 __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing& R, uint32_t tmem_base, int gk,
                                               int ntiles_cta, int warp, int lane) {
-  constexpr int CPT = NP / 2;
+  constexpr int CPT = NP / (kEpiWarps / 4);      // accumulator columns per thread
+  constexpr int LDW = (CPT % 32 == 0) ? 32 : 16;   // columns per tcgen05.ld
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int h = warp >> 2;                // column half (epilogue warps are 0..7)
+    const int h = warp >> 2;                // column slice (kEpiWarps / 4 slices of CPT columns)
     const int r = q * 32 + lane;            // tile row = TMEM lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const int col0 = h * CPT;
@@ -383,7 +402,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
       const uint32_t tbuf = tmem_base + bsel * kBufCols + lane_sel + col0;
       const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
-      const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B);
+      const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B) && !P.dbg_nostore;
       const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
                                  (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
       // ring position of this tile's gamma items: after the first min(insert_after, len) items of the
@@ -409,7 +428,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       {
         uint32_t(&xu)[CPT] = reinterpret_cast<uint32_t(&)[CPT]>(xr);
 #pragma unroll
-        for (int c = 0; c < CPT; c += 32) tmem_ld32(tbuf + c, reinterpret_cast<uint32_t(&)[32]>(xu[c]));
+        for (int c = 0; c < CPT; c += LDW) tmem_ldn<LDW>(tbuf + c, reinterpret_cast<uint32_t(&)[LDW]>(xu[c]));
         tmem_ld_wait();
       }
       tc_fence_before();
@@ -450,12 +469,12 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         tc_fence_after();
         // ---- pass 2: out = x * rsqrt(norm + beta)   (IGDN: x * sqrt = x * n * rsqrt(n)) ----
 #pragma unroll
-        for (int c = 0; c < CPT; c += 32) {
-          uint32_t tr[32];
-          tmem_ld32(tbuf + c, tr);
+        for (int c = 0; c < CPT; c += LDW) {
+          uint32_t tr[LDW];
+          tmem_ldn<LDW>(tbuf + c, tr);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
+          for (int k = 0; k < LDW; k += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(&R.s_beta[col0 + c + k]);
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -575,7 +594,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int gk = gdn ? P.gdn_kblocks : 0;
   const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 8) {
+  if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // warpgroup 2 hands registers to the epilogue
   if (warp == kProdWarp) {
     // ===================== TMA producer =====================
@@ -708,7 +727,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   } else {
     // ===================== epilogue warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
     R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
@@ -788,7 +807,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int nt = (total_super - pi + npairs - 1) / npairs;             // super tiles of this pair
   const uint32_t full_L = mapa_shared(smem_u32(full_bar), 0);
 
-  if (warp >= 8) {
+  if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == kProdWarp) {
       // ===================== TMA producer (both CTAs) =====================
@@ -911,7 +930,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue warps (both CTAs, own tile) =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
     R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
@@ -1003,7 +1022,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
   // a tap contributes to channel chunk kc iff its K range covers it
 
-  if (warp >= 8) {
+  if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == kProdWarp) {
       // ===================== A-region producer (warp-uniform loop, elected lane issues) =====================
@@ -1169,7 +1188,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
     R.ring_base = smem_base; R.slot_bytes = a_slot; R.nslots = (uint32_t)SA; R.empty_bar = aempty;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
@@ -1259,7 +1278,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t afull_L = mapa_shared(smem_u32(afull), 0), bfull_L = mapa_shared(smem_u32(bfull), 0);
   auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
 
-  if (warp >= 8) {
+  if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == kProdWarp) {
       // ===================== A-region producer (both CTAs: own tile, completion on the leader's barrier) ==========
@@ -1428,7 +1447,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue warps (both CTAs, own tile) =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
     R.ring_base = smem_base; R.slot_bytes = a_slot; R.nslots = (uint32_t)SA; R.empty_bar = aempty;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
@@ -1540,7 +1559,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // ring position of tile it's first A slot
   auto base_pos = [&](int it) -> uint32_t { return it == 0 ? 0u : (uint32_t)(2 + per_tile * (it - 1)); };
 
-  if (warp >= 8) {
+  if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == kProdWarp) {
       // ===================== TMA: resident operands once, then the raw image boxes =====================
@@ -1612,7 +1631,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (gk) gdn_of(ntiles_cta - 1);
     } else {
       // ===================== patch builders (warps 10, 11) =====================
-      const int tb = (int)threadIdx.x - 32 * kProdBWarp;                // 0..63 = pixel x inside the tile
+      const int tb = (int)threadIdx.x - 32 * kProdBWarp;                // 0..63 = pixel x inside the tile (warps kProdBWarp, +1)
       for (int it = 0; it < ntiles_cta; ++it) {
         const int rs = it & 1;
         const uint32_t p0 = base_pos(it);
@@ -1653,7 +1672,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else {
     // ===================== epilogue warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
     R.ring_base = ring_base; R.slot_bytes = kATileBytes; R.nslots = (uint32_t)S; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
@@ -2075,6 +2094,7 @@ int forward_first(const LdicConvDesc* d, const Layer& L, const void* x, const vo
   P.out_sX = L.out_sX; P.out_sY = L.out_sY; P.out_sN = L.out_sN;
   P.jobs[0] = L.jobs[0];
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
+  P.dbg_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
   const int fixed = (2 + L.Np / 64) * L.Np * kBlockK * 2 + 2 * kRawSlot + 256 + 2 * L.Np * 4 + 1024;
   int S = (227 * 1024 - fixed) / kATileBytes;
   if (S > kMaxStages) S = kMaxStages;
@@ -2230,6 +2250,7 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   for (int t = 0; t < kMaxTaps; ++t) P.taps[t] = L.taps[t];
   if (strided) for (int t = 0; t < L.ntaps_total; ++t) { P.taps[t].dx = (short)(2 * L.taps[t].dx + L.taps[t].px); P.taps[t].px = 0; }
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
+  P.dbg_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
   static unsigned long long* dbg_buf = nullptr;
   const bool want_dbg = getenv("LDIC_DEBUG_TIMING") != nullptr;
   if (want_dbg && !dbg_buf) cudaMalloc(&dbg_buf, 32 * sizeof(unsigned long long));
