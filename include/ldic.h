@@ -199,6 +199,22 @@ LDIC_API void ldic_conv_out_shape(const LdicConvDesc* d, int* Ho, int* Wo);
  * (gamma_bf16 / beta_tiled from ldic_gdn_prepare).                              */
 LDIC_API int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                       const void* gamma_bf16, const float* beta_tiled, void* y, void* stream);
+/* The merged last synthesis deconv (LDIC_DECONV_GS_5x5_MERGED) with the tail of Net.forward fused into its
+ * epilogue: per-image 1x1 conv of the M-channel IGDN output with w[B][3][M] (batch_conv, model/net.py:527-537,
+ * :811) and the a11 squared level error against the NCHW fp32 input image (model/net.py:864-868), so the
+ * M-channel full-resolution tensor never makes a round trip through HBM.  y_or_null (optional) still receives
+ * the [B,2H,2W,M] fp32 NHWC tensor; x_tilde_nchw (optional) the reconstruction; sq_err[B] is accumulated
+ * into (zero it first).  H, W of the tail are the image size (= 2 x the layer's input size).            */
+typedef struct {
+  const float* x_nchw;
+  const float* w;
+  float* x_tilde_nchw;
+  unsigned long long* sq_err;
+  int H, W;
+} LdicConvTail;
+LDIC_API int ldic_conv_forward_fused_tail(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                                 const void* gamma_bf16, const float* beta_tiled, void* y_or_null,
+                                 const LdicConvTail* tail, void* stream);
 /* Plain CUDA-core fp32 direct convolution of the same layer kinds on NHWC fp32
  * tensors (validation aid for the tensor-core path at sizes the CPU oracle
  * cannot reach; not used by the product forward).                               */

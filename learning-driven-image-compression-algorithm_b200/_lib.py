@@ -53,6 +53,11 @@ class ConvDesc(C.Structure):
                 ("out_f32", C.c_int), ("aux0", C.c_int), ("aux1", C.c_int)]
 
 
+class ConvTail(C.Structure):
+    _fields_ = [("x_nchw", C.c_void_p), ("w", C.c_void_p), ("x_tilde_nchw", C.c_void_p), ("sq_err", C.c_void_p),
+                ("H", C.c_int), ("W", C.c_int)]
+
+
 class SyntaxArgs(C.Structure):
     _fields_ = ([(n, C.c_int) for n in ("B", "h", "w", "N", "M")] +
                 [(n, C.c_void_p) for n in (
@@ -100,6 +105,8 @@ _SIGS = {
     "ldic_syntax_workspace_elems": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ldic_syntax_branch": (C.c_int, [C.POINTER(SyntaxArgs), C.c_void_p]),
     "ldic_debug_last_timeout": (C.c_int, [C.POINTER(C.c_ulonglong)]),
+    "ldic_conv_forward_fused_tail": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.POINTER(ConvTail), C.c_void_p]),
     "ldic_conv_forward_f32_reference_kernel": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                                          C.c_void_p, C.c_void_p]),
 }

@@ -48,4 +48,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// a11 arithmetic on one sample (model/net.py:864-868): squared difference of the 8-bit levels, exact integer
+__device__ __forceinline__ unsigned int sq_level_err(float x, float xt, int clamp_pm1) {
+  if (clamp_pm1) xt = fminf(fmaxf(xt, -1.f), 1.f);
+  float gt = rintf(__fmul_rn(__fadd_rn(x, 1.f), 127.5f));
+  float xh = __fmul_rn(__fadd_rn(xt, 1.f), 127.5f);
+  xh = rintf(fminf(fmaxf(xh, 0.f), 255.f));
+  float d = xh - gt;   // integers: exact
+  return (unsigned int)(d * d);
+}
+
 }  // namespace ldic

@@ -79,6 +79,12 @@ struct ConvParams {
   void* out;
   unsigned long long* dbg;   // optional cycle counters of CTA 0 (LDIC_DEBUG_TIMING=1), else null
   int dbg_nostore;           // experiment: skip the epilogue's global stores (LDIC_DEBUG_NOSTORE=1)
+  // fused tail of Net.forward on the merged last deconv: per-image 1x1 conv (batch_conv) + 8-bit-level squared error
+  const float* tail_x;       // NCHW fp32 input image [B,3,tail_H,tail_W], or null (no tail)
+  const float* tail_w;       // [B][3][Cg] per-image filters
+  float* tail_xo;            // optional NCHW fp32 reconstruction
+  unsigned long long* tail_sq;  // [B] exact sums (accumulated into)
+  int tail_H, tail_W;
 };
 
 // ---------------------------------------------------------------------------------
@@ -378,6 +384,35 @@ struct EpiRing {
   uint32_t buf_free_cl, x2_ready_cl;
 };
 
+// Fused tail on the CPT accumulator columns of one thread (CPT / CG output pixels of CG channels each); every index
+// into xr is a compile-time constant so the accumulators stay in registers.
+template <int CPT, int CG>
+__device__ __forceinline__ unsigned long long fused_tail_pixels(const ConvParams& P, const float (&xr)[CPT], int col0, int n,
+                                                                int oy0, int ox0) {
+  unsigned long long acc = 0;
+  if constexpr (CPT % CG == 0) {
+    const float* wn = P.tail_w + (long long)n * 3 * CG;
+#pragma unroll
+    for (int jj = 0; jj < CPT; jj += CG) {
+      const int g = (col0 + jj) / CG;
+      const int oy = oy0 + (g >> 1), ox = ox0 + (g & 1);
+      float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int m = 0; m < CG; ++m) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = fmaf(xr[jj + m], __ldg(wn + c * CG + m), o[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const long long idx = (((long long)n * 3 + c) * P.tail_H + oy) * P.tail_W + ox;
+        if (P.tail_xo) P.tail_xo[idx] = o[c];
+        acc += sq_level_err(__ldg(P.tail_x + idx), o[c], 0);
+      }
+    }
+  }
+  return acc;
+}
+
 template <int NP, bool CL = false>
 __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing& R, uint32_t tmem_base, int gk,
                                               int ntiles_cta, int warp, int lane) {
@@ -495,6 +530,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         for (int c = 0; c < CPT; ++c) xr[c] = xr[c] > 0.f ? xr[c] : 0.2f * xr[c];
       }
 
+      unsigned long long tail_acc = 0;       // fused tail: this thread's squared level error on this tile
       if (valid) {
         // 256-bit stores: every lane writes whole 32-byte sectors of its own pixel row
         if (P.ngroups == 1) {
@@ -516,20 +552,40 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
           }
         } else {
           // merged sub-pixel phases: Cg (a power of two >= 8) channels per output pixel, group g = col / Cg
+          if (P.out) {
 #pragma unroll
-          for (int j = 0; j < CPT / 8; ++j) {
-            const int col = col0 + j * 8;
-            const int g = col >> P.cg_shift, cc = col & (P.Cg - 1);
-            const long long off = pix_base + (long long)(g >> 1) * P.out_sY + (long long)(g & 1) * P.out_sX + cc;
-            const float* x8 = &xr[j * 8];
-            if (P.out_f32) {
-              st_global_v8(reinterpret_cast<float*>(P.out) + off, x8);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off);
-              *dst = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
-                                pack_bf16x2(x8[6], x8[7]));
+            for (int j = 0; j < CPT / 8; ++j) {
+              const int col = col0 + j * 8;
+              const int g = col >> P.cg_shift, cc = col & (P.Cg - 1);
+              const long long off = pix_base + (long long)(g >> 1) * P.out_sY + (long long)(g & 1) * P.out_sX + cc;
+              const float* x8 = &xr[j * 8];
+              if (P.out_f32) {
+                st_global_v8(reinterpret_cast<float*>(P.out) + off, x8);
+              } else {
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off);
+                *dst = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
+                                  pack_bf16x2(x8[6], x8[7]));
+              }
             }
           }
+          if constexpr (NP <= 128) if (P.tail_x) {   // merged deconv: Np = 4 x Cg = 64 or 128 accumulator columns
+            // batch_conv (model/net.py:527-537, :811): x~[c] = sum_m w[n][c][m] * v[m] on this thread's output pixels,
+            // then the a11 squared level error against the input image (model/net.py:864-868)
+            if (P.Cg == 16) tail_acc = fused_tail_pixels<CPT, 16>(P, xr, col0, gn_, gy_ * P.sy + jb.oy_off, gx_ * P.sx + jb.ox_off);
+            else if (P.Cg == 32) tail_acc = fused_tail_pixels<CPT, 32>(P, xr, col0, gn_, gy_ * P.sy + jb.oy_off, gx_ * P.sx + jb.ox_off);
+          }
+        }
+      }
+      if constexpr (NP <= 128) if (P.tail_x) {
+        // exact integer sums: the order of the atomic adds does not matter.  One image per tile (TN == 1): one
+        // warp-level sum and one atomic per warp; tiles spanning images: one atomic per contributing thread.
+        if (P.TN == 1) {
+          unsigned long long v = tail_acc;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && v) atomicAdd(P.tail_sq + tc.n0, v);
+        } else if (tail_acc) {
+          atomicAdd(P.tail_sq + gn_, tail_acc);
         }
       }
     }
@@ -2207,13 +2263,31 @@ extern "C" int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, con
   return check_launch("k_pack_weights");
 }
 
+namespace {
+int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                      const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, void* stream);
+}
 extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                                  const void* gamma_bf16, const float* beta_tiled, void* y, void* stream) {
+  if (!y) return fail(LDIC_EINVAL, "conv: null output tensor");
+  return conv_forward_impl(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, nullptr, stream);
+}
+extern "C" int ldic_conv_forward_fused_tail(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                                            const void* gamma_bf16, const float* beta_tiled, void* y_or_null,
+                                            const LdicConvTail* tail, void* stream) {
+  if (!tail || !tail->x_nchw || !tail->w || !tail->sq_err) return fail(LDIC_EINVAL, "conv tail: x_nchw, w and sq_err are required");
+  if (!d || d->kind != LDIC_DECONV_GS_5x5_MERGED) return fail(LDIC_EINVAL, "conv tail: only the merged last deconv carries the fused tail");
+  if (tail->H != 2 * d->H || tail->W != 2 * d->W) return fail(LDIC_EINVAL, "conv tail: image size must be twice the layer input");
+  return conv_forward_impl(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y_or_null, tail, stream);
+}
+namespace {
+int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                      const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, void* stream) {
   Layer L;
   int rc = build_layer(d, &L);
   if (rc) return rc;
   if (d->B == 0) return LDIC_OK;
-  if (!x || !w_packed || !y) return fail(LDIC_EINVAL, "conv: null tensor");
+  if (!x || !w_packed || (!y && !tail)) return fail(LDIC_EINVAL, "conv: null tensor");
   if ((rc = ensure_timeout_report())) return rc;
   const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
   if (gdn && (!gamma_bf16 || !beta_tiled)) return fail(LDIC_EINVAL, "conv: GDN epilogue needs gamma_bf16 and beta_tiled");
@@ -2251,6 +2325,10 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   if (strided) for (int t = 0; t < L.ntaps_total; ++t) { P.taps[t].dx = (short)(2 * L.taps[t].dx + L.taps[t].px); P.taps[t].px = 0; }
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
   P.dbg_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
+  if (tail) {
+    P.tail_x = tail->x_nchw; P.tail_w = tail->w; P.tail_xo = tail->x_tilde_nchw; P.tail_sq = tail->sq_err;
+    P.tail_H = tail->H; P.tail_W = tail->W;
+  }
   static unsigned long long* dbg_buf = nullptr;
   const bool want_dbg = getenv("LDIC_DEBUG_TIMING") != nullptr;
   if (want_dbg && !dbg_buf) cudaMalloc(&dbg_buf, 32 * sizeof(unsigned long long));
@@ -2419,6 +2497,7 @@ extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const voi
   }
   return rc;
 }
+}  // namespace
 
 // ---------------------------------------------------------------------------------
 // CUDA-core fp32 direct convolution of the same layer kinds (validation aid).

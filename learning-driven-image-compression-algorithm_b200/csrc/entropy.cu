@@ -494,15 +494,6 @@ extern "C" int ldic_round_likelihood_bpp(const LdicLikelihoodArgs* a, void* stre
 // ------------------------------------------------------------------------------------
 // a11: MSE on 8-bit levels (exact integer accumulation)
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int sq_level_err(float x, float xt, int clamp_pm1) {
-  if (clamp_pm1) xt = fminf(fmaxf(xt, -1.f), 1.f);
-  float gt = rintf(__fmul_rn(__fadd_rn(x, 1.f), 127.5f));
-  float xh = __fmul_rn(__fadd_rn(xt, 1.f), 127.5f);
-  xh = rintf(fminf(fmaxf(xh, 0.f), 255.f));
-  float d = xh - gt;   // integers: exact
-  return (unsigned int)(d * d);
-}
-
 __global__ void __launch_bounds__(256) k_mse_sum(const float* __restrict__ x, const float* __restrict__ xt,
                                                  long long chw, int clamp_pm1, unsigned long long* __restrict__ out) {
   const int b = blockIdx.y;

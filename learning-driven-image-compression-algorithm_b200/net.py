@@ -204,6 +204,7 @@ class Net(nn.Module):
         self.context_tf32 = True
         self.context_on_torch = False     # True: run the context transform with torch ops (cross-check in tests)
         self.syntax_on_torch = os.environ.get("LDIC_SYNTAX_FUSED", "1") == "0"   # True: syntax branch as stock torch ops
+        self.tail_fused = os.environ.get("LDIC_TAIL_FUSED", "1") != "0"          # batch_conv + MSE inside the last deconv
 
     # -- checkpoint compatibility ---------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -232,8 +233,8 @@ class Net(nn.Module):
 
     # -- the hot path -----------------------------------------------------------------------
     @torch.no_grad()
-    def rd_forward(self, inputs: torch.Tensor, want_x_hat: bool = False, want_likelihoods: bool = False
-                   ) -> Dict[str, torch.Tensor]:
+    def rd_forward(self, inputs: torch.Tensor, want_x_hat: bool = False, want_likelihoods: bool = False,
+                   want_xt16: bool = False) -> Dict[str, torch.Tensor]:
         """Rate-distortion forward of Net.forward(mode='test') (model/net.py:539-871).
         Returns the per-stream sum(ln L) (`bits` = [z, y, syntax]), the exact per-image
         squared-error sums and, on request, x_hat / likelihood tensors."""
@@ -299,8 +300,15 @@ class Net(nn.Module):
                                                       syn_second.contiguous(),
                                                       lik_bound=self.entropy_bottleneck_z3_syntax.likelihood_bound)
 
-        xt16 = self.s_model.forward_nhwc(y_round_bf16)                              # :800   (B,H,W,M) fp32 NHWC
-        sq_err, x_hat = ops.syntax_conv_mse(x, xt16, conv_w.reshape(B, 3, M), want_x_tilde=want_x_hat)   # :811,:864-868
+        fused = None
+        if self.tail_fused:      # g_s with batch_conv + squared level error in the last deconv's epilogue
+            fused = self.s_model.forward_nhwc_fused_tail(y_round_bf16, x, conv_w.reshape(B, 3, M),        # :800,:811,:864-868
+                                                         want_x_tilde=want_x_hat, want_out=want_xt16)
+        if fused is not None:
+            sq_err, x_hat, xt16 = fused
+        else:
+            xt16 = self.s_model.forward_nhwc(y_round_bf16)                          # :800   (B,H,W,M) fp32 NHWC
+            sq_err, x_hat = ops.syntax_conv_mse(x, xt16, conv_w.reshape(B, 3, M), want_x_tilde=want_x_hat)   # :811,:864-868
 
         out = {"bits": torch.cat([sum_z, sum_y, sum_syn]), "sq_err": sq_err}
         if want_x_hat:

@@ -389,6 +389,36 @@ class ConvTC:
             f += 2.0 * self.cout * self.cout * B * ho * wo
         return f
 
+    def fused_tail(self, x: torch.Tensor, image: torch.Tensor, conv_w: torch.Tensor, *, want_x_tilde: bool = False,
+                   want_out: bool = False):
+        """Merged last synthesis deconv + batch_conv + squared level error in one kernel
+        (ldic_conv_forward_fused_tail).  x: NHWC bf16 layer input; image: NCHW fp32 (B,3,2H,2W); conv_w: (B,3,M).
+        Returns (sq_err int64[B], x_tilde NCHW or None, layer output NHWC fp32 or None)."""
+        _req(x, torch.bfloat16, "x")
+        image = _req(image, torch.float32, "image").contiguous()
+        conv_w = _req(conv_w, torch.float32, "conv_w").contiguous()
+        if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
+            raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
+        B, H, W, _ = x.shape
+        if tuple(image.shape) != (B, 3, 2 * H, 2 * W) or conv_w.numel() != B * 3 * self.cout:
+            raise LdicError("fused_tail: image must be (B,3,2H,2W) and conv_w (B,3,Cout)")
+        sq = torch.zeros(B, dtype=torch.int64, device=x.device)
+        xo = torch.empty_like(image) if want_x_tilde else None
+        out = torch.empty(self.out_dims(B, H, W), dtype=torch.float32, device=x.device) if want_out else None
+        t = _lib.ConvTail(_ptr(image), _ptr(conv_w), _ptr(xo), _ptr(sq), 2 * H, 2 * W)
+        d = self._desc(B, H, W)
+        prof = PROFILE
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(_L().ldic_conv_forward_fused_tail(C.byref(d), _ptr(x), _ptr(self.w_packed), _ptr(self.bias_packed),
+                                                _ptr(self.gamma_bf16), _ptr(self.beta_tiled), _ptr(out), C.byref(t), _stream()),
+              "ldic_conv_forward_fused_tail")
+        if prof is not None:
+            e1.record()
+            prof.append((self, (B, H, W), e0, e1))
+        return sq, xo, out
+
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.kind == _lib.LDIC_CONV_FIRST_5x5S2:
             _req(x, torch.float32, "x")

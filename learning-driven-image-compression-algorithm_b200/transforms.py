@@ -144,6 +144,18 @@ class synthesisTransformModel(_PlannedTransform):
             t = layer(t)
         return t
 
+    def forward_nhwc_fused_tail(self, y_hat_nhwc_bf16, image_nchw, conv_w, want_x_tilde=False, want_out=False):
+        """g_s with batch_conv (model/net.py:811) and the squared level error (:864-868) fused into the last
+        deconv's epilogue.  Returns (sq_err int64[B], x_tilde or None, 16-channel g_s output or None); None when
+        the last layer is not the merged small-Cout kind (caller falls back to forward_nhwc + syntax_conv_mse)."""
+        L = self.plan()
+        if L[-1].kind != _lib.LDIC_DECONV_GS_5x5_MERGED:
+            return None
+        t = y_hat_nhwc_bf16
+        for layer in L[:-1]:
+            t = layer(t)
+        return L[-1].fused_tail(t, image_nchw, conv_w, want_x_tilde=want_x_tilde, want_out=want_out)
+
     def forward(self, inputs):
         L = self.plan()
         x = ops.nchw_to_nhwc_bf16(inputs, L[0].cin_pad) if self.cin_offset == 0 else None

@@ -64,8 +64,8 @@ def test_net_512x768_scalars(ldic):
     assert abs(v_psnr.item() - k["v_psnr"]) < PSNR_ATOL_DB
     # batch independence at full size: image 0 of a batch of 2 gives the same per-image numbers
     x2 = torch.cat([x, dw.make_input(1, 1, 512, 768)], 0).cuda()
-    out2 = net.rd_forward(x2)
-    out1 = net.rd_forward(x.cuda())
+    out2 = net.rd_forward(x2, want_xt16=True)
+    out1 = net.rd_forward(x.cuda(), want_xt16=True)
     # our kernels are batch-invariant bit for bit (g_a latent, g_s output); the torch-op context /
     # syntax branches may pick batch-dependent cuDNN algorithms, so the scalars get a tolerance
     assert torch.equal(out2["latents"]["y"][0], out1["latents"]["y"][0])
@@ -106,6 +106,25 @@ def test_syntax_branch_kernels_vs_torch_modules(ldic, B, H, W):
     o2 = net.rd_forward(x)
     assert torch.allclose(o1["bits"], o2["bits"], rtol=1e-5)
     assert (o1["sq_err"] - o2["sq_err"]).abs().max().item() <= 1e-4 * o2["sq_err"].max().item()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 512, 768)])
+def test_fused_tail_matches_separate_kernels(ldic, B, H, W):
+    """batch_conv + squared level error inside the last deconv's epilogue (ldic_conv_forward_fused_tail) against the
+    unfused path (16-channel g_s output in HBM + ldic_syntax_conv_mse): same arithmetic, exact integer sums."""
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    x = dw.make_input(7, B, H, W).cuda()
+    net.tail_fused = True
+    o1 = net.rd_forward(x, want_x_hat=True, want_xt16=True)
+    net.tail_fused = False
+    o2 = net.rd_forward(x, want_x_hat=True)
+    assert torch.equal(o1["sq_err"], o2["sq_err"])
+    assert torch.equal(o1["x_hat"], o2["x_hat"])
+    assert torch.equal(o1["latents"]["xt16"], o2["latents"]["xt16"])
+    net.tail_fused = True
+    o3 = net.rd_forward(x)                     # product configuration: nothing but the sums leaves the kernel
+    assert torch.equal(o3["sq_err"], o2["sq_err"]) and o3["latents"]["xt16"] is None
 
 
 def test_state_dict_contract(ldic):
