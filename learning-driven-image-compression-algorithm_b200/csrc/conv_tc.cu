@@ -476,6 +476,27 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         xr[c] += b4.x; xr[c + 1] += b4.y; xr[c + 2] += b4.z; xr[c + 3] += b4.w;
       }
 
+      // stores columns [c, c+n) of this thread's pixel (ngroups == 1: contiguous channels): whole 32-byte sectors
+      bool stored = false;
+      auto store_cols = [&](int c, int n) {
+        if (P.out_f32) {
+          float* dst = reinterpret_cast<float*>(P.out) + pix_base + col0 + c;
+#pragma unroll
+          for (int j = 0; j < LDW / 8; ++j) if (8 * j < n) st_global_v8(dst + 8 * j, &xr[c + 8 * j]);
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + pix_base + col0 + c;
+#pragma unroll
+          for (int j = 0; j < LDW / 16; ++j) {
+            if (16 * j < n) {
+              const float* x16 = &xr[c + j * 16];
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(x16[2 * e], x16[2 * e + 1]);
+              st_global_v8(dst + 16 * j, pk);
+            }
+          }
+        }
+      };
       if (gk) {
         // x^2 -> bf16 -> A slots (K-major, 128B swizzle: 16-byte chunk index XOR (row & 7))
         if (edbg) e_t0 = clock64();
@@ -503,23 +524,30 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         if (edbg) e_norm += clock64() - e_t0;
         tc_fence_after();
         // ---- pass 2: out = x * rsqrt(norm + beta)   (IGDN: x * sqrt = x * n * rsqrt(n)) ----
+        // The TMEM read of chunk c+1 is in flight while chunk c is normalised, and every finished chunk is
+        // stored at once (its stores drain while the next chunks are computed).
+        constexpr int NCH = CPT / LDW;
+        uint32_t tr[2][LDW];
+        tmem_ldn<LDW>(tbuf, tr[0]);
 #pragma unroll
-        for (int c = 0; c < CPT; c += LDW) {
-          uint32_t tr[LDW];
-          tmem_ldn<LDW>(tbuf + c, tr);
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int c = ch * LDW;
           tmem_ld_wait();
+          if (ch + 1 < NCH) tmem_ldn<LDW>(tbuf + c + LDW, tr[(ch + 1) & 1]);
 #pragma unroll
           for (int k = 0; k < LDW; k += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(&R.s_beta[col0 + c + k]);
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float nrm = __uint_as_float(tr[k + e]) + bb[e];
+              const float nrm = __uint_as_float(tr[ch & 1][k + e]) + bb[e];
               const float rs = rsqrt_approx(nrm);
               xr[c + k + e] *= igdn ? nrm * rs : rs;
             }
           }
+          if (P.ngroups == 1 && valid) store_cols(c, LDW);
         }
+        stored = (P.ngroups == 1);
         tc_fence_before();
         if (CL) mbar_arrive_cluster(R.buf_free_cl + 8u * bsel); else mbar_arrive(&R.buf_free[bsel]);   // norm drained: free for tile it+2
       } else if (P.act == LDIC_ACT_RELU) {
@@ -535,20 +563,9 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         // 256-bit stores: every lane writes whole 32-byte sectors of its own pixel row
         if (P.ngroups == 1) {
           // this thread's CPT columns are contiguous channels of one output pixel
-          if (P.out_f32) {
-            float* dst = reinterpret_cast<float*>(P.out) + pix_base + col0;
+          if (!stored) {
 #pragma unroll
-            for (int j = 0; j < CPT / 8; ++j) st_global_v8(dst + 8 * j, &xr[8 * j]);
-          } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + pix_base + col0;
-#pragma unroll
-            for (int j = 0; j < CPT / 16; ++j) {
-              const float* x16 = &xr[j * 16];
-              uint32_t pk[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(x16[2 * e], x16[2 * e + 1]);
-              st_global_v8(dst + 16 * j, pk);
-            }
+            for (int c = 0; c < CPT; c += LDW) store_cols(c, LDW);
           }
         } else {
           // merged sub-pixel phases: Cg (a power of two >= 8) channels per output pixel, group g = col / Cg
