@@ -48,7 +48,7 @@ constexpr int kMaxTaps = 112;
 constexpr int kMaxJobs = 16;
 constexpr int kTmemCols = 512;
 constexpr int kBufCols = 256;           // two TMEM accumulator buffers at columns 0 and 256
-constexpr int kGdnInsert = 4;            // conv stages of the next tile issued before the previous tile's GDN stages
+constexpr int kGdnInsertDefault = 4;     // conv stages of the next tile issued before the previous tile's GDN stages
 
 // one filter tap = one spatial offset of the gather + a K range: nkc 64-wide blocks starting at
 // channel a_c0 of the activation and column b_c0 of the tap's packed weight block
@@ -67,6 +67,7 @@ struct ConvParams {
   // halo variant: one (TH+dy range) x (TW+dx range) activation region per 64-channel chunk serves all taps
   int halo, SA, SB, a_slot_bytes, RW, RH, dxmin, dymin;
   int G;                    // halo: filter taps per B-ring slot (one TMA box of G*Np weight rows)
+  int gdn_insert;           // streaming kernels: conv stages of tile it+1 issued before the GDN stages of tile it
   int super_per_job;        // CTA-pair kernel: (tiles_per_job + 1) / 2 pairs of adjacent tiles per job
   int ngroups, Cg;          // accumulator columns = ngroups x Cg
   int sy, sx;               // output pixel = grid pixel * (sy,sx) + job offset (+ sub-pixel group offset)
@@ -662,7 +663,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Schedule (identical in all roles).  The CTA walks its tiles it = 0,1,..; tile `it` accumulates into
   // TMEM buffer it&1 (columns 0 / 256).  With the GDN epilogue, the gamma contraction of tile it-1
   // (gk ring stages whose A half is written by the epilogue warps) is issued after the first
-  // min(kGdnInsert, nkb) conv stages of tile `it`, into the buffer tile it-1 has just been drained from
+  // min(P.gdn_insert, nkb) conv stages of tile `it`, into the buffer tile it-1 has just been drained from
   // (the norm overwrites the accumulator in place), so the tensor pipe never waits for the epilogue.
   const int gk = gdn ? P.gdn_kblocks : 0;
   const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -704,7 +705,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             my_w1 = (uint32_t)t.a_c0 | ((uint32_t)t.b_c0 << 16);
           }
         }
-        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
         const int x0 = tc.x0 * cs, y0 = tc.y0 * cs;
         int cb = 0;
         for (int tp = 0; tp < ntaps; ++tp) {
@@ -776,7 +777,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int it = 0; it < ntiles_cta; ++it) {
         const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
         if (tc.job != cur_job) { cur_job = tc.job; nkb = P.jobs[cur_job].nkb; }
-        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
         const int bsel = it & 1;
         long long t0 = 0;
         if (dbg) t0 = clock64();
@@ -804,7 +805,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     EpiRing R;
     R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
-    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = kGdnInsert;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
     epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
   }
 
@@ -916,7 +917,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             my_w1 = (uint32_t)t.a_c0 | ((uint32_t)t.b_c0 << 16);
           }
         }
-        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
         const int x0 = tc.x0 * cs, y0 = tc.y0 * cs;
         int cb = 0;
         for (int tp = 0; tp < ntaps; ++tp) {
@@ -981,7 +982,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int it = 0; it < nt; ++it) {
         const int job = (pi + it * npairs) / P.super_per_job;
         if (job != cur_job) { cur_job = job; nkb = P.jobs[cur_job].nkb; }
-        const int jins = (gk && it > 0) ? (nkb < kGdnInsert ? nkb : kGdnInsert) : -1;
+        const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
         const int bsel = it & 1;
         if (dbg) t0 = clock64();
         mbar_wait_cl(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
@@ -1007,7 +1008,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     EpiRing R;
     R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
-    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = kGdnInsert;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
     R.t_first = pi; R.t_stride = npairs; R.rank = (int)rank;
     R.buf_free_cl = mapa_shared(smem_u32(buf_free), 0); R.x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0);
     epilogue_role<NP, true>(P, R, tmem_base, gk, nt, warp, lane);
@@ -1749,7 +1750,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     EpiRing R;
     R.ring_base = ring_base; R.slot_bytes = kATileBytes; R.nslots = (uint32_t)S; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
-    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = kGdnInsert;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
     epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
   }
 
@@ -2168,6 +2169,7 @@ int forward_first(const LdicConvDesc* d, const Layer& L, const void* x, const vo
   P.jobs[0] = L.jobs[0];
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
   P.dbg_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
+  P.gdn_insert = kGdnInsertDefault;
   const int fixed = (2 + L.Np / 64) * L.Np * kBlockK * 2 + 2 * kRawSlot + 256 + 2 * L.Np * 4 + 1024;
   int S = (227 * 1024 - fixed) / kATileBytes;
   if (S > kMaxStages) S = kMaxStages;
@@ -2342,6 +2344,8 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
   if (strided) for (int t = 0; t < L.ntaps_total; ++t) { P.taps[t].dx = (short)(2 * L.taps[t].dx + L.taps[t].px); P.taps[t].px = 0; }
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
   P.dbg_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
+  P.gdn_insert = kGdnInsertDefault;
+  if (const char* e = getenv("LDIC_GDN_INSERT")) { int v = atoi(e); if (v >= 1 && v <= 16) P.gdn_insert = v; }   // tuning aid
   if (tail) {
     P.tail_x = tail->x_nchw; P.tail_w = tail->w; P.tail_xo = tail->x_tilde_nchw; P.tail_sq = tail->sq_err;
     P.tail_H = tail->H; P.tail_W = tail->W;
