@@ -151,6 +151,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     ldic_b200._lib.check(ldic_b200._lib.load().ldic_check_device(local), "device")
     if world > 1:
+        # keep stdout to the one JSON line (some boxes export NCCL_DEBUG=VERSION, which prints to stdout)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     hbm_peak, tc_peak_sus, tc_peak_burst, peak_src = peaks()
