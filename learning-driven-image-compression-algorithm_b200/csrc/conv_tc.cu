@@ -429,7 +429,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
     const bool igdn = (P.act == LDIC_ACT_IGDN);
     uint32_t sbase = 0;                     // ring position of the first stage of tile `it`'s stream
     const bool edbg = P.dbg != nullptr && blockIdx.x == 0 && warp == 0;
-    long long e_acc = 0, e_norm = 0, e_slot = 0, e_t0 = 0;
+    long long e_acc = 0, e_norm = 0, e_slot = 0, e_t0 = 0, e_p1 = 0, e_p2 = 0, e_t1 = 0;
     const long long e_begin = edbg ? clock64() : 0;
     for (int it = 0; it < ntiles_cta; ++it) {
       const TileCoord tc = CL ? decode_tile2(P, R.t_first + it * R.t_stride, R.rank) : decode_tile(P, blockIdx.x + it * gridDim.x);
@@ -455,7 +455,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
 
       if (edbg) e_t0 = clock64();
       mbar_wait(&R.acc_full[bsel], par);
-      if (edbg) e_acc += clock64() - e_t0;
+      if (edbg) { e_t1 = clock64(); e_acc += e_t1 - e_t0; }
       tc_fence_after();
 
       // ---- pass 1: accumulator -> registers (+bias) ----
@@ -500,12 +500,14 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       };
       if (gk) {
         // x^2 -> bf16 -> A slots (K-major, 128B swizzle: 16-byte chunk index XOR (row & 7))
-        if (edbg) e_t0 = clock64();
-        for (int kb = 0; kb < gk; ++kb) {
-          const uint32_t kc2 = gpos + kb;
+        if (edbg) { e_t0 = clock64(); e_p1 += e_t0 - e_t1; }
+        {
+          // the gk operand slots are released in ring order by the MMA warp's commits: waiting for the LAST one
+          // covers all of them (one barrier round trip instead of gk)
+          const uint32_t kc2 = gpos + (uint32_t)gk - 1u;
           mbar_wait(&R.empty_bar[kc2 % R.nslots], ((kc2 / R.nslots) & 1) ^ 1);
         }
-        if (edbg) e_slot += clock64() - e_t0;
+        if (edbg) { e_t1 = clock64(); e_slot += e_t1 - e_t0; }
         const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
 #pragma unroll
         for (int j = 0; j < CPT / 8; ++j) {
@@ -520,9 +522,9 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
         if (CL) mbar_arrive_cluster(R.x2_ready_cl + 8u * bsel); else mbar_arrive(&R.x2_ready[bsel]);
-        if (edbg) e_t0 = clock64();
+        if (edbg) { e_t0 = clock64(); e_p1 += e_t0 - e_t1; }
         mbar_wait(&R.norm_full[bsel], par);
-        if (edbg) e_norm += clock64() - e_t0;
+        if (edbg) { e_t1 = clock64(); e_norm += e_t1 - e_t0; }
         tc_fence_after();
         // ---- pass 2: out = x * rsqrt(norm + beta)   (IGDN: x * sqrt = x * n * rsqrt(n)) ----
         // The TMEM read of chunk c+1 is in flight while chunk c is normalised, and every finished chunk is
@@ -594,6 +596,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
           }
         }
       }
+      if (edbg) e_p2 += clock64() - e_t1;
       if constexpr (NP <= 128) if (P.tail_x) {
         // exact integer sums: the order of the atomic adds does not matter.  One image per tile (TN == 1): one
         // warp-level sum and one atomic per warp; tiles spanning images: one atomic per contributing thread.
@@ -610,6 +613,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
     if (edbg && lane == 0) {
       P.dbg[16] = (unsigned long long)(clock64() - e_begin); P.dbg[17] = (unsigned long long)e_acc;
       P.dbg[18] = (unsigned long long)e_norm; P.dbg[19] = (unsigned long long)e_slot; P.dbg[20] = (unsigned long long)ntiles_cta;
+      P.dbg[21] = (unsigned long long)e_p1; P.dbg[22] = (unsigned long long)e_p2;
     }
 }
 
@@ -2170,6 +2174,11 @@ int forward_first(const LdicConvDesc* d, const Layer& L, const void* x, const vo
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
   P.dbg_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
   P.gdn_insert = kGdnInsertDefault;
+  static unsigned long long* dbg_buf1 = nullptr;
+  const bool want_dbg = getenv("LDIC_DEBUG_TIMING") != nullptr;
+  if (want_dbg && !dbg_buf1) cudaMalloc(&dbg_buf1, 32 * sizeof(unsigned long long));
+  if (want_dbg) cudaMemset(dbg_buf1, 0, 32 * sizeof(unsigned long long));
+  P.dbg = want_dbg ? dbg_buf1 : nullptr;
   const int fixed = (2 + L.Np / 64) * L.Np * kBlockK * 2 + 2 * kRawSlot + 256 + 2 * L.Np * 4 + 1024;
   int S = (227 * 1024 - fixed) / kATileBytes;
   if (S > kMaxStages) S = kMaxStages;
@@ -2198,11 +2207,19 @@ int forward_first(const LdicConvDesc* d, const Layer& L, const void* x, const vo
     tmG = tmW;
   }
   switch (L.Np) {
-    case 64: return launch_first<64>(tmX, tmW, tmG, P, st);
-    case 128: return launch_first<128>(tmX, tmW, tmG, P, st);
-    case 192: return launch_first<192>(tmX, tmW, tmG, P, st);
+    case 64: rc = launch_first<64>(tmX, tmW, tmG, P, st); break;
+    case 128: rc = launch_first<128>(tmX, tmW, tmG, P, st); break;
+    case 192: rc = launch_first<192>(tmX, tmW, tmG, P, st); break;
+    default: return fail(LDIC_EINVAL, "first conv: unsupported Np %d", L.Np);
   }
-  return fail(LDIC_EINVAL, "first conv: unsupported Np %d", L.Np);
+  if (want_dbg && rc == LDIC_OK) {
+    unsigned long long h[32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_buf1, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[ldic timing] first layer: epilogue total %llu cyc over %llu tiles: wait_acc %llu wait_norm %llu wait_slots %llu | busy pass 1 %llu pass 2 + stores %llu\n",
+            h[16], h[20], h[17], h[18], h[19], h[21], h[22]);
+  }
+  return rc;
 }
 
 unsigned long long* g_timeout_host = nullptr;
@@ -2515,6 +2532,7 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
             h[4] ? (double)h[0] / h[4] : 0.0, h[4] ? (double)h[1] / h[4] : 0.0, h[8], h[9]);
     fprintf(stderr, "[ldic timing]   epilogue total %llu cyc over %llu tiles: wait_acc %llu wait_norm %llu wait_slots %llu; mma wait_afull %llu\n",
             h[16], h[20], h[17], h[18], h[19], h[6]);
+    fprintf(stderr, "[ldic timing]   epilogue busy: pass 1 (acc -> x^2 written) %llu, pass 2 + stores (or whole epilogue without GDN) %llu\n", h[21], h[22]);
   }
   return rc;
 }

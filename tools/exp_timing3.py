@@ -25,3 +25,12 @@ for name, layer, x in layers:
     layer(x)
     torch.cuda.synchronize()
     del os.environ["LDIC_DEBUG_TIMING"]
+w1 = torch.randn(C, 3, 5, 5, device=dev) * 0.1
+l1 = ops.ConvTC(_lib.LDIC_CONV_FIRST_5x5S2, w1, b, act=_lib.ACT_GDN, gdn=g)
+x1 = torch.randn(16, 3, 512, 768, device=dev)
+for _ in range(2): l1(x1)
+torch.cuda.synchronize()
+os.environ["LDIC_DEBUG_TIMING"] = "1"
+l1(x1); torch.cuda.synchronize()
+os.environ["LDIC_DEBUG_NOSTORE"] = "1"
+l1(x1); torch.cuda.synchronize()
