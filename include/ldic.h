@@ -244,6 +244,19 @@ typedef struct {
 LDIC_API long long ldic_syntax_workspace_elems(int B, int h, int w, int N, int M);
 LDIC_API int ldic_syntax_branch(const LdicSyntaxArgs* args, void* stream);
 
+/* ---- a12: progressive trit-plane quantisation + per-plane likelihood (BASELINE configs[4]) ----------
+ * Builder-defined extension: the reference's model/Trit_Plane.py:25-57 crashes and holds neither
+ * trit planes nor a likelihood, so there is NO reference oracle for this entry point beyond the quantiser /
+ * Gaussian mass it shares with a6/a7 ("parity unpinned").
+ *   q = clamp(round(v - mu), -H, H), H = (3^L - 1)/2;  q + H = sum_l t_l 3^l (t_l in {0,1,2});
+ *   L_l = P(t_l | more significant trits) from the interval thirds of N(mu, max(sigma, scale_bound)), >= lik_bound.
+ * planes: int8 [L][n] (plane L-1 most significant) or NULL; q_out: int32 [n] or NULL; sum_ln_per_plane: float [L];
+ * workspace: ldic_tritplane_workspace_bytes() bytes, zeroed once before the first use.  mu may be NULL (= 0). */
+LDIC_API size_t ldic_tritplane_workspace_bytes(void);
+LDIC_API int ldic_tritplane_likelihood(const float* v, const float* mu, const float* sigma, long long n, int L,
+                              float scale_bound, float lik_bound, signed char* planes, int* q_out,
+                              float* sum_ln_per_plane, void* workspace, void* stream);
+
 /* Diagnostics: every in-kernel barrier wait of the conv kernels is bounded; a starved wait records
  * {flag, block, thread, barrier byte offset in dynamic shared memory, parity} in host-mapped memory and
  * traps.  Returns 1 and fills out5 when a timeout has been recorded in this process, else 0 (host call,

@@ -104,6 +104,9 @@ _SIGS = {
                                     C.c_void_p, C.c_void_p]),
     "ldic_syntax_workspace_elems": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ldic_syntax_branch": (C.c_int, [C.POINTER(SyntaxArgs), C.c_void_p]),
+    "ldic_tritplane_workspace_bytes": (C.c_size_t, []),
+    "ldic_tritplane_likelihood": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_float,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldic_debug_last_timeout": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "ldic_conv_forward_fused_tail": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.POINTER(ConvTail), C.c_void_p]),

@@ -214,6 +214,35 @@ def gaussian_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch
 
 
 # --------------------------------------------------------------------------------------
+# a12 (builder-defined extension, no reference oracle: see include/ldic.h)
+# --------------------------------------------------------------------------------------
+_tp_ws_cache = {}
+
+
+def tritplane_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch.Tensor] = None, planes: int = 4, *,
+                         scale_bound: float = 0.11, lik_bound: float = 1e-9, want_planes: bool = True, want_q: bool = True):
+    """Trit planes (int8 [L, *v.shape]), symbols q = clamp(round(v - mu)) (int32) and sum(ln L_l) per plane (float [L])."""
+    v = _req(v, torch.float32, "v").contiguous()
+    sigma = _req(sigma, torch.float32, "sigma").contiguous()
+    if mu is not None:
+        mu = _req(mu, torch.float32, "mu").contiguous()
+    if sigma.shape != v.shape or (mu is not None and mu.shape != v.shape):
+        raise LdicError("tritplane: v, mu, sigma must have the same shape")
+    n = v.numel()
+    key = v.device.index if v.device.index is not None else torch.cuda.current_device()
+    ws = _tp_ws_cache.get(key)
+    if ws is None:
+        ws = torch.zeros((int(_L().ldic_tritplane_workspace_bytes()) + 7) // 8, dtype=torch.int64, device=v.device)
+        _tp_ws_cache[key] = ws
+    pl = torch.empty((planes,) + tuple(v.shape), dtype=torch.int8, device=v.device) if want_planes else None
+    q = torch.empty(v.shape, dtype=torch.int32, device=v.device) if want_q else None
+    sums = torch.empty(planes, dtype=torch.float32, device=v.device)
+    check(_L().ldic_tritplane_likelihood(_ptr(v), _ptr(mu), _ptr(sigma), n, int(planes), float(scale_bound), float(lik_bound),
+                                         _ptr(pl), _ptr(q), _ptr(sums), _ptr(ws), _stream()), "ldic_tritplane_likelihood")
+    return pl, q, sums
+
+
+# --------------------------------------------------------------------------------------
 # a11
 # --------------------------------------------------------------------------------------
 def mse_sum(x: torch.Tensor, x_tilde: torch.Tensor, clamp_pm1: bool = False) -> torch.Tensor:
