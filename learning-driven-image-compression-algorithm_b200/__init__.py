@@ -11,6 +11,7 @@ from .layers import (GDN, GaussianConditional, GaussianModel, LowerBound, ModelG
 from .transforms import (analysisTransformModel, synthesisTransformModel, h_analysisTransformModel,  # noqa: F401
                          h_synthesisTransformModel)
 from .net import Net                                        # noqa: F401
+from . import eval as evaluation                            # noqa: F401  (eval_net.py driver)
 
 __all__ = ["GDN", "ModelGDN", "ModelIGDN", "LowerBound", "NonNegativeParametrizer", "GaussianModel",
            "GaussianConditional", "bypass_round", "ste_round", "analysisTransformModel", "synthesisTransformModel",

@@ -1,0 +1,97 @@
+"""Evaluation driver of the reference (eval_net.py:19-128, the branch without pre-processing) on the B200 path.
+
+What the reference does per image and this module reproduces:
+  * ToTensor -> (3,h,w) in [0,1]; pad with ONES at the bottom / right to a multiple of 64 (eval_net.py:68-81);
+    map to [-1,1] (:84);
+  * Net((1,h,w,3),(1,h,w,3), is_high, post_processing) -- the UNPADDED size is the bpp denominator
+    (model/net.py:856-859) while v_mse / v_psnr are taken over the padded tensor (:864-869);
+  * load_state_dict(torch.load(weight_path), strict=True); forward(data, 'test', num).
+
+Unlike the reference (one image per forward, a new Net per image) images that share a padded size are batched;
+per-image bpp is formed from the per-image sums of ln L (the reference only returns the batch mean).
+The module never touches a CPU fallback: tensors go to the current CUDA device and through libldic_b200.
+"""
+from __future__ import annotations
+
+import glob
+import math
+from typing import Dict, Iterable, List, Sequence, Tuple
+
+import torch
+
+from .layers import psnr_from_sq_err
+from .net import Net
+
+
+def pad_to_multiple(img: torch.Tensor, multiple: int = 64) -> torch.Tensor:
+    """eval_net.py:68-84: (3,h,w) in [0,1] -> (1,3,hp,wp) in [-1,1], padded with ONES (white) bottom / right."""
+    if img.dim() != 3:
+        raise ValueError("expected a (C,h,w) image")
+    c, h, w = img.shape
+    hp = h if h % multiple == 0 else (h // multiple) * multiple + multiple
+    wp = w if w % multiple == 0 else (w // multiple) * multiple + multiple
+    out = torch.ones(c, hp, wp, dtype=img.dtype, device=img.device)
+    out[:, :h, :w] = img
+    return out.unsqueeze(0) * 2.0 - 1.0
+
+
+def load_image(path: str) -> torch.Tensor:
+    """PIL -> (3,h,w) float32 in [0,1] (what torchvision's ToTensor returns for an 8-bit RGB image)."""
+    from PIL import Image          # optional dependency, only for reading files
+    import numpy as np
+    a = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+    return torch.from_numpy(a).permute(2, 0, 1).float().div_(255.0)
+
+
+@torch.no_grad()
+def evaluate_images(net: Net, images: Sequence[torch.Tensor], batch_size: int = 16) -> List[Dict[str, float]]:
+    """Per-image {'bpp', 'psnr', 'mse', 'h', 'w'} exactly as the reference forms them for a batch of one
+    (bpp over the unpadded h*w, MSE/PSNR over the padded tensor).  Images are grouped by padded size."""
+    dev = next(net.parameters()).device
+    groups: Dict[Tuple[int, int], List[int]] = {}
+    padded = []
+    for i, img in enumerate(images):
+        x = pad_to_multiple(img.float())
+        padded.append(x)
+        groups.setdefault((x.shape[2], x.shape[3]), []).append(i)
+    out: List[Dict[str, float]] = [None] * len(images)          # type: ignore
+    for (hp, wp), idx in groups.items():
+        for k in range(0, len(idx), batch_size):
+            chunk = idx[k:k + batch_size]
+            xb = torch.cat([padded[i] for i in chunk], 0).to(dev, non_blocking=True)
+            r = net.rd_forward(xb, per_image_bits=True)
+            v_mse, _ = psnr_from_sq_err(r["sq_err"], 3 * hp * wp)
+            bits = r["bits_per_image"].sum(1).cpu()              # sum of ln L over the three streams, per image
+            for j, i in enumerate(chunk):
+                h, w = images[i].shape[1], images[i].shape[2]
+                mse = float(v_mse[j])
+                out[i] = {"bpp": float(bits[j]) / (-math.log(2) * h * w), "mse": mse,
+                          "psnr": 20.0 * math.log10(255.0 / math.sqrt(mse)) if mse > 0 else float("inf"), "h": h, "w": w}
+    return out
+
+
+def val(data_path: str, weight_path: str, is_high: bool = False, post_processing: bool = False, batch_size: int = 16,
+        device: str = "cuda"):
+    """eval_net.py:19 `val` (pre_processing=False branch): prints the per-image line and the averages."""
+    paths = sorted(glob.glob(data_path))
+    images = [load_image(p) for p in paths]
+    net = Net((1, 64, 64, 3), (1, 64, 64, 3), is_high, post_processing).to(device).eval()
+    net.load_state_dict(torch.load(weight_path, map_location=device), strict=True)
+    res = evaluate_images(net, images, batch_size)
+    for p, r in zip(paths, res):
+        print(p, r["bpp"], r["psnr"], r["mse"])
+    n = max(len(res), 1)
+    print('[WITHOUT PRE-PROCESSING] bpp: %.4f psnr: %.4f  v_mse: %.4f' % (
+        sum(r["bpp"] for r in res) / n, sum(r["psnr"] for r in res) / n, sum(r["mse"] for r in res) / n))
+    return res
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser(description="eval_net.py of the reference on libldic_b200")
+    ap.add_argument("--data", required=True, help="glob of image files")
+    ap.add_argument("--weights", required=True, help="reference checkpoint (state dict)")
+    ap.add_argument("--high", action="store_true")
+    ap.add_argument("--batch", type=int, default=16)
+    a = ap.parse_args()
+    val(a.data, a.weights, is_high=a.high, batch_size=a.batch)

@@ -234,12 +234,13 @@ class Net(nn.Module):
     # -- the hot path -----------------------------------------------------------------------
     @torch.no_grad()
     def rd_forward(self, inputs: torch.Tensor, want_x_hat: bool = False, want_likelihoods: bool = False,
-                   want_xt16: bool = False) -> Dict[str, torch.Tensor]:
+                   want_xt16: bool = False, per_image_bits: bool = False) -> Dict[str, torch.Tensor]:
         """Rate-distortion forward of Net.forward(mode='test') (model/net.py:539-871).
         Returns the per-stream sum(ln L) (`bits` = [z, y, syntax]), the exact per-image
         squared-error sums and, on request, x_hat / likelihood tensors."""
         if not inputs.is_cuda:
             raise ops.LdicError("Net runs on CUDA only (no CPU fallback)")
+        want_likelihoods = want_likelihoods or per_image_bits
         x = inputs.contiguous().float()
         B, _, H, W = x.shape
         N, M = self.N, self.M
@@ -315,6 +316,9 @@ class Net(nn.Module):
             out["x_hat"] = x_hat
         if want_likelihoods:
             out["likelihoods"] = {"y": lik_y.permute(0, 3, 1, 2), "z": lik_z.permute(0, 3, 1, 2), "syntax": lik_syn}
+        if per_image_bits:       # sum(ln L) per image and stream (the reference only forms the batch total, :857)
+            out["bits_per_image"] = torch.stack([torch.log(l.reshape(B, -1).double()).sum(1)
+                                                 for l in (lik_z, lik_y, lik_syn)], 1)
         out["latents"] = {"y": y, "z": z, "h2": h2, "ctx": ctx, "z3_syntax": z3_syntax, "conv_w": conv_w, "xt16": xt16}
         return out
 

@@ -127,6 +127,23 @@ def test_fused_tail_matches_separate_kernels(ldic, B, H, W):
     assert torch.equal(o3["sq_err"], o2["sq_err"]) and o3["latents"]["xt16"] is None
 
 
+def test_eval_driver_matches_reference_eval_net(ldic):
+    """eval_net.py:68-96 (pad with ones to x64, bpp over the unpadded size) through ldic_b200.evaluation, against the
+    golden fixture the unmodified reference produced for a 60x50 image; batching does not change per-image numbers."""
+    d = L("net_evalpad_60x50.npz")
+    net = build(ldic, d)
+    img = d["img"]
+    x = ldic.evaluation.pad_to_multiple(img)
+    assert torch.equal(x, rp.eval_pad(img))
+    other = torch.rand(3, 64, 40, generator=torch.Generator().manual_seed(1))
+    res = ldic.evaluation.evaluate_images(net, [img, other, img], batch_size=8)
+    for r in (res[0], res[2]):
+        assert abs(r["bpp"] / d["bpp"].item() - 1) < BPP_RTOL
+        assert abs(r["psnr"] - d["v_psnr"].item()) < PSNR_ATOL_DB
+        assert (r["h"], r["w"]) == (60, 50)
+    assert res[0] == res[2] and res[1]["w"] == 40
+
+
 def test_state_dict_contract(ldic):
     net = ldic.Net((1, 64, 64, 3), (1, 64, 64, 3), False, False)
     sd = dw.make_state_dict(0)

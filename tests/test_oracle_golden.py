@@ -117,3 +117,18 @@ def test_net_default_gain_and_config1():
     # thread-count dependent summation order in torch.sum: compare scalars to 1e-6
     for k in ("bpp", "v_mse", "v_psnr", "bits"):
         assert torch.allclose(o[k], d[k], rtol=2e-6, atol=0), k
+
+
+def test_eval_pad_matches_driver_padding():
+    """ldic_b200.evaluation.pad_to_multiple == eval_net.py:68-84 (CPU-only host logic, no kernels involved)."""
+    import importlib.util, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # import the module file directly: the package __init__ is importable on CPU, only kernel calls need a GPU
+    sys.path.insert(0, root)
+    import ldic_b200
+    for h, w in ((60, 50), (64, 64), (65, 128), (1, 1)):
+        img = torch.rand(3, h, w)
+        a = ldic_b200.evaluation.pad_to_multiple(img)
+        b = rp.eval_pad(img)
+        assert a.shape == b.shape and torch.equal(a, b)
+        assert a.shape[2] % 64 == 0 and a.shape[3] % 64 == 0
