@@ -257,6 +257,24 @@ LDIC_API int ldic_tritplane_likelihood(const float* v, const float* mu, const fl
                               float scale_bound, float lik_bound, signed char* planes, int* q_out,
                               float* sum_ln_per_plane, void* workspace, void* stream);
 
+/* ---- f2: window attention (layers/win_attention.py:38-209; blocks of layers/layers.py:56-111) --------------
+ * WinBasedAttention.forward = x + proj(W-MSA(qkv(x))) on 8x8 (or 4x4) windows with an optional cyclic shift.  The
+ * qkv and proj Linears are 1x1 convs (ldic_conv_forward, LDIC_CONV_1x1: three of them, q pre-scaled by
+ * head_dim^-0.5, :108); the entry points below are what lies between and around them.
+ *   ldic_window_attention_bias: bias[h][i][j] = table[index[i][j]][h]  (:101-104); table float [(2ws-1)^2][heads],
+ *     index int64 [ws^2][ws^2] (the module's relative_position_index buffer), bias float [heads][ws^2][ws^2].
+ *   ldic_window_attention_core: q, k, v, out: bf16 NHWC token images [B][H][W][C]; for every window and head
+ *     out = softmax(q k^T + bias + shift mask) v (:106-123).  window_partition / window_reverse (:6-36), torch.roll
+ *     and its reverse (:181-200) are index arithmetic; the 0 / -100 mask of :160-177 is derived from the token
+ *     coordinates.  C % heads == 0, C % 8 == 0, head_dim even and <= 32, heads <= 16, ws in {4, 8} dividing H, W.
+ *   ldic_residual_nhwc_to_nchw_f32: y = shortcut + o (:204-205), o NHWC fp32 with Cp >= C channels per pixel.   */
+LDIC_API int ldic_window_attention_bias(const float* table, const long long* index, float* bias, int heads, int ws,
+                               void* stream);
+LDIC_API int ldic_window_attention_core(const void* q, const void* k, const void* v, const float* bias, void* out, int B,
+                               int H, int W, int C, int heads, int ws, int shift, void* stream);
+LDIC_API int ldic_residual_nhwc_to_nchw_f32(const float* o_nhwc, const float* shortcut_nchw, float* y_nchw, int B, int C,
+                                   int H, int W, int Cp, void* stream);
+
 /* Diagnostics: every in-kernel barrier wait of the conv kernels is bounded; a starved wait records
  * {flag, block, thread, barrier byte offset in dynamic shared memory, parity} in host-mapped memory and
  * traps.  Returns 1 and fills out5 when a timeout has been recorded in this process, else 0 (host call,

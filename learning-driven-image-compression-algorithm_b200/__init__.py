@@ -7,12 +7,13 @@ The directory name carries the reference's (hyphenated) name; import it as ``ldi
 from . import _lib, ops                                     # noqa: F401
 from ._lib import LdicError, EXPORTED_SYMBOLS, lib_path     # noqa: F401
 from .layers import (GDN, GaussianConditional, GaussianModel, LowerBound, ModelGDN, ModelIGDN,   # noqa: F401
-                     NonNegativeParametrizer, bypass_round, ste_round, psnr_from_sq_err)
+                     NonNegativeParametrizer, WinBasedAttention, WindowAttention, bypass_round, ste_round,
+                     psnr_from_sq_err)
 from .transforms import (analysisTransformModel, synthesisTransformModel, h_analysisTransformModel,  # noqa: F401
                          h_synthesisTransformModel)
 from .net import Net                                        # noqa: F401
 from . import eval as evaluation                            # noqa: F401  (eval_net.py driver)
 
 __all__ = ["GDN", "ModelGDN", "ModelIGDN", "LowerBound", "NonNegativeParametrizer", "GaussianModel",
-           "GaussianConditional", "bypass_round", "ste_round", "analysisTransformModel", "synthesisTransformModel",
+           "GaussianConditional", "WindowAttention", "WinBasedAttention", "bypass_round", "ste_round", "analysisTransformModel", "synthesisTransformModel",
            "h_analysisTransformModel", "h_synthesisTransformModel", "Net", "ops", "LdicError"]

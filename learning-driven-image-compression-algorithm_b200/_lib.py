@@ -107,6 +107,11 @@ _SIGS = {
     "ldic_tritplane_workspace_bytes": (C.c_size_t, []),
     "ldic_tritplane_likelihood": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_window_attention_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ldic_window_attention_core": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ldic_residual_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_void_p]),
     "ldic_debug_last_timeout": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "ldic_conv_forward_fused_tail": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.POINTER(ConvTail), C.c_void_p]),

@@ -1,0 +1,260 @@
+// Window attention core: softmax(q k^T + rel-pos bias + shift mask) v for one 8x8 (or 4x4) window
+// per CTA, one warp per head, bf16 tensor-core MMAs with fp32 softmax.
+//   reference: layers/win_attention.py:96-126 (WindowAttention.forward between the qkv and proj Linears),
+//              :6-36 (window_partition / window_reverse), :160-193 (shift mask, cyclic shift).
+// The qkv and proj projections run as 1x1 convs on the tcgen05 kernel (conv_tc.cu); this kernel does the part in
+// between.  Window partition, cyclic shift and its reverse are index arithmetic on the NHWC token image: token
+// (i, j) of window (wy, wx) is pixel ((wy*ws + i + shift) mod H, (wx*ws + j + shift) mod W), read and written in
+// place (no rolled / partitioned copies).  The 0 / -100 shift mask is recomputed from the region ids of the two
+// tokens (:160-177) instead of being built on the host every call.
+//
+// Per CTA: the window's q | k | v rows (N tokens x 3*C bf16) are staged in shared memory with coalesced 16-byte
+// loads (row pitch padded by 16 B so that the 8 fragment rows hit different banks), V is transposed per head.
+// Per warp (= head): S = Q K^T with mma.sync.m16n8k16 (head_dim padded to a multiple of 16 with zeros), softmax on
+// the accumulator fragments (row max / sum across the 4 lanes of a quad), P (bf16) is re-used as the A fragment of
+// O = P V.  FLOPs are 14 % of the block; the kernel is bound by the 96 KB of qkv it streams per window.
+#include "common.cuh"
+
+using namespace ldic;
+
+namespace {
+
+constexpr int kWaMaxTokens = 64;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct WaParams {
+  const __nv_bfloat16 *q, *k, *v;      // [B*H*W][C] token images (q already scaled by head_dim^-0.5)
+  __nv_bfloat16* out;                  // [B*H*W][C]
+  const float* bias;                   // [heads][N][N] relative position bias (already gathered)
+  int B, H, W, C, heads, ws, shift;
+};
+
+// HD = head_dim padded to a multiple of 16 (24 -> 32, 16 -> 16); N = ws*ws tokens (64 or 16)
+template <int HD, int N>
+__global__ void __launch_bounds__(256) k_window_attention(WaParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int C = P.C, hd = C / P.heads;
+  const int pitch = 3 * C * 2 + 16;                      // bytes per token row (q | k | v), +16: bank spread
+  uint8_t* s_qkv = smem;                                 // [N][pitch]
+  __nv_bfloat16* s_vt = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)N * pitch);   // [heads][HD][N + 8]
+  __shared__ int s_pix[kWaMaxTokens];                    // token -> pixel index in the (B,H,W) image
+  __shared__ int s_reg[kWaMaxTokens];                    // token -> region id of the shift mask
+
+  const int ws = P.ws, nwx = P.W / ws, nwy = P.H / ws;
+  const int win = blockIdx.x;
+  const int b = win / (nwx * nwy), wr = win % (nwx * nwy), wy = wr / nwx, wx = wr % nwx;
+  if (threadIdx.x < N) {
+    const int i = threadIdx.x / ws, j = threadIdx.x % ws;
+    const int ys = wy * ws + i, xs = wx * ws + j;        // position in the shifted image
+    const int y = (ys + P.shift) % P.H, x = (xs + P.shift) % P.W;      // torch.roll(x, -shift): shifted[p] = x[p + shift]
+    s_pix[threadIdx.x] = (b * P.H + y) * P.W + x;
+    int ry = 0, rx = 0;
+    if (P.shift > 0) {
+      ry = ys < P.H - ws ? 0 : (ys < P.H - P.shift ? 1 : 2);
+      rx = xs < P.W - ws ? 0 : (xs < P.W - P.shift ? 1 : 2);
+    }
+    s_reg[threadIdx.x] = ry * 3 + rx;
+  }
+  __syncthreads();
+  // ---- stage q | k | v rows: 16-byte chunks, C/8 chunks per tensor and token ----
+  {
+    const int cpt = C / 8;
+    for (int i = threadIdx.x; i < N * 3 * cpt; i += blockDim.x) {
+      const int t = i / (3 * cpt), r = i - t * 3 * cpt, which = r / cpt, c8 = r - which * cpt;
+      const __nv_bfloat16* src = (which == 0 ? P.q : which == 1 ? P.k : P.v) + (long long)s_pix[t] * C + c8 * 8;
+      *reinterpret_cast<uint4*>(s_qkv + (size_t)t * pitch + (which * C + c8 * 8) * 2) = __ldg(reinterpret_cast<const uint4*>(src));
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  constexpr int VP = N + 8;                              // pitch of the transposed V rows (elements)
+  for (int h = warp; h < P.heads; h += blockDim.x / 32) {
+    // ---- V^T of this head: s_vt[h][d][token] (zeros for the padded dims) ----
+    __nv_bfloat16* vt = s_vt + (size_t)h * HD * VP;
+    for (int i = lane; i < HD * N; i += 32) {
+      const int d = i / N, tok = i - d * N;
+      vt[d * VP + tok] = d < hd ? *reinterpret_cast<const __nv_bfloat16*>(s_qkv + (size_t)tok * pitch + (2 * C + h * hd + d) * 2)
+                                : __float2bfloat16_rn(0.f);
+    }
+    __syncwarp();
+    const float* bias_h = P.bias + (size_t)h * N * N;
+#pragma unroll 1
+    for (int mt = 0; mt < N / 16; ++mt) {                // 16 query rows at a time
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      // A fragments of Q: k-tiles of 16 dims
+      uint32_t qa[HD / 16][4];
+#pragma unroll
+      for (int kt = 0; kt < HD / 16; ++kt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = (e & 1) ? r1 : r0, col = kt * 16 + t4 * 2 + ((e & 2) ? 8 : 0);
+          qa[kt][e] = col < hd ? *reinterpret_cast<const uint32_t*>(s_qkv + (size_t)row * pitch + (h * hd + col) * 2) : 0u;
+        }
+      }
+      // S = Q K^T : N/8 key tiles
+      float s[N / 8][4];
+#pragma unroll
+      for (int nt = 0; nt < N / 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const uint8_t* krow = s_qkv + (size_t)(nt * 8 + g) * pitch + (C + h * hd) * 2;
+#pragma unroll
+        for (int kt = 0; kt < HD / 16; ++kt) {
+          const int c0 = kt * 16 + t4 * 2, c1 = c0 + 8;
+          const uint32_t b0 = c0 < hd ? *reinterpret_cast<const uint32_t*>(krow + c0 * 2) : 0u;
+          const uint32_t b1 = c1 < hd ? *reinterpret_cast<const uint32_t*>(krow + c1 * 2) : 0u;
+          mma_bf16_16816(s[nt], qa[kt], b0, b1);
+        }
+      }
+      // + bias + mask, softmax over the N keys of rows r0 (elements 0,1) and r1 (elements 2,3)
+      const int reg0 = s_reg[r0], reg1 = s_reg[r1];
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < N / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + t4 * 2 + (e & 1), row = (e & 2) ? r1 : r0;
+          float v = s[nt][e] + __ldg(bias_h + row * N + col);
+          if (P.shift > 0 && s_reg[col] != ((e & 2) ? reg1 : reg0)) v += -100.f;
+          s[nt][e] = v;
+          if (e & 2) m1 = fmaxf(m1, v); else m0 = fmaxf(m0, v);
+        }
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < N / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p = __expf(s[nt][e] - ((e & 2) ? m1 : m0));
+          s[nt][e] = p;
+          if (e & 2) l1 += p; else l0 += p;
+        }
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      // O = P V : the S accumulator fragments of key tiles (2kt, 2kt+1) are the A fragment of k-tile kt
+      float o[HD / 8][4];
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < N / 16; ++kt) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kt][0], s[2 * kt][1]);
+        pa[1] = pack_bf16x2(s[2 * kt][2], s[2 * kt][3]);
+        pa[2] = pack_bf16x2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+#pragma unroll
+        for (int dt = 0; dt < HD / 8; ++dt) {
+          const __nv_bfloat16* vr = vt + (size_t)(dt * 8 + g) * VP + kt * 16 + t4 * 2;
+          mma_bf16_16816(o[dt], pa, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+        }
+      }
+      // normalise and write rows r0, r1 of this head back to their pixels (window_reverse + reverse shift)
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      __nv_bfloat16* d0 = P.out + (long long)s_pix[r0] * C + h * hd;
+      __nv_bfloat16* d1 = P.out + (long long)s_pix[r1] * C + h * hd;
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) {
+        const int col = dt * 8 + t4 * 2;
+        if (col < hd) {
+          *reinterpret_cast<uint32_t*>(d0 + col) = pack_bf16x2(o[dt][0] * i0, o[dt][1] * i0);
+          *reinterpret_cast<uint32_t*>(d1 + col) = pack_bf16x2(o[dt][2] * i1, o[dt][3] * i1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int HD, int N>
+int launch_wa(const WaParams& P, cudaStream_t st) {
+  const size_t smem = (size_t)N * (3 * P.C * 2 + 16) + (size_t)P.heads * HD * (N + 8) * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDIC_CUDA(cudaFuncSetAttribute(k_window_attention<HD, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) return fail(LDIC_EINVAL, "window attention: shared memory budget exceeded (%zu)", smem);
+  const int nwin = P.B * (P.H / P.ws) * (P.W / P.ws);
+  k_window_attention<HD, N><<<nwin, 256, smem, st>>>(P);
+  return check_launch("k_window_attention");
+}
+
+// bias[h][i][j] = table[index[i][j]][h]   (layers/win_attention.py:101-104)
+__global__ void k_gather_rel_bias(const float* __restrict__ table, const long long* __restrict__ index, float* __restrict__ bias,
+                                  int heads, int NN) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < heads * NN) {
+    const int h = i / NN, ij = i - h * NN;
+    bias[i] = table[index[ij] * heads + h];
+  }
+}
+
+// y (NCHW fp32) = shortcut (NCHW fp32) + o (NHWC fp32): the block's residual (layers/win_attention.py:204-205),
+// 32x32 tiles through shared memory so both sides stay coalesced.
+__global__ void __launch_bounds__(256) k_residual_nhwc_to_nchw(const float* __restrict__ o, const float* __restrict__ sc,
+                                                               float* __restrict__ y, int C, long long HW, int Cp) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const long long p = p0 + r;
+    const int c = c0 + tx;
+    t[r][tx] = (p < HW && c < Cp) ? o[((long long)b * HW + p) * Cp + c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const long long p = p0 + tx;
+    if (c < C && p < HW) {
+      const long long i = ((long long)b * C + c) * HW + p;
+      y[i] = sc[i] + t[tx][r];
+    }
+  }
+}
+
+
+}  // namespace
+
+extern "C" int ldic_window_attention_bias(const float* table, const long long* index, float* bias, int heads, int ws, void* stream) {
+  if (!table || !index || !bias || heads <= 0 || ws <= 0) return fail(LDIC_EINVAL, "window attention bias: bad argument");
+  const int NN = ws * ws * ws * ws;
+  k_gather_rel_bias<<<(heads * NN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(table, index, bias, heads, NN);
+  return check_launch("k_gather_rel_bias");
+}
+
+extern "C" int ldic_window_attention_core(const void* q, const void* k, const void* v, const float* bias, void* out, int B, int H,
+                                          int W, int C, int heads, int ws, int shift, void* stream) {
+  if (!q || !k || !v || !bias || !out) return fail(LDIC_EINVAL, "window attention: null tensor");
+  if (B <= 0) return LDIC_OK;
+  if (heads <= 0 || C % heads || C % 8 || (ws != 8 && ws != 4) || H % ws || W % ws || shift < 0 || shift >= ws)
+    return fail(LDIC_EINVAL, "window attention: need C %% heads == 0, C %% 8 == 0, window 8 or 4 dividing H and W, 0 <= shift < window");
+  const int hd = C / heads;
+  if (hd % 2 || hd > 32) return fail(LDIC_EINVAL, "window attention: head_dim must be even and <= 32 (got %d)", hd);
+  if (heads > 16) return fail(LDIC_EINVAL, "window attention: at most 16 heads");
+  WaParams P{(const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, bias, B, H, W, C, heads, ws, shift};
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool wide = hd > 16;
+  if (ws == 8) return wide ? launch_wa<32, 64>(P, st) : launch_wa<16, 64>(P, st);
+  return wide ? launch_wa<32, 16>(P, st) : launch_wa<16, 16>(P, st);
+}
+
+extern "C" int ldic_residual_nhwc_to_nchw_f32(const float* o_nhwc, const float* shortcut_nchw, float* y_nchw, int B, int C, int H,
+                                              int W, int Cp, void* stream) {
+  if (!o_nhwc || !shortcut_nchw || !y_nchw) return fail(LDIC_EINVAL, "residual: null tensor");
+  if (B <= 0 || H <= 0 || W <= 0) return LDIC_OK;
+  if (Cp < C) return fail(LDIC_EINVAL, "residual: Cp < C");
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, B);
+  k_residual_nhwc_to_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>(o_nhwc, shortcut_nchw, y_nchw, C, HW, Cp);
+  return check_launch("k_residual_nhwc_to_nchw");
+}

@@ -8,6 +8,7 @@ as the reference; forward runs on libldic_b200 kernels (CUDA only, no fallback).
   ModelGDN / ModelIGDN                             <- model/gdn.py:29-156 (the classes model/net.py uses)
   GaussianModel, bypass_round                      <- model/net.py:266-286, 416-426
   GaussianConditional (eval forward)               <- CompressAI semantics used at model/Net_unet.py:1057
+  WindowAttention, WinBasedAttention               <- layers/win_attention.py:38-209
 """
 from __future__ import annotations
 
@@ -16,7 +17,7 @@ import math
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 
 
 class LowerBound(nn.Module):
@@ -176,6 +177,97 @@ class GaussianConditional(nn.Module):
                                              form=ops.FORM_GAUSSIAN_CONDITIONAL, lik_bound=self.likelihood_bound,
                                              scale_bound=self.scale_bound, want_vhat=True)
         return vh, lik
+
+
+class WindowAttention(nn.Module):
+    """layers/win_attention.py:38-126.  Holds the reference's parameters under the reference's names
+    (relative_position_bias_table, relative_position_index, qkv, proj); the arithmetic runs in
+    WinBasedAttention.forward on libldic_b200 (three 1x1 tcgen05 convs, the window kernel, one 1x1 conv)."""
+
+    def __init__(self, dim=192, window_size=(8, 8), num_heads=8, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        if window_size[0] != window_size[1]:
+            raise ops.LdicError("WindowAttention: square windows only")
+        if attn_drop or proj_drop:
+            raise NotImplementedError("WindowAttention: dropout is a training feature (out of scope)")
+        self.dim, self.window_size, self.num_heads = dim, tuple(window_size), num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        ws = window_size[0]
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) * (2 * ws - 1), num_heads))
+        coords = torch.stack(torch.meshgrid([torch.arange(ws), torch.arange(ws)], indexing="ij"))
+        cf = torch.flatten(coords, 1)
+        rel = (cf[:, :, None] - cf[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += ws - 1
+        rel[:, :, 1] += ws - 1
+        rel[:, :, 0] *= 2 * ws - 1
+        self.register_buffer("relative_position_index", rel.sum(-1))
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self._key = None
+
+    def packed(self):
+        """(q, k, v, proj ConvTC layers, bias[heads, N, N]) for the current parameter versions."""
+        ps = [self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, self.relative_position_bias_table]
+        key = tuple((p._version, p.data_ptr()) for p in ps if p is not None)
+        if self._key != key:
+            Cd = self.dim
+            w = self.qkv.weight.detach().float()
+            b = self.qkv.bias.detach().float() if self.qkv.bias is not None else torch.zeros(3 * Cd, device=w.device)
+            mk = lambda wt, bs, f32: ops.ConvTC(_lib.LDIC_CONV_1x1, wt.contiguous(), bs.contiguous(), out_f32=f32)
+            q = mk(w[:Cd] * self.scale, b[:Cd] * self.scale, False)        # q = q * scale (:108) folded into the weights
+            k = mk(w[Cd:2 * Cd], b[Cd:2 * Cd], False)
+            v = mk(w[2 * Cd:], b[2 * Cd:], False)
+            pr = mk(self.proj.weight.detach().float(), self.proj.bias.detach().float(), True)
+            bias = ops.window_attention_bias(self.relative_position_bias_table.detach(), self.relative_position_index,
+                                             self.num_heads, self.window_size[0])
+            self._packed = (q, k, v, pr, bias)
+            self._key = key
+        return self._packed
+
+    def forward(self, x, mask=None):
+        """x: (num_windows*B, N, C) window tokens as in the reference; mask must be None here (the shifted-window
+        mask is derived inside the kernel when called through WinBasedAttention)."""
+        if mask is not None:
+            raise NotImplementedError("WindowAttention.forward(mask=...): call WinBasedAttention, which derives the mask")
+        Bn, N, Cd = x.shape
+        ws = self.window_size[0]
+        img = x.reshape(Bn, ws, ws, Cd).permute(0, 3, 1, 2).contiguous()
+        o = _window_block(self, img, ws, 0, residual=False)
+        return o.permute(0, 2, 3, 1).reshape(Bn, N, Cd)
+
+
+def _window_block(attn: "WindowAttention", x: torch.Tensor, ws: int, shift: int, residual: bool) -> torch.Tensor:
+    B, Cd, H, W = x.shape
+    q, k, v, pr, bias = attn.packed()
+    t = ops.nchw_to_nhwc_bf16(x, q.cin_pad)
+    o = ops.window_attention_core(q(t), k(t), v(t), bias, attn.num_heads, ws, shift)
+    if o.shape[-1] != pr.cin_pad:
+        raise ops.LdicError("window attention: dim must be a multiple of 64")
+    o = pr(o)
+    if residual:
+        return ops.residual_nhwc_to_nchw(o, x)
+    return ops.nhwc_to_nchw_f32(o, Cd)
+
+
+class WinBasedAttention(nn.Module):
+    """layers/win_attention.py:129-209: x (B,C,H,W) -> x + (S)W-MSA(x).  Same constructor and state-dict keys
+    (attn.qkv.*, attn.proj.*, attn.relative_position_bias_table, attn.relative_position_index)."""
+
+    def __init__(self, dim=192, num_heads=8, window_size=8, shift_size=0, qkv_bias=True, qk_scale=None, drop=0.,
+                 attn_drop=0., drop_path=0.):
+        super().__init__()
+        self.dim, self.num_heads, self.window_size, self.shift_size = dim, num_heads, window_size, shift_size
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        if drop_path:
+            raise NotImplementedError("WinBasedAttention: drop_path is a training feature (out of scope)")
+        self.attn = WindowAttention(dim, window_size=(window_size, window_size), num_heads=num_heads, qkv_bias=qkv_bias,
+                                    qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()
+
+    def forward(self, x):
+        return _window_block(self.attn, x, self.window_size, self.shift_size, residual=True)
 
 
 def psnr_from_sq_err(sq_err: torch.Tensor, chw: int):

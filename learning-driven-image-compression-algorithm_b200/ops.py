@@ -476,6 +476,52 @@ class ConvTC:
         return out
 
 
+# --------------------------------------------------------------------------------------
+# f2: window attention (layers/win_attention.py)
+# --------------------------------------------------------------------------------------
+def window_attention_bias(table: torch.Tensor, index: torch.Tensor, heads: int, ws: int) -> torch.Tensor:
+    """relative_position_bias_table[(2ws-1)^2, heads] + relative_position_index[ws^2, ws^2] -> bias [heads, ws^2, ws^2]."""
+    table = _req(table, torch.float32, "relative_position_bias_table").contiguous()
+    index = _req(index, torch.int64, "relative_position_index").contiguous()
+    n = ws * ws
+    if tuple(table.shape) != ((2 * ws - 1) ** 2, heads) or index.numel() != n * n:
+        raise LdicError("window_attention_bias: table must be ((2ws-1)^2, heads) and index (ws^2, ws^2)")
+    bias = torch.empty(heads, n, n, dtype=torch.float32, device=table.device)
+    check(_L().ldic_window_attention_bias(_ptr(table), _ptr(index), _ptr(bias), int(heads), int(ws), _stream()),
+          "ldic_window_attention_bias")
+    return bias
+
+
+def window_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: torch.Tensor, heads: int, ws: int,
+                          shift: int) -> torch.Tensor:
+    """q (pre-scaled), k, v: contiguous NHWC bf16 [B,H,W,C] -> softmax(q k^T + bias + shift mask) v, same layout."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, torch.bfloat16, n)
+        if t.dim() != 4 or not t.is_contiguous() or t.shape != q.shape:
+            raise LdicError("window_attention_core: q, k, v must be contiguous NHWC bf16 tensors of one shape")
+    _req(bias, torch.float32, "bias")
+    B, H, W, Cc = q.shape
+    if tuple(bias.shape) != (heads, ws * ws, ws * ws) or not bias.is_contiguous():
+        raise LdicError("window_attention_core: bias must be contiguous (heads, ws^2, ws^2)")
+    out = torch.empty_like(q)
+    check(_L().ldic_window_attention_core(_ptr(q), _ptr(k), _ptr(v), _ptr(bias), _ptr(out), B, H, W, Cc, int(heads), int(ws),
+                                          int(shift), _stream()), "ldic_window_attention_core")
+    return out
+
+
+def residual_nhwc_to_nchw(o_nhwc: torch.Tensor, shortcut_nchw: torch.Tensor) -> torch.Tensor:
+    """shortcut (B,C,H,W) fp32 + o (B,H,W,Cp>=C) fp32 -> (B,C,H,W) fp32."""
+    o = _req(o_nhwc, torch.float32, "o")
+    sc = _req(shortcut_nchw, torch.float32, "shortcut").contiguous()
+    B, Cc, H, W = sc.shape
+    if o.dim() != 4 or not o.is_contiguous() or tuple(o.shape[:3]) != (B, H, W) or o.shape[3] < Cc:
+        raise LdicError("residual_nhwc_to_nchw: o must be contiguous (B,H,W,Cp>=C)")
+    y = torch.empty_like(sc)
+    check(_L().ldic_residual_nhwc_to_nchw_f32(_ptr(o), _ptr(sc), _ptr(y), B, Cc, H, W, int(o.shape[3]), _stream()),
+          "ldic_residual_nhwc_to_nchw_f32")
+    return y
+
+
 def syntax_branch(y: torch.Tensor, h2: torch.Tensor, M: int, syntax_model, prediction_model_syntax, conv_weights_gen):
     """The syntax side branch on libldic_b200 (ldic_syntax_branch): y, h2 are NHWC fp32 [B,h,w,N].
     Returns (z3 [B,M,1,1], z3_round, mu, sigma [B,M,1,1], conv_w [B,3,M,1,1])."""

@@ -418,3 +418,60 @@ def eval_pad(img: Tensor, multiple: int = 64) -> Tensor:
     img = torch.cat((img, torch.ones(3, hp - h, w)), 1)
     img = torch.cat((img, torch.ones(3, hp, wp - w)), 2)
     return img.unsqueeze(0) * 2.0 - 1.0
+
+
+# ---------------------------------------------------------------------------------------------
+# window attention block (layers/win_attention.py:38-209), functional restatement.
+# Pinned by tests/golden/win_attention.npz (outputs of the unmodified reference class).
+# ---------------------------------------------------------------------------------------------
+def win_rel_position_index(ws: int) -> Tensor:
+    """layers/win_attention.py:66-76."""
+    coords = torch.stack(torch.meshgrid([torch.arange(ws), torch.arange(ws)], indexing="ij"))
+    cf = torch.flatten(coords, 1)
+    rel = (cf[:, :, None] - cf[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws - 1
+    rel[:, :, 1] += ws - 1
+    rel[:, :, 0] *= 2 * ws - 1
+    return rel.sum(-1)
+
+
+def win_shift_mask(H: int, W: int, ws: int, shift: int) -> Tensor:
+    """layers/win_attention.py:160-177: (nW, ws*ws, ws*ws) with 0 / -100."""
+    img = torch.zeros(1, H, W, 1)
+    cnt = 0
+    for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+        for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            img[:, hs, wsl, :] = cnt
+            cnt += 1
+    mw = img.view(1, H // ws, ws, W // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws)
+    am = mw.unsqueeze(1) - mw.unsqueeze(2)
+    return am.masked_fill(am != 0, -100.0).masked_fill(am == 0, 0.0)
+
+
+def win_based_attention(sd: Dict[str, Tensor], x: Tensor, num_heads: int, ws: int, shift: int, prefix: str = "") -> Tensor:
+    """WinBasedAttention.forward (layers/win_attention.py:150-209): x (B,C,H,W) -> x + W-MSA(x)."""
+    B, C, H, W = x.shape
+    g = lambda k: sd[prefix + k]
+    t = x.permute(0, 2, 3, 1)
+    if shift > 0:
+        t = torch.roll(t, shifts=(-shift, -shift), dims=(1, 2))
+    win = t.reshape(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, C)
+    Bn, N, _ = win.shape
+    hd = C // num_heads
+    qkv = F.linear(win, g("attn.qkv.weight"), g("attn.qkv.bias")).reshape(Bn, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0] * hd ** -0.5, qkv[1], qkv[2]
+    attn = q @ k.transpose(-2, -1)
+    idx = g("attn.relative_position_index").reshape(-1).long()
+    bias = g("attn.relative_position_bias_table")[idx].reshape(N, N, -1).permute(2, 0, 1)
+    attn = attn + bias.unsqueeze(0)
+    if shift > 0:
+        m = win_shift_mask(H, W, ws, shift)
+        nW = m.shape[0]
+        attn = (attn.view(Bn // nW, nW, num_heads, N, N) + m.unsqueeze(1).unsqueeze(0)).view(-1, num_heads, N, N)
+    attn = torch.softmax(attn, -1)
+    o = (attn @ v).transpose(1, 2).reshape(Bn, N, C)
+    o = F.linear(o, g("attn.proj.weight"), g("attn.proj.bias"))
+    o = o.view(B, H // ws, W // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
+    if shift > 0:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    return x + o.permute(0, 3, 1, 2)

@@ -132,3 +132,14 @@ def test_eval_pad_matches_driver_padding():
         b = rp.eval_pad(img)
         assert a.shape == b.shape and torch.equal(a, b)
         assert a.shape[2] % 64 == 0 and a.shape[3] % 64 == 0
+
+
+@pytest.mark.parametrize("tag", ["noshift", "shift", "small"])
+def test_win_attention_oracle_vs_reference_golden(tag):
+    """the oracle's window attention against outputs of the unmodified layers/win_attention.py."""
+    d = np.load(os.path.join(G, "win_attention.npz"))
+    dim, heads, ws, shift, B, H, W = [int(v) for v in d[f"{tag}_cfg"]]
+    sd = {k[len(tag) + 4:]: torch.from_numpy(d[k]) for k in d.files if k.startswith(f"{tag}_sd_")}
+    y = rp.win_based_attention(sd, torch.from_numpy(d[f"{tag}_x"]), heads, ws, shift)
+    assert torch.equal(sd["attn.relative_position_index"].long(), rp.win_rel_position_index(ws))
+    torch.testing.assert_close(y, torch.from_numpy(d[f"{tag}_y"]), rtol=1e-5, atol=1e-5)

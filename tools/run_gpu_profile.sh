@@ -11,7 +11,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launch.log 2>&1
 echo "launchlist exit $?" >> gpurun_out/summary.txt
-timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:conv_tc_kernel|conv_halo_kernel|conv_first_kernel|k_likelihood|k_syntax_conv" -s 66 -c 22 -o gpurun_out/prof_step -f $BENCH > gpurun_out/ncu_step.log 2>&1
+timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|conv_halo|conv_first|k_likelihood" -s 57 -c 19 -o gpurun_out/prof_step -f $BENCH > gpurun_out/ncu_step.log 2>&1
 echo "ncu step exit $?" >> gpurun_out/summary.txt
 timeout 120 python tools/prof_likelihood.py 5 > gpurun_out/lik_plain.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_likelihood -s 3 -c 1 -o gpurun_out/prof_lik -f python tools/prof_likelihood.py 5 > gpurun_out/ncu_lik.log 2>&1
