@@ -24,6 +24,7 @@
 // model/gdn.py:69-92,134-156 (GDN/IGDN).
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 
 using namespace ldic;
@@ -273,8 +274,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {      // arrive on a barrier of any CTA of the cluster
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a barrier of any CTA of the cluster.  Default semantics (.release at .cta scope, the form CUTLASS's
+// ClusterBarrier::arrive uses): what the waiter consumes is shared-memory operand data already made visible to the
+// async proxy by fence.proxy.async, and TMEM reads ordered by tcgen05.fence::before_thread_sync.  The
+// .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, which also waits for every global store of the thread
+// to be acknowledged by L2: 17 % of all warp stall samples of the deconv-3 launch (profiles/r01_ncu_d3pair_stalls.txt).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
   uint32_t ok;
@@ -431,8 +437,13 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
     const bool edbg = P.dbg != nullptr && blockIdx.x == 0 && warp == 0;
     long long e_acc = 0, e_norm = 0, e_slot = 0, e_t0 = 0, e_p1 = 0, e_p2 = 0, e_t1 = 0;
     const long long e_begin = edbg ? clock64() : 0;
-    for (int it = 0; it < ntiles_cta; ++it) {
-      const TileCoord tc = CL ? decode_tile2(P, R.t_first + it * R.t_stride, R.rank) : decode_tile(P, blockIdx.x + it * gridDim.x);
+    // tile coordinates are decoded two tiles ahead, in the shadow of the wait for the gamma contraction (five integer
+    // divisions: 6 % of the epilogue warps' samples when done at the top of the loop)
+    auto decode_it = [&](int i) {
+      return CL ? decode_tile2(P, R.t_first + i * R.t_stride, R.rank) : decode_tile(P, blockIdx.x + i * gridDim.x);
+    };
+    TileCoord tc = decode_it(0), tc_n1 = decode_it(1), tc_n2 = tc_n1;
+    for (int it = 0; it < ntiles_cta; ++it, tc = tc_n1, tc_n1 = tc_n2) {
       const Job jb = P.jobs[tc.job];
       const int bsel = it & 1;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
@@ -447,8 +458,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       sbase += (uint32_t)len_this + ((gk && it > 0) ? (uint32_t)gk : 0u);
       uint32_t gpos = sbase;
       if (gk && it + 1 < ntiles_cta) {
-        const Job jn = P.jobs[CL ? (R.t_first + (it + 1) * R.t_stride) / P.super_per_job
-                                 : decode_tile(P, blockIdx.x + (it + 1) * gridDim.x).job];
+        const Job jn = P.jobs[tc_n1.job];
         const int len_next = R.use_chunks ? jn.nchunks : jn.nkb;
         gpos += (uint32_t)(len_next < R.insert_after ? len_next : R.insert_after);
       }
@@ -470,6 +480,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       tc_fence_before();
       if (!gk) {                                 // no GDN: the buffer can take the tile after next right away
         if (CL) mbar_arrive_cluster(R.buf_free_cl + 8u * bsel); else mbar_arrive(&R.buf_free[bsel]);
+        tc_n2 = decode_it(it + 2);
       }
 #pragma unroll
       for (int c = 0; c < CPT; c += 4) {
@@ -523,6 +534,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
         if (CL) mbar_arrive_cluster(R.x2_ready_cl + 8u * bsel); else mbar_arrive(&R.x2_ready[bsel]);
         if (edbg) { e_t0 = clock64(); e_p1 += e_t0 - e_t1; }
+        tc_n2 = decode_it(it + 2);
         mbar_wait(&R.norm_full[bsel], par);
         if (edbg) { e_t1 = clock64(); e_norm += e_t1 - e_t0; }
         tc_fence_after();
@@ -535,24 +547,30 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           const int c = ch * LDW;
-          tmem_ld_wait();
-          if (ch + 1 < NCH) tmem_ldn<LDW>(tbuf + c + LDW, tr[(ch + 1) & 1]);
+          float bb[LDW];                         // this chunk's beta: the shared loads are in flight during the TMEM wait
 #pragma unroll
           for (int k = 0; k < LDW; k += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(&R.s_beta[col0 + c + k]);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            bb[k] = b4.x; bb[k + 1] = b4.y; bb[k + 2] = b4.z; bb[k + 3] = b4.w;
+          }
+          tmem_ld_wait();
+          if (ch + 1 < NCH) {
+            tmem_ldn<LDW>(tbuf + c + LDW, tr[(ch + 1) & 1]);
+          } else {
+            // the last norm chunk is in registers: the accumulator buffer is free for tile it+2 now, not after the
+            // remaining arithmetic and stores
+            tc_fence_before();
+            if (CL) mbar_arrive_cluster(R.buf_free_cl + 8u * bsel); else mbar_arrive(&R.buf_free[bsel]);
+          }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float nrm = __uint_as_float(tr[ch & 1][k + e]) + bb[e];
-              const float rs = rsqrt_approx(nrm);
-              xr[c + k + e] *= igdn ? nrm * rs : rs;
-            }
+          for (int k = 0; k < LDW; ++k) {
+            const float nrm = __uint_as_float(tr[ch & 1][k]) + bb[k];
+            const float rs = rsqrt_approx(nrm);
+            xr[c + k] *= igdn ? nrm * rs : rs;
           }
           if (P.ngroups == 1 && valid) store_cols(c, LDW);
         }
         stored = (P.ngroups == 1);
-        tc_fence_before();
-        if (CL) mbar_arrive_cluster(R.buf_free_cl + 8u * bsel); else mbar_arrive(&R.buf_free[bsel]);   // norm drained: free for tile it+2
       } else if (P.act == LDIC_ACT_RELU) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) xr[c] = fmaxf(xr[c], 0.f);
@@ -887,66 +905,80 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == kProdWarp) {
-      // ===================== TMA producer (both CTAs) =====================
-      uint32_t slot = 0, ph = 0;
-      int stages_r = stages;
-      asm volatile("" : "+r"(stages_r));
-      const bool pdbg = P.dbg != nullptr && blockIdx.x == 0;
-      long long t_empty = 0, tp0 = 0;
-      const long long tp_begin = clock64();
-      const int row_half = (int)rank * (NP / 2);
-      auto advance = [&]() { if (++slot == (uint32_t)stages_r) { slot = 0; ph ^= 1; } };
-      auto load_gamma = [&]() {
-        for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring (B half only)
-          mbar_wait(&empty_bar[slot], ph ^ 1);
-          if (elect_one()) {
-            if (leader) mbar_expect_tx(&full_bar[slot], 2 * kBHalfBytes);
-            tma_load_2d_cg2(smem_base + slot * kStageBytes + kATileBytes, &tmG, full_L + 8u * slot, kb * kBlockK, row_half);
-          }
-          advance();
-        }
-      };
-      const int cs = P.mode == 2 ? 2 : 1;                     // input pixels per tile pixel (strided TMA box)
-      int cur_job = -1, ntaps = 0, tap_begin = 0, nkb = 0;
-      uint32_t my_w0 = 0, my_w1 = 0;                          // lane t: tap t of the current job, packed
-      for (int it = 0; it < nt; ++it) {
-        const TileCoord tc = decode_tile2(P, pi + it * npairs, (int)rank);
-        if (tc.job != cur_job) {
-          cur_job = tc.job;
-          ntaps = P.jobs[cur_job].ntaps; tap_begin = P.jobs[cur_job].tap_begin; nkb = P.jobs[cur_job].nkb;
-          if (lane < ntaps) {
-            const Tap t = P.taps[tap_begin + lane];
-            my_w0 = (uint32_t)(uint8_t)t.dx | ((uint32_t)(uint8_t)t.dy << 8) | ((uint32_t)t.nkc << 24);
-            my_w1 = (uint32_t)t.a_c0 | ((uint32_t)t.b_c0 << 16);
-          }
-        }
-        const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
-        const int x0 = tc.x0 * cs, y0 = tc.y0 * cs;
-        int cb = 0;
-        for (int tp = 0; tp < ntaps; ++tp) {
-          const uint32_t w0 = __shfl_sync(0xffffffffu, my_w0, tp), w1 = __shfl_sync(0xffffffffu, my_w1, tp);
-          const int dx = (int)(int8_t)(w0 & 0xff), dy = (int)(int8_t)((w0 >> 8) & 0xff);
-          const int nkc = (int)(w0 >> 24), a_c0 = (int)(w1 & 0xffff), b_c0 = (int)(w1 >> 16);
-          const int brow = (tap_begin + tp) * NP + row_half;
-          for (int kc = 0; kc < nkc; ++kc, ++cb) {
-            if (cb == jins) load_gamma();
-            const uint32_t a_dst = smem_base + slot * kStageBytes;
-            if (pdbg) tp0 = clock64();
-            mbar_wait(&empty_bar[slot], ph ^ 1);
-            if (pdbg) t_empty += clock64() - tp0;
-            if (elect_one()) {
-              if (leader) mbar_expect_tx(&full_bar[slot], 2 * kStageBytes);
-              tma_load_4d_cg2(a_dst, &tmA, full_L + 8u * slot, a_c0 + kc * kBlockK, x0 + dx, y0 + dy, tc.n0);
-              tma_load_2d_cg2(a_dst + kATileBytes, &tmW, full_L + 8u * slot, b_c0 + kc * kBlockK, brow);
+    if (warp == kProdWarp || warp == kProdBWarp) {
+      // ===================== TMA producers (both CTAs): warp kProdWarp loads the activation tiles, warp
+      // kProdBWarp the weight / gamma half tiles.  One warp issuing both copies of a stage spent ~420 cycles per
+      // stage against the 384 cycles the tensor pipe needs for it (wait_full 133 cycles per stage in the MMA warp);
+      // two warps walk the same ring in lockstep order, each waiting on the stage's empty barrier itself.  The A
+      // warp's expect_tx carries the bytes of the whole stage (a complete_tx that lands first only drives the
+      // transaction count negative while the arrival is still pending); gamma stages belong to the B warp alone.
+      auto produce = [&](auto is_a_tag) {
+        constexpr bool IS_A = decltype(is_a_tag)::value;
+        uint32_t slot = 0, ph = 0;
+        int stages_r = stages;
+        asm volatile("" : "+r"(stages_r));
+        const bool pdbg = IS_A && P.dbg != nullptr && blockIdx.x == 0;
+        long long t_empty = 0, tp0 = 0;
+        const long long tp_begin = clock64();
+        const int row_half = (int)rank * (NP / 2);
+        auto advance = [&]() { if (++slot == (uint32_t)stages_r) { slot = 0; ph ^= 1; } };
+        auto load_gamma = [&]() {
+          for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring (B half only)
+            if constexpr (!IS_A) {
+              mbar_wait(&empty_bar[slot], ph ^ 1);
+              if (elect_one()) {
+                if (leader) mbar_expect_tx(&full_bar[slot], 2 * kBHalfBytes);
+                tma_load_2d_cg2(smem_base + slot * kStageBytes + kATileBytes, &tmG, full_L + 8u * slot, kb * kBlockK, row_half);
+              }
             }
             advance();
           }
+        };
+        const int cs = P.mode == 2 ? 2 : 1;                     // input pixels per tile pixel (strided TMA box)
+        int cur_job = -1, ntaps = 0, tap_begin = 0, nkb = 0;
+        uint32_t my_w0 = 0, my_w1 = 0;                          // lane t: tap t of the current job, packed
+        for (int it = 0; it < nt; ++it) {
+          const TileCoord tc = decode_tile2(P, pi + it * npairs, (int)rank);
+          if (tc.job != cur_job) {
+            cur_job = tc.job;
+            ntaps = P.jobs[cur_job].ntaps; tap_begin = P.jobs[cur_job].tap_begin; nkb = P.jobs[cur_job].nkb;
+            if (lane < ntaps) {
+              const Tap t = P.taps[tap_begin + lane];
+              my_w0 = (uint32_t)(uint8_t)t.dx | ((uint32_t)(uint8_t)t.dy << 8) | ((uint32_t)t.nkc << 24);
+              my_w1 = (uint32_t)t.a_c0 | ((uint32_t)t.b_c0 << 16);
+            }
+          }
+          const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
+          const int x0 = tc.x0 * cs, y0 = tc.y0 * cs;
+          int cb = 0;
+          for (int tp = 0; tp < ntaps; ++tp) {
+            const uint32_t w0 = __shfl_sync(0xffffffffu, my_w0, tp), w1 = __shfl_sync(0xffffffffu, my_w1, tp);
+            const int dx = (int)(int8_t)(w0 & 0xff), dy = (int)(int8_t)((w0 >> 8) & 0xff);
+            const int nkc = (int)(w0 >> 24), a_c0 = (int)(w1 & 0xffff), b_c0 = (int)(w1 >> 16);
+            const int brow = (tap_begin + tp) * NP + row_half;
+            for (int kc = 0; kc < nkc; ++kc, ++cb) {
+              if (cb == jins) load_gamma();
+              const uint32_t a_dst = smem_base + slot * kStageBytes;
+              if (pdbg) tp0 = clock64();
+              mbar_wait(&empty_bar[slot], ph ^ 1);
+              if (pdbg) t_empty += clock64() - tp0;
+              if (elect_one()) {
+                if constexpr (IS_A) {
+                  if (leader) mbar_expect_tx(&full_bar[slot], 2 * kStageBytes);
+                  tma_load_4d_cg2(a_dst, &tmA, full_L + 8u * slot, a_c0 + kc * kBlockK, x0 + dx, y0 + dy, tc.n0);
+                } else {
+                  tma_load_2d_cg2(a_dst + kATileBytes, &tmW, full_L + 8u * slot, b_c0 + kc * kBlockK, brow);
+                }
+              }
+              advance();
+            }
+          }
+          if (cb == jins) load_gamma();
         }
-        if (cb == jins) load_gamma();
-      }
-      if (gk) load_gamma();                                   // contraction of the last tile
-      if (pdbg && lane == 0) { P.dbg[8] = (unsigned long long)(clock64() - tp_begin); P.dbg[9] = (unsigned long long)t_empty; }
+        if (gk) load_gamma();                                   // contraction of the last tile
+        if (pdbg && lane == 0) { P.dbg[8] = (unsigned long long)(clock64() - tp_begin); P.dbg[9] = (unsigned long long)t_empty; }
+      };
+      if (warp == kProdWarp) produce(std::true_type{}); else produce(std::false_type{});
     } else if (warp == kMmaWarp && leader) {
       // ===================== MMA issuer (leader CTA only) =====================
       uint32_t slot = 0, ph = 0;
