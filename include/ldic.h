@@ -124,6 +124,15 @@ LDIC_API int ldic_round_likelihood_bpp(const LdicLikelihoodArgs* args, void* str
  * sq_err must be zeroed by the caller (it is accumulated into).                */
 LDIC_API int ldic_mse_sum(const float* x, const float* x_tilde, int B, long long chw, int clamp_pm1,
                  unsigned long long* sq_err, void* stream);
+/* Scalar tail of Net.forward (model/net.py:856-869) in two launches instead of ~25 elementwise ones:
+ *   ldic_rd_pack_metrics: bits3 = [sum ln L_z, sum ln L_y, sum ln L_syntax] (float, device), sq_err[B] ->
+ *     packed5 = [the three sums, sum_i 20 log10(255 / sqrt(sq_err_i / chw)), B] in double (the five numbers the
+ *     multi-GPU all-reduce carries) and v_mse[B] = sq_err / chw (float, may be NULL);
+ *   ldic_rd_finish_metrics: bpp_psnr[0] = (packed5[0]+[1]+[2]) / (-ln2 * packed5[4] * pixels_per_image)  (:856-861),
+ *     bpp_psnr[1] = packed5[3] / packed5[4]  (:869, mean of the per-image PSNR).                              */
+LDIC_API int ldic_rd_pack_metrics(const float* bits3, const unsigned long long* sq_err, int B, long long chw,
+                         double* packed5, float* v_mse, void* stream);
+LDIC_API int ldic_rd_finish_metrics(const double* packed5, double pixels_per_image, float* bpp_psnr, void* stream);
 /* Fused tail of Net.forward: per-image 1x1 conv (batch_conv, model/net.py:527-537)
  * of the 16-channel NHWC fp32 synthesis output with weights w[B][3][M], then the
  * a11 arithmetic against the NCHW fp32 input x.  x_tilde_nchw (optional) receives

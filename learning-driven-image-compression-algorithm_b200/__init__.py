@@ -13,6 +13,7 @@ from .transforms import (analysisTransformModel, synthesisTransformModel, h_anal
                          h_synthesisTransformModel)
 from .net import Net                                        # noqa: F401
 from . import eval as evaluation                            # noqa: F401  (eval_net.py driver)
+from .graph import GraphedEvaluator                         # noqa: F401
 
 __all__ = ["GDN", "ModelGDN", "ModelIGDN", "LowerBound", "NonNegativeParametrizer", "GaussianModel",
            "GaussianConditional", "WindowAttention", "WinBasedAttention", "bypass_round", "ste_round", "analysisTransformModel", "synthesisTransformModel",

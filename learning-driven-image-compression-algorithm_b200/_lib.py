@@ -84,6 +84,8 @@ _SIGS = {
     "ldic_likelihood_workspace_bytes": (C.c_size_t, []),
     "ldic_round_likelihood_bpp": (C.c_int, [C.POINTER(LikelihoodArgs), C.c_void_p]),
     "ldic_mse_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    "ldic_rd_pack_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_rd_finish_metrics": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "ldic_syntax_conv_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldic_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -520,6 +520,50 @@ __global__ void __launch_bounds__(256) k_mse_sum(const float* __restrict__ x, co
     atomicAdd(out + b, s);
   }
 }
+// ------------------------------------------------------------------------------------
+// a9 / a11 scalar tail: the per-batch bpp / PSNR arithmetic of model/net.py:856-869 on the three sum(ln L)
+// and the B exact squared-error sums.  One block; fixed summation order (deterministic).
+//   packed5 = [sum ln L_z, sum ln L_y, sum ln L_syn, sum_i 20 log10(255 / sqrt(mse_i)), B]   (double: what the
+//             multi-GPU all-reduce carries), v_mse[i] = sq_err[i] / chw.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rd_pack(const float* __restrict__ bits3, const unsigned long long* __restrict__ sq_err,
+                                                 int B, double chw, double* __restrict__ packed5, float* __restrict__ v_mse) {
+  __shared__ double ws[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    const double mse = (double)sq_err[i] / chw;
+    if (v_mse) v_mse[i] = (float)mse;
+    acc += 20.0 * log10(255.0 / sqrt(mse));
+  }
+  ws[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < 256; ++k) s += ws[k];
+    packed5[0] = (double)bits3[0]; packed5[1] = (double)bits3[1]; packed5[2] = (double)bits3[2];
+    packed5[3] = s; packed5[4] = (double)B;
+  }
+}
+// bpp = sum(ln L) / (-ln 2 * n * th * tw), v_psnr = sum_i psnr_i / n   (n images in the possibly all-reduced packed5)
+__global__ void k_rd_finish(const double* __restrict__ packed5, double pixels_per_image, float* __restrict__ bpp_psnr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double n = packed5[4];
+    bpp_psnr[0] = (float)((packed5[0] + packed5[1] + packed5[2]) / (-0.6931471805599453 * n * pixels_per_image));
+    bpp_psnr[1] = (float)(packed5[3] / n);
+  }
+}
+extern "C" int ldic_rd_pack_metrics(const float* bits3, const unsigned long long* sq_err, int B, long long chw, double* packed5,
+                                    float* v_mse, void* stream) {
+  if (!bits3 || !sq_err || !packed5 || B <= 0 || chw <= 0) return fail(LDIC_EINVAL, "rd_pack_metrics: bad argument");
+  k_rd_pack<<<1, 256, 0, (cudaStream_t)stream>>>(bits3, sq_err, B, (double)chw, packed5, v_mse);
+  return check_launch("k_rd_pack");
+}
+extern "C" int ldic_rd_finish_metrics(const double* packed5, double pixels_per_image, float* bpp_psnr, void* stream) {
+  if (!packed5 || !bpp_psnr || !(pixels_per_image > 0)) return fail(LDIC_EINVAL, "rd_finish_metrics: bad argument");
+  k_rd_finish<<<1, 32, 0, (cudaStream_t)stream>>>(packed5, pixels_per_image, bpp_psnr);
+  return check_launch("k_rd_finish");
+}
+
 extern "C" int ldic_mse_sum(const float* x, const float* x_tilde, int B, long long chw, int clamp_pm1,
                             unsigned long long* sq_err, void* stream) {
   if (B < 0 || chw < 0) return fail(LDIC_EINVAL, "mse: bad shape");

@@ -256,9 +256,10 @@ class Net(nn.Module):
         z_hat_bf16 = torch.empty(z.shape, dtype=torch.bfloat16, device=x.device)
         sigma_z = self.z2_sigma.detach().reshape(N).contiguous()
         lik_z = torch.empty_like(z) if want_likelihoods else None
-        sum_z = ops.likelihood_rows(z, Pz, N, v_rs=N, sigma=sigma_z, sigma_mode=1, quant=ops.QUANT_ROUND,     # :676,:781
-                                    lik_bound=self.entropy_bottleneck_z2.likelihood_bound,
-                                    v_hat_bf16=z_hat_bf16, vb_rs=N, lik=lik_z)
+        bits = torch.empty(3, dtype=torch.float32, device=x.device)                 # sum(ln L) of z, y, syntax
+        ops.likelihood_rows(z, Pz, N, v_rs=N, sigma=sigma_z, sigma_mode=1, quant=ops.QUANT_ROUND,             # :676,:781
+                            lik_bound=self.entropy_bottleneck_z2.likelihood_bound,
+                            v_hat_bf16=z_hat_bf16, vb_rs=N, lik=lik_z, sum_out=bits[0:1])
         h2 = self.hs_model.forward_nhwc(z_hat_bf16)                                 # :681   (B,h,w,N) fp32 NHWC
 
         y_nchw = y.permute(0, 3, 1, 2)                                              # channels-last view, no copy
@@ -292,14 +293,15 @@ class Net(nn.Module):
             ctx = self.prediction_model.raw_tc(y_round_bf16, h2, M)                 # :784  (P,1,2,Cp): mu | log sigma
             ctx_rs, ctx_sig_off = 2 * ctx.shape[-1], ctx.shape[-1]
         lik_y = torch.empty(B, h, w, Cc, dtype=torch.float32, device=x.device) if want_likelihoods else None
-        sum_y = ops.likelihood_rows(y, P, Cc, v_rs=N, v_off=M, mu=ctx, mu_mode=2, mu_rs=ctx_rs, mu_off=0,      # :786
-                                    sigma=ctx, sigma_mode=2, sigma_rs=ctx_rs, sigma_off=ctx_sig_off, sigma_is_log=True,
-                                    quant=ops.QUANT_ROUND, lik_bound=self.entropy_bottleneck_z3.likelihood_bound,
-                                    lik=lik_y)
+        ops.likelihood_rows(y, P, Cc, v_rs=N, v_off=M, mu=ctx, mu_mode=2, mu_rs=ctx_rs, mu_off=0,              # :786
+                            sigma=ctx, sigma_mode=2, sigma_rs=ctx_rs, sigma_off=ctx_sig_off, sigma_is_log=True,
+                            quant=ops.QUANT_ROUND, lik_bound=self.entropy_bottleneck_z3.likelihood_bound,
+                            lik=lik_y, sum_out=bits[1:2])
         # syntax stream: "sigma" <- first return (mu), "mu" <- second (sigma): reference quirk H2
-        _, lik_syn, sum_syn = ops.gaussian_likelihood(z3_syntax_rounded.contiguous(), syn_first.contiguous(),
-                                                      syn_second.contiguous(),
-                                                      lik_bound=self.entropy_bottleneck_z3_syntax.likelihood_bound)
+        _, lik_syn, _ = ops.gaussian_likelihood(z3_syntax_rounded.contiguous(), syn_first.contiguous(),
+                                                syn_second.contiguous(), want_lik=want_likelihoods,
+                                                lik_bound=self.entropy_bottleneck_z3_syntax.likelihood_bound,
+                                                sum_out=bits[2:3])
 
         fused = None
         if self.tail_fused:      # g_s with batch_conv + squared level error in the last deconv's epilogue
@@ -311,7 +313,7 @@ class Net(nn.Module):
             xt16 = self.s_model.forward_nhwc(y_round_bf16)                          # :800   (B,H,W,M) fp32 NHWC
             sq_err, x_hat = ops.syntax_conv_mse(x, xt16, conv_w.reshape(B, 3, M), want_x_tilde=want_x_hat)   # :811,:864-868
 
-        out = {"bits": torch.cat([sum_z, sum_y, sum_syn]), "sq_err": sq_err}
+        out = {"bits": bits, "sq_err": sq_err}
         if want_x_hat:
             out["x_hat"] = x_hat
         if want_likelihoods:
@@ -325,10 +327,9 @@ class Net(nn.Module):
     def metrics(self, out: Dict[str, torch.Tensor], batch: int, H: int, W: int):
         """bpp / v_mse / v_psnr exactly as model/net.py:856-869 forms them."""
         tb, th, tw, tc = self.test_size
-        num_pixels = batch * th * tw
-        bpp = out["bits"].sum() / (-math.log(2) * num_pixels)
-        v_mse, v_psnr = psnr_from_sq_err(out["sq_err"], 3 * H * W)
-        return bpp, v_mse, v_psnr
+        packed, v_mse = ops.rd_pack_metrics(out["bits"], out["sq_err"], 3 * H * W)
+        r = ops.rd_finish_metrics(packed, float(th * tw))
+        return r[0], v_mse, r[1]
 
     def forward(self, inputs, mode='train', num=1):
         if mode != 'test':

@@ -167,7 +167,8 @@ def likelihood_rows(v, rows, cols, *, v_rs, v_off=0, mu=None, mu_mode=0, mu_rs=0
 
 def gaussian_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch.Tensor] = None, *,
                         quant: int = QUANT_NONE, form: int = FORM_GAUSSIAN_MODEL, lik_bound: float = 1e-8,
-                        scale_bound: float = 0.11, want_lik: bool = True, want_vhat: bool = False
+                        scale_bound: float = 0.11, want_lik: bool = True, want_vhat: bool = False,
+                        sum_out: Optional[torch.Tensor] = None
                         ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], torch.Tensor]:
     """Module-surface form on (B,C,H,W) tensors with torch broadcasting rules limited to the
     reference's two cases: same-shape sigma/mu, or (1,C,1,1) sigma with mu == 0 / (1,C,1,1).
@@ -182,13 +183,14 @@ def gaussian_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch
             # general per-channel mean: fold it in by expanding (rare; not on the reference path)
             return gaussian_likelihood(v, sigma.expand_as(v).contiguous(), mu.expand_as(v).contiguous(), quant=quant,
                                        form=form, lik_bound=lik_bound, scale_bound=scale_bound, want_lik=want_lik,
-                                       want_vhat=want_vhat)
+                                       want_vhat=want_vhat, sum_out=sum_out)
         vc = v.contiguous()
         sg = sigma.reshape(Cc).contiguous()
         lik = torch.empty_like(vc) if want_lik else None
         vh = torch.empty_like(vc) if want_vhat else None
         s = likelihood_rows(vc, B * Cc, H * W, v_rs=H * W, sigma=sg, sigma_mode=3, sigma_period=Cc, quant=quant,
-                            form=form, lik_bound=lik_bound, scale_bound=scale_bound, v_hat=vh, v_hat_rs=H * W, lik=lik)
+                            form=form, lik_bound=lik_bound, scale_bound=scale_bound, v_hat=vh, v_hat_rs=H * W, lik=lik,
+                            sum_out=sum_out)
         return vh, lik, s
     if sigma.shape != v.shape or (mu is not None and mu.shape != v.shape):
         sigma = sigma.expand_as(v)
@@ -209,7 +211,7 @@ def gaussian_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch
     vh = torch.empty_like(v) if want_vhat else None
     s = likelihood_rows(v, 1, n, v_rs=n, mu=m, mu_mode=2 if m is not None else 0, mu_rs=n, sigma=sg, sigma_mode=2,
                         sigma_rs=n, quant=quant, form=form, lik_bound=lik_bound, scale_bound=scale_bound, v_hat=vh,
-                        v_hat_rs=n, lik=lik)
+                        v_hat_rs=n, lik=lik, sum_out=sum_out)
     return vh, lik, s
 
 
@@ -255,6 +257,31 @@ def mse_sum(x: torch.Tensor, x_tilde: torch.Tensor, clamp_pm1: bool = False) -> 
     chw = x.numel() // max(B, 1)
     out = torch.zeros(B, dtype=torch.int64, device=x.device)
     check(_L().ldic_mse_sum(_ptr(x), _ptr(xt), B, chw, int(bool(clamp_pm1)), _ptr(out), _stream()), "ldic_mse_sum")
+    return out
+
+
+def rd_pack_metrics(bits3: torch.Tensor, sq_err: torch.Tensor, chw: int, want_v_mse: bool = True):
+    """[sum ln L z, y, syntax] (float[3]) + exact squared-error sums (int64[B]) -> (packed5 double[5], v_mse float[B])."""
+    bits3 = _req(bits3, torch.float32, "bits")
+    sq_err = _req(sq_err, torch.int64, "sq_err")
+    if bits3.numel() != 3 or not bits3.is_contiguous() or not sq_err.is_contiguous():
+        raise LdicError("rd_pack_metrics: bits must be 3 contiguous floats, sq_err contiguous int64")
+    B = sq_err.numel()
+    packed = torch.empty(5, dtype=torch.float64, device=bits3.device)
+    v_mse = torch.empty(B, dtype=torch.float32, device=bits3.device) if want_v_mse else None
+    check(_L().ldic_rd_pack_metrics(_ptr(bits3), _ptr(sq_err), B, int(chw), _ptr(packed), _ptr(v_mse), _stream()),
+          "ldic_rd_pack_metrics")
+    return packed, v_mse
+
+
+def rd_finish_metrics(packed5: torch.Tensor, pixels_per_image: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """packed5 (possibly all-reduced) -> float[2] = (bpp, v_psnr)."""
+    packed5 = _req(packed5, torch.float64, "packed5")
+    if packed5.numel() != 5 or not packed5.is_contiguous():
+        raise LdicError("rd_finish_metrics: packed5 must be 5 contiguous doubles")
+    if out is None:
+        out = torch.empty(2, dtype=torch.float32, device=packed5.device)
+    check(_L().ldic_rd_finish_metrics(_ptr(packed5), float(pixels_per_image), _ptr(out), _stream()), "ldic_rd_finish_metrics")
     return out
 
 

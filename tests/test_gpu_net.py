@@ -171,3 +171,45 @@ def test_forward_dict_view(ldic):
     bits = sum(torch.log(l).sum() for l in o["likelihoods"].values())
     out = net.rd_forward(x)
     assert abs(bits.item() - out["bits"][:2].sum().item()) < 1e-3 * abs(bits.item())
+
+
+def test_metric_kernels_match_reference_arithmetic(ldic):
+    """ldic_rd_pack_metrics / ldic_rd_finish_metrics against model/net.py:856-869 evaluated with torch on the host."""
+    import math
+    bits = torch.tensor([-12345.678, -987654.3, -321.5])
+    sq = torch.tensor([3 * 64 * 64 * 900, 3 * 64 * 64 * 17 + 5, 123456789], dtype=torch.int64)
+    chw, th, tw = 3 * 64 * 64, 64, 64
+    packed, v_mse = ldic.ops.rd_pack_metrics(bits.cuda(), sq.cuda(), chw)
+    r = ldic.ops.rd_finish_metrics(packed, float(th * tw)).cpu()
+    mse = sq.double() / chw
+    assert torch.equal(v_mse.cpu(), mse.float())
+    psnr = (20 * torch.log10(255.0 / torch.sqrt(mse))).mean()
+    bpp = bits.double().sum() / (-math.log(2) * 3 * th * tw)
+    assert packed.cpu()[4].item() == 3.0 and torch.equal(packed.cpu()[:3], bits.double())
+    assert abs(r[0].item() / bpp.item() - 1) < 1e-6 and abs(r[1].item() - psnr.item()) < 1e-5
+
+
+def test_graph_replay_is_bit_identical_to_eager(ldic):
+    """GraphedEvaluator replays exactly the eager launch sequence: same sums, same squared errors, new data per replay."""
+    B, H, W = 2, 64, 128
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    xs = [dw.make_input(s, B, H, W).cuda() for s in (0, 1)]
+    eager = []
+    for x in xs:
+        out = net.rd_forward(x)
+        bpp, v_mse, v_psnr = net.metrics(out, B, H, W)
+        eager.append((out["bits"].clone(), out["sq_err"].clone(), bpp.clone(), v_psnr.clone(), v_mse.clone()))
+    bufs = [torch.empty_like(xs[0]) for _ in range(2)]
+    gev = ldic.GraphedEvaluator(net, bufs)
+    assert gev.launches_per_replay > 20
+    for rep in range(2):
+        for k in (0, 1):
+            src = xs[(k + rep) % 2]
+            bufs[k].copy_(src)
+            n0 = ldic.ops.launch_count()
+            bpp, psnr, out = gev(k)
+            assert ldic.ops.launch_count() - n0 == 1          # only the finish kernel is launched from the host
+            e = eager[(k + rep) % 2]
+            assert torch.equal(out["bits"], e[0]) and torch.equal(out["sq_err"], e[1])
+            assert torch.equal(bpp, e[2]) and torch.equal(psnr, e[3]) and torch.equal(out["v_mse"], e[4])
