@@ -67,6 +67,8 @@ struct ConvParams {
   int stages;
   // halo variant: one (TH+dy range) x (TW+dx range) activation region per 64-channel chunk serves all taps
   int halo, SA, SB, a_slot_bytes, RW, RH, dxmin, dymin;
+  int ndx;                  // halo: 1 = one region, taps address it with row-shifted descriptor starts; > 1 = "aligned
+                            // halo": ndx copies of a TW-wide region, one per dx, so every tap starts 1024-byte aligned
   int G;                    // halo: filter taps per B-ring slot (one TMA box of G*Np weight rows)
   int gdn_insert;           // streaming kernels: conv stages of tile it+1 issued before the GDN stages of tile it
   int super_per_job;        // CTA-pair kernel: (tiles_per_job + 1) / 2 pairs of adjacent tiles per job
@@ -1126,7 +1128,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int gk = gdn ? P.gdn_kblocks : 0;
   const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const uint32_t region_bytes = (uint32_t)(P.RW * P.RH * 128);
+  const uint32_t sub_bytes = (uint32_t)(P.RW * P.RH * 128);
+  const uint32_t region_bytes = sub_bytes * (uint32_t)P.ndx;
   const uint32_t sbo = (uint32_t)P.RW * 128u;
   // a tap contributes to channel chunk kc iff its K range covers it
   auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
@@ -1156,8 +1159,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (elect_one()) {
             mbar_expect_tx(&afull[sa], region_bytes);
-            tma_load_4d(smem_base + sa * a_slot, &tmA, &afull[sa], (jb.kc0 + ci) * kBlockK, tc.x0 + P.dxmin,
-                        tc.y0 + P.dymin, tc.n0);
+            for (int sx = 0; sx < P.ndx; ++sx)
+              tma_load_4d(smem_base + sa * a_slot + (uint32_t)sx * sub_bytes, &tmA, &afull[sa], (jb.kc0 + ci) * kBlockK,
+                          tc.x0 + P.dxmin + sx, tc.y0 + P.dymin, tc.n0);
           }
           adv();
         }
@@ -1383,7 +1387,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int npairs = (int)gridDim.x >> 1, pi = (int)blockIdx.x >> 1;
   const int total_super = P.super_per_job * P.njobs;
   const int nt = (total_super - pi + npairs - 1) / npairs;             // super tiles of this pair
-  const uint32_t region_bytes = (uint32_t)(P.RW * P.RH * 128);
+  const uint32_t sub_bytes = (uint32_t)(P.RW * P.RH * 128);
+  const uint32_t region_bytes = sub_bytes * (uint32_t)P.ndx;
   const uint32_t sbo = (uint32_t)P.RW * 128u;
   const uint32_t afull_L = mapa_shared(smem_u32(afull), 0), bfull_L = mapa_shared(smem_u32(bfull), 0);
   auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
@@ -1412,8 +1417,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           if (elect_one()) {
             if (leader) mbar_expect_tx(&afull[sa], 2 * region_bytes);
-            tma_load_4d_cg2(smem_base + sa * a_slot, &tmA, afull_L + 8u * sa, (jb.kc0 + ci) * kBlockK, tc.x0 + P.dxmin,
-                            tc.y0 + P.dymin, tc.n0);
+            for (int sx = 0; sx < P.ndx; ++sx)
+              tma_load_4d_cg2(smem_base + sa * a_slot + (uint32_t)sx * sub_bytes, &tmA, afull_L + 8u * sa,
+                              (jb.kc0 + ci) * kBlockK, tc.x0 + P.dxmin + sx, tc.y0 + P.dymin, tc.n0);
           }
           adv();
         }
@@ -1477,9 +1483,14 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int cur_job = -1, ntaps = 0, nchunks = 0, kc0 = 0;
       int my_a_c0 = 1 << 30, my_a_c1 = 0;
       uint32_t my_lo = 0;
+      const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
+      long long t_a = 0, t_b = 0, t_buf = 0, t_x2 = 0, t0 = 0, n_it = 0;
+      const long long t_begin = clock64();
       auto gdn_of = [&](int j) {            // norm(j) = x^2 . gamma^T, in place over acc(j), both tiles of the pair
         const int bsel = j & 1;
+        if (dbg) t0 = clock64();
         mbar_wait_cl(&x2_ready[bsel], (j >> 1) & 1);
+        if (dbg) t_x2 += clock64() - t0;
         tc_fence_after();
         for (int kb = 0; kb < gk; ++kb) {
           mbar_wait_cl(&afull[sa], pa);
@@ -1511,14 +1522,18 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int jins = (gk && it > 0) ? (nchunks < kHaloInsert ? nchunks : kHaloInsert) : -1;
         const int bsel = it & 1;
         const uint32_t d_tmem = tmem_base + bsel * kBufCols;
+        if (dbg) t0 = clock64();
         mbar_wait_cl(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
+        if (dbg) t_buf += clock64() - t0;
         tc_fence_after();
         bool first = true;
         for (int ci = 0; ci < nchunks; ++ci) {
           if (ci == jins) gdn_of(it - 1);
           const int c = (kc0 + ci) * kBlockK;
           const uint32_t mask = __ballot_sync(0xffffffffu, c >= my_a_c0 && c < my_a_c1);   // taps covering this chunk
+          if (dbg) t0 = clock64();
           mbar_wait_cl(&afull[sa], pa);
+          if (dbg) t_a += clock64() - t0;
           const uint32_t a_reg_lo = a_lo0 + sa_lo;
           for (int tp = 0; tp < ntaps; tp += G_r) {
             if (!((mask >> tp) & 1u)) continue;
@@ -1529,7 +1544,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (g < G_r) alo[g] = a_reg_lo + __shfl_sync(0xffffffffu, my_lo, (tp + g) & 31);
             }
             const int ng = (ntaps - tp < G_r) ? ntaps - tp : G_r;
+            if (dbg) t0 = clock64();
             mbar_wait_cl(&bfull[sb], pb);
+            if (dbg) { t_b += clock64() - t0; ++n_it; }
             tc_fence_after();
             if (elect_one()) {
               const uint32_t bslot_lo = b_lo0 + sb_lo;
@@ -1554,6 +1571,11 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (nchunks == jins) gdn_of(it - 1);
       }
       if (gk) gdn_of(nt - 1);
+      if (dbg && lane == 0) {
+        P.dbg[0] = (unsigned long long)(clock64() - t_begin); P.dbg[1] = (unsigned long long)t_b;
+        P.dbg[2] = (unsigned long long)t_buf; P.dbg[3] = (unsigned long long)t_x2; P.dbg[4] = (unsigned long long)n_it;
+        P.dbg[5] = (unsigned long long)nt; P.dbg[6] = (unsigned long long)t_a;
+      }
     }
   } else {
     // ===================== epilogue warps (both CTAs, own tile) =====================
@@ -2428,8 +2450,14 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
     halo = halo && (halo_mode == 2 || (halo_mode == 1 && L.Np <= 64));
     if (halo) {
       P.halo = 1; P.dxmin = dxmin; P.dymin = dymin;
-      P.RW = 8 + dxmax - dxmin; P.RH = 16 + dymax - dymin;
-      P.a_slot_bytes = (P.RW * P.RH * 128 + 1023) / 1024 * 1024;
+      P.RW = 8 + dxmax - dxmin; P.RH = 16 + dymax - dymin; P.ndx = 1;
+      // Aligned halo: one 8-pixel-wide copy of the region per dx (row pitch 8 x 128 B = one swizzle atom), so the A
+      // descriptor of every tap starts on a 1024-byte boundary (dy shifts move by whole atoms) and the MMAs run at
+      // full rate; costs (dx range) x the region bytes of L2 -> SM traffic instead of one widened region.
+      bool aligned = dxmax > dxmin;
+      if (const char* e = getenv("LDIC_HALO_ALIGNED")) aligned = aligned && atoi(e) != 0;   // tuning aid
+      if (aligned) { P.ndx = dxmax - dxmin + 1; P.RW = 8; }
+      P.a_slot_bytes = (P.ndx * P.RW * P.RH * 128 + 1023) / 1024 * 1024;
       // taps per B slot: one TMA box holds up to 256 weight rows; only when every tap covers every chunk
       bool uniform = true;
       for (int t = 0; t < L.ntaps_total; ++t) uniform = uniform && L.taps[t].a_c0 == 0 && L.taps[t].nkc == L.taps[0].nkc;
@@ -2458,7 +2486,8 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
       P.total_tiles = P.tiles_per_job * P.njobs;
       P.super_per_job = (P.tiles_per_job + 1) / 2;
       for (int t = 0; t < L.ntaps_total; ++t)
-        P.taps[t].halo_off = ((P.taps[t].dy - dymin) * P.RW + (P.taps[t].dx - dxmin)) * 128;
+        P.taps[t].halo_off = P.ndx > 1 ? (P.taps[t].dx - dxmin) * (P.RW * P.RH * 128) + (P.taps[t].dy - dymin) * P.RW * 128
+                                       : ((P.taps[t].dy - dymin) * P.RW + (P.taps[t].dx - dxmin)) * 128;
       for (int j = 0; j < L.njobs; ++j) {
         int lo = 1 << 30, hi = 0;
         for (int t = 0; t < P.jobs[j].ntaps; ++t) {
