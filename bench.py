@@ -208,6 +208,8 @@ def run_ours(args):
 
     # per-launch CUDA events around every conv launch: the same K steps issued eagerly (events cannot be read back
     # from inside a graph replay); the kernels and their durations are the ones of the timed region
+    # (single stream: with g_s overlapped on the side stream the per-launch times would include SM contention)
+    overlap_was, net.overlap_streams = net.overlap_streams, False
     ops.PROFILE = []
     sync_all()
     e0.record()
@@ -216,6 +218,7 @@ def run_ours(args):
     e1.record()
     sync_all()
     prof, ops.PROFILE = ops.PROFILE, None
+    net.overlap_streams = overlap_was
     eager_ms = e0.elapsed_time(e1)
 
     # conv kernel roofline from the events recorded around every conv_tc launch of the timed region
@@ -334,6 +337,8 @@ def run_ours(args):
                         f"({gev.launches_per_replay} launches of libldic_b200), + 1 metric kernel per step" if use_graph
                         else "eager launches"),
         "eager_ms_per_step": eager_ms / args.steps,
+        "streams": ("g_s (3 deconv + fused tail) on a second stream next to the hyperprior / syntax / context chain"
+                    if net.overlap_streams else "single stream"),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_first / conv_tc / conv_halo kernels (g_a, g_s, h_a, h_s, context convs + fused GDN/IGDN)",
                      "achieved": achieved_tf, "peak": tc_peak_sus, "unit": "TFLOP/s",

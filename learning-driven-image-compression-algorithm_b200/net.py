@@ -205,6 +205,13 @@ class Net(nn.Module):
         self.context_on_torch = False     # True: run the context transform with torch ops (cross-check in tests)
         self.syntax_on_torch = os.environ.get("LDIC_SYNTAX_FUSED", "1") == "0"   # True: syntax branch as stock torch ops
         self.tail_fused = os.environ.get("LDIC_TAIL_FUSED", "1") != "0"          # batch_conv + MSE inside the last deconv
+        # g_s depends on round(y) only (its last layer also on the syntax filters): run it on a second stream next to
+        # the hyperprior / syntax / context chain, whose small-grid kernels leave most SMs idle
+        # -- measured NEGATIVE (3.45 vs 3.23 ms per step): the conv kernels are persistent with a static tile partition,
+        # so two of them never share the SMs usefully and a small concurrent kernel delays 12..48 CTAs of the big one
+        # (tail effect).  Kept as an experiment switch (LDIC_OVERLAP=1), off by default.
+        self.overlap_streams = os.environ.get("LDIC_OVERLAP", "0") == "1"
+        self._side_streams = {}
 
     # -- checkpoint compatibility ---------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -251,6 +258,16 @@ class Net(nn.Module):
 
         y = self.a_model.forward_nhwc(x)                                            # :627   (B,h,w,N) fp32 NHWC
         y_round_bf16, y_abs_bf16, _ = ops.latent_prep(y)                            # :197 abs, :741 round
+        overlap = (self.overlap_streams and self.tail_fused and not self.syntax_on_torch and not self.context_on_torch
+                   and self.s_model.has_fused_tail())
+        if overlap:
+            main = torch.cuda.current_stream(x.device)
+            side = self._side_streams.get(x.device.index)
+            if side is None:
+                side = self._side_streams[x.device.index] = torch.cuda.Stream(device=x.device)
+            side.wait_stream(main)                                                  # fork: round(y) is ready
+            with torch.cuda.stream(side):
+                gs_body = self.s_model.forward_nhwc_body(y_round_bf16)              # :800   first three deconv + IGDN
         z = self.ha_model.forward_nhwc(y_abs_bf16)                                  # :666   (B,h/4,w/4,N) fp32
         Pz = z.shape[0] * z.shape[1] * z.shape[2]
         z_hat_bf16 = torch.empty(z.shape, dtype=torch.bfloat16, device=x.device)
@@ -278,6 +295,11 @@ class Net(nn.Module):
         else:
             z3_syntax, z3_syntax_rounded, syn_first, syn_second, conv_w = ops.syntax_branch(
                 y, h2, M, self.syntax_model, self.prediction_model_syntax, self.conv_weights_gen)       # :712-719,:753,:789,:805
+        if overlap:                        # the per-image filters are ready: last deconv + batch_conv + MSE on the side stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fused_side = self.s_model.fused_tail(gs_body, x, conv_w.reshape(B, 3, M),                 # :800,:811,:864-868
+                                                     want_x_tilde=want_x_hat, want_out=want_xt16)
         if self.context_on_torch:          # cross-check path only (tests); the product path is raw_tc
             prev_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
             try:
@@ -304,7 +326,10 @@ class Net(nn.Module):
                                                 sum_out=bits[2:3])
 
         fused = None
-        if self.tail_fused:      # g_s with batch_conv + squared level error in the last deconv's epilogue
+        if overlap:
+            main.wait_stream(side)                                                  # join
+            fused = fused_side
+        elif self.tail_fused:    # g_s with batch_conv + squared level error in the last deconv's epilogue
             fused = self.s_model.forward_nhwc_fused_tail(y_round_bf16, x, conv_w.reshape(B, 3, M),        # :800,:811,:864-868
                                                          want_x_tilde=want_x_hat, want_out=want_xt16)
         if fused is not None:

@@ -148,13 +148,24 @@ class synthesisTransformModel(_PlannedTransform):
         """g_s with batch_conv (model/net.py:811) and the squared level error (:864-868) fused into the last
         deconv's epilogue.  Returns (sq_err int64[B], x_tilde or None, 16-channel g_s output or None); None when
         the last layer is not the merged small-Cout kind (caller falls back to forward_nhwc + syntax_conv_mse)."""
-        L = self.plan()
-        if L[-1].kind != _lib.LDIC_DECONV_GS_5x5_MERGED:
+        if not self.has_fused_tail():
             return None
+        t = self.forward_nhwc_body(y_hat_nhwc_bf16)
+        return self.fused_tail(t, image_nchw, conv_w, want_x_tilde=want_x_tilde, want_out=want_out)
+
+    def has_fused_tail(self) -> bool:
+        return self.plan()[-1].kind == _lib.LDIC_DECONV_GS_5x5_MERGED
+
+    def forward_nhwc_body(self, y_hat_nhwc_bf16):
+        """The first three deconv + IGDN layers (they depend on the rounded latent only)."""
         t = y_hat_nhwc_bf16
-        for layer in L[:-1]:
+        for layer in self.plan()[:-1]:
             t = layer(t)
-        return L[-1].fused_tail(t, image_nchw, conv_w, want_x_tilde=want_x_tilde, want_out=want_out)
+        return t
+
+    def fused_tail(self, t, image_nchw, conv_w, want_x_tilde=False, want_out=False):
+        """Last deconv + IGDN + batch_conv + squared level error on the output of forward_nhwc_body."""
+        return self.plan()[-1].fused_tail(t, image_nchw, conv_w, want_x_tilde=want_x_tilde, want_out=want_out)
 
     def forward(self, inputs):
         L = self.plan()

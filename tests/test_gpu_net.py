@@ -213,3 +213,19 @@ def test_graph_replay_is_bit_identical_to_eager(ldic):
             e = eager[(k + rep) % 2]
             assert torch.equal(out["bits"], e[0]) and torch.equal(out["sq_err"], e[1])
             assert torch.equal(bpp, e[2]) and torch.equal(psnr, e[3]) and torch.equal(out["v_mse"], e[4])
+
+
+def test_two_stream_forward_is_bit_identical_to_single_stream(ldic):
+    """g_s on the side stream (Net.overlap_streams) changes the schedule, not one bit of the results."""
+    B, H, W = 2, 64, 128
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    x = dw.make_input(3, B, H, W).cuda()
+    res = []
+    for ov in (True, False, True):
+        net.overlap_streams = ov
+        out = net.rd_forward(x, want_x_hat=True)
+        torch.cuda.synchronize()
+        res.append((out["bits"].clone(), out["sq_err"].clone(), out["x_hat"].clone()))
+    for r in res[1:]:
+        assert torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1]) and torch.equal(r[2], res[0][2])
