@@ -1,7 +1,7 @@
 # round-end evidence: tests, bench lines (ours + reference arm), launch list, full ncu capture of one step, likelihood kernel capture
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
-for t in test_gpu_entropy test_gpu_conv test_gpu_net; do
+for t in test_gpu_entropy test_gpu_conv test_gpu_net test_gpu_winattn test_tritplane; do
   timeout 300 python -m pytest tests/$t.py -q -m gpu -x --no-header -p no:cacheprovider > gpurun_out/$t.log 2>&1
   echo "$t exit $?" >> gpurun_out/summary.txt
 done
@@ -11,7 +11,8 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launch.log 2>&1
 echo "launchlist exit $?" >> gpurun_out/summary.txt
-timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|conv_halo|conv_first|k_likelihood" -s 57 -c 19 -o gpurun_out/prof_step -f $BENCH > gpurun_out/ncu_step.log 2>&1
+# one whole step, launches issued eagerly (21 matching launches per step: 1 conv_first, 16 conv_tc2, 1 conv_halo2, 3 likelihood)
+timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|conv_halo|conv_first|k_likelihood" -s 63 -c 21 -o gpurun_out/prof_step -f $BENCH --no-graph > gpurun_out/ncu_step.log 2>&1
 echo "ncu step exit $?" >> gpurun_out/summary.txt
 timeout 120 python tools/prof_likelihood.py 5 > gpurun_out/lik_plain.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_likelihood -s 3 -c 1 -o gpurun_out/prof_lik -f python tools/prof_likelihood.py 5 > gpurun_out/ncu_lik.log 2>&1
