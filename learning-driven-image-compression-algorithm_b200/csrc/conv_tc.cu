@@ -1483,14 +1483,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int cur_job = -1, ntaps = 0, nchunks = 0, kc0 = 0;
       int my_a_c0 = 1 << 30, my_a_c1 = 0;
       uint32_t my_lo = 0;
-      const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
-      long long t_a = 0, t_b = 0, t_buf = 0, t_x2 = 0, t0 = 0, n_it = 0;
-      const long long t_begin = clock64();
+      // (no cycle counters here: the MMA warp runs with 64 registers, six 64-bit counters spilled and cost 20 %)
       auto gdn_of = [&](int j) {            // norm(j) = x^2 . gamma^T, in place over acc(j), both tiles of the pair
         const int bsel = j & 1;
-        if (dbg) t0 = clock64();
         mbar_wait_cl(&x2_ready[bsel], (j >> 1) & 1);
-        if (dbg) t_x2 += clock64() - t0;
         tc_fence_after();
         for (int kb = 0; kb < gk; ++kb) {
           mbar_wait_cl(&afull[sa], pa);
@@ -1522,18 +1518,14 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int jins = (gk && it > 0) ? (nchunks < kHaloInsert ? nchunks : kHaloInsert) : -1;
         const int bsel = it & 1;
         const uint32_t d_tmem = tmem_base + bsel * kBufCols;
-        if (dbg) t0 = clock64();
         mbar_wait_cl(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
-        if (dbg) t_buf += clock64() - t0;
         tc_fence_after();
         bool first = true;
         for (int ci = 0; ci < nchunks; ++ci) {
           if (ci == jins) gdn_of(it - 1);
           const int c = (kc0 + ci) * kBlockK;
           const uint32_t mask = __ballot_sync(0xffffffffu, c >= my_a_c0 && c < my_a_c1);   // taps covering this chunk
-          if (dbg) t0 = clock64();
           mbar_wait_cl(&afull[sa], pa);
-          if (dbg) t_a += clock64() - t0;
           const uint32_t a_reg_lo = a_lo0 + sa_lo;
           for (int tp = 0; tp < ntaps; tp += G_r) {
             if (!((mask >> tp) & 1u)) continue;
@@ -1544,9 +1536,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (g < G_r) alo[g] = a_reg_lo + __shfl_sync(0xffffffffu, my_lo, (tp + g) & 31);
             }
             const int ng = (ntaps - tp < G_r) ? ntaps - tp : G_r;
-            if (dbg) t0 = clock64();
             mbar_wait_cl(&bfull[sb], pb);
-            if (dbg) { t_b += clock64() - t0; ++n_it; }
             tc_fence_after();
             if (elect_one()) {
               const uint32_t bslot_lo = b_lo0 + sb_lo;
@@ -1571,11 +1561,6 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (nchunks == jins) gdn_of(it - 1);
       }
       if (gk) gdn_of(nt - 1);
-      if (dbg && lane == 0) {
-        P.dbg[0] = (unsigned long long)(clock64() - t_begin); P.dbg[1] = (unsigned long long)t_b;
-        P.dbg[2] = (unsigned long long)t_buf; P.dbg[3] = (unsigned long long)t_x2; P.dbg[4] = (unsigned long long)n_it;
-        P.dbg[5] = (unsigned long long)nt; P.dbg[6] = (unsigned long long)t_a;
-      }
     }
   } else {
     // ===================== epilogue warps (both CTAs, own tile) =====================
@@ -2454,8 +2439,10 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
       // Aligned halo: one 8-pixel-wide copy of the region per dx (row pitch 8 x 128 B = one swizzle atom), so the A
       // descriptor of every tap starts on a 1024-byte boundary (dy shifts move by whole atoms) and the MMAs run at
       // full rate; costs (dx range) x the region bytes of L2 -> SM traffic instead of one widened region.
-      bool aligned = dxmax > dxmin;
-      if (const char* e = getenv("LDIC_HALO_ALIGNED")) aligned = aligned && atoi(e) != 0;   // tuning aid
+      // Measured: no gain (the MMAs of this kernel are bound by their own shared-memory operand reads, not by the
+      // descriptor alignment), so the single widened region stays the default.
+      bool aligned = false;
+      if (const char* e = getenv("LDIC_HALO_ALIGNED")) aligned = dxmax > dxmin && atoi(e) != 0;   // experiment switch
       if (aligned) { P.ndx = dxmax - dxmin + 1; P.RW = 8; }
       P.a_slot_bytes = (P.ndx * P.RW * P.RH * 128 + 1023) / 1024 * 1024;
       // taps per B slot: one TMA box holds up to 256 weight rows; only when every tap covers every chunk

@@ -57,23 +57,27 @@ __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float
     const int ky = tap / 3, kx = tap - ky * 3;
     const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
     const bool in = live && iy >= 0 && iy < H && ix >= 0 && ix < W;
-    float xv[kScChunk];
+    // One float4 of the pixel's channels at a time, the next one already in flight.  The loop is deliberately NOT
+    // unrolled over the 32 channels: straight-line code of 32 x (COUT/4 loads + COUT FMAs) is ~40 KB for COUT = 64 and
+    // runs once or twice per warp, i.e. at instruction-fetch speed (sm_down1 took 55 us for 56 MFLOP).
     const float4* xp = reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * xs + c0);
-#pragma unroll
-    for (int j4 = 0; j4 < kScChunk / 4; ++j4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (in && 4 * j4 < ck) v = __ldg(xp + j4);
-      xv[4 * j4] = v.x; xv[4 * j4 + 1] = v.y; xv[4 * j4 + 2] = v.z; xv[4 * j4 + 3] = v.w;
-    }
     const float4* wr = reinterpret_cast<const float4*>(wp + ((size_t)tap * Cin + c0) * COUT);
+    const int n4 = ck / 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 vn = in ? __ldg(xp) : zero4;
+#pragma unroll 1
+    for (int j4 = 0; j4 < n4; ++j4) {
+      const float4 v = vn;
+      if (j4 + 1 < n4) vn = in ? __ldg(xp + j4 + 1) : zero4;
+      const float x4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < kScChunk; ++j) {
-      if (j < ck) {
+      for (int u = 0; u < 4; ++u) {
+        const float4* wj = wr + (j4 * 4 + u) * (COUT / 4);
 #pragma unroll
         for (int c4 = 0; c4 < COUT / 4; ++c4) {
-          const float4 w4 = __ldg(wr + j * (COUT / 4) + c4);
-          acc[4 * c4] = fmaf(xv[j], w4.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(xv[j], w4.y, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(xv[j], w4.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(xv[j], w4.w, acc[4 * c4 + 3]);
+          const float4 w4 = __ldg(wj + c4);
+          acc[4 * c4] = fmaf(x4[u], w4.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(x4[u], w4.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(x4[u], w4.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(x4[u], w4.w, acc[4 * c4 + 3]);
         }
       }
     }
