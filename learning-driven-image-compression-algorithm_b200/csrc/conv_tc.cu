@@ -67,6 +67,7 @@ struct ConvParams {
   int stages;
   // halo variant: one (TH+dy range) x (TW+dx range) activation region per 64-channel chunk serves all taps
   int halo, SA, SB, a_slot_bytes, RW, RH, dxmin, dymin;
+  int x_ovl;                // tiles overlap by x_ovl pixels in x (wide-N merged deconv: 2 = one halo pixel per side), else 0
   int ndx;                  // halo: 1 = one region, taps address it with row-shifted descriptor starts; > 1 = "aligned
                             // halo": ndx copies of a TW-wide region, one per dx, so every tap starts 1024-byte aligned
   int G;                    // halo: filter taps per B-ring slot (one TMA box of G*Np weight rows)
@@ -361,7 +362,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, int t) {
   int tx = r - ty * P.tiles_x;
   c.n0 = tn * P.TN;
   c.y0 = ty * P.TH;
-  c.x0 = tx * P.TW;
+  c.x0 = tx * (P.TW - P.x_ovl) - (P.x_ovl >> 1);
   return c;
 }
 
@@ -637,6 +638,131 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Epilogue of the wide-N merged last deconv (CTA-pair streaming kernel, W3 = true).
+// The accumulator holds NP = 3 * NPO columns: block dxi = columns [dxi*NPO, +NPO) is
+//   D[p][dxi] = sum_dy sum_k X[p + (dy, 0)][k] * W[(dy, dxi - 1)][k][.]        (NPO = 4 sub-pixel phases x Cg channels)
+// i.e. the three dx taps are carried side by side in N instead of as separate N = NPO MMAs (an SS-mode MMA costs
+// ~55 cycles at N = 64 but 96 at N = 192: 36 MMAs per tile instead of 108).  The transposed conv output of pixel p is
+//   acc[p] = D[p-1][0] + D[p][1] + D[p+1][2],
+// and with TW = 32 a warp is one row of the tile (lane = x), so the neighbours are lanes -1 / +1: two shuffles per
+// column.  Lanes 0 and 31 are halo pixels (tiles overlap by 2 in x), they contribute but are not written.
+// Then the usual IGDN (x^2 tile -> gamma contraction with N = NPO -> x * sqrt(norm)), optional NHWC store of the
+// 4 x Cg sub-pixel outputs, and the fused tail (batch_conv + squared level error).
+// ---------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& R, uint32_t tmem_base, int gk,
+                                            int ntiles_cta, int warp, int lane) {
+  constexpr int NPO = NP / 3;
+  constexpr int CPT = NPO / (kEpiWarps / 4);             // output columns per thread (32)
+  static_assert(CPT == 32, "wide-N merged deconv: 64 logical columns, 8 epilogue warps");
+  const int q = warp & 3, h = warp >> 2;
+  const int r = q * 32 + lane;
+  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+  const int col0 = h * CPT;
+  const int xi = r & (P.TW - 1), yi = (r >> P.tw_shift) & (P.TH - 1), ni = r >> (P.tw_shift + P.th_shift);
+  uint32_t sbase = 0;
+  auto decode_it = [&](int i) { return decode_tile2(P, R.t_first + i * R.t_stride, R.rank); };
+  TileCoord tc = decode_it(0), tc_n1 = decode_it(1), tc_n2 = tc_n1;
+  for (int it = 0; it < ntiles_cta; ++it, tc = tc_n1, tc_n1 = tc_n2) {
+    const Job jb = P.jobs[tc.job];
+    const int bsel = it & 1;
+    const uint32_t par = (uint32_t)(it >> 1) & 1u;
+    const uint32_t tbuf = tmem_base + bsel * kBufCols + lane_sel;
+    const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
+    const bool valid = xi >= 1 && xi <= P.TW - 2 && gx_ < P.Wg && gy_ < P.Hg && gn_ < P.B && !P.dbg_nostore;
+    const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
+                               (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
+    sbase += (uint32_t)jb.nkb + (it > 0 ? (uint32_t)gk : 0u);
+    uint32_t gpos = sbase;
+    if (it + 1 < ntiles_cta) {
+      const int len_next = P.jobs[tc_n1.job].nkb;
+      gpos += (uint32_t)(len_next < R.insert_after ? len_next : R.insert_after);
+    }
+    mbar_wait(&R.acc_full[bsel], par);
+    tc_fence_after();
+    // ---- pass 1: the three dx blocks of this thread's 32 columns, combined across the x neighbours ----
+    float xr[CPT];
+    {
+      uint32_t d0[CPT], d1[CPT], d2[CPT];
+      tmem_ldn<32>(tbuf + 0 * NPO + col0, d0);
+      tmem_ldn<32>(tbuf + 1 * NPO + col0, d1);
+      tmem_ldn<32>(tbuf + 2 * NPO + col0, d2);
+      tmem_ld_wait();
+      const float* sb = R.s_bias;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(d0[c]), 1);       // D[p-1][0]
+        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[c]), 1);     // D[p+1][2]
+        xr[c] = (up + __uint_as_float(d1[c])) + dn + sb[col0 + c];
+      }
+    }
+    tc_fence_before();
+    // x^2 -> bf16 -> the one operand slot of the gamma contraction (K = NPO = 64 columns)
+    {
+      const uint32_t kc2 = gpos;
+      mbar_wait(&R.empty_bar[kc2 % R.nslots], ((kc2 / R.nslots) & 1) ^ 1);
+      const uint32_t a_addr = R.ring_base + (kc2 % R.nslots) * R.slot_bytes;
+      const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
+#pragma unroll
+      for (int j = 0; j < CPT / 8; ++j) {
+        const uint32_t chunk = (uint32_t)((col0 + j * 8) >> 3);
+        const float* x8 = &xr[j * 8];
+        st_shared_v4(a_addr + row_off + ((chunk ^ rx) << 4), pack_bf16x2(x8[0] * x8[0], x8[1] * x8[1]),
+                     pack_bf16x2(x8[2] * x8[2], x8[3] * x8[3]), pack_bf16x2(x8[4] * x8[4], x8[5] * x8[5]),
+                     pack_bf16x2(x8[6] * x8[6], x8[7] * x8[7]));
+      }
+      fence_async_smem();
+      mbar_arrive_cluster(R.x2_ready_cl + 8u * bsel);
+    }
+    tc_n2 = decode_it(it + 2);
+    mbar_wait(&R.norm_full[bsel], par);
+    tc_fence_after();
+    // ---- pass 2: IGDN  out = x * sqrt(norm + beta) = x * n * rsqrt(n)   (GDN: x * rsqrt(n)) ----
+    {
+      uint32_t tr[CPT];
+      tmem_ldn<32>(tbuf + col0, tr);           // the contraction wrote norm over columns [0, NPO) of the buffer
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_cluster(R.buf_free_cl + 8u * bsel);
+      const bool igdn = (P.act == LDIC_ACT_IGDN);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const float nrm = __uint_as_float(tr[c]) + R.s_beta[col0 + c];
+        const float rs = rsqrt_approx(nrm);
+        xr[c] *= igdn ? nrm * rs : rs;
+      }
+    }
+    unsigned long long tail_acc = 0;
+    if (valid) {
+      if (P.out) {
+#pragma unroll
+        for (int j = 0; j < CPT / 8; ++j) {
+          const int col = col0 + j * 8;
+          const int g = col >> P.cg_shift, cc = col & (P.Cg - 1);
+          const long long off = pix_base + (long long)(g >> 1) * P.out_sY + (long long)(g & 1) * P.out_sX + cc;
+          const float* x8 = &xr[j * 8];
+          if (P.out_f32) {
+            st_global_v8(reinterpret_cast<float*>(P.out) + off, x8);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + off);
+            *dst = make_uint4(pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]),
+                              pack_bf16x2(x8[6], x8[7]));
+          }
+        }
+      }
+      if (P.tail_x && P.Cg == 16)
+        tail_acc = fused_tail_pixels<CPT, 16>(P, xr, col0, gn_, gy_ * P.sy + jb.oy_off, gx_ * P.sx + jb.ox_off);
+    }
+    if (P.tail_x) {                            // TN == 1: one image per tile, one warp-level sum and one atomic per warp
+      unsigned long long v = tail_acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v) atomicAdd(P.tail_sq + tc.n0, v);
+    }
+  }
+}
+
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -849,13 +975,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // both CTAs land on the leader's full barriers, tcgen05.commit multicasts to both CTAs, the peer's epilogue
 // reaches the leader's x2_ready / buf_free barriers through shared::cluster addresses.
 // ---------------------------------------------------------------------------------
-template <int NP>
+// W3 = true: wide-N form of the merged last deconv (see epilogue_w3): NP = 3 * NPO accumulator columns, bias / beta /
+// gamma refer to the NPO logical columns and the gamma contraction is an N = NPO MMA.
+template <int NP, bool W3 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
+  constexpr int NPO = W3 ? NP / 3 : NP;
   constexpr int kBHalfBytes = (NP / 2) * kBlockK * 2;
+  constexpr int kGHalfBytes = (NPO / 2) * kBlockK * 2;
   constexpr int kStageBytes = kATileBytes + kBHalfBytes;
   constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr uint32_t kIdescG = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPO >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -891,8 +1022,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (gdn) prefetch_tmap(&tmG);
   }
   if (warp == kMmaWarp) tmem_alloc_cg2(tmem_ptr, kTmemCols);
-  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
-  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
+  for (int i = threadIdx.x; i < NPO * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < NPO; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -922,15 +1053,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool pdbg = IS_A && P.dbg != nullptr && blockIdx.x == 0;
         long long t_empty = 0, tp0 = 0;
         const long long tp_begin = clock64();
-        const int row_half = (int)rank * (NP / 2);
+        const int row_half = (int)rank * (NP / 2), row_half_g = (int)rank * (NPO / 2);
         auto advance = [&]() { if (++slot == (uint32_t)stages_r) { slot = 0; ph ^= 1; } };
         auto load_gamma = [&]() {
           for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring (B half only)
             if constexpr (!IS_A) {
               mbar_wait(&empty_bar[slot], ph ^ 1);
               if (elect_one()) {
-                if (leader) mbar_expect_tx(&full_bar[slot], 2 * kBHalfBytes);
-                tma_load_2d_cg2(smem_base + slot * kStageBytes + kATileBytes, &tmG, full_L + 8u * slot, kb * kBlockK, row_half);
+                if (leader) mbar_expect_tx(&full_bar[slot], 2 * kGHalfBytes);
+                tma_load_2d_cg2(smem_base + slot * kStageBytes + kATileBytes, &tmG, full_L + 8u * slot, kb * kBlockK, row_half_g);
               }
             }
             advance();
@@ -992,7 +1123,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
       long long t_full = 0, t_buf = 0, t_x2 = 0, n_st = 0, t0 = 0;
       const long long t_begin = clock64();
-      auto mma_stage = [&](uint32_t d_tmem, bool first) {
+      auto mma_stage = [&](uint32_t d_tmem, bool first, uint32_t idesc) {
         if (dbg) t0 = clock64();
         mbar_wait_cl(&full_bar[slot], ph);
         if (dbg) { t_full += clock64() - t0; ++n_st; }
@@ -1001,7 +1132,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t alo = a_lo0 + slot_lo, blo = b_lo0 + slot_lo;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16_lh_cg2(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, kIdesc2, !(first && k == 0));
+            umma_bf16_lh_cg2(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, idesc, !(first && k == 0));
           tc_commit_mc(&empty_bar[slot]);                    // frees the slot in both CTAs when these MMAs retire
         }
         ++slot; slot_lo += (uint32_t)(kStageBytes >> 4);
@@ -1013,7 +1144,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait_cl(&x2_ready[bsel], (j >> 1) & 1);          // x^2 tiles written by the epilogue warps of both CTAs
         if (dbg) t_x2 += clock64() - t0;
         tc_fence_after();
-        for (int kb = 0; kb < gk; ++kb) mma_stage(tmem_base + bsel * kBufCols, kb == 0);
+        for (int kb = 0; kb < gk; ++kb) mma_stage(tmem_base + bsel * kBufCols, kb == 0, kIdescG);
         if (elect_one()) tc_commit_mc(&norm_full[bsel]);
       };
       int cur_job = -1, nkb = 0;
@@ -1028,7 +1159,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
           if (kb == jins) gdn_of(it - 1);
-          mma_stage(tmem_base + bsel * kBufCols, kb == 0);
+          mma_stage(tmem_base + bsel * kBufCols, kb == 0, kIdesc2);
         }
         if (elect_one()) tc_commit_mc(&acc_full[bsel]);
         if (nkb == jins) gdn_of(it - 1);
@@ -1049,7 +1180,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
     R.t_first = pi; R.t_stride = npairs; R.rank = (int)rank;
     R.buf_free_cl = mapa_shared(smem_u32(buf_free), 0); R.x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0);
-    epilogue_role<NP, true>(P, R, tmem_base, gk, nt, warp, lane);
+    if constexpr (W3) epilogue_w3<NP>(P, R, tmem_base, gk, nt, warp, lane);
+    else epilogue_role<NP, true>(P, R, tmem_base, gk, nt, warp, lane);
   }
 
   tc_fence_before();
@@ -2105,9 +2237,9 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g
   return check_launch("conv_halo_kernel");
 }
 
-template <int NP, int HALO>
+template <int NP, int HALO, bool W3 = false>
 int launch_pair(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
-  auto kern = HALO ? conv_halo2_kernel<NP> : conv_tc2_kernel<NP>;
+  auto kern = HALO ? conv_halo2_kernel<NP> : conv_tc2_kernel<NP, W3>;
   const size_t smem = HALO ? (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * (NP / 2) * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
                                  (size_t)(P.nbias + 1) * NP * sizeof(float) + 64
                            : (size_t)P.stages * (kATileBytes + (NP / 2) * kBlockK * 2) + 1024 + 256 + (size_t)(P.nbias + 1) * NP * sizeof(float);
@@ -2418,9 +2550,30 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
   P.stages = stages;
   if (gdn && stages < P.gdn_kblocks + 1) return fail(LDIC_EINVAL, "conv: not enough pipeline stages for the GDN epilogue");
 
+  // ---- wide-N form of the merged last deconv (epilogue_w3): the three dx taps ride side by side in N = 3 * Np, the dy
+  // taps are three stride-1 gathers of a 32 x 4 pixel tile (tiles overlap by one halo pixel per side in x) ----
+  bool wide3 = d->kind == LDIC_DECONV_GS_5x5_MERGED && gdn && L.Np == 64 && L.ngroups == 4 && L.Cg == 16 && L.njobs == 1 &&
+               L.ntaps_total == 9 && L.nbias == 1;
+  if (const char* e = getenv("LDIC_TAIL_WIDE")) wide3 = wide3 && atoi(e) != 0;           // tuning aid: LDIC_TAIL_WIDE=0
+  if (wide3) {
+    P.TW = 32; P.TH = 4; P.TN = 1; P.tw_shift = 5; P.th_shift = 2; P.x_ovl = 2;
+    P.tiles_x = (L.Wg + P.TW - P.x_ovl - 1) / (P.TW - P.x_ovl);
+    P.tiles_y = (L.Hg + P.TH - 1) / P.TH;
+    P.tiles_n = L.Bg;
+    P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
+    P.total_tiles = P.tiles_per_job;
+    const short nkc = L.taps[0].nkc;
+    for (int t = 0; t < 3; ++t) {            // packed weights are [tap = (dy+1)*3 + (dx+1)][Np][K]: rows t*3*Np .. +3*Np = one dy
+      Tap tp; memset(&tp, 0, sizeof(tp));
+      tp.dx = 0; tp.dy = (short)(t - 1); tp.nkc = nkc;
+      P.taps[t] = tp;
+    }
+    P.jobs[0].ntaps = 3; P.jobs[0].tap_begin = 0; P.jobs[0].nkb = 3 * nkc;
+  }
+
   // ---- halo variant (stride-1 gathers with spatial taps): one region load per 64-channel chunk ----
   bool halo = false, pair = false;
-  if (L.mode == 0) {
+  if (L.mode == 0 && !wide3) {
     int dxmin = 0, dxmax = 0, dymin = 0, dymax = 0;
     for (int t = 0; t < L.ntaps_total; ++t) {
       dxmin = L.taps[t].dx < dxmin ? L.taps[t].dx : dxmin; dxmax = L.taps[t].dx > dxmax ? L.taps[t].dx : dxmax;
@@ -2493,10 +2646,12 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
   // CTA pairs for the streaming kernel (cta_group::2): not for the x-parity fallback view
   bool pair_stream = !halo && P.mode != 1;
   if (const char* e = getenv("LDIC_PAIR")) pair_stream = pair_stream && atoi(e) != 0;      // tuning aid: LDIC_PAIR=0
+  const int NpK = wide3 ? 3 * L.Np : L.Np;        // accumulator columns of the kernel
+  if (wide3 && !pair_stream) return fail(LDIC_EINVAL, "conv: the wide-N merged deconv needs the CTA-pair kernel (unset LDIC_PAIR / LDIC_TAIL_WIDE=0)");
   if (pair_stream) {
     P.super_per_job = (P.tiles_per_job + 1) / 2;
-    const int stage2 = kATileBytes + (L.Np / 2) * kBlockK * 2;
-    int st2 = (227 * 1024 - 2048 - (L.nbias + 1) * L.Np * 4) / stage2;
+    const int stage2 = kATileBytes + (NpK / 2) * kBlockK * 2;
+    int st2 = (227 * 1024 - 2048 - (L.nbias + 1) * NpK * 4) / stage2;
     if (st2 > kMaxStages) st2 = kMaxStages;
     if (const char* e = getenv("LDIC_STAGES")) { int v = atoi(e); if (v >= 2 && v < st2) st2 = v; }
     P.stages = st2;
@@ -2530,7 +2685,7 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.ntaps_total * L.Np};
     cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? L.Np / 2 : L.Np * (halo ? P.G : 1))};
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? NpK / 2 : L.Np * (halo ? P.G : 1))};
     if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
   }
   if (gdn) {
@@ -2556,6 +2711,8 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
       case 192: rc = launch_halo<192>(tmA, tmW, tmG, P, st); break;
       case 256: rc = launch_halo<256>(tmA, tmW, tmG, P, st); break;
     }
+  } else if (wide3) {
+    rc = launch_pair<192, 0, true>(tmA, tmW, tmG, P, st);
   } else if (pair_stream) {
     switch (L.Np) {
       case 64: rc = launch_pair<64, 0>(tmA, tmW, tmG, P, st); break;
