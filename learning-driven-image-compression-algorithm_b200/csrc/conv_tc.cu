@@ -662,6 +662,11 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
   const int col0 = h * CPT;
   const int xi = r & (P.TW - 1), yi = (r >> P.tw_shift) & (P.TH - 1), ni = r >> (P.tw_shift + P.th_shift);
   uint32_t sbase = 0;
+  const bool edbg = P.dbg != nullptr && blockIdx.x == 0 && warp == 0;
+  long long e_acc = 0, e_norm = 0, e_slot = 0, e_t0 = 0, e_p1 = 0, e_p2 = 0, e_t1 = 0;
+  const long long e_begin = edbg ? clock64() : 0;
+  float wreg[48];                        // the current image's batch_conv filter (3 x 16), reloaded when the image changes
+  int w_n = -1;
   auto decode_it = [&](int i) { return decode_tile2(P, R.t_first + i * R.t_stride, R.rank); };
   TileCoord tc = decode_it(0), tc_n1 = decode_it(1), tc_n2 = tc_n1;
   for (int it = 0; it < ntiles_cta; ++it, tc = tc_n1, tc_n1 = tc_n2) {
@@ -679,7 +684,9 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
       const int len_next = P.jobs[tc_n1.job].nkb;
       gpos += (uint32_t)(len_next < R.insert_after ? len_next : R.insert_after);
     }
+    if (edbg) e_t0 = clock64();
     mbar_wait(&R.acc_full[bsel], par);
+    if (edbg) { e_t1 = clock64(); e_acc += e_t1 - e_t0; }
     tc_fence_after();
     // ---- pass 1: the three dx blocks of this thread's 32 columns, combined across the x neighbours ----
     float xr[CPT];
@@ -701,7 +708,9 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
     // x^2 -> bf16 -> the one operand slot of the gamma contraction (K = NPO = 64 columns)
     {
       const uint32_t kc2 = gpos;
+      if (edbg) { e_t0 = clock64(); e_p1 += e_t0 - e_t1; }
       mbar_wait(&R.empty_bar[kc2 % R.nslots], ((kc2 / R.nslots) & 1) ^ 1);
+      if (edbg) { e_t1 = clock64(); e_slot += e_t1 - e_t0; }
       const uint32_t a_addr = R.ring_base + (kc2 % R.nslots) * R.slot_bytes;
       const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
 #pragma unroll
@@ -716,7 +725,14 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
       mbar_arrive_cluster(R.x2_ready_cl + 8u * bsel);
     }
     tc_n2 = decode_it(it + 2);
+    if (P.tail_x && tc.n0 != w_n && tc.n0 < P.B) {       // warp-uniform: tiles of one image come in runs
+      w_n = tc.n0;
+#pragma unroll
+      for (int i = 0; i < 48; ++i) wreg[i] = __ldg(P.tail_w + (long long)w_n * 48 + i);
+    }
+    if (edbg) { e_t0 = clock64(); e_p1 += e_t0 - e_t1; }
     mbar_wait(&R.norm_full[bsel], par);
+    if (edbg) { e_t1 = clock64(); e_norm += e_t1 - e_t0; }
     tc_fence_after();
     // ---- pass 2: IGDN  out = x * sqrt(norm + beta) = x * n * rsqrt(n)   (GDN: x * rsqrt(n)) ----
     {
@@ -751,15 +767,41 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
           }
         }
       }
-      if (P.tail_x && P.Cg == 16)
-        tail_acc = fused_tail_pixels<CPT, 16>(P, xr, col0, gn_, gy_ * P.sy + jb.oy_off, gx_ * P.sx + jb.ox_off);
+      if (P.tail_x) {
+        // batch_conv (model/net.py:527-537, :811) on this thread's two output pixels with the filter in registers,
+        // then the a11 squared level error against the input image (model/net.py:864-868)
+        const int oy0 = gy_ * P.sy + jb.oy_off, ox0 = gx_ * P.sx + jb.ox_off;
+#pragma unroll
+        for (int jj = 0; jj < CPT; jj += 16) {
+          const int g = (col0 + jj) >> 4;
+          const int oy = oy0 + (g >> 1), ox = ox0 + (g & 1);
+          float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[c] = fmaf(xr[jj + m], wreg[c * 16 + m], o[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const long long idx = (((long long)gn_ * 3 + c) * P.tail_H + oy) * P.tail_W + ox;
+            if (P.tail_xo) P.tail_xo[idx] = o[c];
+            tail_acc += sq_level_err(__ldg(P.tail_x + idx), o[c], 0);
+          }
+        }
+      }
     }
+    if (edbg) e_p2 += clock64() - e_t1;
     if (P.tail_x) {                            // TN == 1: one image per tile, one warp-level sum and one atomic per warp
       unsigned long long v = tail_acc;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0 && v) atomicAdd(P.tail_sq + tc.n0, v);
     }
+  }
+  if (edbg && lane == 0) {
+    P.dbg[16] = (unsigned long long)(clock64() - e_begin); P.dbg[17] = (unsigned long long)e_acc;
+    P.dbg[18] = (unsigned long long)e_norm; P.dbg[19] = (unsigned long long)e_slot; P.dbg[20] = (unsigned long long)ntiles_cta;
+    P.dbg[21] = (unsigned long long)e_p1; P.dbg[22] = (unsigned long long)e_p2;
   }
 }
 
