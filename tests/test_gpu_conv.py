@@ -141,10 +141,13 @@ def test_deconv_gs_igdn_with_channel_offset(ldic, B, H, W):
     close(y, ref, 2e-3, 5e-4)
 
 
-def test_deconv_gs_merged_small_cout(ldic):
+@pytest.mark.parametrize("B,H,W", [(2, 12, 20), (1, 4, 30), (1, 5, 31), (3, 3, 1), (1, 9, 61), (1, 32, 48)])
+def test_deconv_gs_merged_small_cout(ldic, B, H, W):
+    """Merged last deconv (wide-N form: dx taps in N, 32 x 4 tiles overlapping by one halo pixel per side in x):
+    widths around the 30-pixel tile stride, heights that are not multiples of 4, a one-pixel-wide image."""
     L = ldic._lib
     N, M = 192, 16
-    x = bf(rnd((2, N, 12, 20), 17))
+    x = bf(rnd((B, N, H, W), 17))
     w, b = rnd((N, M, 5, 5), 18, 0.02), rnd((M,), 19, 0.1)
     bp, gp = gdn_params(M, 20)
     ref = F.conv_transpose2d(F.pad(x, (1, 0, 1, 0)), bf(w), b, stride=2, padding=3, output_padding=1)
@@ -152,8 +155,26 @@ def test_deconv_gs_merged_small_cout(ldic):
     layer = ldic.ops.ConvTC(L.LDIC_DECONV_GS_5x5_MERGED, w.cuda(), b.cuda(), act=L.ACT_IGDN, out_f32=True,
                             gdn=(bp.cuda(), gp.cuda()) + rp.model_gdn_constants())
     y = layer(to_nhwc_bf16(x)).cpu().permute(0, 3, 1, 2)
-    assert y.shape == ref.shape == (2, M, 24, 40)
+    assert y.shape == ref.shape == (B, M, 2 * H, 2 * W)
     close(y, ref, 2e-3, 5e-4)
+
+
+def test_deconv_gs_merged_wide_vs_tap_accumulating_form(ldic, monkeypatch):
+    """The wide-N kernel against the earlier formulation of the same layer (nine N=64 taps accumulated in TMEM,
+    LDIC_TAIL_WIDE=0): same operands, fp32 accumulation on both sides, only the summation order of the three dx
+    contributions differs -- which can flip the bf16 rounding of an x^2 operand of the IGDN contraction, hence the
+    bf16-operand tolerance of the oracle comparisons rather than an fp32 one."""
+    L = ldic._lib
+    N, M = 192, 16
+    x = to_nhwc_bf16(bf(rnd((2, N, 20, 45), 21)))
+    w, b = rnd((N, M, 5, 5), 22, 0.02), rnd((M,), 23, 0.1)
+    bp, gp = gdn_params(M, 24)
+    layer = ldic.ops.ConvTC(L.LDIC_DECONV_GS_5x5_MERGED, w.cuda(), b.cuda(), act=L.ACT_IGDN, out_f32=True,
+                            gdn=(bp.cuda(), gp.cuda()) + rp.model_gdn_constants())
+    y_wide = layer(x).cpu()
+    monkeypatch.setenv("LDIC_TAIL_WIDE", "0")
+    y_taps = layer(x).cpu()
+    close(y_wide, y_taps, 2e-3, 5e-4)
 
 
 def test_deconv_hs_and_s1(ldic):

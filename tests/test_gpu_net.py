@@ -229,3 +229,31 @@ def test_two_stream_forward_is_bit_identical_to_single_stream(ldic):
         res.append((out["bits"].clone(), out["sq_err"].clone(), out["x_hat"].clone()))
     for r in res[1:]:
         assert torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1]) and torch.equal(r[2], res[0][2])
+
+
+def test_full_size_batch_properties(ldic):
+    """BASELINE configs[1] shape (768x512) through size-independent properties: images are independent units, so a
+    batch must give exactly the per-image squared errors of its images run alone (integer sums) and the sum of their
+    log-likelihood sums; a second run of the same batch is bit-identical (fixed summation order everywhere except the
+    exact integer atomics)."""
+    B, H, W = 4, 512, 768
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    x = dw.make_input(11, B, H, W).cuda()
+    out = net.rd_forward(x)
+    bits, sq = out["bits"].clone(), out["sq_err"].clone()
+    out2 = net.rd_forward(x)
+    assert torch.equal(out2["bits"], bits) and torch.equal(out2["sq_err"], sq)
+    single_bits = torch.zeros(3, dtype=torch.float64)
+    for i in range(B):
+        oi = net.rd_forward(x[i:i + 1].contiguous())
+        assert oi["sq_err"].item() == sq[i].item()
+        single_bits += oi["bits"].double().cpu()
+    assert torch.allclose(single_bits, bits.double().cpu(), rtol=2e-6, atol=0)
+    # symbols: the rounded latent the kernels used is torch.round of the latent they produced, bit for bit
+    y = out["latents"]["y"]
+    z = out["latents"]["z"]
+    _, _, yr = ldic.ops.latent_prep(y, want_round_bf16=False, want_abs_bf16=False, want_round_f32=True)
+    assert torch.equal(yr, torch.round(y)) and torch.isfinite(z).all()
+    bpp, v_mse, v_psnr = net.metrics(out, B, H, W)
+    assert v_mse.shape == (B,) and torch.isfinite(bpp) and torch.isfinite(v_psnr)
