@@ -319,6 +319,25 @@ def run_ours(args):
     lik_gbs = 20.0 * n_el / (lik_ms * 1e-3) / 1e9
     del v, mu, sg, vh, lk
 
+    # ---------------- window attention core against the HBM roofline: the 1/4-resolution block of
+    # BASELINE configs[3] (1152x1920 padded crops, 4 images per GPU): 288 x 480 tokens x 192 channels, 8x8 windows, shift 4
+    wa_B, wa_H, wa_W, wa_C, wa_heads, wa_ws = 4, 288, 480, 192, 8, 8
+    qkv = [torch.randn(wa_B, wa_H, wa_W, wa_C, device=dev).to(torch.bfloat16) for _ in range(3)]
+    wa_bias = torch.randn(wa_heads, wa_ws * wa_ws, wa_ws * wa_ws, device=dev) * 0.1
+    for _ in range(3):
+        ops.window_attention_core(qkv[0], qkv[1], qkv[2], wa_bias, wa_heads, wa_ws, 4)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        ops.window_attention_core(qkv[0], qkv[1], qkv[2], wa_bias, wa_heads, wa_ws, 4)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wa_ms = e0.elapsed_time(e1) / reps
+    wa_tokens = wa_B * wa_H * wa_W
+    wa_bytes = wa_tokens * wa_C * 2 * 4                      # q, k, v read + out written, bf16
+    wa_gbs = wa_bytes / (wa_ms * 1e-3) / 1e9
+    del qkv, wa_bias
+
     conv_traffic, lik_traffic = measured_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -355,6 +374,11 @@ def run_ours(args):
                                 "achieved": lik_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": lik_gbs / hbm_peak,
                                 "traffic": lik_traffic, "bytes_per_elem": 20, "elems": n_el, "ms": lik_ms,
                                 "peak_source": f"{peak_src} hbm_gbs", "workload": "C5-size 16x192x128x128, per-element mu/sigma"},
+        "roofline_window_attention": {"bound": "hbm", "kernel": "k_window_attention<32,64> (softmax(q k^T + bias + shift mask) v per 8x8 window)",
+                                      "achieved": wa_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": wa_gbs / hbm_peak,
+                                      "traffic": None, "bytes_per_token": wa_C * 2 * 4, "tokens": wa_tokens, "ms": wa_ms,
+                                      "peak_source": f"{peak_src} hbm_gbs",
+                                      "workload": "4 x 288x480 tokens x 192 ch (1/4 resolution of a 1152x1920 crop), 8 heads, window 8, shift 4"},
         "parity": {"bpp": float(bpp.item()), "psnr_db": float(psnr.item())},
     }
     if world == 1 and not args.no_cpu_baseline:

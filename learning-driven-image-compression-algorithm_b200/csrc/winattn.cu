@@ -9,10 +9,11 @@
 // tokens (:160-177) instead of being built on the host every call.
 //
 // Per CTA: the window's q | k | v rows (N tokens x 3*C bf16) are staged in shared memory with coalesced 16-byte
-// loads (row pitch padded by 16 B so that the 8 fragment rows hit different banks), V is transposed per head.
-// Per warp (= head): S = Q K^T with mma.sync.m16n8k16 (head_dim padded to a multiple of 16 with zeros), softmax on
-// the accumulator fragments (row max / sum across the 4 lanes of a quad), P (bf16) is re-used as the A fragment of
-// O = P V.  FLOPs are 14 % of the block; the kernel is bound by the 96 KB of qkv it streams per window.
+// loads (row pitch padded by 16 B so that the 8 fragment rows hit different banks).
+// Per warp (= head): S = Q K^T with mma.sync.m16n8k16 (head_dim padded to a multiple of 16 with zeros, K fragments
+// held in registers), softmax on the accumulator fragments (row max / sum across the 4 lanes of a quad), P (bf16) is
+// re-used as the A fragment of O = P V whose B operand is read from the row-major V rows with ldmatrix.trans.
+// FLOPs are 14 % of the block; the kernel streams 96 KB per window.
 #include "common.cuh"
 
 using namespace ldic;
@@ -35,14 +36,22 @@ struct WaParams {
   int B, H, W, C, heads, ws, shift;
 };
 
-// HD = head_dim padded to a multiple of 16 (24 -> 32, 16 -> 16); N = ws*ws tokens (64 or 16)
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(saddr));
+}
+
+// HD = head_dim padded to a multiple of 16 (24 -> 32, 16 -> 16); N = ws*ws tokens (64 or 16).
+// Shared memory: the window's q | k | v rows, [N][3C bf16 + 16 B] (the pad spreads the 8 rows of a fragment over the
+// banks).  Per warp = head: K fragments are loaded once (registers) and reused by every 16-row query tile; V is read
+// as the col-major B operand of O = P V straight from its row-major rows with ldmatrix.trans (no transposed copy);
+// the output of a query tile is written over that tile's own q columns of this head, and the whole [N][C] result
+// leaves with coalesced 16-byte stores.
 template <int HD, int N>
-__global__ void __launch_bounds__(256) k_window_attention(WaParams P) {
+__global__ void __launch_bounds__(256, 2) k_window_attention(WaParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int C = P.C, hd = C / P.heads;
-  const int pitch = 3 * C * 2 + 16;                      // bytes per token row (q | k | v), +16: bank spread
+  const int pitch = 3 * C * 2 + 16;                      // bytes per token row (q | k | v)
   uint8_t* s_qkv = smem;                                 // [N][pitch]
-  __nv_bfloat16* s_vt = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)N * pitch);   // [heads][HD][N + 8]
   __shared__ int s_pix[kWaMaxTokens];                    // token -> pixel index in the (B,H,W) image
   __shared__ int s_reg[kWaMaxTokens];                    // token -> region id of the shift mask
 
@@ -62,32 +71,45 @@ __global__ void __launch_bounds__(256) k_window_attention(WaParams P) {
     s_reg[threadIdx.x] = ry * 3 + rx;
   }
   __syncthreads();
-  // ---- stage q | k | v rows: 16-byte chunks, C/8 chunks per tensor and token ----
-  {
-    const int cpt = C / 8;
-    for (int i = threadIdx.x; i < N * 3 * cpt; i += blockDim.x) {
-      const int t = i / (3 * cpt), r = i - t * 3 * cpt, which = r / cpt, c8 = r - which * cpt;
-      const __nv_bfloat16* src = (which == 0 ? P.q : which == 1 ? P.k : P.v) + (long long)s_pix[t] * C + c8 * 8;
-      *reinterpret_cast<uint4*>(s_qkv + (size_t)t * pitch + (which * C + c8 * 8) * 2) = __ldg(reinterpret_cast<const uint4*>(src));
+  // ---- stage q | k | v rows with cp.async (16-byte chunks, a warp per token row): every copy of the window is in
+  // flight at once and nothing passes through registers.  (A flat loop with index divisions and a load -> store
+  // dependency per iteration spent 42 % of the kernel's samples on its shared-memory store.)
+  const int cpt = C / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_qkv);
+#pragma unroll
+  for (int t = warp; t < N; t += 8) {
+    const long long pix = s_pix[t];
+    const uint32_t drow = s_base + (uint32_t)(t * pitch);
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      const __nv_bfloat16* src = (which == 0 ? P.q : which == 1 ? P.k : P.v) + pix * C;
+      for (int c8 = lane; c8 < cpt; c8 += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(drow + (uint32_t)((which * C + c8 * 8) * 2)), "l"(src + c8 * 8)
+                     : "memory");
     }
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  constexpr int VP = N + 8;                              // pitch of the transposed V rows (elements)
   for (int h = warp; h < P.heads; h += blockDim.x / 32) {
-    // ---- V^T of this head: s_vt[h][d][token] (zeros for the padded dims) ----
-    __nv_bfloat16* vt = s_vt + (size_t)h * HD * VP;
-    for (int i = lane; i < HD * N; i += 32) {
-      const int d = i / N, tok = i - d * N;
-      vt[d * VP + tok] = d < hd ? *reinterpret_cast<const __nv_bfloat16*>(s_qkv + (size_t)tok * pitch + (2 * C + h * hd + d) * 2)
-                                : __float2bfloat16_rn(0.f);
+    // ---- K fragments of this head (B operand of S = Q K^T), zero beyond head_dim ----
+    uint32_t kf[N / 8][HD / 16][2];
+#pragma unroll
+    for (int nt = 0; nt < N / 8; ++nt) {
+      const uint8_t* krow = s_qkv + (size_t)(nt * 8 + g) * pitch + (C + h * hd) * 2;
+#pragma unroll
+      for (int kt = 0; kt < HD / 16; ++kt) {
+        const int c0 = kt * 16 + t4 * 2, c1 = c0 + 8;
+        kf[nt][kt][0] = c0 < hd ? *reinterpret_cast<const uint32_t*>(krow + c0 * 2) : 0u;
+        kf[nt][kt][1] = c1 < hd ? *reinterpret_cast<const uint32_t*>(krow + c1 * 2) : 0u;
+      }
     }
-    __syncwarp();
     const float* bias_h = P.bias + (size_t)h * N * N;
+    // ldmatrix.trans row addresses of V: lane l (0..15) -> token (l & 15) of a 16-token k-tile, this head's dims
+    const uint32_t v_lane = s_base + (uint32_t)((lane & 15) * pitch + (2 * C + h * hd) * 2);
 #pragma unroll 1
     for (int mt = 0; mt < N / 16; ++mt) {                // 16 query rows at a time
       const int r0 = mt * 16 + g, r1 = r0 + 8;
-      // A fragments of Q: k-tiles of 16 dims
       uint32_t qa[HD / 16][4];
 #pragma unroll
       for (int kt = 0; kt < HD / 16; ++kt) {
@@ -97,33 +119,31 @@ __global__ void __launch_bounds__(256) k_window_attention(WaParams P) {
           qa[kt][e] = col < hd ? *reinterpret_cast<const uint32_t*>(s_qkv + (size_t)row * pitch + (h * hd + col) * 2) : 0u;
         }
       }
-      // S = Q K^T : N/8 key tiles
       float s[N / 8][4];
 #pragma unroll
       for (int nt = 0; nt < N / 8; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const uint8_t* krow = s_qkv + (size_t)(nt * 8 + g) * pitch + (C + h * hd) * 2;
 #pragma unroll
-        for (int kt = 0; kt < HD / 16; ++kt) {
-          const int c0 = kt * 16 + t4 * 2, c1 = c0 + 8;
-          const uint32_t b0 = c0 < hd ? *reinterpret_cast<const uint32_t*>(krow + c0 * 2) : 0u;
-          const uint32_t b1 = c1 < hd ? *reinterpret_cast<const uint32_t*>(krow + c1 * 2) : 0u;
-          mma_bf16_16816(s[nt], qa[kt], b0, b1);
-        }
+        for (int kt = 0; kt < HD / 16; ++kt) mma_bf16_16816(s[nt], qa[kt], kf[nt][kt][0], kf[nt][kt][1]);
       }
       // + bias + mask, softmax over the N keys of rows r0 (elements 0,1) and r1 (elements 2,3)
       const int reg0 = s_reg[r0], reg1 = s_reg[r1];
       float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < N / 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = nt * 8 + t4 * 2 + (e & 1), row = (e & 2) ? r1 : r0;
-          float v = s[nt][e] + __ldg(bias_h + row * N + col);
-          if (P.shift > 0 && s_reg[col] != ((e & 2) ? reg1 : reg0)) v += -100.f;
-          s[nt][e] = v;
-          if (e & 2) m1 = fmaxf(m1, v); else m0 = fmaxf(m0, v);
+        const int col = nt * 8 + t4 * 2;
+        const float2 b0 = __ldg(reinterpret_cast<const float2*>(bias_h + r0 * N + col));
+        const float2 b1 = __ldg(reinterpret_cast<const float2*>(bias_h + r1 * N + col));
+        float v0 = s[nt][0] + b0.x, v1 = s[nt][1] + b0.y, v2 = s[nt][2] + b1.x, v3 = s[nt][3] + b1.y;
+        if (P.shift > 0) {
+          const int rc0 = s_reg[col], rc1 = s_reg[col + 1];
+          if (rc0 != reg0) v0 += -100.f;
+          if (rc1 != reg0) v1 += -100.f;
+          if (rc0 != reg1) v2 += -100.f;
+          if (rc1 != reg1) v3 += -100.f;
         }
+        s[nt][0] = v0; s[nt][1] = v1; s[nt][2] = v2; s[nt][3] = v3;
+        m0 = fmaxf(m0, fmaxf(v0, v1)); m1 = fmaxf(m1, fmaxf(v2, v3));
       }
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
       m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
@@ -139,7 +159,8 @@ __global__ void __launch_bounds__(256) k_window_attention(WaParams P) {
       }
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      // O = P V : the S accumulator fragments of key tiles (2kt, 2kt+1) are the A fragment of k-tile kt
+      // O = P V : the S accumulator fragments of key tiles (2kt, 2kt+1) are the A fragment of k-tile kt; the B
+      // fragment (V^T) comes from the row-major V rows through ldmatrix.trans.  Dim groups beyond head_dim are skipped.
       float o[HD / 8][4];
 #pragma unroll
       for (int dt = 0; dt < HD / 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
@@ -152,30 +173,41 @@ __global__ void __launch_bounds__(256) k_window_attention(WaParams P) {
         pa[3] = pack_bf16x2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
 #pragma unroll
         for (int dt = 0; dt < HD / 8; ++dt) {
-          const __nv_bfloat16* vr = vt + (size_t)(dt * 8 + g) * VP + kt * 16 + t4 * 2;
-          mma_bf16_16816(o[dt], pa, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+          if (dt * 8 < hd) {                             // warp-uniform
+            uint32_t vb0, vb1;
+            ldmatrix_x2_trans(vb0, vb1, v_lane + (uint32_t)(kt * 16 * pitch + dt * 16));
+            mma_bf16_16816(o[dt], pa, vb0, vb1);
+          }
         }
       }
-      // normalise and write rows r0, r1 of this head back to their pixels (window_reverse + reverse shift)
+      // normalise; rows r0, r1 of this head overwrite the tile's own q columns (no longer needed)
       const float i0 = 1.f / l0, i1 = 1.f / l1;
-      __nv_bfloat16* d0 = P.out + (long long)s_pix[r0] * C + h * hd;
-      __nv_bfloat16* d1 = P.out + (long long)s_pix[r1] * C + h * hd;
+      uint8_t* d0 = s_qkv + (size_t)r0 * pitch + (h * hd) * 2;
+      uint8_t* d1 = s_qkv + (size_t)r1 * pitch + (h * hd) * 2;
+      __syncwarp();                                      // every lane has read its q fragments of this tile
 #pragma unroll
       for (int dt = 0; dt < HD / 8; ++dt) {
         const int col = dt * 8 + t4 * 2;
         if (col < hd) {
-          *reinterpret_cast<uint32_t*>(d0 + col) = pack_bf16x2(o[dt][0] * i0, o[dt][1] * i0);
-          *reinterpret_cast<uint32_t*>(d1 + col) = pack_bf16x2(o[dt][2] * i1, o[dt][3] * i1);
+          *reinterpret_cast<uint32_t*>(d0 + col * 2) = pack_bf16x2(o[dt][0] * i0, o[dt][1] * i0);
+          *reinterpret_cast<uint32_t*>(d1 + col * 2) = pack_bf16x2(o[dt][2] * i1, o[dt][3] * i1);
         }
       }
     }
-    __syncwarp();
+  }
+  __syncthreads();
+  // ---- window_reverse + reverse shift: the [N][C] result back to its pixels, 16 bytes per thread and store ----
+#pragma unroll
+  for (int t = warp; t < N; t += 8) {
+    __nv_bfloat16* dst = P.out + (long long)s_pix[t] * C;
+    for (int c8 = lane; c8 < cpt; c8 += 32)
+      *reinterpret_cast<uint4*>(dst + c8 * 8) = *reinterpret_cast<const uint4*>(s_qkv + (size_t)t * pitch + c8 * 16);
   }
 }
 
 template <int HD, int N>
 int launch_wa(const WaParams& P, cudaStream_t st) {
-  const size_t smem = (size_t)N * (3 * P.C * 2 + 16) + (size_t)P.heads * HD * (N + 8) * 2;
+  const size_t smem = (size_t)N * (3 * P.C * 2 + 16);
   static bool attr_set = false;
   if (!attr_set) {
     LDIC_CUDA(cudaFuncSetAttribute(k_window_attention<HD, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
