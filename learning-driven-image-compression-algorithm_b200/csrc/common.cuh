@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 
 #include "../../include/ldic.h"
 
@@ -13,6 +14,7 @@ namespace ldic {
 
 extern thread_local char g_err[512];
 extern std::atomic<long long> g_launches;
+extern std::mutex g_init_mu;   // guards the lazily initialised per-kernel state (function attributes, occupancy, debug buffers)
 
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;

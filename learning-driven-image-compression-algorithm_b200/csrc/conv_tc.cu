@@ -2254,6 +2254,7 @@ template <int NP>
 int launch_conv(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
   const int stage_bytes = kATileBytes + NP * kBlockK * 2;
   const size_t smem = (size_t)P.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + (size_t)(P.nbias + 1) * NP * sizeof(float);
+  std::lock_guard<std::mutex> init_lock(g_init_mu);
   static bool attr_set = false;
   if (!attr_set) {
     LDIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -2268,6 +2269,7 @@ template <int NP>
 int launch_halo(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
   const size_t smem = (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * NP * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
                       (size_t)(P.nbias + 1) * NP * sizeof(float) + 64;
+  std::lock_guard<std::mutex> init_lock(g_init_mu);
   static bool attr_set = false;
   if (!attr_set) {
     LDIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -2285,6 +2287,7 @@ int launch_pair(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g
   const size_t smem = HALO ? (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * (NP / 2) * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
                                  (size_t)(P.nbias + 1) * NP * sizeof(float) + 64
                            : (size_t)P.stages * (kATileBytes + (NP / 2) * kBlockK * 2) + 1024 + 256 + (size_t)(P.nbias + 1) * NP * sizeof(float);
+  std::lock_guard<std::mutex> init_lock(g_init_mu);
   static bool attr_set = false;
   static int max_clusters = 0;
   if (smem > 227 * 1024) return fail(LDIC_EINVAL, "conv pair kernel: shared memory budget exceeded (%zu)", smem);
@@ -2359,6 +2362,7 @@ int launch_first(const CUtensorMap& x, const CUtensorMap& w, const CUtensorMap& 
   const size_t smem = (size_t)(2 + NP / 64) * NP * kBlockK * 2 + (size_t)P.stages * kATileBytes + 2 * kRawSlot + 256 +
                       2 * NP * sizeof(float) + 1024 /*align*/;
   if (smem > 227 * 1024) return fail(LDIC_EINVAL, "first conv: shared memory budget exceeded (%zu)", smem);
+  std::lock_guard<std::mutex> init_lock(g_init_mu);
   static bool attr_set = false;
   if (!attr_set) {
     LDIC_CUDA(cudaFuncSetAttribute(conv_first_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -2437,6 +2441,7 @@ int forward_first(const LdicConvDesc* d, const Layer& L, const void* x, const vo
 
 unsigned long long* g_timeout_host = nullptr;
 int ensure_timeout_report() {
+  std::lock_guard<std::mutex> init_lock(g_init_mu);
   static bool done = false;
   if (done) return LDIC_OK;
   unsigned long long* h = nullptr;

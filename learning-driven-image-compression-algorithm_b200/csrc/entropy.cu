@@ -7,6 +7,7 @@
 namespace ldic {
 thread_local char g_err[512] = {0};
 std::atomic<long long> g_launches{0};
+std::mutex g_init_mu;
 }  // namespace ldic
 
 using namespace ldic;

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(256, 2) k_window_attention(WaParams P) {
 template <int HD, int N>
 int launch_wa(const WaParams& P, cudaStream_t st) {
   const size_t smem = (size_t)N * (3 * P.C * 2 + 16);
+  std::lock_guard<std::mutex> init_lock(g_init_mu);
   static bool attr_set = false;
   if (!attr_set) {
     LDIC_CUDA(cudaFuncSetAttribute(k_window_attention<HD, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
