@@ -4,21 +4,25 @@
 //
 // One persistent CTA per SM, 384 threads:
 //   warps 0..7   epilogue       (TMEM -> registers -> global), 2 warps per TMEM lane quadrant
-//   warp 8       TMA producer   (A tiles; all lanes issue copies)
-//   warp 9       MMA issuer     (one lane) + TMEM allocator
-//   warp 10      halo kernel only: weight-tile producer
+//   warp 8       TMA producer   (activation tiles / regions; warp-uniform loop, one elected lane issues)
+//   warp 9       MMA issuer     (one elected lane) + TMEM allocator
+//   warp 10      weight / gamma tile producer (CTA-pair and halo kernels); first layer: patch builders (+ warp 11)
 // (setmaxnreg moves registers from warpgroup 2 to the two epilogue warpgroups)
+//
+// Kernels: conv_tc_kernel (1 CTA per tile, fallback), conv_tc2_kernel (CTA pairs, cta_group::2 -- the default;
+// W3 = wide-N form of the merged last deconv), conv_halo_kernel / conv_halo2_kernel (one activation region per
+// channel chunk serves all taps), conv_first_kernel (first analysis layer straight from the NCHW fp32 image).
 //
 // GEMM view: M = 128 output (or, for transposed convs, input-grid) pixels per tile,
 // N = Np accumulator columns (= output channels, or 4 sub-pixel phases x channels for the
 // merged small-Cout deconv), K = taps x Cin_pad walked in 64-channel blocks.
 // A tile  : 128 pixels x 64 channels bf16, gathered by TMA from the NHWC activation
 //           (zero fill outside the image = the reference's ZeroPad2d / conv padding);
-//           stride-2 convs address the input through an (x-parity, x/2) split view.
+//           stride-2 convs use one box with element strides (1,2,2,1).
 // B tile  : Np x 64 slice of the packed weights [tap][Np][Cin_pad].
 // GDN     : acc(+bias) -> x (registers) ; x^2 -> bf16 -> smem A-slot of the SAME pipeline
 //           ring whose B-slot receives a 64-wide K block of gamma; norm = x^2 . gamma^T is
-//           accumulated in a second TMEM region; out = x * rsqrt|sqrt(norm + beta).
+//           accumulated in place over the tile's accumulator; out = x * rsqrt|sqrt(norm + beta).
 //
 // Reference semantics: model/net.py:96-114 (g_a), :126-144 (g_s), :188-216 (h_a/h_s),
 // model/gdn.py:69-92,134-156 (GDN/IGDN).
