@@ -31,16 +31,34 @@ __global__ void k_pack_small(PackArgs a) {
 // y[b][oy][ox][co] = relu(bias[co] + sum_{ky,kx,ci} w[co][ci][ky][kx] * x[b][2oy+ky-1][2ox+kx-1][ci])
 // (Conv2d(k3, s2, p1), zero padding).  x pixels are `xs` floats apart (a channel slice of a wider tensor).
 // Lane = output pixel; the (tap, 32-channel chunk) pairs of the reduction are dealt round-robin to the 8
-// warps of the CTA, so there is no staging and no barrier inside the reduction: every lane reads its own
-// pixel's 32 channels (one 128-byte line, 8 float4) and the whole warp reads the same packed weight row
-// (broadcast).  The eight partial sums are added in a fixed order at the end.
+// warps of the CTA, so there is no barrier inside the reduction: every lane reads its own pixel's 32 channels
+// (one 128-byte line) with 256-bit loads -- whole 32-byte sectors per request; with 128-bit loads every sector
+// crossed the L2 -> L1 path twice (124 MB for the 19 MB input of PredictionModel_Syntax.down0).  The packed weights
+// of the whole layer (9 x Cin x COUT floats, 9 .. 110 KB) are brought into shared memory once per CTA with cp.async
+// and read from there as broadcasts: fetched from global memory inside the reduction every weight row was a first
+// touch on its SM and the kernels ran at L2 latency (ncu: 12-18 long-scoreboard stall cycles per issued instruction,
+// 48 us for the 56 MFLOP of Syntax_Model.down1).  The eight partial sums are added in a fixed order at the end.
+__device__ __forceinline__ void ldg_v8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+
 template <int COUT>
 __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float* __restrict__ x, long long xs,
                                                                      const float* __restrict__ wp,
                                                                      const float* __restrict__ bias, float* __restrict__ y,
                                                                      int B, int H, int W, int Ho, int Wo, int Cin) {
+  extern __shared__ __align__(16) float s_w[];                         // [9][Cin][COUT]
   __shared__ float s_red[kScGroups / 2][kScPix][COUT + 1];
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  {
+    const int n16 = 9 * Cin * COUT / 4;                                // 16-byte chunks
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_w);
+    for (int i = threadIdx.x; i < n16; i += kScThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(wp + (size_t)i * 4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   const long long npix = (long long)B * Ho * Wo;
   const long long p = (long long)blockIdx.x * kScPix + lane;
   const bool live = p < npix;
@@ -51,33 +69,36 @@ __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float
   for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
   const int ck = Cin < kScChunk ? Cin : kScChunk;          // channels per chunk (16 or 32)
   const int nchunk = Cin / ck, npairs = 9 * nchunk;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
 #pragma unroll 1
   for (int q = g; q < npairs; q += kScGroups) {
     const int tap = q / nchunk, c0 = (q - tap * nchunk) * ck;
     const int ky = tap / 3, kx = tap - ky * 3;
     const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
     const bool in = live && iy >= 0 && iy < H && ix >= 0 && ix < W;
-    // One float4 of the pixel's channels at a time, the next one already in flight.  The loop is deliberately NOT
-    // unrolled over the 32 channels: straight-line code of 32 x (COUT/4 loads + COUT FMAs) is ~40 KB for COUT = 64 and
-    // runs once or twice per warp, i.e. at instruction-fetch speed (sm_down1 took 55 us for 56 MFLOP).
-    const float4* xp = reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * xs + c0);
-    const float4* wr = reinterpret_cast<const float4*>(wp + ((size_t)tap * Cin + c0) * COUT);
-    const int n4 = ck / 4;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 vn = in ? __ldg(xp) : zero4;
-#pragma unroll 1
-    for (int j4 = 0; j4 < n4; ++j4) {
-      const float4 v = vn;
-      if (j4 + 1 < n4) vn = in ? __ldg(xp + j4 + 1) : zero4;
-      const float x4[4] = {v.x, v.y, v.z, v.w};
+    const float* xp = x + (((long long)b * H + iy) * W + ix) * xs + c0;
+    float xv[kScChunk / 8][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4* wj = wr + (j4 * 4 + u) * (COUT / 4);
+    for (int j8 = 0; j8 < kScChunk / 8; ++j8) {
+      if (in && 8 * j8 < ck) {
+        ldg_v8(xp + 8 * j8, xv[j8]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[j8][e] = 0.f;
+      }
+    }
+    const float4* wr = reinterpret_cast<const float4*>(s_w + ((size_t)tap * Cin + c0) * COUT);
+#pragma unroll
+    for (int j = 0; j < kScChunk; ++j) {
+      if (j < ck) {                                          // warp-uniform
+        const float4* wj = wr + j * (COUT / 4);
+        const float xu = xv[j >> 3][j & 7];
 #pragma unroll
         for (int c4 = 0; c4 < COUT / 4; ++c4) {
-          const float4 w4 = __ldg(wj + c4);
-          acc[4 * c4] = fmaf(x4[u], w4.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(x4[u], w4.y, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(x4[u], w4.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(x4[u], w4.w, acc[4 * c4 + 3]);
+          const float4 w4 = wj[c4];
+          acc[4 * c4] = fmaf(xu, w4.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(xu, w4.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(xu, w4.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(xu, w4.w, acc[4 * c4 + 3]);
         }
       }
     }
@@ -115,13 +136,23 @@ __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float
 template <int COUT>
 int launch_small_conv(const float* x, long long xs, const float* wp, const float* bias, float* y, int B, int H, int W,
                       int Cin, cudaStream_t st) {
-  if (Cin % 16 || xs % 4 || (((uintptr_t)x) & 15) || (((uintptr_t)wp) & 15) || (((uintptr_t)y) & 15))
-    return fail(LDIC_EINVAL, "syntax branch: small conv needs Cin %% 16 == 0, pixel stride %% 4 == 0 and 16-byte aligned buffers");
+  if (Cin % 16 || xs % 8 || (((uintptr_t)x) & 31) || (((uintptr_t)wp) & 15) || (((uintptr_t)y) & 15))
+    return fail(LDIC_EINVAL, "syntax branch: small conv needs Cin %% 16 == 0, pixel stride %% 8 == 0, a 32-byte aligned input and 16-byte aligned weights / output");
   if (Cin > kScChunk && Cin % kScChunk) return fail(LDIC_EINVAL, "syntax branch: small conv needs Cin <= 32 or a multiple of 32");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long npix = (long long)B * Ho * Wo;
   const unsigned grid = (unsigned)((npix + kScPix - 1) / kScPix);
-  k_small_conv3x3s2_relu<COUT><<<grid, kScThreads, 0, st>>>(x, xs, wp, bias, y, B, H, W, Ho, Wo, Cin);
+  const size_t smem = (size_t)9 * Cin * COUT * sizeof(float);
+  if (smem > 160 * 1024) return fail(LDIC_EINVAL, "syntax branch: 3x3 weights of %d x %d channels do not fit in shared memory", Cin, COUT);
+  {
+    std::lock_guard<std::mutex> init_lock(g_init_mu);
+    static bool attr_set = false;
+    if (!attr_set) {
+      LDIC_CUDA(cudaFuncSetAttribute(k_small_conv3x3s2_relu<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+  }
+  k_small_conv3x3s2_relu<COUT><<<grid, kScThreads, smem, st>>>(x, xs, wp, bias, y, B, H, W, Ho, Wo, Cin);
   return check_launch("k_small_conv3x3s2_relu");
 }
 
