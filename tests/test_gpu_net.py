@@ -257,3 +257,21 @@ def test_full_size_batch_properties(ldic):
     assert torch.equal(yr, torch.round(y)) and torch.isfinite(z).all()
     bpp, v_mse, v_psnr = net.metrics(out, B, H, W)
     assert v_mse.shape == (B,) and torch.isfinite(bpp) and torch.isfinite(v_psnr)
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 64, 128), (5, 128, 64), (1, 192, 320), (7, 64, 64)])
+def test_batch_independence_odd_shapes(ldic, B, H, W):
+    """Odd batch sizes / tile counts (the CTA-pair kernels pad the last pair, the wide tail overlaps tiles in x):
+    every image of a batch gives exactly the squared error it gives alone, and the batch's log-likelihood sums are the
+    sums over its images."""
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    x = dw.make_input(5, B, H, W).cuda()
+    out = net.rd_forward(x)
+    bits, sq = out["bits"].double().cpu(), out["sq_err"].cpu()
+    acc = torch.zeros(3, dtype=torch.float64)
+    for i in range(B):
+        oi = net.rd_forward(x[i:i + 1].contiguous())
+        assert oi["sq_err"].item() == sq[i].item(), (i, oi["sq_err"].item(), sq[i].item())
+        acc += oi["bits"].double().cpu()
+    assert torch.allclose(acc, bits, rtol=5e-6, atol=0), (acc, bits)
