@@ -53,6 +53,9 @@ constexpr int kMaxTaps = 112;
 constexpr int kMaxJobs = 16;
 constexpr int kTmemCols = 512;
 constexpr int kBufCols = 256;           // two TMEM accumulator buffers at columns 0 and 256
+#ifndef LDIC_PAIR_STORE
+#define LDIC_PAIR_STORE 1                 // build switch: lane-pair transposed epilogue stores (0 = one 32-byte chunk per lane)
+#endif
 constexpr int kGdnInsertDefault = 4;     // conv stages of the next tile issued before the previous tile's GDN stages
 
 // one filter tap = one spatial offset of the gather + a K range: nkc 64-wide blocks starting at
@@ -533,6 +536,32 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
           }
         }
       };
+      // bf16 output, 32-column chunks: the two lanes of a pair swap half a chunk so that every store instruction
+      // writes 64 contiguous bytes per pixel with two lanes (16 distinct 128-byte lines per warp instruction instead
+      // of 32 -- the LSU cost of these stores is per line, LDIC_DEBUG_NOSTORE: 2.7 k of deconv 3's 11 k cycles per tile)
+      const bool pair_store = (LDW == 32) && !P.out_f32 && P.ngroups == 1 && (LDIC_PAIR_STORE != 0);
+      long long pb_other = 0;
+      bool valid_other = false;
+      if (pair_store) {
+        pb_other = __shfl_xor_sync(0xffffffffu, pix_base, 1);
+        valid_other = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+      }
+      auto store_cols_paired = [&](int c) {          // all lanes call it (shuffles); stores are predicated
+        uint32_t pk[16], rv[8];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(xr[c + 2 * e], xr[c + 2 * e + 1]);
+        const bool odd = lane & 1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rv[e] = __shfl_xor_sync(0xffffffffu, odd ? pk[e] : pk[8 + e], 1);
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out) + col0 + c + (odd ? 16 : 0);
+        // even lane's pixel: even lane writes its columns [c, c+16), odd lane the even lane's [c+16, c+32)
+        uint32_t d1[8], d2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { d1[e] = odd ? rv[e] : pk[e]; d2[e] = odd ? pk[8 + e] : rv[e]; }
+        if (odd ? valid_other : valid) st_global_v8(out + (odd ? pb_other : pix_base), d1);
+        // odd lane's pixel: even lane writes the odd lane's [c, c+16), odd lane its own [c+16, c+32)
+        if (odd ? valid : valid_other) st_global_v8(out + (odd ? pix_base : pb_other), d2);
+      };
       if (gk) {
         // x^2 -> bf16 -> A slots (K-major, 128B swizzle: 16-byte chunk index XOR (row & 7))
         if (edbg) { e_t0 = clock64(); e_p1 += e_t0 - e_t1; }
@@ -592,7 +621,8 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
             const float rs = rsqrt_approx(nrm);
             xr[c + k] *= igdn ? nrm * rs : rs;
           }
-          if (P.ngroups == 1 && valid) store_cols(c, LDW);
+          if (pair_store) store_cols_paired(c);
+          else if (P.ngroups == 1 && valid) store_cols(c, LDW);
         }
         stored = (P.ngroups == 1);
       } else if (P.act == LDIC_ACT_RELU) {
