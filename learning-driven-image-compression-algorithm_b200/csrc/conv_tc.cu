@@ -80,8 +80,6 @@ struct ConvParams {
   int G;                    // halo: filter taps per B-ring slot (one TMA box of G*Np weight rows)
   int gdn_insert;           // streaming kernels: conv stages of tile it+1 issued before the GDN stages of tile it
   int super_per_job;        // CTA-pair kernel: (tiles_per_job + 1) / 2 pairs of adjacent tiles per job
-  int interleave;           // CTA-pair streaming kernel: a pair walks the njobs jobs (sub-pixel phases) of ONE spatial super
-                            // tile before it moves to its next one, instead of job-major order (see pair_item)
   int ngroups, Cg;          // accumulator columns = ngroups x Cg
   int sy, sx;               // output pixel = grid pixel * (sy,sx) + job offset (+ sub-pixel group offset)
   int nbias;                // 1, or njobs when every job has its own bias vector
@@ -384,21 +382,6 @@ __device__ __forceinline__ TileCoord decode_tile2(const ConvParams& P, int s, in
   if (t >= P.tiles_per_job) { TileCoord c; c.job = job; c.n0 = P.B; c.y0 = 0; c.x0 = 0; return c; }
   return decode_tile(P, job * P.tiles_per_job + t);
 }
-// Work list of pair `pi` (of `npairs`).  Job-major (default): super tiles pi, pi + npairs, ... of the job-major list.
-// Interleaved (transposed convs): item it = (spatial super tile m * npairs + pi, job (it % njobs + pi) % njobs), so the
-// sub-pixel phases with few taps (epilogue bound) and with many taps (MMA bound) alternate on every pair and the two
-// TMEM buffers average them out; job-major order ran whole phases epilogue bound and then a whole phase MMA bound.
-__device__ __forceinline__ int pair_nt(const ConvParams& P, int pi, int npairs) {
-  if (!P.interleave) return (P.super_per_job * P.njobs - pi + npairs - 1) / npairs;
-  return pi < P.super_per_job ? P.njobs * ((P.super_per_job - pi + npairs - 1) / npairs) : 0;
-}
-__device__ __forceinline__ int pair_item(const ConvParams& P, int pi, int npairs, int it) {    // -> job-major super tile index
-  if (!P.interleave) return pi + it * npairs;
-  const int m = it / P.njobs, r = it - m * P.njobs;
-  int job = r + pi % P.njobs;
-  if (job >= P.njobs) job -= P.njobs;
-  return job * P.super_per_job + m * npairs + pi;
-}
 
 // ---------------------------------------------------------------------------------
 // Epilogue role (shared by the streaming and the halo kernels): warps 4..11.
@@ -467,7 +450,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
     // tile coordinates are decoded two tiles ahead, in the shadow of the wait for the gamma contraction (five integer
     // divisions: 6 % of the epilogue warps' samples when done at the top of the loop)
     auto decode_it = [&](int i) {
-      return CL ? decode_tile2(P, pair_item(P, R.t_first, R.t_stride, i), R.rank) : decode_tile(P, blockIdx.x + i * gridDim.x);
+      return CL ? decode_tile2(P, R.t_first + i * R.t_stride, R.rank) : decode_tile(P, blockIdx.x + i * gridDim.x);
     };
     TileCoord tc = decode_it(0), tc_n1 = decode_it(1), tc_n2 = tc_n1;
     for (int it = 0; it < ntiles_cta; ++it, tc = tc_n1, tc_n1 = tc_n2) {
@@ -718,7 +701,7 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
   const long long e_begin = edbg ? clock64() : 0;
   float wreg[48];                        // the current image's batch_conv filter (3 x 16), reloaded when the image changes
   int w_n = -1;
-  auto decode_it = [&](int i) { return decode_tile2(P, pair_item(P, R.t_first, R.t_stride, i), R.rank); };
+  auto decode_it = [&](int i) { return decode_tile2(P, R.t_first + i * R.t_stride, R.rank); };
   TileCoord tc = decode_it(0), tc_n1 = decode_it(1), tc_n2 = tc_n1;
   for (int it = 0; it < ntiles_cta; ++it, tc = tc_n1, tc_n1 = tc_n2) {
     const Job jb = P.jobs[tc.job];
@@ -1125,7 +1108,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int gk = gdn ? P.gdn_kblocks : 0;
   const int npairs = (int)gridDim.x >> 1, pi = (int)blockIdx.x >> 1;
-  const int nt = pair_nt(P, pi, npairs);                               // super tiles of this pair
+  const int total_super = P.super_per_job * P.njobs;
+  const int nt = (total_super - pi + npairs - 1) / npairs;             // super tiles of this pair
   const uint32_t full_L = mapa_shared(smem_u32(full_bar), 0);
 
   if (warp >= kEpiWarps) {
@@ -1163,7 +1147,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int cur_job = -1, ntaps = 0, tap_begin = 0, nkb = 0;
         uint32_t my_w0 = 0, my_w1 = 0;                          // lane t: tap t of the current job, packed
         for (int it = 0; it < nt; ++it) {
-          const TileCoord tc = decode_tile2(P, pair_item(P, pi, npairs, it), (int)rank);
+          const TileCoord tc = decode_tile2(P, pi + it * npairs, (int)rank);
           if (tc.job != cur_job) {
             cur_job = tc.job;
             ntaps = P.jobs[cur_job].ntaps; tap_begin = P.jobs[cur_job].tap_begin; nkb = P.jobs[cur_job].nkb;
@@ -1241,7 +1225,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       };
       int cur_job = -1, nkb = 0;
       for (int it = 0; it < nt; ++it) {
-        const int job = pair_item(P, pi, npairs, it) / P.super_per_job;
+        const int job = (pi + it * npairs) / P.super_per_job;
         if (job != cur_job) { cur_job = job; nkb = P.jobs[cur_job].nkb; }
         const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
         const int bsel = it & 1;
@@ -2754,14 +2738,6 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
     P.stages = st2;
     if (gdn && st2 < P.gdn_kblocks + 1) pair_stream = false;
     else pair = true;                          // weight / gamma maps load half of the rows per CTA
-    // sub-pixel phases interleaved per spatial tile (pair_item): only when the coarser work items (njobs tiles at a
-    // time) do not raise the busiest pair's tile count (deconv 3: 21 x 4 = 84 either way, -2 %; deconv 2: 24 vs 21, +13 %)
-    {
-      const int np = kNumSMs / 2;
-      const int items_jm = (P.super_per_job * L.njobs + np - 1) / np, items_il = L.njobs * ((P.super_per_job + np - 1) / np);
-      P.interleave = (pair && L.transposed && L.njobs == 4 && gdn && !wide3 && items_il <= items_jm) ? 1 : 0;
-    }
-    if (const char* e = getenv("LDIC_INTERLEAVE")) P.interleave = P.interleave && atoi(e) != 0;   // tuning aid
   }
   CUtensorMap tmA, tmW, tmG;
   const cuuint64_t C = (cuuint64_t)L.vC;
