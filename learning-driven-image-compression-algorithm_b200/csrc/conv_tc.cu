@@ -399,6 +399,7 @@ struct EpiRing {
   // the leader CTA and are reached through their shared::cluster addresses
   int t_first, t_stride, rank;
   uint32_t buf_free_cl, x2_ready_cl;
+  int pair_store;           // lane-pair transposed bf16 stores (off for the first layer: measured 6 % slower there)
 };
 
 // Fused tail on the CPT accumulator columns of one thread (CPT / CG output pixels of CG channels each); every index
@@ -522,7 +523,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       // bf16 output, 32-column chunks: the two lanes of a pair swap half a chunk so that every store instruction
       // writes 64 contiguous bytes per pixel with two lanes (16 distinct 128-byte lines per warp instruction instead
       // of 32 -- the LSU cost of these stores is per line, LDIC_DEBUG_NOSTORE: 2.7 k of deconv 3's 11 k cycles per tile)
-      const bool pair_store = (LDW == 32) && !P.out_f32 && P.ngroups == 1 && (LDIC_PAIR_STORE != 0);
+      const bool pair_store = (LDW == 32) && !P.out_f32 && P.ngroups == 1 && (LDIC_PAIR_STORE != 0) && R.pair_store;
       long long pb_other = 0;
       bool valid_other = false;
       if (pair_store) {
@@ -1029,6 +1030,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue warps =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
+    R.pair_store = 1;
     R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
     R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
@@ -1251,6 +1253,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== epilogue warps (both CTAs, own tile) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
+    R.pair_store = 1;
     R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
     R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
@@ -1512,6 +1515,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== epilogue warps =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
+    R.pair_store = 1;
     R.ring_base = smem_base; R.slot_bytes = a_slot; R.nslots = (uint32_t)SA; R.empty_bar = aempty;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
     R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 1; R.insert_after = kHaloInsert;
@@ -1774,6 +1778,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== epilogue warps (both CTAs, own tile) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
+    R.pair_store = 1;
     R.ring_base = smem_base; R.slot_bytes = a_slot; R.nslots = (uint32_t)SA; R.empty_bar = aempty;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
     R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 1; R.insert_after = kHaloInsert;
@@ -1999,6 +2004,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ===================== epilogue warps =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
+    R.pair_store = 0;
     R.ring_base = ring_base; R.slot_bytes = kATileBytes; R.nslots = (uint32_t)S; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
     R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
