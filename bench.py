@@ -89,17 +89,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_images_per_s(n_steps: int, n_warm: int, batch: int = 1):
+def make_u8_batches(rank: int, B: int, nbuf: int):
+    """Synthetic 8-bit imagery (what the reference's eval driver reads from PNG files): `nbuf` distinct batches of B
+    images, uint8 levels (B,3,H,W)."""
+    import torch
+    import det_weights as dw
+    base = dw.make_input(rank, 4, H, W)
+    out = []
+    for i in range(nbuf):     # distinct batches: images rolled so no two buffers are equal
+        xb = torch.cat([torch.roll(base, shifts=(i * 37 + j * 11), dims=3) for j in range((B + 3) // 4)], 0)[:B]
+        out.append(torch.round((xb + 1.0) * 127.5).clamp_(0, 255).to(torch.uint8).contiguous())
+    return out
+
+
+def cpu_port_images_per_s(n_steps: int, n_warm: int, batch: int = 1, high: bool = False):
     """The reference's CPU path (torch-CPU port, one-hot sampler convs as written), all host cores."""
     import torch
     import det_weights as dw
     from oracle import ref_path as rp
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = dw.make_state_dict(0)
-    x = dw.make_input(0, batch, H, W)
-    flt_y = rp.block_sample_filter(176, True)
-    flt_h = rp.block_sample_filter(192, False)
+    N, M = (384, 32) if high else (192, 16)
+    sd = dw.make_state_dict(0, N=N, M=M)
+    x = (make_u8_batches(0, batch, 1)[0].float() / 255.0) * 2.0 - 1.0          # ToTensor + eval_net.py:84
+    flt_y = rp.block_sample_filter(N - M, True)
+    flt_h = rp.block_sample_filter(N, False)
     orig = rp.block_sample_onehot
 
     def cached(xx, masked, flt=None):
@@ -108,10 +122,10 @@ def cpu_port_images_per_s(n_steps: int, n_warm: int, batch: int = 1):
     try:
         with torch.no_grad():
             for _ in range(n_warm):
-                rp.net_forward_test(sd, x, (batch, H, W, 3), faithful_sampler=True, return_intermediates=False)
+                rp.net_forward_test(sd, x, (batch, H, W, 3), M=M, faithful_sampler=True, return_intermediates=False)
             t0 = time.perf_counter()
             for _ in range(n_steps):
-                rp.net_forward_test(sd, x, (batch, H, W, 3), faithful_sampler=True, return_intermediates=False)
+                rp.net_forward_test(sd, x, (batch, H, W, 3), M=M, faithful_sampler=True, return_intermediates=False)
             dt = time.perf_counter() - t0
     finally:
         rp.block_sample_onehot = orig
@@ -122,12 +136,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ips, spi, cores = cpu_port_images_per_s(args.steps, args.warmup, batch=1)
+    high = args.config == "high"
+    ips, spi, cores = cpu_port_images_per_s(args.steps, args.warmup, batch=1, high=high)
     sample = f"1 image 768x512 per step, {args.steps} steps after {args.warmup} warm-up, torch CPU fp32, {cores} threads"
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": spi * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "model/net.py Net.forward(test) N=192 M=16, 768x512, CPU port of the reference path "
+            "config": {"workload": f"model/net.py Net.forward(test) {'N=384 M=32' if high else 'N=192 M=16'}, 768x512, CPU port of the reference path "
                                    "(oracle/ref_path.py, one-hot BlockSample convs as written), 1 image per step"},
             "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -158,17 +173,20 @@ def run_ours(args):
     B = args.batch
     hbm_peak, tc_peak_sus, tc_peak_burst, peak_src = peaks()
 
-    net = ldic_b200.Net((B, H, W, 3), (B, H, W, 3), False, False).to(dev).eval()
-    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    high = args.config == "high"
+    Nw, Mw = (384, 32) if high else (192, 16)
+    net = ldic_b200.Net((B, H, W, 3), (B, H, W, 3), high, False).to(dev).eval()
+    net.load_state_dict(dw.make_state_dict(0, N=Nw, M=Mw), strict=True)
+    net.side_sms = args.side_sms
+    net.auto_graph = not args.no_graph
     ev = ShardedEvaluator(net)
     NBUF = 4
-    base = dw.make_input(rank, 4, H, W)
-    host = []
-    for i in range(NBUF):     # distinct batches: images rolled / flipped so no two buffers are equal
-        xb = torch.cat([torch.roll(base, shifts=(i * 37 + j * 11), dims=3) for j in range(B // 4)], 0)[:B]
-        host.append(xb.contiguous().pin_memory())
+    # 8-bit imagery: the host buffers hold uint8 levels; the first layer applies x = (u/255)*2-1 (eval_net.py:84) itself
+    host = [h.pin_memory() for h in make_u8_batches(rank, B, NBUF)]
+    if args.input == "f32":
+        host = [((h.float() / 255.0) * 2.0 - 1.0).contiguous().pin_memory() for h in host]
     devbuf = [h.to(dev) for h in host]
-    in_bytes = host[0].numel() * 4
+    in_bytes = host[0].numel() * host[0].element_size()
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -208,8 +226,8 @@ def run_ours(args):
 
     # per-launch CUDA events around every conv launch: the same K steps issued eagerly (events cannot be read back
     # from inside a graph replay); the kernels and their durations are the ones of the timed region
-    # (single stream: with g_s overlapped on the side stream the per-launch times would include SM contention)
-    overlap_was, net.overlap_streams = net.overlap_streams, False
+    # (single stream: with the SM partition the per-launch times would include the concurrent kernels)
+    side_was, net.side_sms = net.side_sms, 0
     ops.PROFILE = []
     sync_all()
     e0.record()
@@ -218,10 +236,46 @@ def run_ours(args):
     e1.record()
     sync_all()
     prof, ops.PROFILE = ops.PROFILE, None
-    net.overlap_streams = overlap_was
+    net.side_sms = side_was
+    profiled_eager_ms = e0.elapsed_time(e1)
+    # the nn.Module surface as a user calls it: net(x, 'test') (transparent graph replay unless --no-graph)
+    for i in range(3):
+        net(devbuf[i % NBUF], "test", 1)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        r_mod = net(devbuf[i % NBUF], "test", 1)
+    e1.record()
+    sync_all()
     eager_ms = e0.elapsed_time(e1)
 
     # conv kernel roofline from the events recorded around every conv_tc launch of the timed region
+    # ---------------- multi-GPU correctness on hardware: the all-reduced (bpp, PSNR) of one step equals
+    # the single-GPU result on the same global batch, recomputed serially by rank 0 outside the timed region
+    multi_gpu_equal = None
+    if world > 1:
+        kb = 1 % NBUF
+        bpp_d, psnr_d, _ = step(kb)
+        dist_res = (float(bpp_d.item()), float(psnr_d.item()))
+        sync_all()
+        if rank == 0:
+            packed = torch.zeros(5, dtype=torch.float64, device=dev)
+            for r in range(world):
+                xr = make_u8_batches(r, B, NBUF)[kb]
+                if args.input == "f32":
+                    xr = ((xr.float() / 255.0) * 2.0 - 1.0).contiguous()
+                o = net.rd_forward(xr.to(dev))
+                packed += ops.rd_pack_metrics(o["bits"], o["sq_err"], 3 * H * W, want_v_mse=False)[0]
+            single = ops.rd_finish_metrics(packed, float(H * W)).cpu()
+            err = (abs(dist_res[0] / float(single[0]) - 1.0), abs(dist_res[1] - float(single[1])))
+            multi_gpu_equal = {"equal": bool(err[0] < 1e-6 and err[1] < 1e-5), "bpp_rel_err": err[0], "psnr_abs_err_db": err[1],
+                               "bpp_all_reduced": dist_res[0], "bpp_single_gpu": float(single[0]),
+                               "psnr_all_reduced": dist_res[1], "psnr_single_gpu": float(single[1]),
+                               "global_batch": world * B}
+            if not multi_gpu_equal["equal"]:
+                raise SystemExit(f"multi-GPU result differs from the single-GPU result on the same global batch: {multi_gpu_equal}")
+        sync_all()
+
     conv_ms = sum(a.elapsed_time(b) for (_, _, a, b) in prof)
     conv_flops = sum(layer.flops(*shp) for (layer, shp, _, _) in prof)
     per_layer = {}
@@ -235,8 +289,6 @@ def run_ours(args):
     # Every step: H2D copy of that step's batch from pinned host memory (copy stream, double buffered so it
     # overlaps the previous step's kernels), the forward, and a D2H read of the step's result (bpp, PSNR,
     # per-image MSE) into pinned memory, consumed on the host one step later.
-    for i in range(2):
-        r = net(host[i % NBUF].to(dev, non_blocking=True), "test", 1)     # the public module call, eager
     sync_all()
     d2h_bytes = 4 + 4 + 4 * B
     main = torch.cuda.current_stream(dev)
@@ -343,8 +395,11 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"model/net.py Net.forward(test) N=192 M=16 on batch {B} synthetic 768x512 per GPU "
-                               "(BASELINE configs[1])", "global_batch": world * B, "height": H, "width": W,
+        "config": {"workload": f"model/net.py Net.forward(test) N={Nw} M={Mw} on batch {B} synthetic 768x512 per GPU "
+                               + ("(BASELINE configs[1])" if not high else "(the reference's --high width, model/net.py:446-451)"),
+                   "global_batch": world * B, "height": H, "width": W,
+                   "input": ("uint8 levels (8-bit imagery as eval_net.py reads it); x = (u/255)*2-1 applied inside the first layer"
+                             if args.input == "u8" else "fp32 in [-1,1]"),
                    "weights": "random init (tests/det_weights.py seed 0, gain-boosted)",
                    "l2": f"{NBUF} rotating input batches ({NBUF * in_bytes >> 20} MiB) and ~3 GB of activations per step, both > 126 MB L2",
                    "context_model": "PredictionModel_Context on conv_tc_kernel (TMA patch gather, SURVEY 8 f1); syntax branch on ldic_syntax_branch (fp32 CUDA-core kernels)",
@@ -356,8 +411,11 @@ def run_ours(args):
                         f"({gev.launches_per_replay} launches of libldic_b200), + 1 metric kernel per step" if use_graph
                         else "eager launches"),
         "eager_ms_per_step": eager_ms / args.steps,
-        "streams": ("g_s (3 deconv + fused tail) on a second stream next to the hyperprior / syntax / context chain"
-                    if net.overlap_streams else "single stream"),
+        "eager_note": "net(x, 'test') on device-resident inputs: the nn.Module call a user makes"
+                      + (" (transparent CUDA-graph replay per input shape)" if net.auto_graph else " (every kernel launched from Python)"),
+        "profiled_eager_ms_per_step": profiled_eager_ms / args.steps,
+        "streams": (f"SM partition: hyperprior / syntax chain on a side stream on {net.side_sms} SMs next to g_s deconv 1-3"
+                    if net.side_sms else "single stream"),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_first / conv_tc / conv_halo kernels (g_a, g_s, h_a, h_s, context convs + fused GDN/IGDN)",
                      "achieved": achieved_tf, "peak": tc_peak_sus, "unit": "TFLOP/s",
@@ -366,7 +424,7 @@ def run_ours(args):
                      "peak_source": f"{peak_src} bf16_tflops_sustained",
                      "algorithmic_gflop_per_image": conv_flops / 1e9 / (B * args.steps),
                      "conv_ms_per_step": conv_ms / args.steps,
-                     "share_of_step": conv_ms / eager_ms if eager_ms else None,
+                     "share_of_step": conv_ms / profiled_eager_ms if profiled_eager_ms else None,
                      "share_note": "conv launch time / step time of the eager per-launch-event pass",
                      "per_layer_tflops": {k: round(d[1] / (d[0] * 1e-3) / 1e12, 1) for k, d in per_layer.items() if d[0] > 0},
                      "per_layer_ms_per_step": {k: round(d[0] / args.steps, 4) for k, d in per_layer.items()}},
@@ -379,14 +437,156 @@ def run_ours(args):
                                       "traffic": None, "bytes_per_token": wa_C * 2 * 4, "tokens": wa_tokens, "ms": wa_ms,
                                       "peak_source": f"{peak_src} hbm_gbs",
                                       "workload": "4 x 288x480 tokens x 192 ch (1/4 resolution of a 1152x1920 crop), 8 heads, window 8, shift 4"},
-        "parity": {"bpp": float(bpp.item()), "psnr_db": float(psnr.item())},
+        "parity": {"bpp": float(bpp.item()), "psnr_db": float(psnr.item()), "multi_gpu_equal": multi_gpu_equal,
+                   "note": "gates (bpp 0.5 %, PSNR 0.01 dB vs the unmodified reference) are enforced by tests/test_gpu_net.py at "
+                           "B=1 768x512 and smaller; kernels are bit-exactly batch independent (test_full_size_batch_properties), "
+                           "so B=16 itself is covered by B=1 + batch independence"},
     }
     if world == 1 and not args.no_cpu_baseline:
-        ips, spi, cores = cpu_port_images_per_s(2, 1, batch=1)
+        ips, spi, cores = cpu_port_images_per_s(2, 1, batch=1, high=high)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "1 image 768x512 per step (same net, same weights), 2 timed steps after 1 warm-up, "
                                           "torch CPU fp32 port of the reference path with its one-hot sampler convs"}
     emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_tritplane(args):
+    """BASELINE configs[4]: progressive trit-plane quantisation + per-plane likelihood at 2048x2048 (latents
+    192 x 128 x 128 per image).  A step = one pass of ldic_tritplane_likelihood over this rank's images; images shard
+    over the ranks, the only exchange is one all-reduce of the L per-plane sums.  HBM bound: 12 B read +
+    (L + 4) B written per element.  Parity for this row is UNPINNED (the reference file crashes); the
+    bench checks the bit-exact symbol property q == clamp(round(v - mu)) and the exact reconstruction from the planes."""
+    import torch
+    import torch.distributed as dist
+    import ldic_b200
+    from ldic_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            import numpy as np
+            from oracle import tritplane_ref
+            n = 192 * 128 * 128 // 64                               # bounded sample: 1/64 of one image's latents
+            r = np.random.Generator(np.random.PCG64(0))
+            v = (4 * r.standard_normal(n)).astype(np.float32); mu = r.standard_normal(n).astype(np.float32)
+            sg = np.clip(np.exp(r.standard_normal(n)), 0.05, 20).astype(np.float32)
+            t0 = time.perf_counter()
+            for _ in range(max(args.steps, 1)):
+                tritplane_ref.tritplane(v, sg, mu, planes=4)
+            dt = (time.perf_counter() - t0) / max(args.steps, 1)
+            ips = (n / (192 * 128 * 128)) / dt
+            emit({"impl": "reference", "metric": "2048x2048 imgs/sec (trit-plane symbols + per-plane likelihood)", "value": ips,
+                  "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                  "config": {"workload": "numpy restatement of the trit-plane extension (oracle/tritplane_ref.py), 1/64 image per step"},
+                  "cpu_baseline": {"value": ips, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"{n} latent elements per step"},
+                  "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ldic_b200._lib.check(ldic_b200._lib.load().ldic_check_device(local), "device")
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, _, _, peak_src = peaks()
+    B, Lp = args.batch, 4
+    per_img = 192 * 128 * 128
+    n = B * per_img
+    g = torch.Generator(device=dev).manual_seed(rank)
+    NBUF = 3                                                        # rotating inputs: 3 x 12 B x n >> L2 at the default batch
+    bufs = [(torch.randn(n, device=dev, generator=g) * 4, torch.randn(n, device=dev, generator=g),
+             torch.exp(torch.randn(n, device=dev, generator=g)).clamp_(0.05, 20)) for _ in range(NBUF)]
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def step(i):
+        v, mu, sg = bufs[i % NBUF]
+        pl, q, sums = ops.tritplane_likelihood(v, sg, mu, planes=Lp)
+        s64 = sums.double()
+        if world > 1:
+            dist.all_reduce(s64)
+        return pl, q, s64
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        pl, q, s64 = step(i)
+    e1.record()
+    sync_all()
+    launches = int(ops.launch_count() - n0)
+    tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms = float(tt.item())
+    # kernel alone (events around the launches only, no allocation / reduction in between)
+    v, mu, sg = bufs[0]
+    torch.cuda.synchronize(dev)
+    k_ms = 0.0
+    for i in range(args.steps):
+        v, mu, sg = bufs[i % NBUF]
+        e0.record()
+        ops.tritplane_likelihood(v, sg, mu, planes=Lp)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        k_ms += e0.elapsed_time(e1)
+    k_ms /= args.steps
+    clocks = sampler.stop()
+    # end to end: host buffers in, symbols + planes + sums out
+    hv = [tuple(t.cpu().pin_memory() for t in b) for b in bufs[:2]]
+    out_host = (torch.empty((Lp, n), dtype=torch.int8).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory())
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        dv = [t.to(dev, non_blocking=True) for t in hv[i % 2]]
+        pl_, q_, sums_ = ops.tritplane_likelihood(dv[0], dv[2], dv[1], planes=Lp)
+        out_host[0].copy_(pl_.view(Lp, n), non_blocking=True); out_host[1].copy_(q_, non_blocking=True)
+        sums_.cpu()
+    e1.record()
+    sync_all()
+    tt2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
+    # bit-exact symbol property on the last step's outputs
+    v, mu, sg = bufs[(args.steps - 1) % NBUF]
+    Hh = (3 ** Lp - 1) // 2
+    q_ref = torch.clamp(torch.round(v - mu), -Hh, Hh).to(torch.int32)
+    recon = sum(pl[l].to(torch.int32) * (3 ** l) for l in range(Lp)) - Hh
+    sym_ok = bool(torch.equal(q, q_ref)) and bool(torch.equal(recon, q))
+    if world > 1:
+        ok_t = torch.tensor([int(sym_ok)], device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        sym_ok = bool(ok_t.item())
+    if rank == 0:
+        bytes_per_elem = 12 + Lp + 4
+        gbs = bytes_per_elem * n / (k_ms * 1e-3) / 1e9
+        emit({"metric": "2048x2048 imgs/sec (trit-plane symbols + per-plane likelihood)", "value": world * B * args.steps / (t_ms * 1e-3),
+              "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": f"BASELINE configs[4]: trit-plane quantisation + likelihood, {B} images of 2048x2048 "
+                                     f"(latents 192x128x128) per GPU, {Lp} planes", "global_batch": world * B,
+                         "l2": f"{NBUF} rotating input sets of {12 * n >> 20} MiB", "parity": "UNPINNED (no reference behaviour, SURVEY 8 a12)"},
+              "e2e": {"value": world * B * args.steps / (float(tt2.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 12 * n,
+                      "d2h_bytes_per_step": (Lp + 4) * n + 4 * Lp},
+              "gpu_launches": launches, "clocks": clocks,
+              "roofline": {"bound": "hbm", "kernel": "k_tritplane", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": gbs / hbm_peak, "traffic": None, "bytes_per_elem": bytes_per_elem, "elems": n, "ms": k_ms,
+                           "peak_source": f"{peak_src} hbm_gbs"},
+              "parity": {"symbols_bit_exact": sym_ok, "sum_ln_per_plane": [float(x) for x in s64.tolist()]}})
     if world > 1:
         dist.destroy_process_group()
 
@@ -423,8 +623,14 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--config", default="net", choices=["net", "high", "tritplane"],
+                    help="net: BASELINE configs[1] (headline); high: the N=384 model; tritplane: BASELINE configs[4]")
+    ap.add_argument("--input", default="u8", choices=["u8", "f32"], help="image type of the input buffers")
+    ap.add_argument("--side-sms", type=int, default=0, help="SM partition for the hyperprior / syntax side stream (0: single stream)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config == "tritplane":
+        run_tritplane(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

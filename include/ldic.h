@@ -47,6 +47,12 @@ LDIC_API const char* ldic_last_error(void);
 LDIC_API long long ldic_launch_count(void);
 /* 0 when device `dev` is compute capability 10.x, LDIC_ENOTSUP otherwise. */
 LDIC_API int ldic_check_device(int dev);
+/* Tuning / diagnostic switches.  They are read from the environment ONCE, when the library is loaded
+ * (LDIC_DEBUG_NOSTORE, LDIC_DEBUG_TIMING, LDIC_GDN_INSERT, LDIC_STAGES, LDIC_TAIL_WIDE, LDIC_LIK_GRID); no
+ * entry point calls getenv on its hot path.  ldic_set_tuning changes one at run time (tests, A/B runs): key is
+ * the environment name without the LDIC_ prefix in lower case ("tail_wide", "stages", ...); returns the previous
+ * value or LDIC_EINVAL.  Changing a switch invalidates the cached launch plans.                            */
+LDIC_API int ldic_set_tuning(const char* key, int value);
 
 /* ---- a3: LowerBound + NonNegativeParametrizer ---------------------------------
  * y = max(x, bound)                                   ops/bound_ops.py:21-22
@@ -144,6 +150,10 @@ LDIC_API int ldic_syntax_conv_mse(const float* x_nchw, const float* xt_nhwc, con
 /* NCHW fp32 -> NHWC bf16 (channels padded to Cp with zeros) and back.            */
 LDIC_API int ldic_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W, int Cp, int apply_abs, void* stream);
 LDIC_API int ldic_nhwc_to_nchw_f32(const void* x, int x_is_bf16, float* y, int B, int C, int H, int W, int Cp, void* stream);
+/* uint8 image levels -> fp32 x = (u/255)*2-1: the reference's input map (torchvision ToTensor, then
+ * eval_net.py:84), the same correctly rounded fp32 operations.  Only needed where the first layer is not the
+ * fused LDIC_CONV_FIRST_5x5S2 kernel (which takes the uint8 image directly).                              */
+LDIC_API int ldic_u8_to_f32_pm1(const unsigned char* x, float* y, size_t n, void* stream);
 /* y (NHWC fp32, C channels) -> optional outputs: round(y) bf16, |y| bf16, round(y) fp32.
  * model/net.py:197 (abs), :676/:741 (round).                                     */
 LDIC_API int ldic_latent_prep(const float* y, size_t n, void* y_round_bf16, void* y_abs_bf16, float* y_round_f32, void* stream);
@@ -174,7 +184,10 @@ enum {
   LDIC_CTX_FC = 11,    /* [P,2,2,N] -> [P,1,2,Cout_pad] fp32 (mu | log sigma), Linear(4N, 2*Cout) :302; Cout = N-M   */
   /* First analysis layer fused with its GDN: x is the NCHW fp32 IMAGE (B,3,H,W) itself (not NHWC bf16);
    * ZeroPad2d((1,2,1,2)) + Conv2d(3,Cout,5,2) (+GDN) -> NHWC bf16, no patch matrix in HBM.  Cin = 3,
-   * Cin_pad = 128 (K = 75 padded), Cout_pad <= 192.  model/net.py:97-99.                          */
+   * Cin_pad = 128 (K = 75 padded), Cout_pad <= 192.  model/net.py:97-99.
+   * aux0 = 1: x is the uint8 image (B,3,H,W) of 8-bit levels u; the kernel applies the reference's input map
+   * x = (u/255)*2-1 (ToTensor + eval_net.py:84) while it builds the patches, so the host->device copy carries
+   * 1 byte per sample instead of 4.  W % 16 == 0.                                                  */
   LDIC_CONV_FIRST_5x5S2 = 12
 };
 enum { LDIC_ACT_NONE = 0, LDIC_ACT_RELU = 1, LDIC_ACT_LEAKY02 = 2, LDIC_ACT_GDN = 3, LDIC_ACT_IGDN = 4 };
@@ -187,7 +200,10 @@ typedef struct {
   int Cout_pad;       /* channels of the output tensor in memory                 */
   int act;            /* LDIC_ACT_*                                              */
   int out_f32;        /* 0: bf16 NHWC output, 1: fp32 NHWC output                */
-  int aux0, aux1;     /* kind specific (LDIC_CTX_CONV1: N, M), else 0            */
+  int aux0, aux1;     /* kind specific (LDIC_CTX_CONV1: N, M; LDIC_CONV_FIRST_5x5S2: aux0 = 1 for a uint8 image), else 0 */
+  int sm_limit;       /* SM partition for concurrent streams: 0 = all SMs; n > 0 = at most n SMs; n < 0 = leave |n| SMs
+                         free (the kernels are persistent, one CTA per SM, so the grid size IS the SM footprint)  */
+  int reserved;
 } LdicConvDesc;
 
 /* Elements (bf16) of the packed weight image for this layer, and the packer:
@@ -208,18 +224,24 @@ LDIC_API void ldic_conv_out_shape(const LdicConvDesc* d, int* Ho, int* Wo);
  * (gamma_bf16 / beta_tiled from ldic_gdn_prepare).                              */
 LDIC_API int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                       const void* gamma_bf16, const float* beta_tiled, void* y, void* stream);
+/* Launch plans (tile / tap tables, TMA descriptors, kernel variant, grid) are cached per (descriptor, tensor
+ * addresses, device): a repeated call with the same arguments is a lookup plus one kernel launch.          */
+LDIC_API int ldic_conv_plan_cache_size(void);
+LDIC_API void ldic_conv_plan_cache_clear(void);
 /* The merged last synthesis deconv (LDIC_DECONV_GS_5x5_MERGED) with the tail of Net.forward fused into its
  * epilogue: per-image 1x1 conv of the M-channel IGDN output with w[B][3][M] (batch_conv, model/net.py:527-537,
- * :811) and the a11 squared level error against the NCHW fp32 input image (model/net.py:864-868), so the
+ * :811) and the a11 squared level error against the NCHW input image (model/net.py:864-868), so the
  * M-channel full-resolution tensor never makes a round trip through HBM.  y_or_null (optional) still receives
  * the [B,2H,2W,M] fp32 NHWC tensor; x_tilde_nchw (optional) the reconstruction; sq_err[B] is accumulated
  * into (zero it first).  H, W of the tail are the image size (= 2 x the layer's input size).            */
 typedef struct {
-  const float* x_nchw;
+  const void* x_nchw;         /* fp32 image in [-1,1], or its uint8 levels when x_is_u8 */
   const float* w;
   float* x_tilde_nchw;
   unsigned long long* sq_err;
   int H, W;
+  int x_is_u8;
+  int reserved;
 } LdicConvTail;
 LDIC_API int ldic_conv_forward_fused_tail(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                                  const void* gamma_bf16, const float* beta_tiled, void* y_or_null,

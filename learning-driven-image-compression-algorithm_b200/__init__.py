@@ -5,6 +5,7 @@ The directory name carries the reference's (hyphenated) name; import it as ``ldi
 (repo-root shim ``ldic_b200.py``).
 """
 from . import _lib, ops                                     # noqa: F401
+from . import torch_ops                                     # noqa: F401  (registers torch.ops.ldic.*)
 from ._lib import LdicError, EXPORTED_SYMBOLS, lib_path     # noqa: F401
 from .layers import (GDN, GaussianConditional, GaussianModel, LowerBound, ModelGDN, ModelIGDN,   # noqa: F401
                      NonNegativeParametrizer, WinBasedAttention, WindowAttention, bypass_round, ste_round,

@@ -26,6 +26,7 @@ LDIC_CTX_CONV3 = 10
 LDIC_CTX_FC = 11
 LDIC_CONV_FIRST_5x5S2 = 12
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_GDN, ACT_IGDN = 0, 1, 2, 3, 4
+LDIC_EINVAL_RC = -1
 
 
 class LdicError(RuntimeError):
@@ -50,12 +51,12 @@ class LikelihoodArgs(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int),
                 ("Cout", C.c_int), ("Cin_pad", C.c_int), ("Cout_pad", C.c_int), ("act", C.c_int),
-                ("out_f32", C.c_int), ("aux0", C.c_int), ("aux1", C.c_int)]
+                ("out_f32", C.c_int), ("aux0", C.c_int), ("aux1", C.c_int), ("sm_limit", C.c_int), ("reserved", C.c_int)]
 
 
 class ConvTail(C.Structure):
     _fields_ = [("x_nchw", C.c_void_p), ("w", C.c_void_p), ("x_tilde_nchw", C.c_void_p), ("sq_err", C.c_void_p),
-                ("H", C.c_int), ("W", C.c_int)]
+                ("H", C.c_int), ("W", C.c_int), ("x_is_u8", C.c_int), ("reserved", C.c_int)]
 
 
 class SyntaxArgs(C.Structure):
@@ -74,6 +75,10 @@ _SIGS = {
     "ldic_last_error": (C.c_char_p, []),
     "ldic_launch_count": (C.c_longlong, []),
     "ldic_check_device": (C.c_int, [C.c_int]),
+    "ldic_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
+    "ldic_conv_plan_cache_size": (C.c_int, []),
+    "ldic_conv_plan_cache_clear": (None, []),
+    "ldic_u8_to_f32_pm1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ldic_lower_bound": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ldic_lower_bound_bwd": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ldic_nonneg_reparam": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -37,7 +37,17 @@ inline int check_launch(const char* what) {
     if (e_ != cudaSuccess) return ::ldic::fail(LDIC_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kMaxSMs = 160;      // sizing bound of per-CTA workspaces (B200: 148); grids use num_sms()
+constexpr int kMaxDevices = 64;
+int current_device();             // cudaGetDevice (-1 on error)
+int num_sms();                    // multiprocessor count of the current device (queried once per device)
+
+// Tuning / diagnostic switches, read from the environment once at load time (see ldic_set_tuning in ldic.h)
+struct Tuning {
+  int debug_nostore, debug_timing, gdn_insert, stages_cap, tail_wide, lik_grid;
+  unsigned epoch;                 // bumped by ldic_set_tuning: cached launch plans of older epochs are not reused
+};
+const Tuning& tuning();
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

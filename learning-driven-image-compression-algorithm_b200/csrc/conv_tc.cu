@@ -9,9 +9,9 @@
 //   warp 10      weight / gamma tile producer (CTA-pair and halo kernels); first layer: patch builders (+ warp 11)
 // (setmaxnreg moves registers from warpgroup 2 to the two epilogue warpgroups)
 //
-// Kernels: conv_tc_kernel (1 CTA per tile, fallback), conv_tc2_kernel (CTA pairs, cta_group::2 -- the default;
-// W3 = wide-N form of the merged last deconv), conv_halo_kernel / conv_halo2_kernel (one activation region per
-// channel chunk serves all taps), conv_first_kernel (first analysis layer straight from the NCHW fp32 image).
+// Kernels: conv_tc2_kernel (CTA pairs, cta_group::2; W3 = wide-N form of the merged last deconv), conv_wide_kernel
+// (384 output channels: single-buffered accumulator, gamma contraction tiled over its output channels),
+// conv_first_kernel (first analysis layer straight from the NCHW fp32 or uint8 image).
 //
 // GEMM view: M = 128 output (or, for transposed convs, input-grid) pixels per tile,
 // N = Np accumulator columns (= output channels, or 4 sub-pixel phases x channels for the
@@ -29,6 +29,9 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <type_traits>
+#include <memory>
+#include <unordered_map>
+#include <string.h>
 #include "common.cuh"
 
 using namespace ldic;
@@ -60,11 +63,11 @@ constexpr int kGdnInsertDefault = 4;     // conv stages of the next tile issued 
 
 // one filter tap = one spatial offset of the gather + a K range: nkc 64-wide blocks starting at
 // channel a_c0 of the activation and column b_c0 of the tap's packed weight block
-struct Tap { short dx, dy, px, nkc; int a_c0, b_c0; int halo_off; };
-struct Job { int ntaps, tap_begin, nkb, oy_off, ox_off, out_off; int kc0, nchunks; };
+struct Tap { short dx, dy, px, nkc; int a_c0, b_c0; };
+struct Job { int ntaps, tap_begin, nkb, oy_off, ox_off, out_off; };
 
 struct ConvParams {
-  int mode;                 // 0: stride-1 gather (4-D map), 1: stride-2 gather (5-D parity map)
+  int mode;                 // 0: stride-1 gather, 2: stride-2 gather (one TMA box with element strides (1,2,2,1))
   int TW, TH, TN;
   int tw_shift, th_shift, cg_shift;
   int tiles_x, tiles_y, tiles_n, tiles_per_job, njobs, total_tiles;
@@ -72,12 +75,8 @@ struct ConvParams {
   int gdn_kblocks;          // Np / 64 when act is GDN/IGDN, else 0
   int act, out_f32;
   int stages;
-  // halo variant: one (TH+dy range) x (TW+dx range) activation region per 64-channel chunk serves all taps
-  int halo, SA, SB, a_slot_bytes, RW, RH, dxmin, dymin;
+  int SA, SB;               // conv_wide_kernel: slots of the activation / weight rings
   int x_ovl;                // tiles overlap by x_ovl pixels in x (wide-N merged deconv: 2 = one halo pixel per side), else 0
-  int ndx;                  // halo: 1 = one region, taps address it with row-shifted descriptor starts; > 1 = "aligned
-                            // halo": ndx copies of a TW-wide region, one per dx, so every tap starts 1024-byte aligned
-  int G;                    // halo: filter taps per B-ring slot (one TMA box of G*Np weight rows)
   int gdn_insert;           // streaming kernels: conv stages of tile it+1 issued before the GDN stages of tile it
   int super_per_job;        // CTA-pair kernel: (tiles_per_job + 1) / 2 pairs of adjacent tiles per job
   int ngroups, Cg;          // accumulator columns = ngroups x Cg
@@ -92,7 +91,8 @@ struct ConvParams {
   unsigned long long* dbg;   // optional cycle counters of CTA 0 (LDIC_DEBUG_TIMING=1), else null
   int dbg_nostore;           // experiment: skip the epilogue's global stores (LDIC_DEBUG_NOSTORE=1)
   // fused tail of Net.forward on the merged last deconv: per-image 1x1 conv (batch_conv) + 8-bit-level squared error
-  const float* tail_x;       // NCHW fp32 input image [B,3,tail_H,tail_W], or null (no tail)
+  const void* tail_x;        // NCHW input image [B,3,tail_H,tail_W] (fp32 in [-1,1], or uint8 levels when tail_u8), or null
+  int tail_u8;
   const float* tail_w;       // [B][3][Cg] per-image filters
   float* tail_xo;            // optional NCHW fp32 reconstruction
   unsigned long long* tail_sq;  // [B] exact sums (accumulated into)
@@ -128,6 +128,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // records {block, thread, barrier offset in dynamic smem, parity} in host-mapped memory so that the host can
 // still read which barrier starved after the context is lost (ldic_debug_last_timeout).
 __device__ unsigned long long* g_timeout_report = nullptr;
+constexpr long long kWatchdogCycles = 60000000000LL;   // ~30 s at 2 GHz: a protocol bug, not a time-sliced or profiled GPU
 __device__ __forceinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
   extern __shared__ uint8_t smem_raw[];
   unsigned long long* r = g_timeout_report;
@@ -143,7 +144,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(smem_u32(bar), parity);
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > kWatchdogCycles) mbar_timeout(smem_u32(bar), parity);
   }
 }
 
@@ -308,7 +309,7 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait_cl(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(smem_u32(bar), parity);
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > kWatchdogCycles) mbar_timeout(smem_u32(bar), parity);
   }
 }
 // TMA loads of a CTA pair: the data lands in the executing CTA, the completion may be signalled on a barrier of
@@ -393,7 +394,6 @@ struct EpiRing {
   uint64_t* empty_bar;      // [nslots] "slot free" barriers of that ring
   uint64_t *acc_full, *buf_free, *x2_ready, *norm_full;   // [2] each
   const float *s_bias, *s_beta;
-  int use_chunks;           // stream length of a tile: jobs[].nchunks (halo) or jobs[].nkb (streaming)
   int insert_after;         // GDN items of tile it-1 ride after this many stream items of tile it
   // CTA-pair kernels: tiles are super tiles t_first + it * t_stride decoded for `rank`; buf_free / x2_ready live in
   // the leader CTA and are reached through their shared::cluster addresses
@@ -404,6 +404,20 @@ struct EpiRing {
 
 // Fused tail on the CPT accumulator columns of one thread (CPT / CG output pixels of CG channels each); every index
 // into xr is a compile-time constant so the accumulators stay in registers.
+// a11 on one sample of the fused tail: the image is fp32 in [-1,1] (model/net.py:864) or its uint8 levels -- for an
+// 8-bit image x = (u/255)*2-1 (eval_net.py:84 after ToTensor) the reference's gt = round((x+1)*127.5) is u itself
+// (checked exhaustively for u = 0..255 in tests/test_oracle_golden.py), so the level is used directly.
+__device__ __forceinline__ unsigned int tail_sq_err(const ConvParams& P, long long idx, float xt) {
+  if (P.tail_u8) {
+    const float gt = (float)__ldg(reinterpret_cast<const unsigned char*>(P.tail_x) + idx);
+    float xh = __fmul_rn(__fadd_rn(xt, 1.f), 127.5f);
+    xh = rintf(fminf(fmaxf(xh, 0.f), 255.f));
+    const float d = xh - gt;
+    return (unsigned int)(d * d);
+  }
+  return sq_level_err(__ldg(reinterpret_cast<const float*>(P.tail_x) + idx), xt, 0);
+}
+
 template <int CPT, int CG>
 __device__ __forceinline__ unsigned long long fused_tail_pixels(const ConvParams& P, const float (&xr)[CPT], int col0, int n,
                                                                 int oy0, int ox0) {
@@ -424,7 +438,7 @@ __device__ __forceinline__ unsigned long long fused_tail_pixels(const ConvParams
       for (int c = 0; c < 3; ++c) {
         const long long idx = (((long long)n * 3 + c) * P.tail_H + oy) * P.tail_W + ox;
         if (P.tail_xo) P.tail_xo[idx] = o[c];
-        acc += sq_level_err(__ldg(P.tail_x + idx), o[c], 0);
+        acc += tail_sq_err(P, idx, o[c]);
       }
     }
   }
@@ -465,12 +479,12 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
                                  (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
       // ring position of this tile's gamma items: after the first min(insert_after, len) items of the
       // NEXT tile's stream, or right after this tile's stream when it is the CTA's last tile
-      const int len_this = R.use_chunks ? jb.nchunks : jb.nkb;
+      const int len_this = jb.nkb;
       sbase += (uint32_t)len_this + ((gk && it > 0) ? (uint32_t)gk : 0u);
       uint32_t gpos = sbase;
       if (gk && it + 1 < ntiles_cta) {
         const Job jn = P.jobs[tc_n1.job];
-        const int len_next = R.use_chunks ? jn.nchunks : jn.nkb;
+        const int len_next = jn.nkb;
         gpos += (uint32_t)(len_next < R.insert_after ? len_next : R.insert_after);
       }
 
@@ -820,7 +834,7 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
           for (int c = 0; c < 3; ++c) {
             const long long idx = (((long long)gn_ * 3 + c) * P.tail_H + oy) * P.tail_W + ox;
             if (P.tail_xo) P.tail_xo[idx] = o[c];
-            tail_acc += sq_level_err(__ldg(P.tail_x + idx), o[c], 0);
+            tail_acc += tail_sq_err(P, idx, o[c]);
           }
         }
       }
@@ -837,211 +851,6 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
     P.dbg[16] = (unsigned long long)(clock64() - e_begin); P.dbg[17] = (unsigned long long)e_acc;
     P.dbg[18] = (unsigned long long)e_norm; P.dbg[19] = (unsigned long long)e_slot; P.dbg[20] = (unsigned long long)ntiles_cta;
     P.dbg[21] = (unsigned long long)e_p1; P.dbg[22] = (unsigned long long)e_p2;
-  }
-}
-
-template <int NP>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
-  constexpr int kBTileBytes = NP * kBlockK * 2;
-  constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024 B alignment
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int stages = P.stages;
-  uint8_t* aux = smem_al + (size_t)stages * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [kMaxStages]
-  uint64_t* empty_bar = full_bar + kMaxStages;                         // [kMaxStages]
-  uint64_t* acc_full = empty_bar + kMaxStages;                         // [2] MMA -> epilogue: accumulator complete
-  uint64_t* buf_free = acc_full + 2;                                   // [2] epilogue -> MMA: TMEM buffer drained
-  uint64_t* x2_ready = buf_free + 2;                                   // [2] epilogue -> MMA: x^2 operand written
-  uint64_t* norm_full = x2_ready + 2;                                  // [2] MMA -> epilogue: GDN norm complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
-  float* s_bias = reinterpret_cast<float*>(aux + 256);                 // [NP], 16-byte aligned
-  float* s_beta = s_bias + NP * P.nbias;                               // [NP]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&buf_free[i], kEpiThreads);
-      mbar_init(&x2_ready[i], kEpiThreads);
-      mbar_init(&norm_full[i], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmW);
-    if (gdn) prefetch_tmap(&tmG);
-  }
-  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
-  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
-  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // Schedule (identical in all roles).  The CTA walks its tiles it = 0,1,..; tile `it` accumulates into
-  // TMEM buffer it&1 (columns 0 / 256).  With the GDN epilogue, the gamma contraction of tile it-1
-  // (gk ring stages whose A half is written by the epilogue warps) is issued after the first
-  // min(P.gdn_insert, nkb) conv stages of tile `it`, into the buffer tile it-1 has just been drained from
-  // (the norm overwrites the accumulator in place), so the tensor pipe never waits for the epilogue.
-  const int gk = gdn ? P.gdn_kblocks : 0;
-  const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-
-  if (warp >= kEpiWarps) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // warpgroup 2 hands registers to the epilogue
-  if (warp == kProdWarp) {
-    // ===================== TMA producer =====================
-    // Warp-uniform loop, lane 0 arms the barrier and issues the copies.  The filter taps of the tile's
-    // job live in registers (lane t holds tap t) and are broadcast with shuffles, so the loop body has
-    // no constant-bank loads with computed indices.
-    {
-      uint32_t slot = 0, ph = 0;                              // ring position and pass parity
-      int stages_r = stages;
-      asm volatile("" : "+r"(stages_r));                      // keep the ring size in a register
-      auto advance = [&]() { if (++slot == (uint32_t)stages_r) { slot = 0; ph ^= 1; } };
-      auto load_gamma = [&]() {
-        for (int kb = 0; kb < gk; ++kb) {                     // gamma K-blocks ride the same ring
-          mbar_wait(&empty_bar[slot], ph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&full_bar[slot], kBTileBytes);
-            tma_load_2d(smem_base + slot * kStageBytes + kATileBytes, &tmG, &full_bar[slot], kb * kBlockK, 0);
-          }
-          advance();
-        }
-      };
-      const int th = P.TH, tw128 = P.TW * 128, mode = P.mode;
-      const int cs = mode == 2 ? 2 : 1;                       // input pixels per tile pixel (strided TMA box)
-      int cur_job = -1, ntaps = 0, tap_begin = 0, nkb = 0;
-      uint32_t my_w0 = 0, my_w1 = 0;                          // lane t: tap t of the current job, packed
-      for (int it = 0; it < ntiles_cta; ++it) {
-        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        if (tc.job != cur_job) {
-          cur_job = tc.job;
-          ntaps = P.jobs[cur_job].ntaps; tap_begin = P.jobs[cur_job].tap_begin; nkb = P.jobs[cur_job].nkb;
-          if (lane < ntaps) {
-            const Tap t = P.taps[tap_begin + lane];
-            my_w0 = (uint32_t)(uint8_t)t.dx | ((uint32_t)(uint8_t)t.dy << 8) | ((uint32_t)t.px << 16) | ((uint32_t)t.nkc << 24);
-            my_w1 = (uint32_t)t.a_c0 | ((uint32_t)t.b_c0 << 16);
-          }
-        }
-        const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
-        const int x0 = tc.x0 * cs, y0 = tc.y0 * cs;
-        int cb = 0;
-        for (int tp = 0; tp < ntaps; ++tp) {
-          const uint32_t w0 = __shfl_sync(0xffffffffu, my_w0, tp), w1 = __shfl_sync(0xffffffffu, my_w1, tp);
-          const int dx = (int)(int8_t)(w0 & 0xff), dy = (int)(int8_t)((w0 >> 8) & 0xff), px = (int)((w0 >> 16) & 0xff);
-          const int nkc = (int)(w0 >> 24), a_c0 = (int)(w1 & 0xffff), b_c0 = (int)(w1 >> 16);
-          const int brow = (tap_begin + tp) * NP;
-          for (int kc = 0; kc < nkc; ++kc, ++cb) {
-            if (cb == jins) load_gamma();
-            const uint32_t a_dst = smem_base + slot * kStageBytes;
-            mbar_wait(&empty_bar[slot], ph ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(&full_bar[slot], kStageBytes);
-              if (mode == 1) {
-                for (int j = 0; j < th; ++j)
-                  tma_load_5d(a_dst + j * tw128, &tmA, &full_bar[slot], a_c0 + kc * kBlockK, px,
-                              tc.x0 + dx, 2 * (tc.y0 + j) + dy, tc.n0);
-              } else {
-                tma_load_4d(a_dst, &tmA, &full_bar[slot], a_c0 + kc * kBlockK, x0 + dx, y0 + dy, tc.n0);
-              }
-              tma_load_2d(a_dst + kATileBytes, &tmW, &full_bar[slot], b_c0 + kc * kBlockK, brow);
-            }
-            advance();
-          }
-        }
-        if (cb == jins) load_gamma();
-      }
-      if (gk) load_gamma();                                   // contraction of the last tile
-    }
-  } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer (warp-uniform loop, lane 0 issues) =====================
-    {
-      uint32_t slot = 0, ph = 0;
-      int stages_r = stages;
-      asm volatile("" : "+r"(stages_r));
-      const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
-      long long t_full = 0, t_buf = 0, t_x2 = 0, n_st = 0;
-      const long long t_begin = clock64();
-      const uint32_t hi = desc_hi(1024);
-      const uint32_t a_lo0 = desc_lo(smem_base), b_lo0 = desc_lo(smem_base + kATileBytes);
-      uint32_t slot_lo = 0;                                  // slot * (kStageBytes >> 4)
-      auto mma_stage = [&](uint32_t d_tmem, bool first) {
-        long long t0 = 0;
-        if (dbg) t0 = clock64();
-        mbar_wait(&full_bar[slot], ph);
-        if (dbg) { t_full += clock64() - t0; ++n_st; }
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t alo = a_lo0 + slot_lo, blo = b_lo0 + slot_lo;
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16_lh(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, kIdesc, !(first && k == 0));
-          tc_commit(&empty_bar[slot]);                       // frees the smem slot when these MMAs retire
-        }
-        ++slot; slot_lo += (uint32_t)(kStageBytes >> 4);
-        if (slot == (uint32_t)stages_r) { slot = 0; slot_lo = 0; ph ^= 1; }
-      };
-      auto gdn_of = [&](int j) {                             // norm(j) = x^2 . gamma^T, in place over acc(j)
-        const int bsel = j & 1;
-        long long t0 = 0;
-        if (dbg) t0 = clock64();
-        mbar_wait(&x2_ready[bsel], (j >> 1) & 1);            // x^2 tiles written by the epilogue warps
-        if (dbg) t_x2 += clock64() - t0;
-        tc_fence_after();
-        for (int kb = 0; kb < gk; ++kb) mma_stage(tmem_base + bsel * kBufCols, kb == 0);
-        if (elect_one()) tc_commit(&norm_full[bsel]);
-      };
-      int cur_job = -1, nkb = 0;
-      for (int it = 0; it < ntiles_cta; ++it) {
-        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        if (tc.job != cur_job) { cur_job = tc.job; nkb = P.jobs[cur_job].nkb; }
-        const int jins = (gk && it > 0) ? (nkb < P.gdn_insert ? nkb : P.gdn_insert) : -1;
-        const int bsel = it & 1;
-        long long t0 = 0;
-        if (dbg) t0 = clock64();
-        mbar_wait(&buf_free[bsel], ((it >> 1) & 1) ^ 1);     // epilogue has drained this TMEM buffer
-        if (dbg) t_buf += clock64() - t0;
-        tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          if (kb == jins) gdn_of(it - 1);
-          mma_stage(tmem_base + bsel * kBufCols, kb == 0);
-        }
-        if (elect_one()) tc_commit(&acc_full[bsel]);
-        if (nkb == jins) gdn_of(it - 1);
-      }
-      if (gk) gdn_of(ntiles_cta - 1);
-      if (dbg && lane == 0) {
-        P.dbg[0] = (unsigned long long)(clock64() - t_begin); P.dbg[1] = (unsigned long long)t_full;
-        P.dbg[2] = (unsigned long long)t_buf; P.dbg[3] = (unsigned long long)t_x2; P.dbg[4] = (unsigned long long)n_st;
-        P.dbg[5] = (unsigned long long)ntiles_cta;
-      }
-    }
-  }
-  } else {
-    // ===================== epilogue warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
-    EpiRing R;
-    R.pair_store = 1;
-    R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
-    R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
-    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
-    epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1256,7 +1065,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     R.pair_store = 1;
     R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
-    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.insert_after = P.gdn_insert;
     R.t_first = pi; R.t_stride = npairs; R.rank = (int)rank;
     R.buf_free_cl = mapa_shared(smem_u32(buf_free), 0); R.x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0);
     if constexpr (W3) epilogue_w3<NP>(P, R, tmem_base, gk, nt, warp, lane);
@@ -1273,297 +1082,58 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------
-// Halo variant for stride-1 gathers (transposed-conv phases, 3x3 convs, context conv1).
-// The streaming kernel above re-fetches a 128-pixel A tile for every filter tap, so every input pixel
-// crosses the L2->SM fabric once per tap (~6 TB/s of unique traffic is the measured ceiling).  Here a
-// tile is 16 rows x 8 pixels and ONE (16+dy range) x (8+dx range) pixel region per 64-channel chunk is
-// brought in by a single TMA box; every tap's A operand is that same region addressed through a UMMA
-// descriptor whose start is shifted by whole 128-byte pixel rows and whose 8-row-group stride is the
-// region row pitch (SWIZZLE_128B is applied on absolute address bits, so shifted starts read exactly
-// what TMA wrote: tools/umma_shift_probe.cu).  Two rings: A regions (warp 0) and B weight tiles (warp 2).
+// Wide-accumulator CTA-pair kernel: NP = 384 output channels (the reference's `--high` model, N = 384,
+// model/net.py:446-451).  A GDN layer then needs 384 accumulator columns + 384 norm columns > the 512 TMEM columns,
+// so the accumulator is single-buffered in columns [0, NP) and the gamma contraction is tiled over its
+// OUTPUT channels: norm chunk c (128 columns, TMEM [NP, NP+128)) = x^2[128 px, NP] . gamma[128c..128c+128, :]^T with all
+// NP/64 x^2 operand tiles resident in shared memory; pass 2 re-reads x from the accumulator chunk by chunk, so no
+// thread ever holds more than 64 + 64 fp32 values.
+//   * MMA N <= 256: every K step issues two M256 x N(NP/2) MMAs (column halves 0 and NP/2).
+//   * Two rings instead of one: A (16 KB activation tiles; NP/64 of its slots carry the x^2 tiles during the GDN
+//     phase) and B (this CTA's half of the weight rows of both column halves = NP/2 rows x 128 B; during the GDN
+//     phase one slot carries 3 K blocks of this CTA's 64 gamma rows of the current norm chunk).
+//   * Schedule per tile: main loop -> acc_full -> pass 1 (x^2 tiles) -> per norm chunk: [gamma MMAs -> norm_full ->
+//     pass 2 of the chunk (the MMAs of chunk c+1 run under the arithmetic and stores of chunk c)] -> acc_free.
+//     The tensor pipe idles during passes 1 and 2 (~17 k cycles per tile against 115 k cycles of MMAs for the
+//     5x5 conv at N = 384), the TMA producers run ahead into the free ring slots meanwhile.
+// Layers without GDN at NP = 384 (conv 4, h_a, h_s, context model) use the same kernel with the plain epilogue.
 // ---------------------------------------------------------------------------------
-constexpr int kHaloInsert = 1;          // conv chunks of the next tile issued before the previous tile's GDN items
+constexpr int kWideNC = 128;            // norm chunk (columns)
+constexpr int kWideGPI = 3;             // gamma K blocks per B-ring slot
 
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
-  constexpr int kBTileBytes = NP * kBlockK * 2;
-  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  constexpr int NH = NP / 2;                               // columns per MMA
+  constexpr int kBSlotBytes = (NP / 2) * kBlockK * 2;      // 2 x (NH / 2) weight rows
+  constexpr int kBHalfOff = (NH / 2) * kBlockK * 2;        // column half 1 inside a B slot
+  constexpr int GK = NP / 64;                              // x^2 operand tiles
+  constexpr int NCH = NP / kWideNC;                        // norm chunks
+  constexpr int kGTileBytes = (kWideNC / 2) * kBlockK * 2; // this CTA's 64 gamma rows of one K block
+  constexpr int GITEMS = GK / kWideGPI;                    // B-ring items per norm chunk
+  static_assert(NP % 128 == 0 && NP > 256 && NP + kWideNC <= kTmemCols, "wide kernel: 256 < NP <= 384, multiple of 128");
+  static_assert(GK % kWideGPI == 0 && kWideGPI * kGTileBytes <= kBSlotBytes, "gamma items must fit a B slot");
+  static_assert(kBHalfOff % 1024 == 0 && kGTileBytes % 1024 == 0, "operand tiles start on swizzle atoms");
+  constexpr uint32_t kIdescH = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr uint32_t kIdescG = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kWideNC >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const int SA = P.SA, SB = P.SB;
-  const uint32_t a_slot = (uint32_t)P.a_slot_bytes;
-  const int G = P.G;
-  const uint32_t b_slot = (uint32_t)G * kBTileBytes;                  // G taps of weights per slot
-  const uint32_t b_base = smem_base + (uint32_t)SA * a_slot;
-  uint8_t* aux = smem_al + (size_t)SA * a_slot + (size_t)SB * b_slot;
-  uint64_t* afull = reinterpret_cast<uint64_t*>(aux);                  // [kMaxStages]
-  uint64_t* aempty = afull + kMaxStages;
-  uint64_t* bfull = aempty + kMaxStages;
-  uint64_t* bempty = bfull + kMaxStages;
-  uint64_t* acc_full = bempty + kMaxStages;                            // [2]
-  uint64_t* buf_free = acc_full + 2;
-  uint64_t* x2_ready = buf_free + 2;
-  uint64_t* norm_full = x2_ready + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
-  float* s_bias = reinterpret_cast<float*>(aux + 512);                 // 16-byte aligned
-  float* s_beta = s_bias + NP * P.nbias;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool gdn = (P.act == LDIC_ACT_GDN || P.act == LDIC_ACT_IGDN);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
-    for (int i = 0; i < SB; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&buf_free[i], kEpiThreads);
-      mbar_init(&x2_ready[i], kEpiThreads);
-      mbar_init(&norm_full[i], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmW);
-    if (gdn) prefetch_tmap(&tmG);
-  }
-  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
-  for (int i = threadIdx.x; i < NP * P.nbias; i += kThreads) s_bias[i] = P.bias ? P.bias[i] : 0.f;
-  for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  const int gk = gdn ? P.gdn_kblocks : 0;
-  const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const uint32_t sub_bytes = (uint32_t)(P.RW * P.RH * 128);
-  const uint32_t region_bytes = sub_bytes * (uint32_t)P.ndx;
-  const uint32_t sbo = (uint32_t)P.RW * 128u;
-  // a tap contributes to channel chunk kc iff its K range covers it
-  auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
-  // a tap contributes to channel chunk kc iff its K range covers it
-
-  if (warp >= kEpiWarps) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == kProdWarp) {
-      // ===================== A-region producer (warp-uniform loop, elected lane issues) =====================
-      uint32_t sa = 0, pa = 0;
-      auto adv = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
-      auto reserve_gdn = [&]() {            // hand gk A slots to the epilogue warps (x^2 operand tiles)
-        for (int kb = 0; kb < gk; ++kb) {
-          mbar_wait(&aempty[sa], pa ^ 1);
-          __syncwarp();
-          if (elect_one()) mbar_arrive(&afull[sa]);
-          adv();
-        }
-      };
-      for (int it = 0; it < ntiles_cta; ++it) {
-        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        const Job jb = P.jobs[tc.job];
-        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
-        for (int ci = 0; ci < jb.nchunks; ++ci) {
-          if (ci == jins) reserve_gdn();
-          mbar_wait(&aempty[sa], pa ^ 1);
-          __syncwarp();
-          if (elect_one()) {
-            mbar_expect_tx(&afull[sa], region_bytes);
-            for (int sx = 0; sx < P.ndx; ++sx)
-              tma_load_4d(smem_base + sa * a_slot + (uint32_t)sx * sub_bytes, &tmA, &afull[sa], (jb.kc0 + ci) * kBlockK,
-                          tc.x0 + P.dxmin + sx, tc.y0 + P.dymin, tc.n0);
-          }
-          adv();
-        }
-        if (jb.nchunks == jins) reserve_gdn();
-      }
-      if (gk) reserve_gdn();
-    } else if (warp == kProdBWarp) {
-      // ===================== B (weights / gamma) producer =====================
-      uint32_t sb = 0, pb = 0;
-      auto adv = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
-      auto load_gamma = [&]() {
-        for (int kb = 0; kb < gk; ++kb) {
-          mbar_wait(&bempty[sb], pb ^ 1);
-          __syncwarp();
-          if (elect_one()) {
-            mbar_expect_tx(&bfull[sb], kBTileBytes);
-            tma_load_2d(b_base + sb * b_slot, &tmG, &bfull[sb], kb * kBlockK, 0);
-          }
-          adv();
-        }
-      };
-      for (int it = 0; it < ntiles_cta; ++it) {
-        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        const Job jb = P.jobs[tc.job];
-        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
-        for (int ci = 0; ci < jb.nchunks; ++ci) {
-          if (ci == jins) load_gamma();
-          const int kc = jb.kc0 + ci;
-          for (int tp = 0; tp < jb.ntaps; tp += G) {          // G == 1 unless every tap covers every chunk
-            const Tap tap = P.taps[jb.tap_begin + tp];
-            if (!tap_active(tap, kc)) continue;
-            mbar_wait(&bempty[sb], pb ^ 1);
-            __syncwarp();
-            if (elect_one()) {
-              mbar_expect_tx(&bfull[sb], b_slot);               // the box always spans G*Np rows (zero fill past the end)
-              tma_load_2d(b_base + sb * b_slot, &tmW, &bfull[sb], tap.b_c0 + kc * kBlockK - tap.a_c0,
-                          (jb.tap_begin + tp) * NP);
-            }
-            adv();
-          }
-        }
-        if (jb.nchunks == jins) load_gamma();
-      }
-      if (gk) load_gamma();
-    } else if (warp == kMmaWarp) {
-      // ===================== MMA issuer =====================
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      const bool dbg = P.dbg != nullptr && blockIdx.x == 0;
-      long long t_a = 0, t_b = 0, t_buf = 0, t_x2 = 0, t0 = 0, n_it = 0;
-      const long long t_begin = clock64();
-      const uint32_t hi_a = desc_hi(sbo), hi_b = desc_hi(1024);
-      auto adv_a = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
-      auto adv_b = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
-      auto gdn_of = [&](int j) {            // norm(j) = x^2 . gamma^T, in place over acc(j)
-        const int bsel = j & 1;
-        if (dbg) t0 = clock64();
-        mbar_wait(&x2_ready[bsel], (j >> 1) & 1);
-        if (dbg) t_x2 += clock64() - t0;
-        tc_fence_after();
-        for (int kb = 0; kb < gk; ++kb) {
-          mbar_wait(&afull[sa], pa);
-          mbar_wait(&bfull[sb], pb);
-          tc_fence_after();
-          __syncwarp();
-          const uint32_t alo = desc_lo(smem_base + sa * a_slot), blo = desc_lo(b_base + sb * b_slot);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16_lh(tmem_base + bsel * kBufCols, alo + 2 * k, hi_b, blo + 2 * k, hi_b, kIdesc, (kb | k) != 0);
-            tc_commit(&bempty[sb]);
-            tc_commit(&aempty[sa]);
-          }
-          adv_a(); adv_b();
-        }
-        __syncwarp();
-        if (elect_one()) tc_commit(&norm_full[bsel]);
-      };
-      for (int it = 0; it < ntiles_cta; ++it) {
-        const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-        const Job jb = P.jobs[tc.job];
-        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
-        const int bsel = it & 1;
-        if (dbg) t0 = clock64();
-        mbar_wait(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
-        if (dbg) t_buf += clock64() - t0;
-        tc_fence_after();
-        bool first = true;
-        for (int ci = 0; ci < jb.nchunks; ++ci) {
-          if (ci == jins) gdn_of(it - 1);
-          const int kc = jb.kc0 + ci;
-          if (dbg) t0 = clock64();
-          mbar_wait(&afull[sa], pa);
-          if (dbg) t_a += clock64() - t0;
-          const uint32_t a_addr = smem_base + sa * a_slot;
-          for (int tp = 0; tp < jb.ntaps; tp += G) {
-            if (!tap_active(P.taps[jb.tap_begin + tp], kc)) continue;
-            if (dbg) t0 = clock64();
-            mbar_wait(&bfull[sb], pb);
-            if (dbg) { t_b += clock64() - t0; ++n_it; }
-            tc_fence_after();
-            __syncwarp();
-            const int ng = (jb.ntaps - tp < G) ? jb.ntaps - tp : G;
-            const uint32_t bslot_lo = desc_lo(b_base + sb * b_slot);
-            uint32_t alo[4];                                   // computed warp-uniformly, outside the elected branch
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              alo[g] = (g < ng) ? desc_lo(a_addr + P.taps[jb.tap_begin + tp + g].halo_off) : 0u;
-            if (elect_one()) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (g < ng) {
-                  const uint32_t blo = bslot_lo + (uint32_t)g * (kBTileBytes >> 4);
-#pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k)
-                    umma_bf16_lh(tmem_base + bsel * kBufCols, alo[g] + 2 * k, hi_a, blo + 2 * k, hi_b, kIdesc,
-                                 !(first && g == 0 && k == 0));
-                }
-              }
-              tc_commit(&bempty[sb]);
-            }
-            first = false;
-            adv_b();
-          }
-          __syncwarp();
-          if (elect_one()) tc_commit(&aempty[sa]);            // region consumed by all of its taps
-          adv_a();
-        }
-        __syncwarp();
-        if (elect_one()) tc_commit(&acc_full[bsel]);
-        if (jb.nchunks == jins) gdn_of(it - 1);
-      }
-      if (gk) gdn_of(ntiles_cta - 1);
-      if (dbg && lane == 0) {
-        P.dbg[0] = (unsigned long long)(clock64() - t_begin); P.dbg[1] = (unsigned long long)t_b;
-        P.dbg[2] = (unsigned long long)t_buf; P.dbg[3] = (unsigned long long)t_x2; P.dbg[4] = (unsigned long long)n_it;
-        P.dbg[5] = (unsigned long long)ntiles_cta; P.dbg[6] = (unsigned long long)t_a;
-      }
-    }
-  } else {
-    // ===================== epilogue warps =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
-    EpiRing R;
-    R.pair_store = 1;
-    R.ring_base = smem_base; R.slot_bytes = a_slot; R.nslots = (uint32_t)SA; R.empty_bar = aempty;
-    R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
-    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 1; R.insert_after = kHaloInsert;
-    epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// ---------------------------------------------------------------------------------
-// CTA-pair variant of the halo kernel: two CTAs of a cluster (one SM pair) work on two adjacent tiles with
-// tcgen05.mma.cta_group::2 (M = 256).  Each CTA loads its own activation region but only HALF of every
-// weight / gamma tile (rows rank*Np/2 ..), so the L2 -> SM weight traffic and the shared memory a weight stage
-// occupies are halved (twice the stages in flight for the same bytes).  The leader CTA (rank 0) issues all MMAs;
-// TMA completions of both CTAs land on the leader's "full" barriers, tcgen05.commit multicasts the "empty" /
-// "accumulator ready" arrivals to both CTAs, and the epilogue warps of the peer reach the leader's x2_ready /
-// buf_free barriers through shared::cluster addresses.
-// ---------------------------------------------------------------------------------
-template <int NP>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
-  constexpr int kBHalfBytes = (NP / 2) * kBlockK * 2;
-  constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int SA = P.SA, SB = P.SB;
-  const uint32_t a_slot = (uint32_t)P.a_slot_bytes;
-  const int G = P.G;
-  const uint32_t b_slot = (uint32_t)G * kBHalfBytes;                  // G taps x half of the weight rows per slot
-  const uint32_t b_base = smem_base + (uint32_t)SA * a_slot;
-  uint8_t* aux = smem_al + (size_t)SA * a_slot + (size_t)SB * b_slot;
+  const uint32_t b_base = smem_base + (uint32_t)SA * kATileBytes;
+  uint8_t* aux = smem_al + (size_t)SA * kATileBytes + (size_t)SB * kBSlotBytes;
   uint64_t* afull = reinterpret_cast<uint64_t*>(aux);                  // [kMaxStages]  (leader's are the live ones)
   uint64_t* aempty = afull + kMaxStages;
-  uint64_t* bfull = aempty + kMaxStages;
+  uint64_t* bfull = aempty + kMaxStages;                               // leader's
   uint64_t* bempty = bfull + kMaxStages;
-  uint64_t* acc_full = bempty + kMaxStages;                            // [2]
-  uint64_t* buf_free = acc_full + 2;                                   // leader only
-  uint64_t* x2_ready = buf_free + 2;                                   // leader only
-  uint64_t* norm_full = x2_ready + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_full + 2);
+  uint64_t* acc_full = bempty + kMaxStages;                            // [1] MMA -> epilogues (multicast)
+  uint64_t* acc_free = acc_full + 1;                                   // [1] leader only: epilogues of both CTAs -> MMA
+  uint64_t* x2_ready = acc_free + 1;                                   // [1] leader only
+  uint64_t* norm_full = x2_ready + 1;                                  // [1] multicast, one phase per norm chunk
+  uint64_t* norm_free = norm_full + 1;                                 // [1] leader only
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(norm_free + 1);
   float* s_bias = reinterpret_cast<float*>(aux + 512);
   float* s_beta = s_bias + NP * P.nbias;
 
@@ -1573,14 +1143,13 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool leader = rank == 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
-    for (int i = 0; i < SB; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&buf_free[i], 2 * kEpiThreads);                        // epilogue threads of both CTAs
-      mbar_init(&x2_ready[i], 2 * kEpiThreads);
-      mbar_init(&norm_full[i], 1);
-    }
+    for (int s = 0; s < SA; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 2 * kEpiThreads);
+    mbar_init(x2_ready, 2 * kEpiThreads);
+    mbar_init(norm_full, 1);
+    mbar_init(norm_free, 2 * kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
@@ -1591,205 +1160,301 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   for (int i = threadIdx.x; i < NP; i += kThreads) s_beta[i] = (gdn && P.beta) ? P.beta[i] : 1.f;
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();                                                  // both CTAs' barriers are initialised
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int gk = gdn ? P.gdn_kblocks : 0;
+  const int gk = gdn ? GK : 0;
   const int npairs = (int)gridDim.x >> 1, pi = (int)blockIdx.x >> 1;
   const int total_super = P.super_per_job * P.njobs;
-  const int nt = (total_super - pi + npairs - 1) / npairs;             // super tiles of this pair
-  const uint32_t sub_bytes = (uint32_t)(P.RW * P.RH * 128);
-  const uint32_t region_bytes = sub_bytes * (uint32_t)P.ndx;
-  const uint32_t sbo = (uint32_t)P.RW * 128u;
+  const int nt = (total_super - pi + npairs - 1) / npairs;
   const uint32_t afull_L = mapa_shared(smem_u32(afull), 0), bfull_L = mapa_shared(smem_u32(bfull), 0);
-  auto tap_active = [](const Tap& t, int kc) { const int c = kc * kBlockK; return c >= t.a_c0 && c < t.a_c0 + t.nkc * kBlockK; };
 
   if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == kProdWarp) {
-      // ===================== A-region producer (both CTAs: own tile, completion on the leader's barrier) ==========
+      // ===================== A producer: activation tiles (both CTAs) =====================
       uint32_t sa = 0, pa = 0;
       auto adv = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
-      auto reserve_gdn = [&]() {            // gk A slots become the x^2 operand tiles of the epilogue warps
-        for (int kb = 0; kb < gk; ++kb) {
-          mbar_wait(&aempty[sa], pa ^ 1);
-          __syncwarp();
-          if (leader && elect_one()) mbar_arrive(&afull[sa]);
-          adv();
-        }
-      };
+      const int cs = P.mode == 2 ? 2 : 1;
+      int cur_job = -1, ntaps = 0, tap_begin = 0;
+      uint32_t my_w0 = 0, my_w1 = 0;
       for (int it = 0; it < nt; ++it) {
         const TileCoord tc = decode_tile2(P, pi + it * npairs, (int)rank);
-        const Job jb = P.jobs[tc.job];
-        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
-        for (int ci = 0; ci < jb.nchunks; ++ci) {
-          if (ci == jins) reserve_gdn();
-          mbar_wait(&aempty[sa], pa ^ 1);
-          __syncwarp();
-          if (elect_one()) {
-            if (leader) mbar_expect_tx(&afull[sa], 2 * region_bytes);
-            for (int sx = 0; sx < P.ndx; ++sx)
-              tma_load_4d_cg2(smem_base + sa * a_slot + (uint32_t)sx * sub_bytes, &tmA, afull_L + 8u * sa,
-                              (jb.kc0 + ci) * kBlockK, tc.x0 + P.dxmin + sx, tc.y0 + P.dymin, tc.n0);
+        if (tc.job != cur_job) {
+          cur_job = tc.job;
+          ntaps = P.jobs[cur_job].ntaps; tap_begin = P.jobs[cur_job].tap_begin;
+          if (lane < ntaps) {
+            const Tap t = P.taps[tap_begin + lane];
+            my_w0 = (uint32_t)(uint8_t)t.dx | ((uint32_t)(uint8_t)t.dy << 8) | ((uint32_t)t.nkc << 24);
+            my_w1 = (uint32_t)t.a_c0;
           }
-          adv();
         }
-        if (jb.nchunks == jins) reserve_gdn();
-      }
-      if (gk) reserve_gdn();
-    } else if (warp == kProdBWarp) {
-      // ===================== B producer (both CTAs: half of the weight / gamma rows each) =====================
-      uint32_t sb = 0, pb = 0;
-      const int row_half = (int)rank * (NP / 2);
-      auto adv = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
-      auto load_gamma = [&]() {
-        for (int kb = 0; kb < gk; ++kb) {
-          mbar_wait(&bempty[sb], pb ^ 1);
-          __syncwarp();
-          if (elect_one()) {
-            if (leader) mbar_expect_tx(&bfull[sb], 2 * kBHalfBytes);
-            tma_load_2d_cg2(b_base + sb * b_slot, &tmG, bfull_L + 8u * sb, kb * kBlockK, row_half);
-          }
-          adv();
-        }
-      };
-      for (int it = 0; it < nt; ++it) {
-        const int job = (pi + it * npairs) / P.super_per_job;
-        const Job jb = P.jobs[job];
-        const int jins = (gk && it > 0) ? (jb.nchunks < kHaloInsert ? jb.nchunks : kHaloInsert) : -1;
-        for (int ci = 0; ci < jb.nchunks; ++ci) {
-          if (ci == jins) load_gamma();
-          const int kc = jb.kc0 + ci;
-          for (int tp = 0; tp < jb.ntaps; tp += G) {          // G == 1 unless every tap covers every chunk
-            const Tap tap = P.taps[jb.tap_begin + tp];
-            if (!tap_active(tap, kc)) continue;
-            const int ng = (jb.ntaps - tp < G) ? jb.ntaps - tp : G;
-            mbar_wait(&bempty[sb], pb ^ 1);
-            __syncwarp();
+        const int x0 = tc.x0 * cs, y0 = tc.y0 * cs;
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const uint32_t w0 = __shfl_sync(0xffffffffu, my_w0, tp), w1 = __shfl_sync(0xffffffffu, my_w1, tp);
+          const int dx = (int)(int8_t)(w0 & 0xff), dy = (int)(int8_t)((w0 >> 8) & 0xff);
+          const int nkc = (int)(w0 >> 24), a_c0 = (int)w1;
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&aempty[sa], pa ^ 1);
             if (elect_one()) {
-              if (leader) mbar_expect_tx(&bfull[sb], (uint32_t)(2 * ng) * kBHalfBytes);
-              for (int g = 0; g < ng; ++g)
-                tma_load_2d_cg2(b_base + sb * b_slot + (uint32_t)g * kBHalfBytes, &tmW, bfull_L + 8u * sb,
-                                tap.b_c0 + kc * kBlockK - tap.a_c0, (jb.tap_begin + tp + g) * NP + row_half);
+              if (leader) mbar_expect_tx(&afull[sa], 2 * kATileBytes);
+              tma_load_4d_cg2(smem_base + sa * kATileBytes, &tmA, afull_L + 8u * sa, a_c0 + kc * kBlockK, x0 + dx, y0 + dy, tc.n0);
             }
             adv();
           }
         }
-        if (jb.nchunks == jins) load_gamma();
+        for (int kb = 0; kb < gk; ++kb) adv();       // the x^2 tiles of this tile (written by the epilogue warps)
       }
-      if (gk) load_gamma();
-    } else if (warp == kMmaWarp && leader) {
-      // ===================== MMA issuer (leader CTA only) =====================
-      // Lane t keeps tap t of the current job in registers (A-descriptor offset of its shifted start and its K
-      // range); the loop body has no constant-bank loads with computed indices.
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      int SA_r = SA, SB_r = SB, G_r = G;
-      asm volatile("" : "+r"(SA_r), "+r"(SB_r), "+r"(G_r));
-      const uint32_t hi_a = desc_hi(sbo), hi_b = desc_hi(1024);
-      const uint32_t a_lo0 = desc_lo(smem_base), b_lo0 = desc_lo(b_base);
-      const uint32_t a_slot_lo = a_slot >> 4, b_slot_lo = b_slot >> 4;
-      uint32_t sa_lo = 0, sb_lo = 0;                           // slot index * slot size (16-byte units)
-      auto adv_a = [&]() { ++sa; sa_lo += a_slot_lo; if (sa == (uint32_t)SA_r) { sa = 0; sa_lo = 0; pa ^= 1; } };
-      auto adv_b = [&]() { ++sb; sb_lo += b_slot_lo; if (sb == (uint32_t)SB_r) { sb = 0; sb_lo = 0; pb ^= 1; } };
-      int cur_job = -1, ntaps = 0, nchunks = 0, kc0 = 0;
-      int my_a_c0 = 1 << 30, my_a_c1 = 0;
-      uint32_t my_lo = 0;
-      // (no cycle counters here: the MMA warp runs with 64 registers, six 64-bit counters spilled and cost 20 %)
-      auto gdn_of = [&](int j) {            // norm(j) = x^2 . gamma^T, in place over acc(j), both tiles of the pair
-        const int bsel = j & 1;
-        mbar_wait_cl(&x2_ready[bsel], (j >> 1) & 1);
-        tc_fence_after();
-        for (int kb = 0; kb < gk; ++kb) {
-          mbar_wait_cl(&afull[sa], pa);
-          mbar_wait_cl(&bfull[sb], pb);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t alo = a_lo0 + sa_lo, blo = b_lo0 + sb_lo;
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16_lh_cg2(tmem_base + bsel * kBufCols, alo + 2 * k, hi_b, blo + 2 * k, hi_b, kIdesc2, (kb | k) != 0);
-            tc_commit_mc(&bempty[sb]);
-            tc_commit_mc(&aempty[sa]);
-          }
-          adv_a(); adv_b();
-        }
-        if (elect_one()) tc_commit_mc(&norm_full[bsel]);
-      };
+    } else if (warp == kProdBWarp) {
+      // ===================== B producer: weight rows of both column halves, gamma rows (both CTAs) ============
+      uint32_t sb = 0, pb = 0;
+      auto adv = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
+      const int row_half = (int)rank * (NH / 2), row_g = (int)rank * (kWideNC / 2);
+      int cur_job = -1, ntaps = 0, tap_begin = 0;
+      uint32_t my_w0 = 0, my_w1 = 0;
       for (int it = 0; it < nt; ++it) {
         const int job = (pi + it * npairs) / P.super_per_job;
         if (job != cur_job) {
           cur_job = job;
-          ntaps = P.jobs[job].ntaps; nchunks = P.jobs[job].nchunks; kc0 = P.jobs[job].kc0;
-          my_a_c0 = 1 << 30; my_a_c1 = 0;
+          ntaps = P.jobs[cur_job].ntaps; tap_begin = P.jobs[cur_job].tap_begin;
           if (lane < ntaps) {
-            const Tap t = P.taps[P.jobs[job].tap_begin + lane];
-            my_a_c0 = t.a_c0; my_a_c1 = t.a_c0 + t.nkc * kBlockK; my_lo = (uint32_t)t.halo_off >> 4;
+            const Tap t = P.taps[tap_begin + lane];
+            my_w0 = (uint32_t)t.nkc;
+            my_w1 = (uint32_t)t.b_c0;
           }
         }
-        const int jins = (gk && it > 0) ? (nchunks < kHaloInsert ? nchunks : kHaloInsert) : -1;
-        const int bsel = it & 1;
-        const uint32_t d_tmem = tmem_base + bsel * kBufCols;
-        mbar_wait_cl(&buf_free[bsel], ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        bool first = true;
-        for (int ci = 0; ci < nchunks; ++ci) {
-          if (ci == jins) gdn_of(it - 1);
-          const int c = (kc0 + ci) * kBlockK;
-          const uint32_t mask = __ballot_sync(0xffffffffu, c >= my_a_c0 && c < my_a_c1);   // taps covering this chunk
-          mbar_wait_cl(&afull[sa], pa);
-          const uint32_t a_reg_lo = a_lo0 + sa_lo;
-          for (int tp = 0; tp < ntaps; tp += G_r) {
-            if (!((mask >> tp) & 1u)) continue;
-            uint32_t alo[4];                                   // A descriptors of the (up to 4) taps of this slot
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              alo[g] = 0;
-              if (g < G_r) alo[g] = a_reg_lo + __shfl_sync(0xffffffffu, my_lo, (tp + g) & 31);
-            }
-            const int ng = (ntaps - tp < G_r) ? ntaps - tp : G_r;
-            mbar_wait_cl(&bfull[sb], pb);
-            tc_fence_after();
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const int nkc = (int)__shfl_sync(0xffffffffu, my_w0, tp), b_c0 = (int)__shfl_sync(0xffffffffu, my_w1, tp);
+          const int brow = (tap_begin + tp) * NP + row_half;
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&bempty[sb], pb ^ 1);
             if (elect_one()) {
-              const uint32_t bslot_lo = b_lo0 + sb_lo;
+              const uint32_t dst = b_base + sb * kBSlotBytes;
+              if (leader) mbar_expect_tx(&bfull[sb], 2 * kBSlotBytes);
+              tma_load_2d_cg2(dst, &tmW, bfull_L + 8u * sb, b_c0 + kc * kBlockK, brow);
+              tma_load_2d_cg2(dst + kBHalfOff, &tmW, bfull_L + 8u * sb, b_c0 + kc * kBlockK, brow + NH);
+            }
+            adv();
+          }
+        }
+        if (gk) {
+          for (int c = 0; c < NCH; ++c) {
+            for (int j = 0; j < GITEMS; ++j) {
+              mbar_wait(&bempty[sb], pb ^ 1);
+              if (elect_one()) {
+                const uint32_t dst = b_base + sb * kBSlotBytes;
+                if (leader) mbar_expect_tx(&bfull[sb], 2 * kWideGPI * kGTileBytes);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (g < ng) {
-                  const uint32_t blo = bslot_lo + (uint32_t)g * (kBHalfBytes >> 4);
+                for (int kbi = 0; kbi < kWideGPI; ++kbi)
+                  tma_load_2d_cg2(dst + kbi * kGTileBytes, &tmG, bfull_L + 8u * sb, (j * kWideGPI + kbi) * kBlockK,
+                                  c * kWideNC + row_g);
+              }
+              adv();
+            }
+          }
+        }
+      }
+    } else if (warp == kMmaWarp && leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      auto adv_a = [&]() { if (++sa == (uint32_t)SA) { sa = 0; pa ^= 1; } };
+      auto adv_b = [&]() { if (++sb == (uint32_t)SB) { sb = 0; pb ^= 1; } };
+      const uint32_t hi = desc_hi(1024);
+      const uint32_t a_lo0 = desc_lo(smem_base), b_lo0 = desc_lo(b_base);
+      int cur_job = -1, nkb = 0;
+      for (int it = 0; it < nt; ++it) {
+        const int job = (pi + it * npairs) / P.super_per_job;
+        if (job != cur_job) { cur_job = job; nkb = P.jobs[cur_job].nkb; }
+        mbar_wait_cl(acc_free, ((uint32_t)it & 1u) ^ 1u);          // the previous tile's accumulator has been read
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_cl(&afull[sa], pa);
+          mbar_wait_cl(&bfull[sb], pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t alo = a_lo0 + sa * (uint32_t)(kATileBytes >> 4), blo = b_lo0 + sb * (uint32_t)(kBSlotBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              umma_bf16_lh_cg2(tmem_base, alo + 2 * k, hi, blo + 2 * k, hi, kIdescH, (kb | k) != 0);
+              umma_bf16_lh_cg2(tmem_base + NH, alo + 2 * k, hi, blo + (uint32_t)(kBHalfOff >> 4) + 2 * k, hi, kIdescH, (kb | k) != 0);
+            }
+            tc_commit_mc(&aempty[sa]);
+            tc_commit_mc(&bempty[sb]);
+          }
+          adv_a(); adv_b();
+        }
+        if (elect_one()) tc_commit_mc(acc_full);
+        if (gk) {
+          mbar_wait_cl(x2_ready, (uint32_t)it & 1u);                // x^2 tiles of both CTAs are in the next gk A slots
+          tc_fence_after();
+          for (int c = 0; c < NCH; ++c) {
+            const uint32_t g = (uint32_t)(it * NCH + c);
+            mbar_wait_cl(norm_free, (g & 1u) ^ 1u);                 // the previous norm chunk has been read
+            tc_fence_after();
+            for (int j = 0; j < GITEMS; ++j) {
+              mbar_wait_cl(&bfull[sb], pb);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t blo = b_lo0 + sb * (uint32_t)(kBSlotBytes >> 4);
+#pragma unroll
+                for (int kbi = 0; kbi < kWideGPI; ++kbi) {
+                  const int kb = j * kWideGPI + kbi;
+                  uint32_t xs = sa + (uint32_t)kb; if (xs >= (uint32_t)SA) xs -= (uint32_t)SA;
+                  const uint32_t alo = a_lo0 + xs * (uint32_t)(kATileBytes >> 4);
 #pragma unroll
                   for (int k = 0; k < kBlockK / 16; ++k)
-                    umma_bf16_lh_cg2(d_tmem, alo[g] + 2 * k, hi_a, blo + 2 * k, hi_b, kIdesc2, !(first && g == 0 && k == 0));
+                    umma_bf16_lh_cg2(tmem_base + NP, alo + 2 * k, hi, blo + (uint32_t)(kbi * (kGTileBytes >> 4)) + 2 * k, hi,
+                                     kIdescG, (kb | k) != 0);
                 }
+                tc_commit_mc(&bempty[sb]);
               }
-              tc_commit_mc(&bempty[sb]);
+              adv_b();
             }
-            first = false;
-            adv_b();
+            if (elect_one()) tc_commit_mc(norm_full);
           }
-          if (elect_one()) tc_commit_mc(&aempty[sa]);         // both regions consumed by all of their taps
-          adv_a();
+          for (int kb = 0; kb < gk; ++kb) {                          // hand the x^2 slots back to the A producers
+            if (elect_one()) tc_commit_mc(&aempty[sa]);
+            adv_a();
+          }
         }
-        if (elect_one()) tc_commit_mc(&acc_full[bsel]);
-        if (nchunks == jins) gdn_of(it - 1);
       }
-      if (gk) gdn_of(nt - 1);
     }
   } else {
     // ===================== epilogue warps (both CTAs, own tile) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
-    EpiRing R;
-    R.pair_store = 1;
-    R.ring_base = smem_base; R.slot_bytes = a_slot; R.nslots = (uint32_t)SA; R.empty_bar = aempty;
-    R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
-    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 1; R.insert_after = kHaloInsert;
-    R.t_first = pi; R.t_stride = npairs; R.rank = (int)rank;
-    R.buf_free_cl = mapa_shared(smem_u32(buf_free), 0); R.x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0);
-    epilogue_role<NP, true>(P, R, tmem_base, gk, nt, warp, lane);
+    const int q = warp & 3, h = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int xi = r & (P.TW - 1), yi = (r >> P.tw_shift) & (P.TH - 1), ni = r >> (P.tw_shift + P.th_shift);
+    const bool igdn = (P.act == LDIC_ACT_IGDN);
+    const uint32_t acc_free_cl = mapa_shared(smem_u32(acc_free), 0), x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0),
+                   norm_free_cl = mapa_shared(smem_u32(norm_free), 0);
+    const uint32_t tacc = tmem_base + lane_sel, tnorm = tmem_base + lane_sel + NP;
+    const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
+    const bool odd = lane & 1;
+    uint32_t apos = 0;                           // A-ring position (mod SA) of the tile's first stage
+    for (int it = 0; it < nt; ++it) {
+      const TileCoord tc = decode_tile2(P, pi + it * npairs, (int)rank);
+      const Job jb = P.jobs[tc.job];
+      const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
+      const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B) && !P.dbg_nostore;
+      const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
+                                 (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
+      const long long pb_other = __shfl_xor_sync(0xffffffffu, pix_base, 1);
+      const bool valid_other = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+      const float* sb = s_bias + (P.nbias > 1 ? tc.job * NP : 0);
+      // 32 finished columns [col, col+32) of this thread's pixel -> global (fp32: own sectors; bf16: lane-pair
+      // transposed stores, 64 contiguous bytes per pixel per instruction)
+      auto store32 = [&](const float (&v)[32], int col) {
+        if (P.out_f32) {
+          if (valid) {
+            float* dst = reinterpret_cast<float*>(P.out) + pix_base + col;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st_global_v8(dst + 8 * j, &v[8 * j]);
+          }
+        } else {
+          uint32_t pk[16], rv[8], d1[8], d2[8];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) rv[e] = __shfl_xor_sync(0xffffffffu, odd ? pk[e] : pk[8 + e], 1);
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out) + col + (odd ? 16 : 0);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { d1[e] = odd ? rv[e] : pk[e]; d2[e] = odd ? pk[8 + e] : rv[e]; }
+          if (odd ? valid_other : valid) st_global_v8(out + (odd ? pb_other : pix_base), d1);
+          if (odd ? valid : valid_other) st_global_v8(out + (odd ? pix_base : pb_other), d2);
+        }
+      };
+      apos += (uint32_t)jb.nkb; apos %= (uint32_t)SA;               // first x^2 slot of this tile
+      mbar_wait(acc_full, (uint32_t)it & 1u);
+      tc_fence_after();
+      if (gk) {
+        // ---- pass 1: x = acc + bias; x^2 -> bf16 -> the tile's gk A slots.  All earlier users of those slots are MMAs
+        // that completed before acc_full did (in-order tensor pipe), so no slot barrier is needed here. ----
+#pragma unroll 1
+        for (int cb = 0; cb < NH / 32; ++cb) {
+          const int col = h * NH + cb * 32;
+          uint32_t xu[32];
+          tmem_ld32(tacc + col, xu);
+          tmem_ld_wait();
+          uint32_t xs = apos + (uint32_t)(col >> 6); if (xs >= (uint32_t)SA) xs -= (uint32_t)SA;
+          const uint32_t a_addr = smem_base + xs * kATileBytes + row_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { x8[e] = __uint_as_float(xu[8 * j + e]) + sb[col + 8 * j + e]; x8[e] *= x8[e]; }
+            const uint32_t chunk = (uint32_t)(((col & 63) >> 3) + j);
+            st_shared_v4(a_addr + ((chunk ^ rx) << 4), pack_bf16x2(x8[0], x8[1]), pack_bf16x2(x8[2], x8[3]),
+                         pack_bf16x2(x8[4], x8[5]), pack_bf16x2(x8[6], x8[7]));
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive_cluster(x2_ready_cl);
+        // ---- pass 2, one norm chunk at a time: out = x * rsqrt(norm + beta)  (IGDN: x * sqrt) ----
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const uint32_t g = (uint32_t)(it * NCH + c);
+          const int col = c * kWideNC + h * (kWideNC / 2);           // this thread's 64 columns of the chunk
+          mbar_wait(norm_full, g & 1u);
+          tc_fence_after();
+          uint32_t n0[32], n1[32], x0[32];
+          tmem_ld32(tnorm + h * (kWideNC / 2), n0);
+          tmem_ld32(tnorm + h * (kWideNC / 2) + 32, n1);
+          tmem_ld32(tacc + col, x0);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive_cluster(norm_free_cl);                         // the norm buffer can take the next chunk
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = __uint_as_float(x0[k]) + sb[col + k];
+            const float nrm = __uint_as_float(n0[k]) + s_beta[col + k];
+            const float rs = rsqrt_approx(nrm);
+            v[k] = x * (igdn ? nrm * rs : rs);
+          }
+          tmem_ld32(tacc + col + 32, x0);                            // second half of x, in flight under the stores
+          store32(v, col);
+          tmem_ld_wait();
+          if (c == NCH - 1) { tc_fence_before(); mbar_arrive_cluster(acc_free_cl); }   // the accumulator can take the next tile
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = __uint_as_float(x0[k]) + sb[col + 32 + k];
+            const float nrm = __uint_as_float(n1[k]) + s_beta[col + 32 + k];
+            const float rs = rsqrt_approx(nrm);
+            v[k] = x * (igdn ? nrm * rs : rs);
+          }
+          store32(v, col + 32);
+        }
+        apos += (uint32_t)gk; apos %= (uint32_t)SA;
+      } else {
+        // ---- plain epilogue: bias + activation ----
+#pragma unroll 1
+        for (int cb = 0; cb < NH / 32; ++cb) {
+          const int col = h * NH + cb * 32;
+          uint32_t xu[32];
+          tmem_ld32(tacc + col, xu);
+          tmem_ld_wait();
+          if (cb == NH / 32 - 1) { tc_fence_before(); mbar_arrive_cluster(acc_free_cl); }
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            float x = __uint_as_float(xu[k]) + sb[col + k];
+            if (P.act == LDIC_ACT_RELU) x = fmaxf(x, 0.f);
+            else if (P.act == LDIC_ACT_LEAKY02) x = x > 0.f ? x : 0.2f * x;
+            v[k] = x;
+          }
+          store32(v, col);
+        }
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();                      // the peer's shared memory and barriers stay alive until both CTAs are done
+  cluster_sync_all();
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc_cg2(tmem_base, kTmemCols);
@@ -1816,16 +1481,28 @@ constexpr int kRawW = 2 * kFirstTW + 4 + kRawX0;    // 136 input columns per box
 constexpr int kRawH = 2 * kFirstTH + 3;             // 7 input rows
 constexpr int kRawBytes = 3 * kRawH * kRawW * 4;    // 11088
 constexpr int kRawSlot = (kRawBytes + 127) / 128 * 128;
+// uint8 image (eval_net.py:84: x = (u/255)*2-1): the box starts 16 columns left of the tile (16-byte aligned start),
+// rows are 160 bytes; out-of-image bytes are zero-filled by TMA but a zero LEVEL is x = -1, not the ZeroPad2d's 0,
+// so the patch builders mask the out-of-image taps themselves.
+constexpr int kRawX08 = 16;
+constexpr int kRawW8 = (2 * kFirstTW + 4 + kRawX08 + 15) / 16 * 16;   // 160
+constexpr int kRawBytes8 = 3 * kRawH * kRawW8;                       // 3360
+static_assert(kRawBytes8 <= kRawSlot, "uint8 boxes share the raw ring slots");
 constexpr int kFirstK = 75;
 constexpr int kBuildThreads = 64;                   // warps 10 and 11
 
+__device__ __forceinline__ uint32_t ld_shared_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
 
-template <int NP>
+template <int NP, bool U8 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
@@ -1904,9 +1581,9 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int rs = it & 1;
         mbar_wait(&rempty[rs], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(&rfull[rs], kRawBytes);
-          // x start 4 columns left of the tile: TMA needs a 16-byte aligned start in the innermost dimension
-          tma_load_4d(raw_base + rs * kRawSlot, &tmX, &rfull[rs], 2 * tc.x0 - kRawX0, 2 * tc.y0 - 1, 0, tc.n0);
+          mbar_expect_tx(&rfull[rs], U8 ? kRawBytes8 : kRawBytes);
+          // x start 4 (16) columns left of the tile: TMA needs a 16-byte aligned start in the innermost dimension
+          tma_load_4d(raw_base + rs * kRawSlot, &tmX, &rfull[rs], 2 * tc.x0 - (U8 ? kRawX08 : kRawX0), 2 * tc.y0 - 1, 0, tc.n0);
         }
       }
     } else if (warp == kMmaWarp) {
@@ -1971,11 +1648,25 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(&empty_bar[s1], (((p0 + 1) / (uint32_t)S) & 1u) ^ 1u);
         const uint32_t a0 = ring_base + s0 * kATileBytes, a1 = ring_base + s1 * kATileBytes;
         const uint32_t raw = raw_base + rs * kRawSlot;
+        int ix0 = 0, iy00 = 0;
+        if constexpr (U8) {
+          const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
+          ix0 = 2 * (tc.x0 + tb) - 1; iy00 = 2 * tc.y0 - 1;             // image position of tap (0,0) of row 0
+        }
 #pragma unroll
         for (int ly = 0; ly < kFirstTH; ++ly) {
           const int r = ly * kFirstTW + tb;                             // tile row = TMEM lane
-          const uint32_t src = raw + (uint32_t)((2 * ly) * kRawW + 2 * tb + (kRawX0 - 1)) * 4u;
+          const uint32_t src = U8 ? raw + (uint32_t)((2 * ly) * kRawW8 + 2 * tb + (kRawX08 - 1))
+                                  : raw + (uint32_t)((2 * ly) * kRawW + 2 * tb + (kRawX0 - 1)) * 4u;
           const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
+          uint32_t okx = 0, oky = 0;                                    // uint8: taps inside the image (bit kx / ky)
+          if constexpr (U8) {
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+              okx |= (uint32_t)((unsigned)(ix0 + t) < (unsigned)P.tail_W) << t;
+              oky |= (uint32_t)((unsigned)(iy00 + 2 * ly + t) < (unsigned)P.tail_H) << t;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 10; ++j) {                                // 16-byte chunks: k = 8j .. 8j+7
             uint32_t pk[4];
@@ -1986,7 +1677,16 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               for (int u = 0; u < 2; ++u) {
                 const int k = 8 * j + 2 * e + u;                        // k = (ky*5 + kx)*3 + c
                 v[u] = 0.f;
-                if (k < kFirstK) v[u] = ld_shared_f32(src + (uint32_t)(((k % 3) * kRawH + k / 15) * kRawW + (k / 3) % 5) * 4u);
+                if (k < kFirstK) {
+                  if constexpr (U8) {
+                    // bf16((u/255)*2-1) == bf16(fma(u, 2/255, -1)) for all 256 levels (tests/test_oracle_golden.py)
+                    const float lv = (float)ld_shared_u8(src + (uint32_t)(((k % 3) * kRawH + k / 15) * kRawW8 + (k / 3) % 5));
+                    const bool ok = ((okx >> ((k / 3) % 5)) & (oky >> (k / 15)) & 1u) != 0;
+                    v[u] = ok ? __fmaf_rn(lv, 2.f / 255.f, -1.f) : 0.f;
+                  } else {
+                    v[u] = ld_shared_f32(src + (uint32_t)(((k % 3) * kRawH + k / 15) * kRawW + (k / 3) % 5) * 4u);
+                  }
+                }
               }
               pk[e] = pack_bf16x2(v[0], v[1]);
             }
@@ -2007,7 +1707,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     R.pair_store = 0;
     R.ring_base = ring_base; R.slot_bytes = kATileBytes; R.nslots = (uint32_t)S; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
-    R.s_bias = s_bias; R.s_beta = s_beta; R.use_chunks = 0; R.insert_after = P.gdn_insert;
+    R.s_bias = s_bias; R.s_beta = s_beta; R.insert_after = P.gdn_insert;
     epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
   }
 
@@ -2038,15 +1738,17 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
+enum MapType { MAP_BF16_SW128 = 0, MAP_F32 = 1, MAP_U8 = 2 };   // operand tiles (swizzled) / raw image boxes (linear)
 int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr, bool f32_linear = false) {
+               const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr, int type = MAP_BF16_SW128) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(LDIC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   if (elem_strides) for (int i = 0; i < rank; ++i) es[i] = elem_strides[i];
-  CUresult r = enc(m, f32_linear ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+  const bool linear = type != MAP_BF16_SW128;
+  CUresult r = enc(m, type == MAP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (type == MAP_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), (cuuint32_t)rank,
                    const_cast<void*>(base), dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   f32_linear ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   linear ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(LDIC_ECUDA, "cuTensorMapEncodeTiled failed (%d) rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,
@@ -2136,6 +1838,7 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
     }
     case LDIC_CONV_FIRST_5x5S2: {   // x is the NCHW fp32 image; K = (ky*5+kx)*3 + c, 75 padded to 128 in the packed weights
       if (d->Cin != 3 || d->Cin_pad != 128) return fail(LDIC_EINVAL, "first conv: Cin must be 3 and Cin_pad 128");
+      if (d->aux0 != 0 && d->aux0 != 1) return fail(LDIC_EINVAL, "first conv: aux0 selects the image type (0 fp32 in [-1,1], 1 uint8 levels)");
       if ((d->H & 1) || (d->W & 3)) return fail(LDIC_EINVAL, "first conv: H must be even and W a multiple of 4");
       L->mode = 0; L->k = 5; L->cin_map = 2;
       L->Ho = d->H / 2; L->Wo = d->W / 2; L->Wg = L->Wo; L->Hg = L->Ho;
@@ -2261,8 +1964,8 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
   }
   L->Np = L->ngroups * L->Cg;
   L->Cs = L->Cg;
-  if (L->Np != 64 && L->Np != 128 && L->Np != 192 && L->Np != 256)
-    return fail(LDIC_EINVAL, "conv: accumulator width %d (groups %d x Cout_pad %d) must be 64/128/192/256", L->Np,
+  if (L->Np != 64 && L->Np != 128 && L->Np != 192 && L->Np != 256 && L->Np != 384)
+    return fail(LDIC_EINVAL, "conv: accumulator width %d (groups %d x Cout_pad %d) must be 64/128/192/256/384", L->Np,
                 L->ngroups, L->Cg);
   if (!custom_out) {
     L->out_sX = L->Cg; L->out_sY = (long long)L->Wo * L->Cg; L->out_sN = (long long)L->Ho * L->Wo * L->Cg;
@@ -2275,84 +1978,165 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
   return LDIC_OK;
 }
 
-void choose_tile(int mode, int Wg, int Hg, int B, int* TW, int* TH, int* TN) {
+void choose_tile(int Wg, int Hg, int B, int* TW, int* TH, int* TN) {
   double best = 1e30;
   int bw = 128, bh = 1, bn = 1;
-  for (int tw = 128; tw >= (mode == 1 ? 8 : 1); tw >>= 1) {
+  for (int tw = 128; tw >= 1; tw >>= 1) {
     for (int th = 128 / tw; th >= 1; th >>= 1) {
       int tn = 128 / (tw * th);
-      if (mode == 1 && tn != 1) continue;
       long long tiles = (long long)((Wg + tw - 1) / tw) * ((Hg + th - 1) / th) * ((B + tn - 1) / tn);
-      double cost = (double)tiles * (1.0 + (mode == 1 ? 0.02 * th : 0.0));   // stride-2 tiles issue TH loads per stage
-      if (cost < best - 1e-9) { best = cost; bw = tw; bh = th; bn = tn; }
+      if ((double)tiles < best - 1e-9) { best = (double)tiles; bw = tw; bh = th; bn = tn; }
     }
   }
   *TW = bw; *TH = bh; *TN = bn;
 }
 
-template <int NP>
-int launch_conv(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
-  const int stage_bytes = kATileBytes + NP * kBlockK * 2;
-  const size_t smem = (size_t)P.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + (size_t)(P.nbias + 1) * NP * sizeof(float);
+// ---------------------------------------------------------------------------------
+// Launch plans.  Everything a launch needs that depends only on (layer descriptor, tensor addresses) -- the tap /
+// tile tables, the three TMA descriptors, the kernel variant, grid and shared-memory size -- is built once and kept
+// in a small cache, so a repeated eager call costs a hash lookup and one cudaLaunchKernelEx (no getenv, no
+// cuTensorMapEncodeTiled, no table construction on the hot path).
+// ---------------------------------------------------------------------------------
+enum PlanKernel { PK_PAIR = 0, PK_W3 = 1, PK_WIDE = 2, PK_FIRST = 3, PK_FIRST_U8 = 4 };
+struct Plan {
+  ConvParams P;
+  CUtensorMap a, w, g;
+  int kernel, np, grid;
+  size_t smem;
+  int kind;
+};
+
+// per-device lazily initialised launch state of one kernel instantiation (guarded by g_init_mu)
+struct KernelState { bool attr_set[kMaxDevices]; int max_clusters[kMaxDevices]; };
+
+template <typename K>
+int prepare_kernel(K kern, KernelState& st, bool cluster, int* max_clusters) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return fail(LDIC_ECUDA, "conv: bad current device %d", dev);
   std::lock_guard<std::mutex> init_lock(g_init_mu);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LDIC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  if (!st.attr_set[dev]) {
+    LDIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (cluster) {
+      const int sms = num_sms();
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.blockDim = dim3(kThreads); cfg.gridDim = dim3(sms); cfg.dynamicSmemBytes = 227 * 1024 - 1024;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sms / 2 - 4; }
+      st.max_clusters[dev] = n < sms / 2 ? n : sms / 2;
+    }
+    st.attr_set[dev] = true;
   }
-  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  conv_tc_kernel<NP><<<grid, kThreads, smem, st>>>(a, w, g, P);
-  return check_launch("conv_tc_kernel");
+  if (max_clusters) *max_clusters = st.max_clusters[dev];
+  return LDIC_OK;
 }
 
-template <int NP>
-int launch_halo(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
-  const size_t smem = (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * NP * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
-                      (size_t)(P.nbias + 1) * NP * sizeof(float) + 64;
-  std::lock_guard<std::mutex> init_lock(g_init_mu);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LDIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  if (smem > 227 * 1024) return fail(LDIC_EINVAL, "conv halo: shared memory budget exceeded (%zu)", smem);
-  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  conv_halo_kernel<NP><<<grid, kThreads, smem, st>>>(a, w, g, P);
-  return check_launch("conv_halo_kernel");
-}
-
-template <int NP, int HALO, bool W3 = false>
-int launch_pair(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
-  auto kern = HALO ? conv_halo2_kernel<NP> : conv_tc2_kernel<NP, W3>;
-  const size_t smem = HALO ? (size_t)P.SA * P.a_slot_bytes + (size_t)P.SB * P.G * (NP / 2) * kBlockK * 2 + 1024 /*align*/ + 512 /*barriers*/ +
-                                 (size_t)(P.nbias + 1) * NP * sizeof(float) + 64
-                           : (size_t)P.stages * (kATileBytes + (NP / 2) * kBlockK * 2) + 1024 + 256 + (size_t)(P.nbias + 1) * NP * sizeof(float);
-  std::lock_guard<std::mutex> init_lock(g_init_mu);
-  static bool attr_set = false;
-  static int max_clusters = 0;
-  if (smem > 227 * 1024) return fail(LDIC_EINVAL, "conv pair kernel: shared memory budget exceeded (%zu)", smem);
+template <typename K>
+int launch_cluster2(K kern, const char* name, const Plan& pl, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-  if (!attr_set) {
-    LDIC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg.gridDim = dim3(kNumSMs);
-    cfg.dynamicSmemBytes = 227 * 1024 - 1024;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / 2 - 4; }
-    cfg.dynamicSmemBytes = smem;
-    max_clusters = n < kNumSMs / 2 ? n : kNumSMs / 2;
-    attr_set = true;
+  cfg.blockDim = dim3(kThreads); cfg.gridDim = dim3(pl.grid); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, pl.a, pl.w, pl.g, pl.P);
+  if (e != cudaSuccess) return fail(LDIC_ECUDA, "%s launch: %s", name, cudaGetErrorString(e));
+  return check_launch(name);
+}
+
+template <int NP, bool W3>
+int plan_pair(Plan* pl) {
+  static KernelState ks;
+  int mc = 0;
+  int rc = prepare_kernel(conv_tc2_kernel<NP, W3>, ks, true, &mc);
+  if (rc) return rc;
+  const int total_super = pl->P.super_per_job * pl->P.njobs;
+  pl->grid = 2 * (total_super < mc ? total_super : mc);
+  return LDIC_OK;
+}
+template <int NP>
+int plan_wide(Plan* pl) {
+  static KernelState ks;
+  int mc = 0;
+  int rc = prepare_kernel(conv_wide_kernel<NP>, ks, true, &mc);
+  if (rc) return rc;
+  const int total_super = pl->P.super_per_job * pl->P.njobs;
+  pl->grid = 2 * (total_super < mc ? total_super : mc);
+  return LDIC_OK;
+}
+template <int NP, bool U8>
+int plan_first(Plan* pl) {
+  static KernelState ks;
+  int rc = prepare_kernel(conv_first_kernel<NP, U8>, ks, false, nullptr);
+  if (rc) return rc;
+  const int sms = num_sms();
+  pl->grid = pl->P.total_tiles < sms ? pl->P.total_tiles : sms;
+  return LDIC_OK;
+}
+
+int finish_plan(Plan* pl) {
+  switch (pl->kernel) {
+    case PK_PAIR:
+      switch (pl->np) {
+        case 64: return plan_pair<64, false>(pl);
+        case 128: return plan_pair<128, false>(pl);
+        case 192: return plan_pair<192, false>(pl);
+        case 256: return plan_pair<256, false>(pl);
+      }
+      break;
+    case PK_W3: return plan_pair<192, true>(pl);
+    case PK_WIDE: return plan_wide<384>(pl);
+    case PK_FIRST:
+      switch (pl->np) {
+        case 64: return plan_first<64, false>(pl);
+        case 128: return plan_first<128, false>(pl);
+        case 192: return plan_first<192, false>(pl);
+      }
+      break;
+    case PK_FIRST_U8:
+      switch (pl->np) {
+        case 64: return plan_first<64, true>(pl);
+        case 128: return plan_first<128, true>(pl);
+        case 192: return plan_first<192, true>(pl);
+      }
+      break;
   }
-  const int total_super = P.super_per_job * P.njobs;
-  const int npairs = total_super < max_clusters ? total_super : max_clusters;
-  cfg.gridDim = dim3(2 * npairs);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, w, g, P);
-  if (e != cudaSuccess) return fail(LDIC_ECUDA, "conv pair kernel launch: %s", cudaGetErrorString(e));
-  return check_launch(HALO ? "conv_halo2_kernel" : "conv_tc2_kernel");
+  return fail(LDIC_EINVAL, "conv: no kernel for variant %d with %d accumulator columns", pl->kernel, pl->np);
+}
+
+int launch_plan(const Plan& pl, cudaStream_t st) {
+  switch (pl.kernel) {
+    case PK_PAIR:
+      switch (pl.np) {
+        case 64: return launch_cluster2(conv_tc2_kernel<64, false>, "conv_tc2_kernel", pl, st);
+        case 128: return launch_cluster2(conv_tc2_kernel<128, false>, "conv_tc2_kernel", pl, st);
+        case 192: return launch_cluster2(conv_tc2_kernel<192, false>, "conv_tc2_kernel", pl, st);
+        case 256: return launch_cluster2(conv_tc2_kernel<256, false>, "conv_tc2_kernel", pl, st);
+      }
+      break;
+    case PK_W3: return launch_cluster2(conv_tc2_kernel<192, true>, "conv_tc2_kernel(wide tail)", pl, st);
+    case PK_WIDE: return launch_cluster2(conv_wide_kernel<384>, "conv_wide_kernel", pl, st);
+    case PK_FIRST:
+    case PK_FIRST_U8: {
+      const bool u8 = pl.kernel == PK_FIRST_U8;
+      switch (pl.np) {
+        case 64: if (u8) conv_first_kernel<64, true><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P);
+                 else conv_first_kernel<64, false><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P); break;
+        case 128: if (u8) conv_first_kernel<128, true><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P);
+                  else conv_first_kernel<128, false><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P); break;
+        case 192: if (u8) conv_first_kernel<192, true><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P);
+                  else conv_first_kernel<192, false><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P); break;
+        default: return fail(LDIC_EINVAL, "first conv: unsupported Np %d", pl.np);
+      }
+      return check_launch("conv_first_kernel");
+    }
+  }
+  return fail(LDIC_EINVAL, "conv: bad plan");
 }
 
 // generic weight packer: Wp[t][n][k]
@@ -2397,27 +2181,26 @@ __global__ void k_pack_weights(const float* __restrict__ w, const float* __restr
   }
 }
 
-template <int NP>
-int launch_first(const CUtensorMap& x, const CUtensorMap& w, const CUtensorMap& g, const ConvParams& P, cudaStream_t st) {
-  const size_t smem = (size_t)(2 + NP / 64) * NP * kBlockK * 2 + (size_t)P.stages * kATileBytes + 2 * kRawSlot + 256 +
-                      2 * NP * sizeof(float) + 1024 /*align*/;
-  if (smem > 227 * 1024) return fail(LDIC_EINVAL, "first conv: shared memory budget exceeded (%zu)", smem);
-  std::lock_guard<std::mutex> init_lock(g_init_mu);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LDIC_CUDA(cudaFuncSetAttribute(conv_first_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  conv_first_kernel<NP><<<grid, kThreads, smem, st>>>(x, w, g, P);
-  return check_launch("conv_first_kernel");
+// SM partition (LdicConvDesc::sm_limit): the kernels are persistent with one CTA (or one CTA of a pair) per SM and walk
+// their tiles with a grid stride, so capping the grid caps the SMs the launch occupies; the rest stay free for a
+// kernel of another stream.
+void apply_sm_limit(const LdicConvDesc* d, Plan* pl) {
+  if (d->sm_limit == 0) return;
+  const int sms = num_sms();
+  int avail = d->sm_limit > 0 ? d->sm_limit : sms + d->sm_limit;
+  if (avail > sms) avail = sms;
+  if (avail < 2) avail = 2;
+  if (pl->kernel != PK_FIRST && pl->kernel != PK_FIRST_U8) avail &= ~1;       // whole CTA pairs
+  if (pl->grid > avail) pl->grid = avail;
 }
 
-int forward_first(const LdicConvDesc* d, const Layer& L, const void* x, const void* w_packed, const float* bias_packed,
-                  const void* gamma_bf16, const float* beta_tiled, void* y, cudaStream_t st) {
+int build_plan_first(const LdicConvDesc* d, const Layer& L, const void* x, const void* w_packed, const float* bias_packed,
+                     const void* gamma_bf16, const float* beta_tiled, void* y, Plan* pl) {
   const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
+  const bool u8 = d->aux0 == 1;
   if (L.Np > 192) return fail(LDIC_EINVAL, "first conv: at most 192 output channels (weights and gamma stay resident in shared memory)");
-  ConvParams P;
+  if (u8 && (d->W % 16)) return fail(LDIC_EINVAL, "first conv (uint8 image): W must be a multiple of 16");
+  ConvParams& P = pl->P;
   memset(&P, 0, sizeof(P));
   P.mode = 0; P.TW = kFirstTW; P.TH = kFirstTH; P.TN = 1; P.tw_shift = 6; P.th_shift = 1;
   P.tiles_x = (L.Wg + P.TW - 1) / P.TW; P.tiles_y = (L.Hg + P.TH - 1) / P.TH; P.tiles_n = L.Bg;
@@ -2429,73 +2212,216 @@ int forward_first(const LdicConvDesc* d, const Layer& L, const void* x, const vo
   P.out_sX = L.out_sX; P.out_sY = L.out_sY; P.out_sN = L.out_sN;
   P.jobs[0] = L.jobs[0];
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
-  P.dbg_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
+  P.dbg_nostore = tuning().debug_nostore;
   P.gdn_insert = kGdnInsertDefault;
-  static unsigned long long* dbg_buf1 = nullptr;
-  const bool want_dbg = getenv("LDIC_DEBUG_TIMING") != nullptr;
-  if (want_dbg && !dbg_buf1) cudaMalloc(&dbg_buf1, 32 * sizeof(unsigned long long));
-  if (want_dbg) cudaMemset(dbg_buf1, 0, 32 * sizeof(unsigned long long));
-  P.dbg = want_dbg ? dbg_buf1 : nullptr;
+  P.tail_H = d->H; P.tail_W = d->W;             // image size: the uint8 patch builder masks out-of-image taps itself
   const int fixed = (2 + L.Np / 64) * L.Np * kBlockK * 2 + 2 * kRawSlot + 256 + 2 * L.Np * 4 + 1024;
   int S = (227 * 1024 - fixed) / kATileBytes;
   if (S > kMaxStages) S = kMaxStages;
   if (S < P.gdn_kblocks + 2) return fail(LDIC_EINVAL, "first conv: not enough shared memory for the operand ring");
   P.stages = S;
-  CUtensorMap tmX, tmW, tmG;
+  pl->smem = (size_t)(2 + L.Np / 64) * L.Np * kBlockK * 2 + (size_t)S * kATileBytes + 2 * kRawSlot + 256 +
+             2 * L.Np * sizeof(float) + 1024 /*align*/;
+  if (pl->smem > 227 * 1024) return fail(LDIC_EINVAL, "first conv: shared memory budget exceeded (%zu)", pl->smem);
   int rc;
   {
+    const cuuint64_t es = u8 ? 1 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)d->W, (cuuint64_t)d->H, 3, (cuuint64_t)d->B};
-    cuuint64_t str[3] = {(cuuint64_t)d->W * 4, (cuuint64_t)d->H * d->W * 4, (cuuint64_t)3 * d->H * d->W * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kRawW, (cuuint32_t)kRawH, 3, 1};
-    if ((rc = encode_map(&tmX, x, 4, dims, str, box, nullptr, true))) return rc;
+    cuuint64_t str[3] = {(cuuint64_t)d->W * es, (cuuint64_t)d->H * d->W * es, (cuuint64_t)3 * d->H * d->W * es};
+    cuuint32_t box[4] = {(cuuint32_t)(u8 ? kRawW8 : kRawW), (cuuint32_t)kRawH, 3, 1};
+    if ((rc = encode_map(&pl->a, x, 4, dims, str, box, nullptr, u8 ? MAP_U8 : MAP_F32))) return rc;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.Np};
     cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
-    if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
+    if ((rc = encode_map(&pl->w, w_packed, 2, dims, str, box))) return rc;
   }
   if (gdn) {
     cuuint64_t dims[2] = {(cuuint64_t)L.Np, (cuuint64_t)L.Np};
     cuuint64_t str[1] = {(cuuint64_t)L.Np * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)L.Np};
-    if ((rc = encode_map(&tmG, gamma_bf16, 2, dims, str, box))) return rc;
+    if ((rc = encode_map(&pl->g, gamma_bf16, 2, dims, str, box))) return rc;
   } else {
-    tmG = tmW;
+    pl->g = pl->w;
   }
-  switch (L.Np) {
-    case 64: rc = launch_first<64>(tmX, tmW, tmG, P, st); break;
-    case 128: rc = launch_first<128>(tmX, tmW, tmG, P, st); break;
-    case 192: rc = launch_first<192>(tmX, tmW, tmG, P, st); break;
-    default: return fail(LDIC_EINVAL, "first conv: unsupported Np %d", L.Np);
-  }
-  if (want_dbg && rc == LDIC_OK) {
-    unsigned long long h[32];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, dbg_buf1, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[ldic timing] first layer: epilogue total %llu cyc over %llu tiles: wait_acc %llu wait_norm %llu wait_slots %llu | busy pass 1 %llu pass 2 + stores %llu\n",
-            h[16], h[20], h[17], h[18], h[19], h[21], h[22]);
-  }
-  return rc;
+  pl->kernel = u8 ? PK_FIRST_U8 : PK_FIRST;
+  pl->np = L.Np;
+  if ((rc = finish_plan(pl))) return rc;
+  apply_sm_limit(d, pl);
+  return LDIC_OK;
 }
+
+int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+               const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, Plan* pl) {
+  Layer L;
+  int rc = build_layer(d, &L);
+  if (rc) return rc;
+  pl->kind = d->kind;
+  const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
+  if (gdn && (!gamma_bf16 || !beta_tiled)) return fail(LDIC_EINVAL, "conv: GDN epilogue needs gamma_bf16 and beta_tiled");
+  if (gdn && L.njobs > 4) return fail(LDIC_EINVAL, "conv: GDN epilogue is not available for the context layers");
+  if ((((uintptr_t)x) & 15) || (((uintptr_t)w_packed) & 15) || (((uintptr_t)y) & 31)) return fail(LDIC_EINVAL, "conv: x / weights must be 16-byte and y 32-byte aligned");
+  if (L.Cs % 16) return fail(LDIC_EINVAL, "conv: output channel count must be a multiple of 16");
+  if (d->kind == LDIC_CONV_FIRST_5x5S2)
+    return build_plan_first(d, L, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, pl);
+
+  const Tuning& tn = tuning();
+  ConvParams& P = pl->P;
+  memset(&P, 0, sizeof(P));
+  // stride-2 gathers: one TMA box with element strides (2,2) over (W,H) per stage
+  const bool strided = L.mode == 1;
+  P.mode = strided ? 2 : 0;
+  choose_tile(L.Wg, L.Hg, L.Bg, &P.TW, &P.TH, &P.TN);
+  auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
+  P.tw_shift = ilog2(P.TW); P.th_shift = ilog2(P.TH); P.cg_shift = ilog2(L.Cg);
+  if (L.ngroups > 1 && ((1 << P.cg_shift) != L.Cg || L.Cg < 8)) return fail(LDIC_EINVAL, "conv: merged deconv needs a power-of-two Cout_pad >= 8");
+  P.tiles_x = (L.Wg + P.TW - 1) / P.TW;
+  P.tiles_y = (L.Hg + P.TH - 1) / P.TH;
+  P.tiles_n = (L.Bg + P.TN - 1) / P.TN;
+  P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
+  P.njobs = L.njobs;
+  P.total_tiles = P.tiles_per_job * P.njobs;
+  P.Wg = L.Wg; P.Hg = L.Hg; P.B = L.Bg;
+  P.gdn_kblocks = gdn ? L.Np / 64 : 0;
+  P.act = d->act; P.out_f32 = d->out_f32;
+  P.ngroups = L.ngroups; P.Cg = L.Cg; P.sy = L.sy; P.sx = L.sx; P.nbias = L.nbias;
+  P.out_sX = L.out_sX; P.out_sY = L.out_sY; P.out_sN = L.out_sN;
+  for (int j = 0; j < kMaxJobs; ++j) P.jobs[j] = L.jobs[j];
+  for (int t = 0; t < kMaxTaps; ++t) P.taps[t] = L.taps[t];
+  if (strided) for (int t = 0; t < L.ntaps_total; ++t) { P.taps[t].dx = (short)(2 * L.taps[t].dx + L.taps[t].px); P.taps[t].px = 0; }
+  P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
+  P.dbg_nostore = tn.debug_nostore;
+  P.gdn_insert = tn.gdn_insert >= 1 && tn.gdn_insert <= 16 ? tn.gdn_insert : kGdnInsertDefault;
+  if (tail) {
+    P.tail_x = tail->x_nchw; P.tail_w = tail->w; P.tail_xo = tail->x_tilde_nchw; P.tail_sq = tail->sq_err;
+    P.tail_H = tail->H; P.tail_W = tail->W; P.tail_u8 = tail->x_is_u8;
+  }
+
+  // ---- wide-N form of the merged last deconv (epilogue_w3): the three dx taps ride side by side in N = 3 * Np, the dy
+  // taps are three stride-1 gathers of a 32 x 4 pixel tile (tiles overlap by one halo pixel per side in x) ----
+  const bool wide3 = d->kind == LDIC_DECONV_GS_5x5_MERGED && gdn && L.Np == 64 && L.ngroups == 4 && L.Cg == 16 && L.njobs == 1 &&
+                     L.ntaps_total == 9 && L.nbias == 1 && tn.tail_wide;
+  if (wide3) {
+    P.TW = 32; P.TH = 4; P.TN = 1; P.tw_shift = 5; P.th_shift = 2; P.x_ovl = 2;
+    P.tiles_x = (L.Wg + P.TW - P.x_ovl - 1) / (P.TW - P.x_ovl);
+    P.tiles_y = (L.Hg + P.TH - 1) / P.TH;
+    P.tiles_n = L.Bg;
+    P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
+    P.total_tiles = P.tiles_per_job;
+    const short nkc = L.taps[0].nkc;
+    for (int t = 0; t < 3; ++t) {            // packed weights are [tap = (dy+1)*3 + (dx+1)][Np][K]: rows t*3*Np .. +3*Np = one dy
+      Tap tp; memset(&tp, 0, sizeof(tp));
+      tp.dx = 0; tp.dy = (short)(t - 1); tp.nkc = nkc;
+      P.taps[t] = tp;
+    }
+    P.jobs[0].ntaps = 3; P.jobs[0].tap_begin = 0; P.jobs[0].nkb = 3 * nkc;
+  }
+  if (tail && L.Np > 128) return fail(LDIC_EINVAL, "conv tail: the merged last deconv must have at most 128 accumulator columns");
+  P.super_per_job = (P.tiles_per_job + 1) / 2;
+
+  const bool wide = L.Np > 256;              // single-buffered 384-column accumulator, chunked gamma contraction
+  const int NpK = wide3 ? 3 * L.Np : L.Np;   // accumulator columns of the kernel
+  if (wide) {
+    if (L.Np != 384) return fail(LDIC_EINVAL, "conv: accumulator width %d not supported (64/128/192/256/384)", L.Np);
+    if (L.ngroups != 1) return fail(LDIC_EINVAL, "conv: merged sub-pixel phases need at most 256 accumulator columns");
+    const int bslot = (L.Np / 2) * kBlockK * 2;
+    const int budget = 227 * 1024 - 1024 - 512 - (L.nbias + 1) * L.Np * 4 - 64;
+    int SA = gdn ? L.Np / 64 + 2 : 5;        // the GDN phase holds Np/64 x^2 tiles in the A ring
+    int SB = (budget - SA * kATileBytes) / bslot;
+    while (SB < 3 && SA > (gdn ? L.Np / 64 + 1 : 3)) { --SA; SB = (budget - SA * kATileBytes) / bslot; }
+    if (SB > kMaxStages) SB = kMaxStages;
+    if (SA > kMaxStages) SA = kMaxStages;
+    if (SB < 2) return fail(LDIC_EINVAL, "conv (wide): shared memory budget exceeded");
+    P.SA = SA; P.SB = SB;
+    pl->smem = (size_t)SA * kATileBytes + (size_t)SB * bslot + 1024 + 512 + (size_t)(L.nbias + 1) * L.Np * sizeof(float) + 64;
+  } else {
+    const int stage2 = kATileBytes + (NpK / 2) * kBlockK * 2;
+    int st2 = (227 * 1024 - 2048 - (L.nbias + 1) * NpK * 4) / stage2;
+    if (st2 > kMaxStages) st2 = kMaxStages;
+    if (tn.stages_cap >= 2 && tn.stages_cap < st2) st2 = tn.stages_cap;
+    P.stages = st2;
+    if (gdn && st2 < P.gdn_kblocks + 1) return fail(LDIC_EINVAL, "conv: not enough pipeline stages for the GDN epilogue");
+    pl->smem = (size_t)st2 * stage2 + 1024 + 256 + (size_t)(L.nbias + 1) * NpK * sizeof(float);
+  }
+  if (pl->smem > 227 * 1024) return fail(LDIC_EINVAL, "conv: shared memory budget exceeded (%zu)", pl->smem);
+
+  const cuuint64_t C = (cuuint64_t)L.vC;
+  {
+    cuuint64_t dims[4] = {C, (cuuint64_t)L.vW, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
+    cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
+    if (strided) {
+      cuuint32_t box[4] = {64, (cuuint32_t)(2 * P.TW), (cuuint32_t)(2 * P.TH), (cuuint32_t)P.TN};
+      cuuint32_t es[4] = {1, 2, 2, 1};
+      if ((rc = encode_map(&pl->a, x, 4, dims, str, box, es))) return rc;
+    } else {
+      cuuint32_t box[4] = {64, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
+      if ((rc = encode_map(&pl->a, x, 4, dims, str, box))) return rc;
+    }
+  }
+  {
+    // each CTA of a pair loads half of the weight rows (wide kernel: half of each column half = a quarter per box)
+    cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.ntaps_total * L.Np};
+    cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(wide ? L.Np / 4 : NpK / 2)};
+    if ((rc = encode_map(&pl->w, w_packed, 2, dims, str, box))) return rc;
+  }
+  if (gdn) {
+    cuuint64_t dims[2] = {(cuuint64_t)L.Np, (cuuint64_t)L.Np};
+    cuuint64_t str[1] = {(cuuint64_t)L.Np * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(wide ? kWideNC / 2 : L.Np / 2)};
+    if ((rc = encode_map(&pl->g, gamma_bf16, 2, dims, str, box))) return rc;
+  } else {
+    pl->g = pl->w;
+  }
+  pl->kernel = wide ? PK_WIDE : (wide3 ? PK_W3 : PK_PAIR);
+  pl->np = L.Np;
+  if ((rc = finish_plan(pl))) return rc;
+  apply_sm_limit(d, pl);
+  return LDIC_OK;
+}
+
+// ---- plan cache -----------------------------------------------------------------------------------
+struct PlanKey {
+  LdicConvDesc d;
+  const void *x, *w, *bias, *gamma, *beta, *y;
+  LdicConvTail tail;
+  int has_tail, device;
+  unsigned epoch;
+  bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
+};
+struct PlanKeyHash {
+  size_t operator()(const PlanKey& k) const {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(PlanKey); ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+std::mutex g_plan_mu;
+std::unordered_map<PlanKey, std::shared_ptr<Plan>, PlanKeyHash> g_plans;
+constexpr size_t kMaxPlans = 1024;
 
 unsigned long long* g_timeout_host = nullptr;
 int ensure_timeout_report() {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return LDIC_OK;
   std::lock_guard<std::mutex> init_lock(g_init_mu);
-  static bool done = false;
-  if (done) return LDIC_OK;
-  unsigned long long* h = nullptr;
-  unsigned long long* dptr = nullptr;
-  if (cudaHostAlloc((void**)&h, 8 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
-      cudaHostGetDevicePointer((void**)&dptr, h, 0) != cudaSuccess) {
-    cudaGetLastError();
-    done = true;                      // diagnostics only: run without the report buffer
-    return LDIC_OK;
+  static bool done[kMaxDevices] = {};
+  if (done[dev]) return LDIC_OK;
+  done[dev] = true;                     // diagnostics only: on any failure run without the report buffer
+  unsigned long long* h = g_timeout_host;
+  if (!h) {
+    if (cudaHostAlloc((void**)&h, 8 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return LDIC_OK;
+    }
+    memset(h, 0, 8 * sizeof(unsigned long long));
+    g_timeout_host = h;
   }
-  memset(h, 0, 8 * sizeof(unsigned long long));
-  LDIC_CUDA(cudaMemcpyToSymbol(g_timeout_report, &dptr, sizeof(dptr)));
-  g_timeout_host = h;
-  done = true;
+  unsigned long long* dptr = nullptr;
+  if (cudaHostGetDevicePointer((void**)&dptr, h, 0) != cudaSuccess) { cudaGetLastError(); return LDIC_OK; }
+  if (cudaMemcpyToSymbol(g_timeout_report, &dptr, sizeof(dptr)) != cudaSuccess) cudaGetLastError();
   return LDIC_OK;
 }
 
@@ -2552,7 +2478,7 @@ extern "C" int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, con
     for (int g = 0; g < 4; ++g) { T.ky[t][g] = L.tap_ky[t][g]; T.kx[t][g] = L.tap_kx[t][g]; }
   }
   long long total = (long long)T.ntaps * T.Np * T.Kw;
-  int grid = (int)((total + 255) / 256 > kNumSMs * 8 ? kNumSMs * 8 : (total + 255) / 256);
+  int grid = (int)((total + 255) / 256 > num_sms() * 8 ? num_sms() * 8 : (total + 255) / 256);
   k_pack_weights<<<grid, 256, 0, (cudaStream_t)stream>>>(w, bias, T, (__nv_bfloat16*)w_packed, bias_packed);
   return check_launch("k_pack_weights");
 }
@@ -2575,260 +2501,63 @@ extern "C" int ldic_conv_forward_fused_tail(const LdicConvDesc* d, const void* x
   return conv_forward_impl(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y_or_null, tail, stream);
 }
 namespace {
+void print_debug_timing(const Plan& pl, cudaStream_t st) {     // debugging aid only (LDIC_DEBUG_TIMING=1): synchronises
+  unsigned long long h[32];
+  cudaStreamSynchronize(st);
+  cudaMemcpy(h, pl.P.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+  fprintf(stderr, "[ldic timing] kind %d Np %d tiles/cta %llu stages %llu | mma total %llu cyc: wait_full %llu wait_buf %llu wait_x2 %llu "
+          "(per stage: total %.0f wait_full %.0f) | producer total %llu wait_empty %llu\n", pl.kind, pl.np, h[5], h[4], h[0], h[1], h[2], h[3],
+          h[4] ? (double)h[0] / h[4] : 0.0, h[4] ? (double)h[1] / h[4] : 0.0, h[8], h[9]);
+  fprintf(stderr, "[ldic timing]   epilogue total %llu cyc over %llu tiles: wait_acc %llu wait_norm %llu wait_slots %llu | busy pass 1 %llu pass 2 + stores %llu\n",
+          h[16], h[20], h[17], h[18], h[19], h[21], h[22]);
+}
+
 int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                       const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, void* stream) {
-  Layer L;
-  int rc = build_layer(d, &L);
-  if (rc) return rc;
-  if (d->B == 0) return LDIC_OK;
+  if (!d) return fail(LDIC_EINVAL, "conv: null desc");
+  if (d->B == 0) { Layer L; return build_layer(d, &L); }
   if (!x || !w_packed || (!y && !tail)) return fail(LDIC_EINVAL, "conv: null tensor");
+  int rc;
   if ((rc = ensure_timeout_report())) return rc;
-  const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
-  if (gdn && (!gamma_bf16 || !beta_tiled)) return fail(LDIC_EINVAL, "conv: GDN epilogue needs gamma_bf16 and beta_tiled");
-  if (gdn && L.njobs > 4) return fail(LDIC_EINVAL, "conv: GDN epilogue is not available for the context layers");
-  if ((((uintptr_t)x) & 15) || (((uintptr_t)w_packed) & 15) || (((uintptr_t)y) & 31)) return fail(LDIC_EINVAL, "conv: x / weights must be 16-byte and y 32-byte aligned");
-  if (L.Cs % 16) return fail(LDIC_EINVAL, "conv: output channel count must be a multiple of 16");
-  if (d->kind == LDIC_CONV_FIRST_5x5S2)
-    return forward_first(d, L, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, (cudaStream_t)stream);
-
-  ConvParams P;
-  memset(&P, 0, sizeof(P));
-  P.mode = L.mode;
-  // stride-2 gathers: one TMA box with element strides (2,2) over (W,H) per stage (mode 2) instead of TH boxes of the
-  // x-parity view (mode 1, kept as a tuning fallback: LDIC_S2_STRIDED=0)
-  bool strided = L.mode == 1;
-  if (const char* e = getenv("LDIC_S2_STRIDED")) strided = strided && atoi(e) != 0;
-  if (strided) P.mode = 2;
-  choose_tile(strided ? 0 : L.mode, L.Wg, L.Hg, L.Bg, &P.TW, &P.TH, &P.TN);
-  auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
-  P.tw_shift = ilog2(P.TW); P.th_shift = ilog2(P.TH); P.cg_shift = ilog2(L.Cg);
-  if (L.ngroups > 1 && ((1 << P.cg_shift) != L.Cg || L.Cg < 8)) return fail(LDIC_EINVAL, "conv: merged deconv needs a power-of-two Cout_pad >= 8");
-  P.tiles_x = (L.Wg + P.TW - 1) / P.TW;
-  P.tiles_y = (L.Hg + P.TH - 1) / P.TH;
-  P.tiles_n = (L.Bg + P.TN - 1) / P.TN;
-  P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
-  P.njobs = L.njobs;
-  P.total_tiles = P.tiles_per_job * P.njobs;
-  P.Wg = L.Wg; P.Hg = L.Hg; P.B = L.Bg;
-  P.gdn_kblocks = gdn ? L.Np / 64 : 0;
-  P.act = d->act; P.out_f32 = d->out_f32;
-  P.ngroups = L.ngroups; P.Cg = L.Cg; P.sy = L.sy; P.sx = L.sx; P.nbias = L.nbias;
-  P.out_sX = L.out_sX; P.out_sY = L.out_sY; P.out_sN = L.out_sN;
-  for (int j = 0; j < kMaxJobs; ++j) P.jobs[j] = L.jobs[j];
-  for (int t = 0; t < kMaxTaps; ++t) P.taps[t] = L.taps[t];
-  if (strided) for (int t = 0; t < L.ntaps_total; ++t) { P.taps[t].dx = (short)(2 * L.taps[t].dx + L.taps[t].px); P.taps[t].px = 0; }
-  P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
-  P.dbg_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
-  P.gdn_insert = kGdnInsertDefault;
-  if (const char* e = getenv("LDIC_GDN_INSERT")) { int v = atoi(e); if (v >= 1 && v <= 16) P.gdn_insert = v; }   // tuning aid
-  if (tail) {
-    P.tail_x = tail->x_nchw; P.tail_w = tail->w; P.tail_xo = tail->x_tilde_nchw; P.tail_sq = tail->sq_err;
-    P.tail_H = tail->H; P.tail_W = tail->W;
-  }
-  static unsigned long long* dbg_buf = nullptr;
-  const bool want_dbg = getenv("LDIC_DEBUG_TIMING") != nullptr;
-  if (want_dbg && !dbg_buf) cudaMalloc(&dbg_buf, 32 * sizeof(unsigned long long));
-  if (want_dbg) cudaMemset(dbg_buf, 0, 32 * sizeof(unsigned long long));
-  P.dbg = want_dbg ? dbg_buf : nullptr;
-  const int stage_bytes = kATileBytes + L.Np * kBlockK * 2;
-  int stages = (227 * 1024 - 2048 - (L.nbias + 1) * L.Np * 4) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (const char* e = getenv("LDIC_STAGES")) { int v = atoi(e); if (v >= 2 && v < stages) stages = v; }   // tuning aid
-  P.stages = stages;
-  if (gdn && stages < P.gdn_kblocks + 1) return fail(LDIC_EINVAL, "conv: not enough pipeline stages for the GDN epilogue");
-
-  // ---- wide-N form of the merged last deconv (epilogue_w3): the three dx taps ride side by side in N = 3 * Np, the dy
-  // taps are three stride-1 gathers of a 32 x 4 pixel tile (tiles overlap by one halo pixel per side in x) ----
-  bool wide3 = d->kind == LDIC_DECONV_GS_5x5_MERGED && gdn && L.Np == 64 && L.ngroups == 4 && L.Cg == 16 && L.njobs == 1 &&
-               L.ntaps_total == 9 && L.nbias == 1;
-  if (const char* e = getenv("LDIC_TAIL_WIDE")) wide3 = wide3 && atoi(e) != 0;           // tuning aid: LDIC_TAIL_WIDE=0
-  if (wide3) {
-    P.TW = 32; P.TH = 4; P.TN = 1; P.tw_shift = 5; P.th_shift = 2; P.x_ovl = 2;
-    P.tiles_x = (L.Wg + P.TW - P.x_ovl - 1) / (P.TW - P.x_ovl);
-    P.tiles_y = (L.Hg + P.TH - 1) / P.TH;
-    P.tiles_n = L.Bg;
-    P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
-    P.total_tiles = P.tiles_per_job;
-    const short nkc = L.taps[0].nkc;
-    for (int t = 0; t < 3; ++t) {            // packed weights are [tap = (dy+1)*3 + (dx+1)][Np][K]: rows t*3*Np .. +3*Np = one dy
-      Tap tp; memset(&tp, 0, sizeof(tp));
-      tp.dx = 0; tp.dy = (short)(t - 1); tp.nkc = nkc;
-      P.taps[t] = tp;
-    }
-    P.jobs[0].ntaps = 3; P.jobs[0].tap_begin = 0; P.jobs[0].nkb = 3 * nkc;
-  }
-
-  // ---- halo variant (stride-1 gathers with spatial taps): one region load per 64-channel chunk ----
-  bool halo = false, pair = false;
-  if (L.mode == 0 && !wide3) {
-    int dxmin = 0, dxmax = 0, dymin = 0, dymax = 0;
-    for (int t = 0; t < L.ntaps_total; ++t) {
-      dxmin = L.taps[t].dx < dxmin ? L.taps[t].dx : dxmin; dxmax = L.taps[t].dx > dxmax ? L.taps[t].dx : dxmax;
-      dymin = L.taps[t].dy < dymin ? L.taps[t].dy : dymin; dymax = L.taps[t].dy > dymax ? L.taps[t].dy : dymax;
-    }
-    const long long halo_tiles = (long long)((L.Wg + 7) / 8) * ((L.Hg + 15) / 16) * L.Bg;
-    halo = (dxmax > dxmin || dymax > dymin) && halo_tiles * 10 <= (long long)P.tiles_per_job * 13;
-    // UMMA reads of the shifted (not 1024-byte aligned) halo descriptors run at about half rate, which only pays
-    // when the weight tiles are small and several taps share a stage: narrow accumulators (merged last deconv)
-    int halo_mode = 1;                                                             // 0 never, 1 Np <= 64, 2 whenever possible
-    if (const char* e = getenv("LDIC_HALO")) halo_mode = atoi(e);                  // tuning aid
-    halo = halo && (halo_mode == 2 || (halo_mode == 1 && L.Np <= 64));
-    if (halo) {
-      P.halo = 1; P.dxmin = dxmin; P.dymin = dymin;
-      P.RW = 8 + dxmax - dxmin; P.RH = 16 + dymax - dymin; P.ndx = 1;
-      // Aligned halo: one 8-pixel-wide copy of the region per dx (row pitch 8 x 128 B = one swizzle atom), so the A
-      // descriptor of every tap starts on a 1024-byte boundary (dy shifts move by whole atoms) and the MMAs run at
-      // full rate; costs (dx range) x the region bytes of L2 -> SM traffic instead of one widened region.
-      // Measured: no gain (the MMAs of this kernel are bound by their own shared-memory operand reads, not by the
-      // descriptor alignment), so the single widened region stays the default.
-      bool aligned = false;
-      if (const char* e = getenv("LDIC_HALO_ALIGNED")) aligned = dxmax > dxmin && atoi(e) != 0;   // experiment switch
-      if (aligned) { P.ndx = dxmax - dxmin + 1; P.RW = 8; }
-      P.a_slot_bytes = (P.ndx * P.RW * P.RH * 128 + 1023) / 1024 * 1024;
-      // taps per B slot: one TMA box holds up to 256 weight rows; only when every tap covers every chunk
-      bool uniform = true;
-      for (int t = 0; t < L.ntaps_total; ++t) uniform = uniform && L.taps[t].a_c0 == 0 && L.taps[t].nkc == L.taps[0].nkc;
-      P.G = uniform ? 256 / L.Np : 1;
-      if (P.G > 4) P.G = 4;
-      if (P.G < 1) P.G = 1;
-      if (const char* e = getenv("LDIC_HALO_G")) { int g = atoi(e); if (g >= 1 && g <= P.G) P.G = g; }     // tuning aid
-      // CTA pairs (cta_group::2): each CTA stages half of the weight rows -> half the bytes per weight stage
-      pair = true;
-      if (const char* e = getenv("LDIC_HALO2")) pair = atoi(e) != 0;                      // tuning aid: LDIC_HALO2=0 = one CTA per tile
-      const int bbytes = P.G * (pair ? L.Np / 2 : L.Np) * kBlockK * 2;
-      const int budget = 227 * 1024 - 1024 - 512 - (L.nbias + 1) * L.Np * 4 - 64;
-      int SA = P.gdn_kblocks + 2; if (SA < 3) SA = 3;
-      if (const char* e = getenv("LDIC_HALO_SA")) SA = P.gdn_kblocks + atoi(e);            // tuning aid: region slots beyond the x^2 tiles
-      if (SA > kMaxStages) SA = kMaxStages;
-      int SB = (budget - SA * P.a_slot_bytes) / bbytes;
-      while (SB < 3 && SA > P.gdn_kblocks + 1 && SA > 2) { --SA; SB = (budget - SA * P.a_slot_bytes) / bbytes; }
-      if (SB > kMaxStages) SB = kMaxStages;
-      if (SB < 2 || SA < P.gdn_kblocks + 1) halo = false;
-      P.SA = SA; P.SB = SB;
-    }
-    if (halo) {
-      P.TW = 8; P.TH = 16; P.TN = 1; P.tw_shift = 3; P.th_shift = 4;
-      P.tiles_x = (L.Wg + 7) / 8; P.tiles_y = (L.Hg + 15) / 16; P.tiles_n = L.Bg;
-      P.tiles_per_job = P.tiles_x * P.tiles_y * P.tiles_n;
-      P.total_tiles = P.tiles_per_job * P.njobs;
-      P.super_per_job = (P.tiles_per_job + 1) / 2;
-      for (int t = 0; t < L.ntaps_total; ++t)
-        P.taps[t].halo_off = P.ndx > 1 ? (P.taps[t].dx - dxmin) * (P.RW * P.RH * 128) + (P.taps[t].dy - dymin) * P.RW * 128
-                                       : ((P.taps[t].dy - dymin) * P.RW + (P.taps[t].dx - dxmin)) * 128;
-      for (int j = 0; j < L.njobs; ++j) {
-        int lo = 1 << 30, hi = 0;
-        for (int t = 0; t < P.jobs[j].ntaps; ++t) {
-          const Tap& tp = P.taps[P.jobs[j].tap_begin + t];
-          const int c0 = tp.a_c0 / kBlockK;
-          lo = c0 < lo ? c0 : lo; hi = c0 + tp.nkc > hi ? c0 + tp.nkc : hi;
-        }
-        P.jobs[j].kc0 = lo; P.jobs[j].nchunks = hi - lo;
-      }
-    } else {
-      P.halo = 0;
-    }
-  }
-
-  if (!halo) pair = false;
-  // CTA pairs for the streaming kernel (cta_group::2): not for the x-parity fallback view
-  bool pair_stream = !halo && P.mode != 1;
-  if (const char* e = getenv("LDIC_PAIR")) pair_stream = pair_stream && atoi(e) != 0;      // tuning aid: LDIC_PAIR=0
-  const int NpK = wide3 ? 3 * L.Np : L.Np;        // accumulator columns of the kernel
-  if (wide3 && !pair_stream) return fail(LDIC_EINVAL, "conv: the wide-N merged deconv needs the CTA-pair kernel (unset LDIC_PAIR / LDIC_TAIL_WIDE=0)");
-  if (pair_stream) {
-    P.super_per_job = (P.tiles_per_job + 1) / 2;
-    const int stage2 = kATileBytes + (NpK / 2) * kBlockK * 2;
-    int st2 = (227 * 1024 - 2048 - (L.nbias + 1) * NpK * 4) / stage2;
-    if (st2 > kMaxStages) st2 = kMaxStages;
-    if (const char* e = getenv("LDIC_STAGES")) { int v = atoi(e); if (v >= 2 && v < st2) st2 = v; }
-    P.stages = st2;
-    if (gdn && st2 < P.gdn_kblocks + 1) pair_stream = false;
-    else pair = true;                          // weight / gamma maps load half of the rows per CTA
-  }
-  CUtensorMap tmA, tmW, tmG;
-  const cuuint64_t C = (cuuint64_t)L.vC;
-  if (halo) {
-    cuuint64_t dims[4] = {C, (cuuint64_t)L.vW, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
-    cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)P.RW, (cuuint32_t)P.RH, 1};
-    if ((rc = encode_map(&tmA, x, 4, dims, str, box))) return rc;
-  } else if (strided) {
-    cuuint64_t dims[4] = {C, (cuuint64_t)L.vW, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
-    cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(2 * P.TW), (cuuint32_t)(2 * P.TH), (cuuint32_t)P.TN};
-    cuuint32_t es[4] = {1, 2, 2, 1};
-    if ((rc = encode_map(&tmA, x, 4, dims, str, box, es))) return rc;
-  } else if (L.mode == 1) {
-    cuuint64_t dims[5] = {C, 2, (cuuint64_t)L.vW / 2, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
-    cuuint64_t str[4] = {C * 2, 2 * C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
-    cuuint32_t box[5] = {64, 1, (cuuint32_t)P.TW, 1, 1};
-    if ((rc = encode_map(&tmA, x, 5, dims, str, box))) return rc;
-  } else {
-    cuuint64_t dims[4] = {C, (cuuint64_t)L.vW, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
-    cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)P.TW, (cuuint32_t)P.TH, (cuuint32_t)P.TN};
-    if ((rc = encode_map(&tmA, x, 4, dims, str, box))) return rc;
-  }
+  const Tuning& tn = tuning();
+  PlanKey key;
+  memset(&key, 0, sizeof(key));
+  key.d = *d; key.x = x; key.w = w_packed; key.bias = bias_packed; key.gamma = gamma_bf16; key.beta = beta_tiled; key.y = y;
+  if (tail) { key.tail = *tail; key.has_tail = 1; }
+  key.device = current_device(); key.epoch = tn.epoch;
+  std::shared_ptr<Plan> pl;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)L.Kw, (cuuint64_t)L.ntaps_total * L.Np};
-    cuuint64_t str[1] = {(cuuint64_t)L.Kw * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? NpK / 2 : L.Np * (halo ? P.G : 1))};
-    if ((rc = encode_map(&tmW, w_packed, 2, dims, str, box))) return rc;
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) pl = it->second;
   }
-  if (gdn) {
-    cuuint64_t dims[2] = {(cuuint64_t)L.Np, (cuuint64_t)L.Np};
-    cuuint64_t str[1] = {(cuuint64_t)L.Np * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? L.Np / 2 : L.Np)};
-    if ((rc = encode_map(&tmG, gamma_bf16, 2, dims, str, box))) return rc;
-  } else {
-    tmG = tmW;
+  if (!pl) {
+    pl = std::make_shared<Plan>();
+    if ((rc = build_plan(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, tail, pl.get()))) return rc;
+    if (tn.debug_timing) {
+      unsigned long long* buf = nullptr;
+      if (cudaMalloc(&buf, 32 * sizeof(unsigned long long)) == cudaSuccess) pl->P.dbg = buf;   // lives as long as the plan cache
+    }
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (g_plans.size() >= kMaxPlans) g_plans.clear();
+    g_plans.emplace(key, pl);
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (halo && pair) {
-    switch (L.Np) {
-      case 64: rc = launch_pair<64, 1>(tmA, tmW, tmG, P, st); break;
-      case 128: rc = launch_pair<128, 1>(tmA, tmW, tmG, P, st); break;
-      case 192: rc = launch_pair<192, 1>(tmA, tmW, tmG, P, st); break;
-      case 256: rc = launch_pair<256, 1>(tmA, tmW, tmG, P, st); break;
-    }
-  } else if (halo) {
-    switch (L.Np) {
-      case 64: rc = launch_halo<64>(tmA, tmW, tmG, P, st); break;
-      case 128: rc = launch_halo<128>(tmA, tmW, tmG, P, st); break;
-      case 192: rc = launch_halo<192>(tmA, tmW, tmG, P, st); break;
-      case 256: rc = launch_halo<256>(tmA, tmW, tmG, P, st); break;
-    }
-  } else if (wide3) {
-    rc = launch_pair<192, 0, true>(tmA, tmW, tmG, P, st);
-  } else if (pair_stream) {
-    switch (L.Np) {
-      case 64: rc = launch_pair<64, 0>(tmA, tmW, tmG, P, st); break;
-      case 128: rc = launch_pair<128, 0>(tmA, tmW, tmG, P, st); break;
-      case 192: rc = launch_pair<192, 0>(tmA, tmW, tmG, P, st); break;
-      case 256: rc = launch_pair<256, 0>(tmA, tmW, tmG, P, st); break;
-    }
-  } else
-  switch (L.Np) {
-    case 64: rc = launch_conv<64>(tmA, tmW, tmG, P, st); break;
-    case 128: rc = launch_conv<128>(tmA, tmW, tmG, P, st); break;
-    case 192: rc = launch_conv<192>(tmA, tmW, tmG, P, st); break;
-    case 256: rc = launch_conv<256>(tmA, tmW, tmG, P, st); break;
-    default: return fail(LDIC_EINVAL, "conv: unsupported Np %d", L.Np);
-  }
-  if (want_dbg && rc == LDIC_OK) {     // debugging aid only: synchronises
-    unsigned long long h[32];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[ldic timing] kind %d Np %d tiles/cta %llu stages %llu | mma total %llu cyc: wait_full %llu wait_buf %llu wait_x2 %llu "
-            "(per stage: total %.0f wait_full %.0f) | producer total %llu wait_empty %llu\n", d->kind, L.Np, h[5], h[4], h[0], h[1], h[2], h[3],
-            h[4] ? (double)h[0] / h[4] : 0.0, h[4] ? (double)h[1] / h[4] : 0.0, h[8], h[9]);
-    fprintf(stderr, "[ldic timing]   epilogue total %llu cyc over %llu tiles: wait_acc %llu wait_norm %llu wait_slots %llu; mma wait_afull %llu\n",
-            h[16], h[20], h[17], h[18], h[19], h[6]);
-    fprintf(stderr, "[ldic timing]   epilogue busy: pass 1 (acc -> x^2 written) %llu, pass 2 + stores (or whole epilogue without GDN) %llu\n", h[21], h[22]);
-  }
+  if (pl->P.dbg) cudaMemsetAsync(pl->P.dbg, 0, 32 * sizeof(unsigned long long), st);
+  rc = launch_plan(*pl, st);
+  if (rc == LDIC_OK && pl->P.dbg) print_debug_timing(*pl, st);
   return rc;
 }
 }  // namespace
+
+extern "C" int ldic_conv_plan_cache_size(void) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  return (int)g_plans.size();
+}
+extern "C" void ldic_conv_plan_cache_clear(void) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_plans.clear();
+}
 
 // ---------------------------------------------------------------------------------
 // CUDA-core fp32 direct convolution of the same layer kinds (validation aid).
@@ -2889,7 +2618,7 @@ extern "C" int ldic_conv_forward_f32_reference_kernel(const LdicConvDesc* d, con
   for (int j = 0; j < kMaxJobs; ++j) T.jobs[j] = L.jobs[j];
   for (int t = 0; t < kMaxTaps; ++t) { T.taps[t] = L.taps[t]; T.ky[t] = (signed char)L.tap_ky[t][0]; T.kx[t] = (signed char)L.tap_kx[t][0]; }
   long long total = (long long)T.njobs * T.B * T.Hg * T.Wg * T.Cout;
-  int grid = (int)((total + 255) / 256 > kNumSMs * 16 ? kNumSMs * 16 : (total + 255) / 256);
+  int grid = (int)((total + 255) / 256 > num_sms() * 16 ? num_sms() * 16 : (total + 255) / 256);
   k_conv_ref<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nhwc, w, bias, y_nhwc, T);
   return check_launch("k_conv_ref");
 }

@@ -3,11 +3,44 @@
 // sm_100a; every kernel is a coalesced, vectorised streaming pass.
 #include "common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace ldic {
 thread_local char g_err[512] = {0};
 std::atomic<long long> g_launches{0};
 std::mutex g_init_mu;
+
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return dev;
+}
+int num_sms() {
+  static std::atomic<int> sms[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    if (n > kMaxSMs) n = kMaxSMs;
+    sms[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
+static Tuning g_tuning = [] {
+  auto env = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  Tuning t;
+  t.debug_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
+  t.debug_timing = getenv("LDIC_DEBUG_TIMING") != nullptr;
+  t.gdn_insert = env("LDIC_GDN_INSERT", 0);
+  t.stages_cap = env("LDIC_STAGES", 0);
+  t.tail_wide = env("LDIC_TAIL_WIDE", 1);
+  t.lik_grid = env("LDIC_LIK_GRID", 0);
+  t.epoch = 0;
+  return t;
+}();
+const Tuning& tuning() { return g_tuning; }
 }  // namespace ldic
 
 using namespace ldic;
@@ -15,6 +48,24 @@ using namespace ldic;
 extern "C" int ldic_version(void) { return 100; }
 extern "C" const char* ldic_last_error(void) { return g_err; }
 extern "C" long long ldic_launch_count(void) { return g_launches.load(); }
+extern "C" int ldic_set_tuning(const char* key, int value) {
+  if (!key) return fail(LDIC_EINVAL, "set_tuning: null key");
+  Tuning& t = const_cast<Tuning&>(tuning());
+  int* f = nullptr;
+  if (!strcmp(key, "debug_nostore")) f = &t.debug_nostore;
+  else if (!strcmp(key, "debug_timing")) f = &t.debug_timing;
+  else if (!strcmp(key, "gdn_insert")) f = &t.gdn_insert;
+  else if (!strcmp(key, "stages")) f = &t.stages_cap;
+  else if (!strcmp(key, "tail_wide")) f = &t.tail_wide;
+  else if (!strcmp(key, "lik_grid")) f = &t.lik_grid;
+  if (!f) return fail(LDIC_EINVAL, "set_tuning: unknown key '%s'", key);
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  const int old = *f;
+  *f = value;
+  ++t.epoch;
+  return old;
+}
+
 extern "C" int ldic_check_device(int dev) {
   cudaDeviceProp p;
   LDIC_CUDA(cudaGetDeviceProperties(&p, dev));
@@ -44,7 +95,8 @@ __global__ void k_nonneg(const float* __restrict__ p, float bound, float pedesta
     o[i] = __fsub_rn(__fmul_rn(t, t), pedestal);
   }
 }
-static inline int grid_for(size_t n, int threads = 256, int max_blocks = kNumSMs * 8) {
+static inline int grid_for(size_t n, int threads = 256, int max_blocks = 0) {
+  if (max_blocks <= 0) max_blocks = num_sms() * 8;
   size_t b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
   return (int)(b > (size_t)max_blocks ? max_blocks : b);
@@ -173,7 +225,7 @@ extern "C" int ldic_gdn_nchw_f32(const float* x, const float* beta_eff, const fl
 // a6+a7+a8+a9: quantise + Gaussian likelihood + sum(ln L), one streaming pass.
 // ------------------------------------------------------------------------------------
 constexpr int kLikThreads = 256;
-constexpr int kLikMaxBlocks = kNumSMs * 32;
+constexpr int kLikMaxBlocks = kMaxSMs * 32;
 
 struct LikWs {
   unsigned int ticket;
@@ -472,8 +524,8 @@ extern "C" int ldic_round_likelihood_bpp(const LdicLikelihoodArgs* a, void* stre
   const bool fast = vec4 && a->form == 0 && P.mu_mode == 2 && P.sg_mode == 2 && a->quant <= 1;
   if (fast) {
     // 5 CTAs of 256 threads per SM measured best on B200 (5.55 TB/s; 8/SM: 4.9, 32/SM: 5.5)
-    int gmax = 5 * kNumSMs;
-    if (const char* e = getenv("LDIC_LIK_GRID")) { int g = atoi(e) * kNumSMs; if (g >= 1 && g <= kLikMaxBlocks) gmax = g; }   // tuning aid
+    int gmax = 5 * num_sms();
+    if (tuning().lik_grid > 0) { int g = tuning().lik_grid * num_sms(); if (g >= 1 && g <= kLikMaxBlocks) gmax = g; }   // tuning aid
     if (grid > gmax) grid = gmax;
     if (a->quant == 1) {
       if (a->sigma_is_log) k_likelihood_fast<1, true><<<grid, kLikThreads, 0, st>>>(P);
@@ -570,7 +622,7 @@ extern "C" int ldic_mse_sum(const float* x, const float* x_tilde, int B, long lo
   if (B < 0 || chw < 0) return fail(LDIC_EINVAL, "mse: bad shape");
   if (B == 0 || chw == 0) return LDIC_OK;
   long long blocks = (chw / 4 + 255) / 256;
-  int per_img = (int)(blocks < 1 ? 1 : (blocks > kNumSMs * 4 ? kNumSMs * 4 : blocks));
+  int per_img = (int)(blocks < 1 ? 1 : (blocks > num_sms() * 4 ? num_sms() * 4 : blocks));
   k_mse_sum<<<dim3(per_img, B), 256, 0, (cudaStream_t)stream>>>(x, x_tilde, chw, clamp_pm1, sq_err);
   return check_launch("k_mse_sum");
 }
@@ -623,7 +675,7 @@ extern "C" int ldic_syntax_conv_mse(const float* x_nchw, const float* xt_nhwc, c
   if (B <= 0 || H <= 0 || W <= 0) return (B == 0 || H == 0 || W == 0) ? LDIC_OK : fail(LDIC_EINVAL, "syntax_conv_mse: bad shape");
   long long HW = (long long)H * W;
   long long blocks = (HW + 255) / 256;
-  int per_img = (int)(blocks > kNumSMs * 4 ? kNumSMs * 4 : blocks);
+  int per_img = (int)(blocks > num_sms() * 4 ? num_sms() * 4 : blocks);
   dim3 grid(per_img, B);
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 16) k_syntax_conv_mse<16><<<grid, 256, 0, st>>>(x_nchw, xt_nhwc, w, HW, x_tilde_nchw, sq_err);
@@ -709,6 +761,19 @@ __global__ void k_latent_prep(const float* __restrict__ y, size_t n, __nv_bfloat
     if (yrf) yrf[i] = r;
   }
 }
+// uint8 levels -> fp32 (u/255)*2-1: torchvision ToTensor followed by eval_net.py:84, the same two correctly rounded
+// fp32 operations per sample (division by 255, then *2 and -1).
+__global__ void k_u8_to_f32_pm1(const unsigned char* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = __fsub_rn(__fmul_rn(__fdiv_rn((float)x[i], 255.f), 2.f), 1.f);
+}
+extern "C" int ldic_u8_to_f32_pm1(const unsigned char* x, float* y, size_t n, void* stream) {
+  if (n == 0) return LDIC_OK;
+  if (!x || !y) return fail(LDIC_EINVAL, "u8_to_f32_pm1: null tensor");
+  k_u8_to_f32_pm1<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  return check_launch("k_u8_to_f32_pm1");
+}
+
 extern "C" int ldic_latent_prep(const float* y, size_t n, void* y_round_bf16, void* y_abs_bf16, float* y_round_f32,
                                 void* stream) {
   if (n == 0) return LDIC_OK;
@@ -798,7 +863,7 @@ extern "C" int ldic_ctx_pack_input(const void* y_round_bf16, const float* h2, vo
   if (P <= 0) return LDIC_OK;
   if (N <= 0 || N % 8) return fail(LDIC_EINVAL, "ctx_pack_input: N must be a multiple of 8");
   long long total = P * (N / 8) * 2;
-  int grid = (int)((total + 255) / 256 > kNumSMs * 16 ? kNumSMs * 16 : (total + 255) / 256);
+  int grid = (int)((total + 255) / 256 > num_sms() * 16 ? num_sms() * 16 : (total + 255) / 256);
   k_ctx_pack_input<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)y_round_bf16, (const float4*)h2, (uint4*)x, P, N / 8);
   return check_launch("k_ctx_pack_input");
 }

@@ -48,17 +48,24 @@ template <int COUT>
 __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float* __restrict__ x, long long xs,
                                                                      const float* __restrict__ wp,
                                                                      const float* __restrict__ bias, float* __restrict__ y,
-                                                                     int B, int H, int W, int Ho, int Wo, int Cin) {
-  extern __shared__ __align__(16) float s_w[];                         // [9][Cin][COUT]
+                                                                     int B, int H, int W, int Ho, int Wo, int Cin,
+                                                                     int cslice) {
+  extern __shared__ __align__(16) float s_w[];                         // [9][cslice][COUT]: one channel slice of the weights
   __shared__ float s_red[kScGroups / 2][kScPix][COUT + 1];
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-  {
-    const int n16 = 9 * Cin * COUT / 4;                                // 16-byte chunks
+  // the layer's weights are staged one slice of `cslice` input channels at a time (all of them when they fit: N = 192;
+  // PredictionModel_Syntax.down0 of the N = 384 model needs three slices of 128)
+  auto stage_weights = [&](int s0, int cs) {
+    const int per_tap = cs * COUT / 4;                                 // 16-byte chunks per tap
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_w);
-    for (int i = threadIdx.x; i < n16; i += kScThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(wp + (size_t)i * 4) : "memory");
+    for (int i = threadIdx.x; i < 9 * per_tap; i += kScThreads) {
+      const int tap = i / per_tap, r = i - tap * per_tap;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u),
+                   "l"(wp + ((size_t)tap * Cin + s0) * COUT + (size_t)r * 4) : "memory");
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  };
+  stage_weights(0, Cin < cslice ? Cin : cslice);
   const long long npix = (long long)B * Ho * Wo;
   const long long p = (long long)blockIdx.x * kScPix + lane;
   const bool live = p < npix;
@@ -68,7 +75,11 @@ __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float
 #pragma unroll
   for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
   const int ck = Cin < kScChunk ? Cin : kScChunk;          // channels per chunk (16 or 32)
-  const int nchunk = Cin / ck, npairs = 9 * nchunk;
+#pragma unroll 1
+  for (int s0 = 0; s0 < Cin; s0 += cslice) {
+  const int cs = Cin - s0 < cslice ? Cin - s0 : cslice;
+  if (s0 > 0) { __syncthreads(); stage_weights(s0, cs); }   // every warp is done with the previous slice
+  const int nchunk = cs / ck, npairs = 9 * nchunk;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 #pragma unroll 1
@@ -77,7 +88,7 @@ __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float
     const int ky = tap / 3, kx = tap - ky * 3;
     const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
     const bool in = live && iy >= 0 && iy < H && ix >= 0 && ix < W;
-    const float* xp = x + (((long long)b * H + iy) * W + ix) * xs + c0;
+    const float* xp = x + (((long long)b * H + iy) * W + ix) * xs + s0 + c0;
     float xv[kScChunk / 8][8];
 #pragma unroll
     for (int j8 = 0; j8 < kScChunk / 8; ++j8) {
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float
         for (int e = 0; e < 8; ++e) xv[j8][e] = 0.f;
       }
     }
-    const float4* wr = reinterpret_cast<const float4*>(s_w + ((size_t)tap * Cin + c0) * COUT);
+    const float4* wr = reinterpret_cast<const float4*>(s_w + ((size_t)tap * cs + c0) * COUT);
 #pragma unroll
     for (int j = 0; j < kScChunk; ++j) {
       if (j < ck) {                                          // warp-uniform
@@ -102,6 +113,7 @@ __global__ void __launch_bounds__(kScThreads) k_small_conv3x3s2_relu(const float
         }
       }
     }
+  }
   }
   // fixed-order tree over the 8 warps: (g) += (g + 4), then warp 0 adds warps 1, 2, 3
   if (g >= kScGroups / 2) {
@@ -142,17 +154,22 @@ int launch_small_conv(const float* x, long long xs, const float* wp, const float
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long npix = (long long)B * Ho * Wo;
   const unsigned grid = (unsigned)((npix + kScPix - 1) / kScPix);
-  const size_t smem = (size_t)9 * Cin * COUT * sizeof(float);
-  if (smem > 160 * 1024) return fail(LDIC_EINVAL, "syntax branch: 3x3 weights of %d x %d channels do not fit in shared memory", Cin, COUT);
+  const int ck = Cin < kScChunk ? Cin : kScChunk;
+  int cslice = (int)((160 * 1024) / (9 * COUT * sizeof(float))) / ck * ck;     // input channels whose weights fit at once
+  if (cslice > Cin) cslice = Cin;
+  if (cslice < ck) return fail(LDIC_EINVAL, "syntax branch: 3x3 weights of %d x %d channels do not fit in shared memory", Cin, COUT);
+  const size_t smem = (size_t)9 * cslice * COUT * sizeof(float);
   {
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) return fail(LDIC_ECUDA, "syntax branch: bad current device");
     std::lock_guard<std::mutex> init_lock(g_init_mu);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    if (!attr_set[dev]) {
       LDIC_CUDA(cudaFuncSetAttribute(k_small_conv3x3s2_relu<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set = true;
+      attr_set[dev] = true;
     }
   }
-  k_small_conv3x3s2_relu<COUT><<<grid, kScThreads, smem, st>>>(x, xs, wp, bias, y, B, H, W, Ho, Wo, Cin);
+  k_small_conv3x3s2_relu<COUT><<<grid, kScThreads, smem, st>>>(x, xs, wp, bias, y, B, H, W, Ho, Wo, Cin, cslice);
   return check_launch("k_small_conv3x3s2_relu");
 }
 

@@ -21,7 +21,7 @@ namespace {
 constexpr int kTpThreads = 256;
 constexpr int kTpMaxPlanes = 8;
 
-struct TpWs { double partial[kTpMaxPlanes][kNumSMs * 8]; unsigned int ticket; };
+struct TpWs { double partial[kTpMaxPlanes][kMaxSMs * 8]; unsigned int ticket; };
 
 // mass of N(0, s) over [a, b] (a <= b), erfc form (keeps the tails), floor 1e-30 so that ratios stay finite
 __device__ __forceinline__ float gauss_mass(float a, float b, float inv_s_sqrt2) {
@@ -111,7 +111,7 @@ extern "C" int ldic_tritplane_likelihood(const float* v, const float* mu, const 
     return LDIC_OK;
   }
   long long blocks = (n + kTpThreads - 1) / kTpThreads;
-  const int grid = (int)(blocks > kNumSMs * 8 ? kNumSMs * 8 : blocks);
+  const int grid = (int)(blocks > num_sms() * 8 ? num_sms() * 8 : blocks);
   k_tritplane<<<grid, kTpThreads, 0, (cudaStream_t)stream>>>(v, mu, sigma, n, L, scale_bound, lik_bound, planes, q_out,
                                                              sum_ln_per_plane, (TpWs*)workspace);
   return check_launch("k_tritplane");

@@ -208,11 +208,13 @@ __global__ void __launch_bounds__(256, 2) k_window_attention(WaParams P) {
 template <int HD, int N>
 int launch_wa(const WaParams& P, cudaStream_t st) {
   const size_t smem = (size_t)N * (3 * P.C * 2 + 16);
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return fail(LDIC_ECUDA, "window attention: bad current device");
   std::lock_guard<std::mutex> init_lock(g_init_mu);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (!attr_set[dev]) {
     LDIC_CUDA(cudaFuncSetAttribute(k_window_attention<HD, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   if (smem > 200 * 1024) return fail(LDIC_EINVAL, "window attention: shared memory budget exceeded (%zu)", smem);
   const int nwin = P.B * (P.H / P.ws) * (P.W / P.ws);

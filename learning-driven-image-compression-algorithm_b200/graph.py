@@ -31,9 +31,9 @@ class GraphedEvaluator:
         if not inputs:
             raise ops.LdicError("GraphedEvaluator needs at least one static input buffer")
         for x in inputs:
-            if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
-                    and x.dim() == 4 and x.shape == inputs[0].shape):
-                raise ops.LdicError("GraphedEvaluator: inputs must be contiguous CUDA fp32 (B,3,H,W) tensors of one shape")
+            if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.is_contiguous()
+                    and x.dim() == 4 and x.shape == inputs[0].shape and x.dtype == inputs[0].dtype):
+                raise ops.LdicError("GraphedEvaluator: inputs must be contiguous CUDA fp32 / uint8 (B,3,H,W) tensors of one shape")
         self.net, self.group, self.inputs = net, group, list(inputs)
         self.rd_kwargs = dict(rd_kwargs or {})
         B, _, H, W = inputs[0].shape

@@ -33,7 +33,7 @@ class LowerBound(nn.Module):
         self._bound = float(self.bound.detach().cpu()[0])
 
     def forward(self, x):
-        return ops.lower_bound(x, self._bound)
+        return torch.ops.ldic.lower_bound(x.contiguous(), self._bound)      # dispatcher op with the reference's backward
 
 
 class NonNegativeParametrizer(nn.Module):
@@ -56,29 +56,17 @@ class NonNegativeParametrizer(nn.Module):
         if x.requires_grad and torch.is_grad_enabled():
             out = self.lower_bound(x)
             return out ** 2 - self.pedestal
-        return ops.nonneg_reparam(x, self.lower_bound._bound, self._pedestal)
-
-
-class _RoundSTE(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x):
-        # round on our kernel (quant mode 1), identity gradient: model/net.py:416-426
-        _, _, yf = ops.latent_prep(x, want_round_bf16=False, want_abs_bf16=False, want_round_f32=True)
-        return yf
-
-    @staticmethod
-    def backward(ctx, g):
-        return g
+        return torch.ops.ldic.nonneg_reparam(x.contiguous(), self.lower_bound._bound, self._pedestal)
 
 
 def bypass_round(x):
-    """model/net.py:426."""
-    return _RoundSTE.apply(x)
+    """model/net.py:416-426: round on our kernel (quant mode 1), identity gradient (torch.ops.ldic.round_ste)."""
+    return torch.ops.ldic.round_ste(x.contiguous())
 
 
 def ste_round(x):
     """ops/ops.py:20-34: round(x) - x.detach() + x (evaluated in that order)."""
-    return _RoundSTE.apply(x) - x.detach() + x
+    return torch.ops.ldic.round_ste(x.contiguous()) - x.detach() + x
 
 
 class _GDNBase(nn.Module):
@@ -111,7 +99,7 @@ class GDN(_GDNBase):
 
     def forward(self, x):
         be, ge = self._effective(*self.constants())
-        return ops.gdn_nchw(x, be, ge, self.inverse, use_rsqrt=True)
+        return torch.ops.ldic.gdn(x.contiguous(), be, ge, self.inverse, True)
 
 
 class _ModelGDN(_GDNBase):
@@ -136,7 +124,7 @@ class _ModelGDN(_GDNBase):
 
     def forward(self, inputs):
         be, ge = self._effective(*self.constants())
-        return ops.gdn_nchw(inputs, be, ge, self._inverse, use_rsqrt=False)
+        return torch.ops.ldic.gdn(inputs.contiguous(), be, ge, self._inverse, False)
 
 
 class ModelGDN(_ModelGDN):

@@ -11,14 +11,16 @@ Kernel coverage: g_a + GDN (a1,a2,a3), h_a (a4), h_s (a5), rounding
 (a6), GaussianModel likelihoods (a7), bpp reduction (a9), g_s + IGDN (a10),
 batch_conv + MSE/PSNR (a11) and the context model PredictionModel_Context
 (TMA patch gather + 3 convs + fc on the tcgen05 kernel) run on
-libldic_b200.  The tiny syntax branch (Syntax_Model, PredictionModel_Syntax,
-conv_generator: < 0.1 % of the FLOPs) runs as stock torch ops on the GPU.
+libldic_b200, and so does the small syntax branch (Syntax_Model, PredictionModel_Syntax, conv_generator:
+``ldic_syntax_branch``).  Both widths of the reference are supported: N=192/M=16 and the
+``is_high`` model N=384/M=32 (model/net.py:446-451; 384 accumulator columns run on ``conv_wide_kernel``).
+
+No torch-op implementation of any stage lives in this module; tests that cross-check a stage against stock
+torch ops pass their own implementation through ``rd_forward(..., overrides=...)``.
 """
 from __future__ import annotations
 
-import math
-import os
-from typing import Dict, Optional
+from typing import Callable, Dict, Optional
 
 import torch
 import torch.nn as nn
@@ -101,7 +103,6 @@ class PredictionModel_Context(nn.Module):
                                        nn.Conv2d(dim, dim, 3, 1, 1), nn.LeakyReLU(0.2))
         self.fc = nn.Linear(dim * 2 * 2, outdim)
         self.flatten = nn.Flatten()
-        self.max_patches_per_chunk = 32768
 
     @staticmethod
     def sample(x, masked):
@@ -144,20 +145,6 @@ class PredictionModel_Context(nn.Module):
         t = L[2](t)            # (P,2,2,N)
         return L[3](t)         # (P,1,2,Cp) fp32
 
-    def raw(self, y_rounded, h_tilde):
-        """torch-op formulation (unfold gather + cuDNN), kept as the GPU cross-check of raw_tc.
-        fc output (b*h*w, 2c): [:, :c] = mu, [:, c:] = log sigma, rows in (b,h,w) order."""
-        b, c, h, w = y_rounded.shape
-        outs = []
-        rows_per_img = h * w
-        imgs_per_chunk = max(1, self.max_patches_per_chunk // rows_per_img)
-        for i0 in range(0, b, imgs_per_chunk):
-            ys = self.sample(y_rounded[i0:i0 + imgs_per_chunk], True)
-            hs = self.sample(h_tilde[i0:i0 + imgs_per_chunk], False)
-            t = self.transform(torch.cat([ys, hs], 1))
-            outs.append(self.fc(self.flatten(t)))
-        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
-
     def forward(self, y_rounded, h_tilde, y_sampler=None, h_sampler=None):
         """Module surface of the reference: (B,c,h,w) rounded content latent + (B,N,h,w) h_s output
         -> (mu, sigma) as NCHW views of (b,h,w,c) storage (model/net.py:313-319)."""
@@ -182,9 +169,7 @@ class Net(nn.Module):
         self.test_size = test_size
         self.post_processing = post_processing
         self.is_high = is_high
-        N, M = (384, 32) if is_high else (192, 16)
-        if N > 256:
-            raise NotImplementedError("is_high (N=384): fused GDN epilogue supports up to 256 channels in this round")
+        N, M = (384, 32) if is_high else (192, 16)                 # model/net.py:446-451
         self.M, self.N = M, N
         self.a_model = analysisTransformModel(3, [N, N, N, N])
         self.s_model = synthesisTransformModel(N - M, [N, N, N, M])
@@ -201,22 +186,32 @@ class Net(nn.Module):
         self.register_parameter('z2_sigma', self.v_z2_sigma)       # same tensor under two names (model/net.py:482-488)
         self.prediction_model = PredictionModel_Context(in_dim=2 * N - M, dim=N, outdim=(N - M) * 2)
         self.prediction_model_syntax = PredictionModel_Syntax(in_dim=N, dim=M, outdim=M * 2)
-        self.context_tf32 = True
-        self.context_on_torch = False     # True: run the context transform with torch ops (cross-check in tests)
-        self.syntax_on_torch = os.environ.get("LDIC_SYNTAX_FUSED", "1") == "0"   # True: syntax branch as stock torch ops
-        self.tail_fused = os.environ.get("LDIC_TAIL_FUSED", "1") != "0"          # batch_conv + MSE inside the last deconv
-        # g_s depends on round(y) only (its last layer also on the syntax filters): run it on a second stream next to
-        # the hyperprior / syntax / context chain, whose small-grid kernels leave most SMs idle
-        # -- measured NEGATIVE (3.45 vs 3.23 ms per step): the conv kernels are persistent with a static tile partition,
-        # so two of them never share the SMs usefully and a small concurrent kernel delays 12..48 CTAs of the big one
-        # (tail effect).  Kept as an experiment switch (LDIC_OVERLAP=1), off by default.
-        self.overlap_streams = os.environ.get("LDIC_OVERLAP", "0") == "1"
+        self.tail_fused = True            # batch_conv + MSE inside the last deconv's epilogue (False: separate kernels)
+        # SM partition: the hyperprior / syntax chain (h_a, likelihood z, h_s, syntax branch: small grids of 12..48 CTAs)
+        # runs on a side stream on `side_sms` SMs while the first three g_s deconvs, which depend on round(y) only,
+        # run on the remaining SMs of the main stream (persistent kernels with their grids capped accordingly).
+        self.side_sms = 0                 # 0: single stream
         self._side_streams = {}
+        # forward(x, 'test'): transparent CUDA-graph capture / replay per input shape (see forward)
+        self.auto_graph = True
+        self._graphs = {}
+        self._discarded_logged = False
 
     # -- checkpoint compatibility ---------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        kept = {k: v for k, v in state_dict.items()
-                if not (k.endswith("_sampler.sample_filter") or k.startswith(_DISCARDED_PREFIXES))}
+        kept, dropped = {}, []
+        for k, v in state_dict.items():
+            if k.endswith("_sampler.sample_filter") or k.startswith(_DISCARDED_PREFIXES):
+                dropped.append(k)
+            else:
+                kept[k] = v
+        if dropped and not self._discarded_logged:
+            import logging
+            logging.getLogger("ldic_b200").info(
+                "Net.load_state_dict: %d checkpoint entries outside the rate-distortion path are not used "
+                "(one-hot sampler filters, HAN head, add_mean), e.g. %s", len(dropped), dropped[0])
+            self._discarded_logged = True
+        self._graphs.clear()
         return super().load_state_dict(kept, strict=strict, assign=assign)
 
     def base_params(self):
@@ -241,80 +236,83 @@ class Net(nn.Module):
     # -- the hot path -----------------------------------------------------------------------
     @torch.no_grad()
     def rd_forward(self, inputs: torch.Tensor, want_x_hat: bool = False, want_likelihoods: bool = False,
-                   want_xt16: bool = False, per_image_bits: bool = False) -> Dict[str, torch.Tensor]:
+                   want_xt16: bool = False, per_image_bits: bool = False,
+                   overrides: Optional[Dict[str, Callable]] = None) -> Dict[str, torch.Tensor]:
         """Rate-distortion forward of Net.forward(mode='test') (model/net.py:539-871).
         Returns the per-stream sum(ln L) (`bits` = [z, y, syntax]), the exact per-image
-        squared-error sums and, on request, x_hat / likelihood tensors."""
+        squared-error sums and, on request, x_hat / likelihood tensors.
+
+        `inputs`: (B,3,H,W) fp32 in [-1,1], or uint8 = the 8-bit levels of the image; then the first layer applies
+        the reference's map x = (u/255)*2-1 (ToTensor + eval_net.py:84) while it builds its patches and the fused
+        tail compares against the levels, so only 1 byte per sample crosses PCIe.
+        `overrides` (tests only): {"syntax": f(net, y_nchw, h2_nchw) -> (z3, z3_round, first, second, conv_w),
+        "context": f(net, y_nchw, h2_nchw) -> (ctx, row_stride, sigma_offset)} replace a stage of the kernel path."""
         if not inputs.is_cuda:
             raise ops.LdicError("Net runs on CUDA only (no CPU fallback)")
+        with torch.cuda.device(inputs.device):
+            return self._rd_forward(inputs, want_x_hat, want_likelihoods, want_xt16, per_image_bits, overrides or {})
+
+    def _rd_forward(self, inputs, want_x_hat, want_likelihoods, want_xt16, per_image_bits, overrides):
         want_likelihoods = want_likelihoods or per_image_bits
-        x = inputs.contiguous().float()
+        x = inputs.contiguous() if inputs.dtype == torch.uint8 else inputs.contiguous().float()
         B, _, H, W = x.shape
         N, M = self.N, self.M
         if H % 64 or W % 64:
             raise ops.LdicError("H and W must be multiples of 64 (eval_net.py:68-81 pads to 64)")
         h, w = H // 16, W // 16
         P = B * h * w
+        dev = x.device
 
         y = self.a_model.forward_nhwc(x)                                            # :627   (B,h,w,N) fp32 NHWC
         y_round_bf16, y_abs_bf16, _ = ops.latent_prep(y)                            # :197 abs, :741 round
-        overlap = (self.overlap_streams and self.tail_fused and not self.syntax_on_torch and not self.context_on_torch
-                   and self.s_model.has_fused_tail())
-        if overlap:
-            main = torch.cuda.current_stream(x.device)
-            side = self._side_streams.get(x.device.index)
-            if side is None:
-                side = self._side_streams[x.device.index] = torch.cuda.Stream(device=x.device)
-            side.wait_stream(main)                                                  # fork: round(y) is ready
-            with torch.cuda.stream(side):
-                gs_body = self.s_model.forward_nhwc_body(y_round_bf16)              # :800   first three deconv + IGDN
-        z = self.ha_model.forward_nhwc(y_abs_bf16)                                  # :666   (B,h/4,w/4,N) fp32
-        Pz = z.shape[0] * z.shape[1] * z.shape[2]
-        z_hat_bf16 = torch.empty(z.shape, dtype=torch.bfloat16, device=x.device)
-        sigma_z = self.z2_sigma.detach().reshape(N).contiguous()
-        lik_z = torch.empty_like(z) if want_likelihoods else None
-        bits = torch.empty(3, dtype=torch.float32, device=x.device)                 # sum(ln L) of z, y, syntax
-        ops.likelihood_rows(z, Pz, N, v_rs=N, sigma=sigma_z, sigma_mode=1, quant=ops.QUANT_ROUND,             # :676,:781
-                            lik_bound=self.entropy_bottleneck_z2.likelihood_bound,
-                            v_hat_bf16=z_hat_bf16, vb_rs=N, lik=lik_z, sum_out=bits[0:1])
-        h2 = self.hs_model.forward_nhwc(z_hat_bf16)                                 # :681   (B,h,w,N) fp32 NHWC
+        fused_ok = self.tail_fused and self.s_model.has_fused_tail()
+        split = self.side_sms > 0 and fused_ok and not overrides
+        bits = torch.empty(3, dtype=torch.float32, device=dev)                      # sum(ln L) of z, y, syntax
+        lik_z = None
 
-        y_nchw = y.permute(0, 3, 1, 2)                                              # channels-last view, no copy
-        h2_nchw = h2.permute(0, 3, 1, 2)
-        if self.syntax_on_torch:
-            # stock torch ops (cross-check path of tests): Syntax_Model, PredictionModel_Syntax, conv_generator
-            prev_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-            try:
-                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
-                z3_syntax = self.syntax_model(y_nchw[:, :M])                        # :712-719
-                z3_syntax_rounded = torch.round(z3_syntax)                          # :753
-                syn_first, syn_second = self.prediction_model_syntax(z3_syntax_rounded, h2_nchw)   # :789 (mu, sigma) bound swapped
-                conv_w = self.conv_weights_gen(z3_syntax_rounded)                   # :805
-            finally:
-                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
-        else:
-            z3_syntax, z3_syntax_rounded, syn_first, syn_second, conv_w = ops.syntax_branch(
-                y, h2, M, self.syntax_model, self.prediction_model_syntax, self.conv_weights_gen)       # :712-719,:753,:789,:805
-        if overlap:                        # the per-image filters are ready: last deconv + batch_conv + MSE on the side stream
-            side.wait_stream(main)
+        def hyper_chain(sm_limit: int):
+            nonlocal lik_z
+            z = self.ha_model.forward_nhwc(y_abs_bf16, sm_limit=sm_limit)           # :666   (B,h/4,w/4,N) fp32
+            Pz = z.shape[0] * z.shape[1] * z.shape[2]
+            z_hat_bf16 = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
+            sigma_z = self.z2_sigma.detach().reshape(N).contiguous()
+            lik_z = torch.empty_like(z) if want_likelihoods else None
+            ops.likelihood_rows(z, Pz, N, v_rs=N, sigma=sigma_z, sigma_mode=1, quant=ops.QUANT_ROUND,         # :676,:781
+                                lik_bound=self.entropy_bottleneck_z2.likelihood_bound,
+                                v_hat_bf16=z_hat_bf16, vb_rs=N, lik=lik_z, sum_out=bits[0:1])
+            h2 = self.hs_model.forward_nhwc(z_hat_bf16, sm_limit=sm_limit)          # :681   (B,h,w,N) fp32 NHWC
+            if "syntax" in overrides:
+                syn = overrides["syntax"](self, y.permute(0, 3, 1, 2), h2.permute(0, 3, 1, 2))
+            else:
+                syn = ops.syntax_branch(y, h2, M, self.syntax_model, self.prediction_model_syntax,
+                                        self.conv_weights_gen)                      # :712-719,:753,:789,:805
+            return z, h2, syn
+
+        gs_body = None
+        if split:
+            main = torch.cuda.current_stream(dev)
+            side = self._side_streams.get(dev.index)
+            if side is None:
+                side = self._side_streams[dev.index] = torch.cuda.Stream(device=dev)
+            side.wait_stream(main)                                                  # fork: round(y), |y| are ready
             with torch.cuda.stream(side):
-                fused_side = self.s_model.fused_tail(gs_body, x, conv_w.reshape(B, 3, M),                 # :800,:811,:864-868
-                                                     want_x_tilde=want_x_hat, want_out=want_xt16)
-        if self.context_on_torch:          # cross-check path only (tests); the product path is raw_tc
-            prev_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-            try:
-                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(self.context_tf32)
-                y_content_rounded = torch.round(y_nchw[:, M:])                      # :741
-                ctx = self.prediction_model.raw(y_content_rounded, h2_nchw)         # :784  (P, 2(N-M))
-                ctx_rs, ctx_sig_off = ctx.shape[1], N - M
-            finally:
-                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+                z, h2, syn = hyper_chain(self.side_sms)
+            gs_body = self.s_model.forward_nhwc_body(y_round_bf16, sm_limit=-self.side_sms)   # :800 first three deconv + IGDN
+            main.wait_stream(side)                                                  # join
+            if not torch.cuda.is_current_stream_capturing():
+                for t in (z, h2) + tuple(syn):
+                    t.record_stream(main)
+        else:
+            z, h2, syn = hyper_chain(0)
+        z3_syntax, z3_syntax_rounded, syn_first, syn_second, conv_w = syn
 
         Cc = N - M
-        if not self.context_on_torch:
+        if "context" in overrides:
+            ctx, ctx_rs, ctx_sig_off = overrides["context"](self, y.permute(0, 3, 1, 2), h2.permute(0, 3, 1, 2))
+        else:
             ctx = self.prediction_model.raw_tc(y_round_bf16, h2, M)                 # :784  (P,1,2,Cp): mu | log sigma
             ctx_rs, ctx_sig_off = 2 * ctx.shape[-1], ctx.shape[-1]
-        lik_y = torch.empty(B, h, w, Cc, dtype=torch.float32, device=x.device) if want_likelihoods else None
+        lik_y = torch.empty(B, h, w, Cc, dtype=torch.float32, device=dev) if want_likelihoods else None
         ops.likelihood_rows(y, P, Cc, v_rs=N, v_off=M, mu=ctx, mu_mode=2, mu_rs=ctx_rs, mu_off=0,              # :786
                             sigma=ctx, sigma_mode=2, sigma_rs=ctx_rs, sigma_off=ctx_sig_off, sigma_is_log=True,
                             quant=ops.QUANT_ROUND, lik_bound=self.entropy_bottleneck_z3.likelihood_bound,
@@ -325,18 +323,15 @@ class Net(nn.Module):
                                                 lik_bound=self.entropy_bottleneck_z3_syntax.likelihood_bound,
                                                 sum_out=bits[2:3])
 
-        fused = None
-        if overlap:
-            main.wait_stream(side)                                                  # join
-            fused = fused_side
-        elif self.tail_fused:    # g_s with batch_conv + squared level error in the last deconv's epilogue
-            fused = self.s_model.forward_nhwc_fused_tail(y_round_bf16, x, conv_w.reshape(B, 3, M),        # :800,:811,:864-868
-                                                         want_x_tilde=want_x_hat, want_out=want_xt16)
-        if fused is not None:
-            sq_err, x_hat, xt16 = fused
+        if fused_ok:             # g_s with batch_conv + squared level error in the last deconv's epilogue
+            if gs_body is None:
+                gs_body = self.s_model.forward_nhwc_body(y_round_bf16)              # :800
+            sq_err, x_hat, xt16 = self.s_model.fused_tail(gs_body, x, conv_w.reshape(B, 3, M),                # :800,:811,:864-868
+                                                          want_x_tilde=want_x_hat, want_out=want_xt16)
         else:
             xt16 = self.s_model.forward_nhwc(y_round_bf16)                          # :800   (B,H,W,M) fp32 NHWC
-            sq_err, x_hat = ops.syntax_conv_mse(x, xt16, conv_w.reshape(B, 3, M), want_x_tilde=want_x_hat)   # :811,:864-868
+            xf = ops.u8_to_f32_pm1(x) if x.dtype == torch.uint8 else x
+            sq_err, x_hat = ops.syntax_conv_mse(xf, xt16, conv_w.reshape(B, 3, M), want_x_tilde=want_x_hat)   # :811,:864-868
 
         out = {"bits": bits, "sq_err": sq_err}
         if want_x_hat:
@@ -357,10 +352,43 @@ class Net(nn.Module):
         return r[0], v_mse, r[1]
 
     def forward(self, inputs, mode='train', num=1):
+        """model/net.py:539-871 in test mode: (bpp, v_mse[B], v_psnr).
+
+        With `auto_graph` (default) the ~35 launches of a step are captured into a CUDA graph the second time an input
+        shape is seen and replayed afterwards (the input is copied into the graph's static buffer first): the host
+        cost of a step drops from ~35 ctypes calls to one copy and one graph launch.  The returned tensors of a
+        replayed step are clones, so they stay valid across calls like the eager ones."""
         if mode != 'test':
             raise NotImplementedError("only the rate-distortion forward (mode='test') is implemented; training is out of scope")
+        if not inputs.is_cuda:
+            raise ops.LdicError("Net runs on CUDA only (no CPU fallback)")
+        if self.auto_graph and not torch.cuda.is_current_stream_capturing() and ops.PROFILE is None:
+            r = self._graph_forward(inputs)
+            if r is not None:
+                return r
         out = self.rd_forward(inputs)
         return self.metrics(out, inputs.shape[0], inputs.shape[2], inputs.shape[3])
+
+    def _graph_key(self, inputs):
+        return (inputs.device.index, inputs.dtype, tuple(inputs.shape), tuple(self.test_size), self.tail_fused, self.side_sms,
+                tuple((p._version, p.data_ptr()) for p in self.parameters()))
+
+    def _graph_forward(self, inputs):
+        from .graph import GraphedEvaluator
+        key = self._graph_key(inputs)
+        ent = self._graphs.get(key)
+        if ent is None:                      # first sight of this shape: run eagerly, remember it
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            self._graphs[key] = False
+            return None
+        with torch.cuda.device(inputs.device):
+            if ent is False:                 # second sight: capture
+                static = inputs.contiguous().clone()
+                ent = self._graphs[key] = GraphedEvaluator(self, [static])
+            ent.inputs[0].copy_(inputs)
+            bpp, psnr, out = ent(0)
+            return bpp.clone(), out["v_mse"].clone(), psnr.clone()
 
     def forward_dict(self, inputs):
         """CompressAI-style view ({'x_hat', 'likelihoods': {'y','z'}}) that RateDistortionLoss

@@ -33,7 +33,20 @@ def _req(t: torch.Tensor, dtype=None, name="tensor"):
         raise LdicError(f"{name} must be a CUDA tensor (ldic_b200 has no CPU path)")
     if dtype is not None and t.dtype != dtype:
         raise LdicError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's stream: a tensor of another GPU would be dereferenced on the wrong
+        # device.  Net / the module classes enter torch.cuda.device(x.device) themselves; raw op callers must too.
+        raise LdicError(f"{name} lives on {t.device} but the current device is cuda:{torch.cuda.current_device()} "
+                        "(wrap the call in torch.cuda.device(tensor.device))")
     return t
+
+
+def set_tuning(key: str, value: int) -> int:
+    """ldic_set_tuning: change one of the load-time tuning switches (tests / A-B runs); returns the previous value."""
+    r = _L().ldic_set_tuning(key.encode(), int(value))
+    if r < 0:
+        check(r, "ldic_set_tuning")
+    return r
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -45,7 +58,8 @@ def launch_count() -> int:
 
 
 def _workspace(device) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    # one reduction workspace per (device, stream): launches on different streams never share a ticket counter
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
     ws = _ws_cache.get(key)
     if ws is None:
         n = int(_L().ldic_likelihood_workspace_bytes())
@@ -231,7 +245,7 @@ def tritplane_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torc
     if sigma.shape != v.shape or (mu is not None and mu.shape != v.shape):
         raise LdicError("tritplane: v, mu, sigma must have the same shape")
     n = v.numel()
-    key = v.device.index if v.device.index is not None else torch.cuda.current_device()
+    key = (v.device.index if v.device.index is not None else torch.cuda.current_device(), _stream())
     ws = _tp_ws_cache.get(key)
     if ws is None:
         ws = torch.zeros((int(_L().ldic_tritplane_workspace_bytes()) + 7) // 8, dtype=torch.int64, device=v.device)
@@ -323,6 +337,14 @@ def nhwc_to_nchw_f32(x: torch.Tensor, Cc: Optional[int] = None) -> torch.Tensor:
     return y
 
 
+def u8_to_f32_pm1(x: torch.Tensor) -> torch.Tensor:
+    """uint8 levels -> fp32 (u/255)*2-1, the reference's input map (ToTensor + eval_net.py:84), bit-exact."""
+    x = _req(x, torch.uint8, "x").contiguous()
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    check(_L().ldic_u8_to_f32_pm1(_ptr(x), _ptr(y), x.numel(), _stream()), "ldic_u8_to_f32_pm1")
+    return y
+
+
 def latent_prep(y: torch.Tensor, want_round_bf16=True, want_abs_bf16=True, want_round_f32=False):
     y = _req(y, torch.float32, "y").contiguous()
     mk = lambda dt: torch.empty(y.shape, dtype=dt, device=y.device)
@@ -408,9 +430,9 @@ class ConvTC:
             _, _, self.gamma_bf16, self.beta_tiled = gdn_prepare(beta_p, gamma_p, bb, gb, ped, tc_groups=groups,
                                                                  tc_np=self.np_cols)
 
-    def _desc(self, B, H, W) -> ConvDesc:
+    def _desc(self, B, H, W, sm_limit: int = 0) -> ConvDesc:
         return ConvDesc(self.kind, B, H, W, self.cin, self.cout, self.cin_pad, self.cout_pad, self.act,
-                        int(self.out_f32), int(self.aux[0]), int(self.aux[1]))
+                        int(self.out_f32), int(self.aux[0]), int(self.aux[1]), int(sm_limit), 0)
 
     def out_dims(self, B, H, W):
         d = self._desc(B, H, W)
@@ -451,7 +473,9 @@ class ConvTC:
         (ldic_conv_forward_fused_tail).  x: NHWC bf16 layer input; image: NCHW fp32 (B,3,2H,2W); conv_w: (B,3,M).
         Returns (sq_err int64[B], x_tilde NCHW or None, layer output NHWC fp32 or None)."""
         _req(x, torch.bfloat16, "x")
-        image = _req(image, torch.float32, "image").contiguous()
+        if image.dtype not in (torch.float32, torch.uint8):
+            raise LdicError("fused_tail: image must be fp32 in [-1,1] or its uint8 levels")
+        image = _req(image, None, "image").contiguous()
         conv_w = _req(conv_w, torch.float32, "conv_w").contiguous()
         if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
             raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
@@ -459,9 +483,9 @@ class ConvTC:
         if tuple(image.shape) != (B, 3, 2 * H, 2 * W) or conv_w.numel() != B * 3 * self.cout:
             raise LdicError("fused_tail: image must be (B,3,2H,2W) and conv_w (B,3,Cout)")
         sq = torch.zeros(B, dtype=torch.int64, device=x.device)
-        xo = torch.empty_like(image) if want_x_tilde else None
+        xo = torch.empty(image.shape, dtype=torch.float32, device=x.device) if want_x_tilde else None
         out = torch.empty(self.out_dims(B, H, W), dtype=torch.float32, device=x.device) if want_out else None
-        t = _lib.ConvTail(_ptr(image), _ptr(conv_w), _ptr(xo), _ptr(sq), 2 * H, 2 * W)
+        t = _lib.ConvTail(_ptr(image), _ptr(conv_w), _ptr(xo), _ptr(sq), 2 * H, 2 * W, int(image.dtype == torch.uint8), 0)
         d = self._desc(B, H, W)
         prof = PROFILE
         if prof is not None:
@@ -475,11 +499,13 @@ class ConvTC:
             prof.append((self, (B, H, W), e0, e1))
         return sq, xo, out
 
-    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, sm_limit: int = 0) -> torch.Tensor:
+        u8 = False
         if self.kind == _lib.LDIC_CONV_FIRST_5x5S2:
-            _req(x, torch.float32, "x")
+            u8 = x.dtype == torch.uint8          # 8-bit levels: the kernel applies x = (u/255)*2-1 itself (eval_net.py:84)
+            _req(x, torch.uint8 if u8 else torch.float32, "x")
             if x.dim() != 4 or x.shape[1] != self.cin or not x.is_contiguous():
-                raise LdicError(f"first conv input must be a contiguous NCHW fp32 image with {self.cin} channels, got {tuple(x.shape)}")
+                raise LdicError(f"first conv input must be a contiguous NCHW fp32 / uint8 image with {self.cin} channels, got {tuple(x.shape)}")
             B, _, H, W = x.shape
         else:
             _req(x, torch.bfloat16, "x")
@@ -489,7 +515,9 @@ class ConvTC:
         if out is None:
             out = torch.empty(self.out_dims(B, H, W), dtype=torch.float32 if self.out_f32 else torch.bfloat16,
                               device=x.device)
-        d = self._desc(B, H, W)
+        d = self._desc(B, H, W, sm_limit)
+        if u8:
+            d.aux0 = 1
         prof = PROFILE
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -615,8 +643,8 @@ def conv_reference_f32(kind: int, x_nhwc: torch.Tensor, weight: torch.Tensor, bi
     else:
         cout, cin = w.shape[0], w.shape[1]
     B, H, W, _ = x.shape
-    dq = ConvDesc(kind, B, H, W, cin, 8, _pad64(cin), 64, 0, 1, 0, 0)    # shape query only
-    d = ConvDesc(kind, B, H, W, cin, cout, _pad64(cin), 64, 0, 1, 0, 0)
+    dq = ConvDesc(kind, B, H, W, cin, 8, _pad64(cin), 64, 0, 1, 0, 0, 0, 0)    # shape query only
+    d = ConvDesc(kind, B, H, W, cin, cout, _pad64(cin), 64, 0, 1, 0, 0, 0, 0)
     ho, wo = C.c_int(), C.c_int()
     _L().ldic_conv_out_shape(C.byref(dq), C.byref(ho), C.byref(wo))
     y = torch.empty(B, ho.value, wo.value, cout, dtype=torch.float32, device=x.device)

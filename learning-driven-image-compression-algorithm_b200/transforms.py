@@ -86,11 +86,13 @@ class analysisTransformModel(_PlannedTransform):
         return layers
 
     def forward_nhwc(self, x_nchw: torch.Tensor) -> torch.Tensor:
-        """x (B,Cin,H,W) fp32 NCHW -> y (B,H/16,W/16,C) fp32 NHWC."""
+        """x (B,Cin,H,W) NCHW, fp32 in [-1,1] or uint8 levels (mapped like eval_net.py:84) -> y (B,H/16,W/16,C) fp32 NHWC."""
         L = self.plan()
         B, _, H, W = x_nchw.shape
         if H % 16 or W % 16:
             raise ops.LdicError("analysis transform needs H and W to be multiples of 16")
+        if x_nchw.dtype == torch.uint8 and not (self._first_fused and W % 16 == 0):
+            x_nchw = ops.u8_to_f32_pm1(x_nchw)                               # only the fused first layer reads uint8 itself
         if self._first_fused:
             t = L[0](x_nchw.contiguous())                                    # (B,H/2,W/2,C) bf16 NHWC
         elif self._first_im2col:
@@ -156,11 +158,11 @@ class synthesisTransformModel(_PlannedTransform):
     def has_fused_tail(self) -> bool:
         return self.plan()[-1].kind == _lib.LDIC_DECONV_GS_5x5_MERGED
 
-    def forward_nhwc_body(self, y_hat_nhwc_bf16):
+    def forward_nhwc_body(self, y_hat_nhwc_bf16, sm_limit: int = 0):
         """The first three deconv + IGDN layers (they depend on the rounded latent only)."""
         t = y_hat_nhwc_bf16
         for layer in self.plan()[:-1]:
-            t = layer(t)
+            t = layer(t, sm_limit=sm_limit)
         return t
 
     def fused_tail(self, t, image_nchw, conv_w, want_x_tilde=False, want_out=False):
@@ -195,12 +197,12 @@ class h_analysisTransformModel(_PlannedTransform):
                 ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P2, t[4].weight.detach(), t[4].bias.detach(), act=_lib.ACT_NONE,
                            out_f32=True)]
 
-    def forward_nhwc(self, y_abs_nhwc_bf16):
+    def forward_nhwc(self, y_abs_nhwc_bf16, sm_limit: int = 0):
         t = y_abs_nhwc_bf16
         if t.shape[1] % 4 or t.shape[2] % 4:
             raise ops.LdicError("hyper analysis needs latent H and W to be multiples of 4")
         for layer in self.plan():
-            t = layer(t)
+            t = layer(t, sm_limit=sm_limit)
         return t                                       # (B,h/4,w/4,C) fp32 NHWC
 
     def forward(self, inputs):
@@ -229,10 +231,10 @@ class h_synthesisTransformModel(_PlannedTransform):
                 ops.ConvTC(_lib.LDIC_DECONV_S1_3x3, t[4].weight.detach(), t[4].bias.detach(), act=_lib.ACT_NONE,
                            out_f32=True)]
 
-    def forward_nhwc(self, z_hat_nhwc_bf16):
+    def forward_nhwc(self, z_hat_nhwc_bf16, sm_limit: int = 0):
         t = z_hat_nhwc_bf16
         for layer in self.plan():
-            t = layer(t)
+            t = layer(t, sm_limit=sm_limit)
         return t                                       # (B,4h,4w,C) fp32 NHWC
 
     def forward(self, inputs):

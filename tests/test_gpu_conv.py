@@ -159,9 +159,9 @@ def test_deconv_gs_merged_small_cout(ldic, B, H, W):
     close(y, ref, 2e-3, 5e-4)
 
 
-def test_deconv_gs_merged_wide_vs_tap_accumulating_form(ldic, monkeypatch):
-    """The wide-N kernel against the earlier formulation of the same layer (nine N=64 taps accumulated in TMEM,
-    LDIC_TAIL_WIDE=0): same operands, fp32 accumulation on both sides, only the summation order of the three dx
+def test_deconv_gs_merged_wide_vs_tap_accumulating_form(ldic):
+    """The wide-N kernel against the generic formulation of the same layer (nine N=64 taps accumulated in TMEM,
+    tuning switch tail_wide=0): same operands, fp32 accumulation on both sides, only the summation order of the three dx
     contributions differs -- which can flip the bf16 rounding of an x^2 operand of the IGDN contraction, hence the
     bf16-operand tolerance of the oracle comparisons rather than an fp32 one."""
     L = ldic._lib
@@ -172,8 +172,11 @@ def test_deconv_gs_merged_wide_vs_tap_accumulating_form(ldic, monkeypatch):
     layer = ldic.ops.ConvTC(L.LDIC_DECONV_GS_5x5_MERGED, w.cuda(), b.cuda(), act=L.ACT_IGDN, out_f32=True,
                             gdn=(bp.cuda(), gp.cuda()) + rp.model_gdn_constants())
     y_wide = layer(x).cpu()
-    monkeypatch.setenv("LDIC_TAIL_WIDE", "0")
-    y_taps = layer(x).cpu()
+    prev = ldic.ops.set_tuning("tail_wide", 0)
+    try:
+        y_taps = layer(x).cpu()
+    finally:
+        ldic.ops.set_tuning("tail_wide", prev)
     close(y_wide, y_taps, 2e-3, 5e-4)
 
 

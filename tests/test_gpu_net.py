@@ -102,8 +102,18 @@ def test_syntax_branch_kernels_vs_torch_modules(ldic, B, H, W):
     # whole forward: torch-op syntax branch and the kernel branch agree
     x = dw.make_input(3, B, H, W).cuda()
     o1 = net.rd_forward(x)
-    net.syntax_on_torch = True
-    o2 = net.rd_forward(x)
+
+    def syntax_torch(net_, y_nchw, h2_nchw):        # the stage as stock fp32 torch ops (model/net.py:712-719,:753,:789,:805)
+        prev_ = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            z3_ = net_.syntax_model(y_nchw[:, :net_.M])
+            z3r_ = torch.round(z3_)
+            first, second = net_.prediction_model_syntax(z3r_, h2_nchw)
+            return z3_, z3r_, first, second, net_.conv_weights_gen(z3r_)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_
+    o2 = net.rd_forward(x, overrides={"syntax": syntax_torch})
     assert torch.allclose(o1["bits"], o2["bits"], rtol=1e-5)
     assert (o1["sq_err"] - o2["sq_err"]).abs().max().item() <= 1e-4 * o2["sq_err"].max().item()
 
@@ -215,15 +225,16 @@ def test_graph_replay_is_bit_identical_to_eager(ldic):
             assert torch.equal(bpp, e[2]) and torch.equal(psnr, e[3]) and torch.equal(out["v_mse"], e[4])
 
 
-def test_two_stream_forward_is_bit_identical_to_single_stream(ldic):
-    """g_s on the side stream (Net.overlap_streams) changes the schedule, not one bit of the results."""
-    B, H, W = 2, 64, 128
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (4, 256, 384)])
+def test_two_stream_forward_is_bit_identical_to_single_stream(ldic, B, H, W):
+    """The SM partition (Net.side_sms: hyperprior / syntax chain on a side stream next to the first three g_s deconvs,
+    grids capped through LdicConvDesc.sm_limit) changes the schedule, not one bit of the results."""
     net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
     net.load_state_dict(dw.make_state_dict(0), strict=True)
     x = dw.make_input(3, B, H, W).cuda()
     res = []
-    for ov in (True, False, True):
-        net.overlap_streams = ov
+    for ov in (28, 0, 28):
+        net.side_sms = ov
         out = net.rd_forward(x, want_x_hat=True)
         torch.cuda.synchronize()
         res.append((out["bits"].clone(), out["sq_err"].clone(), out["x_hat"].clone()))

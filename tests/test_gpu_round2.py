@@ -1,0 +1,273 @@
+"""Round-2 GPU parity: width-generic kernels (hidden 128 / latent 192, and the N=384 `--high` model on the
+wide-accumulator kernel), the uint8 input path, the SM partition, transparent graph replay, launch-plan cache,
+and the torch.library operator layer.  Golden fixtures come from the unmodified reference
+(tests/golden/make_golden_r2.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import det_weights as dw
+from oracle import ref_path as rp
+from test_gpu_conv import bf, close, gdn_oracle_bf16, gdn_params, rnd, to_nhwc_bf16
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+BPP_RTOL, PSNR_ATOL_DB = 5e-3, 1e-2
+
+
+def L(name):
+    d = np.load(os.path.join(G, name))
+    return {k: torch.from_numpy(np.asarray(d[k])) for k in d.files}
+
+
+@pytest.fixture(scope="module")
+def ldic():
+    import ldic_b200
+    ldic_b200._lib.check(ldic_b200._lib.load().ldic_check_device(0), "device")
+    return ldic_b200
+
+
+def rel(a, b):
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+
+
+# ---------------------------------------------------------------------------------------------------
+# wide-accumulator kernel (384 output channels)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,act", [(1, 16, 16, "gdn"), (2, 20, 36, "gdn"), (3, 10, 14, "none"), (1, 64, 96, "relu")])
+def test_wide_conv_s2_384(ldic, B, H, W, act):
+    """ZeroPad2d((1,2,1,2)) + Conv2d(384,384,5,2) (+GDN) on conv_wide_kernel vs fp32 conv2d on the same bf16 operands."""
+    K = ldic._lib
+    C = 384
+    x = bf(rnd((B, C, H, W), 1))
+    w, b = rnd((C, C, 5, 5), 2, 0.01), rnd((C,), 3, 0.1)
+    ref = F.conv2d(F.pad(x, (1, 2, 1, 2)), bf(w), b, stride=2)
+    kw = {}
+    if act == "gdn":
+        bp, gp = gdn_params(C, 4)
+        kw = dict(act=K.ACT_GDN, gdn=(bp.cuda(), gp.cuda()) + rp.model_gdn_constants())
+        ref = gdn_oracle_bf16(ref, bp, gp, False)
+    elif act == "relu":
+        kw = dict(act=K.ACT_RELU)
+        ref = F.relu(ref)
+    layer = ldic.ops.ConvTC(K.LDIC_CONV_S2_5x5_P12, w.cuda(), b.cuda(), out_f32=True, **kw)
+    assert layer.np_cols == 384
+    y = layer(to_nhwc_bf16(x)).cpu().permute(0, 3, 1, 2)
+    assert y.shape == ref.shape
+    close(y, ref, 2e-3, 1e-3)
+    y16 = ldic.ops.ConvTC(K.LDIC_CONV_S2_5x5_P12, w.cuda(), b.cuda(), out_f32=False, **kw)(to_nhwc_bf16(x))
+    assert y16.dtype == torch.bfloat16
+    close(y16.float().cpu().permute(0, 3, 1, 2), ref, 1e-2, 4e-3)           # bf16 output rounding
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 8), (2, 5, 11)])
+def test_wide_deconv_gs_igdn_384(ldic, B, H, W):
+    """ZeroPad2d((1,0,1,0)) + ConvTranspose2d(352->384, k5,s2,p3,op1) + IGDN with the content channels at offset 32 of
+    the 384-channel latent (model/net.py:126-131 at N=384, M=32)."""
+    K = ldic._lib
+    N, M = 384, 32
+    x = bf(rnd((B, N - M, H, W), 11))
+    w, b = rnd((N - M, N, 5, 5), 12, 0.01), rnd((N,), 13, 0.1)
+    bp, gp = gdn_params(N, 14)
+    ref = F.conv_transpose2d(F.pad(x, (1, 0, 1, 0)), bf(w), b, stride=2, padding=3, output_padding=1)
+    ref = gdn_oracle_bf16(ref, bp, gp, True)
+    xin = torch.zeros(B, H, W, N, dtype=torch.bfloat16)
+    xin[..., M:] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    layer = ldic.ops.ConvTC(K.LDIC_DECONV_GS_5x5, w.cuda(), b.cuda(), act=K.ACT_IGDN, out_f32=True, cin_pad=N,
+                            cin_offset=M, gdn=(bp.cuda(), gp.cuda()) + rp.model_gdn_constants())
+    y = layer(xin.cuda()).cpu().permute(0, 3, 1, 2)
+    assert y.shape == ref.shape == (B, N, 2 * H, 2 * W)
+    close(y, ref, 2e-3, 1e-3)
+
+
+def test_wide_gemm_first_layer_384(ldic):
+    """The N=384 first layer: im2col patch matrix + 1x1 GEMM + GDN(384) on the wide kernel (K = 128: two stages per tile,
+    the epilogue phases dominate -- exercises the ring bookkeeping with nkb < ring size)."""
+    sd = dw.make_state_dict(2, N=384, M=32)
+    net = ldic.Net((1, 64, 64, 3), (1, 64, 64, 3), True, False).cuda().eval()
+    net.load_state_dict(sd, strict=True)
+    x = dw.make_input(5, 3, 64, 192)
+    with torch.no_grad():
+        y_ref = rp.analysis_transform(sd, x)
+        y = net.a_model(x.cuda()).cpu()
+    assert y.shape == y_ref.shape == (3, 384, 4, 12)
+    assert rel(y, y_ref) < 1e-2, rel(y, y_ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference goldens at the other widths
+# ---------------------------------------------------------------------------------------------------
+def test_transforms_128_192_vs_reference_golden(ldic):
+    """BASELINE config 1 widths (hidden 128, latent 192): the four transform classes against outputs of the
+    unmodified reference classes (model/net.py:91-216)."""
+    from make_golden_r2 import widths_state_dict, sub
+    d = L("widths_128_192.npz")
+    sd = widths_state_dict(int(d["seed"]))
+    B, H, W = int(d["B"]), int(d["H"]), int(d["W"])
+    x = dw.make_input(int(d["xseed"]), B, H, W).cuda()
+    ga = ldic.analysisTransformModel(3, [128, 128, 128, 192]).cuda().eval()
+    ga.load_state_dict(sub(sd, "a."), strict=True)
+    gs = ldic.synthesisTransformModel(192, [128, 128, 128, 16]).cuda().eval()
+    gs.load_state_dict(sub(sd, "s."), strict=True)
+    ha = ldic.h_analysisTransformModel(192, [128, 128, 128], [1, 2, 2]).cuda().eval()
+    ha.load_state_dict(sub(sd, "ha."), strict=True)
+    hs = ldic.h_synthesisTransformModel(128, [128, 128, 192], [2, 2, 1]).cuda().eval()
+    hs.load_state_dict(sub(sd, "hs."), strict=True)
+    with torch.no_grad():
+        y = ga(x).cpu()
+        assert y.shape == d["y"].shape and rel(y, d["y"]) < 1e-2, rel(y, d["y"])
+        assert (torch.round(y) != torch.round(d["y"])).float().mean().item() < 0.02
+        xt = gs(torch.round(d["y"]).cuda()).cpu()                  # fed with the reference's symbols
+        assert xt.shape == d["xt16"].shape and rel(xt, d["xt16"]) < 1e-2, rel(xt, d["xt16"])
+        z = ha(d["y"].cuda()).cpu()
+        assert z.shape == d["z"].shape and rel(z, d["z"]) < 1e-2, rel(z, d["z"])
+        h2 = hs(torch.round(d["z"]).cuda()).cpu()
+        assert h2.shape == d["h2"].shape and rel(h2, d["h2"]) < 1e-2, rel(h2, d["h2"])
+
+
+@pytest.mark.parametrize("name", ["net_high_64x64_b1.npz", "net_high_128x192_b2.npz"])
+def test_net_high_vs_reference_golden(ldic, name):
+    """Net(is_high=True): N=384, M=32 (model/net.py:446-451) against the unmodified reference, BASELINE gates."""
+    d = L(name)
+    B, H, W = int(d["B"]), int(d["H"]), int(d["W"])
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), True, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(int(d["seed"]), N=384, M=32, boost=True), strict=True)
+    x = dw.make_input(int(d["seed"]), B, H, W).cuda()
+    bpp, v_mse, v_psnr = net(x, "test", 1)
+    assert v_mse.shape == (B,)
+    assert abs(bpp.item() / d["bpp"].item() - 1) < BPP_RTOL, (bpp.item(), d["bpp"].item())
+    assert abs(v_psnr.item() - d["v_psnr"].item()) < PSNR_ATOL_DB, (v_psnr.item(), d["v_psnr"].item())
+    out = net.rd_forward(x, want_xt16=True)
+    y = out["latents"]["y"].permute(0, 3, 1, 2).cpu()
+    assert rel(y, d["z3"]) < 1e-2, rel(y, d["z3"])
+    assert (torch.round(y) != torch.round(d["z3"])).float().mean().item() < 0.02
+    z = out["latents"]["z"].permute(0, 3, 1, 2).cpu()
+    assert rel(z, d["z2"]) < 3e-2, rel(z, d["z2"])
+    bits_ref = d["bits"]
+    assert torch.allclose(out["bits"].cpu(), bits_ref, rtol=1e-2), (out["bits"].cpu(), bits_ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# uint8 input path
+# ---------------------------------------------------------------------------------------------------
+def u8_image(seed, B, H, W):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 64, 64, 192), (2, 32, 80, 128), (1, 128, 272, 64)])
+def test_first_layer_uint8_equals_fp32_path(ldic, B, H, W, C):
+    """LDIC_CONV_FIRST_5x5S2 with aux0 = 1 (uint8 levels, x = (u/255)*2-1 applied while building patches, out-of-image
+    taps masked in the builder) is bit-identical to the fp32-image kernel fed with the reference's map."""
+    K = ldic._lib
+    u = u8_image(3, B, H, W)
+    xf = (u.float() / 255.0) * 2.0 - 1.0                          # ToTensor + eval_net.py:84 on the CPU
+    w, b = rnd((C, 3, 5, 5), 5, 0.2), rnd((C,), 6, 0.1)
+    bp, gp = gdn_params(C, 7)
+    layer = ldic.ops.ConvTC(K.LDIC_CONV_FIRST_5x5S2, w.cuda(), b.cuda(), act=K.ACT_GDN,
+                            gdn=(bp.cuda(), gp.cuda()) + rp.model_gdn_constants())
+    y_f = layer(xf.cuda())
+    y_u = layer(u.cuda())
+    assert torch.equal(y_f, y_u)
+    assert torch.equal(ldic.ops.u8_to_f32_pm1(u.cuda()).cpu(), xf)
+
+
+@pytest.mark.parametrize("high", [False, True])
+def test_net_uint8_input_equals_fp32_input(ldic, high):
+    """Net.rd_forward on the uint8 levels (first layer + fused tail read them directly) gives the bits and the exact
+    squared-error sums of the fp32 path on x = (u/255)*2-1."""
+    B, H, W = 2, 64, 128
+    N, M = (384, 32) if high else (192, 16)
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), high, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(1, N=N, M=M), strict=True)
+    u = u8_image(9, B, H, W).cuda()
+    xf = ((u.float() / 255.0) * 2.0 - 1.0)
+    o_u = net.rd_forward(u, want_x_hat=True)
+    o_f = net.rd_forward(xf, want_x_hat=True)
+    assert torch.equal(o_u["bits"], o_f["bits"])
+    assert torch.equal(o_u["sq_err"], o_f["sq_err"])
+    assert torch.equal(o_u["x_hat"], o_f["x_hat"])
+    net.tail_fused = False
+    o_s = net.rd_forward(u)
+    assert torch.equal(o_s["sq_err"], o_f["sq_err"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# host side: plan cache, graph replay behind forward(), dispatcher ops, device guard
+# ---------------------------------------------------------------------------------------------------
+def test_launch_plan_cache_and_auto_graph(ldic):
+    B, H, W = 2, 64, 128
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    x = dw.make_input(3, B, H, W).cuda()
+    lib = ldic._lib.load()
+    lib.ldic_conv_plan_cache_clear()
+    net.auto_graph = False
+    r0 = [t.clone() for t in net(x, "test", 1)]
+    n_plans = lib.ldic_conv_plan_cache_size()
+    assert n_plans >= 15
+    r1 = [t.clone() for t in net(x, "test", 1)]
+    assert lib.ldic_conv_plan_cache_size() == n_plans            # steady state: every launch is a cache hit
+    net.auto_graph = True
+    res = [[t.clone() for t in net(x, "test", 1)] for _ in range(4)]   # eager, capture + replay, replay, replay
+    n0 = ldic.ops.launch_count()
+    res.append([t.clone() for t in net(x, "test", 1)])
+    assert ldic.ops.launch_count() - n0 == 1                      # replay: only the finish kernel is launched from the host
+    for r in [r1] + res:
+        for a, b in zip(r, r0):
+            assert torch.equal(a, b)
+    x2 = dw.make_input(4, B, H, W).cuda()                         # new content, same shape: replay must see it
+    e = [t.clone() for t in net(x2, "test", 1)]
+    net.auto_graph = False
+    for a, b in zip(e, net(x2, "test", 1)):
+        assert torch.equal(a, b)
+
+
+def test_torch_library_ops_dispatch(ldic):
+    """torch.ops.ldic.* reach the same kernels (thin C-ABI torch custom-op layer)."""
+    d = L("leaf_ops.npz")
+    x = d["lb_x"].cuda().requires_grad_(True)
+    y = torch.ops.ldic.lower_bound(x, 0.11)
+    y.backward(d["lb_gout"].cuda())
+    assert torch.equal(y.detach().cpu(), d["lb_out"]) and torch.equal(x.grad.cpu(), d["lb_grad"])
+    r = torch.ops.ldic.round_ste(d["rnd_in"].cuda())
+    assert torch.equal(r.cpu(), d["bypass_round"])
+    g = L("gaussian_model.npz")
+    vh, lik, s = torch.ops.ldic.round_likelihood_bpp(g["v"].cuda(), g["sigma"].cuda(), g["mu"].cuda(), 1, 0, 1e-8, 0.11)
+    assert torch.equal(vh.cpu(), g["v_rounded"])
+    m = ~torch.isnan(g["lik"])
+    assert torch.allclose(lik.cpu()[m], g["lik"][m], rtol=1e-4, atol=5e-7)
+    # conv through the dispatcher == conv through ConvTC
+    K = ldic._lib
+    C = 192
+    xin = to_nhwc_bf16(bf(rnd((1, C, 16, 16), 1)))
+    w, b = rnd((C, C, 5, 5), 2, 0.02), rnd((C,), 3, 0.1)
+    layer = ldic.ops.ConvTC(K.LDIC_CONV_S2_5x5_P12, w.cuda(), b.cuda(), out_f32=True)
+    y1 = layer(xin)
+    y2 = torch.ops.ldic.conv_forward(xin, layer.w_packed, layer.bias_packed, None, None, layer.kind, layer.cin, layer.cout,
+                                     layer.cin_pad, layer.cout_pad, layer.act, True, 0, 0)
+    assert torch.equal(y1, y2)
+    with pytest.raises(NotImplementedError):
+        torch.ops.ldic.gdn(torch.zeros(1, 4, 2, 2), torch.zeros(4), torch.zeros(4, 4), False, True)
+
+
+def test_two_likelihood_launches_on_two_streams_do_not_share_a_workspace(ldic):
+    """re-entrant, stream-ordered calls.  The reduction workspace (ticket + per-CTA partials) is per
+    (device, stream); concurrent launches give the single-stream sums."""
+    n = 1 << 22
+    v, mu, sg = (t.cuda() for t in dw.likelihood_synthetic(0, n))
+    sg = sg.abs().clamp_min(0.05)
+    ref = ldic.ops.gaussian_likelihood(v, sg, mu, quant=1, want_lik=False)[2].clone()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(8):
+        for s in (s1, s2):
+            with torch.cuda.stream(s):
+                outs.append(ldic.ops.gaussian_likelihood(v, sg, mu, quant=1, want_lik=False)[2])
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o, ref)

@@ -143,3 +143,51 @@ def test_win_attention_oracle_vs_reference_golden(tag):
     y = rp.win_based_attention(sd, torch.from_numpy(d[f"{tag}_x"]), heads, ws, shift)
     assert torch.equal(sd["attn.relative_position_index"].long(), rp.win_rel_position_index(ws))
     torch.testing.assert_close(y, torch.from_numpy(d[f"{tag}_y"]), rtol=1e-5, atol=1e-5)
+
+
+def test_net_high_forward_full():
+    """Round 2: the `--high` model (N=384, M=32; model/net.py:446-451).  The oracle reproduces the unmodified reference
+    bit for bit at this width too (tests/golden/make_golden_r2.py)."""
+    d = L("net_high_64x64_b1.npz")
+    sd = dw.make_state_dict(int(d["seed"]), N=384, M=32, boost=True)
+    x = dw.make_input(int(d["seed"]), 1, 64, 64)
+    with torch.no_grad():
+        o = rp.net_forward_test(sd, x, (1, 64, 64, 3), M=32)
+    for k in ("z3", "z2", "h2", "mu", "sigma", "z2_lik", "y_lik", "syn_lik", "x_tilde16", "z3_syntax", "conv_weights"):
+        assert torch.equal(o[k], d[k]), k
+    for k in ("bpp", "v_mse", "v_psnr"):
+        assert torch.equal(o[k], d[k]), k
+
+
+def test_transforms_at_128_192_widths():
+    """BASELINE config 1 widths: oracle transforms vs the unmodified reference classes at [128,128,128,192]."""
+    sys_path = os.path.join(os.path.dirname(__file__), "golden")
+    import sys
+    if sys_path not in sys.path:
+        sys.path.insert(0, sys_path)
+    from make_golden_r2 import widths_state_dict
+    d = L("widths_128_192.npz")
+    sd = widths_state_dict(int(d["seed"]))
+    x = dw.make_input(int(d["xseed"]), int(d["B"]), int(d["H"]), int(d["W"]))
+    with torch.no_grad():
+        y = rp.analysis_transform(sd, x, prefix="a.transform.")
+        assert torch.equal(y, d["y"])
+        assert torch.equal(rp.synthesis_transform(sd, torch.round(y), prefix="s.transform."), d["xt16"])
+        z = rp.h_analysis_transform(sd, y, prefix="ha.transform.")
+        assert torch.equal(z, d["z"])
+        assert torch.equal(rp.h_synthesis_transform(sd, torch.round(z), prefix="hs.transform."), d["h2"])
+
+
+def test_uint8_input_map_identities():
+    """The two facts the uint8 input path of the kernels relies on, checked for all 256 levels:
+    (i) the bf16 operand of the first layer: bf16((u/255)*2-1) == bf16(fma(u, fl(2/255), -1));
+    (ii) the a11 ground truth: round(((u/255)*2-1 + 1) * 127.5) == u  (model/net.py:864 on eval_net.py:84 inputs)."""
+    u = np.arange(256, dtype=np.float32)
+    x = (u / np.float32(255.0)) * np.float32(2.0) - np.float32(1.0)
+    c = np.float32(2.0) / np.float32(255.0)
+    fma = np.array([np.float32(np.float64(a) * np.float64(c) - 1.0) for a in u], dtype=np.float32)   # one rounding
+    assert torch.equal(torch.from_numpy(fma).bfloat16(), torch.from_numpy(x).bfloat16())
+    gt = np.rint((x + np.float32(1.0)) * np.float32(127.5))
+    assert (gt == u).all()
+    xt = (torch.arange(256, dtype=torch.uint8).float() / 255.0) * 2.0 - 1.0                           # torch's ToTensor path
+    assert torch.equal(xt, torch.from_numpy(x))
