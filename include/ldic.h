@@ -144,7 +144,7 @@ LDIC_API int ldic_rd_finish_metrics(const double* packed5, double pixels_per_ima
  * a11 arithmetic against the NCHW fp32 input x.  x_tilde_nchw (optional) receives
  * the reconstruction.                                                           */
 LDIC_API int ldic_syntax_conv_mse(const float* x_nchw, const float* xt_nhwc, const float* w, int B, int M,
-                         int H, int W, float* x_tilde_nchw, unsigned long long* sq_err, void* stream);
+                         int H, int W, int tanh_out, float* x_tilde_nchw, unsigned long long* sq_err, void* stream);
 
 /* ---- layout / dtype glue ------------------------------------------------------------ */
 /* NCHW fp32 -> NHWC bf16 (channels padded to Cp with zeros) and back.            */
@@ -224,8 +224,9 @@ LDIC_API void ldic_conv_out_shape(const LdicConvDesc* d, int* Ho, int* Wo);
  * (gamma_bf16 / beta_tiled from ldic_gdn_prepare).                              */
 LDIC_API int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                       const void* gamma_bf16, const float* beta_tiled, void* y, void* stream);
-/* Launch plans (tile / tap tables, TMA descriptors, kernel variant, grid) are cached per (descriptor, tensor
- * addresses, device): a repeated call with the same arguments is a lookup plus one kernel launch.          */
+/* Launch plans (tile / tap tables, TMA descriptors, kernel variant, grid) are cached per (descriptor, parameter
+ * tensors, device); the activation addresses of a call are patched into a copy of the cached plan, so a repeated
+ * call is a lookup, one cuTensorMapReplaceAddress and one kernel launch.                                      */
 LDIC_API int ldic_conv_plan_cache_size(void);
 LDIC_API void ldic_conv_plan_cache_clear(void);
 /* The merged last synthesis deconv (LDIC_DECONV_GS_5x5_MERGED) with the tail of Net.forward fused into its
@@ -241,7 +242,7 @@ typedef struct {
   unsigned long long* sq_err;
   int H, W;
   int x_is_u8;
-  int reserved;
+  int tanh_out;               /* x~ = tanh(batch_conv(...)) (U-Net family, model/net_unet_ha_hs.py:980) */
 } LdicConvTail;
 LDIC_API int ldic_conv_forward_fused_tail(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                                  const void* gamma_bf16, const float* beta_tiled, void* y_or_null,

@@ -56,7 +56,7 @@ class ConvDesc(C.Structure):
 
 class ConvTail(C.Structure):
     _fields_ = [("x_nchw", C.c_void_p), ("w", C.c_void_p), ("x_tilde_nchw", C.c_void_p), ("sq_err", C.c_void_p),
-                ("H", C.c_int), ("W", C.c_int), ("x_is_u8", C.c_int), ("reserved", C.c_int)]
+                ("H", C.c_int), ("W", C.c_int), ("x_is_u8", C.c_int), ("tanh_out", C.c_int)]
 
 
 class SyntaxArgs(C.Structure):
@@ -91,7 +91,7 @@ _SIGS = {
     "ldic_mse_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "ldic_rd_pack_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldic_rd_finish_metrics": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
-    "ldic_syntax_conv_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+    "ldic_syntax_conv_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldic_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_void_p]),

@@ -93,6 +93,7 @@ struct ConvParams {
   // fused tail of Net.forward on the merged last deconv: per-image 1x1 conv (batch_conv) + 8-bit-level squared error
   const void* tail_x;        // NCHW input image [B,3,tail_H,tail_W] (fp32 in [-1,1], or uint8 levels when tail_u8), or null
   int tail_u8;
+  int tail_tanh;             // x~ = tanh(batch_conv(...)) before the level error (U-Net family, model/net_unet_ha_hs.py:980)
   const float* tail_w;       // [B][3][Cg] per-image filters
   float* tail_xo;            // optional NCHW fp32 reconstruction
   unsigned long long* tail_sq;  // [B] exact sums (accumulated into)
@@ -437,6 +438,7 @@ __device__ __forceinline__ unsigned long long fused_tail_pixels(const ConvParams
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const long long idx = (((long long)n * 3 + c) * P.tail_H + oy) * P.tail_W + ox;
+        if (P.tail_tanh) o[c] = tanhf(o[c]);
         if (P.tail_xo) P.tail_xo[idx] = o[c];
         acc += tail_sq_err(P, idx, o[c]);
       }
@@ -833,6 +835,7 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const long long idx = (((long long)gn_ * 3 + c) * P.tail_H + oy) * P.tail_W + ox;
+            if (P.tail_tanh) o[c] = tanhf(o[c]);
             if (P.tail_xo) P.tail_xo[idx] = o[c];
             tail_acc += tail_sq_err(P, idx, o[c]);
           }
@@ -1204,7 +1207,14 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             adv();
           }
         }
-        for (int kb = 0; kb < gk; ++kb) adv();       // the x^2 tiles of this tile (written by the epilogue warps)
+        // The tile's gk x^2 slots are written by the epilogue warps, not by TMA.  Their `afull` barriers still have to
+        // complete one phase per ring pass (the MMA warp's parity bookkeeping is per pass), so the leader arrives on them
+        // once the slot's previous occupant has been consumed.
+        for (int kb = 0; kb < gk; ++kb) {
+          mbar_wait(&aempty[sa], pa ^ 1);
+          if (leader && elect_one()) mbar_arrive(&afull[sa]);
+          adv();
+        }
       }
     } else if (warp == kProdBWarp) {
       // ===================== B producer: weight rows of both column halves, gamma rows (both CTAs) ============
@@ -1738,6 +1748,21 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
+typedef CUresult (*PFN_replaceAddress)(CUtensorMap*, void*);
+PFN_replaceAddress get_replace_address() {
+  static PFN_replaceAddress fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapReplaceAddress", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_replaceAddress)p;
+    tried = true;
+  }
+  return fn;
+}
+
 enum MapType { MAP_BF16_SW128 = 0, MAP_F32 = 1, MAP_U8 = 2 };   // operand tiles (swizzled) / raw image boxes (linear)
 int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr, int type = MAP_BF16_SW128) {
@@ -2261,7 +2286,7 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
   const bool gdn = d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN;
   if (gdn && (!gamma_bf16 || !beta_tiled)) return fail(LDIC_EINVAL, "conv: GDN epilogue needs gamma_bf16 and beta_tiled");
   if (gdn && L.njobs > 4) return fail(LDIC_EINVAL, "conv: GDN epilogue is not available for the context layers");
-  if ((((uintptr_t)x) & 15) || (((uintptr_t)w_packed) & 15) || (((uintptr_t)y) & 31)) return fail(LDIC_EINVAL, "conv: x / weights must be 16-byte and y 32-byte aligned");
+  if (((uintptr_t)w_packed) & 15) return fail(LDIC_EINVAL, "conv: packed weights must be 16-byte aligned");
   if (L.Cs % 16) return fail(LDIC_EINVAL, "conv: output channel count must be a multiple of 16");
   if (d->kind == LDIC_CONV_FIRST_5x5S2)
     return build_plan_first(d, L, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, pl);
@@ -2295,7 +2320,7 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
   P.gdn_insert = tn.gdn_insert >= 1 && tn.gdn_insert <= 16 ? tn.gdn_insert : kGdnInsertDefault;
   if (tail) {
     P.tail_x = tail->x_nchw; P.tail_w = tail->w; P.tail_xo = tail->x_tilde_nchw; P.tail_sq = tail->sq_err;
-    P.tail_H = tail->H; P.tail_W = tail->W; P.tail_u8 = tail->x_is_u8;
+    P.tail_H = tail->H; P.tail_W = tail->W; P.tail_u8 = tail->x_is_u8; P.tail_tanh = tail->tanh_out;
   }
 
   // ---- wide-N form of the merged last deconv (epilogue_w3): the three dx taps ride side by side in N = 3 * Np, the dy
@@ -2382,11 +2407,14 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
 }
 
 // ---- plan cache -----------------------------------------------------------------------------------
+// The key holds what a plan depends on structurally: the layer, its (long-lived) parameter tensors and the device.
+// The activation addresses x / y and the tail's pointers change from call to call (torch's allocator hands out
+// different blocks) and are patched into a copy of the cached plan: cuTensorMapReplaceAddress for the one TMA
+// descriptor that embeds x, plain parameter fields for the rest.
 struct PlanKey {
   LdicConvDesc d;
-  const void *x, *w, *bias, *gamma, *beta, *y;
-  LdicConvTail tail;
-  int has_tail, device;
+  const void *w, *bias, *gamma, *beta;
+  int has_tail, tail_H, tail_W, tail_u8, tail_tanh, has_y, device;
   unsigned epoch;
   bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
 };
@@ -2520,10 +2548,12 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
   int rc;
   if ((rc = ensure_timeout_report())) return rc;
   const Tuning& tn = tuning();
+  if ((((uintptr_t)x) & 15) || (((uintptr_t)y) & 31)) return fail(LDIC_EINVAL, "conv: x must be 16-byte and y 32-byte aligned");
   PlanKey key;
   memset(&key, 0, sizeof(key));
-  key.d = *d; key.x = x; key.w = w_packed; key.bias = bias_packed; key.gamma = gamma_bf16; key.beta = beta_tiled; key.y = y;
-  if (tail) { key.tail = *tail; key.has_tail = 1; }
+  key.d = *d; key.w = w_packed; key.bias = bias_packed; key.gamma = gamma_bf16; key.beta = beta_tiled;
+  if (tail) { key.has_tail = 1; key.tail_H = tail->H; key.tail_W = tail->W; key.tail_u8 = tail->x_is_u8; key.tail_tanh = tail->tanh_out; }
+  key.has_y = y != nullptr;
   key.device = current_device(); key.epoch = tn.epoch;
   std::shared_ptr<Plan> pl;
   {
@@ -2531,18 +2561,29 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
     auto it = g_plans.find(key);
     if (it != g_plans.end()) pl = it->second;
   }
-  if (!pl) {
-    pl = std::make_shared<Plan>();
-    if ((rc = build_plan(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, tail, pl.get()))) return rc;
-    if (tn.debug_timing) {
-      unsigned long long* buf = nullptr;
-      if (cudaMalloc(&buf, 32 * sizeof(unsigned long long)) == cudaSuccess) pl->P.dbg = buf;   // lives as long as the plan cache
-    }
+  cudaStream_t st = (cudaStream_t)stream;
+  PFN_replaceAddress repl = get_replace_address();
+  if (pl && repl) {
+    Plan p = *pl;                                   // per-call copy: this call's activation addresses
+    if (repl(&p.a, const_cast<void*>(x)) != CUDA_SUCCESS) return fail(LDIC_ECUDA, "conv: cuTensorMapReplaceAddress failed");
+    p.P.out = y;
+    if (tail) { p.P.tail_x = tail->x_nchw; p.P.tail_w = tail->w; p.P.tail_xo = tail->x_tilde_nchw; p.P.tail_sq = tail->sq_err; }
+    if (p.P.dbg) cudaMemsetAsync(p.P.dbg, 0, 32 * sizeof(unsigned long long), st);
+    rc = launch_plan(p, st);
+    if (rc == LDIC_OK && p.P.dbg) print_debug_timing(p, st);
+    return rc;
+  }
+  pl = std::make_shared<Plan>();
+  if ((rc = build_plan(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, tail, pl.get()))) return rc;
+  if (tn.debug_timing) {
+    unsigned long long* buf = nullptr;
+    if (cudaMalloc(&buf, 32 * sizeof(unsigned long long)) == cudaSuccess) pl->P.dbg = buf;   // lives as long as the plan cache
+  }
+  {
     std::lock_guard<std::mutex> lk(g_plan_mu);
     if (g_plans.size() >= kMaxPlans) g_plans.clear();
-    g_plans.emplace(key, pl);
+    g_plans[key] = pl;
   }
-  cudaStream_t st = (cudaStream_t)stream;
   if (pl->P.dbg) cudaMemsetAsync(pl->P.dbg, 0, 32 * sizeof(unsigned long long), st);
   rc = launch_plan(*pl, st);
   if (rc == LDIC_OK && pl->P.dbg) print_debug_timing(*pl, st);

@@ -630,7 +630,7 @@ extern "C" int ldic_mse_sum(const float* x, const float* x_tilde, int B, long lo
 // batch_conv (per-image 1x1, M -> 3) + the a11 arithmetic.  One thread per pixel.
 template <int M>
 __global__ void __launch_bounds__(256) k_syntax_conv_mse(const float* __restrict__ x, const float* __restrict__ xt,
-                                                         const float* __restrict__ w, long long HW,
+                                                         const float* __restrict__ w, long long HW, int tanh_out,
                                                          float* __restrict__ xo, unsigned long long* __restrict__ out) {
   const int b = blockIdx.y;
   __shared__ float ws[3 * M];
@@ -652,7 +652,11 @@ __global__ void __launch_bounds__(256) k_syntax_conv_mse(const float* __restrict
         o2 = fmaf(tv[k], ws[2 * M + q * 4 + k], o2);
       }
     }
-    const float o[3] = {o0, o1, o2};
+    float o[3] = {o0, o1, o2};
+    if (tanh_out) {                          // U-Net family: x~ = tanh(batch_conv(...)) (model/net_unet_ha_hs.py:980)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[c] = tanhf(o[c]);
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       long long idx = ((long long)b * 3 + c) * HW + p;
@@ -671,15 +675,15 @@ __global__ void __launch_bounds__(256) k_syntax_conv_mse(const float* __restrict
   }
 }
 extern "C" int ldic_syntax_conv_mse(const float* x_nchw, const float* xt_nhwc, const float* w, int B, int M, int H, int W,
-                                    float* x_tilde_nchw, unsigned long long* sq_err, void* stream) {
+                                    int tanh_out, float* x_tilde_nchw, unsigned long long* sq_err, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0) return (B == 0 || H == 0 || W == 0) ? LDIC_OK : fail(LDIC_EINVAL, "syntax_conv_mse: bad shape");
   long long HW = (long long)H * W;
   long long blocks = (HW + 255) / 256;
   int per_img = (int)(blocks > num_sms() * 4 ? num_sms() * 4 : blocks);
   dim3 grid(per_img, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (M == 16) k_syntax_conv_mse<16><<<grid, 256, 0, st>>>(x_nchw, xt_nhwc, w, HW, x_tilde_nchw, sq_err);
-  else if (M == 32) k_syntax_conv_mse<32><<<grid, 256, 0, st>>>(x_nchw, xt_nhwc, w, HW, x_tilde_nchw, sq_err);
+  if (M == 16) k_syntax_conv_mse<16><<<grid, 256, 0, st>>>(x_nchw, xt_nhwc, w, HW, tanh_out, x_tilde_nchw, sq_err);
+  else if (M == 32) k_syntax_conv_mse<32><<<grid, 256, 0, st>>>(x_nchw, xt_nhwc, w, HW, tanh_out, x_tilde_nchw, sq_err);
   else return fail(LDIC_EINVAL, "syntax_conv_mse: M=%d unsupported (16 or 32)", M);
   return check_launch("k_syntax_conv_mse");
 }

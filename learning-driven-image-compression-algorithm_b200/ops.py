@@ -299,7 +299,7 @@ def rd_finish_metrics(packed5: torch.Tensor, pixels_per_image: float, out: Optio
     return out
 
 
-def syntax_conv_mse(x_nchw, xt_nhwc, w, want_x_tilde=False):
+def syntax_conv_mse(x_nchw, xt_nhwc, w, want_x_tilde=False, tanh_out=False):
     x = _req(x_nchw, torch.float32, "x").contiguous()
     xt = _req(xt_nhwc, torch.float32, "x_tilde16").contiguous()
     w = _req(w, torch.float32, "w").contiguous()
@@ -307,7 +307,7 @@ def syntax_conv_mse(x_nchw, xt_nhwc, w, want_x_tilde=False):
     M = xt.shape[-1]
     out = torch.zeros(B, dtype=torch.int64, device=x.device)
     xo = torch.empty_like(x) if want_x_tilde else None
-    check(_L().ldic_syntax_conv_mse(_ptr(x), _ptr(xt), _ptr(w), B, M, H, W, _ptr(xo), _ptr(out), _stream()),
+    check(_L().ldic_syntax_conv_mse(_ptr(x), _ptr(xt), _ptr(w), B, M, H, W, int(bool(tanh_out)), _ptr(xo), _ptr(out), _stream()),
           "ldic_syntax_conv_mse")
     return out, xo
 
@@ -468,7 +468,7 @@ class ConvTC:
         return f
 
     def fused_tail(self, x: torch.Tensor, image: torch.Tensor, conv_w: torch.Tensor, *, want_x_tilde: bool = False,
-                   want_out: bool = False):
+                   want_out: bool = False, tanh_out: bool = False):
         """Merged last synthesis deconv + batch_conv + squared level error in one kernel
         (ldic_conv_forward_fused_tail).  x: NHWC bf16 layer input; image: NCHW fp32 (B,3,2H,2W); conv_w: (B,3,M).
         Returns (sq_err int64[B], x_tilde NCHW or None, layer output NHWC fp32 or None)."""
@@ -485,7 +485,7 @@ class ConvTC:
         sq = torch.zeros(B, dtype=torch.int64, device=x.device)
         xo = torch.empty(image.shape, dtype=torch.float32, device=x.device) if want_x_tilde else None
         out = torch.empty(self.out_dims(B, H, W), dtype=torch.float32, device=x.device) if want_out else None
-        t = _lib.ConvTail(_ptr(image), _ptr(conv_w), _ptr(xo), _ptr(sq), 2 * H, 2 * W, int(image.dtype == torch.uint8), 0)
+        t = _lib.ConvTail(_ptr(image), _ptr(conv_w), _ptr(xo), _ptr(sq), 2 * H, 2 * W, int(image.dtype == torch.uint8), int(bool(tanh_out)))
         d = self._desc(B, H, W)
         prof = PROFILE
         if prof is not None:

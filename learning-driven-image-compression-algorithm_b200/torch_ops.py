@@ -98,9 +98,15 @@ def _register():
     @lib.custom_op(f"{NS}::round_likelihood_bpp", mutates_args=(), device_types=_dev)
     def round_likelihood_bpp(v: Tensor, sigma: Tensor, mu: Optional[Tensor], quant: int, form: int, lik_bound: float,
                              scale_bound: float) -> Tuple[Tensor, Tensor, Tensor]:
+        shape = v.shape
+        if v.dim() != 4:                       # any shape with elementwise sigma / mu: one row of v.numel() elements
+            if sigma.shape != shape or (mu is not None and mu.shape != shape):
+                raise ops.LdicError("round_likelihood_bpp: non-4D inputs need sigma / mu of v's shape")
+            v, sigma = v.reshape(1, 1, 1, -1), sigma.reshape(1, 1, 1, -1)
+            mu = None if mu is None else mu.reshape(1, 1, 1, -1)
         vh, lik, s = ops.gaussian_likelihood(v, sigma, mu, quant=quant, form=form, lik_bound=lik_bound,
                                              scale_bound=scale_bound, want_lik=True, want_vhat=True)
-        return vh, lik, s
+        return vh.reshape(shape), lik.reshape(shape), s
 
     @round_likelihood_bpp.register_fake
     def _(v, sigma, mu, quant, form, lik_bound, scale_bound):

@@ -165,9 +165,10 @@ class synthesisTransformModel(_PlannedTransform):
             t = layer(t, sm_limit=sm_limit)
         return t
 
-    def fused_tail(self, t, image_nchw, conv_w, want_x_tilde=False, want_out=False):
+    def fused_tail(self, t, image_nchw, conv_w, want_x_tilde=False, want_out=False, tanh_out=False):
         """Last deconv + IGDN + batch_conv + squared level error on the output of forward_nhwc_body."""
-        return self.plan()[-1].fused_tail(t, image_nchw, conv_w, want_x_tilde=want_x_tilde, want_out=want_out)
+        return self.plan()[-1].fused_tail(t, image_nchw, conv_w, want_x_tilde=want_x_tilde, want_out=want_out,
+                                          tanh_out=tanh_out)
 
     def forward(self, inputs):
         L = self.plan()

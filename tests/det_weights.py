@@ -102,6 +102,31 @@ def make_state_dict(seed: int = 0, N: int = 192, M: int = 16, boost: bool = True
     return sd
 
 
+def widths_state_dict(seed: int = 11):
+    """Deterministic weights of the four transform classes at hidden width 128 / latent width 192."""
+    sd = {}
+    H, Lw, M = 128, 192, 16
+    for (ci, co), idx in zip([(3, H), (H, H), (H, H), (H, Lw)], (1, 4, 7, 10)):
+        _conv(sd, seed, f"a.transform.{idx}", co, ci, 5, gain=30.0 if idx == 10 else 1.0)
+    for idx in (2, 5, 8):
+        _gdn(sd, seed, f"a.transform.{idx}", H)
+    for (ci, co), idx in zip([(Lw, H), (H, H), (H, H), (H, M)], (1, 4, 7, 10)):
+        _conv(sd, seed, f"s.transform.{idx}", co, ci, 5, transposed=True, gain=4.0 if idx == 10 else 1.0)
+    for co, idx in zip((H, H, H, M), (2, 5, 8, 11)):
+        _gdn(sd, seed, f"s.transform.{idx}", co)
+    _conv(sd, seed, "ha.transform.0", H, Lw, 3)
+    _conv(sd, seed, "ha.transform.2", H, H, 5)
+    _conv(sd, seed, "ha.transform.4", H, H, 5, gain=8.0)
+    _conv(sd, seed, "hs.transform.0", H, H, 5, transposed=True)
+    _conv(sd, seed, "hs.transform.2", H, H, 5, transposed=True)
+    _conv(sd, seed, "hs.transform.4", Lw, H, 3, transposed=True, gain=20.0)
+    return sd
+
+
+def sub_state_dict(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
 def make_input(seed: int, B: int, H: int, W: int) -> torch.Tensor:
     """x in [-1,1) like eval_net.py:84; smooth-ish + noise so layers see structure."""
     r = _rng(seed, f"x{B}x{H}x{W}")

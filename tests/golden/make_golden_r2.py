@@ -29,29 +29,7 @@ import det_weights as dw  # noqa: E402
 from make_golden import save  # noqa: E402
 
 
-def widths_state_dict(seed: int = 11):
-    """Deterministic weights of the four transform classes at hidden width 128 / latent width 192."""
-    sd = {}
-    H, Lw, M = 128, 192, 16
-    for (ci, co), idx in zip([(3, H), (H, H), (H, H), (H, Lw)], (1, 4, 7, 10)):
-        dw._conv(sd, seed, f"a.transform.{idx}", co, ci, 5, gain=30.0 if idx == 10 else 1.0)
-    for idx in (2, 5, 8):
-        dw._gdn(sd, seed, f"a.transform.{idx}", H)
-    for (ci, co), idx in zip([(Lw, H), (H, H), (H, H), (H, M)], (1, 4, 7, 10)):
-        dw._conv(sd, seed, f"s.transform.{idx}", co, ci, 5, transposed=True, gain=4.0 if idx == 10 else 1.0)
-    for co, idx in zip((H, H, H, M), (2, 5, 8, 11)):
-        dw._gdn(sd, seed, f"s.transform.{idx}", co)
-    dw._conv(sd, seed, "ha.transform.0", H, Lw, 3)
-    dw._conv(sd, seed, "ha.transform.2", H, H, 5)
-    dw._conv(sd, seed, "ha.transform.4", H, H, 5, gain=8.0)
-    dw._conv(sd, seed, "hs.transform.0", H, H, 5, transposed=True)
-    dw._conv(sd, seed, "hs.transform.2", H, H, 5, transposed=True)
-    dw._conv(sd, seed, "hs.transform.4", Lw, H, 3, transposed=True, gain=20.0)
-    return sd
-
-
-def sub(sd, prefix):
-    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+from det_weights import widths_state_dict, sub_state_dict as sub  # noqa: E402,F401
 
 
 def main():
@@ -61,7 +39,7 @@ def main():
 
     # ---- transform classes at 128 / 192 ------------------------------------------------------------
     sd = widths_state_dict()
-    B, H, W = 2, 64, 96
+    B, H, W = 2, 64, 128                     # latent 4 x 8: h_a's stride-2 layers need even sizes on our side
     x = dw.make_input(21, B, H, W)
     with torch.no_grad():
         ga = net_mod.analysisTransformModel(3, [128, 128, 128, 192]).eval()
@@ -121,6 +99,9 @@ def main():
     save("net_high_128x192_b2.npz", seed=4, boost=1, B=2, H=128, W=192, th=128, tw=192, N=384, M=32,
          **{k: r_[k] for k in ("bpp", "v_mse", "v_psnr", "bits", "z3", "z2", "h2", "z3_syntax", "conv_weights")},
          x_tilde16_sub=r_["x_tilde16"][:, :, ::4, ::4])
+    r_ = run_high(1, 256, 256, 6)
+    save("net_high_256x256_b1.npz", seed=6, boost=1, B=1, H=256, W=256, th=256, tw=256, N=384, M=32,
+         **{k: r_[k] for k in ("bpp", "v_mse", "v_psnr", "bits", "z3", "z2")})
     print("done")
 
 
