@@ -591,6 +591,134 @@ def run_tritplane(args):
         dist.destroy_process_group()
 
 
+def run_unet(args):
+    """BASELINE configs[2] (768x512, global batch 64 sharded over the GPUs) and, with --crop 1280x2048, configs[3]
+    (1920x1080 crops padded to the multiple of 256 the model needs, global batch 32): the U-Net-family Net (model/net_unet_ha_hs.py) with
+    its hot path on libldic_b200 and its other blocks as stock torch modules.  Random-init weights by name
+    (tests/det_weights.py::unet_param_fill), synthetic images."""
+    import torch
+    import torch.distributed as dist
+    import ldic_b200
+    from ldic_b200 import ops, net_unet
+    from ldic_b200.layers import WinBasedAttention
+    import det_weights as dw
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            emit({"impl": "reference", "unavailable": "the U-Net family needs compressai / timm and two modules missing from the "
+                  "reference tree; it only runs with restated dependencies in the build container (oracle/unet_harness.py)"})
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ldic_b200._lib.check(ldic_b200._lib.load().ldic_check_device(local), "device")
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    Hh, Ww = (int(v) for v in args.crop.split("x"))
+    gb = args.global_batch if args.global_batch else (64 if (Hh, Ww) == (512, 768) else 32)
+    B = max(1, gb // world) if not args.batch_set else args.batch
+    net = net_unet.Net((B, Hh, Ww, 3), (B, Hh, Ww, 3), False, False).to(dev).eval()
+    fill = dw.unet_param_fill([(n, tuple(p.shape)) for n, p in net.named_parameters()], 0)
+    net.load_state_dict({**net.state_dict(), **{k: v.to(dev) for k, v in fill.items()}}, strict=True)
+    base = dw.make_input(rank, 2, Hh, Ww)
+    NBUF = 2
+    host = [torch.cat([torch.roll(base, shifts=i * 37 + j * 11, dims=3) for j in range((B + 1) // 2)], 0)[:B].contiguous().pin_memory()
+            for i in range(NBUF)]
+    devbuf = [h.to(dev) for h in host]
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def step(x):
+        out = net.rd_forward(x)
+        _, h, w, _ = net.train_size
+        bits3 = torch.stack([out["bits"].sum(), out["bits"].new_zeros(()), out["bits"].new_zeros(())]).contiguous()
+        packed, _ = ops.rd_pack_metrics(bits3, out["sq_err"], 3 * Hh * Ww, want_v_mse=False)
+        if world > 1:
+            dist.all_reduce(packed)
+        return ops.rd_finish_metrics(packed, float(h * w))
+    for i in range(max(args.warmup, 3)):
+        r = step(devbuf[i % NBUF])
+    sync_all()
+    sampler = ClockSampler(local)
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        r = step(devbuf[i % NBUF])
+    e1.record()
+    sync_all()
+    launches = int(ops.launch_count() - n0)
+    tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms = float(tt.item())
+    # share of the step inside the window-attention blocks / the Win_noShift_Attention modules (events around the modules)
+    spans = {"WinBasedAttention": [], "Win_noShift_Attention": []}
+    hooks = []
+    for mod in net.modules():
+        tag = "WinBasedAttention" if isinstance(mod, WinBasedAttention) else ("Win_noShift_Attention" if isinstance(mod, net_unet.Win_noShift_Attention) else None)
+        if tag:
+            def pre(m, i, tag=tag):
+                e = torch.cuda.Event(enable_timing=True); e.record(); m._e0 = e
+            def post(m, i, o, tag=tag):
+                e = torch.cuda.Event(enable_timing=True); e.record(); spans[tag].append((m._e0, e))
+            hooks += [mod.register_forward_pre_hook(pre), mod.register_forward_hook(post)]
+    e0.record()
+    step(devbuf[0])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    hooked_ms = e0.elapsed_time(e1)
+    share = {k: sum(a.elapsed_time(b) for a, b in v) / hooked_ms for k, v in spans.items()}
+    for h in hooks:
+        h.remove()
+    # end to end
+    xin = [torch.empty_like(devbuf[0]) for _ in range(2)]
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        xin[i % 2].copy_(host[i % NBUF], non_blocking=True)
+        rr = step(xin[i % 2]).cpu()
+    e1.record()
+    sync_all()
+    tt2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
+    if rank == 0:
+        cfgname = "configs[2]" if (Hh, Ww) == (512, 768) else "configs[3]"
+        emit({"metric": f"{Ww}x{Hh} imgs/sec (U-Net family: g_a -> U-Net hyperprior -> slice entropy model -> bpp -> g_s)",
+              "value": world * B * args.steps / (t_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+              "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+              "scaling": "strong" if not args.batch_set else "weak", "vs_baseline": None, "dtype": "bf16 (kernels) / fp32-TF32 (torch blocks)",
+              "data": "synthetic",
+              "config": {"workload": f"BASELINE {cfgname}: model/net_unet_ha_hs.py Net.forward(test), {Ww}x{Hh}, global batch {world * B} "
+                                     f"({B} per GPU)", "global_batch": world * B, "height": Hh, "width": Ww,
+                         "weights": "random init by name (tests/det_weights.py::unet_param_fill)",
+                         "l2": "activations of one step are several GB (> 126 MB L2)", "launch_mode": "eager",
+                         "parity": "restated deps (tests/test_gpu_unet.py)"},
+              "e2e": {"value": world * B * args.steps / (float(tt2.item()) * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": 8},
+              "gpu_launches": launches, "clocks": clocks,
+              "share_of_step": {"WinBasedAttention_blocks": share["WinBasedAttention"],
+                                "Win_noShift_Attention_modules": share["Win_noShift_Attention"],
+                                "note": "CUDA-event spans around the modules in one eager step"},
+              "roofline": {"bound": "tensor", "kernel": "mixed: libldic_b200 kernels + cuDNN/cuBLAS blocks", "achieved": None,
+                           "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None},
+              "parity": {"bpp": float(r[0].item()), "psnr_db": float(r[1].item())}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -623,12 +751,18 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying CUDA graphs")
-    ap.add_argument("--config", default="net", choices=["net", "high", "tritplane"],
-                    help="net: BASELINE configs[1] (headline); high: the N=384 model; tritplane: BASELINE configs[4]")
+    ap.add_argument("--config", default="net", choices=["net", "high", "tritplane", "unet"],
+                    help="net: BASELINE configs[1] (headline); high: the N=384 model; tritplane: BASELINE configs[4]; "
+                         "unet: the U-Net family, configs[2] (768x512, global batch 64) or with --crop 1280x2048 configs[3]")
+    ap.add_argument("--crop", default="512x768", help="unet: image size HxW, multiples of 256 (configs[3]: 1080x1920 crops pad to 1280x2048)")
+    ap.add_argument("--global-batch", type=int, default=0, help="unet: global batch (default 64 at 768x512, else 32)")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"], help="image type of the input buffers")
     ap.add_argument("--side-sms", type=int, default=0, help="SM partition for the hyperprior / syntax side stream (0: single stream)")
     args = ap.parse_args()
-    if args.config == "tritplane":
+    args.batch_set = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
+    if args.config == "unet":
+        run_unet(args)
+    elif args.config == "tritplane":
         run_tritplane(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -254,7 +254,59 @@ class WinBasedAttention(nn.Module):
                                     qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
         self.drop_path = nn.Identity()
 
+    def kernel_shape(self) -> bool:
+        """True when (dim, heads, window) is a shape ldic_window_attention_core is built for: the hot blocks of the
+        reference (dim 192 / 128 / 64, 8 heads, windows 8 and 4).  The U-Net hyperprior also instantiates this class at
+        dims 96 / 256 / 512 with 2x2 and 4x4 windows on 1/64-resolution maps (model/Block_unet.py:783-806,849-851);
+        those few small blocks run the same arithmetic as torch ops (`forward_torch`) -- an explicit choice by shape,
+        reported by `backend`, not a fallback for a missing library."""
+        hd = self.dim // self.num_heads
+        return self.dim % 64 == 0 and self.dim % self.num_heads == 0 and hd % 2 == 0 and hd <= 32 and \
+            self.window_size in (4, 8) and self.num_heads <= 16
+
+    @property
+    def backend(self) -> str:
+        return "ldic" if self.kernel_shape() else "torch"
+
+    def forward_torch(self, x):
+        """layers/win_attention.py:150-209 with torch ops (window partition, cyclic shift, 0 / -100 mask, softmax)."""
+        B, Cd, H, W = x.shape
+        ws, sh, nh = self.window_size, self.shift_size, self.num_heads
+        a = self.attn
+        t = x.permute(0, 2, 3, 1)
+        mask = None
+        if sh > 0:
+            img = torch.zeros((1, H, W, 1), device=x.device)
+            cnt = 0
+            for hs in (slice(0, -ws), slice(-ws, -sh), slice(-sh, None)):
+                for wsl in (slice(0, -ws), slice(-ws, -sh), slice(-sh, None)):
+                    img[:, hs, wsl, :] = cnt
+                    cnt += 1
+            mw = img.view(1, H // ws, ws, W // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws)
+            mask = mw.unsqueeze(1) - mw.unsqueeze(2)
+            mask = mask.masked_fill(mask != 0, float(-100.0)).masked_fill(mask == 0, float(0.0))
+            t = torch.roll(t, shifts=(-sh, -sh), dims=(1, 2))
+        win = t.reshape(B, H // ws, ws, W // ws, ws, Cd).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, Cd)
+        Bn, Nt, _ = win.shape
+        qkv = a.qkv(win).reshape(Bn, Nt, 3, nh, Cd // nh).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0] * a.scale, qkv[1], qkv[2]
+        attn = q @ k.transpose(-2, -1)
+        bias = a.relative_position_bias_table[a.relative_position_index.view(-1)].view(Nt, Nt, -1).permute(2, 0, 1)
+        attn = attn + bias.unsqueeze(0)
+        if mask is not None:
+            nW = mask.shape[0]
+            attn = (attn.view(Bn // nW, nW, nh, Nt, Nt) + mask.unsqueeze(1).unsqueeze(0)).view(-1, nh, Nt, Nt)
+        o = (torch.softmax(attn, dim=-1) @ v).transpose(1, 2).reshape(Bn, Nt, Cd)
+        o = a.proj(o).view(B, H // ws, W // ws, ws, ws, Cd).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, Cd)
+        if sh > 0:
+            o = torch.roll(o, shifts=(sh, sh), dims=(1, 2))
+        return x + o.permute(0, 3, 1, 2)
+
     def forward(self, x):
+        if not self.kernel_shape():
+            if not x.is_cuda:
+                raise ops.LdicError("WinBasedAttention runs on CUDA only")
+            return self.forward_torch(x)
         return _window_block(self.attn, x, self.window_size, self.shift_size, residual=True)
 
 

@@ -150,3 +150,49 @@ def likelihood_synthetic(seed: int, n: int):
         sigma[12:16] = np.array([-1.0, 0.11, 0.0, 1e-3], dtype=np.float32)
         mu[16:20] = np.array([0.25, -0.25, 0.5, -0.5], dtype=np.float32)
     return torch.from_numpy(v), torch.from_numpy(mu), torch.from_numpy(sigma)
+
+
+def unet_param_fill(named_shapes, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic values for the PARAMETERS of the U-Net-family Net (model/net_unet_ha_hs.py), by name and shape,
+    so that the reference (build container) and our assembly (GPU box) can be given identical weights without shipping a
+    200 MB state-dict.  `named_shapes`: iterable of (name, shape) over named_parameters().  Buffers keep their
+    constructor values on both sides.  Gains are chosen so that latents quantise to non-trivial symbols."""
+    out: Dict[str, torch.Tensor] = {}
+    for name, shape in named_shapes:
+        shape = tuple(shape)
+        leaf = name.rsplit(".", 1)[-1]
+        if name in ("v_z2_sigma", "z2_sigma") or leaf == "quantiles":
+            continue                                            # constructor values
+        if leaf == "beta":                                      # GDN parameters are stored reparametrised (sqrt of the value + pedestal)
+            r = _rng(seed, name)
+            v = 1.0 + 0.5 * r.uniform(-1, 1, size=shape)
+            out[name] = torch.sqrt(torch.from_numpy(v.astype(np.float32)) + 2.0 ** -36)
+        elif leaf == "gamma":
+            r = _rng(seed, name)
+            ch = shape[0]
+            v = 0.1 * np.eye(ch) + 0.02 * np.abs(r.standard_normal(size=shape)) / math.sqrt(ch / 16.0)
+            out[name] = torch.sqrt(torch.from_numpy(v.astype(np.float32)) + 2.0 ** -36)
+        elif leaf in ("relative_position_bias_table", "relative_position_params"):
+            out[name] = _uniform(seed, name, shape, 0.3)
+        elif len(shape) == 1:
+            if leaf == "weight":                                # LayerNorm scale
+                out[name] = 1.0 + _uniform(seed, name, shape, 0.1)
+            elif name.startswith("cc_scale_transforms.") and name.split(".")[2] == "4":
+                out[name] = 0.8 + _uniform(seed, name, shape, 0.3)   # scale head bias: most sigmas above the 0.11 bound
+            else:
+                out[name] = _uniform(seed, name, shape, 0.05)
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            gain = 1.0
+            if name.startswith("a_model.transform.15."):
+                gain = 15.0                                     # latent y: std of a few quantisation steps
+            elif name.startswith("cc_scale_transforms.") and name.split(".")[2] == "4":
+                gain = 30.0
+            elif name.startswith("cc_mean_transforms.") and name.split(".")[2] == "4":
+                gain = 25.0
+            elif name.startswith("s_model.transform."):         # transposed convs: hold the activation scale through g_s
+                gain = {"2": 0.85, "5": 3.0, "9": 1.5, "12": 1.2}.get(name.split(".")[2], 1.0)   # (IGDN grows like x^2 above 1)
+            elif name.startswith("syntax_model.conv."):
+                gain = 12.0
+            out[name] = _uniform(seed, name, shape, gain / math.sqrt(fan_in))
+    return out

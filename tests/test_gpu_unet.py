@@ -1,0 +1,79 @@
+"""U-Net-family Net (model/net_unet_ha_hs.py, BASELINE configs[2] / [3]) on the kernels + stock-torch blocks against
+fixtures produced by the reference's own file ("restated deps": tests/golden/make_golden_unet.py, oracle/unet_harness.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import det_weights as dw
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+BPP_RTOL, PSNR_ATOL_DB = 5e-3, 1e-2
+
+
+def L(name):
+    d = np.load(os.path.join(G, name))
+    return {k: torch.from_numpy(np.asarray(d[k])) for k in d.files}
+
+
+def test_unet_state_dict_keys_match_reference():
+    """Every non-HAN / non-sampler key of the reference's state-dict, with its shape (dumped from the live reference)."""
+    import ldic_b200
+    from ldic_b200 import net_unet
+    net = net_unet.Net((1, 256, 256, 3), (1, 256, 256, 3), False, False)
+    ours = {k: list(v.shape) for k, v in net.state_dict().items()}
+    ref = json.load(open(os.path.join(G, "unet_state_keys.json")))
+    assert ours == ref
+    # reference checkpoints also carry the one-hot sampler buffers and the HAN head: accepted and dropped under strict=True
+    sd = dict(net.state_dict())
+    sd["y_sampler.sample_filter"] = torch.zeros(1)
+    sd["HAN.head.0.weight"] = torch.zeros(1)
+    net.load_state_dict(sd, strict=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["unet_256x256_b1.npz", "unet_256x512_b2.npz"])
+def test_unet_forward_vs_reference_golden(name):
+    import ldic_b200
+    from ldic_b200 import net_unet
+    ldic_b200._lib.check(ldic_b200._lib.load().ldic_check_device(0), "device")
+    d = L(name)
+    B, H, W, seed = int(d["B"]), int(d["H"]), int(d["W"]), int(d["seed"])
+    net = net_unet.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    fill = dw.unet_param_fill([(n, tuple(p.shape)) for n, p in net.named_parameters()], seed)
+    net.load_state_dict({**net.state_dict(), **{k: v.cuda() for k, v in fill.items()}}, strict=True)
+    # the hot blocks are on the kernels, the small hyperprior windows on the torch path
+    assert net.a_model.transform[8].conv_b[0].backend == "ldic" and net.s_model.transform[7].conv_b[0].backend == "ldic"
+    assert net.h_a.SpatialTransformer1.backend == "torch"
+    x = dw.make_input(seed, B, H, W).cuda()
+    n0 = ldic_b200.ops.launch_count()
+    bpp, v_mse, v_psnr = net(x, "test", 1)
+    assert ldic_b200.ops.launch_count() - n0 > 100            # convs, GDNs, attention cores, likelihoods, tail
+    assert v_mse.shape == (B,)
+    out = net.rd_forward(x, want_x_hat=True)
+    rel = lambda a, b: ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+    y = out["latents"]["y"].cpu()
+    assert rel(y, d["z3"]) < 1.5e-2, rel(y, d["z3"])
+    assert rel(out["latents"]["y_hat"].cpu(), d["y_hat"]) < 5e-2
+    assert rel(out["latents"]["z3_syntax"].cpu(), d["z3_syntax"]) < 2e-2
+    assert abs(bpp.item() / d["bpp"].item() - 1) < BPP_RTOL, (bpp.item(), d["bpp"].item())
+    assert abs(v_psnr.item() - d["v_psnr"].item()) < PSNR_ATOL_DB, (v_psnr.item(), d["v_psnr"].item())
+    bits_ref = d["bits"]
+    assert ((out["bits"].cpu() - bits_ref).abs() < 2 * BPP_RTOL * bits_ref.abs().sum()).all(), (out["bits"].cpu(), bits_ref)
+    assert out["x_hat"].abs().max().item() <= 1.0              # tanh
+
+
+@pytest.mark.gpu
+def test_unet_symbols_bit_exact_on_reference_latents():
+    """BASELINE gate: quantised symbols are bit-exact when fed the reference's y (and its mu / sigma): the
+    GaussianConditional kernel on the fixture's latents reproduces y_hat - lrp, i.e. round(y - mu) + mu, exactly."""
+    import ldic_b200
+    d = L("unet_256x256_b1.npz")
+    y, mu, sc = d["z3"].cuda(), d["means"].cuda(), d["scales"].cuda()
+    vh, lik, s = ldic_b200.ops.gaussian_likelihood(y, sc, mu, quant=ldic_b200.ops.QUANT_DEQUANT,
+                                                   form=ldic_b200.ops.FORM_GAUSSIAN_CONDITIONAL, lik_bound=1e-9,
+                                                   scale_bound=0.11, want_vhat=True)
+    assert torch.equal(vh.cpu(), torch.round(d["z3"] - d["means"]) + d["means"])
+    assert abs(s.item() / d["bits"].sum().item() - 1) < 1e-4
