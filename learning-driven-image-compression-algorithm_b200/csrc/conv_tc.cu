@@ -447,13 +447,16 @@ __device__ __forceinline__ unsigned long long fused_tail_pixels(const ConvParams
   return acc;
 }
 
-template <int NP, bool CL = false>
+// EW = number of epilogue warps (EW / 4 per TMEM lane quadrant, NP / (EW / 4) accumulator columns per thread): 8 in the
+// streaming kernels; the first layer, which IS its epilogue (5 conv MMAs per tile), runs 12 at NP = 192.
+template <int NP, bool CL = false, int EW = kEpiWarps>
 __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing& R, uint32_t tmem_base, int gk,
                                               int ntiles_cta, int warp, int lane) {
-  constexpr int CPT = NP / (kEpiWarps / 4);      // accumulator columns per thread
-  constexpr int LDW = (CPT % 32 == 0) ? 32 : 16;   // columns per tcgen05.ld
+  static_assert(EW % 4 == 0 && NP % (EW / 4) == 0 && (NP / (EW / 4)) % 16 == 0, "epilogue warps must split the columns in 16s");
+  constexpr int CPT = NP / (EW / 4);             // accumulator columns per thread
+  constexpr int LDW = (EW == 8 && CPT % 32 == 0) ? 32 : 16;   // columns per tcgen05.ld (16: register budget of 12 / 16 warps)
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int h = warp >> 2;                // column slice (kEpiWarps / 4 slices of CPT columns)
+    const int h = warp >> 2;                // column slice (EW / 4 slices of CPT columns)
     const int r = q * 32 + lane;            // tile row = TMEM lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const int col0 = h * CPT;
@@ -1497,14 +1500,23 @@ constexpr int kRawSlot = (kRawBytes + 127) / 128 * 128;
 constexpr int kRawX08 = 16;
 constexpr int kRawW8 = (2 * kFirstTW + 4 + kRawX08 + 15) / 16 * 16;   // 160
 constexpr int kRawBytes8 = 3 * kRawH * kRawW8;                       // 3360
-static_assert(kRawBytes8 <= kRawSlot, "uint8 boxes share the raw ring slots");
+constexpr int kStage8Off = kRawBytes8;                               // bf16 copy of the box behind it in the same raw slot
+static_assert(kRawBytes8 % 16 == 0 && kRawBytes8 + 2 * kRawBytes8 <= kRawSlot, "uint8 box + its bf16 copy share a raw ring slot");
 constexpr int kFirstK = 75;
 constexpr int kBuildThreads = 64;                   // warps 10 and 11
 
-__device__ __forceinline__ uint32_t ld_shared_u8(uint32_t addr) {
+__device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return (uint32_t)v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
   uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   float v;
@@ -1512,12 +1524,16 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
   return v;
 }
 
-template <int NP, bool U8 = false>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NP, bool U8 = false, int EW = kEpiWarps>
+__global__ void __launch_bounds__(EW * 32 + 128, 1)
 conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
   constexpr int kBTileBytes = NP * kBlockK * 2;
   constexpr int GK = NP / 64;
+  // roles: warps 0..EW-1 epilogue, EW TMA, EW+1 MMA, EW+2 / EW+3 patch builders
+  constexpr int kEpiThreads = EW * 32, kThreads = EW * 32 + 128, kProdWarp = EW, kMmaWarp = EW + 1, kProdBWarp = EW + 2;
+  constexpr int kEpiWarps = EW;
+  constexpr int kEpiRegs = EW == 8 ? 216 : (EW == 12 ? 144 : 104);
   constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
@@ -1658,47 +1674,56 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(&empty_bar[s1], (((p0 + 1) / (uint32_t)S) & 1u) ^ 1u);
         const uint32_t a0 = ring_base + s0 * kATileBytes, a1 = ring_base + s1 * kATileBytes;
         const uint32_t raw = raw_base + rs * kRawSlot;
-        int ix0 = 0, iy00 = 0;
         if constexpr (U8) {
+          // uint8 image: first turn the whole box into the bf16 operand values x = (u/255)*2-1 once (every level is used
+          // by ~6 patches), zero outside the image (TMA zero-fills the LEVELS there, but a zero level is x = -1, not the
+          // ZeroPad2d's 0).  bf16((u/255)*2-1) == bf16(fma(u, 2/255, -1)) for all 256 levels (tests/test_oracle_golden.py).
           const TileCoord tc = decode_tile(P, blockIdx.x + it * gridDim.x);
-          ix0 = 2 * (tc.x0 + tb) - 1; iy00 = 2 * tc.y0 - 1;             // image position of tap (0,0) of row 0
+          const int bx0 = 2 * tc.x0 - kRawX08, by0 = 2 * tc.y0 - 1;      // image position of the box origin
+          for (int g = tb; g < kRawBytes8 / 4; g += kBuildThreads) {
+            const uint32_t w4 = ld_shared_u32(raw + 4u * (uint32_t)g);
+            const int xx = (g % (kRawW8 / 4)) * 4, rr = (g / (kRawW8 / 4)) % kRawH;
+            const bool rowok = (unsigned)(by0 + rr) < (unsigned)P.tail_H;
+            float v4[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const bool ok = rowok && (unsigned)(bx0 + xx + b) < (unsigned)P.tail_W;
+              v4[b] = ok ? __fmaf_rn((float)((w4 >> (8 * b)) & 0xffu), 2.f / 255.f, -1.f) : 0.f;
+            }
+            st_shared_v2(raw + kStage8Off + 8u * (uint32_t)g, pack_bf16x2(v4[0], v4[1]), pack_bf16x2(v4[2], v4[3]));
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kBuildThreads) : "memory");   // the two builder warps only
         }
 #pragma unroll
         for (int ly = 0; ly < kFirstTH; ++ly) {
           const int r = ly * kFirstTW + tb;                             // tile row = TMEM lane
-          const uint32_t src = U8 ? raw + (uint32_t)((2 * ly) * kRawW8 + 2 * tb + (kRawX08 - 1))
+          const uint32_t src = U8 ? raw + kStage8Off + (uint32_t)((2 * ly) * kRawW8 + 2 * tb + (kRawX08 - 1)) * 2u
                                   : raw + (uint32_t)((2 * ly) * kRawW + 2 * tb + (kRawX0 - 1)) * 4u;
           const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
-          uint32_t okx = 0, oky = 0;                                    // uint8: taps inside the image (bit kx / ky)
-          if constexpr (U8) {
-#pragma unroll
-            for (int t = 0; t < 5; ++t) {
-              okx |= (uint32_t)((unsigned)(ix0 + t) < (unsigned)P.tail_W) << t;
-              oky |= (uint32_t)((unsigned)(iy00 + 2 * ly + t) < (unsigned)P.tail_H) << t;
-            }
-          }
 #pragma unroll
           for (int j = 0; j < 10; ++j) {                                // 16-byte chunks: k = 8j .. 8j+7
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float v[2];
+              if constexpr (U8) {
+                uint32_t h2[2];
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int k = 8 * j + 2 * e + u;                        // k = (ky*5 + kx)*3 + c
-                v[u] = 0.f;
-                if (k < kFirstK) {
-                  if constexpr (U8) {
-                    // bf16((u/255)*2-1) == bf16(fma(u, 2/255, -1)) for all 256 levels (tests/test_oracle_golden.py)
-                    const float lv = (float)ld_shared_u8(src + (uint32_t)(((k % 3) * kRawH + k / 15) * kRawW8 + (k / 3) % 5));
-                    const bool ok = ((okx >> ((k / 3) % 5)) & (oky >> (k / 15)) & 1u) != 0;
-                    v[u] = ok ? __fmaf_rn(lv, 2.f / 255.f, -1.f) : 0.f;
-                  } else {
-                    v[u] = ld_shared_f32(src + (uint32_t)(((k % 3) * kRawH + k / 15) * kRawW + (k / 3) % 5) * 4u);
-                  }
+                for (int u = 0; u < 2; ++u) {
+                  const int k = 8 * j + 2 * e + u;                      // k = (ky*5 + kx)*3 + c
+                  h2[u] = 0u;
+                  if (k < kFirstK) h2[u] = ld_shared_u16(src + (uint32_t)(((k % 3) * kRawH + k / 15) * kRawW8 + (k / 3) % 5) * 2u);
                 }
+                pk[e] = h2[0] | (h2[1] << 16);
+              } else {
+                float v[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int k = 8 * j + 2 * e + u;                      // k = (ky*5 + kx)*3 + c
+                  v[u] = 0.f;
+                  if (k < kFirstK) v[u] = ld_shared_f32(src + (uint32_t)(((k % 3) * kRawH + k / 15) * kRawW + (k / 3) % 5) * 4u);
+                }
+                pk[e] = pack_bf16x2(v[0], v[1]);
               }
-              pk[e] = pack_bf16x2(v[0], v[1]);
             }
             const uint32_t dst = (j < 8 ? a0 : a1) + row_off + ((((uint32_t)(j & 7)) ^ rx) << 4);
             st_shared_v4(dst, pk[0], pk[1], pk[2], pk[3]);
@@ -1718,7 +1743,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     R.ring_base = ring_base; R.slot_bytes = kATileBytes; R.nslots = (uint32_t)S; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
     R.s_bias = s_bias; R.s_beta = s_beta; R.insert_after = P.gdn_insert;
-    epilogue_role<NP>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
+    epilogue_role<NP, false, EW>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
   }
 
   tc_fence_before();
@@ -2027,6 +2052,7 @@ struct Plan {
   ConvParams P;
   CUtensorMap a, w, g;
   int kernel, np, grid;
+  int epi_warps;           // first-layer kernel: 12 epilogue warps at 192 channels (three per TMEM lane quadrant), else 8
   size_t smem;
   int kind;
 };
@@ -2094,10 +2120,10 @@ int plan_wide(Plan* pl) {
   pl->grid = 2 * (total_super < mc ? total_super : mc);
   return LDIC_OK;
 }
-template <int NP, bool U8>
+template <int NP, bool U8, int EW>
 int plan_first(Plan* pl) {
   static KernelState ks;
-  int rc = prepare_kernel(conv_first_kernel<NP, U8>, ks, false, nullptr);
+  int rc = prepare_kernel(conv_first_kernel<NP, U8, EW>, ks, false, nullptr);
   if (rc) return rc;
   const int sms = num_sms();
   pl->grid = pl->P.total_tiles < sms ? pl->P.total_tiles : sms;
@@ -2118,16 +2144,16 @@ int finish_plan(Plan* pl) {
     case PK_WIDE: return plan_wide<384>(pl);
     case PK_FIRST:
       switch (pl->np) {
-        case 64: return plan_first<64, false>(pl);
-        case 128: return plan_first<128, false>(pl);
-        case 192: return plan_first<192, false>(pl);
+        case 64: return plan_first<64, false, 8>(pl);
+        case 128: return plan_first<128, false, 8>(pl);
+        case 192: return pl->epi_warps == 12 ? plan_first<192, false, 12>(pl) : plan_first<192, false, 8>(pl);
       }
       break;
     case PK_FIRST_U8:
       switch (pl->np) {
-        case 64: return plan_first<64, true>(pl);
-        case 128: return plan_first<128, true>(pl);
-        case 192: return plan_first<192, true>(pl);
+        case 64: return plan_first<64, true, 8>(pl);
+        case 128: return plan_first<128, true, 8>(pl);
+        case 192: return pl->epi_warps == 12 ? plan_first<192, true, 12>(pl) : plan_first<192, true, 8>(pl);
       }
       break;
   }
@@ -2150,12 +2176,15 @@ int launch_plan(const Plan& pl, cudaStream_t st) {
     case PK_FIRST_U8: {
       const bool u8 = pl.kernel == PK_FIRST_U8;
       switch (pl.np) {
-        case 64: if (u8) conv_first_kernel<64, true><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P);
-                 else conv_first_kernel<64, false><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P); break;
-        case 128: if (u8) conv_first_kernel<128, true><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P);
-                  else conv_first_kernel<128, false><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P); break;
-        case 192: if (u8) conv_first_kernel<192, true><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P);
-                  else conv_first_kernel<192, false><<<pl.grid, kThreads, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P); break;
+#define LDIC_LAUNCH_FIRST(NPV, U8V, EWV) \
+  conv_first_kernel<NPV, U8V, EWV><<<pl.grid, EWV * 32 + 128, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P)
+        case 64: if (u8) LDIC_LAUNCH_FIRST(64, true, 8); else LDIC_LAUNCH_FIRST(64, false, 8); break;
+        case 128: if (u8) LDIC_LAUNCH_FIRST(128, true, 8); else LDIC_LAUNCH_FIRST(128, false, 8); break;
+        case 192:
+          if (pl.epi_warps == 12) { if (u8) LDIC_LAUNCH_FIRST(192, true, 12); else LDIC_LAUNCH_FIRST(192, false, 12); }
+          else { if (u8) LDIC_LAUNCH_FIRST(192, true, 8); else LDIC_LAUNCH_FIRST(192, false, 8); }
+          break;
+#undef LDIC_LAUNCH_FIRST
         default: return fail(LDIC_EINVAL, "first conv: unsupported Np %d", pl.np);
       }
       return check_launch("conv_first_kernel");
@@ -2272,6 +2301,7 @@ int build_plan_first(const LdicConvDesc* d, const Layer& L, const void* x, const
   }
   pl->kernel = u8 ? PK_FIRST_U8 : PK_FIRST;
   pl->np = L.Np;
+  pl->epi_warps = (L.Np == 192 && tuning().first_epi != 8) ? 12 : 8;
   if ((rc = finish_plan(pl))) return rc;
   apply_sm_limit(d, pl);
   return LDIC_OK;

@@ -37,6 +37,7 @@ static Tuning g_tuning = [] {
   t.stages_cap = env("LDIC_STAGES", 0);
   t.tail_wide = env("LDIC_TAIL_WIDE", 1);
   t.lik_grid = env("LDIC_LIK_GRID", 0);
+  t.first_epi = env("LDIC_FIRST_EPI", 0);      // epilogue warps of the first-layer kernel: 0 = default (12 at 192 channels), 8
   t.epoch = 0;
   return t;
 }();
@@ -58,6 +59,7 @@ extern "C" int ldic_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "stages")) f = &t.stages_cap;
   else if (!strcmp(key, "tail_wide")) f = &t.tail_wide;
   else if (!strcmp(key, "lik_grid")) f = &t.lik_grid;
+  else if (!strcmp(key, "first_epi")) f = &t.first_epi;
   if (!f) return fail(LDIC_EINVAL, "set_tuning: unknown key '%s'", key);
   std::lock_guard<std::mutex> lk(g_init_mu);
   const int old = *f;

@@ -11,8 +11,6 @@ weight version) on NHWC bf16 activations.
 """
 from __future__ import annotations
 
-import os
-
 import torch
 import torch.nn as nn
 
@@ -41,7 +39,13 @@ class _PlannedTransform(nn.Module):
 
 
 class analysisTransformModel(_PlannedTransform):
-    """model/net.py:91-118.  4x [ZeroPad2d((1,2,1,2)) -> Conv2d(k5,s2)] with GDN after convs 1-3."""
+    """model/net.py:91-118.  4x [ZeroPad2d((1,2,1,2)) -> Conv2d(k5,s2)] with GDN after convs 1-3.
+
+    First layer (Cin = 3): up to 192 output channels run on conv_first_kernel (patches built from the NCHW image in
+    shared memory, GDN fused, weights and gamma resident); wider models (N = 384) build a bf16 patch matrix with
+    ldic_im2col_5x5s2 and run the 1x1 GEMM + GDN on conv_wide_kernel.  `first_fused = False` forces the patch-matrix
+    form (tests cross-check the two)."""
+    first_fused = True
 
     def __init__(self, in_dim, num_filters, conv_trainable=True):
         super().__init__()
@@ -60,8 +64,7 @@ class analysisTransformModel(_PlannedTransform):
         c1 = t[1]
         self._kp1 = ops._pad64(25 * c1.in_channels)
         self._first_fused = False
-        if (c1.in_channels == 3 and c1.out_channels in (64, 128, 192)
-                and os.environ.get("LDIC_FIRST_FUSED", "1") != "0"):
+        if c1.in_channels == 3 and c1.out_channels in (64, 128, 192) and self.first_fused:
             # first layer + GDN straight from the NCHW fp32 image (no patch matrix in HBM)
             layers.append(ops.ConvTC(_lib.LDIC_CONV_FIRST_5x5S2, c1.weight.detach(), c1.bias.detach(),
                                      act=_lib.ACT_GDN, gdn=self._gdn_args(t[2])))

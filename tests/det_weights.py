@@ -191,7 +191,8 @@ def unet_param_fill(named_shapes, seed: int = 0) -> Dict[str, torch.Tensor]:
             elif name.startswith("cc_mean_transforms.") and name.split(".")[2] == "4":
                 gain = 25.0
             elif name.startswith("s_model.transform."):         # transposed convs: hold the activation scale through g_s
-                gain = {"2": 0.85, "5": 3.0, "9": 1.5, "12": 1.2}.get(name.split(".")[2], 1.0)   # (IGDN grows like x^2 above 1)
+                gain = {"2": 0.45, "5": 2.2, "9": 1.3, "12": 1.2}.get(name.split(".")[2], 1.0)   # (IGDN grows like x^2 above 1:
+                # keep |x| below ~1 so that a flipped symbol is not amplified four times on its way to the image)
             elif name.startswith("syntax_model.conv."):
                 gain = 12.0
             out[name] = _uniform(seed, name, shape, gain / math.sqrt(fan_in))
