@@ -177,7 +177,8 @@ def run_ours(args):
     Nw, Mw = (384, 32) if high else (192, 16)
     net = ldic_b200.Net((B, H, W, 3), (B, H, W, 3), high, False).to(dev).eval()
     net.load_state_dict(dw.make_state_dict(0, N=Nw, M=Mw), strict=True)
-    net.side_sms = args.side_sms
+    if args.side_sms >= 0:
+        net.side_sms = args.side_sms
     net.auto_graph = not args.no_graph
     ev = ShardedEvaluator(net)
     NBUF = 4
@@ -757,7 +758,7 @@ def main():
     ap.add_argument("--crop", default="512x768", help="unet: image size HxW, multiples of 256 (configs[3]: 1080x1920 crops pad to 1280x2048)")
     ap.add_argument("--global-batch", type=int, default=0, help="unet: global batch (default 64 at 768x512, else 32)")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"], help="image type of the input buffers")
-    ap.add_argument("--side-sms", type=int, default=0, help="SM partition for the hyperprior / syntax side stream (0: single stream)")
+    ap.add_argument("--side-sms", type=int, default=-1, help="SM partition for the hyperprior / syntax side stream (0: single stream; default: Net's)")
     args = ap.parse_args()
     args.batch_set = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
     if args.config == "unet":

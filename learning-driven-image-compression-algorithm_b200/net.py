@@ -190,7 +190,7 @@ class Net(nn.Module):
         # SM partition: the hyperprior / syntax chain (h_a, likelihood z, h_s, syntax branch: small grids of 12..48 CTAs)
         # runs on a side stream on `side_sms` SMs while the first three g_s deconvs, which depend on round(y) only,
         # run on the remaining SMs of the main stream (persistent kernels with their grids capped accordingly).
-        self.side_sms = 0                 # 0: single stream
+        self.side_sms = 12                # SMs of the side stream; 0: single stream (same-box interleaved A/B: 3.31 -> 3.19 ms per step)
         self._side_streams = {}
         # forward(x, 'test'): transparent CUDA-graph capture / replay per input shape (see forward)
         self.auto_graph = True
@@ -300,8 +300,9 @@ class Net(nn.Module):
             gs_body = self.s_model.forward_nhwc_body(y_round_bf16, sm_limit=-self.side_sms)   # :800 first three deconv + IGDN
             main.wait_stream(side)                                                  # join
             if not torch.cuda.is_current_stream_capturing():
-                for t in (z, h2) + tuple(syn):
-                    t.record_stream(main)
+                for t in (z, h2, lik_z) + tuple(syn):
+                    if t is not None:
+                        t.record_stream(main)
         else:
             z, h2, syn = hyper_chain(0)
         z3_syntax, z3_syntax_rounded, syn_first, syn_second, conv_w = syn
