@@ -376,7 +376,7 @@ def run_ours(args):
     # BASELINE configs[3] (1152x1920 padded crops, 4 images per GPU): 288 x 480 tokens x 192 channels, 8x8 windows, shift 4
     wa_B, wa_H, wa_W, wa_C, wa_heads, wa_ws = 4, 288, 480, 192, 8, 8
     qkv = [torch.randn(wa_B, wa_H, wa_W, wa_C, device=dev).to(torch.bfloat16) for _ in range(3)]
-    wa_bias = torch.randn(wa_heads, wa_ws * wa_ws, wa_ws * wa_ws, device=dev) * 0.1
+    wa_bias = torch.randn((2 * wa_ws - 1) ** 2, wa_heads, device=dev) * 0.1      # relative_position_bias_table, indexed in the kernel
     for _ in range(3):
         ops.window_attention_core(qkv[0], qkv[1], qkv[2], wa_bias, wa_heads, wa_ws, 4)
     torch.cuda.synchronize(dev)

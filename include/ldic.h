@@ -304,6 +304,11 @@ LDIC_API int ldic_window_attention_bias(const float* table, const long long* ind
                                void* stream);
 LDIC_API int ldic_window_attention_core(const void* q, const void* k, const void* v, const float* bias, void* out, int B,
                                int H, int W, int C, int heads, int ws, int shift, void* stream);
+/* Same with the module's relative_position_bias_table [(2ws-1)^2][heads] itself (layers/win_attention.py:64): the kernel
+ * keeps the table in shared memory and derives bias(i, j) from the two tokens' window coordinates, instead of streaming
+ * the gathered [heads][N][N] tensor (128 KB per window at 8 heads, 8x8 windows) through L2.                      */
+LDIC_API int ldic_window_attention_core_table(const void* q, const void* k, const void* v, const float* table, void* out, int B,
+                                     int H, int W, int C, int heads, int ws, int shift, void* stream);
 LDIC_API int ldic_residual_nhwc_to_nchw_f32(const float* o_nhwc, const float* shortcut_nchw, float* y_nchw, int B, int C,
                                    int H, int W, int Cp, void* stream);
 

@@ -117,6 +117,8 @@ _SIGS = {
     "ldic_window_attention_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldic_window_attention_core": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ldic_window_attention_core_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldic_residual_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_int, C.c_void_p]),
     "ldic_debug_last_timeout": (C.c_int, [C.POINTER(C.c_ulonglong)]),

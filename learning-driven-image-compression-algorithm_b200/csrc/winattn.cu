@@ -21,6 +21,7 @@ using namespace ldic;
 namespace {
 
 constexpr int kWaMaxTokens = 64;
+constexpr int kWaMaxHeads = 16, kWaMaxTab = 15 * 15;      // (2 * 8 - 1)^2 table entries per head
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -32,8 +33,10 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 struct WaParams {
   const __nv_bfloat16 *q, *k, *v;      // [B*H*W][C] token images (q already scaled by head_dim^-0.5)
   __nv_bfloat16* out;                  // [B*H*W][C]
-  const float* bias;                   // [heads][N][N] relative position bias (already gathered)
+  const float* bias;                   // [heads][N][N] relative position bias (already gathered), or, with bias_table, the
+                                       // module's relative_position_bias_table [(2ws-1)^2][heads] itself
   int B, H, W, C, heads, ws, shift;
+  int bias_table;
 };
 
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t saddr) {
@@ -54,6 +57,17 @@ __global__ void __launch_bounds__(256, 2) k_window_attention(WaParams P) {
   uint8_t* s_qkv = smem;                                 // [N][pitch]
   __shared__ int s_pix[kWaMaxTokens];                    // token -> pixel index in the (B,H,W) image
   __shared__ int s_reg[kWaMaxTokens];                    // token -> region id of the shift mask
+  // relative position bias table, [head][(2ws-1)^2]: 7.2 KB at 8 heads / 8x8 windows.  The gathered [heads][N][N] form is
+  // 128 KB per window -- more than the window's q | k | v rows -- and does not stay in L1 next to two CTAs' shared memory:
+  // its loads ran at L2 latency in front of every softmax (ncu: the kernel's top stall).  bias(i, j) =
+  // table[(yi - yj + ws-1) * (2ws-1) + (xi - xj + ws-1)] (layers/win_attention.py:64-78, 101-104) is index arithmetic.
+  __shared__ float s_tab[kWaMaxHeads * kWaMaxTab];
+  const int ws_ = P.ws, Lt = (2 * ws_ - 1) * (2 * ws_ - 1);
+  if (P.bias_table)
+    for (int i = threadIdx.x; i < P.heads * Lt; i += blockDim.x) {
+      const int hh = i / Lt, idx = i - hh * Lt;
+      s_tab[i] = __ldg(P.bias + idx * P.heads + hh);
+    }
 
   const int ws = P.ws, nwx = P.W / ws, nwy = P.H / ws;
   const int win = blockIdx.x;
@@ -129,11 +143,22 @@ __global__ void __launch_bounds__(256, 2) k_window_attention(WaParams P) {
       // + bias + mask, softmax over the N keys of rows r0 (elements 0,1) and r1 (elements 2,3)
       const int reg0 = s_reg[r0], reg1 = s_reg[r1];
       float m0 = -INFINITY, m1 = -INFINITY;
+      const int wsh = ws == 8 ? 3 : 2, tw = 2 * ws - 1;
+      const float* tab_h = s_tab + h * Lt;
+      const int t0 = ((r0 >> wsh) + ws - 1) * tw + (r0 & (ws - 1)) + ws - 1;      // table index of (row r0, column 0)
+      const int t1 = ((r1 >> wsh) + ws - 1) * tw + (r1 & (ws - 1)) + ws - 1;
 #pragma unroll
       for (int nt = 0; nt < N / 8; ++nt) {
         const int col = nt * 8 + t4 * 2;
-        const float2 b0 = __ldg(reinterpret_cast<const float2*>(bias_h + r0 * N + col));
-        const float2 b1 = __ldg(reinterpret_cast<const float2*>(bias_h + r1 * N + col));
+        float2 b0, b1;
+        if (P.bias_table) {                              // column (ci, cj): index drops by ci * (2ws-1) + cj; col + 1 is cj + 1
+          const int dc = (col >> wsh) * tw + (col & (ws - 1));
+          b0.x = tab_h[t0 - dc]; b0.y = tab_h[t0 - dc - 1];
+          b1.x = tab_h[t1 - dc]; b1.y = tab_h[t1 - dc - 1];
+        } else {
+          b0 = __ldg(reinterpret_cast<const float2*>(bias_h + r0 * N + col));
+          b1 = __ldg(reinterpret_cast<const float2*>(bias_h + r1 * N + col));
+        }
         float v0 = s[nt][0] + b0.x, v1 = s[nt][1] + b0.y, v2 = s[nt][2] + b1.x, v3 = s[nt][3] + b1.y;
         if (P.shift > 0) {
           const int rc0 = s_reg[col], rc1 = s_reg[col + 1];
@@ -267,8 +292,18 @@ extern "C" int ldic_window_attention_bias(const float* table, const long long* i
   return check_launch("k_gather_rel_bias");
 }
 
+static int window_attention_impl(const void* q, const void* k, const void* v, const float* bias, int bias_table, void* out,
+                                 int B, int H, int W, int C, int heads, int ws, int shift, void* stream);
 extern "C" int ldic_window_attention_core(const void* q, const void* k, const void* v, const float* bias, void* out, int B, int H,
                                           int W, int C, int heads, int ws, int shift, void* stream) {
+  return window_attention_impl(q, k, v, bias, 0, out, B, H, W, C, heads, ws, shift, stream);
+}
+extern "C" int ldic_window_attention_core_table(const void* q, const void* k, const void* v, const float* table, void* out,
+                                                int B, int H, int W, int C, int heads, int ws, int shift, void* stream) {
+  return window_attention_impl(q, k, v, table, 1, out, B, H, W, C, heads, ws, shift, stream);
+}
+static int window_attention_impl(const void* q, const void* k, const void* v, const float* bias, int bias_table, void* out,
+                                 int B, int H, int W, int C, int heads, int ws, int shift, void* stream) {
   if (!q || !k || !v || !bias || !out) return fail(LDIC_EINVAL, "window attention: null tensor");
   if (B <= 0) return LDIC_OK;
   if (heads <= 0 || C % heads || C % 8 || (ws != 8 && ws != 4) || H % ws || W % ws || shift < 0 || shift >= ws)
@@ -276,7 +311,8 @@ extern "C" int ldic_window_attention_core(const void* q, const void* k, const vo
   const int hd = C / heads;
   if (hd % 2 || hd > 32) return fail(LDIC_EINVAL, "window attention: head_dim must be even and <= 32 (got %d)", hd);
   if (heads > 16) return fail(LDIC_EINVAL, "window attention: at most 16 heads");
-  WaParams P{(const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, bias, B, H, W, C, heads, ws, shift};
+  WaParams P{(const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, bias, B, H, W, C, heads, ws, shift,
+             bias_table};
   cudaStream_t st = (cudaStream_t)stream;
   const bool wide = hd > 16;
   if (ws == 8) return wide ? launch_wa<32, 64>(P, st) : launch_wa<16, 64>(P, st);

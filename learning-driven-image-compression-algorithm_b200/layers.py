@@ -208,8 +208,17 @@ class WindowAttention(nn.Module):
             k = mk(w[Cd:2 * Cd], b[Cd:2 * Cd], False)
             v = mk(w[2 * Cd:], b[2 * Cd:], False)
             pr = mk(self.proj.weight.detach().float(), self.proj.bias.detach().float(), True)
-            bias = ops.window_attention_bias(self.relative_position_bias_table.detach(), self.relative_position_index,
-                                             self.num_heads, self.window_size[0])
+            # the kernel indexes the (2ws-1)^2 x heads table itself (relative_position_index is the standard Swin index,
+            # layers/win_attention.py:64-78; ops.window_attention_bias gathers the [heads, N, N] form for any other index)
+            ws = self.window_size[0]
+            cf = torch.stack(torch.meshgrid([torch.arange(ws), torch.arange(ws)], indexing="ij")).flatten(1)
+            rel = (cf[:, :, None] - cf[:, None, :]).permute(1, 2, 0) + (ws - 1)
+            standard = rel[:, :, 0] * (2 * ws - 1) + rel[:, :, 1]
+            if torch.equal(self.relative_position_index.detach().cpu().long(), standard):
+                bias = self.relative_position_bias_table.detach().float().contiguous()
+            else:                # a checkpoint with a different index buffer: gather the [heads, N, N] form with it
+                bias = ops.window_attention_bias(self.relative_position_bias_table.detach(), self.relative_position_index,
+                                                 self.num_heads, ws)
             self._packed = (q, k, v, pr, bias)
             self._key = key
         return self._packed

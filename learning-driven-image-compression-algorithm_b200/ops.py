@@ -556,9 +556,15 @@ def window_attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bia
             raise LdicError("window_attention_core: q, k, v must be contiguous NHWC bf16 tensors of one shape")
     _req(bias, torch.float32, "bias")
     B, H, W, Cc = q.shape
-    if tuple(bias.shape) != (heads, ws * ws, ws * ws) or not bias.is_contiguous():
-        raise LdicError("window_attention_core: bias must be contiguous (heads, ws^2, ws^2)")
     out = torch.empty_like(q)
+    if bias.dim() == 2:          # the module's relative_position_bias_table [(2ws-1)^2, heads]: indexed inside the kernel
+        if tuple(bias.shape) != ((2 * ws - 1) ** 2, heads) or not bias.is_contiguous():
+            raise LdicError("window_attention_core: bias table must be contiguous ((2ws-1)^2, heads)")
+        check(_L().ldic_window_attention_core_table(_ptr(q), _ptr(k), _ptr(v), _ptr(bias), _ptr(out), B, H, W, Cc, int(heads),
+                                                    int(ws), int(shift), _stream()), "ldic_window_attention_core_table")
+        return out
+    if tuple(bias.shape) != (heads, ws * ws, ws * ws) or not bias.is_contiguous():
+        raise LdicError("window_attention_core: bias must be contiguous (heads, ws^2, ws^2) or the table ((2ws-1)^2, heads)")
     check(_L().ldic_window_attention_core(_ptr(q), _ptr(k), _ptr(v), _ptr(bias), _ptr(out), B, H, W, Cc, int(heads), int(ws),
                                           int(shift), _stream()), "ldic_window_attention_core")
     return out

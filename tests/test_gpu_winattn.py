@@ -92,3 +92,17 @@ def test_rejects_bad_shapes(ldic):
         blk(torch.randn(1, 192, 12, 16).cuda())       # H not a multiple of the window
     with pytest.raises(ldic.LdicError):
         blk(torch.randn(1, 192, 16, 16))              # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("dim,heads,ws,shift,H,W", [(192, 8, 8, 4, 32, 48), (192, 8, 4, 2, 16, 24), (128, 8, 4, 0, 8, 8), (64, 8, 4, 2, 12, 8)])
+def test_bias_table_path_equals_gathered_bias(ldic, dim, heads, ws, shift, H, W):
+    """ldic_window_attention_core_table (bias indexed from the (2ws-1)^2 x heads table in shared memory) is bit-identical
+    to the kernel fed the gathered [heads, N, N] bias (layers/win_attention.py:101-104)."""
+    g = torch.Generator().manual_seed(ws + shift + H)
+    q, k, v = (torch.randn(2, H, W, dim, generator=g).to(torch.bfloat16).cuda() for _ in range(3))
+    blk = ldic.WinBasedAttention(dim=dim, num_heads=heads, window_size=ws, shift_size=shift)
+    table = (torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5).cuda()
+    gathered = ldic.ops.window_attention_bias(table, blk.attn.relative_position_index.cuda(), heads, ws)
+    o_tab = ldic.ops.window_attention_core(q, k, v, table, heads, ws, shift)
+    o_gat = ldic.ops.window_attention_core(q, k, v, gathered, heads, ws, shift)
+    assert torch.equal(o_tab, o_gat)

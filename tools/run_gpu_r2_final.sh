@@ -24,9 +24,18 @@ echo "ncu high exit $?" >> gpurun_out/summary.txt
 timeout 120 python tools/prof_tritplane.py 5 > gpurun_out/trit_plain.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tritplane -s 3 -c 1 -o gpurun_out/prof_trit -f python tools/prof_tritplane.py 5 > gpurun_out/ncu_trit.log 2>&1
 echo "ncu trit exit $?" >> gpurun_out/summary.txt
+timeout 120 python tools/prof_winattn.py 5 > gpurun_out/winattn_plain.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_window_attention -s 3 -c 1 -o gpurun_out/prof_winattn -f python tools/prof_winattn.py 5 > gpurun_out/ncu_winattn.log 2>&1
+echo "ncu winattn exit $?" >> gpurun_out/summary.txt
 timeout 120 python tools/prof_likelihood.py 5 > gpurun_out/lik_plain.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_likelihood -s 3 -c 1 -o gpurun_out/prof_lik -f python tools/prof_likelihood.py 5 > gpurun_out/ncu_lik.log 2>&1
 echo "ncu lik exit $?" >> gpurun_out/summary.txt
+# reports -> raw CSV pages here (the .ncu-rep files of several full captures exceed what travels back), keep the small ones
+for r in prof_step prof_high prof_trit prof_lik prof_winattn; do
+  if [ -f gpurun_out/$r.ncu-rep ]; then ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/${r}_raw.csv 2>/dev/null; fi
+done
+ncu -i gpurun_out/prof_step.ncu-rep --page source --csv --kernel-name regex:conv_first -c 1 > gpurun_out/src_first.csv 2>/dev/null
+rm -f gpurun_out/prof_step.ncu-rep gpurun_out/prof_high.ncu-rep
 nproc > gpurun_out/nproc.txt; lscpu | head -20 >> gpurun_out/nproc.txt
 cat gpurun_out/summary.txt; tail -n 3 gpurun_out/pytest_gpu.log gpurun_out/trit_plain.log gpurun_out/lik_plain.log
 for f in bench bench_sustained bench_nograph bench_high bench_trit bench_unet_b16 bench_ref; do python - <<PY
