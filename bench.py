@@ -33,12 +33,22 @@ H, W = 512, 768
 
 def measured_traffic():
     """dram__bytes_read+write of the roofline kernels from the committed ncu --set full capture (profiles/)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            return float(t["conv_kernels"]["dram_bytes_per_step"]), float(t["likelihood_c5"]["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None, None
+
+
+def measured_traffic_of(key):
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)
-        return float(t["conv_kernels"]["dram_bytes_per_step"]), float(t["likelihood_c5"]["dram_bytes_per_launch"])
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return float(json.load(f)[key]["dram_bytes_per_launch"])
     except Exception:
-        return None, None
+        return None
 
 
 def peaks():
@@ -421,7 +431,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "conv_first / conv_tc / conv_halo kernels (g_a, g_s, h_a, h_s, context convs + fused GDN/IGDN)",
                      "achieved": achieved_tf, "peak": tc_peak_sus, "unit": "TFLOP/s",
                      "frac": achieved_tf / tc_peak_sus if tc_peak_sus else None,
-                     "traffic": conv_traffic, "traffic_note": "DRAM bytes of all conv launches of one step (ncu --set full, profiles/r01_traffic.json)",
+                     "traffic": conv_traffic, "traffic_note": "DRAM bytes of all conv launches of one step (ncu --set full, profiles/r02_traffic.json)",
                      "peak_source": f"{peak_src} bf16_tflops_sustained",
                      "algorithmic_gflop_per_image": conv_flops / 1e9 / (B * args.steps),
                      "conv_ms_per_step": conv_ms / args.steps,
@@ -435,7 +445,7 @@ def run_ours(args):
                                 "peak_source": f"{peak_src} hbm_gbs", "workload": "C5-size 16x192x128x128, per-element mu/sigma"},
         "roofline_window_attention": {"bound": "hbm", "kernel": "k_window_attention<32,64> (softmax(q k^T + bias + shift mask) v per 8x8 window)",
                                       "achieved": wa_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": wa_gbs / hbm_peak,
-                                      "traffic": None, "bytes_per_token": wa_C * 2 * 4, "tokens": wa_tokens, "ms": wa_ms,
+                                      "traffic": measured_traffic_of("window_attention"), "bytes_per_token": wa_C * 2 * 4, "tokens": wa_tokens, "ms": wa_ms,
                                       "peak_source": f"{peak_src} hbm_gbs",
                                       "workload": "4 x 288x480 tokens x 192 ch (1/4 resolution of a 1152x1920 crop), 8 heads, window 8, shift 4"},
         "parity": {"bpp": float(bpp.item()), "psnr_db": float(psnr.item()), "multi_gpu_equal": multi_gpu_equal,
@@ -585,7 +595,9 @@ def run_tritplane(args):
                       "d2h_bytes_per_step": (Lp + 4) * n + 4 * Lp},
               "gpu_launches": launches, "clocks": clocks,
               "roofline": {"bound": "hbm", "kernel": "k_tritplane", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": gbs / hbm_peak, "traffic": None, "bytes_per_elem": bytes_per_elem, "elems": n, "ms": k_ms,
+                           "frac": gbs / hbm_peak, "traffic": measured_traffic_of("tritplane_c5") if B == 16 else None,
+                           "bytes_per_elem": bytes_per_elem, "elems": n, "ms": k_ms,
+                           "note": "ALU bound, not HBM bound: 10 erfc + 5 log evaluations per element (L + 1 nested interval masses)",
                            "peak_source": f"{peak_src} hbm_gbs"},
               "parity": {"symbols_bit_exact": sym_ok, "sum_ln_per_plane": [float(x) for x in s64.tolist()]}})
     if world > 1:

@@ -1533,7 +1533,8 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // roles: warps 0..EW-1 epilogue, EW TMA, EW+1 MMA, EW+2 / EW+3 patch builders
   constexpr int kEpiThreads = EW * 32, kThreads = EW * 32 + 128, kProdWarp = EW, kMmaWarp = EW + 1, kProdBWarp = EW + 2;
   constexpr int kEpiWarps = EW;
-  constexpr int kEpiRegs = EW == 8 ? 216 : (EW == 12 ? 144 : 112);
+  constexpr int kEpiRegs = EW == 8 ? 216 : 144;
+  static_assert(EW == 8 || EW == 12, "first layer: 8 or 12 epilogue warps");
   constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
@@ -2146,14 +2147,14 @@ int finish_plan(Plan* pl) {
       switch (pl->np) {
         case 64: return plan_first<64, false, 8>(pl);
         case 128: return plan_first<128, false, 8>(pl);
-        case 192: return pl->epi_warps == 12 ? plan_first<192, false, 12>(pl) : (pl->epi_warps == 16 ? plan_first<192, false, 16>(pl) : plan_first<192, false, 8>(pl));
+        case 192: return pl->epi_warps == 12 ? plan_first<192, false, 12>(pl) : plan_first<192, false, 8>(pl);
       }
       break;
     case PK_FIRST_U8:
       switch (pl->np) {
         case 64: return plan_first<64, true, 8>(pl);
         case 128: return plan_first<128, true, 8>(pl);
-        case 192: return pl->epi_warps == 12 ? plan_first<192, true, 12>(pl) : (pl->epi_warps == 16 ? plan_first<192, true, 16>(pl) : plan_first<192, true, 8>(pl));
+        case 192: return pl->epi_warps == 12 ? plan_first<192, true, 12>(pl) : plan_first<192, true, 8>(pl);
       }
       break;
   }
@@ -2182,7 +2183,6 @@ int launch_plan(const Plan& pl, cudaStream_t st) {
         case 128: if (u8) LDIC_LAUNCH_FIRST(128, true, 8); else LDIC_LAUNCH_FIRST(128, false, 8); break;
         case 192:
           if (pl.epi_warps == 12) { if (u8) LDIC_LAUNCH_FIRST(192, true, 12); else LDIC_LAUNCH_FIRST(192, false, 12); }
-          else if (pl.epi_warps == 16) { if (u8) LDIC_LAUNCH_FIRST(192, true, 16); else LDIC_LAUNCH_FIRST(192, false, 16); }
           else { if (u8) LDIC_LAUNCH_FIRST(192, true, 8); else LDIC_LAUNCH_FIRST(192, false, 8); }
           break;
 #undef LDIC_LAUNCH_FIRST
@@ -2302,7 +2302,7 @@ int build_plan_first(const LdicConvDesc* d, const Layer& L, const void* x, const
   }
   pl->kernel = u8 ? PK_FIRST_U8 : PK_FIRST;
   pl->np = L.Np;
-  pl->epi_warps = L.Np != 192 ? 8 : (tuning().first_epi == 8 ? 8 : (tuning().first_epi == 16 ? 16 : 12));
+  pl->epi_warps = (L.Np == 192 && tuning().first_epi != 8) ? 12 : 8;
   if ((rc = finish_plan(pl))) return rc;
   apply_sm_limit(d, pl);
   return LDIC_OK;

@@ -191,6 +191,7 @@ class Net(nn.Module):
         # runs on a side stream on `side_sms` SMs while the first three g_s deconvs, which depend on round(y) only,
         # run on the remaining SMs of the main stream (persistent kernels with their grids capped accordingly).
         self.side_sms = 12                # SMs of the side stream; 0: single stream (same-box interleaved A/B: 3.31 -> 3.19 ms per step)
+        self.side_eager = False           # also partition when launching eagerly (tests)
         self._side_streams = {}
         # forward(x, 'test'): transparent CUDA-graph capture / replay per input shape (see forward)
         self.auto_graph = True
@@ -266,7 +267,11 @@ class Net(nn.Module):
         y = self.a_model.forward_nhwc(x)                                            # :627   (B,h,w,N) fp32 NHWC
         y_round_bf16, y_abs_bf16, _ = ops.latent_prep(y)                            # :197 abs, :741 round
         fused_ok = self.tail_fused and self.s_model.has_fused_tail()
-        split = self.side_sms > 0 and fused_ok and not overrides
+        # the SM partition pays off where launches cost no host time, i.e. inside a graph capture (forward() and
+        # GraphedEvaluator replay graphs); issued eagerly, the fork / join and the side stream's allocator pool cost more
+        # host time than the overlap returns (4.3 vs 2.9 ms per step from Python), unless `side_eager` asks for it
+        split = (self.side_sms > 0 and fused_ok and not overrides
+                 and (self.side_eager or torch.cuda.is_current_stream_capturing()))
         bits = torch.empty(3, dtype=torch.float32, device=dev)                      # sum(ln L) of z, y, syntax
         lik_z = None
 
