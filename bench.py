@@ -679,17 +679,30 @@ def run_unet(args):
     spans = {"WinBasedAttention": [], "Win_noShift_Attention": []}
     hooks = []
     for mod in net.modules():
-        tag = "WinBasedAttention" if isinstance(mod, WinBasedAttention) else ("Win_noShift_Attention" if isinstance(mod, net_unet.Win_noShift_Attention) else None)
-        if tag:
-            def pre(m, i, tag=tag):
+        if isinstance(mod, net_unet.Win_noShift_Attention):
+            def pre(m, i):
                 e = torch.cuda.Event(enable_timing=True); e.record(); m._e0 = e
-            def post(m, i, o, tag=tag):
-                e = torch.cuda.Event(enable_timing=True); e.record(); spans[tag].append((m._e0, e))
+            def post(m, i, o):
+                e = torch.cuda.Event(enable_timing=True); e.record(); spans["Win_noShift_Attention"].append((m._e0, e))
             hooks += [mod.register_forward_pre_hook(pre), mod.register_forward_hook(post)]
-    e0.record()
-    step(devbuf[0])
-    e1.record()
-    torch.cuda.synchronize(dev)
+    # the attention blocks are entered through forward() (NCHW surface) or forward_nhwc() (inside the NHWC pipeline)
+    orig = (WinBasedAttention.forward, WinBasedAttention.forward_nhwc)
+
+    def timed(fn):
+        def f(self, t):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(); r_ = fn(self, t); eb.record()
+            spans["WinBasedAttention"].append((ea, eb))
+            return r_
+        return f
+    WinBasedAttention.forward, WinBasedAttention.forward_nhwc = timed(orig[0]), timed(orig[1])
+    try:
+        e0.record()
+        step(devbuf[0])
+        e1.record()
+        torch.cuda.synchronize(dev)
+    finally:
+        WinBasedAttention.forward, WinBasedAttention.forward_nhwc = orig
     hooked_ms = e0.elapsed_time(e1)
     share = {k: sum(a.elapsed_time(b) for a, b in v) / hooked_ms for k, v in spans.items()}
     for h in hooks:

@@ -190,7 +190,8 @@ enum {
    * 1 byte per sample instead of 4.  W % 16 == 0.                                                  */
   LDIC_CONV_FIRST_5x5S2 = 12
 };
-enum { LDIC_ACT_NONE = 0, LDIC_ACT_RELU = 1, LDIC_ACT_LEAKY02 = 2, LDIC_ACT_GDN = 3, LDIC_ACT_IGDN = 4 };
+enum { LDIC_ACT_NONE = 0, LDIC_ACT_RELU = 1, LDIC_ACT_LEAKY02 = 2, LDIC_ACT_GDN = 3, LDIC_ACT_IGDN = 4,
+       LDIC_ACT_LEAKY001 = 5 /* nn.LeakyReLU() default slope 0.01: CompressAI ResidualBlock, layers/layers.py:87-102 */ };
 
 typedef struct {
   int kind;           /* LDIC_CONV_* */
@@ -224,6 +225,11 @@ LDIC_API void ldic_conv_out_shape(const LdicConvDesc* d, int* Ho, int* Wo);
  * (gamma_bf16 / beta_tiled from ldic_gdn_prepare).                              */
 LDIC_API int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                       const void* gamma_bf16, const float* beta_tiled, void* y, void* stream);
+/* y = act(conv(x) + bias) + r: the residual connection of a ResidualBlock (CompressAI, used by layers/layers.py:87-102) or of
+ * WinBasedAttention (layers/win_attention.py:204-205) fused into the epilogue.  r is an NHWC bf16 tensor of y's shape; plain
+ * layers only (no GDN, one job, at most 192 output channels).                                                        */
+LDIC_API int ldic_conv_forward_residual(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                               const void* residual_bf16, void* y, void* stream);
 /* Launch plans (tile / tap tables, TMA descriptors, kernel variant, grid) are cached per (descriptor, parameter
  * tensors, device); the activation addresses of a call are patched into a copy of the cached plan, so a repeated
  * call is a lookup, one cuTensorMapReplaceAddress and one kernel launch.                                      */
@@ -311,6 +317,11 @@ LDIC_API int ldic_window_attention_core_table(const void* q, const void* k, cons
                                      int H, int W, int C, int heads, int ws, int shift, void* stream);
 LDIC_API int ldic_residual_nhwc_to_nchw_f32(const float* o_nhwc, const float* shortcut_nchw, float* y_nchw, int B, int C,
                                    int H, int W, int Cp, void* stream);
+
+/* y (NCHW fp32) = x (NCHW fp32) + a * sigmoid(b) with a, b NHWC bf16 [B,H,W,Cp]: the gate and residual that close
+ * Win_noShift_Attention (layers/layers.py:104-111), fused with the return to the module surface's layout.         */
+LDIC_API int ldic_gate_residual_nhwc_to_nchw_f32(const void* a_nhwc_bf16, const void* b_nhwc_bf16, const float* x_nchw, float* y_nchw,
+                                        int B, int C, int H, int W, int Cp, void* stream);
 
 /* Diagnostics: every in-kernel barrier wait of the conv kernels is bounded; a starved wait records
  * {flag, block, thread, barrier byte offset in dynamic shared memory, parity} in host-mapped memory and

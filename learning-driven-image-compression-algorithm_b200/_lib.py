@@ -25,7 +25,7 @@ LDIC_CTX_CONV2 = 9
 LDIC_CTX_CONV3 = 10
 LDIC_CTX_FC = 11
 LDIC_CONV_FIRST_5x5S2 = 12
-ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_GDN, ACT_IGDN = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_GDN, ACT_IGDN, ACT_LEAKY001 = 0, 1, 2, 3, 4, 5
 LDIC_EINVAL_RC = -1
 
 
@@ -109,6 +109,8 @@ _SIGS = {
     "ldic_conv_out_shape": (None, [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ldic_conv_forward": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "ldic_conv_forward_residual": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
     "ldic_syntax_workspace_elems": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ldic_syntax_branch": (C.c_int, [C.POINTER(SyntaxArgs), C.c_void_p]),
     "ldic_tritplane_workspace_bytes": (C.c_size_t, []),
@@ -121,6 +123,8 @@ _SIGS = {
                                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldic_residual_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_int, C.c_void_p]),
+    "ldic_gate_residual_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                     C.c_int, C.c_int, C.c_void_p]),
     "ldic_debug_last_timeout": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "ldic_conv_forward_fused_tail": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.POINTER(ConvTail), C.c_void_p]),

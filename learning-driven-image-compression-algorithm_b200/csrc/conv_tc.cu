@@ -89,6 +89,7 @@ struct ConvParams {
   const float* beta;
   void* out;
   unsigned long long* dbg;   // optional cycle counters of CTA 0 (LDIC_DEBUG_TIMING=1), else null
+  const __nv_bfloat16* residual;   // optional NHWC bf16 tensor of the output's shape added after the activation (no GDN)
   int dbg_nostore;           // experiment: skip the epilogue's global stores (LDIC_DEBUG_NOSTORE=1)
   // fused tail of Net.forward on the merged last deconv: per-image 1x1 conv (batch_conv) + 8-bit-level squared error
   const void* tail_x;        // NCHW input image [B,3,tail_H,tail_W] (fp32 in [-1,1], or uint8 levels when tail_u8), or null
@@ -449,7 +450,7 @@ __device__ __forceinline__ unsigned long long fused_tail_pixels(const ConvParams
 
 // EW = number of epilogue warps (EW / 4 per TMEM lane quadrant, NP / (EW / 4) accumulator columns per thread): 8 in the
 // streaming kernels; the first layer, which IS its epilogue (5 conv MMAs per tile), runs 12 at NP = 192.
-template <int NP, bool CL = false, int EW = kEpiWarps>
+template <int NP, bool CL = false, int EW = kEpiWarps, bool RES = false>
 __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing& R, uint32_t tmem_base, int gk,
                                               int ntiles_cta, int warp, int lane) {
   static_assert(EW % 4 == 0 && NP % (EW / 4) == 0 && (NP / (EW / 4)) % 16 == 0, "epilogue warps must split the columns in 16s");
@@ -631,9 +632,29 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       } else if (P.act == LDIC_ACT_RELU) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) xr[c] = fmaxf(xr[c], 0.f);
-      } else if (P.act == LDIC_ACT_LEAKY02) {
+      } else if (P.act == LDIC_ACT_LEAKY02 || P.act == LDIC_ACT_LEAKY001) {
+        const float slope = P.act == LDIC_ACT_LEAKY02 ? 0.2f : 0.01f;
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) xr[c] = xr[c] > 0.f ? xr[c] : 0.2f * xr[c];
+        for (int c = 0; c < CPT; ++c) xr[c] = xr[c] > 0.f ? xr[c] : slope * xr[c];
+      }
+      if constexpr (RES) {
+        // residual connection fused in: out = act(conv(x) + bias) + r, r an NHWC bf16 tensor of the output's shape
+        // (ResidualBlock: layers/layers.py:87-102 via CompressAI; WinBasedAttention: layers/win_attention.py:204-205)
+        if (valid && P.residual) {
+          const __nv_bfloat16* rp = P.residual + pix_base + col0;
+#pragma unroll
+          for (int c = 0; c < CPT; c += 16) {
+            uint32_t u[8];
+            asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                         : "l"(rp + c));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              xr[c + 2 * e] += __uint_as_float(u[e] << 16);
+              xr[c + 2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u);
+            }
+          }
+        }
       }
 
       unsigned long long tail_acc = 0;       // fused tail: this thread's squared level error on this tile
@@ -870,7 +891,7 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
 // ---------------------------------------------------------------------------------
 // W3 = true: wide-N form of the merged last deconv (see epilogue_w3): NP = 3 * NPO accumulator columns, bias / beta /
 // gamma refer to the NPO logical columns and the gamma contraction is an N = NPO MMA.
-template <int NP, bool W3 = false>
+template <int NP, bool W3 = false, bool RES = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
@@ -1075,7 +1096,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     R.t_first = pi; R.t_stride = npairs; R.rank = (int)rank;
     R.buf_free_cl = mapa_shared(smem_u32(buf_free), 0); R.x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0);
     if constexpr (W3) epilogue_w3<NP>(P, R, tmem_base, gk, nt, warp, lane);
-    else epilogue_role<NP, true>(P, R, tmem_base, gk, nt, warp, lane);
+    else epilogue_role<NP, true, kEpiWarps, RES>(P, R, tmem_base, gk, nt, warp, lane);
   }
 
   tc_fence_before();
@@ -1457,6 +1478,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float x = __uint_as_float(xu[k]) + sb[col + k];
             if (P.act == LDIC_ACT_RELU) x = fmaxf(x, 0.f);
             else if (P.act == LDIC_ACT_LEAKY02) x = x > 0.f ? x : 0.2f * x;
+            else if (P.act == LDIC_ACT_LEAKY001) x = x > 0.f ? x : 0.01f * x;
             v[k] = x;
           }
           store32(v, col);
@@ -2048,7 +2070,7 @@ void choose_tile(int Wg, int Hg, int B, int* TW, int* TH, int* TN) {
 // in a small cache, so a repeated eager call costs a hash lookup and one cudaLaunchKernelEx (no getenv, no
 // cuTensorMapEncodeTiled, no table construction on the hot path).
 // ---------------------------------------------------------------------------------
-enum PlanKernel { PK_PAIR = 0, PK_W3 = 1, PK_WIDE = 2, PK_FIRST = 3, PK_FIRST_U8 = 4 };
+enum PlanKernel { PK_PAIR = 0, PK_W3 = 1, PK_WIDE = 2, PK_FIRST = 3, PK_FIRST_U8 = 4, PK_PAIR_RES = 5 };
 struct Plan {
   ConvParams P;
   CUtensorMap a, w, g;
@@ -2101,11 +2123,11 @@ int launch_cluster2(K kern, const char* name, const Plan& pl, cudaStream_t st) {
   return check_launch(name);
 }
 
-template <int NP, bool W3>
+template <int NP, bool W3, bool RES = false>
 int plan_pair(Plan* pl) {
   static KernelState ks;
   int mc = 0;
-  int rc = prepare_kernel(conv_tc2_kernel<NP, W3>, ks, true, &mc);
+  int rc = prepare_kernel(conv_tc2_kernel<NP, W3, RES>, ks, true, &mc);
   if (rc) return rc;
   const int total_super = pl->P.super_per_job * pl->P.njobs;
   pl->grid = 2 * (total_super < mc ? total_super : mc);
@@ -2141,6 +2163,13 @@ int finish_plan(Plan* pl) {
         case 256: return plan_pair<256, false>(pl);
       }
       break;
+    case PK_PAIR_RES:
+      switch (pl->np) {
+        case 64: return plan_pair<64, false, true>(pl);
+        case 128: return plan_pair<128, false, true>(pl);
+        case 192: return plan_pair<192, false, true>(pl);
+      }
+      break;
     case PK_W3: return plan_pair<192, true>(pl);
     case PK_WIDE: return plan_wide<384>(pl);
     case PK_FIRST:
@@ -2169,6 +2198,13 @@ int launch_plan(const Plan& pl, cudaStream_t st) {
         case 128: return launch_cluster2(conv_tc2_kernel<128, false>, "conv_tc2_kernel", pl, st);
         case 192: return launch_cluster2(conv_tc2_kernel<192, false>, "conv_tc2_kernel", pl, st);
         case 256: return launch_cluster2(conv_tc2_kernel<256, false>, "conv_tc2_kernel", pl, st);
+      }
+      break;
+    case PK_PAIR_RES:
+      switch (pl.np) {
+        case 64: return launch_cluster2(conv_tc2_kernel<64, false, true>, "conv_tc2_kernel(+residual)", pl, st);
+        case 128: return launch_cluster2(conv_tc2_kernel<128, false, true>, "conv_tc2_kernel(+residual)", pl, st);
+        case 192: return launch_cluster2(conv_tc2_kernel<192, false, true>, "conv_tc2_kernel(+residual)", pl, st);
       }
       break;
     case PK_W3: return launch_cluster2(conv_tc2_kernel<192, true>, "conv_tc2_kernel(wide tail)", pl, st);
@@ -2309,7 +2345,8 @@ int build_plan_first(const LdicConvDesc* d, const Layer& L, const void* x, const
 }
 
 int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
-               const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, Plan* pl) {
+               const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, Plan* pl,
+               const void* residual = nullptr) {
   Layer L;
   int rc = build_layer(d, &L);
   if (rc) return rc;
@@ -2431,6 +2468,12 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
     pl->g = pl->w;
   }
   pl->kernel = wide ? PK_WIDE : (wide3 ? PK_W3 : PK_PAIR);
+  if (residual) {
+    if (gdn || wide || wide3 || L.ngroups != 1 || L.njobs != 1 || L.Np > 192 || tail || (((uintptr_t)residual) & 31))
+      return fail(LDIC_EINVAL, "conv: the fused residual needs a plain (no GDN, one job) layer of at most 192 output channels and a 32-byte aligned residual");
+    pl->kernel = PK_PAIR_RES;
+    P.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  }
   pl->np = L.Np;
   if ((rc = finish_plan(pl))) return rc;
   apply_sm_limit(d, pl);
@@ -2445,7 +2488,7 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
 struct PlanKey {
   LdicConvDesc d;
   const void *w, *bias, *gamma, *beta;
-  int has_tail, tail_H, tail_W, tail_u8, tail_tanh, has_y, device;
+  int has_tail, tail_H, tail_W, tail_u8, tail_tanh, has_y, has_res, device;
   unsigned epoch;
   bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
 };
@@ -2544,12 +2587,19 @@ extern "C" int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, con
 
 namespace {
 int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
-                      const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, void* stream);
+                      const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, void* stream,
+                      const void* residual = nullptr);
 }
 extern "C" int ldic_conv_forward(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                                  const void* gamma_bf16, const float* beta_tiled, void* y, void* stream) {
   if (!y) return fail(LDIC_EINVAL, "conv: null output tensor");
   return conv_forward_impl(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, nullptr, stream);
+}
+extern "C" int ldic_conv_forward_residual(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
+                                          const void* residual_bf16, void* y, void* stream) {
+  if (!y || !residual_bf16) return fail(LDIC_EINVAL, "conv: null output / residual tensor");
+  if (d && (d->act == LDIC_ACT_GDN || d->act == LDIC_ACT_IGDN)) return fail(LDIC_EINVAL, "conv: the fused residual excludes the GDN epilogue");
+  return conv_forward_impl(d, x, w_packed, bias_packed, nullptr, nullptr, y, nullptr, stream, residual_bf16);
 }
 extern "C" int ldic_conv_forward_fused_tail(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
                                             const void* gamma_bf16, const float* beta_tiled, void* y_or_null,
@@ -2572,7 +2622,8 @@ void print_debug_timing(const Plan& pl, cudaStream_t st) {     // debugging aid 
 }
 
 int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed, const float* bias_packed,
-                      const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, void* stream) {
+                      const void* gamma_bf16, const float* beta_tiled, void* y, const LdicConvTail* tail, void* stream,
+                      const void* residual) {
   if (!d) return fail(LDIC_EINVAL, "conv: null desc");
   if (d->B == 0) { Layer L; return build_layer(d, &L); }
   if (!x || !w_packed || (!y && !tail)) return fail(LDIC_EINVAL, "conv: null tensor");
@@ -2585,6 +2636,7 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
   key.d = *d; key.w = w_packed; key.bias = bias_packed; key.gamma = gamma_bf16; key.beta = beta_tiled;
   if (tail) { key.has_tail = 1; key.tail_H = tail->H; key.tail_W = tail->W; key.tail_u8 = tail->x_is_u8; key.tail_tanh = tail->tanh_out; }
   key.has_y = y != nullptr;
+  key.has_res = residual != nullptr;
   key.device = current_device(); key.epoch = tn.epoch;
   std::shared_ptr<Plan> pl;
   {
@@ -2598,6 +2650,7 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
     Plan p = *pl;                                   // per-call copy: this call's activation addresses
     if (repl(&p.a, const_cast<void*>(x)) != CUDA_SUCCESS) return fail(LDIC_ECUDA, "conv: cuTensorMapReplaceAddress failed");
     p.P.out = y;
+    p.P.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     if (tail) { p.P.tail_x = tail->x_nchw; p.P.tail_w = tail->w; p.P.tail_xo = tail->x_tilde_nchw; p.P.tail_sq = tail->sq_err; }
     if (p.P.dbg) cudaMemsetAsync(p.P.dbg, 0, 32 * sizeof(unsigned long long), st);
     rc = launch_plan(p, st);
@@ -2605,7 +2658,7 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
     return rc;
   }
   pl = std::make_shared<Plan>();
-  if ((rc = build_plan(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, tail, pl.get()))) return rc;
+  if ((rc = build_plan(d, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, tail, pl.get(), residual))) return rc;
   if (tn.debug_timing) {
     unsigned long long* buf = nullptr;
     if (cudaMalloc(&buf, 32 * sizeof(unsigned long long)) == cudaSuccess) pl->P.dbg = buf;   // lives as long as the plan cache

@@ -283,6 +283,38 @@ __global__ void __launch_bounds__(256) k_residual_nhwc_to_nchw(const float* __re
 }
 
 
+// y (NCHW fp32) = x (NCHW fp32) + a * sigmoid(b), a / b NHWC bf16: the gate + residual that closes Win_noShift_Attention
+// (layers/layers.py:104-111) fused with the way back to the module surface's layout.
+__global__ void __launch_bounds__(256) k_gate_residual_nhwc_to_nchw(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                                    const float* __restrict__ x, float* __restrict__ y, int C,
+                                                                    long long HW, int Cp) {
+  __shared__ float t[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const long long p = p0 + r;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < Cp) {
+      const long long i = ((long long)n * HW + p) * Cp + c;
+      const float av = __bfloat162float(a[i]), bv = __bfloat162float(b[i]);
+      v = av / (1.f + __expf(-bv));
+    }
+    t[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const long long p = p0 + tx;
+    if (c < C && p < HW) {
+      const long long i = ((long long)n * C + c) * HW + p;
+      y[i] = x[i] + t[tx][r];
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int ldic_window_attention_bias(const float* table, const long long* index, float* bias, int heads, int ws, void* stream) {
@@ -328,4 +360,16 @@ extern "C" int ldic_residual_nhwc_to_nchw_f32(const float* o_nhwc, const float* 
   dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, B);
   k_residual_nhwc_to_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>(o_nhwc, shortcut_nchw, y_nchw, C, HW, Cp);
   return check_launch("k_residual_nhwc_to_nchw");
+}
+
+extern "C" int ldic_gate_residual_nhwc_to_nchw_f32(const void* a_nhwc_bf16, const void* b_nhwc_bf16, const float* x_nchw, float* y_nchw,
+                                                   int B, int C, int H, int W, int Cp, void* stream) {
+  if (!a_nhwc_bf16 || !b_nhwc_bf16 || !x_nchw || !y_nchw) return fail(LDIC_EINVAL, "gate: null tensor");
+  if (B <= 0 || H <= 0 || W <= 0) return LDIC_OK;
+  if (Cp < C) return fail(LDIC_EINVAL, "gate: Cp < C");
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, B);
+  k_gate_residual_nhwc_to_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a_nhwc_bf16, (const __nv_bfloat16*)b_nhwc_bf16,
+                                                                       x_nchw, y_nchw, C, HW, Cp);
+  return check_launch("k_gate_residual_nhwc_to_nchw");
 }

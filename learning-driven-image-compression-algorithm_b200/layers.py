@@ -223,6 +223,15 @@ class WindowAttention(nn.Module):
             self._key = key
         return self._packed
 
+    def packed_proj_bf16(self):
+        """The proj Linear as a conv layer with bf16 output (NHWC pipelines that keep the residual stream in bf16)."""
+        key = (self.proj.weight._version, self.proj.weight.data_ptr(), self.proj.bias._version)
+        if getattr(self, "_pkey16", None) != key:
+            self._p16 = ops.ConvTC(_lib.LDIC_CONV_1x1, self.proj.weight.detach().float().contiguous(),
+                                   self.proj.bias.detach().float().contiguous(), out_f32=False)
+            self._pkey16 = key
+        return self._p16
+
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C) window tokens as in the reference; mask must be None here (the shifted-window
         mask is derived inside the kernel when called through WinBasedAttention)."""
@@ -246,6 +255,16 @@ def _window_block(attn: "WindowAttention", x: torch.Tensor, ws: int, shift: int,
     if residual:
         return ops.residual_nhwc_to_nchw(o, x)
     return ops.nhwc_to_nchw_f32(o, Cd)
+
+
+def _window_block_nhwc(attn: "WindowAttention", t: torch.Tensor, ws: int, shift: int) -> torch.Tensor:
+    """NHWC bf16 in, NHWC bf16 out, x + (S)W-MSA(x) with the residual added in the proj conv's epilogue."""
+    q, k, v, pr, bias = attn.packed()
+    if t.shape[-1] != q.cin_pad:
+        raise ops.LdicError("window attention: dim must be a multiple of 64")
+    o = ops.window_attention_core(q(t), k(t), v(t), bias, attn.num_heads, ws, shift)
+    prb = attn.packed_proj_bf16()
+    return prb(o, residual=t)
 
 
 class WinBasedAttention(nn.Module):
@@ -310,6 +329,10 @@ class WinBasedAttention(nn.Module):
         if sh > 0:
             o = torch.roll(o, shifts=(sh, sh), dims=(1, 2))
         return x + o.permute(0, 3, 1, 2)
+
+    def forward_nhwc(self, t):
+        """(B,H,W,C) bf16 NHWC -> same: the block inside an NHWC bf16 pipeline (Win_noShift_Attention on the kernels)."""
+        return _window_block_nhwc(self.attn, t, self.window_size, self.shift_size)
 
     def forward(self, x):
         if not self.kernel_shape():

@@ -40,6 +40,21 @@ from .net import PredictionModel_Context, _DISCARDED_PREFIXES, conv_generator
 from .transforms import _PlannedTransform
 
 
+# The 3x3 / 1x1 convolutions of ResidualBlock, ResidualBlockWithStride and Win_noShift_Attention (13 + 1 per attention
+# module at dim 192: 70 % of the family's FLOPs) run on the tcgen05 conv kernel (bf16 operands, fp32 accumulation, the
+# LeakyReLU / GDN in the epilogue) when the channel count is a multiple of 64.  False: stock torch convs (cuDNN), which
+# the tests use as the cross-check of the kernel path.
+KERNEL_CONVS = True
+
+
+def _versions(*mods):
+    return tuple((p._version, p.data_ptr()) for m in mods for p in m.parameters())
+
+
+def _kernel_ok(x, *channels):
+    return KERNEL_CONVS and x.is_cuda and all(c % 64 == 0 for c in channels)
+
+
 def conv1x1(i, o, stride=1):
     return nn.Conv2d(i, o, kernel_size=1, stride=stride)
 
@@ -83,7 +98,26 @@ class ResidualBlock(nn.Module):
         self.conv2 = conv3x3(out_ch, out_ch)
         self.skip = conv1x1(in_ch, out_ch) if in_ch != out_ch else None
 
+    _plan = _plan_key = None
+
+    def _ldic(self):
+        key = _versions(self.conv1, self.conv2)
+        if self._plan is None or self._plan_key != key:
+            mk = lambda c, f32: ops.ConvTC(_lib.LDIC_CONV_S1_3x3_P1, c.weight.detach(), c.bias.detach(),
+                                           act=_lib.ACT_LEAKY001, out_f32=f32)
+            self._plan, self._plan_key = (mk(self.conv1, False), mk(self.conv2, True), mk(self.conv2, False)), key
+        return self._plan
+
+    def forward_nhwc(self, t):
+        """NHWC bf16 -> NHWC bf16; the residual is added in conv2's epilogue (fp32, before the bf16 rounding)."""
+        c1, c2, c2b = self._ldic()
+        return c2b(c1(t), residual=t)
+
     def forward(self, x):
+        if self.skip is None and _kernel_ok(x, self.conv1.in_channels, self.conv1.out_channels):
+            c1, c2, _ = self._ldic()
+            o = c2(c1(ops.nchw_to_nhwc_bf16(x, c1.cin_pad)))                 # NHWC fp32
+            return ops.residual_nhwc_to_nchw(o, x)                           # + identity, back to NCHW
         out = self.leaky_relu(self.conv2(self.leaky_relu(self.conv1(x))))
         return out + (x if self.skip is None else self.skip(x))
 
@@ -100,9 +134,22 @@ class ResidualBlockWithStride(nn.Module):
         self.gdn = CAGDN(out_ch)
         self.skip = conv1x1(in_ch, out_ch, stride=stride) if (stride != 1 or in_ch != out_ch) else None
 
+    _plan = _plan_key = None
+
     def forward(self, x):
-        out = self.gdn(self.conv2(self.leaky_relu(self.conv1(x))))
-        return out + (x if self.skip is None else self.skip(x))
+        h = self.leaky_relu(self.conv1(x))
+        identity = x if self.skip is None else self.skip(x)
+        if _kernel_ok(x, self.conv2.in_channels, self.conv2.out_channels):
+            # conv2 + GDN in one tensor-core kernel (the GDN as the epilogue's gamma contraction)
+            key = _versions(self.conv2, self.gdn)
+            if self._plan is None or self._plan_key != key:
+                g = self.gdn
+                self._plan = ops.ConvTC(_lib.LDIC_CONV_S1_3x3_P1, self.conv2.weight.detach(), self.conv2.bias.detach(),
+                                        act=_lib.ACT_GDN, out_f32=True, gdn=(g.beta.detach(), g.gamma.detach()) + g.constants())
+                self._plan_key = key
+            o = self._plan(ops.nchw_to_nhwc_bf16(h, self._plan.cin_pad))
+            return ops.residual_nhwc_to_nchw(o, identity)
+        return self.gdn(self.conv2(h)) + identity
 
 
 class _ResidualUnit(nn.Module):
@@ -129,8 +176,38 @@ class Win_noShift_Attention(nn.Module):
         self.conv_b = nn.Sequential(wa(), conv1x1(N, N), wa(), ResidualBlock(N, N), conv3x3(N, N), wa(), ResidualBlock(N, N),
                                     conv7x7(N, N), wa(), ResidualBlock(N, N))
 
+    _plan = _plan_key = None
+
+    def _singles(self):
+        """conv_b[1] / conv_b[4] (a lone 1x1 / 3x3 conv, no activation) as kernel layers with bf16 output."""
+        key = _versions(self.conv_b[1], self.conv_b[4])
+        if self._plan is None or self._plan_key != key:
+            mk = lambda c, k: ops.ConvTC(k, c.weight.detach(), c.bias.detach(), out_f32=False)
+            self._plan = {1: mk(self.conv_b[1], _lib.LDIC_CONV_1x1), 4: mk(self.conv_b[4], _lib.LDIC_CONV_S1_3x3_P1)}
+            self._plan_key = key
+        return self._plan
+
     def forward(self, x):
-        return self.conv_a(x) * torch.sigmoid(self.conv_b(x)) + x
+        C = x.shape[1]
+        if not (_kernel_ok(x, C) and all(m.kernel_shape() for m in self.conv_b if isinstance(m, WinBasedAttention))):
+            return self.conv_a(x) * torch.sigmoid(self.conv_b(x)) + x
+        # Kernel path: the whole module runs on NHWC bf16 tensors -- one layout change in, one (fused with the gate and
+        # the outer residual) out; every inner residual is added in a conv epilogue.  Only the 7x7 conv goes through
+        # cuDNN (its 49 taps exceed the tap table of the conv kernel's producer warps).
+        xb = ops.nchw_to_nhwc_bf16(x, C)
+        a = xb
+        for rb in self.conv_a:
+            a = rb.forward_nhwc(a)
+        singles = self._singles()
+        b = xb
+        for i, m in enumerate(self.conv_b):
+            if i in singles:
+                b = singles[i](b)
+            elif isinstance(m, (WinBasedAttention, ResidualBlock)):
+                b = m.forward_nhwc(b)
+            else:                               # conv7x7
+                b = ops.nchw_to_nhwc_bf16(m(ops.nhwc_to_nchw_f32(b, C)), C)
+        return ops.gate_residual_nhwc_to_nchw(a, b, x)
 
 
 class WMSA(nn.Module):
@@ -430,16 +507,34 @@ class analysisTransformModel(_PlannedTransform):
 
     def _build_plan(self):
         t = self.transform
+        dev = t[6].weight.device
+
+        def gdn_only(g):
+            """A stand-alone GDN as a 1x1 conv with the identity matrix + the fused GDN epilogue: the channel contraction
+            runs on the tensor cores and the result leaves as the NHWC bf16 tensor the next conv reads (the fp32
+            CUDA-core kernel behind ModelGDN.forward costs ~4 ms per call at 1/2 resolution and batch 16)."""
+            C = g.beta.numel()
+            return ops.ConvTC(_lib.LDIC_CONV_1x1, torch.eye(C, device=dev), torch.zeros(C, device=dev), act=_lib.ACT_GDN,
+                              out_f32=False, gdn=self._gdn_args(g))
         return [ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P12, t[6].weight.detach(), t[6].bias.detach(), act=_lib.ACT_GDN,
                            out_f32=True, gdn=self._gdn_args(t[7])),
-                ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P12, t[15].weight.detach(), t[15].bias.detach(), out_f32=True)]
+                ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P12, t[15].weight.detach(), t[15].bias.detach(), out_f32=True),
+                gdn_only(t[4]), gdn_only(t[13])]
 
     def forward(self, x):
         t, L = self.transform, self.plan()
-        x = t[4](t[3](t[2](t[1](t[0](x)))))
-        x = ops.nhwc_to_nchw_f32(L[0](ops.nchw_to_nhwc_bf16(x, L[0].cin_pad)), t[6].out_channels)     # 5 + 6 + 7
-        x = t[13](t[12](t[11](t[10](t[9](t[8](x))))))
-        x = ops.nhwc_to_nchw_f32(L[1](ops.nchw_to_nhwc_bf16(x, L[1].cin_pad)), t[15].out_channels)    # 14 + 15
+        x = t[3](t[2](t[1](t[0](x))))
+        if _kernel_ok(x, x.shape[1]):
+            g = L[2](ops.nchw_to_nhwc_bf16(x, L[2].cin_pad))                                         # 4 (GDN) -> NHWC bf16
+        else:
+            g = ops.nchw_to_nhwc_bf16(t[4](x), L[0].cin_pad)
+        x = ops.nhwc_to_nchw_f32(L[0](g), t[6].out_channels)                                         # 5 + 6 + 7
+        x = t[12](t[11](t[10](t[9](t[8](x)))))
+        if _kernel_ok(x, x.shape[1]):
+            g = L[3](ops.nchw_to_nhwc_bf16(x, L[3].cin_pad))                                         # 13 (GDN)
+        else:
+            g = ops.nchw_to_nhwc_bf16(t[13](x), L[1].cin_pad)
+        x = ops.nhwc_to_nchw_f32(L[1](g), t[15].out_channels)                                        # 14 + 15
         return t[16](x)
 
 

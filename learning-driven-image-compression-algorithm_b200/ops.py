@@ -499,7 +499,8 @@ class ConvTC:
             prof.append((self, (B, H, W), e0, e1))
         return sq, xo, out
 
-    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, sm_limit: int = 0) -> torch.Tensor:
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, sm_limit: int = 0,
+                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         u8 = False
         if self.kind == _lib.LDIC_CONV_FIRST_5x5S2:
             u8 = x.dtype == torch.uint8          # 8-bit levels: the kernel applies x = (u/255)*2-1 itself (eval_net.py:84)
@@ -522,9 +523,16 @@ class ConvTC:
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(_L().ldic_conv_forward(C.byref(d), _ptr(x), _ptr(self.w_packed), _ptr(self.bias_packed),
-                                     _ptr(self.gamma_bf16), _ptr(self.beta_tiled), _ptr(out), _stream()),
-              "ldic_conv_forward")
+        if residual is not None:          # y = act(conv(x) + bias) + residual (NHWC bf16 of the output's shape)
+            _req(residual, torch.bfloat16, "residual")
+            if tuple(residual.shape) != tuple(out.shape) or not residual.is_contiguous():
+                raise LdicError("conv residual must be a contiguous NHWC bf16 tensor of the output's shape")
+            check(_L().ldic_conv_forward_residual(C.byref(d), _ptr(x), _ptr(self.w_packed), _ptr(self.bias_packed),
+                                                  _ptr(residual), _ptr(out), _stream()), "ldic_conv_forward_residual")
+        else:
+            check(_L().ldic_conv_forward(C.byref(d), _ptr(x), _ptr(self.w_packed), _ptr(self.bias_packed),
+                                         _ptr(self.gamma_bf16), _ptr(self.beta_tiled), _ptr(out), _stream()),
+                  "ldic_conv_forward")
         if prof is not None:
             e1.record()
             prof.append((self, (B, H, W), e0, e1))
@@ -580,6 +588,20 @@ def residual_nhwc_to_nchw(o_nhwc: torch.Tensor, shortcut_nchw: torch.Tensor) -> 
     y = torch.empty_like(sc)
     check(_L().ldic_residual_nhwc_to_nchw_f32(_ptr(o), _ptr(sc), _ptr(y), B, Cc, H, W, int(o.shape[3]), _stream()),
           "ldic_residual_nhwc_to_nchw_f32")
+    return y
+
+
+def gate_residual_nhwc_to_nchw(a_nhwc: torch.Tensor, b_nhwc: torch.Tensor, x_nchw: torch.Tensor) -> torch.Tensor:
+    """x (B,C,H,W) fp32 + a * sigmoid(b), a / b contiguous NHWC bf16 (B,H,W,Cp>=C) -> (B,C,H,W) fp32."""
+    _req(a_nhwc, torch.bfloat16, "a"); _req(b_nhwc, torch.bfloat16, "b")
+    x = _req(x_nchw, torch.float32, "x").contiguous()
+    B, Cc, H, W = x.shape
+    if a_nhwc.shape != b_nhwc.shape or not a_nhwc.is_contiguous() or not b_nhwc.is_contiguous() or \
+            tuple(a_nhwc.shape[:3]) != (B, H, W) or a_nhwc.shape[3] < Cc:
+        raise LdicError("gate_residual_nhwc_to_nchw: a, b must be contiguous (B,H,W,Cp>=C) bf16 tensors")
+    y = torch.empty_like(x)
+    check(_L().ldic_gate_residual_nhwc_to_nchw_f32(_ptr(a_nhwc), _ptr(b_nhwc), _ptr(x), _ptr(y), B, Cc, H, W,
+                                                   int(a_nhwc.shape[3]), _stream()), "ldic_gate_residual_nhwc_to_nchw_f32")
     return y
 
 

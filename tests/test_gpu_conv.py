@@ -246,3 +246,28 @@ def test_context_model_tc_vs_oracle(ldic):
     with torch.no_grad():
         mu_b, _ = rp.prediction_context(sdb, yr, h2)
     assert rel(mu.cpu(), mu_b) < 6e-3
+
+
+@pytest.mark.parametrize("C,act,f32", [(192, "leaky001", False), (64, "none", True), (128, "leaky001", False)])
+def test_conv_fused_residual(ldic, C, act, f32):
+    """ldic_conv_forward_residual: y = act(conv3x3(x) + b) + r, r NHWC bf16 (ResidualBlock of CompressAI as used by
+    layers/layers.py:87-102: conv -> LeakyReLU(0.01) -> + identity), against torch on the same bf16 operands."""
+    L = ldic._lib
+    x = bf(rnd((2, C, 20, 28), 51))
+    r = bf(rnd((2, C, 20, 28), 52))
+    w, b = rnd((C, C, 3, 3), 53, 0.03), rnd((C,), 54, 0.1)
+    ref = F.conv2d(x, bf(w), b, padding=1)
+    a = L.ACT_NONE
+    if act == "leaky001":
+        ref = F.leaky_relu(ref, 0.01)
+        a = L.ACT_LEAKY001
+    ref = ref + r
+    layer = ldic.ops.ConvTC(L.LDIC_CONV_S1_3x3_P1, w.cuda(), b.cuda(), act=a, out_f32=f32)
+    y = layer(to_nhwc_bf16(x), residual=to_nhwc_bf16(r))
+    assert y.dtype == (torch.float32 if f32 else torch.bfloat16)
+    if f32:
+        close(y.cpu().permute(0, 3, 1, 2), ref, 1e-4, 3e-4)
+    else:
+        close(y.float().cpu().permute(0, 3, 1, 2), ref, 1e-2, 4e-3)
+    y0 = layer(to_nhwc_bf16(x))                                  # the same layer without a residual still works
+    close(y0.float().cpu().permute(0, 3, 1, 2), ref - r, 1e-2, 4e-3)

@@ -120,3 +120,28 @@ def test_unet_synthesis_on_reference_symbols(name):
     assert r < 1e-2, r
     assert abs(psnr - d["v_psnr"].item()) < PSNR_ATOL_DB, (psnr, d["v_psnr"].item())
     assert torch.allclose(v_mse.float(), d["v_mse"], rtol=2e-3), (v_mse, d["v_mse"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,ws,shift,H,W", [(192, 8, 4, 32, 48), (192, 4, 2, 16, 24), (64, 4, 2, 8, 12)])
+def test_win_noshift_attention_kernel_convs_vs_torch_convs(dim, ws, shift, H, W):
+    """Win_noShift_Attention (layers/layers.py:56-111) with its ResidualBlock / 1x1 / 3x3 convs on the tcgen05 kernel
+    (bf16 operands) against the same module with stock fp32 torch convs: bf16-operand budget."""
+    import ldic_b200
+    from ldic_b200 import net_unet
+    torch.manual_seed(dim + ws)
+    blk = net_unet.Win_noShift_Attention(dim=dim, num_heads=8, window_size=ws, shift_size=shift).cuda().eval()
+    x = torch.randn(2, dim, H, W, device="cuda")
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            net_unet.KERNEL_CONVS = True
+            y_k = blk(x)
+            net_unet.KERNEL_CONVS = False
+            y_t = blk(x)
+    finally:
+        net_unet.KERNEL_CONVS = True
+        torch.backends.cudnn.allow_tf32 = prev
+    r = ((y_k - y_t).pow(2).mean().sqrt() / (y_t - x).pow(2).mean().sqrt()).item()      # relative to the block's own term
+    assert r < 2e-2, r
