@@ -85,6 +85,13 @@ __global__ void __launch_bounds__(256, 2) k_window_attention(WaParams P) {
     s_reg[threadIdx.x] = ry * 3 + rx;
   }
   __syncthreads();
+  // only the windows that straddle the wrap-around of the cyclic shift (the last window row / column) hold tokens of
+  // different regions: everywhere else the 0 / -100 mask is all zeros and its loads and compares are skipped
+  bool masked = false;
+  if (P.shift > 0) {
+    const int ra = s_reg[0];
+    masked = (s_reg[ws - 1] != ra) || (s_reg[N - ws] != ra) || (s_reg[N - 1] != ra);   // regions are monotone in i and j
+  }
   // ---- stage q | k | v rows with cp.async (16-byte chunks, a warp per token row): every copy of the window is in
   // flight at once and nothing passes through registers.  (A flat loop with index divisions and a load -> store
   // dependency per iteration spent 42 % of the kernel's samples on its shared-memory store.)
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(256, 2) k_window_attention(WaParams P) {
           b1 = __ldg(reinterpret_cast<const float2*>(bias_h + r1 * N + col));
         }
         float v0 = s[nt][0] + b0.x, v1 = s[nt][1] + b0.y, v2 = s[nt][2] + b1.x, v3 = s[nt][3] + b1.y;
-        if (P.shift > 0) {
+        if (masked) {
           const int rc0 = s_reg[col], rc1 = s_reg[col + 1];
           if (rc0 != reg0) v0 += -100.f;
           if (rc1 != reg0) v1 += -100.f;
