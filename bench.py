@@ -190,6 +190,8 @@ def run_ours(args):
     if args.side_sms >= 0:
         net.side_sms = args.side_sms
     net.auto_graph = not args.no_graph
+    if args.parity_tf32:
+        net.parity_tf32 = True          # g_a / h_a with kind::tf32 MMAs (SURVEY H4's precision comparison, ~half rate there)
     ev = ShardedEvaluator(net)
     NBUF = 4
     # 8-bit imagery: the host buffers hold uint8 levels; the first layer applies x = (u/255)*2-1 (eval_net.py:84) itself
@@ -405,7 +407,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": "bf16" if not args.parity_tf32 else "tf32 (g_a, h_a) + bf16", "data": "synthetic",
         "config": {"workload": f"model/net.py Net.forward(test) N={Nw} M={Mw} on batch {B} synthetic 768x512 per GPU "
                                + ("(BASELINE configs[1])" if not high else "(the reference's --high width, model/net.py:446-451)"),
                    "global_batch": world * B, "height": H, "width": W,
@@ -783,6 +785,7 @@ def main():
     ap.add_argument("--crop", default="512x768", help="unet: image size HxW, multiples of 256 (configs[3]: 1080x1920 crops pad to 1280x2048)")
     ap.add_argument("--global-batch", type=int, default=0, help="unet: global batch (default 64 at 768x512, else 32)")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"], help="image type of the input buffers")
+    ap.add_argument("--parity-tf32", action="store_true", help="run g_a / h_a in the TF32 parity mode (not the headline configuration)")
     ap.add_argument("--side-sms", type=int, default=-1, help="SM partition for the hyperprior / syntax side stream (0: single stream; default: Net's)")
     args = ap.parse_args()
     args.batch_set = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])

@@ -164,6 +164,8 @@ LDIC_API int ldic_ctx_pack_input(const void* y_round_bf16, const float* h2, void
  * A[p][(ky*5+kx)*Cin+ci] = x[ci, 2oy+ky-1, 2ox+kx-1] (zero outside), zero for
  * k >= 25*Cin.  model/net.py:97-98 (ZeroPad2d((1,2,1,2)) + Conv2d k5 s2).       */
 LDIC_API int ldic_im2col_5x5s2(const float* x, void* a, int B, int Cin, int H, int W, int Kp, void* stream);
+/* fp32 patch matrix for the TF32 parity mode (LdicConvDesc.precision = 1) */
+LDIC_API int ldic_im2col_5x5s2_f32(const float* x, float* a, int B, int Cin, int H, int W, int Kp, void* stream);
 
 /* ---- a1/a4/a5/a10: tensor-core implicit-GEMM convolutions ---------------------------- */
 enum {
@@ -204,7 +206,12 @@ typedef struct {
   int aux0, aux1;     /* kind specific (LDIC_CTX_CONV1: N, M; LDIC_CONV_FIRST_5x5S2: aux0 = 1 for a uint8 image), else 0 */
   int sm_limit;       /* SM partition for concurrent streams: 0 = all SMs; n > 0 = at most n SMs; n < 0 = leave |n| SMs
                          free (the kernels are persistent, one CTA per SM, so the grid size IS the SM footprint)  */
-  int reserved;
+  int precision;      /* 0: bf16 operands (product path).  1: TF32 parity mode (kind::tf32, about half the rate): x and y are
+                         fp32 NHWC, ldic_conv_pack_weights writes fp32 (tf32-rounded) weights, gamma is the fp32 [Cout][Cout]
+                         gamma_eff of ldic_gdn_prepare.  Kinds 0-3 with 128 / 192 output channels (g_a, h_a): SURVEY H4's
+                         precision comparison -- how many symbols flip because of bf16 operands.  1 rounds the fp32
+                         outputs to tf32 (a layer that feeds another TF32 layer: the tensor core would truncate), 2 keeps
+                         them as they are (the layer that feeds the quantiser).                                        */
 } LdicConvDesc;
 
 /* Elements (bf16) of the packed weight image for this layer, and the packer:

@@ -51,7 +51,7 @@ class LikelihoodArgs(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int),
                 ("Cout", C.c_int), ("Cin_pad", C.c_int), ("Cout_pad", C.c_int), ("act", C.c_int),
-                ("out_f32", C.c_int), ("aux0", C.c_int), ("aux1", C.c_int), ("sm_limit", C.c_int), ("reserved", C.c_int)]
+                ("out_f32", C.c_int), ("aux0", C.c_int), ("aux1", C.c_int), ("sm_limit", C.c_int), ("precision", C.c_int)]
 
 
 class ConvTail(C.Structure):
@@ -100,6 +100,7 @@ _SIGS = {
     "ldic_latent_prep": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldic_ctx_pack_input": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "ldic_im2col_5x5s2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ldic_im2col_5x5s2_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldic_conv_weight_elems": (C.c_longlong, [C.POINTER(ConvDesc)]),
     "ldic_conv_n_cols": (C.c_int, [C.POINTER(ConvDesc)]),
     "ldic_conv_bias_elems": (C.c_int, [C.POINTER(ConvDesc)]),

@@ -89,6 +89,7 @@ struct ConvParams {
   const float* beta;
   void* out;
   unsigned long long* dbg;   // optional cycle counters of CTA 0 (LDIC_DEBUG_TIMING=1), else null
+  int tf_round_out;          // TF32 mode: round the fp32 outputs to tf32 (layers that feed another tf32 layer)
   const __nv_bfloat16* residual;   // optional NHWC bf16 tensor of the output's shape added after the activation (no GDN)
   int dbg_nostore;           // experiment: skip the epilogue's global stores (LDIC_DEBUG_NOSTORE=1)
   // fused tail of Net.forward on the merged last deconv: per-image 1x1 conv (batch_conv) + 8-bit-level squared error
@@ -349,6 +350,23 @@ __device__ __forceinline__ void umma_bf16_lh_cg2(uint32_t d_tmem, uint32_t a_lo,
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
+// kind::tf32 form of the same (fp32 operands in shared memory, K = 8 per instruction = the same 32 bytes per row)
+__device__ __forceinline__ void umma_tf32_lh_cg2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {        // round to nearest (the tensor core would truncate)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
 // completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit_mc(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -450,7 +468,7 @@ __device__ __forceinline__ unsigned long long fused_tail_pixels(const ConvParams
 
 // EW = number of epilogue warps (EW / 4 per TMEM lane quadrant, NP / (EW / 4) accumulator columns per thread): 8 in the
 // streaming kernels; the first layer, which IS its epilogue (5 conv MMAs per tile), runs 12 at NP = 192.
-template <int NP, bool CL = false, int EW = kEpiWarps, bool RES = false>
+template <int NP, bool CL = false, int EW = kEpiWarps, bool RES = false, bool TF = false>
 __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing& R, uint32_t tmem_base, int gk,
                                               int ntiles_cta, int warp, int lane) {
   static_assert(EW % 4 == 0 && NP % (EW / 4) == 0 && (NP / (EW / 4)) % 16 == 0, "epilogue warps must split the columns in 16s");
@@ -524,6 +542,14 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       auto store_cols = [&](int c, int n) {
         if (P.out_f32) {
           float* dst = reinterpret_cast<float*>(P.out) + pix_base + col0 + c;
+          if constexpr (TF) {
+            // an activation that feeds another kind::tf32 layer is rounded to tf32 here (round to nearest): the tensor
+            // core would truncate the fp32 value it reads, a one-sided error that adds up coherently over K
+            if (P.tf_round_out) {
+#pragma unroll
+              for (int k = 0; k < LDW; ++k) if (k < n) xr[c + k] = __uint_as_float(to_tf32(xr[c + k]));
+            }
+          }
 #pragma unroll
           for (int j = 0; j < LDW / 8; ++j) if (8 * j < n) st_global_v8(dst + 8 * j, &xr[c + 8 * j]);
         } else {
@@ -577,6 +603,19 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         }
         if (edbg) { e_t1 = clock64(); e_slot += e_t1 - e_t0; }
         const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
+        if constexpr (TF) {
+          // TF32 parity mode: the x^2 operand stays fp32 (rounded to tf32): 32 columns per 128-byte row, NP / 32 slots
+#pragma unroll
+          for (int j = 0; j < CPT / 4; ++j) {
+            const int col = col0 + j * 4;
+            const uint32_t kc2 = gpos + (col >> 5);
+            const uint32_t a_addr = R.ring_base + (kc2 % R.nslots) * R.slot_bytes;
+            const uint32_t chunk = (uint32_t)((col & 31) >> 2);
+            const float* x4 = &xr[j * 4];
+            st_shared_v4(a_addr + row_off + ((chunk ^ rx) << 4), to_tf32(x4[0] * x4[0]), to_tf32(x4[1] * x4[1]),
+                         to_tf32(x4[2] * x4[2]), to_tf32(x4[3] * x4[3]));
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < CPT / 8; ++j) {
           const int col = col0 + j * 8;
@@ -587,6 +626,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
           st_shared_v4(a_addr + row_off + ((chunk ^ rx) << 4), pack_bf16x2(x8[0] * x8[0], x8[1] * x8[1]),
                        pack_bf16x2(x8[2] * x8[2], x8[3] * x8[3]), pack_bf16x2(x8[4] * x8[4], x8[5] * x8[5]),
                        pack_bf16x2(x8[6] * x8[6], x8[7] * x8[7]));
+        }
         }
         fence_async_smem();                  // generic-proxy writes -> visible to the tensor-core (async) proxy
         if (CL) mbar_arrive_cluster(R.x2_ready_cl + 8u * bsel); else mbar_arrive(&R.x2_ready[bsel]);
@@ -891,7 +931,9 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
 // ---------------------------------------------------------------------------------
 // W3 = true: wide-N form of the merged last deconv (see epilogue_w3): NP = 3 * NPO accumulator columns, bias / beta /
 // gamma refer to the NPO logical columns and the gamma contraction is an N = NPO MMA.
-template <int NP, bool W3 = false, bool RES = false>
+// TF = true: TF32 parity mode (kind::tf32): activations, weights and gamma are fp32 in memory; the host describes them
+// to TMA as bf16 tensors with twice the channels, so every byte count, box and descriptor below is unchanged.
+template <int NP, bool W3 = false, bool RES = false, bool TF = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
@@ -899,8 +941,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int kBHalfBytes = (NP / 2) * kBlockK * 2;
   constexpr int kGHalfBytes = (NPO / 2) * kBlockK * 2;
   constexpr int kStageBytes = kATileBytes + kBHalfBytes;
-  constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-  constexpr uint32_t kIdescG = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPO >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr uint32_t kFmt = TF ? 2u : 1u;      // a / b format: 1 = BF16, 2 = TF32
+  constexpr uint32_t kIdesc2 = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr uint32_t kIdescG = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(NPO >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1046,7 +1089,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t alo = a_lo0 + slot_lo, blo = b_lo0 + slot_lo;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16_lh_cg2(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, idesc, !(first && k == 0));
+            if constexpr (TF) umma_tf32_lh_cg2(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, idesc, !(first && k == 0));
+            else umma_bf16_lh_cg2(d_tmem, alo + 2 * k, hi, blo + 2 * k, hi, idesc, !(first && k == 0));
           tc_commit_mc(&empty_bar[slot]);                    // frees the slot in both CTAs when these MMAs retire
         }
         ++slot; slot_lo += (uint32_t)(kStageBytes >> 4);
@@ -1096,7 +1140,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     R.t_first = pi; R.t_stride = npairs; R.rank = (int)rank;
     R.buf_free_cl = mapa_shared(smem_u32(buf_free), 0); R.x2_ready_cl = mapa_shared(smem_u32(x2_ready), 0);
     if constexpr (W3) epilogue_w3<NP>(P, R, tmem_base, gk, nt, warp, lane);
-    else epilogue_role<NP, true, kEpiWarps, RES>(P, R, tmem_base, gk, nt, warp, lane);
+    else epilogue_role<NP, true, kEpiWarps, RES, TF>(P, R, tmem_base, gk, nt, warp, lane);
   }
 
   tc_fence_before();
@@ -2070,7 +2114,7 @@ void choose_tile(int Wg, int Hg, int B, int* TW, int* TH, int* TN) {
 // in a small cache, so a repeated eager call costs a hash lookup and one cudaLaunchKernelEx (no getenv, no
 // cuTensorMapEncodeTiled, no table construction on the hot path).
 // ---------------------------------------------------------------------------------
-enum PlanKernel { PK_PAIR = 0, PK_W3 = 1, PK_WIDE = 2, PK_FIRST = 3, PK_FIRST_U8 = 4, PK_PAIR_RES = 5 };
+enum PlanKernel { PK_PAIR = 0, PK_W3 = 1, PK_WIDE = 2, PK_FIRST = 3, PK_FIRST_U8 = 4, PK_PAIR_RES = 5, PK_PAIR_TF = 6 };
 struct Plan {
   ConvParams P;
   CUtensorMap a, w, g;
@@ -2123,11 +2167,11 @@ int launch_cluster2(K kern, const char* name, const Plan& pl, cudaStream_t st) {
   return check_launch(name);
 }
 
-template <int NP, bool W3, bool RES = false>
+template <int NP, bool W3, bool RES = false, bool TF = false>
 int plan_pair(Plan* pl) {
   static KernelState ks;
   int mc = 0;
-  int rc = prepare_kernel(conv_tc2_kernel<NP, W3, RES>, ks, true, &mc);
+  int rc = prepare_kernel(conv_tc2_kernel<NP, W3, RES, TF>, ks, true, &mc);
   if (rc) return rc;
   const int total_super = pl->P.super_per_job * pl->P.njobs;
   pl->grid = 2 * (total_super < mc ? total_super : mc);
@@ -2170,6 +2214,12 @@ int finish_plan(Plan* pl) {
         case 192: return plan_pair<192, false, true>(pl);
       }
       break;
+    case PK_PAIR_TF:
+      switch (pl->np) {
+        case 128: return plan_pair<128, false, false, true>(pl);
+        case 192: return plan_pair<192, false, false, true>(pl);
+      }
+      break;
     case PK_W3: return plan_pair<192, true>(pl);
     case PK_WIDE: return plan_wide<384>(pl);
     case PK_FIRST:
@@ -2207,6 +2257,12 @@ int launch_plan(const Plan& pl, cudaStream_t st) {
         case 192: return launch_cluster2(conv_tc2_kernel<192, false, true>, "conv_tc2_kernel(+residual)", pl, st);
       }
       break;
+    case PK_PAIR_TF:
+      switch (pl.np) {
+        case 128: return launch_cluster2(conv_tc2_kernel<128, false, false, true>, "conv_tc2_kernel(tf32)", pl, st);
+        case 192: return launch_cluster2(conv_tc2_kernel<192, false, false, true>, "conv_tc2_kernel(tf32)", pl, st);
+      }
+      break;
     case PK_W3: return launch_cluster2(conv_tc2_kernel<192, true>, "conv_tc2_kernel(wide tail)", pl, st);
     case PK_WIDE: return launch_cluster2(conv_wide_kernel<384>, "conv_wide_kernel", pl, st);
     case PK_FIRST:
@@ -2236,8 +2292,9 @@ struct PackTable {
   signed char ky[kMaxTaps][4], kx[kMaxTaps][4];
   short co_base[kMaxTaps];
 };
+template <typename TW>
 __global__ void k_pack_weights(const float* __restrict__ w, const float* __restrict__ bias, PackTable T,
-                               __nv_bfloat16* __restrict__ wp, float* __restrict__ bp) {
+                               TW* __restrict__ wp, float* __restrict__ bp) {
   const long long total = (long long)T.ntaps * T.Np * T.Kw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int kc = (int)(i % T.Kw);
@@ -2262,7 +2319,8 @@ __global__ void k_pack_weights(const float* __restrict__ w, const float* __restr
                                    : ((((long long)cot * T.Cin + ci) * T.k + ky) * T.k + kx);
       v = w[idx];
     }
-    wp[i] = __float2bfloat16_rn(v);
+    if constexpr (std::is_same<TW, float>::value) wp[i] = __uint_as_float(to_tf32(v));   // TF32 parity mode
+    else wp[i] = __float2bfloat16_rn(v);
   }
   if (bp) {
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < T.Np * T.nbias; n += gridDim.x * blockDim.x) {
@@ -2356,8 +2414,22 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
   if (gdn && L.njobs > 4) return fail(LDIC_EINVAL, "conv: GDN epilogue is not available for the context layers");
   if (((uintptr_t)w_packed) & 15) return fail(LDIC_EINVAL, "conv: packed weights must be 16-byte aligned");
   if (L.Cs % 16) return fail(LDIC_EINVAL, "conv: output channel count must be a multiple of 16");
-  if (d->kind == LDIC_CONV_FIRST_5x5S2)
+  if (d->kind == LDIC_CONV_FIRST_5x5S2) {
+    if (d->precision) return fail(LDIC_EINVAL, "first conv: TF32 mode goes through the patch matrix (ldic_im2col_5x5s2_f32 + LDIC_CONV_1x1)");
     return build_plan_first(d, L, x, w_packed, bias_packed, gamma_bf16, beta_tiled, y, pl);
+  }
+  // TF32 parity mode (LdicConvDesc.precision = 1): fp32 activations / weights / gamma.  TMA and the UMMA descriptors
+  // only see bytes, so the fp32 tensors are described as bf16 tensors with twice the channels: every K block below is
+  // 64 "bf16 columns" = 32 fp32 channels, the tap tables count in those units, the kernel issues kind::tf32 MMAs.
+  const bool tf32 = d->precision == 1 || d->precision == 2;      // 2: fp32 outputs kept unrounded (the layer feeding the quantiser)
+  if (tf32) {
+    if (d->kind != LDIC_CONV_S2_5x5_P12 && d->kind != LDIC_CONV_S2_5x5_P2 && d->kind != LDIC_CONV_S1_3x3_P1 && d->kind != LDIC_CONV_1x1)
+      return fail(LDIC_EINVAL, "conv: TF32 mode covers the analysis-side kinds (5x5 s2, 3x3 s1, 1x1)");
+    if (!d->out_f32 || tail || residual || (L.Np != 128 && L.Np != 192)) return fail(LDIC_EINVAL, "conv: TF32 mode needs fp32 output and 128 / 192 output channels");
+    L.vC *= 2; L.Kw *= 2;
+    for (int t = 0; t < L.ntaps_total; ++t) { L.taps[t].nkc = (short)(2 * L.taps[t].nkc); L.taps[t].a_c0 *= 2; L.taps[t].b_c0 *= 2; }
+    for (int j = 0; j < L.njobs; ++j) L.jobs[j].nkb *= 2;
+  }
 
   const Tuning& tn = tuning();
   ConvParams& P = pl->P;
@@ -2376,8 +2448,8 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
   P.njobs = L.njobs;
   P.total_tiles = P.tiles_per_job * P.njobs;
   P.Wg = L.Wg; P.Hg = L.Hg; P.B = L.Bg;
-  P.gdn_kblocks = gdn ? L.Np / 64 : 0;
-  P.act = d->act; P.out_f32 = d->out_f32;
+  P.gdn_kblocks = gdn ? L.Np / (tf32 ? 32 : 64) : 0;
+  P.act = d->act; P.out_f32 = d->out_f32; P.tf_round_out = d->precision == 1;
   P.ngroups = L.ngroups; P.Cg = L.Cg; P.sy = L.sy; P.sx = L.sx; P.nbias = L.nbias;
   P.out_sX = L.out_sX; P.out_sY = L.out_sY; P.out_sN = L.out_sN;
   for (int j = 0; j < kMaxJobs; ++j) P.jobs[j] = L.jobs[j];
@@ -2460,14 +2532,15 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
     if ((rc = encode_map(&pl->w, w_packed, 2, dims, str, box))) return rc;
   }
   if (gdn) {
-    cuuint64_t dims[2] = {(cuuint64_t)L.Np, (cuuint64_t)L.Np};
-    cuuint64_t str[1] = {(cuuint64_t)L.Np * 2};
+    const cuuint64_t gcols = (cuuint64_t)L.Np * (tf32 ? 2 : 1);
+    cuuint64_t dims[2] = {gcols, (cuuint64_t)L.Np};
+    cuuint64_t str[1] = {gcols * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(wide ? kWideNC / 2 : L.Np / 2)};
     if ((rc = encode_map(&pl->g, gamma_bf16, 2, dims, str, box))) return rc;
   } else {
     pl->g = pl->w;
   }
-  pl->kernel = wide ? PK_WIDE : (wide3 ? PK_W3 : PK_PAIR);
+  pl->kernel = wide ? PK_WIDE : (wide3 ? PK_W3 : (tf32 ? PK_PAIR_TF : PK_PAIR));
   if (residual) {
     if (gdn || wide || wide3 || L.ngroups != 1 || L.njobs != 1 || L.Np > 192 || tail || (((uintptr_t)residual) & 31))
       return fail(LDIC_EINVAL, "conv: the fused residual needs a plain (no GDN, one job) layer of at most 192 output channels and a 32-byte aligned residual");
@@ -2581,7 +2654,8 @@ extern "C" int ldic_conv_pack_weights(const LdicConvDesc* d, const float* w, con
   }
   long long total = (long long)T.ntaps * T.Np * T.Kw;
   int grid = (int)((total + 255) / 256 > num_sms() * 8 ? num_sms() * 8 : (total + 255) / 256);
-  k_pack_weights<<<grid, 256, 0, (cudaStream_t)stream>>>(w, bias, T, (__nv_bfloat16*)w_packed, bias_packed);
+  if (d->precision) k_pack_weights<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w, bias, T, (float*)w_packed, bias_packed);
+  else k_pack_weights<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(w, bias, T, (__nv_bfloat16*)w_packed, bias_packed);
   return check_launch("k_pack_weights");
 }
 

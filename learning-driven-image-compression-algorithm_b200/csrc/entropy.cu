@@ -3,6 +3,7 @@
 // sm_100a; every kernel is a coalesced, vectorised streaming pass.
 #include "common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 #include <string.h>
 
 namespace ldic {
@@ -793,7 +794,8 @@ extern "C" int ldic_latent_prep(const float* y, size_t n, void* y_round_bf16, vo
 // 16-byte (8 x bf16) chunks of A[p][k], k = (ky*5+kx)*Cin + ci, so the stores are fully coalesced.
 constexpr int kI2cPix = 64;
 constexpr int kI2cSpan = 2 * kI2cPix + 4;      // input columns 2*ox0-1 .. 2*ox0+2*63+3 (+1 pad)
-__global__ void __launch_bounds__(256) k_im2col_5x5s2(const float* __restrict__ x, __nv_bfloat16* __restrict__ a,
+template <typename TO>
+__global__ void __launch_bounds__(256) k_im2col_5x5s2(const float* __restrict__ x, TO* __restrict__ a,
                                                       int Cin, int H, int W, int Ho, int Wo, int Kp) {
   extern __shared__ float sx[];                 // [5*Cin][kI2cSpan]
   const int ox0 = blockIdx.x * kI2cPix, oy = blockIdx.y, b = blockIdx.z;
@@ -830,11 +832,30 @@ __global__ void __launch_bounds__(256) k_im2col_5x5s2(const float* __restrict__ 
       const int off = lut[q * 8 + e];
       v[e] = off >= 0 ? sx[off + 2 * px] : 0.f;
     }
-    uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(a + (p_row + ox0 + px) * Kp + q * 8) = o;
+    if constexpr (std::is_same<TO, float>::value) {             // TF32 parity mode: fp32 patch matrix
+      float4* dst = reinterpret_cast<float4*>(a + (p_row + ox0 + px) * Kp + q * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {                            // round to tf32 (the tensor core would truncate)
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v[e]));
+        v[e] = __uint_as_float(r);
+      }
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(a + (p_row + ox0 + px) * Kp + q * 8) = o;
+    }
   }
 }
+static int im2col_impl(const float* x, void* a, int out_f32, int B, int Cin, int H, int W, int Kp, void* stream);
 extern "C" int ldic_im2col_5x5s2(const float* x, void* a, int B, int Cin, int H, int W, int Kp, void* stream) {
+  return im2col_impl(x, a, 0, B, Cin, H, W, Kp, stream);
+}
+extern "C" int ldic_im2col_5x5s2_f32(const float* x, float* a, int B, int Cin, int H, int W, int Kp, void* stream) {
+  return im2col_impl(x, a, 1, B, Cin, H, W, Kp, stream);
+}
+static int im2col_impl(const float* x, void* a, int out_f32, int B, int Cin, int H, int W, int Kp, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0) return LDIC_OK;
   if ((H & 1) || (W & 1) || Kp % 8 || Kp < 25 * Cin) return fail(LDIC_EINVAL, "im2col: H,W must be even and Kp>=25*Cin, Kp%%8==0");
   if (Cin > 8 || B > 65535 || H / 2 > 65535) return fail(LDIC_EINVAL, "im2col: Cin <= 8 and B, H/2 <= 65535");
@@ -842,7 +863,8 @@ extern "C" int ldic_im2col_5x5s2(const float* x, void* a, int B, int Cin, int H,
   int Ho = H / 2, Wo = W / 2;
   dim3 grid((Wo + kI2cPix - 1) / kI2cPix, Ho, B);
   size_t smem = (size_t)5 * Cin * kI2cSpan * sizeof(float);
-  k_im2col_5x5s2<<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)a, Cin, H, W, Ho, Wo, Kp);
+  if (out_f32) k_im2col_5x5s2<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (float*)a, Cin, H, W, Ho, Wo, Kp);
+  else k_im2col_5x5s2<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)a, Cin, H, W, Ho, Wo, Kp);
   return check_launch("k_im2col_5x5s2");
 }
 

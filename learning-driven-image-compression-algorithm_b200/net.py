@@ -198,6 +198,22 @@ class Net(nn.Module):
         self._graphs = {}
         self._discarded_logged = False
 
+    # -- TF32 parity mode ---------------------------------------------------------
+    @property
+    def parity_tf32(self) -> bool:
+        return self.a_model.precision == "tf32"
+
+    @parity_tf32.setter
+    def parity_tf32(self, on: bool):
+        """True: the analysis side (g_a, h_a -- the layers that decide the symbols) runs with fp32 activations and
+        kind::tf32 MMAs (10-bit mantissa operands instead of bf16's 7), at about half the rate of those layers.  It is
+        the precision comparison SURVEY H4 asks for: how many symbols flip against the fp32 reference because of the
+        operand type.  The rate-optimised product path is bf16 (default)."""
+        p = "tf32" if on else "bf16"
+        self.a_model.precision = p
+        self.ha_model.precision = p
+        self._graphs.clear()
+
     # -- checkpoint compatibility ---------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         kept, dropped = {}, []
@@ -266,6 +282,8 @@ class Net(nn.Module):
 
         y = self.a_model.forward_nhwc(x)                                            # :627   (B,h,w,N) fp32 NHWC
         y_round_bf16, y_abs_bf16, _ = ops.latent_prep(y)                            # :197 abs, :741 round
+        if self.ha_model.precision == "tf32":
+            y_abs_bf16 = torch.abs(y)                                               # TF32 parity mode: h_a reads fp32 |y|
         fused_ok = self.tail_fused and self.s_model.has_fused_tail()
         # the SM partition pays off where launches cost no host time, i.e. inside a graph capture (forward() and
         # GraphedEvaluator replay graphs); issued eagerly, the fork / join and the side stream's allocator pool cost more
@@ -377,6 +395,7 @@ class Net(nn.Module):
 
     def _graph_key(self, inputs):
         return (inputs.device.index, inputs.dtype, tuple(inputs.shape), tuple(self.test_size), self.tail_fused, self.side_sms,
+                self.a_model.precision,
                 tuple((p._version, p.data_ptr()) for p in self.parameters()))
 
     def _graph_forward(self, inputs):

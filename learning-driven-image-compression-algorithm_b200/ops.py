@@ -355,11 +355,12 @@ def latent_prep(y: torch.Tensor, want_round_bf16=True, want_abs_bf16=True, want_
     return yr, ya, yf
 
 
-def im2col_5x5s2(x: torch.Tensor, Kp: int = 128) -> torch.Tensor:
+def im2col_5x5s2(x: torch.Tensor, Kp: int = 128, out_f32: bool = False) -> torch.Tensor:
     x = _req(x, torch.float32, "x").contiguous()
     B, Cin, H, W = x.shape
-    a = torch.empty(B, H // 2, W // 2, Kp, dtype=torch.bfloat16, device=x.device)
-    check(_L().ldic_im2col_5x5s2(_ptr(x), _ptr(a), B, Cin, H, W, Kp, _stream()), "ldic_im2col_5x5s2")
+    a = torch.empty(B, H // 2, W // 2, Kp, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    fn = _L().ldic_im2col_5x5s2_f32 if out_f32 else _L().ldic_im2col_5x5s2
+    check(fn(_ptr(x), _ptr(a), B, Cin, H, W, Kp, _stream()), "ldic_im2col_5x5s2")
     return a
 
 
@@ -376,7 +377,14 @@ class ConvTC:
 
     def __init__(self, kind: int, weight: torch.Tensor, bias: Optional[torch.Tensor], *, act: int = _lib.ACT_NONE,
                  out_f32: bool = False, cin_pad: Optional[int] = None, cin_offset: int = 0,
-                 cout_pad: Optional[int] = None, gdn: Optional[tuple] = None, aux=(0, 0)):
+                 cout_pad: Optional[int] = None, gdn: Optional[tuple] = None, aux=(0, 0), precision: str = "bf16"):
+        if precision not in ("bf16", "tf32", "tf32_last"):
+            raise LdicError("ConvTC precision must be 'bf16', 'tf32' or 'tf32_last'")
+        # TF32 parity mode: fp32 NHWC activations, kind::tf32 MMAs (~half rate).  'tf32' rounds the outputs to tf32 (they
+        # feed another tf32 layer), 'tf32_last' leaves them fp32 (they feed the quantiser)
+        self.tf32 = 1 if precision == "tf32" else (2 if precision == "tf32_last" else 0)
+        if self.tf32:
+            out_f32 = True
         w = _req(weight, torch.float32, "weight").contiguous()
         transposed = kind in (_lib.LDIC_DECONV_GS_5x5, _lib.LDIC_DECONV_HS_5x5, _lib.LDIC_DECONV_S1_3x3,
                               _lib.LDIC_DECONV_GS_5x5_MERGED)
@@ -416,7 +424,7 @@ class ConvTC:
         nb = L.ldic_conv_bias_elems(C.byref(d))
         if n < 0 or self.np_cols < 0 or nb < 0:
             check(-1, "ldic_conv_weight_elems")
-        self.w_packed = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+        self.w_packed = torch.empty(n, dtype=torch.float32 if self.tf32 else torch.bfloat16, device=w.device)
         self.bias_packed = torch.empty(nb, dtype=torch.float32, device=w.device)
         b = None if bias is None else _req(bias, torch.float32, "bias").contiguous()
         check(L.ldic_conv_pack_weights(C.byref(d), _ptr(w), _ptr(b), int(cin_offset), _ptr(self.w_packed),
@@ -427,12 +435,20 @@ class ConvTC:
                 raise LdicError("GDN epilogue needs (beta_p, gamma_p, beta_bound, gamma_bound, pedestal)")
             beta_p, gamma_p, bb, gb, ped = gdn
             groups = self.np_cols // self.cout_pad
-            _, _, self.gamma_bf16, self.beta_tiled = gdn_prepare(beta_p, gamma_p, bb, gb, ped, tc_groups=groups,
-                                                                 tc_np=self.np_cols)
+            if self.tf32:        # fp32 gamma_eff [C, C] rounded to tf32 (the tensor core would truncate), beta_eff as is
+                if groups != 1 or self.np_cols != beta_p.numel():
+                    raise LdicError("TF32 mode: GDN over exactly the layer's output channels")
+                be, ge, _, _ = gdn_prepare(beta_p, gamma_p, bb, gb, ped)
+                gi = ge.contiguous().view(torch.int32)
+                self.gamma_bf16 = ((gi + 0x1000) & ~0x1FFF).view(torch.float32).contiguous()
+                self.beta_tiled = be.contiguous()
+            else:
+                _, _, self.gamma_bf16, self.beta_tiled = gdn_prepare(beta_p, gamma_p, bb, gb, ped, tc_groups=groups,
+                                                                     tc_np=self.np_cols)
 
     def _desc(self, B, H, W, sm_limit: int = 0) -> ConvDesc:
         return ConvDesc(self.kind, B, H, W, self.cin, self.cout, self.cin_pad, self.cout_pad, self.act,
-                        int(self.out_f32), int(self.aux[0]), int(self.aux[1]), int(sm_limit), 0)
+                        int(self.out_f32), int(self.aux[0]), int(self.aux[1]), int(sm_limit), int(self.tf32))
 
     def out_dims(self, B, H, W):
         d = self._desc(B, H, W)
@@ -509,9 +525,10 @@ class ConvTC:
                 raise LdicError(f"first conv input must be a contiguous NCHW fp32 / uint8 image with {self.cin} channels, got {tuple(x.shape)}")
             B, _, H, W = x.shape
         else:
-            _req(x, torch.bfloat16, "x")
+            _req(x, torch.float32 if self.tf32 else torch.bfloat16, "x")
             if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
-                raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
+                raise LdicError(f"conv input must be contiguous NHWC {'fp32' if self.tf32 else 'bf16'} with {self.cin_pad} "
+                                f"channels, got {tuple(x.shape)}")
             B, H, W, _ = x.shape
         if out is None:
             out = torch.empty(self.out_dims(B, H, W), dtype=torch.float32 if self.out_f32 else torch.bfloat16,

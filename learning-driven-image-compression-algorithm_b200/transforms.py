@@ -25,9 +25,10 @@ def _versions(module: nn.Module):
 class _PlannedTransform(nn.Module):
     _plan = None
     _plan_key = None
+    precision = "bf16"      # "tf32": TF32 parity mode of the analysis-side transforms (g_a, h_a): fp32 activations, kind::tf32
 
     def plan(self):
-        key = _versions(self)
+        key = _versions(self) + (self.precision,)
         if self._plan is None or self._plan_key != key:
             with torch.no_grad():
                 self._plan = self._build_plan()
@@ -64,6 +65,20 @@ class analysisTransformModel(_PlannedTransform):
         c1 = t[1]
         self._kp1 = ops._pad64(25 * c1.in_channels)
         self._first_fused = False
+        if self.precision == "tf32":
+            if c1.in_channels * 25 > 128:
+                raise ops.LdicError("TF32 mode: the first layer goes through the 128-column patch matrix (Cin <= 5)")
+            pr = dict(precision="tf32")
+            w1 = c1.weight.detach().permute(0, 2, 3, 1).reshape(c1.out_channels, -1).contiguous()
+            layers.append(ops.ConvTC(_lib.LDIC_CONV_1x1, w1, c1.bias.detach(), act=_lib.ACT_GDN, cin_pad=self._kp1,
+                                     gdn=self._gdn_args(t[2]), **pr))
+            self._first_im2col = True
+            for ci, gi in ((4, 5), (7, 8)):
+                layers.append(ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P12, t[ci].weight.detach(), t[ci].bias.detach(),
+                                         act=_lib.ACT_GDN, gdn=self._gdn_args(t[gi]), **pr))
+            layers.append(ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P12, t[10].weight.detach(), t[10].bias.detach(),
+                                     act=_lib.ACT_NONE, precision="tf32_last"))
+            return layers
         if c1.in_channels == 3 and c1.out_channels in (64, 128, 192) and self.first_fused:
             # first layer + GDN straight from the NCHW fp32 image (no patch matrix in HBM)
             layers.append(ops.ConvTC(_lib.LDIC_CONV_FIRST_5x5S2, c1.weight.detach(), c1.bias.detach(),
@@ -94,12 +109,12 @@ class analysisTransformModel(_PlannedTransform):
         B, _, H, W = x_nchw.shape
         if H % 16 or W % 16:
             raise ops.LdicError("analysis transform needs H and W to be multiples of 16")
-        if x_nchw.dtype == torch.uint8 and not (self._first_fused and W % 16 == 0):
+        if x_nchw.dtype == torch.uint8 and not (self._first_fused and W % 16 == 0):   # (also the TF32 mode)
             x_nchw = ops.u8_to_f32_pm1(x_nchw)                               # only the fused first layer reads uint8 itself
         if self._first_fused:
             t = L[0](x_nchw.contiguous())                                    # (B,H/2,W/2,C) bf16 NHWC
         elif self._first_im2col:
-            a = ops.im2col_5x5s2(x_nchw, Kp=self._kp1)                       # (B,H/2,W/2,Kp)
+            a = ops.im2col_5x5s2(x_nchw, Kp=self._kp1, out_f32=self.precision == "tf32")   # (B,H/2,W/2,Kp)
             t = L[0](a.view(1, 1, B * (H // 2) * (W // 2), self._kp1)).view(B, H // 2, W // 2, -1)
         else:
             t = L[0](ops.nchw_to_nhwc_bf16(x_nchw, ops._pad64(x_nchw.shape[1])))
@@ -196,10 +211,11 @@ class h_analysisTransformModel(_PlannedTransform):
 
     def _build_plan(self):
         t = self.transform
-        return [ops.ConvTC(_lib.LDIC_CONV_S1_3x3_P1, t[0].weight.detach(), t[0].bias.detach(), act=_lib.ACT_RELU),
-                ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P2, t[2].weight.detach(), t[2].bias.detach(), act=_lib.ACT_RELU),
+        pr = dict(precision=self.precision)
+        return [ops.ConvTC(_lib.LDIC_CONV_S1_3x3_P1, t[0].weight.detach(), t[0].bias.detach(), act=_lib.ACT_RELU, **pr),
+                ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P2, t[2].weight.detach(), t[2].bias.detach(), act=_lib.ACT_RELU, **pr),
                 ops.ConvTC(_lib.LDIC_CONV_S2_5x5_P2, t[4].weight.detach(), t[4].bias.detach(), act=_lib.ACT_NONE,
-                           out_f32=True)]
+                           out_f32=True, precision="tf32_last" if self.precision == "tf32" else "bf16")]
 
     def forward_nhwc(self, y_abs_nhwc_bf16, sm_limit: int = 0):
         t = y_abs_nhwc_bf16
