@@ -606,6 +606,157 @@ def run_tritplane(args):
         dist.destroy_process_group()
 
 
+def run_codec(args):
+    """SURVEY row f4 (the "what comes next" row): the whole encoder x -> bitstreams.  A step = Net.rd_forward on one batch
+    of 768x512 images + rANS coding of its three symbol streams (z, y content, syntax) into one bitstream per image and
+    stream.  Images shard over the ranks; nothing is exchanged.  The reference has no entropy coder (it estimates the
+    rate), so the parity of this stage is UNPINNED against it; the bench checks the exact round trip of the coded
+    symbols and reports coded vs estimated bpp."""
+    import torch
+    import torch.distributed as dist
+    import ldic_b200
+    from ldic_b200 import ops
+    import det_weights as dw
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "768x512 imgs/sec encoded to bitstreams (g_a->hyperprior->context model->rANS)"
+    if args.impl == "reference":
+        if rank == 0:
+            import numpy as np
+            from oracle import rans_ref
+            # one image per step: the CPU port of the reference forward (all host cores) + the numpy restatement of the
+            # coder on one image's worth of content symbols (synthetic symbols following their model; 1 core)
+            n_fw = max(1, min(args.steps, 2))
+            _, fw_s, cores = cpu_port_images_per_s(n_fw, 1)
+            n, S = 32 * 48 * 176, 132
+            r = np.random.Generator(np.random.PCG64(0))
+            mu = (3 * r.standard_normal(n)).astype(np.float32)
+            sg = np.exp(0.8 * r.standard_normal(n) + 0.2).astype(np.float32)
+            k = np.rint(mu + sg * r.standard_normal(n)).astype(np.int64)
+            t0 = time.perf_counter()
+            for _ in range(n_fw):
+                rans_ref.encode_segment(k, mu, sg, S)
+            rans_s = (time.perf_counter() - t0) / n_fw
+            dt = fw_s + rans_s
+            ips = 1.0 / dt
+            emit({"impl": "reference", "metric": metric, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                  "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                  "dtype": "f32 + int64", "data": "synthetic",
+                  "config": {"workload": "CPU port of the reference forward (oracle/ref_path.py, 1 image 768x512 per step) + numpy "
+                                         "restatement of the rANS coder on one image's content symbols (oracle/rans_ref.py); the "
+                                         "reference itself has no coder", "forward_s": fw_s, "rans_s": rans_s},
+                  "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{n_fw} image(s): forward on {cores} cores + {n} symbols coded on 1 core"},
+                  "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ldic_b200._lib.check(ldic_b200._lib.load().ldic_check_device(local), "device")
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, _, _, peak_src = peaks()
+    B = args.batch
+    net = ldic_b200.Net((B, H, W, 3), (B, H, W, 3), False, False).to(dev).eval()
+    net.load_state_dict(dw.make_state_dict(0), strict=True)
+    NBUF = 4
+    host = [t.pin_memory() for t in make_u8_batches(rank, B, NBUF)]
+    xs = [t.to(dev) for t in host]
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def step(x):
+        out = net.rd_forward(x)
+        return out, net.entropy_encode(out)
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            step(xs[i % NBUF])
+        sync_all()
+        sampler = ClockSampler(local)
+        n0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            out, enc = step(xs[i % NBUF])
+        e1.record()
+        sync_all()
+        launches = int(ops.launch_count() - n0)
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        # the entropy-coding stage alone (events around the encoder / decoder calls of the last step's latents)
+        lat = out["latents"]
+        h, w, Cc = H // 16, W // 16, net.N - net.M
+        ekw = dict(mu=lat["ctx"], mu_mode=2, mu_rs=lat["ctx_rs"], sigma=lat["ctx"], sigma_mode=2, sigma_rs=lat["ctx_rs"],
+                   sigma_off=lat["ctx_sig_off"], sigma_is_log=True)
+        y_hat = torch.empty(B, h, w, Cc, device=dev)
+        enc_ms = dec_ms = 0.0
+        for i in range(args.steps):
+            e0.record(); ency = ops.rans_encode_rows(lat["y"], B * h * w, Cc, h * w, v_rs=net.N, v_off=net.M, **ekw); e1.record()
+            torch.cuda.synchronize(dev); enc_ms += e0.elapsed_time(e1)
+            e0.record(); ops.rans_decode_rows(ency, B * h * w, Cc, h * w, y_hat, v_hat_rs=Cc, check_status=False, **ekw); e1.record()
+            torch.cuda.synchronize(dev); dec_ms += e0.elapsed_time(e1)
+        enc_ms /= args.steps; dec_ms /= args.steps
+        clocks = sampler.stop()
+        round_trip = bool(torch.equal(y_hat, torch.round(lat["y"][..., net.M:])))
+        z_hat = net.decode_z(enc["z"], B, H, W)
+        round_trip = round_trip and bool(torch.equal(z_hat, torch.round(lat["z"])))
+        sizes = {k: v.nbytes() for k, v in enc.items()}
+        coded_bits = 8.0 * sum(sum(v) for v in sizes.values())
+        est_bits = float(out["bits"].double().sum().item()) / -math.log(2.0)
+        # end to end: uint8 host images in, bitstream bytes out (sizes first, then exactly the coded bytes)
+        sync_all()
+        d2h = 0
+        e0.record()
+        for i in range(args.steps):
+            x = host[i % NBUF].to(dev, non_blocking=True)
+            out_, enc_ = step(x)
+            for v in enc_.values():
+                d2h += sum(len(b) for b in v.tobytes()) + 4 * B
+        e1.record()
+        sync_all()
+        tt2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
+        ok_t = torch.tensor([int(round_trip)], device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        round_trip = bool(ok_t.item())
+    t_ms = float(tt.item())
+    if rank == 0:
+        nsym = B * h * w * Cc
+        alg_bytes = 12.0 * nsym + sum(sizes["y"])                  # v, mu, log sigma read once; bitstream written once
+        gbs = alg_bytes / (enc_ms * 1e-3) / 1e9
+        emit({"metric": metric, "value": world * B * args.steps / (t_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+              "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "bf16 (transforms) + int32 (coder)", "data": "synthetic",
+              "config": {"workload": f"SURVEY f4: model/net.py Net forward + rANS coding of z / y / syntax symbols, 768x512, batch {B} "
+                                     "per GPU, one bitstream per image and stream", "global_batch": world * B, "height": H, "width": W,
+                         "weights": "deterministic random init (tests/det_weights.py)", "launch_mode": "eager",
+                         "l2": f"{NBUF} rotating input batches; activations of one step exceed L2",
+                         "parity": "UNPINNED against the reference (it has no entropy coder); exact round trip + CPU restatement (tests/test_gpu_rans.py)"},
+              "e2e": {"value": world * B * args.steps / (float(tt2.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * H * W,
+                      "d2h_bytes_per_step": d2h // max(args.steps, 1)},
+              "gpu_launches": launches, "clocks": clocks,
+              "roofline": {"bound": "hbm", "kernel": "rANS encoder of the content symbols (k_rans_ops / k_rans_enc_streams / k_rans_pack + 3 small)",
+                           "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                           "bytes_per_symbol": alg_bytes / nsym, "symbols": nsym, "ms": enc_ms, "decode_ms": dec_ms,
+                           "note": "latency bound, not HBM bound: the rANS state recurrence is sequential within a stream "
+                                   "(2048 symbols per stream by default; ~300 cycles per symbol on one thread)",
+                           "peak_source": f"{peak_src} hbm_gbs"},
+              "parity": {"round_trip_exact": round_trip, "bpp_coded": coded_bits / (B * H * W), "bpp_estimated": est_bits / (B * H * W),
+                         "bytes_per_image": {k: sum(v) / B for k, v in sizes.items()}}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_unet(args):
     """BASELINE configs[2] (768x512, global batch 64 sharded over the GPUs) and, with --crop 1280x2048, configs[3]
     (1920x1080 crops padded to the multiple of 256 the model needs, global batch 32): the U-Net-family Net (model/net_unet_ha_hs.py) with
@@ -779,9 +930,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying CUDA graphs")
-    ap.add_argument("--config", default="net", choices=["net", "high", "tritplane", "unet"],
+    ap.add_argument("--config", default="net", choices=["net", "high", "tritplane", "unet", "codec"],
                     help="net: BASELINE configs[1] (headline); high: the N=384 model; tritplane: BASELINE configs[4]; "
-                         "unet: the U-Net family, configs[2] (768x512, global batch 64) or with --crop 1280x2048 configs[3]")
+                         "codec: forward + rANS bitstreams (SURVEY f4); unet: the U-Net family, configs[2] (768x512, global batch 64) or with --crop 1280x2048 configs[3]")
     ap.add_argument("--crop", default="512x768", help="unet: image size HxW, multiples of 256 (configs[3]: 1080x1920 crops pad to 1280x2048)")
     ap.add_argument("--global-batch", type=int, default=0, help="unet: global batch (default 64 at 768x512, else 32)")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"], help="image type of the input buffers")
@@ -793,6 +944,8 @@ def main():
         run_unet(args)
     elif args.config == "tritplane":
         run_tritplane(args)
+    elif args.config == "codec":
+        run_codec(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -302,6 +302,45 @@ LDIC_API int ldic_tritplane_likelihood(const float* v, const float* mu, const fl
                               float scale_bound, float lik_bound, signed char* planes, int* q_out,
                               float* sum_ln_per_plane, void* workspace, void* stream);
 
+/* ---- f4: rANS entropy coder over the quantised latents --------------------------------------
+ * Builder-defined extension: the reference only ESTIMATES the rate (model/net.py:856-861) and holds no entropy coder
+ * or bitstream, so there is no reference oracle for these entry points ("parity unpinned" against the reference).
+ * They are pinned by (1) decode(encode(x)) == x bit for bit, (2) byte-for-byte equality with the CPU restatement
+ * oracle/rans_ref.py, (3) 8 * bytes within a fraction of a percent (+ header) of the sum(-log2 L) that
+ * ldic_round_likelihood_bpp returns for the same symbols (tests/test_gpu_rans.py).
+ * Addressing as in LdicLikelihoodArgs (rows x cols, row strides, broadcast modes 0..3; mode 3 of mu shares
+ * sigma_period).  rows_per_segment rows form one segment = one independent bitstream (one image); every segment
+ * holds seg_elems = rows_per_segment * cols symbols, interleaved over `streams` rANS states (symbol i -> stream
+ * i % streams, at most 65535 symbols per stream; more streams = more parallelism, 6 bytes of header each).
+ * quant: 1 = symbols round(v), model N(mu, sigma) (GaussianModel, model/net.py:272-286,:741);
+ *        2 = symbols round(v - mu), model N(0, sigma), decoder returns symbol + mu (model/net_unet_ha_hs.py:937).
+ * Integer model (16-bit frequencies from a 24-bit normal-CDF table, window of 2 + ceil(6 sigma) integers each side
+ * of rint(mu), the rest escaped out of band) and byte layout: header of csrc/rans.cu.
+ * encode: out = segments x out_stride bytes (out_stride >= ldic_rans_max_bytes for a guaranteed fit, multiple of 4),
+ *   sizes[segment] = bytes written (0 if it did not fit), status[segment] = 0 or a bit set of
+ *   1 = a symbol was NaN / beyond 2^30 (coded as 0), 2 = out_stride too small, 4 = bad header, 8 = corrupt stream.
+ * decode: v_hat[row * v_hat_rs + v_hat_off + col] receives the symbols (fp32); args->v is ignored.
+ * workspace: ldic_rans_workspace_bytes(segments, seg_elems, streams) bytes, 256-byte aligned, no initialisation.  */
+typedef struct {
+  const float* v;      long long v_rs;      long long v_off;
+  const float* mu;     long long mu_rs;     long long mu_off;     int mu_mode;
+  const float* sigma;  long long sigma_rs;  long long sigma_off;  int sigma_mode;
+  int sigma_period;
+  long long rows, cols, rows_per_segment;
+  int quant, sigma_is_log;
+  float scale_bound;   /* sigma = max(sigma, scale_bound) when > 0 (GaussianConditional: 0.11) */
+  int streams;
+} LdicRansArgs;
+LDIC_API size_t ldic_rans_max_bytes(long long seg_elems, int streams);
+LDIC_API size_t ldic_rans_workspace_bytes(long long segments, long long seg_elems, int streams);
+LDIC_API int ldic_rans_encode(const LdicRansArgs* args, unsigned char* out, long long out_stride, unsigned int* sizes,
+                     unsigned int* status, void* workspace, void* stream);
+LDIC_API int ldic_rans_decode(const LdicRansArgs* args, const unsigned char* in, long long in_stride, const unsigned int* sizes,
+                     float* v_hat, long long v_hat_rs, long long v_hat_off, unsigned int* status, void* workspace,
+                     void* stream);
+/* the 24-bit normal-CDF table of the format: T[i] = round(Phi(-8 + i/128) * 2^24), *entries = 2049 (host memory) */
+LDIC_API const unsigned int* ldic_rans_phi_table(int* entries);
+
 /* ---- f2: window attention (layers/win_attention.py:38-209; blocks of layers/layers.py:56-111) --------------
  * WinBasedAttention.forward = x + proj(W-MSA(qkv(x))) on 8x8 (or 4x4) windows with an optional cyclic shift.  The
  * qkv and proj Linears are 1x1 convs (ldic_conv_forward, LDIC_CONV_1x1: three of them, q pre-scaled by

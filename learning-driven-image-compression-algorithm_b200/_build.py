@@ -8,7 +8,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libldic_b200.so")
-SOURCES = ["entropy.cu", "conv_tc.cu", "syntax.cu", "tritplane.cu", "winattn.cu"]
+SOURCES = ["entropy.cu", "conv_tc.cu", "syntax.cu", "tritplane.cu", "winattn.cu", "rans.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared"]
 

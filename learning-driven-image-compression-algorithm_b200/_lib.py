@@ -48,6 +48,17 @@ class LikelihoodArgs(C.Structure):
     ]
 
 
+class RansArgs(C.Structure):
+    _fields_ = [
+        ("v", C.c_void_p), ("v_rs", C.c_longlong), ("v_off", C.c_longlong),
+        ("mu", C.c_void_p), ("mu_rs", C.c_longlong), ("mu_off", C.c_longlong), ("mu_mode", C.c_int),
+        ("sigma", C.c_void_p), ("sigma_rs", C.c_longlong), ("sigma_off", C.c_longlong), ("sigma_mode", C.c_int),
+        ("sigma_period", C.c_int),
+        ("rows", C.c_longlong), ("cols", C.c_longlong), ("rows_per_segment", C.c_longlong),
+        ("quant", C.c_int), ("sigma_is_log", C.c_int), ("scale_bound", C.c_float), ("streams", C.c_int),
+    ]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int),
                 ("Cout", C.c_int), ("Cin_pad", C.c_int), ("Cout_pad", C.c_int), ("act", C.c_int),
@@ -117,6 +128,12 @@ _SIGS = {
     "ldic_tritplane_workspace_bytes": (C.c_size_t, []),
     "ldic_tritplane_likelihood": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_rans_max_bytes": (C.c_size_t, [C.c_longlong, C.c_int]),
+    "ldic_rans_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_longlong, C.c_int]),
+    "ldic_rans_encode": (C.c_int, [C.POINTER(RansArgs), C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_rans_decode": (C.c_int, [C.POINTER(RansArgs), C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
+                                  C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_rans_phi_table": (C.POINTER(C.c_uint), [C.POINTER(C.c_int)]),
     "ldic_window_attention_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldic_window_attention_core": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import Callable, Dict, Optional
 
+import math
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -365,8 +367,73 @@ class Net(nn.Module):
         if per_image_bits:       # sum(ln L) per image and stream (the reference only forms the batch total, :857)
             out["bits_per_image"] = torch.stack([torch.log(l.reshape(B, -1).double()).sum(1)
                                                  for l in (lik_z, lik_y, lik_syn)], 1)
-        out["latents"] = {"y": y, "z": z, "h2": h2, "ctx": ctx, "z3_syntax": z3_syntax, "conv_w": conv_w, "xt16": xt16}
+        out["latents"] = {"y": y, "z": z, "h2": h2, "ctx": ctx, "z3_syntax": z3_syntax, "conv_w": conv_w, "xt16": xt16,
+                          "ctx_rs": ctx_rs, "ctx_sig_off": ctx_sig_off, "syn_first": syn_first, "syn_second": syn_second}
         return out
+
+    # ---- f4: actual bitstreams (the reference only estimates the rate, model/net.py:856-861) ----------------------------
+    def entropy_encode(self, out: Dict[str, torch.Tensor], symbols_per_stream: int = 2048) -> Dict[str, "ops.RansStreams"]:
+        """rANS-codes the three symbol streams of one rd_forward result with the very (mu, sigma) its likelihoods were
+        evaluated with: z = round(z) under the per-channel N(0, sigma_z) (:676,:781), y = the N-M content channels of
+        round(y) under the context model's (mu, sigma) (:784-786), syntax = round(z3_syntax) under the syntax prior
+        (:789).  One independent bitstream per image and stream; nothing is synchronised here."""
+        lat = out["latents"]
+        y, z = lat["y"], lat["z"]
+        B, h, w, N = y.shape
+        M, Cc = self.M, self.N - self.M
+        hz, wz = z.shape[1], z.shape[2]
+        sps = symbols_per_stream
+        sigma_z = self.z2_sigma.detach().reshape(N).contiguous()
+        enc = {}
+        enc["z"] = ops.rans_encode_rows(z, B * hz * wz, N, hz * wz, v_rs=N, sigma=sigma_z, sigma_mode=1,
+                                        streams=ops.rans_streams_for(hz * wz * N, sps))
+        enc["y"] = ops.rans_encode_rows(y, B * h * w, Cc, h * w, v_rs=N, v_off=M, mu=lat["ctx"], mu_mode=2, mu_rs=lat["ctx_rs"],
+                                        sigma=lat["ctx"], sigma_mode=2, sigma_rs=lat["ctx_rs"], sigma_off=lat["ctx_sig_off"],
+                                        sigma_is_log=True, streams=ops.rans_streams_for(h * w * Cc, sps))
+        enc["syntax"] = ops.rans_encode(lat["z3_syntax"].reshape(B, -1, 1, 1), lat["syn_first"].reshape(B, -1, 1, 1),
+                                        lat["syn_second"].reshape(B, -1, 1, 1), streams=1)
+        return enc
+
+    def compress(self, inputs: torch.Tensor, symbols_per_stream: int = 2048):
+        """x -> per-image bitstreams: a list of {"z": bytes, "y": bytes, "syntax": bytes} and the dict
+        {"bpp_coded", "bpp_estimated"} (coded = 8 * bytes over the batch's pixels; estimated = the reference's
+        sum(-log2 L) figure of the same forward, model/net.py:856-861)."""
+        out = self.rd_forward(inputs)
+        with torch.cuda.device(inputs.device):
+            enc = self.entropy_encode(out, symbols_per_stream)
+            parts = {k: v.tobytes() for k, v in enc.items()}
+        B, _, H, W = inputs.shape
+        streams = [{k: parts[k][b] for k in parts} for b in range(B)]
+        coded = 8.0 * sum(len(v) for s in streams for v in s.values()) / (B * H * W)
+        est = float(out["bits"].double().sum().item()) / (-math.log(2.0) * B * H * W)
+        return streams, {"bpp_coded": coded, "bpp_estimated": est}
+
+    def decode_z(self, z_streams, batch: int, H: int, W: int, symbols_per_stream: int = 2048) -> torch.Tensor:
+        """The hyper-latent symbols (B, H/64, W/64, N) fp32 NHWC from their bitstreams alone (the prior is a model
+        parameter): the first step of a decoder; h_s of the result reproduces the encoder's h2 bit for bit."""
+        N = self.N
+        hz, wz = H // 64, W // 64
+        dev = self.z2_sigma.device
+        with torch.cuda.device(dev):
+            z_hat = torch.empty(batch, hz, wz, N, dtype=torch.float32, device=dev)
+            sigma_z = self.z2_sigma.detach().reshape(N).contiguous()
+            ops.rans_decode_rows(z_streams, batch * hz * wz, N, hz * wz, z_hat, v_hat_rs=N, sigma=sigma_z, sigma_mode=1,
+                                 streams=ops.rans_streams_for(hz * wz * N, symbols_per_stream))
+        return z_hat
+
+    def decode_y(self, y_streams, ctx: torch.Tensor, ctx_rs: int, ctx_sig_off: int, batch: int, H: int, W: int,
+                 symbols_per_stream: int = 2048) -> torch.Tensor:
+        """The content symbols (B, H/16, W/16, N-M) fp32 NHWC given the context model's (mu | log sigma) tensor.  The
+        reference's context model is causal over y_hat (BlockSample with masked=True, model/net.py:219-242), so a real
+        decoder alternates it with this call over wavefronts; here the whole tensor is supplied at once."""
+        Cc = self.N - self.M
+        h, w = H // 16, W // 16
+        with torch.cuda.device(ctx.device):
+            y_hat = torch.empty(batch, h, w, Cc, dtype=torch.float32, device=ctx.device)
+            ops.rans_decode_rows(y_streams, batch * h * w, Cc, h * w, y_hat, v_hat_rs=Cc, mu=ctx, mu_mode=2, mu_rs=ctx_rs,
+                                 sigma=ctx, sigma_mode=2, sigma_rs=ctx_rs, sigma_off=ctx_sig_off, sigma_is_log=True,
+                                 streams=ops.rans_streams_for(h * w * Cc, symbols_per_stream))
+        return y_hat
 
     def metrics(self, out: Dict[str, torch.Tensor], batch: int, H: int, W: int):
         """bpp / v_mse / v_psnr exactly as model/net.py:856-869 forms them."""

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, LikelihoodArgs, LdicError, check
+from ._lib import ConvDesc, LikelihoodArgs, RansArgs, LdicError, check
 
 _ws_cache = {}
 # bench.py sets this to a list to get (layer, (B,H,W), start_event, end_event) per conv launch
@@ -227,6 +227,174 @@ def gaussian_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch
                         sigma_rs=n, quant=quant, form=form, lik_bound=lik_bound, scale_bound=scale_bound, v_hat=vh,
                         v_hat_rs=n, lik=lik, sum_out=sum_out)
     return vh, lik, s
+
+
+# --------------------------------------------------------------------------------------
+# f4: rANS entropy coder (builder-defined extension: the reference only estimates the rate, see include/ldic.h)
+# --------------------------------------------------------------------------------------
+RANS_STATUS = {1: "a symbol was NaN or beyond 2^30", 2: "output capacity too small", 4: "bad header", 8: "corrupt stream"}
+
+
+def rans_streams_for(seg_elems: int, symbols_per_stream: int = 2048) -> int:
+    """Number of interleaved rANS states per segment: about `symbols_per_stream` symbols each (6 header bytes per
+    stream; fewer symbols per stream = more GPU parallelism, more header)."""
+    return max(1, -(-int(seg_elems) // max(1, min(int(symbols_per_stream), 65535))))
+
+
+def _rans_status_check(status: torch.Tensor, what: str):
+    st = status.cpu().tolist()
+    bad = [(i, v) for i, v in enumerate(st) if v]
+    if bad:
+        i, v = bad[0]
+        why = ", ".join(t for b, t in RANS_STATUS.items() if v & b)
+        raise LdicError(f"{what}: segment {i}: {why}")
+
+
+class RansStreams:
+    """Device-resident result of rans_encode_rows: `buf` uint8 [segments, stride], `sizes` int32 [segments]."""
+
+    def __init__(self, buf, sizes, status, streams, seg_elems, quant):
+        self.buf, self.sizes, self.status = buf, sizes, status
+        self.streams, self.seg_elems, self.quant = streams, seg_elems, quant
+
+    def check(self):
+        _rans_status_check(self.status, "rans encode")
+        return self
+
+    def nbytes(self):
+        """Bytes per segment (synchronises)."""
+        self.check()
+        return self.sizes.cpu().tolist()
+
+    def tobytes(self):
+        """One bytes object per segment (synchronises)."""
+        sizes = self.nbytes()
+        m = max(sizes) if sizes else 0
+        host = self.buf[:, :m].cpu().numpy()
+        return [host[i, :n].tobytes() for i, n in enumerate(sizes)]
+
+
+def _rans_args(rows, cols, rows_per_segment, v, v_rs, v_off, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs, sigma_off,
+               sigma_period, quant, sigma_is_log, scale_bound, streams):
+    a = RansArgs()
+    a.v, a.v_rs, a.v_off = _ptr(v), v_rs, v_off
+    a.mu, a.mu_rs, a.mu_off, a.mu_mode = _ptr(mu), mu_rs, mu_off, mu_mode
+    a.sigma, a.sigma_rs, a.sigma_off, a.sigma_mode, a.sigma_period = _ptr(sigma), sigma_rs, sigma_off, sigma_mode, sigma_period
+    a.rows, a.cols, a.rows_per_segment = rows, cols, rows_per_segment
+    a.quant, a.sigma_is_log, a.scale_bound, a.streams = quant, int(bool(sigma_is_log)), float(scale_bound), streams
+    return a
+
+
+def _rans_ws(device, segs, seg_elems, streams):
+    n = int(_L().ldic_rans_workspace_bytes(segs, seg_elems, streams))
+    return torch.empty(max(n, 256), dtype=torch.uint8, device=device)     # torch's allocator hands out >= 512-byte alignment
+
+
+def rans_encode_rows(v, rows, cols, rows_per_segment, *, v_rs, v_off=0, mu=None, mu_mode=0, mu_rs=0, mu_off=0,
+                     sigma=None, sigma_mode=2, sigma_rs=0, sigma_off=0, sigma_period=1, quant=QUANT_ROUND,
+                     sigma_is_log=False, scale_bound=0.0, streams: Optional[int] = None,
+                     capacity: Optional[int] = None) -> RansStreams:
+    """Raw strided form of ldic_rans_encode (same addressing as likelihood_rows): one bitstream per `rows_per_segment`
+    rows.  Stream-ordered, no synchronisation; read the result with RansStreams.tobytes() / .nbytes()."""
+    _req(v, torch.float32, "v")
+    _req(sigma, torch.float32, "sigma")
+    if rows_per_segment <= 0 or rows % rows_per_segment:
+        raise LdicError("rows must be a multiple of rows_per_segment")
+    segs, seg_elems = rows // rows_per_segment, rows_per_segment * cols
+    S = int(streams) if streams else rans_streams_for(seg_elems)
+    stride = int(capacity) if capacity else int(_L().ldic_rans_max_bytes(seg_elems, S))
+    stride = (stride + 3) & ~3
+    buf = torch.empty((max(segs, 1), stride), dtype=torch.uint8, device=v.device)
+    sizes = torch.zeros(max(segs, 1), dtype=torch.int32, device=v.device)
+    status = torch.zeros(max(segs, 1), dtype=torch.int32, device=v.device)
+    if segs == 0:
+        return RansStreams(buf[:0], sizes[:0], status[:0], S, seg_elems, quant)
+    a = _rans_args(rows, cols, rows_per_segment, v, v_rs, v_off, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs,
+                   sigma_off, sigma_period, quant, sigma_is_log, scale_bound, S)
+    ws = _rans_ws(v.device, segs, seg_elems, S)
+    check(_L().ldic_rans_encode(C.byref(a), _ptr(buf), stride, _ptr(sizes), _ptr(status), _ptr(ws), _stream()), "ldic_rans_encode")
+    return RansStreams(buf[:segs], sizes[:segs], status[:segs], S, seg_elems, quant)
+
+
+def rans_decode_rows(data, rows, cols, rows_per_segment, v_hat, *, v_hat_rs, v_hat_off=0, mu=None, mu_mode=0, mu_rs=0, mu_off=0,
+                     sigma=None, sigma_mode=2, sigma_rs=0, sigma_off=0, sigma_period=1, quant=QUANT_ROUND,
+                     sigma_is_log=False, scale_bound=0.0, streams: Optional[int] = None, check_status: bool = True) -> torch.Tensor:
+    """ldic_rans_decode: `data` is a RansStreams or a list of bytes objects (one per segment); the symbols land in
+    v_hat[row * v_hat_rs + v_hat_off + col].  Returns the per-segment status tensor (raises on a bad stream unless
+    check_status=False)."""
+    _req(v_hat, torch.float32, "v_hat")
+    _req(sigma, torch.float32, "sigma")
+    segs, seg_elems = rows // rows_per_segment, rows_per_segment * cols
+    if isinstance(data, RansStreams):
+        buf, sizes, S = data.buf, data.sizes, data.streams
+        if not buf.is_contiguous():
+            buf = buf.contiguous()
+    else:
+        if len(data) != segs:
+            raise LdicError(f"expected {segs} bitstreams, got {len(data)}")
+        S = int(streams) if streams else rans_streams_for(seg_elems)
+        stride = (max([len(b) for b in data] + [32]) + 3) & ~3
+        host = torch.zeros((segs, stride), dtype=torch.uint8)
+        for i, b in enumerate(data):
+            if len(b):
+                host[i, :len(b)] = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+        buf = host.to(v_hat.device)
+        sizes = torch.tensor([len(b) for b in data], dtype=torch.int32, device=v_hat.device)
+    status = torch.zeros(max(segs, 1), dtype=torch.int32, device=v_hat.device)
+    if segs == 0:
+        return status[:0]
+    a = _rans_args(rows, cols, rows_per_segment, None, 0, 0, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs, sigma_off,
+                   sigma_period, quant, sigma_is_log, scale_bound, S)
+    ws = _rans_ws(v_hat.device, segs, seg_elems, S)
+    check(_L().ldic_rans_decode(C.byref(a), _ptr(buf), buf.stride(0) if segs else 0, _ptr(sizes), _ptr(v_hat), v_hat_rs, v_hat_off,
+                                _ptr(status), _ptr(ws), _stream()), "ldic_rans_decode")
+    if check_status:
+        _rans_status_check(status[:segs], "rans decode")
+    return status[:segs]
+
+
+def _rans_surface(v_shape, sigma, mu):
+    """Addressing of the module-surface forms: (B,C,H,W) contiguous, sigma / mu of the same shape or per channel."""
+    B, Cc, H, W = v_shape
+    per_channel = sigma.numel() == Cc and sigma.numel() != B * Cc * H * W
+    if per_channel:
+        kw = dict(sigma=sigma.reshape(Cc).contiguous(), sigma_mode=3, sigma_period=Cc)
+        if mu is not None:
+            kw.update(mu=mu.reshape(Cc).contiguous(), mu_mode=3)
+        return B * Cc, H * W, Cc, kw
+    n = Cc * H * W
+    kw = dict(sigma=sigma.expand(v_shape).contiguous(), sigma_mode=2, sigma_rs=n)
+    if mu is not None:
+        kw.update(mu=mu.expand(v_shape).contiguous(), mu_mode=2, mu_rs=n)
+    return B, n, 1, kw
+
+
+def rans_encode(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch.Tensor] = None, *, quant: int = QUANT_ROUND,
+                scale_bound: float = 0.0, streams: Optional[int] = None) -> RansStreams:
+    """Entropy-codes a (B,C,H,W) latent, one bitstream per image, with the Gaussian parameters the likelihood ops take
+    (same-shape sigma / mu, or (1,C,1,1) per-channel ones)."""
+    v = _req(v, torch.float32, "v").contiguous()
+    if v.dim() != 4:
+        raise LdicError("expected (B,C,H,W)")
+    rows, cols, rps, kw = _rans_surface(tuple(v.shape), sigma, mu)
+    return rans_encode_rows(v, rows, cols, rps, v_rs=cols, quant=quant, scale_bound=scale_bound, streams=streams, **kw)
+
+
+def rans_decode(data, shape, sigma: torch.Tensor, mu: Optional[torch.Tensor] = None, *, quant: int = QUANT_ROUND,
+                scale_bound: float = 0.0, streams: Optional[int] = None) -> torch.Tensor:
+    """Inverse of rans_encode: the (B,C,H,W) fp32 tensor of symbols (quant 1) or symbols + mu (quant 2)."""
+    shape = tuple(int(d) for d in shape)
+    rows, cols, rps, kw = _rans_surface(shape, sigma, mu)
+    out = torch.empty(shape, dtype=torch.float32, device=sigma.device)
+    rans_decode_rows(data, rows, cols, rps, out, v_hat_rs=cols, quant=quant, scale_bound=scale_bound, streams=streams, **kw)
+    return out
+
+
+def rans_phi_table():
+    """The 2049-entry 24-bit normal-CDF table of the bitstream format (host list)."""
+    n = C.c_int(0)
+    p = _L().ldic_rans_phi_table(C.byref(n))
+    return [int(p[i]) for i in range(n.value)]
 
 
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,121 @@
+"""CPU tests of the rANS restatement (oracle/rans_ref.py) that the CUDA coder is compared with on the GPU:
+known-answer vectors, exact round trips incl. escapes and degenerate parameters, coded size against the estimated rate,
+and the format's normal-CDF table (library copy == committed header == recomputed from math.erfc)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import rans_ref as rr
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _kat():
+    d = np.load(os.path.join(GOLDEN, "rans_kat.npz"))
+    return [{k: d[f"c{i}_{k}"] for k in ("v", "mu", "sigma", "k", "S", "quant", "blob")} for i in range(int(d["cases"]))]
+
+
+def test_known_answer_vectors():
+    for c in _kat():
+        S, quant = int(c["S"]), int(c["quant"])
+        mu = c["mu"] if quant == 1 else np.zeros_like(c["mu"])
+        blob = rr.encode_segment(c["k"], mu, c["sigma"], S, quant)
+        assert blob == c["blob"].tobytes()
+        assert np.array_equal(rr.decode_segment(blob, mu, c["sigma"], S, quant), c["k"])
+
+
+def test_phi_table_three_copies_agree():
+    import ldic_b200
+    T = rr.phi_table()
+    assert T[0] == 0 and T[-1] == 1 << 24 and np.all(np.diff(T) >= 0) and T[1024] == 1 << 23
+    lib_T = np.array(ldic_b200.ops.rans_phi_table(), dtype=np.int64)          # host function, no GPU involved
+    assert np.array_equal(T, lib_T)
+    hdr = open(os.path.join(os.path.dirname(GOLDEN), "..", "learning-driven-image-compression-algorithm_b200", "csrc",
+                            "rans_phi_table.h")).read()
+    vals = np.array([int(x) for x in re.findall(r"(\d+)u", hdr)], dtype=np.int64)
+    assert np.array_equal(T, vals)
+
+
+def test_integer_model_is_a_valid_distribution():
+    rng = np.random.default_rng(0)
+    mu = np.concatenate([rng.standard_normal(200) * 50, [0.5, -0.5, 1e9, -1e9, np.nan, 0.0]]).astype(np.float32)
+    sigma = np.concatenate([np.exp(rng.standard_normal(200) * 3), [0.0, -1.0, np.nan, 1e-30, 1e30, 200.0]]).astype(np.float32)
+    mu_s, sg_s, m, R = rr.make_model(mu, sigma)
+    assert np.all(R >= 3) and np.all(R <= 1023) and np.all(np.isfinite(mu_s)) and np.all(sg_s > 0)
+    for i in range(mu.size):
+        j = np.arange(0, 2 * R[i] + 2)
+        c = rr.cdf_at(mu_s[i:i + 1], sg_s[i:i + 1], m[i:i + 1], R[i:i + 1], j)
+        assert c[0] == 0 and c[-1] == 65536 and np.all(np.diff(c) >= 1), (mu[i], sigma[i])
+
+
+@pytest.mark.parametrize("n,S", [(0, 1), (1, 1), (1, 5), (31, 4), (1000, 1), (1000, 33), (5000, 5000)])
+def test_round_trip_sizes_and_stream_counts(n, S):
+    rng = np.random.default_rng(n * 31 + S)
+    mu = (rng.standard_normal(n) * 4).astype(np.float32)
+    sigma = np.exp(rng.standard_normal(n) * 1.5).astype(np.float32)
+    k = np.rint(mu + sigma * rng.standard_normal(n)).astype(np.int64)
+    blob = rr.encode_segment(k, mu, sigma, S)
+    assert np.array_equal(rr.decode_segment(blob, mu, sigma, S), k)
+    states_off, counts_off, esc_off = rr.layout(S)
+    assert len(blob) >= esc_off and len(blob) <= esc_off + 10 * n
+
+
+def test_round_trip_escapes_and_degenerate_parameters():
+    rng = np.random.default_rng(7)
+    n = 3000
+    mu = (rng.standard_normal(n) * 2).astype(np.float32)
+    sigma = np.exp(rng.standard_normal(n)).astype(np.float32)
+    k = np.rint(mu + sigma * rng.standard_normal(n)).astype(np.int64)
+    k[::97] += 12345                      # far outside every window
+    k[5::131] -= 1 << 29
+    sigma[3::211] = 0.0                   # sanitised to 1e-6
+    sigma[4::223] = np.nan
+    mu[6::199] = np.nan
+    mu[8::251] = 3e9
+    sigma[9::241] = 1e20                  # window capped at R = 1023
+    blob = rr.encode_segment(k, mu, sigma, 16)
+    assert np.array_equal(rr.decode_segment(blob, mu, sigma, 16), k)
+    E = np.frombuffer(blob, dtype="<u4", count=8)[3]
+    assert E >= len(k[::97])
+
+
+def test_coded_size_tracks_the_estimated_rate():
+    """8 * bytes vs sum(-log2 L) with L = Phi((k-mu+.5)/s) - Phi((k-mu-.5)/s) (GaussianModel, model/net.py:272-286)."""
+    from math import erf, sqrt
+    rng = np.random.default_rng(11)
+    n, S = 40000, 20
+    mu = (rng.standard_normal(n) * 3).astype(np.float32)
+    sigma = np.exp(rng.standard_normal(n) * 0.8 + 0.3).astype(np.float32)
+    k = np.rint(mu + sigma * rng.standard_normal(n)).astype(np.int64)
+    Phi = np.vectorize(lambda t: 0.5 * (1.0 + erf(t / sqrt(2.0))))
+    L = Phi((k - mu.astype(np.float64) + 0.5) / sigma) - Phi((k - mu.astype(np.float64) - 0.5) / sigma)
+    est = float(-np.log2(np.maximum(L, 1e-8)).sum())
+    blob = rr.encode_segment(k, mu, sigma, S)
+    E = int(np.frombuffer(blob, dtype="<u4", count=8)[3])
+    overhead = 8 * (rr.HEADER + 6 * S + 8 * E)
+    ideal = rr.ideal_bits(k, mu, sigma)
+    assert abs(ideal - est) < 0.005 * est                      # the 16-bit integer model costs < 0.5 % over the true Gaussian
+    assert 8 * len(blob) - overhead < ideal + 32 * S + 64      # rANS itself: below one state flush per stream over ideal
+    assert 8 * len(blob) < 1.01 * est + overhead
+
+
+def test_corrupt_streams_are_rejected_or_differ():
+    rng = np.random.default_rng(3)
+    n, S = 2000, 8
+    mu = (rng.standard_normal(n) * 2).astype(np.float32)
+    sigma = np.exp(rng.standard_normal(n) * 0.5).astype(np.float32)
+    k = np.rint(mu + sigma * rng.standard_normal(n)).astype(np.int64)
+    blob = bytearray(rr.encode_segment(k, mu, sigma, S))
+    with pytest.raises(ValueError):
+        rr.decode_segment(bytes(blob[:-2]), mu, sigma, S)                    # truncated
+    bad = bytearray(blob); bad[0] ^= 1
+    with pytest.raises(ValueError):
+        rr.decode_segment(bytes(bad), mu, sigma, S)                          # magic
+    bad = bytearray(blob); bad[-1] ^= 0x10
+    try:
+        out = rr.decode_segment(bytes(bad), mu, sigma, S)
+        assert not np.array_equal(out, k)
+    except ValueError:
+        pass
