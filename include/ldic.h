@@ -314,7 +314,7 @@ LDIC_API int ldic_tritplane_likelihood(const float* v, const float* mu, const fl
  * i % streams, at most 65535 symbols per stream; more streams = more parallelism, 6 bytes of header each).
  * quant: 1 = symbols round(v), model N(mu, sigma) (GaussianModel, model/net.py:272-286,:741);
  *        2 = symbols round(v - mu), model N(0, sigma), decoder returns symbol + mu (model/net_unet_ha_hs.py:937).
- * Integer model (16-bit frequencies from a 24-bit normal-CDF table, window of 2 + ceil(6 sigma) integers each side
+ * Integer model (16-bit frequencies from a 24-bit normal-CDF table, window of max(15, 2 + ceil(6 sigma)) integers each side
  * of rint(mu), the rest escaped out of band) and byte layout: header of csrc/rans.cu.
  * encode: out = segments x out_stride bytes (out_stride >= ldic_rans_max_bytes for a guaranteed fit, multiple of 4),
  *   sizes[segment] = bytes written (0 if it did not fit), status[segment] = 0 or a bit set of

@@ -12,7 +12,7 @@
 //          quant 2: k = round(v - mu) coded with N(0, sigma), v^ = k + mu   (GaussianConditional "dequantize",
 //                   model/net_unet_ha_hs.py:937)
 // Integer model of one symbol (16-bit probabilities): window of Nsym = 2R+1 integers around m = rint(mu),
-//   R = min(1023, 2 + ceil(6 sigma));   C(j) = ((Phi24(t_j) * (65536 - Nsym)) >> 24) + j,  t_j = (k_j - 1/2 - mu) * (1 / sigma)  [fp32, each op rounded],
+//   R = min(1023, max(15, 2 + ceil(6 sigma)));   C(j) = ((Phi24(t_j) * (65536 - Nsym)) >> 24) + j,  t_j = (k_j - 1/2 - mu) * (1 / sigma)  [fp32, each op rounded],
 //   C(0) = 0, C(Nsym) = 65536; Phi24 = 24-bit table of the normal CDF (step 1/128, linear interpolation in integers).
 // Every symbol of the window has frequency >= 1; the two edge symbols double as escape markers ("at or beyond the
 // edge") and the escaped values travel out of band as (index, value) pairs.
@@ -65,7 +65,7 @@ __device__ __forceinline__ Model make_model(float mu, float sigma) {
   M.mu = mu; M.inv = __frcp_rn(sigma);
   M.m = (int)rintf(mu);
   const float r = ceilf(__fmul_rn(6.f, sigma));
-  M.R = r >= 1021.f ? 1023 : 2 + (int)r;
+  M.R = r >= 1021.f ? 1023 : max(15, 2 + (int)r);
   return M;
 }
 

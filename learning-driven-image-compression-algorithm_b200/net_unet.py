@@ -629,13 +629,18 @@ class Net(nn.Module):
         return super().load_state_dict(kept, strict=strict, assign=assign)
 
     @torch.no_grad()
-    def rd_forward(self, inputs: torch.Tensor, want_x_hat: bool = False) -> Dict[str, torch.Tensor]:
+    def rd_forward(self, inputs: torch.Tensor, want_x_hat: bool = False, want_bitstreams: bool = False) -> Dict[str, torch.Tensor]:
+        """`want_bitstreams`: also rANS-code every slice's symbols round(y - mu) under N(0, max(scale, 0.11)) -- the very
+        quantiser and model of the GaussianConditional call (:937) -- into one bitstream per image and slice
+        (out["streams"][i], out["slice_params"][i] = (mu, scale) for ops.rans_decode).  The reference only estimates this
+        rate; its z never reaches a likelihood (:882-885) and its h_s consumes encoder-side skip tensors (:892), so the
+        family has no self-contained decoder and only the slice streams are coded."""
         if not inputs.is_cuda:
             raise ops.LdicError("Net runs on CUDA only (no CPU fallback)")
         with torch.cuda.device(inputs.device):
-            return self._rd_forward(inputs.contiguous().float(), want_x_hat)
+            return self._rd_forward(inputs.contiguous().float(), want_x_hat, want_bitstreams)
 
-    def _rd_forward(self, x, want_x_hat):
+    def _rd_forward(self, x, want_x_hat, want_bitstreams=False):
         B, _, H, W = x.shape
         if H % 256 or W % 256:
             # 16x down to y, 4x more inside the syntax model whose Win_noShift_Attention uses 4x4 windows
@@ -654,6 +659,7 @@ class Net(nn.Module):
         y_slices = z3.chunk(S, 1)
         y_hat_slices = []
         bits = torch.zeros(S, dtype=torch.float32, device=x.device)
+        streams, slice_params, dequantised = [], [], []
         for i, y_slice in enumerate(y_slices):                                      # :916-950
             support = y_hat_slices[:self.max_support_slices]
             mean_support = self.atten_mean[i](torch.cat([latent_means] + support, dim=1))
@@ -666,6 +672,12 @@ class Net(nn.Module):
                                                         lik_bound=self.gaussian_conditional.likelihood_bound,
                                                         scale_bound=self.gaussian_conditional.scale_bound,
                                                         want_lik=False, want_vhat=True, sum_out=bits[i:i + 1])
+            if want_bitstreams:
+                mu_c, sc_c = mu.contiguous(), scale.contiguous()
+                streams.append(ops.rans_encode(y_slice.contiguous(), sc_c, mu_c, quant=ops.QUANT_DEQUANT,
+                                               scale_bound=self.gaussian_conditional.scale_bound))
+                slice_params.append((mu_c, sc_c))
+                dequantised.append(y_hat_slice)
             lrp = self.lrp_transforms[i](torch.cat([mean_support, y_hat_slice], dim=1))
             y_hat_slices.append(y_hat_slice + 0.5 * torch.tanh(lrp))                # :947-948
         y_hat = torch.cat(y_hat_slices, dim=1)
@@ -680,6 +692,8 @@ class Net(nn.Module):
         out = {"bits": bits, "sq_err": sq_err, "latents": {"y": z3, "z": z, "y_hat": y_hat, "z3_syntax": z3_syntax}}
         if want_x_hat:
             out["x_hat"] = x_hat
+        if want_bitstreams:
+            out["streams"], out["slice_params"], out["slice_symbols"] = streams, slice_params, dequantised
         return out
 
     def metrics(self, out, H: int, W: int):

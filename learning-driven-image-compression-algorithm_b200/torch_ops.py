@@ -20,11 +20,14 @@ Registered operators
     ldic::conv_forward(x, w_packed, bias_packed, gamma_bf16?, beta_tiled?, kind, cin, cout, cin_pad, cout_pad,
                        act, out_f32, aux0, aux1) -> y                           a1/a4/a5/a10 model/net.py:91-216
     ldic::window_attention(q, k, v, bias, heads, ws, shift) -> out              f2   layers/win_attention.py:38-127
+    ldic::rans_encode(v, sigma, mu?, quant, scale_bound, streams) -> (bytes[B, cap], sizes[B], status[B])
+    ldic::rans_decode(bytes, sizes, sigma, mu?, shape, quant, scale_bound, streams) -> (v_hat, status[B])
+                                                                                f4   (no reference coder: csrc/rans.cu)
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -177,8 +180,45 @@ def _register():
     def _(q, k, v, bias, heads, ws, shift):
         return torch.empty_like(q)
 
+    # ---- f4 ---------------------------------------------------------------------------------------
+    def _rans_capacity(shape, streams):
+        Bb, Cc, Hh, Ww = (int(d) for d in shape)
+        n = Cc * Hh * Ww
+        S = int(streams) if streams > 0 else ops.rans_streams_for(n)
+        return S, (int(_lib.load().ldic_rans_max_bytes(n, S)) + 3) & ~3
+
+    @lib.custom_op(f"{NS}::rans_encode", mutates_args=(), device_types=_dev)
+    def rans_encode(v: Tensor, sigma: Tensor, mu: Optional[Tensor], quant: int, scale_bound: float,
+                    streams: int) -> Tuple[Tensor, Tensor, Tensor]:
+        e = ops.rans_encode(v, sigma, mu, quant=quant, scale_bound=scale_bound, streams=streams if streams > 0 else None)
+        return e.buf, e.sizes, e.status
+
+    @rans_encode.register_fake
+    def _(v, sigma, mu, quant, scale_bound, streams):
+        S, cap = _rans_capacity(v.shape, streams)
+        B = int(v.shape[0])
+        return (v.new_empty((B, cap), dtype=torch.uint8), v.new_empty((B,), dtype=torch.int32),
+                v.new_empty((B,), dtype=torch.int32))
+
+    @lib.custom_op(f"{NS}::rans_decode", mutates_args=(), device_types=_dev)
+    def rans_decode(buf: Tensor, sizes: Tensor, sigma: Tensor, mu: Optional[Tensor], shape: List[int], quant: int,
+                    scale_bound: float, streams: int) -> Tuple[Tensor, Tensor]:
+        n = int(shape[1]) * int(shape[2]) * int(shape[3])
+        S = int(streams) if streams > 0 else ops.rans_streams_for(n)
+        data = ops.RansStreams(buf, sizes, None, S, n, quant)
+        rows, cols, rps, kw = ops._rans_surface(tuple(int(d) for d in shape), sigma, mu)
+        out = torch.empty(tuple(int(d) for d in shape), dtype=torch.float32, device=sigma.device)
+        st = ops.rans_decode_rows(data, rows, cols, rps, out, v_hat_rs=cols, quant=quant, scale_bound=scale_bound,
+                                  check_status=False, **kw)
+        return out, st.clone()
+
+    @rans_decode.register_fake
+    def _(buf, sizes, sigma, mu, shape, quant, scale_bound, streams):
+        return (sigma.new_empty(tuple(int(d) for d in shape), dtype=torch.float32),
+                sigma.new_empty((int(shape[0]),), dtype=torch.int32))
+
     return ("lower_bound", "lower_bound_bwd", "nonneg_reparam", "round_ste", "gdn", "round_likelihood_bpp", "mse_sum",
-            "rd_metrics", "conv_forward", "window_attention")
+            "rd_metrics", "conv_forward", "window_attention", "rans_encode", "rans_decode")
 
 
 REGISTERED = _register()

@@ -35,7 +35,7 @@ _T = phi_table()
 
 
 def make_model(mu: np.ndarray, sigma: np.ndarray):
-    """Sanitised (mu, sigma), window centre m = rint(mu) and half width R = min(1023, 2 + ceil(6 sigma))."""
+    """Sanitised (mu, sigma), window centre m = rint(mu) and half width R = min(1023, max(15, 2 + ceil(6 sigma)))."""
     mu = np.asarray(mu, dtype=f32).copy()
     sigma = np.asarray(sigma, dtype=f32).copy()
     with np.errstate(invalid="ignore"):
@@ -45,7 +45,7 @@ def make_model(mu: np.ndarray, sigma: np.ndarray):
     sigma[sigma > f32(1e6)] = f32(1e6)
     m = np.rint(mu).astype(np.int64)
     r = np.ceil(f32(6.0) * sigma)
-    R = np.where(r >= 1021.0, 1023, 2 + r.astype(np.int64)).astype(np.int64)
+    R = np.where(r >= 1021.0, 1023, np.maximum(15, 2 + r.astype(np.int64))).astype(np.int64)
     return mu, sigma, m, R
 
 

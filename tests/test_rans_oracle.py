@@ -43,7 +43,7 @@ def test_integer_model_is_a_valid_distribution():
     mu = np.concatenate([rng.standard_normal(200) * 50, [0.5, -0.5, 1e9, -1e9, np.nan, 0.0]]).astype(np.float32)
     sigma = np.concatenate([np.exp(rng.standard_normal(200) * 3), [0.0, -1.0, np.nan, 1e-30, 1e30, 200.0]]).astype(np.float32)
     mu_s, sg_s, m, R = rr.make_model(mu, sigma)
-    assert np.all(R >= 3) and np.all(R <= 1023) and np.all(np.isfinite(mu_s)) and np.all(sg_s > 0)
+    assert np.all(R >= 15) and np.all(R <= 1023) and np.all(np.isfinite(mu_s)) and np.all(sg_s > 0)
     for i in range(mu.size):
         j = np.arange(0, 2 * R[i] + 2)
         c = rr.cdf_at(mu_s[i:i + 1], sg_s[i:i + 1], m[i:i + 1], R[i:i + 1], j)
