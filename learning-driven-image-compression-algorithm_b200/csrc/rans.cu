@@ -256,63 +256,67 @@ __device__ __forceinline__ unsigned run_count(unsigned n, unsigned Ls, unsigned 
   return b >= n ? 0u : min(Ls, (unsigned)(n - b));
 }
 
-// One warp = 32 streams.  Their runs lie one after the other in memory, so the warp moves ops in tiles of 32 symbols per
-// stream with coalesced 256-byte reads (lane = position, loop over the streams), transposes them through shared memory,
-// and each lane then walks its own stream's tile backwards; the next tile is already in registers while the dependent
-// chain of the current one runs.  Emitted words take the same road in the other direction.
+// One thread per stream.  With one warp per scheduler every instruction costs its full latency (ncu: ~5.5 cycles per
+// instruction, "wait" stalls), so the kernel is written for instruction count: each lane reads its own run straight from
+// global memory in blocks of 16 ops (two register buffers, the next block in flight under the dependent chain of the
+// current one; a 32-byte sector serves four consecutive ops of a lane) and stores its words straight back (2-byte
+// stores, merged in L2).  Per symbol the chain is compare -> select -> multiply-high -> multiply-subtract -> compare ->
+// add, without a branch: a full block is a straight line of 16 steps, only the ragged top block of a run is guarded.
+constexpr int kEncBlk = 16;
+
+__device__ __forceinline__ void rans_put(uint32_t& x, uint16_t*& wp, const uint2 op) {
+  const uint32_t start = op.x & 0xffffu, freq = op.x >> 16;
+  const bool emit = x >= (freq << 16);
+  if (emit) *wp = (uint16_t)x;
+  wp += emit ? 1 : 0;
+  x = emit ? x >> 16 : x;
+  const uint32_t q = __umulhi(x, op.y);
+  const uint32_t r = x - q * freq;                       // q is floor(x / freq) or one less
+  x = (q << 16) + r + start + (r >= freq ? 65536u - freq : 0u);
+}
+
+__device__ __forceinline__ void rans_load_block(uint2 (&op)[kEncBlk], const uint2* __restrict__ o, int b, unsigned cnt) {
+#pragma unroll
+  for (int u = 0; u < kEncBlk; ++u) {
+    const unsigned p = (unsigned)b * kEncBlk + u;
+    op[u] = (b >= 0 && p < cnt) ? __ldg(o + p) : make_uint2(1u << 16, 0u);
+  }
+}
+
+__device__ __forceinline__ void rans_chain_block(uint32_t& x, uint16_t*& wp, const uint2 (&op)[kEncBlk], int b, unsigned cnt) {
+  if ((unsigned)(b + 1) * kEncBlk <= cnt) {
+#pragma unroll
+    for (int u = kEncBlk - 1; u >= 0; --u) rans_put(x, wp, op[u]);
+  } else {
+#pragma unroll
+    for (int u = kEncBlk - 1; u >= 0; --u)
+      if ((unsigned)b * kEncBlk + u < cnt) rans_put(x, wp, op[u]);
+  }
+}
+
 __global__ void __launch_bounds__(kStreamThreads) k_rans_enc_streams(const uint2* __restrict__ ops, unsigned n, unsigned S,
                                                                      uint16_t* __restrict__ slab, uint32_t* __restrict__ states,
                                                                      uint32_t* __restrict__ wcount) {
-  __shared__ uint2 s_op[32][33];
-  __shared__ uint16_t s_w[32][34];
   const long long seg = blockIdx.y;
-  const int lane = threadIdx.x;
-  const unsigned s0 = blockIdx.x * kStreamThreads, s = s0 + lane;
-  const unsigned Ls = run_length(n, S);
-  const unsigned cnt = s < S ? run_count(n, Ls, s) : 0u;
-  const uint2* o = ops + seg * n;
-  uint16_t* wout = slab + seg * n;
-  const int tiles = (int)((run_count(n, Ls, s0) + 31) / 32);       // stream s0 has the longest run of the warp
+  const unsigned s = blockIdx.x * kStreamThreads + threadIdx.x;
+  if (s >= S) return;
+  const unsigned Ls = run_length(n, S), cnt = run_count(n, Ls, s);
+  const uint2* o = ops + seg * n + (size_t)s * Ls;
+  uint16_t* wrow = slab + seg * n + (size_t)s * Ls;
   uint32_t x = kRansL;
-  unsigned nw = 0;
-  uint2 nxt[32];
-  auto fetch = [&](int t) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const unsigned cj = __shfl_sync(0xffffffffu, cnt, j);
-      const unsigned p = (unsigned)t * 32u + lane;
-      nxt[j] = p < cj ? __ldg(o + (size_t)(s0 + j) * Ls + p) : make_uint2(1u << 16, 0u);
-    }
-  };
-  if (tiles > 0) fetch(tiles - 1);
-  for (int t = tiles - 1; t >= 0; --t) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) s_op[j][lane] = nxt[j];
-    __syncwarp();
-    if (t > 0) fetch(t - 1);
-    unsigned tw = 0;
-#pragma unroll 8
-    for (int u = 31; u >= 0; --u) {
-      if ((unsigned)t * 32u + u < cnt) {
-        const uint2 op = s_op[lane][u];
-        const uint32_t start = op.x & 0xffffu, freq = op.x >> 16;
-        if (x >= (freq << 16)) { s_w[lane][tw++] = (uint16_t)x; x >>= 16; }
-        uint32_t q = __umulhi(x, op.y);
-        uint32_t r = x - q * freq;
-        if (r >= freq) { ++q; r -= freq; }
-        x = (q << 16) + r + start;
-      }
-    }
-    __syncwarp();
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) {
-      const unsigned cj = __shfl_sync(0xffffffffu, tw, j), bj = __shfl_sync(0xffffffffu, nw, j);
-      if ((unsigned)lane < cj) wout[(size_t)(s0 + j) * Ls + bj + lane] = s_w[j][lane];
-    }
-    nw += tw;
-    __syncwarp();
+  uint16_t* wp = wrow;
+  uint2 A[kEncBlk], B[kEncBlk];
+  int b = (int)((cnt + kEncBlk - 1) / kEncBlk) - 1;      // top block (may be ragged)
+  rans_load_block(A, o, b, cnt);
+  for (; b >= 0; b -= 2) {
+    rans_load_block(B, o, b - 1, cnt);
+    rans_chain_block(x, wp, A, b, cnt);
+    if (b - 1 < 0) break;
+    rans_load_block(A, o, b - 2, cnt);
+    rans_chain_block(x, wp, B, b - 1, cnt);
   }
-  if (s < S) { states[seg * S + s] = x; wcount[seg * S + s] = nw; }
+  states[seg * S + s] = x;
+  wcount[seg * S + s] = (uint32_t)(wp - wrow);
 }
 
 // ---- encoder pass 5: scan the word counts, write header / states / counts (one CTA per segment) --------------------

@@ -1,4 +1,6 @@
 # ncu capture of the rANS kernels at the bench size (one encode + one decode at 2048 symbols per stream)
+# usage: bash tools/prof_rans_ncu.sh [kernel regex, default k_rans]
+K=${1:-k_rans}
 mkdir -p gpurun_out
 cat > /tmp/rans_once.py <<'PY'
 import sys, torch
@@ -20,7 +22,7 @@ for _ in range(2):
     ops.rans_decode_rows(enc, P, Cc, h * w, out, v_hat_rs=Cc, **kw)
 torch.cuda.synchronize()
 PY
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_rans -c 18 -o gpurun_out/rans_full -f python /tmp/rans_once.py > gpurun_out/rans_ncu.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:$K -c 18 -o gpurun_out/rans_full -f python /tmp/rans_once.py > gpurun_out/rans_ncu.log 2>&1
 echo "ncu exit $?"
 ncu -i gpurun_out/rans_full.ncu-rep --page raw --csv > gpurun_out/rans_full_raw.csv 2> /dev/null
 ncu -i gpurun_out/rans_full.ncu-rep --page source --csv --kernel-name regex:k_rans_enc_streams > gpurun_out/rans_enc_source.csv 2> /dev/null

@@ -7,8 +7,9 @@ timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "s
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/summary.txt
 timeout 600 python bench.py --steps 20 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/bench_nograph.json 2> gpurun_out/bench_nograph.err; echo "bench nograph exit $?" >> gpurun_out/summary.txt
 timeout 900 python bench.py --config unet --batch 16 --steps 5 --warmup 3 > gpurun_out/bench_unet_b16.json 2> gpurun_out/bench_unet_b16.err; echo "bench unet b16 exit $?" >> gpurun_out/summary.txt
+timeout 600 python bench.py --config codec --steps 10 --warmup 3 > gpurun_out/bench_codec.json 2> gpurun_out/bench_codec.err; echo "bench codec exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -n 3 gpurun_out/pytest_gpu.log
-for f in bench bench_nograph bench_unet_b16; do python - <<PY
+for f in bench bench_nograph bench_unet_b16 bench_codec; do python - <<PY
 import json
 try:
     d=json.loads(open("gpurun_out/$f.json").read().strip().splitlines()[-1])
