@@ -674,22 +674,27 @@ def run_codec(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def step(x):
-        out = net.rd_forward(x)
+    ev = None if args.no_graph else ldic_b200.GraphedEvaluator(net, xs, entropy_code=True)
+
+    def step(k):
+        if ev is not None:                       # one CUDA graph per static input buffer: forward + coder
+            _, _, out = ev(k)
+            return out, out["streams"]
+        out = net.rd_forward(xs[k])
         return out, net.entropy_encode(out)
     with torch.no_grad():
         for i in range(max(args.warmup, 3)):
-            step(xs[i % NBUF])
+            step(i % NBUF)
         sync_all()
         sampler = ClockSampler(local)
         n0 = ops.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            out, enc = step(xs[i % NBUF])
+            out, enc = step(i % NBUF)
         e1.record()
         sync_all()
-        launches = int(ops.launch_count() - n0)
+        launches = int(ops.launch_count() - n0) + (ev.launches_per_replay * args.steps if ev is not None else 0)
         tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         # the entropy-coding stage alone (events around the encoder / decoder calls of the last step's latents)
         lat = out["latents"]
@@ -716,10 +721,9 @@ def run_codec(args):
         d2h = 0
         e0.record()
         for i in range(args.steps):
-            x = host[i % NBUF].to(dev, non_blocking=True)
-            out_, enc_ = step(x)
-            for v in enc_.values():
-                d2h += sum(len(b) for b in v.tobytes()) + 4 * B
+            xs[i % NBUF].copy_(host[i % NBUF], non_blocking=True)
+            out_, enc_ = step(i % NBUF)
+            d2h += sum(len(b) + 8 for v in ops.rans_tobytes(enc_.values()) for b in v)
         e1.record()
         sync_all()
         tt2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -739,7 +743,8 @@ def run_codec(args):
               "vs_baseline": None, "dtype": "bf16 (transforms) + int32 (coder)", "data": "synthetic",
               "config": {"workload": f"SURVEY f4: model/net.py Net forward + rANS coding of z / y / syntax symbols, 768x512, batch {B} "
                                      "per GPU, one bitstream per image and stream", "global_batch": world * B, "height": H, "width": W,
-                         "weights": "deterministic random init (tests/det_weights.py)", "launch_mode": "eager",
+                         "weights": "deterministic random init (tests/det_weights.py)",
+                         "launch_mode": "eager" if ev is None else "CUDA graph replay (forward + coder in one graph per input buffer)",
                          "l2": f"{NBUF} rotating input batches; activations of one step exceed L2",
                          "parity": "UNPINNED against the reference (it has no entropy coder); exact round trip + CPU restatement (tests/test_gpu_rans.py)"},
               "e2e": {"value": world * B * args.steps / (float(tt2.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * H * W,

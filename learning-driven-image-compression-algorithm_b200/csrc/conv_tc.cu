@@ -164,13 +164,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
 __device__ __forceinline__ bool elect_one() {     // true on exactly one lane of a converged warp
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -195,17 +188,10 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// Same, with the two smem descriptors given as 32-bit halves (lo = start address >> 4 | LBO, hi = SBO, version,
-// swizzle mode): the issuing thread only does one 32-bit add per operand per K step.
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16.  The two smem descriptors
+// (K-major, 128-byte swizzled operand tiles: rows of 128 B, 8-row groups `SBO` bytes apart) are given as 32-bit halves
+// (lo = start address >> 4 | LBO, hi = SBO >> 4 | descriptor version 1 << 14 | SWIZZLE_128B 2 << 29): the issuing thread
+// only does one 32-bit add per operand per K step.
 __device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                              uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -219,17 +205,6 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uin
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
-
-// K-major, 128-byte swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t sbo_bytes = 1024) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;          // stride byte offset between 8-row groups (1024 when dense)
-  d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-  return d;
-}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -27,7 +27,7 @@ class GraphedEvaluator:
     overwritten by the next replay of the same graph."""
 
     def __init__(self, net, inputs: Sequence[torch.Tensor], group: Optional[dist.ProcessGroup] = None,
-                 rd_kwargs: Optional[dict] = None):
+                 rd_kwargs: Optional[dict] = None, entropy_code: bool = False):
         if not inputs:
             raise ops.LdicError("GraphedEvaluator needs at least one static input buffer")
         for x in inputs:
@@ -36,6 +36,7 @@ class GraphedEvaluator:
                 raise ops.LdicError("GraphedEvaluator: inputs must be contiguous CUDA fp32 / uint8 (B,3,H,W) tensors of one shape")
         self.net, self.group, self.inputs = net, group, list(inputs)
         self.rd_kwargs = dict(rd_kwargs or {})
+        self.entropy_code = bool(entropy_code)    # also capture Net.entropy_encode: out["streams"] = the rANS bitstreams
         B, _, H, W = inputs[0].shape
         self.chw = 3 * H * W
         _, th, tw, _ = net.test_size
@@ -70,6 +71,8 @@ class GraphedEvaluator:
 
     def _step(self, x) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor]:
         out = self.net.rd_forward(x, **self.rd_kwargs)
+        if self.entropy_code:
+            out["streams"] = self.net.entropy_encode(out)
         packed, v_mse = ops.rd_pack_metrics(out["bits"], out["sq_err"], self.chw)
         return out, packed, v_mse
 

@@ -401,7 +401,7 @@ class Net(nn.Module):
         out = self.rd_forward(inputs)
         with torch.cuda.device(inputs.device):
             enc = self.entropy_encode(out, symbols_per_stream)
-            parts = {k: v.tobytes() for k, v in enc.items()}
+            parts = dict(zip(enc.keys(), ops.rans_tobytes(enc.values())))
         B, _, H, W = inputs.shape
         streams = [{k: parts[k][b] for k in parts} for b in range(B)]
         coded = 8.0 * sum(len(v) for s in streams for v in s.values()) / (B * H * W)

@@ -274,6 +274,34 @@ class RansStreams:
         return [host[i, :n].tobytes() for i, n in enumerate(sizes)]
 
 
+def rans_tobytes(streams) -> list:
+    """[RansStreams, ...] -> [[bytes per segment], ...] with two synchronisations in total: one device-to-host copy of
+    all sizes and status words, then the coded bytes of every stream (only the bytes that were written)."""
+    streams = list(streams)
+    if not streams:
+        return []
+    meta = torch.cat([t.reshape(-1) for e in streams for t in (e.sizes, e.status)]).cpu().tolist()
+    sizes, pos = [], 0
+    for e in streams:
+        k = e.sizes.numel()
+        sz, st = meta[pos:pos + k], meta[pos + k:pos + 2 * k]
+        pos += 2 * k
+        bad = [(i, v) for i, v in enumerate(st) if v]
+        if bad:
+            i, v = bad[0]
+            raise LdicError(f"rans encode: segment {i}: " + ", ".join(t for b, t in RANS_STATUS.items() if v & b))
+        sizes.append(sz)
+    hosts = []
+    for e, sz in zip(streams, sizes):
+        m = max(sz) if sz else 0
+        h = torch.empty((len(sz), m), dtype=torch.uint8, pin_memory=True)
+        if m:
+            h.copy_(e.buf[:, :m], non_blocking=True)
+        hosts.append(h)
+    torch.cuda.current_stream().synchronize()
+    return [[h[i, :n].numpy().tobytes() for i, n in enumerate(sz)] for h, sz in zip(hosts, sizes)]
+
+
 def _rans_args(rows, cols, rows_per_segment, v, v_rs, v_off, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs, sigma_off,
                sigma_period, quant, sigma_is_log, scale_bound, streams):
     a = RansArgs()
