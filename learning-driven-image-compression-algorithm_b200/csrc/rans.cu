@@ -21,8 +21,8 @@
 // fully parallel pass turns (v, mu, sigma) into (start, freq, floor(2^32 / freq)) triples, one thread per stream runs
 // the sequential state recurrence backwards over its run (the division is a multiply-high + one correction), a scan +
 // pack pass concatenates the streams.  Decoding: one WARP per stream -- the lanes fetch the parameters of 32 symbols at
-// a time and, per symbol, evaluate 32 candidates of the integer CDF at once (a 32-ary search: one round for windows of
-// up to 33 integers, at most three).
+// a time and, per symbol, each lane owns one sub-interval of the window (one integer for windows of up to 32, i.e.
+// sigma <= 2.2; wider windows continue with a 32-ary search inside the winning sub-interval, at most two more rounds).
 // Bitstream (little endian), per segment:
 //   u32 magic 'LRA1' | u32 n | u32 S | u32 E | u32 W | u32 quant | u32 0 | u32 0 | u32 state[S] | u16 words_of_stream[S] (+pad to 4)
 //   | {u32 index, i32 value} escape[E] | u16 word[W]   (stream 0's words first, each in decoding order)
@@ -402,25 +402,27 @@ __global__ void __launch_bounds__(1024) k_rans_dec_scan(unsigned n, unsigned S, 
 // ---- decoder pass 2: one warp per stream ---------------------------------------------------------------------------
 constexpr int kDecWarps = 4;
 
-// C(j) for 0 < j < Nsym
-__device__ __forceinline__ uint32_t cdf_inner(int m, int R, float mu, float inv, int j) {
-  const float k = (float)(m - R + j);
-  const float t = __fmul_rn(__fsub_rn(__fsub_rn(k, 0.5f), mu), inv);
-  return (uint32_t)(((unsigned long long)phi24(t) * (uint32_t)(65536 - (2 * R + 1))) >> 24) + (uint32_t)j;
+// C(j) for 0 < j < Nsym from base = (float)(m - R) - 1/2 (exact) and scale = 65536 - Nsym: the same bits as cdf_at
+__device__ __forceinline__ uint32_t cdf_from(float base, float mu, float inv, uint32_t scale, int j) {
+  const float t = __fmul_rn(__fsub_rn(__fadd_rn(base, (float)j), mu), inv);
+  return (uint32_t)(((unsigned long long)phi24(t) * scale) >> 24) + (uint32_t)j;
 }
 
-// The first round of the 32-ary search does not depend on the coder state (candidates j = (lane + 1) step over the whole
-// window), so it is evaluated one symbol ahead, off the dependent chain slot -> compare -> state update -> next slot.
-struct Cand { float mu, inv; int m, R, step; uint32_t cj; };
+// Per symbol the 32 lanes own the 32 sub-intervals [l step, (l+1) step) of the window (step = ceil(Nsym / 32): 1 for
+// windows of up to 32 integers); a lane's cumulative bounds do not depend on the coder state, so they are computed one
+// symbol ahead, off the dependent chain  slot -> "is it mine" ballot -> winner's state update -> shuffle -> next slot.
+// Wider windows (sigma > 2.2) continue with a 32-ary search inside the winner's interval.
+struct Cand { float base, mu, inv; uint32_t scale; int step, nsym; uint32_t c_lo, c_hi; };
 
 __global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_streams(Addr A, unsigned n, unsigned S,
                                                                      const unsigned char* __restrict__ in, long long in_stride,
                                                                      const uint32_t* __restrict__ wcount,
                                                                      const uint32_t* __restrict__ woffs, float* __restrict__ v_hat,
                                                                      long long vh_rs, long long vh_off, uint32_t* __restrict__ status) {
+  __shared__ float4 s_par[kDecWarps][32];
   const long long seg = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const unsigned s = blockIdx.x * kDecWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned s = blockIdx.x * kDecWarps + wib;
   if (s >= S) return;
   const uint32_t c = wcount[seg * S + s];
   if (c == 0xffffffffu) return;                           // header rejected
@@ -435,24 +437,31 @@ __global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_streams(Addr A, uns
   uint32_t x = reinterpret_cast<const uint32_t*>(src + L.states_off)[s];
   uint32_t wnext = wpos < wend ? words[wpos] : 0u;        // the next word, fetched before it is needed
   const unsigned Ls = run_length(n, S), cnt = run_count(n, Ls, s);
-  const unsigned base = s * Ls;
+  const unsigned base_i = s * Ls;
   bool corrupt = false;
   for (unsigned p0 = 0; p0 < cnt; p0 += 32) {
     // each lane fetches the parameters of one of the next 32 symbols (coalesced), then the warp decodes them in order
     const bool valid = p0 + lane < cnt;
     long long row = 0; unsigned col = 0; float mu_raw = 0.f, sigma = 1.f;
-    if (valid) load_params(A, seg, base + p0 + lane, row, col, mu_raw, sigma);
+    if (valid) load_params(A, seg, base_i + p0 + lane, row, col, mu_raw, sigma);
     const Model Mm = make_model(A.quant == 2 ? 0.f : mu_raw, sigma);
-    int my_k = 0;
+    const int my_k0 = Mm.m - Mm.R;
+    __syncwarp();
+    s_par[wib][lane] = make_float4(Mm.mu, Mm.inv, (float)my_k0 - 0.5f, __int_as_float(Mm.R));
+    __syncwarp();
+    int my_j = 0;
     const int todo = min(32u, cnt - p0);
     auto prep = [&](int u) {
       Cand q;
-      q.mu = __shfl_sync(0xffffffffu, Mm.mu, u); q.inv = __shfl_sync(0xffffffffu, Mm.inv, u);
-      q.m = __shfl_sync(0xffffffffu, Mm.m, u); q.R = __shfl_sync(0xffffffffu, Mm.R, u);
-      const int nsym = 2 * q.R + 1;
-      q.step = (nsym + 31) >> 5;
-      const int jl = (lane + 1) * q.step;
-      q.cj = jl < nsym ? cdf_inner(q.m, q.R, q.mu, q.inv, jl) : 0xffffffffu;
+      const float4 P = s_par[wib][u];
+      q.mu = P.x; q.inv = P.y; q.base = P.z;
+      q.nsym = 2 * __float_as_int(P.w) + 1;
+      q.scale = (uint32_t)(65536 - q.nsym);
+      q.step = (q.nsym + 31) >> 5;
+      const int jh = (lane + 1) * q.step;                  // this lane owns [jh - step, min(jh, nsym))
+      q.c_hi = jh < q.nsym ? cdf_from(q.base, q.mu, q.inv, q.scale, jh) : 65536u;
+      q.c_lo = __shfl_up_sync(0xffffffffu, q.c_hi, 1);
+      if (lane == 0) q.c_lo = 0u;
       return q;
     };
     Cand cur = prep(0);
@@ -460,24 +469,31 @@ __global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_streams(Addr A, uns
       Cand nxt = cur;
       if (u + 1 < todo) nxt = prep(u + 1);
       const uint32_t slot = x & 0xffffu;
-      int lo = 0, hi = 2 * cur.R + 1;
-      uint32_t c_lo = 0u, c_hi = 65536u;                  // C(lo) <= slot < C(hi)
-      int step = cur.step;
-      uint32_t cj = cur.cj;
-      while (true) {
-        const int t = __popc(__ballot_sync(0xffffffffu, cj <= slot));        // C is increasing: lanes 0..t-1 (out of range = 2^32-1)
-        const uint32_t c_prev = __shfl_sync(0xffffffffu, cj, max(t - 1, 0));
-        const uint32_t c_next = __shfl_sync(0xffffffffu, cj, min(t, 31));
-        const int jn = lo + (t + 1) * step;
-        if (t > 0) c_lo = c_prev;
-        if (t < 32 && jn < hi) { hi = jn; c_hi = c_next; }
-        lo += t * step;
-        if (hi - lo <= 1) break;
-        step = (hi - lo + 31) >> 5;                       // windows wider than 33: another round inside [lo, hi)
-        const int jl = lo + (lane + 1) * step;
-        cj = jl < hi ? cdf_inner(cur.m, cur.R, cur.mu, cur.inv, jl) : 0xffffffffu;
+      // C is strictly increasing, so exactly one lane has c_lo <= slot < c_hi (empty tail intervals are [65536, 65536))
+      const int w = __ffs(__ballot_sync(0xffffffffu, cur.c_lo <= slot && slot < cur.c_hi)) - 1;
+      int j;
+      if (cur.step == 1) {
+        const uint32_t xw = (cur.c_hi - cur.c_lo) * (x >> 16) + slot - cur.c_lo;
+        x = __shfl_sync(0xffffffffu, xw, w);
+        j = w;
+      } else {
+        int lo = w * cur.step, hi = min(lo + cur.step, cur.nsym);
+        uint32_t c_lo = __shfl_sync(0xffffffffu, cur.c_lo, w), c_hi = __shfl_sync(0xffffffffu, cur.c_hi, w);
+        while (hi - lo > 1) {                              // 32-ary search inside [lo, hi): C(lo) <= slot < C(hi)
+          const int step = (hi - lo + 31) >> 5;
+          const int jl = lo + (lane + 1) * step;
+          const uint32_t cj = jl < hi ? cdf_from(cur.base, cur.mu, cur.inv, cur.scale, jl) : 0xffffffffu;
+          const int t = __popc(__ballot_sync(0xffffffffu, cj <= slot));
+          const uint32_t c_prev = __shfl_sync(0xffffffffu, cj, max(t - 1, 0));
+          const uint32_t c_next = __shfl_sync(0xffffffffu, cj, min(t, 31));
+          const int jn = lo + (t + 1) * step;
+          if (t > 0) c_lo = c_prev;
+          if (t < 32 && jn < hi) { hi = jn; c_hi = c_next; }
+          lo += t * step;
+        }
+        x = (c_hi - c_lo) * (x >> 16) + slot - c_lo;
+        j = lo;
       }
-      x = (c_hi - c_lo) * (x >> 16) + slot - c_lo;
       if (x < kRansL) {
         if (wpos < wend) {
           x = (x << 16) | wnext;
@@ -485,11 +501,11 @@ __global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_streams(Addr A, uns
           wnext = wpos < wend ? words[wpos] : 0u;
         } else { corrupt = true; x |= kRansL; }
       }
-      if (lane == u) my_k = cur.m - cur.R + lo;
+      if (lane == u) my_j = j;
       cur = nxt;
     }
     if (valid) {
-      const float kf = (float)my_k;
+      const float kf = (float)(my_k0 + my_j);
       v_hat[row * vh_rs + vh_off + col] = A.quant == 2 ? __fadd_rn(kf, mu_raw) : kf;
     }
   }
