@@ -720,10 +720,36 @@ def run_codec(args):
         sync_all()
         d2h = 0
         e0.record()
-        for i in range(args.steps):
-            xs[i % NBUF].copy_(host[i % NBUF], non_blocking=True)
-            out_, enc_ = step(i % NBUF)
-            d2h += sum(len(b) + 8 for v in ops.rans_tobytes(enc_.values()) for b in v)
+        # a serving loop: the H2D copy of step i+1 runs on its own stream under step i's kernels, and step i's bitstreams
+        # are read back on a third stream (sizes first, then exactly the coded bytes) while step i+1 runs
+        main = torch.cuda.current_stream(dev)
+        in_stream, out_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        h2d_ev = [torch.cuda.Event() for _ in range(NBUF)]
+        used_ev = [torch.cuda.Event() for _ in range(NBUF)]
+        done_ev = [torch.cuda.Event() for _ in range(NBUF)]
+
+        def prefetch(i):
+            k = i % NBUF
+            with torch.cuda.stream(in_stream):
+                if i >= NBUF:
+                    in_stream.wait_event(used_ev[k])
+                xs[k].copy_(host[k], non_blocking=True)
+                h2d_ev[k].record(in_stream)
+        prefetch(0)
+        pending = None
+        for i in range(args.steps + 1):
+            if i < args.steps:
+                k = i % NBUF
+                if i + 1 < args.steps:
+                    prefetch(i + 1)
+                main.wait_event(h2d_ev[k])
+                enc_k = step(k)[1]
+                used_ev[k].record(main); done_ev[k].record(main)
+            if pending is not None:
+                out_stream.wait_event(done_ev[pending[1]])
+                with torch.cuda.stream(out_stream):
+                    d2h += sum(len(b) + 8 for v in ops.rans_tobytes(pending[0].values()) for b in v)
+            pending = (enc_k, k) if i < args.steps else None
         e1.record()
         sync_all()
         tt2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -89,6 +89,10 @@ def test_strided_nhwc_slices_and_broadcast_modes_vs_oracle(ldic):
         assert blobs[b] == rr.encode_segment(k, np.zeros_like(sg), sg, 7), b
     assert torch.equal(ops.rans_decode(blobs, v.shape, sig_n, streams=7), torch.round(v))
     assert torch.equal(ops.rans_decode(enc, v.shape, sig_n), torch.round(v))       # device-resident streams
+    # batched readback (two synchronisations for any number of streams), optionally on a copy stream
+    enc2 = ops.rans_encode(v, sig_n, streams=3)
+    assert ops.rans_tobytes([enc, enc2]) == [blobs, enc2.tobytes()]
+    assert ops.rans_tobytes([enc, enc2], copy_stream=torch.cuda.Stream()) == [blobs, enc2.tobytes()]
 
 
 def test_dequantize_form_with_scale_bound_vs_oracle(ldic):
