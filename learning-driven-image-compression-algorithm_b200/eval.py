@@ -19,6 +19,7 @@ from typing import Dict, Iterable, List, Sequence, Tuple
 
 import torch
 
+from . import ops
 from .layers import psnr_from_sq_err
 from .net import Net
 
@@ -43,10 +44,36 @@ def load_image(path: str) -> torch.Tensor:
     return torch.from_numpy(a).permute(2, 0, 1).float().div_(255.0)
 
 
+CONTAINER_MAGIC = b"LDIC"
+
+
+def pack_container(h: int, w: int, hp: int, wp: int, streams: Dict[str, bytes]) -> bytes:
+    """One image's bitstreams as a file: 'LDIC' | u32 h, w, hp, wp | u32 len(z), len(y), len(syntax) | z | y | syntax
+    (each part is a self-describing rANS segment of csrc/rans.cu)."""
+    import struct
+    parts = [streams[k] for k in ("z", "y", "syntax")]
+    return CONTAINER_MAGIC + struct.pack("<7I", h, w, hp, wp, *(len(p) for p in parts)) + b"".join(parts)
+
+
+def unpack_container(blob: bytes):
+    """Inverse of pack_container: (h, w, hp, wp, {"z","y","syntax"})."""
+    import struct
+    if blob[:4] != CONTAINER_MAGIC or len(blob) < 32:
+        raise ValueError("not an LDIC container")
+    h, w, hp, wp, nz, ny, ns = struct.unpack_from("<7I", blob, 4)
+    if 32 + nz + ny + ns != len(blob):
+        raise ValueError("LDIC container: sizes do not add up")
+    o = 32
+    return h, w, hp, wp, {"z": blob[o:o + nz], "y": blob[o + nz:o + nz + ny], "syntax": blob[o + nz + ny:]}
+
+
 @torch.no_grad()
-def evaluate_images(net: Net, images: Sequence[torch.Tensor], batch_size: int = 16) -> List[Dict[str, float]]:
+def evaluate_images(net: Net, images: Sequence[torch.Tensor], batch_size: int = 16,
+                    bitstreams: bool = False) -> List[Dict[str, float]]:
     """Per-image {'bpp', 'psnr', 'mse', 'h', 'w'} exactly as the reference forms them for a batch of one
-    (bpp over the unpadded h*w, MSE/PSNR over the padded tensor).  Images are grouped by padded size."""
+    (bpp over the unpadded h*w, MSE/PSNR over the padded tensor).  Images are grouped by padded size.
+    `bitstreams`: also entropy-code every image (Net.entropy_encode) and add 'bpp_coded' = 8 * bytes / (h*w) and
+    'container' (pack_container of its three streams) -- the reference only estimates 'bpp'."""
     dev = next(net.parameters()).device
     groups: Dict[Tuple[int, int], List[int]] = {}
     padded = []
@@ -62,24 +89,41 @@ def evaluate_images(net: Net, images: Sequence[torch.Tensor], batch_size: int = 
             r = net.rd_forward(xb, per_image_bits=True)
             v_mse, _ = psnr_from_sq_err(r["sq_err"], 3 * hp * wp)
             bits = r["bits_per_image"].sum(1).cpu()              # sum of ln L over the three streams, per image
+            coded = None
+            if bitstreams:
+                with torch.cuda.device(dev):
+                    enc = net.entropy_encode(r)
+                    coded = dict(zip(enc.keys(), ops.rans_tobytes(enc.values())))
             for j, i in enumerate(chunk):
                 h, w = images[i].shape[1], images[i].shape[2]
                 mse = float(v_mse[j])
                 out[i] = {"bpp": float(bits[j]) / (-math.log(2) * h * w), "mse": mse,
                           "psnr": 20.0 * math.log10(255.0 / math.sqrt(mse)) if mse > 0 else float("inf"), "h": h, "w": w}
+                if coded is not None:
+                    blob = pack_container(h, w, hp, wp, {k: v[j] for k, v in coded.items()})
+                    out[i]["container"] = blob
+                    out[i]["bpp_coded"] = 8.0 * len(blob) / (h * w)
     return out
 
 
 def val(data_path: str, weight_path: str, is_high: bool = False, post_processing: bool = False, batch_size: int = 16,
-        device: str = "cuda"):
-    """eval_net.py:19 `val` (pre_processing=False branch): prints the per-image line and the averages."""
+        device: str = "cuda", bitstream_dir: str = None):
+    """eval_net.py:19 `val` (pre_processing=False branch): prints the per-image line and the averages.
+    `bitstream_dir`: also write one `<image name>.ldic` file per image and print the coded bpp next to the estimate."""
     paths = sorted(glob.glob(data_path))
     images = [load_image(p) for p in paths]
     net = Net((1, 64, 64, 3), (1, 64, 64, 3), is_high, post_processing).to(device).eval()
     net.load_state_dict(torch.load(weight_path, map_location=device), strict=True)
-    res = evaluate_images(net, images, batch_size)
+    res = evaluate_images(net, images, batch_size, bitstreams=bitstream_dir is not None)
     for p, r in zip(paths, res):
-        print(p, r["bpp"], r["psnr"], r["mse"])
+        if bitstream_dir is not None:
+            import os
+            os.makedirs(bitstream_dir, exist_ok=True)
+            with open(os.path.join(bitstream_dir, os.path.splitext(os.path.basename(p))[0] + ".ldic"), "wb") as f:
+                f.write(r["container"])
+            print(p, r["bpp"], r["psnr"], r["mse"], "coded bpp", r["bpp_coded"])
+        else:
+            print(p, r["bpp"], r["psnr"], r["mse"])
     n = max(len(res), 1)
     print('[WITHOUT PRE-PROCESSING] bpp: %.4f psnr: %.4f  v_mse: %.4f' % (
         sum(r["bpp"] for r in res) / n, sum(r["psnr"] for r in res) / n, sum(r["mse"] for r in res) / n))
@@ -93,5 +137,6 @@ if __name__ == "__main__":
     ap.add_argument("--weights", required=True, help="reference checkpoint (state dict)")
     ap.add_argument("--high", action="store_true")
     ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--bitstreams", default=None, metavar="DIR", help="write one .ldic bitstream file per image into DIR")
     a = ap.parse_args()
-    val(a.data, a.weights, is_high=a.high, batch_size=a.batch)
+    val(a.data, a.weights, is_high=a.high, batch_size=a.batch, bitstream_dir=a.bitstreams)

@@ -293,3 +293,26 @@ def test_unet_family_slice_bitstreams(ldic):
     # -log2(1e-9) = 29.9 bits, the coder 16 (inside the window) or 96 (escape): only the upper bound is tight here (the
     # two-sided 1 % check on symbols that follow their model is test_round_trip_and_rate_at_the_bench_size)
     assert 0.5 * est < coded - 96 * esc < 1.02 * est + 8 * 4 * B * 200, (coded, est, esc)
+
+
+def test_eval_driver_writes_decodable_containers(ldic):
+    """evaluation.evaluate_images(bitstreams=True): per image an LDIC container whose z stream decodes from the file and
+    the model alone (padded size from the header) and whose size gives a coded bpp next to the estimated one."""
+    ev = ldic.evaluation
+    net = ldic.Net((1, 64, 64, 3), (1, 64, 64, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(5), strict=True)
+    g = torch.Generator().manual_seed(8)
+    imgs = [torch.rand(3, 100, 70, generator=g), torch.rand(3, 128, 128, generator=g), torch.rand(3, 100, 70, generator=g)]
+    res = ev.evaluate_images(net, imgs, batch_size=4, bitstreams=True)
+    plain = ev.evaluate_images(net, imgs, batch_size=4)
+    for r, p, img in zip(res, plain, imgs):
+        assert r["bpp"] == p["bpp"] and r["psnr"] == p["psnr"]
+        h, w, hp, wp, streams = ev.unpack_container(r["container"])
+        assert (h, w) == (img.shape[1], img.shape[2]) and hp % 64 == 0 and wp % 64 == 0
+        assert r["bpp_coded"] == 8.0 * len(r["container"]) / (h * w)
+        x = ev.pad_to_multiple(img).cuda()
+        lat = net.rd_forward(x)["latents"]
+        assert torch.equal(net.decode_z([streams["z"]], 1, hp, wp), torch.round(lat["z"]))
+        y_hat = net.decode_y([streams["y"]], lat["ctx"], lat["ctx_rs"], lat["ctx_sig_off"], 1, hp, wp)
+        assert torch.equal(y_hat, torch.round(lat["y"][..., net.M:]))
+        assert 0.5 * r["bpp"] < r["bpp_coded"] < 1.1 * r["bpp"] + 8.0 * 700 / (h * w)

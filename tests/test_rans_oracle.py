@@ -119,3 +119,14 @@ def test_corrupt_streams_are_rejected_or_differ():
         assert not np.array_equal(out, k)
     except ValueError:
         pass
+
+
+def test_container_round_trip_and_rejection():
+    import ldic_b200
+    ev = ldic_b200.evaluation
+    s = {"z": b"\x01\x02\x03", "y": b"", "syntax": bytes(range(40))}
+    blob = ev.pack_container(100, 70, 128, 128, s)
+    assert ev.unpack_container(blob) == (100, 70, 128, 128, s)
+    for bad in (blob[:-1], b"XDIC" + blob[4:], blob[:20]):
+        with pytest.raises(ValueError):
+            ev.unpack_container(bad)
