@@ -285,6 +285,8 @@ typedef struct {
   const float *cg_w0, *cg_b0, *cg_w1, *cg_b1, *cg_w2, *cg_b2;
   float *sm_ds1, *sm_ds2, *ps_ds0, *ps_ds1, *pool_part;
   float *z3, *z3_round, *mu, *sigma, *conv_w;
+  const float* z3_round_in;   /* optional [B,M]: the decoder's path -- conv_generator runs on these (entropy-decoded) symbols
+                                 instead of round(Syntax_Model(y)); z3 / z3_round are still written from y */
 } LdicSyntaxArgs;
 LDIC_API long long ldic_syntax_workspace_elems(int B, int h, int w, int N, int M);
 LDIC_API int ldic_syntax_branch(const LdicSyntaxArgs* args, void* stream);
@@ -318,7 +320,8 @@ LDIC_API int ldic_tritplane_likelihood(const float* v, const float* mu, const fl
  * of rint(mu), the rest escaped out of band) and byte layout: header of csrc/rans.cu.
  * encode: out = segments x out_stride bytes (out_stride >= ldic_rans_max_bytes for a guaranteed fit, multiple of 4),
  *   sizes[segment] = bytes written (0 if it did not fit), status[segment] = 0 or a bit set of
- *   1 = a symbol was NaN / beyond 2^30 (coded as 0), 2 = out_stride too small, 4 = bad header, 8 = corrupt stream.
+ *   1 = a symbol was NaN / beyond 2^30 (coded as 0), 2 = out_stride too small, 4 = bad header, 8 = corrupt stream,
+ *   16 = decode_ranges called out of order / with a range that crosses streams.
  * decode: v_hat[row * v_hat_rs + v_hat_off + col] receives the symbols (fp32); args->v is ignored.
  * workspace: ldic_rans_workspace_bytes(segments, seg_elems, streams) bytes, 256-byte aligned, no initialisation.  */
 typedef struct {
@@ -338,6 +341,19 @@ LDIC_API int ldic_rans_encode(const LdicRansArgs* args, unsigned char* out, long
 LDIC_API int ldic_rans_decode(const LdicRansArgs* args, const unsigned char* in, long long in_stride, const unsigned int* sizes,
                      float* v_hat, long long v_hat_rs, long long v_hat_off, unsigned int* status, void* workspace,
                      void* stream);
+/* Incremental decoding, for decoders whose (mu, sigma) depend on symbols decoded earlier (the causal context model of
+ * model/net.py:289-319 walked along wavefronts, ldic_b200.Net.decompress).  decode_begin validates the segments and
+ * fills `state` (16 bytes per stream and segment: segments * streams * 16 bytes, 16-byte aligned) with the streams'
+ * cursors; every decode_ranges call decodes, in every segment, the nranges symbol ranges [ranges[2j], ranges[2j] +
+ * ranges[2j+1]) (device array of int pairs; count <= 0 = skip).  A range must lie inside ONE stream and start exactly
+ * where that stream stopped (else status bit 16); args->mu / sigma must be valid for the symbols of the ranges at the
+ * time of the call.  v_hat_bf16 (optional) receives a bf16 copy with its own row addressing.  Escaped symbols inside a
+ * range are written in the same call; a stream is checked against its final state when its last symbol is decoded. */
+LDIC_API int ldic_rans_decode_begin(const LdicRansArgs* args, const unsigned char* in, long long in_stride,
+                           const unsigned int* sizes, void* state, unsigned int* status, void* workspace, void* stream);
+LDIC_API int ldic_rans_decode_ranges(const LdicRansArgs* args, const unsigned char* in, long long in_stride, void* state,
+                            const int* ranges, int nranges, float* v_hat, long long v_hat_rs, long long v_hat_off,
+                            void* v_hat_bf16, long long vb_rs, long long vb_off, unsigned int* status, void* stream);
 /* the 24-bit normal-CDF table of the format: T[i] = round(Phi(-8 + i/128) * 2^24), *entries = 2049 (host memory) */
 LDIC_API const unsigned int* ldic_rans_phi_table(int* entries);
 

@@ -78,7 +78,7 @@ class SyntaxArgs(C.Structure):
                     "ps_down0_w", "ps_down0_b", "ps_down1_w", "ps_down1_b", "ps_fc_w", "ps_fc_b",
                     "cg_w0", "cg_b0", "cg_w1", "cg_b1", "cg_w2", "cg_b2",
                     "sm_ds1", "sm_ds2", "ps_ds0", "ps_ds1", "pool_part",
-                    "z3", "z3_round", "mu", "sigma", "conv_w")])
+                    "z3", "z3_round", "mu", "sigma", "conv_w", "z3_round_in")])
 
 
 _SIGS = {
@@ -133,6 +133,11 @@ _SIGS = {
     "ldic_rans_encode": (C.c_int, [C.POINTER(RansArgs), C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldic_rans_decode": (C.c_int, [C.POINTER(RansArgs), C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
                                   C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldic_rans_decode_begin": (C.c_int, [C.POINTER(RansArgs), C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
+    "ldic_rans_decode_ranges": (C.c_int, [C.POINTER(RansArgs), C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong,
+                                         C.c_void_p, C.c_void_p]),
     "ldic_rans_phi_table": (C.POINTER(C.c_uint), [C.POINTER(C.c_int)]),
     "ldic_window_attention_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldic_window_attention_core": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

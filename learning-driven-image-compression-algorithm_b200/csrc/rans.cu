@@ -45,7 +45,7 @@ __device__ const uint32_t c_phi[LDIC_RANS_PHI_N + 1] = {LDIC_RANS_PHI_TABLE};
 const uint32_t h_phi[LDIC_RANS_PHI_N + 1] = {LDIC_RANS_PHI_TABLE};
 
 // status bits (per segment)
-enum { ST_SYMBOL_RANGE = 1, ST_CAPACITY = 2, ST_HEADER = 4, ST_CORRUPT = 8 };
+enum { ST_SYMBOL_RANGE = 1, ST_CAPACITY = 2, ST_HEADER = 4, ST_CORRUPT = 8, ST_ORDER = 16 };
 
 struct Addr {
   const float* v; long long v_rs, v_off;
@@ -414,46 +414,34 @@ __device__ __forceinline__ uint32_t cdf_from(float base, float mu, float inv, ui
 // Wider windows (sigma > 2.2) continue with a 32-ary search inside the winner's interval.
 struct Cand { float base, mu, inv; uint32_t scale; int step, nsym; uint32_t c_lo, c_hi; };
 
-__global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_streams(Addr A, unsigned n, unsigned S,
-                                                                     const unsigned char* __restrict__ in, long long in_stride,
-                                                                     const uint32_t* __restrict__ wcount,
-                                                                     const uint32_t* __restrict__ woffs, float* __restrict__ v_hat,
-                                                                     long long vh_rs, long long vh_off, uint32_t* __restrict__ status) {
-  __shared__ float4 s_par[kDecWarps][32];
-  const long long seg = blockIdx.y;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const unsigned s = blockIdx.x * kDecWarps + wib;
-  if (s >= S) return;
-  const uint32_t c = wcount[seg * S + s];
-  if (c == 0xffffffffu) return;                           // header rejected
-  const unsigned char* src = in + seg * in_stride;
-  const uint32_t* h = reinterpret_cast<const uint32_t*>(src);
-  const Layout L = layout_of(S);
-  const uint32_t W = h[4];
-  const uint16_t* words = reinterpret_cast<const uint16_t*>(src + L.esc_off + 8ull * h[3]);
-  uint32_t wpos = woffs[seg * S + s];
-  const uint32_t wend = wpos + c;
-  if (wend > W) { if (lane == 0) atomicOr(status + seg, (uint32_t)ST_CORRUPT); return; }
-  uint32_t x = reinterpret_cast<const uint32_t*>(src + L.states_off)[s];
-  uint32_t wnext = wpos < wend ? words[wpos] : 0u;        // the next word, fetched before it is needed
-  const unsigned Ls = run_length(n, S), cnt = run_count(n, Ls, s);
-  const unsigned base_i = s * Ls;
-  bool corrupt = false;
-  for (unsigned p0 = 0; p0 < cnt; p0 += 32) {
+// where the decoded symbols go: fp32 (always) and optionally a bf16 copy (the rounded latent image the context model
+// and the synthesis transform read), both with row addressing
+struct DecOut { float* v; long long rs, off; __nv_bfloat16* vb; long long vb_rs, vb_off; };
+
+struct DecCursor { uint32_t x, wpos, wend, wnext; bool corrupt; };
+
+// Decodes positions [p_begin, p_end) of stream s (symbols base_i + p of segment seg); warp-collective.
+__device__ __forceinline__ void decode_run(const Addr& A, long long seg, unsigned base_i, unsigned p_begin, unsigned p_end,
+                                           const uint16_t* __restrict__ words, DecCursor& cur_, const DecOut& O,
+                                           float4* s_par, int lane) {
+  uint32_t x = cur_.x, wpos = cur_.wpos, wnext = cur_.wnext;
+  const uint32_t wend = cur_.wend;
+  bool corrupt = cur_.corrupt;
+  for (unsigned p0 = p_begin; p0 < p_end; p0 += 32) {
     // each lane fetches the parameters of one of the next 32 symbols (coalesced), then the warp decodes them in order
-    const bool valid = p0 + lane < cnt;
+    const bool valid = p0 + lane < p_end;
     long long row = 0; unsigned col = 0; float mu_raw = 0.f, sigma = 1.f;
     if (valid) load_params(A, seg, base_i + p0 + lane, row, col, mu_raw, sigma);
     const Model Mm = make_model(A.quant == 2 ? 0.f : mu_raw, sigma);
     const int my_k0 = Mm.m - Mm.R;
     __syncwarp();
-    s_par[wib][lane] = make_float4(Mm.mu, Mm.inv, (float)my_k0 - 0.5f, __int_as_float(Mm.R));
+    s_par[lane] = make_float4(Mm.mu, Mm.inv, (float)my_k0 - 0.5f, __int_as_float(Mm.R));
     __syncwarp();
     int my_j = 0;
-    const int todo = min(32u, cnt - p0);
+    const int todo = min(32u, p_end - p0);
     auto prep = [&](int u) {
       Cand q;
-      const float4 P = s_par[wib][u];
+      const float4 P = s_par[u];
       q.mu = P.x; q.inv = P.y; q.base = P.z;
       q.nsym = 2 * __float_as_int(P.w) + 1;
       q.scale = (uint32_t)(65536 - q.nsym);
@@ -506,10 +494,114 @@ __global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_streams(Addr A, uns
     }
     if (valid) {
       const float kf = (float)(my_k0 + my_j);
-      v_hat[row * vh_rs + vh_off + col] = A.quant == 2 ? __fadd_rn(kf, mu_raw) : kf;
+      const float vv = A.quant == 2 ? __fadd_rn(kf, mu_raw) : kf;
+      O.v[row * O.rs + O.off + col] = vv;
+      if (O.vb) O.vb[row * O.vb_rs + O.vb_off + col] = __float2bfloat16_rn(vv);
     }
   }
-  if (lane == 0 && (corrupt || x != kRansL || wpos != wend)) atomicOr(status + seg, (uint32_t)ST_CORRUPT);
+  cur_.x = x; cur_.wpos = wpos; cur_.wnext = wnext; cur_.corrupt = corrupt;
+}
+
+__global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_streams(Addr A, unsigned n, unsigned S,
+                                                                     const unsigned char* __restrict__ in, long long in_stride,
+                                                                     const uint32_t* __restrict__ wcount,
+                                                                     const uint32_t* __restrict__ woffs, DecOut O,
+                                                                     uint32_t* __restrict__ status) {
+  __shared__ float4 s_par[kDecWarps][32];
+  const long long seg = blockIdx.y;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned s = blockIdx.x * kDecWarps + wib;
+  if (s >= S) return;
+  const uint32_t c = wcount[seg * S + s];
+  if (c == 0xffffffffu) return;                           // header rejected
+  const unsigned char* src = in + seg * in_stride;
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(src);
+  const Layout L = layout_of(S);
+  const uint32_t W = h[4];
+  const uint16_t* words = reinterpret_cast<const uint16_t*>(src + L.esc_off + 8ull * h[3]);
+  DecCursor cur;
+  cur.wpos = woffs[seg * S + s];
+  cur.wend = cur.wpos + c;
+  if (cur.wend > W) { if (lane == 0) atomicOr(status + seg, (uint32_t)ST_CORRUPT); return; }
+  cur.x = reinterpret_cast<const uint32_t*>(src + L.states_off)[s];
+  cur.wnext = cur.wpos < cur.wend ? words[cur.wpos] : 0u; // the next word, fetched before it is needed
+  cur.corrupt = false;
+  const unsigned Ls = run_length(n, S), cnt = run_count(n, Ls, s);
+  decode_run(A, seg, s * Ls, 0u, cnt, words, cur, O, s_par[wib], lane);
+  if (lane == 0 && (cur.corrupt || cur.x != kRansL || cur.wpos != cur.wend)) atomicOr(status + seg, (uint32_t)ST_CORRUPT);
+}
+
+// ---- incremental decoding (a decoder whose (mu, sigma) depend on symbols decoded earlier, e.g. the causal context
+// model of model/net.py:289-319 walked along wavefronts): the streams' cursors live in a caller-owned state buffer
+// (uint4 {x, next word, end word, next symbol of the run} per stream), k_rans_dec_init fills it from the bitstream,
+// k_rans_dec_ranges decodes one [first, first + count) symbol range per warp (inside ONE stream, continuing exactly
+// where that stream stopped) and applies the escapes that fall into the range.
+__global__ void __launch_bounds__(256) k_rans_dec_init(unsigned S, const unsigned char* __restrict__ in, long long in_stride,
+                                                       const uint32_t* __restrict__ wcount, const uint32_t* __restrict__ woffs,
+                                                       uint4* __restrict__ state, uint32_t* __restrict__ status) {
+  const long long seg = blockIdx.y;
+  const unsigned s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= S) return;
+  const uint32_t c = wcount[seg * S + s];
+  const unsigned char* src = in + seg * in_stride;
+  uint4 st = make_uint4(0u, 0u, 0u, 0xffffffffu);         // next = 2^32-1: unusable
+  if (c != 0xffffffffu) {
+    const uint32_t W = reinterpret_cast<const uint32_t*>(src)[4];
+    const uint32_t wpos = woffs[seg * S + s];
+    if (wpos + c <= W) st = make_uint4(reinterpret_cast<const uint32_t*>(src + layout_of(S).states_off)[s], wpos, wpos + c, 0u);
+    else atomicOr(status + seg, (uint32_t)ST_CORRUPT);
+  }
+  state[seg * S + s] = st;
+}
+
+__global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_ranges(Addr A, unsigned n, unsigned S,
+                                                                    const unsigned char* __restrict__ in, long long in_stride,
+                                                                    uint4* __restrict__ state, const int* __restrict__ ranges,
+                                                                    int nranges, DecOut O, uint32_t* __restrict__ status) {
+  __shared__ float4 s_par[kDecWarps][32];
+  const long long seg = blockIdx.y;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int j = blockIdx.x * kDecWarps + wib;
+  if (j >= nranges) return;
+  const int first = ranges[2 * j], count = ranges[2 * j + 1];
+  if (count <= 0) return;
+  const unsigned Ls = run_length(n, S);
+  const unsigned s = (unsigned)first / Ls, p = (unsigned)first - s * Ls;
+  const unsigned cnt = s < S ? run_count(n, Ls, s) : 0u;
+  if (first < 0 || s >= S || p + (unsigned)count > cnt) { if (lane == 0) atomicOr(status + seg, (uint32_t)ST_ORDER); return; }
+  const uint4 st = state[seg * S + s];
+  if (st.w != p) { if (lane == 0) atomicOr(status + seg, (uint32_t)ST_ORDER); return; }   // not where this stream stopped
+  const unsigned char* src = in + seg * in_stride;
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(src);
+  const uint32_t E = h[3];
+  const Layout L = layout_of(S);
+  const uint16_t* words = reinterpret_cast<const uint16_t*>(src + L.esc_off + 8ull * E);
+  DecCursor cur;
+  cur.x = st.x; cur.wpos = st.y; cur.wend = st.z; cur.corrupt = false;
+  cur.wnext = cur.wpos < cur.wend ? words[cur.wpos] : 0u;
+  decode_run(A, seg, s * Ls, p, p + (unsigned)count, words, cur, O, s_par[wib], lane);
+  const unsigned next = p + (unsigned)count;
+  if (lane == 0) {
+    state[seg * S + s] = make_uint4(cur.x, cur.wpos, cur.wend, next);
+    if (cur.corrupt || (next == cnt && (cur.x != kRansL || cur.wpos != cur.wend))) atomicOr(status + seg, (uint32_t)ST_CORRUPT);
+  }
+  // escapes inside [first, first + count): the list is sorted by index
+  if (E) {
+    const uint32_t* esc = reinterpret_cast<const uint32_t*>(src + L.esc_off);
+    uint32_t lo = 0, hi = E;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (esc[2 * mid] < (uint32_t)first) lo = mid + 1; else hi = mid; }
+    __syncwarp();
+    for (uint32_t e = lo + lane; e < E; e += 32) {
+      const uint32_t i = esc[2 * e];
+      if (i >= (uint32_t)(first + count)) break;
+      long long row; unsigned col; float mu_raw, sigma;
+      load_params(A, seg, i, row, col, mu_raw, sigma);
+      const float kf = (float)(int)esc[2 * e + 1];
+      const float vv = A.quant == 2 ? __fadd_rn(kf, mu_raw) : kf;
+      O.v[row * O.rs + O.off + col] = vv;
+      if (O.vb) O.vb[row * O.vb_rs + O.vb_off + col] = __float2bfloat16_rn(vv);
+    }
+  }
 }
 
 // ---- decoder pass 3: overwrite the escaped symbols ----------------------------------------------------------------
@@ -655,13 +747,47 @@ LDIC_API int ldic_rans_decode(const LdicRansArgs* a, const unsigned char* in, lo
   k_rans_dec_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, in, in_stride, sizes, w.wcount, w.woffs, status);
   if (int r = check_launch("k_rans_dec_scan")) return r;
   if (n == 0) return LDIC_OK;
+  DecOut O; O.v = v_hat; O.rs = v_hat_rs; O.off = v_hat_off; O.vb = nullptr; O.vb_rs = 0; O.vb_off = 0;
   k_rans_dec_streams<<<dim3((S + kDecWarps - 1) / kDecWarps, (unsigned)segs), kDecWarps * 32, 0, st>>>(
-      A, (unsigned)n, S, in, in_stride, w.wcount, w.woffs, v_hat, v_hat_rs, v_hat_off, status);
+      A, (unsigned)n, S, in, in_stride, w.wcount, w.woffs, O, status);
   if (int r = check_launch("k_rans_dec_streams")) return r;
   k_rans_dec_escapes<<<dim3(8, (unsigned)segs), kOpsThreads, 0, st>>>(A, (unsigned)n, S, in, in_stride, w.wcount, v_hat, v_hat_rs,
                                                                      v_hat_off, status);
   if (int r = check_launch("k_rans_dec_escapes")) return r;
   return LDIC_OK;
+}
+
+LDIC_API int ldic_rans_decode_begin(const LdicRansArgs* a, const unsigned char* in, long long in_stride, const unsigned int* sizes,
+                                    void* state, unsigned int* status, void* workspace, void* stream) {
+  Addr A; long long segs, n;
+  if (int r = make_addr(a, false, &A, &segs, &n)) return r;
+  if (!in || !sizes || !status || !workspace || !state) return fail(LDIC_EINVAL, "rans decode_begin: null buffer");
+  if ((in_stride & 3) || ((uintptr_t)in & 3) || ((uintptr_t)workspace & 255) || ((uintptr_t)state & 15))
+    return fail(LDIC_EINVAL, "rans decode_begin: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (segs == 0) return LDIC_OK;
+  const unsigned S = (unsigned)a->streams;
+  Ws w; carve(workspace, segs, n, S, &w);
+  LDIC_CUDA(cudaMemsetAsync(status, 0, 4 * segs, st));
+  k_rans_dec_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, in, in_stride, sizes, w.wcount, w.woffs, status);
+  if (int r = check_launch("k_rans_dec_scan")) return r;
+  k_rans_dec_init<<<dim3((S + 255) / 256, (unsigned)segs), 256, 0, st>>>(S, in, in_stride, w.wcount, w.woffs, (uint4*)state, status);
+  return check_launch("k_rans_dec_init");
+}
+
+LDIC_API int ldic_rans_decode_ranges(const LdicRansArgs* a, const unsigned char* in, long long in_stride, void* state,
+                                     const int* ranges, int nranges, float* v_hat, long long v_hat_rs, long long v_hat_off,
+                                     void* v_hat_bf16, long long vb_rs, long long vb_off, unsigned int* status, void* stream) {
+  Addr A; long long segs, n;
+  if (int r = make_addr(a, false, &A, &segs, &n)) return r;
+  if (!in || !status || !state || !v_hat || (nranges > 0 && !ranges)) return fail(LDIC_EINVAL, "rans decode_ranges: null buffer");
+  if (nranges < 0 || nranges > 65535 * kDecWarps) return fail(LDIC_EINVAL, "rans decode_ranges: nranges");
+  if (segs == 0 || nranges == 0 || n == 0) return LDIC_OK;
+  DecOut O; O.v = v_hat; O.rs = v_hat_rs; O.off = v_hat_off;
+  O.vb = reinterpret_cast<__nv_bfloat16*>(v_hat_bf16); O.vb_rs = vb_rs; O.vb_off = vb_off;
+  k_rans_dec_ranges<<<dim3((nranges + kDecWarps - 1) / kDecWarps, (unsigned)segs), kDecWarps * 32, 0, (cudaStream_t)stream>>>(
+      A, (unsigned)n, (unsigned)a->streams, in, in_stride, (uint4*)state, ranges, nranges, O, status);
+  return check_launch("k_rans_dec_ranges");
 }
 
 }  // extern "C"

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kHeadThreads) k_syntax_head(LdicSyntaxArgs a, 
     a.z3[(long long)b * M + threadIdx.x] = z;
     const float zr = rintf(z);                                      // torch.round, model/net.py:753
     a.z3_round[(long long)b * M + threadIdx.x] = zr;
-    v1[threadIdx.x] = zr;
+    v1[threadIdx.x] = a.z3_round_in ? a.z3_round_in[(long long)b * M + threadIdx.x] : zr;
   }
   __syncthreads();
   // ---- PredictionModel_Syntax (model/net.py:393-413): pooled h2 | ds0 | ds1 -> fc ----

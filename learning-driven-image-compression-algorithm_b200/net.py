@@ -372,6 +372,15 @@ class Net(nn.Module):
         return out
 
     # ---- f4: actual bitstreams (the reference only estimates the rate, model/net.py:856-861) ----------------------------
+    def y_streams(self, h: int, w: int, symbols_per_stream: int = 2048) -> int:
+        """Streams per image of the content latent: every row of the latent is cut into k equal runs (k the smallest
+        divisor of w that brings a run to about `symbols_per_stream` symbols), so no stream crosses a row -- the decoder
+        walks wavefronts (pixel (r, c) at step c + 2r, see `decompress`) and a stream must be consumed in order."""
+        Cc = self.N - self.M
+        limit = min(65535, max(Cc, symbols_per_stream + symbols_per_stream // 4))
+        k = next((d for d in range(1, w + 1) if w % d == 0 and (w // d) * Cc <= limit), w)
+        return h * k
+
     def entropy_encode(self, out: Dict[str, torch.Tensor], symbols_per_stream: int = 2048) -> Dict[str, "ops.RansStreams"]:
         """rANS-codes the three symbol streams of one rd_forward result with the very (mu, sigma) its likelihoods were
         evaluated with: z = round(z) under the per-channel N(0, sigma_z) (:676,:781), y = the N-M content channels of
@@ -389,7 +398,7 @@ class Net(nn.Module):
                                         streams=ops.rans_streams_for(hz * wz * N, sps))
         enc["y"] = ops.rans_encode_rows(y, B * h * w, Cc, h * w, v_rs=N, v_off=M, mu=lat["ctx"], mu_mode=2, mu_rs=lat["ctx_rs"],
                                         sigma=lat["ctx"], sigma_mode=2, sigma_rs=lat["ctx_rs"], sigma_off=lat["ctx_sig_off"],
-                                        sigma_is_log=True, streams=ops.rans_streams_for(h * w * Cc, sps))
+                                        sigma_is_log=True, streams=self.y_streams(h, w, sps))
         enc["syntax"] = ops.rans_encode(lat["z3_syntax"].reshape(B, -1, 1, 1), lat["syn_first"].reshape(B, -1, 1, 1),
                                         lat["syn_second"].reshape(B, -1, 1, 1), streams=1)
         return enc
@@ -432,8 +441,66 @@ class Net(nn.Module):
             y_hat = torch.empty(batch, h, w, Cc, dtype=torch.float32, device=ctx.device)
             ops.rans_decode_rows(y_streams, batch * h * w, Cc, h * w, y_hat, v_hat_rs=Cc, mu=ctx, mu_mode=2, mu_rs=ctx_rs,
                                  sigma=ctx, sigma_mode=2, sigma_rs=ctx_rs, sigma_off=ctx_sig_off, sigma_is_log=True,
-                                 streams=ops.rans_streams_for(h * w * Cc, symbols_per_stream))
+                                 streams=self.y_streams(h, w, symbols_per_stream))
         return y_hat
+
+    @torch.no_grad()
+    def decompress(self, streams, H: int, W: int, symbols_per_stream: int = 2048, want_latents: bool = False):
+        """The decoder: per-image {"z","y","syntax"} byte strings (Net.compress) -> x_hat (B,3,H,W), bit-identical to the
+        encoder's reconstruction (rd_forward(want_x_hat=True)["x_hat"]), from the bytes and the model alone.
+          z       from its stream under the factorised prior; h2 = h_s(z^)                       (model/net.py:676-681)
+          syntax  prior from h2 (PredictionModel_Syntax, :789), symbols -> conv_generator (:805)
+          y       the context model is causal over y^ (BlockSample masked=True, :219-242: pixel (r, c) sees rows r-3..r-1
+                  at columns c-2..c+1 and (r, c-2), (r, c-1)), so pixels are decoded along wavefronts t = c + 2r: at every
+                  step the context model runs on the partially decoded latent (the very kernels of the encoder, hence
+                  the very (mu, sigma)) and the rANS decoder advances the streams of the pixels on the wavefront.
+          x_hat   g_s + IGDN + batch_conv (:800-811)
+        This is the straightforward schedule -- w + 2(h-1) full passes of the context model (110 for 768x512) -- written
+        for exactness, not speed."""
+        B = len(streams)
+        N, M, Cc = self.N, self.M, self.N - self.M
+        if H % 64 or W % 64:
+            raise ops.LdicError("H and W must be multiples of 64")
+        h, w = H // 16, W // 16
+        dev = self.z2_sigma.device
+        with torch.cuda.device(dev):
+            z_hat = self.decode_z([s["z"] for s in streams], B, H, W, symbols_per_stream)
+            h2 = self.hs_model.forward_nhwc(z_hat.to(torch.bfloat16))
+            no_y = torch.zeros(B, h, w, N, dtype=torch.float32, device=dev)
+            mods = (self.syntax_model, self.prediction_model_syntax, self.conv_weights_gen)
+            _, _, syn_first, syn_second, _ = ops.syntax_branch(no_y, h2, M, *mods)          # the prior needs h2 only
+            z3r = ops.rans_decode([s["syntax"] for s in streams], (B, M, 1, 1), syn_first.reshape(B, -1, 1, 1),
+                                  syn_second.reshape(B, -1, 1, 1), streams=1)
+            conv_w = ops.syntax_branch(no_y, h2, M, *mods, z3_round_in=z3r)[4]
+            # wavefront schedule: step t decodes pixel (r, t - 2r) of every row r where that column exists
+            T = w + 2 * (h - 1)
+            table = torch.zeros(T, h, 2, dtype=torch.int32)
+            for t in range(T):
+                for r in range(max(0, (t - w + 2) // 2), min(h - 1, t // 2) + 1):
+                    table[t, r, 0] = (r * w + (t - 2 * r)) * Cc
+                    table[t, r, 1] = Cc
+            table = table.to(dev)
+            y_hat = torch.zeros(B, h, w, Cc, dtype=torch.float32, device=dev)
+            y_hat_bf16 = torch.zeros(B, h, w, N, dtype=torch.bfloat16, device=dev)
+            dec = ops.RansDecoder([s["y"] for s in streams], B * h * w, Cc, h * w,
+                                  streams=self.y_streams(h, w, symbols_per_stream), device=dev)
+            for t in range(T):
+                r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
+                ctx = self.prediction_model.raw_tc(y_hat_bf16, h2, M)
+                rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
+                dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=y_hat_bf16, vb_rs=N, vb_off=M,
+                           mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2, sigma_rs=rs, sigma_off=so, sigma_is_log=True)
+            dec.finish()
+            body = self.s_model.forward_nhwc_body(y_hat_bf16)
+            blank = torch.zeros(B, 3, H, W, dtype=torch.uint8, device=dev)
+            if self.s_model.has_fused_tail():
+                _, x_hat, _ = self.s_model.fused_tail(body, blank, conv_w.reshape(B, 3, M), want_x_tilde=True)
+            else:
+                _, x_hat = ops.syntax_conv_mse(ops.u8_to_f32_pm1(blank), self.s_model.plan()[-1](body), conv_w.reshape(B, 3, M),
+                                               want_x_tilde=True)
+        if want_latents:
+            return x_hat, {"z_hat": z_hat, "h2": h2, "y_hat": y_hat, "z3_round": z3r, "conv_w": conv_w}
+        return x_hat
 
     def metrics(self, out: Dict[str, torch.Tensor], batch: int, H: int, W: int):
         """bpp / v_mse / v_psnr exactly as model/net.py:856-869 forms them."""

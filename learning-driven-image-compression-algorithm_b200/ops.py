@@ -232,7 +232,8 @@ def gaussian_likelihood(v: torch.Tensor, sigma: torch.Tensor, mu: Optional[torch
 # --------------------------------------------------------------------------------------
 # f4: rANS entropy coder (builder-defined extension: the reference only estimates the rate, see include/ldic.h)
 # --------------------------------------------------------------------------------------
-RANS_STATUS = {1: "a symbol was NaN or beyond 2^30", 2: "output capacity too small", 4: "bad header", 8: "corrupt stream"}
+RANS_STATUS = {1: "a symbol was NaN or beyond 2^30", 2: "output capacity too small", 4: "bad header", 8: "corrupt stream",
+               16: "incremental decode out of order"}
 
 
 def rans_streams_for(seg_elems: int, symbols_per_stream: int = 2048) -> int:
@@ -409,6 +410,62 @@ def rans_decode_rows(data, rows, cols, rows_per_segment, v_hat, *, v_hat_rs, v_h
     if check_status:
         _rans_status_check(status[:segs], "rans decode")
     return status[:segs]
+
+
+class RansDecoder:
+    """Incremental decoding (ldic_rans_decode_begin / _ranges): for decoders whose (mu, sigma) depend on symbols decoded
+    earlier.  `dec = RansDecoder(data, rows, cols, rows_per_segment, streams=S, quant=...)`, then per step
+    `dec.decode(ranges, nranges, v_hat, v_hat_rs=..., mu=..., sigma=..., ...)` with `ranges` an int32 device tensor of
+    (first symbol, count) pairs (segment-relative); every range must continue the stream it lies in.  `dec.finish()`
+    synchronises and raises on a corrupt or mis-ordered decode."""
+
+    def __init__(self, data, rows, cols, rows_per_segment, *, streams: int, quant: int = QUANT_ROUND, device=None):
+        segs, seg_elems = rows // rows_per_segment, rows_per_segment * cols
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        if isinstance(data, RansStreams):
+            buf, sizes = data.buf, data.sizes
+            if not buf.is_contiguous():
+                buf = buf.contiguous()
+        else:
+            if len(data) != segs:
+                raise LdicError(f"expected {segs} bitstreams, got {len(data)}")
+            stride = (max([len(b) for b in data] + [32]) + 3) & ~3
+            host = torch.zeros((segs, stride), dtype=torch.uint8)
+            for i, b in enumerate(data):
+                if len(b):
+                    host[i, :len(b)] = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+            buf = host.to(dev)
+            sizes = torch.tensor([len(b) for b in data], dtype=torch.int32, device=dev)
+        self.buf, self.sizes, self.S, self.quant = buf, sizes, int(streams), quant
+        self.rows, self.cols, self.rps, self.segs = rows, cols, rows_per_segment, segs
+        self.status = torch.zeros(max(segs, 1), dtype=torch.int32, device=dev)
+        self.state = torch.empty((max(segs, 1), self.S, 4), dtype=torch.int32, device=dev)
+        ones = torch.ones(1, dtype=torch.float32, device=dev)             # begin only needs the geometry of the problem
+        a = _rans_args(rows, cols, rows_per_segment, None, 0, 0, None, 0, 0, 0, ones, 3, 0, 0, 1, quant, False, 0.0, self.S)
+        ws = _rans_ws(dev, segs, seg_elems, self.S)
+        if segs:
+            check(_L().ldic_rans_decode_begin(C.byref(a), _ptr(buf), buf.stride(0), _ptr(sizes), _ptr(self.state),
+                                              _ptr(self.status), _ptr(ws), _stream()), "ldic_rans_decode_begin")
+
+    def decode(self, ranges: torch.Tensor, nranges: int, v_hat: torch.Tensor, *, v_hat_rs, v_hat_off=0, v_hat_bf16=None,
+               vb_rs=0, vb_off=0, mu=None, mu_mode=0, mu_rs=0, mu_off=0, sigma=None, sigma_mode=2, sigma_rs=0, sigma_off=0,
+               sigma_period=1, sigma_is_log=False, scale_bound=0.0):
+        _req(v_hat, torch.float32, "v_hat")
+        _req(sigma, torch.float32, "sigma")
+        _req(ranges, torch.int32, "ranges")
+        if v_hat_bf16 is not None:
+            _req(v_hat_bf16, torch.bfloat16, "v_hat_bf16")
+        a = _rans_args(self.rows, self.cols, self.rps, None, 0, 0, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs,
+                       sigma_off, sigma_period, self.quant, sigma_is_log, scale_bound, self.S)
+        if self.segs and nranges:
+            check(_L().ldic_rans_decode_ranges(C.byref(a), _ptr(self.buf), self.buf.stride(0), _ptr(self.state), _ptr(ranges),
+                                               int(nranges), _ptr(v_hat), v_hat_rs, v_hat_off, _ptr(v_hat_bf16), vb_rs, vb_off,
+                                               _ptr(self.status), _stream()), "ldic_rans_decode_ranges")
+
+    def finish(self):
+        _rans_status_check(self.status[:self.segs], "rans incremental decode")
+        st = self.state[:self.segs].cpu()
+        return st
 
 
 def _rans_surface(v_shape, sigma, mu):
@@ -848,9 +905,11 @@ def gate_residual_nhwc_to_nchw(a_nhwc: torch.Tensor, b_nhwc: torch.Tensor, x_nch
     return y
 
 
-def syntax_branch(y: torch.Tensor, h2: torch.Tensor, M: int, syntax_model, prediction_model_syntax, conv_weights_gen):
+def syntax_branch(y: torch.Tensor, h2: torch.Tensor, M: int, syntax_model, prediction_model_syntax, conv_weights_gen,
+                  z3_round_in: Optional[torch.Tensor] = None):
     """The syntax side branch on libldic_b200 (ldic_syntax_branch): y, h2 are NHWC fp32 [B,h,w,N].
-    Returns (z3 [B,M,1,1], z3_round, mu, sigma [B,M,1,1], conv_w [B,3,M,1,1])."""
+    Returns (z3 [B,M,1,1], z3_round, mu, sigma [B,M,1,1], conv_w [B,3,M,1,1]).  `z3_round_in` ([B,M] fp32, the decoder's
+    path): conv_w is generated from these symbols instead of round(Syntax_Model(y))."""
     _req(y, torch.float32, "y"); _req(h2, torch.float32, "h2")
     if y.shape != h2.shape or not y.is_contiguous() or not h2.is_contiguous():
         raise LdicError("syntax_branch: y and h2 must be contiguous NHWC fp32 tensors of the same shape")
@@ -884,6 +943,10 @@ def syntax_branch(y: torch.Tensor, h2: torch.Tensor, M: int, syntax_model, predi
     a.sm_ds1, a.sm_ds2, a.ps_ds0, a.ps_ds1, a.pool_part = _ptr(ds1), _ptr(ds2), _ptr(p0), _ptr(p1), _ptr(part)
     z3, z3r, mu, sg, cw = f(B, M, 1, 1), f(B, M, 1, 1), f(B, M, 1, 1), f(B, M, 1, 1), f(B, 3, M, 1, 1)
     a.z3, a.z3_round, a.mu, a.sigma, a.conv_w = _ptr(z3), _ptr(z3r), _ptr(mu), _ptr(sg), _ptr(cw)
+    if z3_round_in is not None:
+        z3_round_in = _req(z3_round_in, torch.float32, "z3_round_in").reshape(B, M).contiguous()
+        keep.append(z3_round_in)
+    a.z3_round_in = _ptr(z3_round_in)
     check(_L().ldic_syntax_branch(C.byref(a), _stream()), "ldic_syntax_branch")
     return z3, z3r, mu, sg, cw
 

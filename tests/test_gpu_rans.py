@@ -316,3 +316,59 @@ def test_eval_driver_writes_decodable_containers(ldic):
         y_hat = net.decode_y([streams["y"]], lat["ctx"], lat["ctx_rs"], lat["ctx_sig_off"], 1, hp, wp)
         assert torch.equal(y_hat, torch.round(lat["y"][..., net.M:]))
         assert 0.5 * r["bpp"] < r["bpp_coded"] < 1.1 * r["bpp"] + 8.0 * 700 / (h * w)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 128, 192), (1, 256, 256)])
+def test_net_decompress_reproduces_the_encoder_reconstruction(ldic, B, H, W):
+    """The whole codec: x -> Net.compress -> bytes -> Net.decompress -> x_hat, from the bytes and the model alone (the
+    causal context model walked along wavefronts with the encoder's own kernels).  The reconstruction and every decoded
+    latent are bit-identical to the encoder's."""
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), False, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(7), strict=True)
+    x = dw.make_input(7, B, H, W).cuda()
+    streams, info = net.compress(x)
+    enc = net.rd_forward(x, want_x_hat=True)
+    x_hat, lat = net.decompress(streams, H, W, want_latents=True)
+    assert torch.equal(lat["z_hat"], torch.round(enc["latents"]["z"]))
+    assert torch.equal(lat["h2"], enc["latents"]["h2"])
+    assert torch.equal(lat["y_hat"], torch.round(enc["latents"]["y"][..., net.M:]))
+    assert torch.equal(lat["conv_w"].reshape(-1), enc["latents"]["conv_w"].reshape(-1))
+    assert torch.equal(x_hat, enc["x_hat"])
+    # a damaged content stream is detected, not silently decoded
+    bad = [dict(s) for s in streams]
+    yb = bytearray(bad[0]["y"]); yb[len(yb) // 2] ^= 0x5A; bad[0]["y"] = bytes(yb)
+    try:
+        x_bad = net.decompress(bad, H, W)
+        assert not torch.equal(x_bad, enc["x_hat"])
+    except ldic.LdicError:
+        pass
+
+
+def test_incremental_decode_order_is_enforced(ldic):
+    ops = ldic.ops
+    g = torch.Generator().manual_seed(6)
+    n, S = 4000, 4
+    mu = (torch.randn(n, generator=g) * 2).cuda()
+    sigma = torch.exp(torch.randn(n, generator=g) * 0.5).cuda()
+    v = (mu + sigma * torch.randn(n, generator=g).cuda()).contiguous()
+    v[10] += 5000.0                                                    # one escape inside the first range
+    blob = _flat_encode(ops, v, mu, sigma, S).tobytes()
+    kw = dict(mu=mu, mu_mode=2, mu_rs=n, sigma=sigma, sigma_mode=2, sigma_rs=n)
+    out = torch.zeros(n, device="cuda")
+    outb = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+    dec = ops.RansDecoder(blob, 1, n, 1, streams=S)
+    # four streams of 1000 symbols, decoded in interleaved pieces
+    pieces = [(0, 300), (1000, 1000), (300, 700), (2000, 1), (2001, 999), (3000, 1000)]
+    for first, count in pieces:
+        r = torch.tensor([[first, count]], dtype=torch.int32, device="cuda")
+        dec.decode(r, 1, out, v_hat_rs=n, v_hat_bf16=outb, vb_rs=n, **kw)
+    dec.finish()
+    assert torch.equal(out, torch.round(v)) and torch.equal(outb.float(), torch.round(v).to(torch.bfloat16).float())
+    dec = ops.RansDecoder(blob, 1, n, 1, streams=S)
+    dec.decode(torch.tensor([[300, 100]], dtype=torch.int32, device="cuda"), 1, out, v_hat_rs=n, **kw)   # skips [0, 300)
+    with pytest.raises(ldic.LdicError, match="out of order"):
+        dec.finish()
+    dec = ops.RansDecoder(blob, 1, n, 1, streams=S)
+    dec.decode(torch.tensor([[900, 200]], dtype=torch.int32, device="cuda"), 1, out, v_hat_rs=n, **kw)   # crosses streams
+    with pytest.raises(ldic.LdicError, match="out of order"):
+        dec.finish()
