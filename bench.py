@@ -715,6 +715,17 @@ def run_codec(args):
         round_trip = round_trip and bool(torch.equal(z_hat, torch.round(lat["z"])))
         sizes = {k: v.nbytes() for k, v in enc.items()}
         coded_bits = 8.0 * sum(sum(v) for v in sizes.values())
+        # the whole decoder (bytes -> x_hat, context model walked along wavefronts) on this step's bitstreams
+        parts = dict(zip(enc.keys(), ops.rans_tobytes(enc.values())))
+        per_image = [{k: parts[k][b] for k in parts} for b in range(B)]
+        x_ref = net.rd_forward(xs[(args.steps - 1) % NBUF], want_x_hat=True)["x_hat"]
+        net.decompress(per_image[:1], H, W)                       # warm-up (plans of the B=1 shapes are not needed later)
+        torch.cuda.synchronize(dev)
+        t_dec = time.perf_counter()
+        x_dec = net.decompress(per_image, H, W)
+        torch.cuda.synchronize(dev)
+        t_dec = time.perf_counter() - t_dec
+        decoder_exact = bool(torch.equal(x_dec, x_ref))
         est_bits = float(out["bits"].double().sum().item()) / -math.log(2.0)
         # end to end: uint8 host images in, bitstream bytes out (sizes first, then exactly the coded bytes)
         sync_all()
@@ -782,6 +793,10 @@ def run_codec(args):
                            "note": "latency bound, not HBM bound: the rANS state recurrence is sequential within a stream "
                                    "(2048 symbols per stream by default; ~300 cycles per symbol on one thread)",
                            "peak_source": f"{peak_src} hbm_gbs"},
+              "decoder": {"images_per_s": B / t_dec, "ms_per_batch": t_dec * 1e3, "x_hat_bit_identical_to_encoder": decoder_exact,
+                          "note": "Net.decompress: bytes -> x_hat from the bitstreams and the model alone; the causal context "
+                                  "model is re-run on the partially decoded latent at each of the w + 2(h-1) wavefront steps "
+                                  "(written for exactness, not speed); rank 0's batch, wall clock"},
               "parity": {"round_trip_exact": round_trip, "bpp_coded": coded_bits / (B * H * W), "bpp_estimated": est_bits / (B * H * W),
                          "bytes_per_image": {k: sum(v) / B for k, v in sizes.items()}}})
     if world > 1:
