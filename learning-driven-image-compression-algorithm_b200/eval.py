@@ -106,6 +106,26 @@ def evaluate_images(net: Net, images: Sequence[torch.Tensor], batch_size: int = 
     return out
 
 
+@torch.no_grad()
+def decode_containers(net: Net, blobs: Sequence[bytes], batch_size: int = 16) -> List[torch.Tensor]:
+    """The decoder side of `evaluate_images(bitstreams=True)`: LDIC containers -> (3,h,w) images in [0,1] (the padded
+    reconstruction of Net.decompress cropped to the unpadded size, mapped back from [-1,1] and clamped).  Containers of
+    one padded size are decoded together."""
+    metas = [unpack_container(b) for b in blobs]
+    groups: Dict[Tuple[int, int], List[int]] = {}
+    for i, (_, _, hp, wp, _) in enumerate(metas):
+        groups.setdefault((hp, wp), []).append(i)
+    out: List[torch.Tensor] = [None] * len(blobs)               # type: ignore
+    for (hp, wp), idx in groups.items():
+        for k in range(0, len(idx), batch_size):
+            chunk = idx[k:k + batch_size]
+            x_hat = net.decompress([metas[i][4] for i in chunk], hp, wp)
+            for j, i in enumerate(chunk):
+                h, w = metas[i][0], metas[i][1]
+                out[i] = ((x_hat[j, :, :h, :w] + 1.0) * 0.5).clamp_(0.0, 1.0)
+    return out
+
+
 def val(data_path: str, weight_path: str, is_high: bool = False, post_processing: bool = False, batch_size: int = 16,
         device: str = "cuda", bitstream_dir: str = None):
     """eval_net.py:19 `val` (pre_processing=False branch): prints the per-image line and the averages.
@@ -138,5 +158,19 @@ if __name__ == "__main__":
     ap.add_argument("--high", action="store_true")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--bitstreams", default=None, metavar="DIR", help="write one .ldic bitstream file per image into DIR")
+    ap.add_argument("--decode", default=None, metavar="DIR",
+                    help="decoder mode: --data is a glob of .ldic files, reconstructions are written as PNG files into DIR")
     a = ap.parse_args()
-    val(a.data, a.weights, is_high=a.high, batch_size=a.batch, bitstream_dir=a.bitstreams)
+    if a.decode is not None:
+        import os
+        from PIL import Image
+        paths = sorted(glob.glob(a.data))
+        net = Net((1, 64, 64, 3), (1, 64, 64, 3), a.high, False).to("cuda").eval()
+        net.load_state_dict(torch.load(a.weights, map_location="cuda"), strict=True)
+        os.makedirs(a.decode, exist_ok=True)
+        for p, img in zip(paths, decode_containers(net, [open(p, "rb").read() for p in paths], a.batch)):
+            arr = (img.permute(1, 2, 0) * 255.0).round().to(torch.uint8).cpu().numpy()
+            Image.fromarray(arr).save(os.path.join(a.decode, os.path.splitext(os.path.basename(p))[0] + ".png"))
+            print(p, "->", arr.shape)
+    else:
+        val(a.data, a.weights, is_high=a.high, batch_size=a.batch, bitstream_dir=a.bitstreams)

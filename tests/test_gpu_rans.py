@@ -316,6 +316,12 @@ def test_eval_driver_writes_decodable_containers(ldic):
         y_hat = net.decode_y([streams["y"]], lat["ctx"], lat["ctx_rs"], lat["ctx_sig_off"], 1, hp, wp)
         assert torch.equal(y_hat, torch.round(lat["y"][..., net.M:]))
         assert 0.5 * r["bpp"] < r["bpp_coded"] < 1.1 * r["bpp"] + 8.0 * 700 / (h * w)
+    # and back: the files alone give the reconstruction of the encoder, cropped to the unpadded size
+    dec = ev.decode_containers(net, [r["container"] for r in res], batch_size=2)
+    for img, d in zip(imgs, dec):
+        x = ev.pad_to_multiple(img).cuda()
+        ref = net.rd_forward(x, want_x_hat=True)["x_hat"][0, :, :img.shape[1], :img.shape[2]]
+        assert d.shape == img.shape and torch.equal(d, ((ref + 1.0) * 0.5).clamp(0.0, 1.0))
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 128, 192), (1, 256, 256)])
