@@ -180,7 +180,9 @@ enum {
   /* Context model PredictionModel_Context (model/net.py:289-319).  The reference materialises one
    * 4x4 patch per latent position with a one-hot 7x7 conv (BlockSample, :219-242); here the first
    * conv gathers the patch cells straight from the latent images by TMA, 16 jobs = 16 patch cells. */
-  LDIC_CTX_CONV1 = 8,  /* x [B,h,w, round(y)(N) | h2(N)] bf16 -> [B*h*w,4,4,N]; aux0=N, aux1=M; Conv2d(2N-M,N,3,1,1) :295 */
+  LDIC_CTX_CONV1 = 8,  /* x [B,h,w, round(y)(N) | h2(N)] bf16 -> [B*h*w,4,4,N]; aux0=N, aux1=M; Conv2d(2N-M,N,3,1,1) :295.
+                          aux1 = M + 256 s (s > 0): x is stored SHEARED by s columns per row -- patch cell (i,j) of the pixel
+                          at (y,x) is read from column x + j - 2 + s (i - 3) -- the wavefront decoder's layout          */
   LDIC_CTX_CONV2 = 9,  /* [P,4,4,N] -> [P,2,2,N]   Conv2d(N,N,3,2,1)  :297                                           */
   LDIC_CTX_CONV3 = 10, /* [P,2,2,N] -> [P,2,2,N]   Conv2d(N,N,3,1,1)  :299                                           */
   LDIC_CTX_FC = 11,    /* [P,2,2,N] -> [P,1,2,Cout_pad] fp32 (mu | log sigma), Linear(4N, 2*Cout) :302; Cout = N-M   */
@@ -348,12 +350,16 @@ LDIC_API int ldic_rans_decode(const LdicRansArgs* args, const unsigned char* in,
  * ranges[2j+1]) (device array of int pairs; count <= 0 = skip).  A range must lie inside ONE stream and start exactly
  * where that stream stopped (else status bit 16); args->mu / sigma must be valid for the symbols of the ranges at the
  * time of the call.  v_hat_bf16 (optional) receives a bf16 copy with its own row addressing.  Escaped symbols inside a
- * range are written in the same call; a stream is checked against its final state when its last symbol is decoded. */
+ * range are written in the same call; a stream is checked against its final state when its last symbol is decoded.
+ * param_row_map / bf16_row_map (optional device arrays of `rows` ints): the per-element (mode 2) mu / sigma of row r
+ * are read from row param_row_map[r], and the bf16 copy of row r goes to row bf16_row_map[r] -- a wavefront decoder
+ * keeps the parameters of the current wavefront only and the rounded latent in a sheared image (Net.decompress).     */
 LDIC_API int ldic_rans_decode_begin(const LdicRansArgs* args, const unsigned char* in, long long in_stride,
                            const unsigned int* sizes, void* state, unsigned int* status, void* workspace, void* stream);
 LDIC_API int ldic_rans_decode_ranges(const LdicRansArgs* args, const unsigned char* in, long long in_stride, void* state,
                             const int* ranges, int nranges, float* v_hat, long long v_hat_rs, long long v_hat_off,
-                            void* v_hat_bf16, long long vb_rs, long long vb_off, unsigned int* status, void* stream);
+                            void* v_hat_bf16, long long vb_rs, long long vb_off, const int* param_row_map,
+                            const int* bf16_row_map, unsigned int* status, void* stream);
 /* the 24-bit normal-CDF table of the format: T[i] = round(Phi(-8 + i/128) * 2^24), *entries = 2049 (host memory) */
 LDIC_API const unsigned int* ldic_rans_phi_table(int* entries);
 

@@ -137,7 +137,7 @@ _SIGS = {
                                         C.c_void_p, C.c_void_p]),
     "ldic_rans_decode_ranges": (C.c_int, [C.POINTER(RansArgs), C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong,
-                                         C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldic_rans_phi_table": (C.POINTER(C.c_uint), [C.POINTER(C.c_int)]),
     "ldic_window_attention_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldic_window_attention_core": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

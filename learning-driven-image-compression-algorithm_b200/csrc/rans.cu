@@ -53,6 +53,7 @@ struct Addr {
   const float* sigma; long long sg_rs, sg_off; int sg_mode; int sg_period;
   unsigned cols; long long rows_per_seg;
   int quant, sigma_is_log; float scale_bound;
+  const int* prow;      // optional: per-element (mode 2) mu / sigma of row r are read from row prow[r] (incremental decoding)
 };
 
 struct Model { int m, R; float mu, inv; };     // inv = 1 / sigma, correctly rounded
@@ -95,11 +96,12 @@ __device__ __forceinline__ void load_params(const Addr& A, long long seg, unsign
   col = i - r * A.cols;
   row = seg * A.rows_per_seg + r;
   mu_raw = 0.f;
-  if (A.mu_mode == 2) mu_raw = __ldg(A.mu + row * A.mu_rs + A.mu_off + col);
+  const long long prow = A.prow ? (long long)__ldg(A.prow + row) : row;
+  if (A.mu_mode == 2) mu_raw = __ldg(A.mu + prow * A.mu_rs + A.mu_off + col);
   else if (A.mu_mode == 1) mu_raw = __ldg(A.mu + col);
   else if (A.mu_mode == 3) mu_raw = __ldg(A.mu + row % A.sg_period);
   float s;
-  if (A.sg_mode == 2) s = __ldg(A.sigma + row * A.sg_rs + A.sg_off + col);
+  if (A.sg_mode == 2) s = __ldg(A.sigma + prow * A.sg_rs + A.sg_off + col);
   else if (A.sg_mode == 1) s = __ldg(A.sigma + col);
   else s = __ldg(A.sigma + row % A.sg_period);
   if (A.sigma_is_log) s = expf(s);
@@ -416,7 +418,11 @@ struct Cand { float base, mu, inv; uint32_t scale; int step, nsym; uint32_t c_lo
 
 // where the decoded symbols go: fp32 (always) and optionally a bf16 copy (the rounded latent image the context model
 // and the synthesis transform read), both with row addressing
-struct DecOut { float* v; long long rs, off; __nv_bfloat16* vb; long long vb_rs, vb_off; };
+struct DecOut { float* v; long long rs, off; __nv_bfloat16* vb; long long vb_rs, vb_off; const int* vb_map; };
+__device__ __forceinline__ void dec_store(const DecOut& O, long long row, unsigned col, float vv) {
+  O.v[row * O.rs + O.off + col] = vv;
+  if (O.vb) O.vb[(O.vb_map ? (long long)__ldg(O.vb_map + row) : row) * O.vb_rs + O.vb_off + col] = __float2bfloat16_rn(vv);
+}
 
 struct DecCursor { uint32_t x, wpos, wend, wnext; bool corrupt; };
 
@@ -494,9 +500,7 @@ __device__ __forceinline__ void decode_run(const Addr& A, long long seg, unsigne
     }
     if (valid) {
       const float kf = (float)(my_k0 + my_j);
-      const float vv = A.quant == 2 ? __fadd_rn(kf, mu_raw) : kf;
-      O.v[row * O.rs + O.off + col] = vv;
-      if (O.vb) O.vb[row * O.vb_rs + O.vb_off + col] = __float2bfloat16_rn(vv);
+      dec_store(O, row, col, A.quant == 2 ? __fadd_rn(kf, mu_raw) : kf);
     }
   }
   cur_.x = x; cur_.wpos = wpos; cur_.wnext = wnext; cur_.corrupt = corrupt;
@@ -597,9 +601,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) k_rans_dec_ranges(Addr A, unsi
       long long row; unsigned col; float mu_raw, sigma;
       load_params(A, seg, i, row, col, mu_raw, sigma);
       const float kf = (float)(int)esc[2 * e + 1];
-      const float vv = A.quant == 2 ? __fadd_rn(kf, mu_raw) : kf;
-      O.v[row * O.rs + O.off + col] = vv;
-      if (O.vb) O.vb[row * O.vb_rs + O.vb_off + col] = __float2bfloat16_rn(vv);
+      dec_store(O, row, col, A.quant == 2 ? __fadd_rn(kf, mu_raw) : kf);
     }
   }
 }
@@ -668,6 +670,7 @@ int make_addr(const LdicRansArgs* a, bool need_v, Addr* A, long long* segs, long
   A->sg_period = a->sigma_period > 0 ? a->sigma_period : 1;
   A->cols = (unsigned)a->cols; A->rows_per_seg = a->rows_per_segment;
   A->quant = a->quant; A->sigma_is_log = a->sigma_is_log; A->scale_bound = a->scale_bound;
+  A->prow = nullptr;
   *segs = a->rows / a->rows_per_segment;
   *n = ne;
   if (*segs > 65535) return fail(LDIC_EINVAL, "rans: at most 65535 segments per call");
@@ -747,7 +750,7 @@ LDIC_API int ldic_rans_decode(const LdicRansArgs* a, const unsigned char* in, lo
   k_rans_dec_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, in, in_stride, sizes, w.wcount, w.woffs, status);
   if (int r = check_launch("k_rans_dec_scan")) return r;
   if (n == 0) return LDIC_OK;
-  DecOut O; O.v = v_hat; O.rs = v_hat_rs; O.off = v_hat_off; O.vb = nullptr; O.vb_rs = 0; O.vb_off = 0;
+  DecOut O; O.v = v_hat; O.rs = v_hat_rs; O.off = v_hat_off; O.vb = nullptr; O.vb_rs = 0; O.vb_off = 0; O.vb_map = nullptr;
   k_rans_dec_streams<<<dim3((S + kDecWarps - 1) / kDecWarps, (unsigned)segs), kDecWarps * 32, 0, st>>>(
       A, (unsigned)n, S, in, in_stride, w.wcount, w.woffs, O, status);
   if (int r = check_launch("k_rans_dec_streams")) return r;
@@ -777,14 +780,16 @@ LDIC_API int ldic_rans_decode_begin(const LdicRansArgs* a, const unsigned char* 
 
 LDIC_API int ldic_rans_decode_ranges(const LdicRansArgs* a, const unsigned char* in, long long in_stride, void* state,
                                      const int* ranges, int nranges, float* v_hat, long long v_hat_rs, long long v_hat_off,
-                                     void* v_hat_bf16, long long vb_rs, long long vb_off, unsigned int* status, void* stream) {
+                                     void* v_hat_bf16, long long vb_rs, long long vb_off, const int* param_row_map,
+                                     const int* bf16_row_map, unsigned int* status, void* stream) {
   Addr A; long long segs, n;
   if (int r = make_addr(a, false, &A, &segs, &n)) return r;
   if (!in || !status || !state || !v_hat || (nranges > 0 && !ranges)) return fail(LDIC_EINVAL, "rans decode_ranges: null buffer");
   if (nranges < 0 || nranges > 65535 * kDecWarps) return fail(LDIC_EINVAL, "rans decode_ranges: nranges");
   if (segs == 0 || nranges == 0 || n == 0) return LDIC_OK;
   DecOut O; O.v = v_hat; O.rs = v_hat_rs; O.off = v_hat_off;
-  O.vb = reinterpret_cast<__nv_bfloat16*>(v_hat_bf16); O.vb_rs = vb_rs; O.vb_off = vb_off;
+  O.vb = reinterpret_cast<__nv_bfloat16*>(v_hat_bf16); O.vb_rs = vb_rs; O.vb_off = vb_off; O.vb_map = bf16_row_map;
+  A.prow = param_row_map;
   k_rans_dec_ranges<<<dim3((nranges + kDecWarps - 1) / kDecWarps, (unsigned)segs), kDecWarps * 32, 0, (cudaStream_t)stream>>>(
       A, (unsigned)n, (unsigned)a->streams, in, in_stride, (uint4*)state, ranges, nranges, O, status);
   return check_launch("k_rans_dec_ranges");

@@ -134,6 +134,20 @@ class PredictionModel_Context(nn.Module):
             self._plan_key = key
         return self._plan
 
+    _sheared = None
+
+    def sheared_conv1(self, N: int, M: int, shear: int):
+        """The first context conv for an input image stored sheared by `shear` columns per row (Net.decompress)."""
+        from . import _lib
+        key = (self._plan_key, shear)
+        if self._sheared is None or self._sheared[0] != key:
+            t = self.transform
+            with torch.no_grad():
+                layer = ops.ConvTC(_lib.LDIC_CTX_CONV1, t[0].weight.detach(), t[0].bias.detach(), act=_lib.ACT_LEAKY02,
+                                   aux=(N, M + 256 * shear))
+            self._sheared = (key, layer)
+        return self._sheared[1]
+
     def raw_tc(self, y_round_bf16: torch.Tensor, h2: torch.Tensor, M: int) -> torch.Tensor:
         """(B,h,w,N) bf16 rounded latent (all N channels; the first M are the syntax channels and
         get zero weights) + (B,h,w,N) fp32 h_s output -> (B*h*w, 1, 2, Cp) fp32: [..,0,:c] = mu,
@@ -445,7 +459,8 @@ class Net(nn.Module):
         return y_hat
 
     @torch.no_grad()
-    def decompress(self, streams, H: int, W: int, symbols_per_stream: int = 2048, want_latents: bool = False):
+    def decompress(self, streams, H: int, W: int, symbols_per_stream: int = 2048, want_latents: bool = False,
+                   schedule: str = "band"):
         """The decoder: per-image {"z","y","syntax"} byte strings (Net.compress) -> x_hat (B,3,H,W), bit-identical to the
         encoder's reconstruction (rd_forward(want_x_hat=True)["x_hat"]), from the bytes and the model alone.
           z       from its stream under the factorised prior; h2 = h_s(z^)                       (model/net.py:676-681)
@@ -455,8 +470,11 @@ class Net(nn.Module):
                   step the context model runs on the partially decoded latent (the very kernels of the encoder, hence
                   the very (mu, sigma)) and the rANS decoder advances the streams of the pixels on the wavefront.
           x_hat   g_s + IGDN + batch_conv (:800-811)
-        This is the straightforward schedule -- w + 2(h-1) full passes of the context model (110 for 768x512) -- written
-        for exactness, not speed."""
+        schedule="full" runs the context model over the whole latent at each of the w + 2(h-1) steps (110 for 768x512);
+        schedule="band" (default) keeps [round(y) | h2] in an image SHEARED by two columns per row, where a wavefront is
+        one column: per step the first context conv runs on the 10-column band its taps reach (LDIC_CTX_CONV1 with
+        sheared tap offsets) and the other three layers on the wavefront's pixels only.  Both give the encoder's
+        (mu, sigma) bit for bit: an output pixel of these kernels depends on its own inputs in a fixed order."""
         B = len(streams)
         N, M, Cc = self.N, self.M, self.N - self.M
         if H % 64 or W % 64:
@@ -484,12 +502,41 @@ class Net(nn.Module):
             y_hat_bf16 = torch.zeros(B, h, w, N, dtype=torch.bfloat16, device=dev)
             dec = ops.RansDecoder([s["y"] for s in streams], B * h * w, Cc, h * w,
                                   streams=self.y_streams(h, w, symbols_per_stream), device=dev)
-            for t in range(T):
-                r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
-                ctx = self.prediction_model.raw_tc(y_hat_bf16, h2, M)
-                rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
-                dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=y_hat_bf16, vb_rs=N, vb_off=M,
-                           mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2, sigma_rs=rs, sigma_off=so, sigma_is_log=True)
+            if schedule == "full":
+                for t in range(T):
+                    r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
+                    ctx = self.prediction_model.raw_tc(y_hat_bf16, h2, M)
+                    rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
+                    dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=y_hat_bf16, vb_rs=N, vb_off=M,
+                               mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2, sigma_rs=rs, sigma_off=so,
+                               sigma_is_log=True)
+            elif schedule == "band":
+                # sheared image: pixel (r, c) lives in column c + 2r + 8 (8 = the reach of the taps to the left), so the
+                # wavefront of step t is column t + 8 and its patches lie in columns [t, t + 10)
+                SH, LEFT, BAND = 2, 8, 10
+                w2 = w + SH * (h - 1) + LEFT + 1
+                flat = ops.ctx_pack_input(y_hat_bf16, h2)                                    # [B,h,w,2N]: zeros | bf16(h2)
+                x_s = torch.zeros(B, h, w2, 2 * N, dtype=torch.bfloat16, device=dev)
+                for r in range(h):
+                    x_s[:, r, LEFT + SH * r:LEFT + SH * r + w] = flat[:, r]
+                pix = torch.arange(B * h * w, device=dev, dtype=torch.int64)
+                row_of = pix // w                                                            # b * h + r
+                prow = row_of.to(torch.int32)
+                vb_map = (row_of * w2 + (pix % w) + SH * (row_of % h) + LEFT).to(torch.int32)
+                L = self.prediction_model.plan(N, M)
+                L0s = self.prediction_model.sheared_conv1(N, M, SH)
+                for t in range(T):
+                    r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
+                    o1 = L0s(x_s[:, :, t:t + BAND].contiguous())                             # (B*h*BAND, 4, 4, N)
+                    sel = o1.view(B, h, BAND, 16 * N)[:, :, LEFT].contiguous().view(B * h, 4, 4, N)
+                    ctx = L[3](L[2](L[1](sel)))                                              # (B*h, 1, 2, Cp): the wavefront's pixels
+                    rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
+                    dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=x_s, vb_rs=2 * N, vb_off=M,
+                               param_row_map=prow, bf16_row_map=vb_map, mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2,
+                               sigma_rs=rs, sigma_off=so, sigma_is_log=True)
+                y_hat_bf16[..., M:] = y_hat.to(torch.bfloat16)
+            else:
+                raise ops.LdicError("decompress: schedule must be 'band' or 'full'")
             dec.finish()
             body = self.s_model.forward_nhwc_body(y_hat_bf16)
             blank = torch.zeros(B, 3, H, W, dtype=torch.uint8, device=dev)

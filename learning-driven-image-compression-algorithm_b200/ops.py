@@ -448,7 +448,7 @@ class RansDecoder:
                                               _ptr(self.status), _ptr(ws), _stream()), "ldic_rans_decode_begin")
 
     def decode(self, ranges: torch.Tensor, nranges: int, v_hat: torch.Tensor, *, v_hat_rs, v_hat_off=0, v_hat_bf16=None,
-               vb_rs=0, vb_off=0, mu=None, mu_mode=0, mu_rs=0, mu_off=0, sigma=None, sigma_mode=2, sigma_rs=0, sigma_off=0,
+               vb_rs=0, vb_off=0, param_row_map=None, bf16_row_map=None, mu=None, mu_mode=0, mu_rs=0, mu_off=0, sigma=None, sigma_mode=2, sigma_rs=0, sigma_off=0,
                sigma_period=1, sigma_is_log=False, scale_bound=0.0):
         _req(v_hat, torch.float32, "v_hat")
         _req(sigma, torch.float32, "sigma")
@@ -460,7 +460,8 @@ class RansDecoder:
         if self.segs and nranges:
             check(_L().ldic_rans_decode_ranges(C.byref(a), _ptr(self.buf), self.buf.stride(0), _ptr(self.state), _ptr(ranges),
                                                int(nranges), _ptr(v_hat), v_hat_rs, v_hat_off, _ptr(v_hat_bf16), vb_rs, vb_off,
-                                               _ptr(self.status), _stream()), "ldic_rans_decode_ranges")
+                                               _ptr(param_row_map), _ptr(bf16_row_map), _ptr(self.status), _stream()),
+                  "ldic_rans_decode_ranges")
 
     def finish(self):
         _rans_status_check(self.status[:self.segs], "rans incremental decode")
@@ -748,7 +749,7 @@ class ConvTC:
         GDN/IGDN: C*C per output pixel; context layers: the taps that fall inside the patch."""
         K = _lib
         if self.kind == K.LDIC_CTX_CONV1:      # 100 in-patch taps per position, 10 of them without the masked y part
-            N, M = self.aux
+            N, M = self.aux[0], self.aux[1] & 0xff
             return 2.0 * B * H * W * self.cout * (100 * self.cin - 10 * (N - M))
         if self.kind == K.LDIC_CTX_CONV2:
             return 2.0 * B * 25 * self.cin * self.cout

@@ -340,6 +340,7 @@ def test_net_decompress_reproduces_the_encoder_reconstruction(ldic, B, H, W):
     assert torch.equal(lat["y_hat"], torch.round(enc["latents"]["y"][..., net.M:]))
     assert torch.equal(lat["conv_w"].reshape(-1), enc["latents"]["conv_w"].reshape(-1))
     assert torch.equal(x_hat, enc["x_hat"])
+    assert torch.equal(net.decompress(streams, H, W, schedule="full"), x_hat)      # whole-latent context passes: same result
     # a damaged content stream is detected, not silently decoded
     bad = [dict(s) for s in streams]
     yb = bytearray(bad[0]["y"]); yb[len(yb) // 2] ^= 0x5A; bad[0]["y"] = bytes(yb)
