@@ -212,6 +212,7 @@ class Net(nn.Module):
         # forward(x, 'test'): transparent CUDA-graph capture / replay per input shape (see forward)
         self.auto_graph = True
         self._graphs = {}
+        self._decode_graphs = {}
         self._discarded_logged = False
 
     # -- TF32 parity mode ---------------------------------------------------------
@@ -458,9 +459,116 @@ class Net(nn.Module):
                                  streams=self.y_streams(h, w, symbols_per_stream))
         return y_hat
 
+    def _wavefront_table(self, h: int, w: int, dev) -> torch.Tensor:
+        """[T, h, 2] int32 (first symbol, count) of the pixel (r, t - 2r) each row r decodes at step t (count 0: none)."""
+        Cc = self.N - self.M
+        T = w + 2 * (h - 1)
+        table = torch.zeros(T, h, 2, dtype=torch.int32)
+        for t in range(T):
+            for r in range(max(0, (t - w + 2) // 2), min(h - 1, t // 2) + 1):
+                table[t, r, 0] = (r * w + (t - 2 * r)) * Cc
+                table[t, r, 1] = Cc
+        return table.to(dev)
+
+    def _decode_y_steps(self, data, h2, table, B, h, w, symbols_per_stream, schedule):
+        """The wavefront loop on `data` (RansStreams or list of bytes) -> (y_hat fp32 [B,h,w,Cc], y_hat bf16 [B,h,w,N],
+        RansDecoder).  No synchronisation: capturable in a CUDA graph when `data` is device resident."""
+        N, M, Cc = self.N, self.M, self.N - self.M
+        dev = h2.device
+        T = w + 2 * (h - 1)
+        y_hat = torch.zeros(B, h, w, Cc, dtype=torch.float32, device=dev)
+        y_hat_bf16 = torch.zeros(B, h, w, N, dtype=torch.bfloat16, device=dev)
+        dec = ops.RansDecoder(data, B * h * w, Cc, h * w, streams=self.y_streams(h, w, symbols_per_stream), device=dev)
+        if schedule == "full":
+            for t in range(T):
+                r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
+                ctx = self.prediction_model.raw_tc(y_hat_bf16, h2, M)
+                rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
+                dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=y_hat_bf16, vb_rs=N, vb_off=M,
+                           mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2, sigma_rs=rs, sigma_off=so, sigma_is_log=True)
+        elif schedule == "band":
+            # sheared image: pixel (r, c) lives in column c + 2r + 8 (8 = the reach of the taps to the left), so the
+            # wavefront of step t is column t + 8 and its patches lie in columns [t, t + 10)
+            SH, LEFT, BAND = 2, 8, 10
+            w2 = w + SH * (h - 1) + LEFT + 1
+            flat = ops.ctx_pack_input(y_hat_bf16, h2)                                        # [B,h,w,2N]: zeros | bf16(h2)
+            x_s = torch.zeros(B, h, w2, 2 * N, dtype=torch.bfloat16, device=dev)
+            for r in range(h):
+                x_s[:, r, LEFT + SH * r:LEFT + SH * r + w] = flat[:, r]
+            pix = torch.arange(B * h * w, device=dev, dtype=torch.int64)
+            row_of = pix // w                                                                # b * h + r
+            prow = row_of.to(torch.int32)
+            vb_map = (row_of * w2 + (pix % w) + SH * (row_of % h) + LEFT).to(torch.int32)
+            L = self.prediction_model.plan(N, M)
+            L0s = self.prediction_model.sheared_conv1(N, M, SH)
+            for t in range(T):
+                r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
+                o1 = L0s(x_s[:, :, t:t + BAND].contiguous())                                 # (B*h*BAND, 4, 4, N)
+                sel = o1.view(B, h, BAND, 16 * N)[:, :, LEFT].contiguous().view(B * h, 4, 4, N)
+                ctx = L[3](L[2](L[1](sel)))                                                  # (B*h, 1, 2, Cp): the wavefront's pixels
+                rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
+                dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=x_s, vb_rs=2 * N, vb_off=M,
+                           param_row_map=prow, bf16_row_map=vb_map, mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2,
+                           sigma_rs=rs, sigma_off=so, sigma_is_log=True)
+            y_hat_bf16[..., M:] = y_hat.to(torch.bfloat16)
+        else:
+            raise ops.LdicError("decompress: schedule must be 'band' or 'full'")
+        return y_hat, y_hat_bf16, dec
+
+    def _decode_y_wavefronts(self, y_blobs, h2, B, h, w, symbols_per_stream, schedule, use_graph):
+        """Eager the first time a shape is seen; from the second time on the ~800 launches of the loop are one CUDA graph
+        over static buffers (bitstreams, h2 in; y_hat out), keyed by shape and parameter versions like Net.forward's."""
+        dev = h2.device
+        Cc = self.N - self.M
+        key = (dev.index, B, h, w, symbols_per_stream, schedule, tuple((p._version, p.data_ptr()) for p in self.parameters()))
+        ent = self._decode_graphs.get(key) if use_graph else None
+        if not use_graph or ent is None:
+            table = self._wavefront_table(h, w, dev)
+            y_hat, y_hat_bf16, dec = self._decode_y_steps(y_blobs, h2, table, B, h, w, symbols_per_stream, schedule)
+            dec.finish()
+            if use_graph:
+                if len(self._decode_graphs) >= 4:
+                    self._decode_graphs.clear()
+                self._decode_graphs[key] = False
+            return y_hat, y_hat_bf16
+        if ent is False:                        # second sight: capture
+            S = self.y_streams(h, w, symbols_per_stream)
+            n = h * w * Cc
+            cap = (int(ops._L().ldic_rans_max_bytes(n, S)) + 3) & ~3
+            st = {"buf": torch.zeros(B, cap, dtype=torch.uint8, device=dev),
+                  "sizes": torch.zeros(B, dtype=torch.int32, device=dev), "h2": torch.empty_like(h2),
+                  "table": self._wavefront_table(h, w, dev), "cap": cap}
+            data = ops.RansStreams(st["buf"], st["sizes"], None, S, n, ops.QUANT_ROUND)
+            st["h2"].copy_(h2)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):       # warm-up on the static buffers (empty streams: every image reports a bad header)
+                self._decode_y_steps(data, st["h2"], st["table"], B, h, w, symbols_per_stream, schedule)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                st["y_hat"], st["y_hat_bf16"], st["dec"] = self._decode_y_steps(data, st["h2"], st["table"], B, h, w,
+                                                                                symbols_per_stream, schedule)
+            st["graph"] = g
+            ent = self._decode_graphs[key] = st
+        sizes = [len(b) for b in y_blobs]
+        if max(sizes) > ent["cap"]:
+            raise ops.LdicError("decompress: a content bitstream is larger than any encoder output for this shape")
+        host = torch.zeros(B, (max(sizes) + 3) & ~3, dtype=torch.uint8)
+        for i, b in enumerate(y_blobs):
+            if len(b):
+                host[i, :len(b)] = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+        ent["buf"][:, :host.shape[1]].copy_(host)
+        ent["sizes"].copy_(torch.tensor(sizes, dtype=torch.int32))
+        ent["h2"].copy_(h2)
+        ent["graph"].replay()
+        ent["dec"].finish()
+        return ent["y_hat"].clone(), ent["y_hat_bf16"].clone()
+
     @torch.no_grad()
     def decompress(self, streams, H: int, W: int, symbols_per_stream: int = 2048, want_latents: bool = False,
-                   schedule: str = "band"):
+                   schedule: str = "band", use_graph: bool = True):
         """The decoder: per-image {"z","y","syntax"} byte strings (Net.compress) -> x_hat (B,3,H,W), bit-identical to the
         encoder's reconstruction (rd_forward(want_x_hat=True)["x_hat"]), from the bytes and the model alone.
           z       from its stream under the factorised prior; h2 = h_s(z^)                       (model/net.py:676-681)
@@ -490,54 +598,8 @@ class Net(nn.Module):
             z3r = ops.rans_decode([s["syntax"] for s in streams], (B, M, 1, 1), syn_first.reshape(B, -1, 1, 1),
                                   syn_second.reshape(B, -1, 1, 1), streams=1)
             conv_w = ops.syntax_branch(no_y, h2, M, *mods, z3_round_in=z3r)[4]
-            # wavefront schedule: step t decodes pixel (r, t - 2r) of every row r where that column exists
-            T = w + 2 * (h - 1)
-            table = torch.zeros(T, h, 2, dtype=torch.int32)
-            for t in range(T):
-                for r in range(max(0, (t - w + 2) // 2), min(h - 1, t // 2) + 1):
-                    table[t, r, 0] = (r * w + (t - 2 * r)) * Cc
-                    table[t, r, 1] = Cc
-            table = table.to(dev)
-            y_hat = torch.zeros(B, h, w, Cc, dtype=torch.float32, device=dev)
-            y_hat_bf16 = torch.zeros(B, h, w, N, dtype=torch.bfloat16, device=dev)
-            dec = ops.RansDecoder([s["y"] for s in streams], B * h * w, Cc, h * w,
-                                  streams=self.y_streams(h, w, symbols_per_stream), device=dev)
-            if schedule == "full":
-                for t in range(T):
-                    r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
-                    ctx = self.prediction_model.raw_tc(y_hat_bf16, h2, M)
-                    rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
-                    dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=y_hat_bf16, vb_rs=N, vb_off=M,
-                               mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2, sigma_rs=rs, sigma_off=so,
-                               sigma_is_log=True)
-            elif schedule == "band":
-                # sheared image: pixel (r, c) lives in column c + 2r + 8 (8 = the reach of the taps to the left), so the
-                # wavefront of step t is column t + 8 and its patches lie in columns [t, t + 10)
-                SH, LEFT, BAND = 2, 8, 10
-                w2 = w + SH * (h - 1) + LEFT + 1
-                flat = ops.ctx_pack_input(y_hat_bf16, h2)                                    # [B,h,w,2N]: zeros | bf16(h2)
-                x_s = torch.zeros(B, h, w2, 2 * N, dtype=torch.bfloat16, device=dev)
-                for r in range(h):
-                    x_s[:, r, LEFT + SH * r:LEFT + SH * r + w] = flat[:, r]
-                pix = torch.arange(B * h * w, device=dev, dtype=torch.int64)
-                row_of = pix // w                                                            # b * h + r
-                prow = row_of.to(torch.int32)
-                vb_map = (row_of * w2 + (pix % w) + SH * (row_of % h) + LEFT).to(torch.int32)
-                L = self.prediction_model.plan(N, M)
-                L0s = self.prediction_model.sheared_conv1(N, M, SH)
-                for t in range(T):
-                    r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
-                    o1 = L0s(x_s[:, :, t:t + BAND].contiguous())                             # (B*h*BAND, 4, 4, N)
-                    sel = o1.view(B, h, BAND, 16 * N)[:, :, LEFT].contiguous().view(B * h, 4, 4, N)
-                    ctx = L[3](L[2](L[1](sel)))                                              # (B*h, 1, 2, Cp): the wavefront's pixels
-                    rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
-                    dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=x_s, vb_rs=2 * N, vb_off=M,
-                               param_row_map=prow, bf16_row_map=vb_map, mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2,
-                               sigma_rs=rs, sigma_off=so, sigma_is_log=True)
-                y_hat_bf16[..., M:] = y_hat.to(torch.bfloat16)
-            else:
-                raise ops.LdicError("decompress: schedule must be 'band' or 'full'")
-            dec.finish()
+            y_hat, y_hat_bf16 = self._decode_y_wavefronts([s["y"] for s in streams], h2, B, h, w, symbols_per_stream,
+                                                          schedule, use_graph)
             body = self.s_model.forward_nhwc_body(y_hat_bf16)
             blank = torch.zeros(B, 3, H, W, dtype=torch.uint8, device=dev)
             if self.s_model.has_fused_tail():

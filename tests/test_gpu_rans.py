@@ -341,6 +341,12 @@ def test_net_decompress_reproduces_the_encoder_reconstruction(ldic, B, H, W):
     assert torch.equal(lat["conv_w"].reshape(-1), enc["latents"]["conv_w"].reshape(-1))
     assert torch.equal(x_hat, enc["x_hat"])
     assert torch.equal(net.decompress(streams, H, W, schedule="full"), x_hat)      # whole-latent context passes: same result
+    # second call of a shape: the wavefront loop is captured into a CUDA graph; third: replayed on other bitstreams
+    assert torch.equal(net.decompress(streams, H, W), x_hat)
+    x2 = torch.roll(x, shifts=17, dims=3)
+    streams2, _ = net.compress(x2)
+    assert torch.equal(net.decompress(streams2, H, W), net.rd_forward(x2, want_x_hat=True)["x_hat"])
+    assert len(net._decode_graphs) >= 1 and any(isinstance(v, dict) for v in net._decode_graphs.values())
     # a damaged content stream is detected, not silently decoded
     bad = [dict(s) for s in streams]
     yb = bytearray(bad[0]["y"]); yb[len(yb) // 2] ^= 0x5A; bad[0]["y"] = bytes(yb)
