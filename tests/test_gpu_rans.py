@@ -385,3 +385,17 @@ def test_incremental_decode_order_is_enforced(ldic):
     dec.decode(torch.tensor([[900, 200]], dtype=torch.int32, device="cuda"), 1, out, v_hat_rs=n, **kw)   # crosses streams
     with pytest.raises(ldic.LdicError, match="out of order"):
         dec.finish()
+
+
+def test_high_model_codec_round_trip(ldic):
+    """The N=384 / M=32 model (model/net.py:446-451): compress -> decompress reproduces the encoder's reconstruction
+    (wide kernels in the context model, 352 content channels per pixel), incl. the graph-replayed second call."""
+    B, H, W = 2, 128, 128
+    net = ldic.Net((B, H, W, 3), (B, H, W, 3), True, False).cuda().eval()
+    net.load_state_dict(dw.make_state_dict(2, N=384, M=32, boost=True), strict=True)
+    x = dw.make_input(2, B, H, W).cuda()
+    streams, info = net.compress(x)
+    ref = net.rd_forward(x, want_x_hat=True)["x_hat"]
+    assert torch.equal(net.decompress(streams, H, W), ref)
+    assert torch.equal(net.decompress(streams, H, W), ref)
+    assert 0.5 * info["bpp_estimated"] < info["bpp_coded"] < 1.05 * info["bpp_estimated"] + 0.2
