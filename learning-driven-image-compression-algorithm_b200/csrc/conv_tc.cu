@@ -91,7 +91,8 @@ struct ConvParams {
   unsigned long long* dbg;   // optional cycle counters of CTA 0 (LDIC_DEBUG_TIMING=1), else null
   int tf_round_out;          // TF32 mode: round the fp32 outputs to tf32 (layers that feed another tf32 layer)
   const __nv_bfloat16* residual;   // optional NHWC bf16 tensor of the output's shape added after the activation (no GDN)
-  int dbg_nostore;           // experiment: skip the epilogue's global stores (LDIC_DEBUG_NOSTORE=1)
+  int dbg_nostore;           // experiments: bit 0 skips the epilogue's global stores (LDIC_DEBUG_NOSTORE=1), bit 1 the first
+                             // layer's patch assembly (ldic_set_tuning("debug_nostore", 2)): which role bounds the kernel?
   // fused tail of Net.forward on the merged last deconv: per-image 1x1 conv (batch_conv) + 8-bit-level squared error
   const void* tail_x;        // NCHW input image [B,3,tail_H,tail_W] (fp32 in [-1,1], or uint8 levels when tail_u8), or null
   int tail_u8;
@@ -473,7 +474,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
       const uint32_t tbuf = tmem_base + bsel * kBufCols + lane_sel + col0;
       const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
-      const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B) && !P.dbg_nostore;
+      const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B) && !(P.dbg_nostore & 1);
       const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
                                  (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
       // ring position of this tile's gamma items: after the first min(insert_after, len) items of the
@@ -765,7 +766,7 @@ __device__ __forceinline__ void epilogue_w3(const ConvParams& P, const EpiRing& 
     const uint32_t par = (uint32_t)(it >> 1) & 1u;
     const uint32_t tbuf = tmem_base + bsel * kBufCols + lane_sel;
     const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
-    const bool valid = xi >= 1 && xi <= P.TW - 2 && gx_ < P.Wg && gy_ < P.Hg && gn_ < P.B && !P.dbg_nostore;
+    const bool valid = xi >= 1 && xi <= P.TW - 2 && gx_ < P.Wg && gy_ < P.Hg && gn_ < P.B && !(P.dbg_nostore & 1);
     const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
                                (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
     sbase += (uint32_t)jb.nkb + (it > 0 ? (uint32_t)gk : 0u);
@@ -1391,7 +1392,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const TileCoord tc = decode_tile2(P, pi + it * npairs, (int)rank);
       const Job jb = P.jobs[tc.job];
       const int gx_ = tc.x0 + xi, gy_ = tc.y0 + yi, gn_ = tc.n0 + ni;
-      const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B) && !P.dbg_nostore;
+      const bool valid = (gx_ < P.Wg) && (gy_ < P.Hg) && (gn_ < P.B) && !(P.dbg_nostore & 1);
       const long long pix_base = (long long)gn_ * P.out_sN + (long long)(gy_ * P.sy + jb.oy_off) * P.out_sY +
                                  (long long)(gx_ * P.sx + jb.ox_off) * P.out_sX + jb.out_off;
       const long long pb_other = __shfl_xor_sync(0xffffffffu, pix_base, 1);
@@ -1526,7 +1527,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //                 16-wide MMA step of a second block)
 //   warp 9        MMA issuer: 5 K steps of conv, then the GDN contraction of the previous tile
 //   warps 0..7    the common epilogue (x^2 operand tiles go into the same 16 KB ring as the A tiles)
-// Ring order (identical in all roles): [A0 A1](tile 0) [A0 A1](1) [x^2 x gk](0) [A0 A1](2) [x^2 x gk](1) ...
+// Ring order: see `a_pos` in the kernel (the x^2 slots of tile t-1 ride before, between or after the A slots of tile t).
 // ---------------------------------------------------------------------------------
 constexpr int kFirstTW = 64, kFirstTH = 2;
 constexpr int kRawX0 = 4;                           // the box starts 4 columns left of the tile (TMA needs a 16-byte
@@ -1631,8 +1632,15 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int ntiles_cta = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  // ring position of tile it's first A slot
-  auto base_pos = [&](int it) -> uint32_t { return it == 0 ? 0u : (uint32_t)(2 + per_tile * (it - 1)); };
+  // Ring order (identical in all roles): [A0 A1](tile 0), then for every tile t >= 1: the first `ins` A slots of tile t,
+  // the gk x^2 slots of tile t-1, the other A slots of tile t; the x^2 slots of the last tile close the sequence.
+  // ins (tuning key first_insert, default 2): with 0 the GDN contraction of tile t-1 is issued before the conv stages of
+  // tile t and never waits for the patch builders; bit-identical results, measured no faster.
+  const int ins = gk ? P.gdn_insert : 2;
+  auto a_pos = [&](int it, int a) -> uint32_t {          // ring position of A slot a (0 / 1) of tile it
+    if (it == 0) return (uint32_t)a;
+    return (uint32_t)(2 + per_tile * (it - 1) + a + (a < ins ? 0 : gk));
+  };
 
   if (warp >= kEpiWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -1658,13 +1666,15 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // ===================== MMA issuer =====================
       const uint32_t hi = desc_hi(1024);
       const uint32_t ring_lo = desc_lo(ring_base), w_lo = desc_lo(w_base), g_lo = desc_lo(g_base);
-      uint32_t slot = 0, ph = 0;
-      auto adv = [&]() { if (++slot == (uint32_t)S) { slot = 0; ph ^= 1; } };
       auto gdn_of = [&](int j) {
         const int bsel = j & 1;
+        // x^2 slots of tile j: after the first `ins` A slots of tile j+1, or right after tile j's own A slots when it is
+        // the CTA's last tile (the same arithmetic as EpiRing::insert_after in the epilogue)
+        const uint32_t pos0 = (uint32_t)(2 + per_tile * j) + (j + 1 < ntiles_cta ? (uint32_t)ins : 0u);
         mbar_wait(&x2_ready[bsel], (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
         for (int kb = 0; kb < gk; ++kb) {
+          const uint32_t slot = (pos0 + (uint32_t)kb) % (uint32_t)S;
           if (elect_one()) {
             const uint32_t alo = ring_lo + slot * (kATileBytes >> 4), blo = g_lo + kb * (kBTileBytes >> 4);
 #pragma unroll
@@ -1672,7 +1682,6 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               umma_bf16_lh(tmem_base + bsel * kBufCols, alo + 2 * k, hi, blo + 2 * k, hi, kIdesc, (kb | k) != 0);
             tc_commit(&empty_bar[slot]);
           }
-          adv();
         }
         if (elect_one()) tc_commit(&norm_full[bsel]);
       };
@@ -1680,28 +1689,34 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int it = 0; it < ntiles_cta; ++it) {
         const int bsel = it & 1;
         const uint32_t d_tmem = tmem_base + bsel * kBufCols;
+        if (gk && it > 0 && ins == 0) gdn_of(it - 1);
         mbar_wait(&buf_free[bsel], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         // K block 0: 64 patch values, K block 1: 16 (11 real + zero padding) -> one K step
-        mbar_wait(&full_bar[slot], ph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t alo = ring_lo + slot * (kATileBytes >> 4);
+        {
+          const uint32_t pos = a_pos(it, 0), slot = pos % (uint32_t)S;
+          mbar_wait(&full_bar[slot], (pos / (uint32_t)S) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t alo = ring_lo + slot * (kATileBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) umma_bf16_lh(d_tmem, alo + 2 * k, hi, w_lo + 2 * k, hi, kIdesc, k != 0);
-          tc_commit(&empty_bar[slot]);
+            for (int k = 0; k < kBlockK / 16; ++k) umma_bf16_lh(d_tmem, alo + 2 * k, hi, w_lo + 2 * k, hi, kIdesc, k != 0);
+            tc_commit(&empty_bar[slot]);
+          }
         }
-        adv();
-        mbar_wait(&full_bar[slot], ph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t alo = ring_lo + slot * (kATileBytes >> 4);
-          umma_bf16_lh(d_tmem, alo, hi, w_lo + (kBTileBytes >> 4), hi, kIdesc, 1u);
-          tc_commit(&empty_bar[slot]);
-          tc_commit(&acc_full[bsel]);
+        if (gk && it > 0 && ins == 1) gdn_of(it - 1);
+        {
+          const uint32_t pos = a_pos(it, 1), slot = pos % (uint32_t)S;
+          mbar_wait(&full_bar[slot], (pos / (uint32_t)S) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t alo = ring_lo + slot * (kATileBytes >> 4);
+            umma_bf16_lh(d_tmem, alo, hi, w_lo + (kBTileBytes >> 4), hi, kIdesc, 1u);
+            tc_commit(&empty_bar[slot]);
+            tc_commit(&acc_full[bsel]);
+          }
         }
-        adv();
-        if (gk && it > 0) gdn_of(it - 1);
+        if (gk && it > 0 && ins >= 2) gdn_of(it - 1);
       }
       if (gk) gdn_of(ntiles_cta - 1);
     } else {
@@ -1709,13 +1724,14 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int tb = (int)threadIdx.x - 32 * kProdBWarp;                // 0..63 = pixel x inside the tile (warps kProdBWarp, +1)
       for (int it = 0; it < ntiles_cta; ++it) {
         const int rs = it & 1;
-        const uint32_t p0 = base_pos(it);
-        const uint32_t s0 = p0 % (uint32_t)S, s1 = (p0 + 1) % (uint32_t)S;
+        const uint32_t p0 = a_pos(it, 0), p1 = a_pos(it, 1);
+        const uint32_t s0 = p0 % (uint32_t)S, s1 = p1 % (uint32_t)S;
         mbar_wait(&rfull[rs], (uint32_t)(it >> 1) & 1u);
         mbar_wait(&empty_bar[s0], ((p0 / (uint32_t)S) & 1u) ^ 1u);
-        mbar_wait(&empty_bar[s1], (((p0 + 1) / (uint32_t)S) & 1u) ^ 1u);
+        mbar_wait(&empty_bar[s1], ((p1 / (uint32_t)S) & 1u) ^ 1u);
         const uint32_t a0 = ring_base + s0 * kATileBytes, a1 = ring_base + s1 * kATileBytes;
         const uint32_t raw = raw_base + rs * kRawSlot;
+        if (!(P.dbg_nostore & 2)) {
         if constexpr (U8) {
           // uint8 image: first turn the whole box into the bf16 operand values x = (u/255)*2-1 once (every level is used
           // by ~6 patches), zero outside the image (TMA zero-fills the LEVELS there, but a zero level is x = -1, not the
@@ -1770,6 +1786,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t dst = (j < 8 ? a0 : a1) + row_off + ((((uint32_t)(j & 7)) ^ rx) << 4);
             st_shared_v4(dst, pk[0], pk[1], pk[2], pk[3]);
           }
+        }
         }
         fence_async_smem();
         mbar_arrive(&full_bar[s0]);
@@ -2338,7 +2355,10 @@ int build_plan_first(const LdicConvDesc* d, const Layer& L, const void* x, const
   P.jobs[0] = L.jobs[0];
   P.bias = bias_packed; P.beta = beta_tiled; P.out = y;
   P.dbg_nostore = tuning().debug_nostore;
-  P.gdn_insert = kGdnInsertDefault;
+  {
+    const int fi = tuning().first_insert;
+    P.gdn_insert = gdn ? (fi < 0 ? 0 : (fi > 2 ? 2 : fi)) : 2;    // see conv_first_kernel: ring order of the x^2 slots
+  }
   P.tail_H = d->H; P.tail_W = d->W;             // image size: the uint8 patch builder masks out-of-image taps itself
   const int fixed = (2 + L.Np / 64) * L.Np * kBlockK * 2 + 2 * kRawSlot + 256 + 2 * L.Np * 4 + 1024;
   int S = (227 * 1024 - fixed) / kATileBytes;

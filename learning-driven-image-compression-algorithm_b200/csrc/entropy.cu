@@ -32,13 +32,17 @@ int num_sms() {
 static Tuning g_tuning = [] {
   auto env = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
   Tuning t;
-  t.debug_nostore = getenv("LDIC_DEBUG_NOSTORE") != nullptr;
+  t.debug_nostore = getenv("LDIC_DEBUG_NOSTORE") ? (atoi(getenv("LDIC_DEBUG_NOSTORE")) ? atoi(getenv("LDIC_DEBUG_NOSTORE")) : 1) : 0;
   t.debug_timing = getenv("LDIC_DEBUG_TIMING") != nullptr;
   t.gdn_insert = env("LDIC_GDN_INSERT", 0);
   t.stages_cap = env("LDIC_STAGES", 0);
   t.tail_wide = env("LDIC_TAIL_WIDE", 1);
   t.lik_grid = env("LDIC_LIK_GRID", 0);
   t.first_epi = env("LDIC_FIRST_EPI", 0);      // epilogue warps of the first-layer kernel: 0 = default (12 at 192 channels), 8
+  // first-layer kernel: how many of tile t+1's two conv stages the MMA warp issues before the GDN contraction of tile t
+  // (2 = default; 0 = the contraction never waits for the patch builders: measured no faster, 0.380 vs 0.378 ms uint8,
+  // 0.346 vs 0.335 ms fp32 -- the wait for the contraction is its own ~1.5 k cycles, not the issue order)
+  t.first_insert = env("LDIC_FIRST_INSERT", 2);
   t.epoch = 0;
   return t;
 }();
@@ -61,6 +65,7 @@ extern "C" int ldic_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "tail_wide")) f = &t.tail_wide;
   else if (!strcmp(key, "lik_grid")) f = &t.lik_grid;
   else if (!strcmp(key, "first_epi")) f = &t.first_epi;
+  else if (!strcmp(key, "first_insert")) f = &t.first_insert;
   if (!f) return fail(LDIC_EINVAL, "set_tuning: unknown key '%s'", key);
   std::lock_guard<std::mutex> lk(g_init_mu);
   const int old = *f;
