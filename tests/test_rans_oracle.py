@@ -130,3 +130,40 @@ def test_container_round_trip_and_rejection():
     for bad in (blob[:-1], b"XDIC" + blob[4:], blob[:20]):
         with pytest.raises(ValueError):
             ev.unpack_container(bad)
+
+
+def test_wavefront_schedule_and_row_aligned_streams():
+    """Host logic of Net.decompress: every pixel is decoded exactly once, after the pixels its context reads
+    (model/net.py:219-242: rows r-3..r-1 at columns c-2..c+1, and (r, c-2), (r, c-1)) and after its predecessor in its
+    stream; content streams never cross a row of the latent."""
+    import ldic_b200
+    net = ldic_b200.Net((1, 64, 64, 3), (1, 64, 64, 3), False, False)
+    Cc = net.N - net.M
+    for h, w in [(4, 4), (8, 12), (32, 48), (16, 16), (5, 7)]:
+        S = net.y_streams(h, w)
+        assert S % h == 0 and (h * w * Cc) % S == 0
+        run = h * w * Cc // S                                   # symbols per stream
+        assert (w * Cc) % run == 0 and run <= 65535             # a whole number of streams per row
+        table = net._wavefront_table(h, w, "cpu").numpy()
+        T = w + 2 * (h - 1)
+        assert table.shape == (T, h, 2)
+        when = {}
+        for t in range(T):
+            for r in range(h):
+                first, count = table[t, r]
+                if count == 0:
+                    continue
+                assert count == Cc and first % Cc == 0
+                p = first // Cc
+                assert p // w == r and (r, p % w) not in when
+                when[(r, p % w)] = t
+        assert len(when) == h * w
+        for (r, c), t in when.items():
+            deps = [(r + i - 3, c + j - 2) for i in range(4) for j in range(4) if not (i == 3 and j >= 2)]
+            for rr, cc in deps:
+                if 0 <= rr < h and 0 <= cc < w:
+                    assert when[(rr, cc)] < t, ((r, c), (rr, cc))
+            if c > 0:                                           # stream predecessor: the pixel to the left (same row)
+                assert when[(r, c - 1)] == t - 1
+    hi = ldic_b200.Net((1, 64, 64, 3), (1, 64, 64, 3), True, False)
+    assert hi.y_streams(32, 48) % 32 == 0 and (48 * (hi.N - hi.M)) % (32 * 48 * (hi.N - hi.M) // hi.y_streams(32, 48)) == 0
