@@ -583,6 +583,7 @@ class Net(nn.Module):
         if post_processing:
             raise NotImplementedError("HAN post-processing (model/han.py) is outside the rate-distortion forward path")
         self.num_slices, self.max_support_slices = 4, 4
+        self.torch_tf32_matmul = True     # see rd_forward
         self.gaussian_conditional = GaussianConditional(None)
         self.gaussian_conditional.lower_bound_scale = LowerBound(0.11)          # state-dict keys of the CompressAI class
         self.gaussian_conditional.likelihood_lower_bound = LowerBound(1e-9)
@@ -637,8 +638,16 @@ class Net(nn.Module):
         family has no self-contained decoder and only the slice streams are coded."""
         if not inputs.is_cuda:
             raise ops.LdicError("Net runs on CUDA only (no CPU fallback)")
-        with torch.cuda.device(inputs.device):
-            return self._rd_forward(inputs.contiguous().float(), want_x_hat, want_bitstreams)
+        # the stock torch blocks: cuDNN convolutions already run TF32 by default; `torch_tf32_matmul` puts the fp32
+        # nn.Linear layers of SWAtten (cuBLAS SIMT sgemm, 5.6 of 59 ms at batch 16) on the same footing for this call
+        prev = torch.backends.cuda.matmul.allow_tf32
+        if self.torch_tf32_matmul:
+            torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            with torch.cuda.device(inputs.device):
+                return self._rd_forward(inputs.contiguous().float(), want_x_hat, want_bitstreams)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
 
     def _rd_forward(self, x, want_x_hat, want_bitstreams=False):
         B, _, H, W = x.shape
