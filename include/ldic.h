@@ -181,8 +181,10 @@ enum {
    * 4x4 patch per latent position with a one-hot 7x7 conv (BlockSample, :219-242); here the first
    * conv gathers the patch cells straight from the latent images by TMA, 16 jobs = 16 patch cells. */
   LDIC_CTX_CONV1 = 8,  /* x [B,h,w, round(y)(N) | h2(N)] bf16 -> [B*h*w,4,4,N]; aux0=N, aux1=M; Conv2d(2N-M,N,3,1,1) :295.
-                          aux1 = M + 256 s (s > 0): x is stored SHEARED by s columns per row -- patch cell (i,j) of the pixel
-                          at (y,x) is read from column x + j - 2 + s (i - 3) -- the wavefront decoder's layout          */
+                          aux1 = M | s << 8 | x_org << 12 | w_in << 16.  s > 0: x is stored SHEARED by s columns per row --
+                          patch cell (i,j) of the pixel at (y,x) is read from column x + j - 2 + s (i - 3); w_in > 0: x is
+                          w_in columns wide and the W output columns start at its column x_org (the wavefront decoder
+                          computes one column of a 10-column band)                                                     */
   LDIC_CTX_CONV2 = 9,  /* [P,4,4,N] -> [P,2,2,N]   Conv2d(N,N,3,2,1)  :297                                           */
   LDIC_CTX_CONV3 = 10, /* [P,2,2,N] -> [P,2,2,N]   Conv2d(N,N,3,1,1)  :299                                           */
   LDIC_CTX_FC = 11,    /* [P,2,2,N] -> [P,1,2,Cout_pad] fp32 (mu | log sigma), Linear(4N, 2*Cout) :302; Cout = N-M   */

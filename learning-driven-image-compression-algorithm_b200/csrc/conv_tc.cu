@@ -2003,8 +2003,15 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
       // patch cells (i+di, j+dj) in [0,3]^2 = image pixels (y+i+di-3, x+j+dj-2) (zero outside the
       // image: BlockSample pads with zeros, model/net.py:238); the y sampler masks cells (3,2),(3,3)
       // (:227-230) -> those taps contract over the h2 channels only.
-      const int N = d->aux0, M = d->aux1 & 0xff, shear = d->aux1 >> 8;   // sheared input: column offset + shear * row offset
-      if (N <= 0 || N % 64 || M < 0 || M >= N || shear < 0 || shear > 8 || d->Cin != 2 * N - M || d->Cin_pad != 2 * N || d->Cout != N || d->Cout_pad != N)
+      // aux1 = M | shear << 8 | x_org << 12 | w_in << 16.  shear: the input image is stored sheared by `shear` columns per
+      // row (column offset + shear * row offset); w_in > 0: the input image is w_in columns wide and the output grid (d->W
+      // columns) starts at its column x_org -- the wavefront decoder computes ONE column of a 10-column band.
+      const int N = d->aux0, M = d->aux1 & 0xff, shear = (d->aux1 >> 8) & 0xf, x_org = (d->aux1 >> 12) & 0xf, w_in = d->aux1 >> 16;
+      if (w_in) {
+        if (w_in < x_org + d->W) return fail(LDIC_EINVAL, "ctx conv1: the output columns must lie inside the input band");
+        L->vW = w_in;
+      }
+      if (N <= 0 || N % 64 || M < 0 || M >= N || d->Cin != 2 * N - M || d->Cin_pad != 2 * N || d->Cout != N || d->Cout_pad != N)
         return fail(LDIC_EINVAL, "ctx conv1: need aux0=N (multiple of 64), aux1=M, Cin=2N-M, Cin_pad=2N, Cout=Cout_pad=N");
       L->mode = 0; L->k = 3; L->cin_map = 1; L->map_N = N; L->map_M = M; L->njobs = 16;
       for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
@@ -2013,7 +2020,7 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
           const int ci = i + di, cj = j + dj;
           if (ci < 0 || ci > 3 || cj < 0 || cj > 3) continue;
           const bool masked = (ci == 3 && cj >= 2);
-          const int tdx = cj - 2 + shear * (ci - 3);
+          const int tdx = cj - 2 + shear * (ci - 3) + x_org;
           int t = masked ? add_tap(tdx, ci - 3, 0, N, N, N / 64) : add_tap(tdx, ci - 3, 0, 0, 0, 2 * N / 64);
           L->tap_ky[t][0] = di + 1; L->tap_kx[t][0] = dj + 1;
           jb.ntaps++;

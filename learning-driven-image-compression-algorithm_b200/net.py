@@ -503,9 +503,8 @@ class Net(nn.Module):
             L0s = self.prediction_model.sheared_conv1(N, M, SH)
             for t in range(T):
                 r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
-                o1 = L0s(x_s[:, :, t:t + BAND].contiguous())                                 # (B*h*BAND, 4, 4, N)
-                sel = o1.view(B, h, BAND, 16 * N)[:, :, LEFT].contiguous().view(B * h, 4, 4, N)
-                ctx = L[3](L[2](L[1](sel)))                                                  # (B*h, 1, 2, Cp): the wavefront's pixels
+                o1 = L0s.column_of_band(x_s[:, :, t:t + BAND].contiguous(), LEFT)            # (B*h, 4, 4, N): the wavefront's pixels
+                ctx = L[3](L[2](L[1](o1)))                                                   # (B*h, 1, 2, Cp)
                 rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
                 dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=x_s, vb_rs=2 * N, vb_off=M,
                            param_row_map=prow, bf16_row_map=vb_map, mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2,
@@ -580,8 +579,8 @@ class Net(nn.Module):
           x_hat   g_s + IGDN + batch_conv (:800-811)
         schedule="full" runs the context model over the whole latent at each of the w + 2(h-1) steps (110 for 768x512);
         schedule="band" (default) keeps [round(y) | h2] in an image SHEARED by two columns per row, where a wavefront is
-        one column: per step the first context conv runs on the 10-column band its taps reach (LDIC_CTX_CONV1 with
-        sheared tap offsets) and the other three layers on the wavefront's pixels only.  Both give the encoder's
+        one column: per step the four context layers run on the wavefront's pixels only, the first one reading the
+        10-column band its taps reach (LDIC_CTX_CONV1 with sheared tap offsets and a band origin).  Both give the encoder's
         (mu, sigma) bit for bit: an output pixel of these kernels depends on its own inputs in a fixed order."""
         B = len(streams)
         N, M, Cc = self.N, self.M, self.N - self.M

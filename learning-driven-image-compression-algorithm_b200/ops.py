@@ -799,6 +799,24 @@ class ConvTC:
             prof.append((self, (B, H, W), e0, e1))
         return sq, xo, out
 
+    def column_of_band(self, x: torch.Tensor, x_org: int) -> torch.Tensor:
+        """LDIC_CTX_CONV1 on a (B,h,w_in,2N) band of the (sheared) context input, for the ONE output column whose patches
+        start at band column x_org (aux1 = M | shear << 8 | x_org << 12 | w_in << 16): (B*h, 4, 4, N)."""
+        if self.kind != _lib.LDIC_CTX_CONV1:
+            raise LdicError("column_of_band: context conv 1 only")
+        _req(x, torch.bfloat16, "x")
+        if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
+            raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
+        B, H, w_in, _ = x.shape
+        if not (0 <= x_org < 16 and x_org < w_in < 32768 and self.aux[1] < (1 << 12)):
+            raise LdicError("column_of_band: bad band geometry")
+        out = torch.empty(self.out_dims(B, H, 1), dtype=torch.float32 if self.out_f32 else torch.bfloat16, device=x.device)
+        d = self._desc(B, H, 1, 0)
+        d.aux1 = int(self.aux[1]) | (int(x_org) << 12) | (int(w_in) << 16)
+        check(_L().ldic_conv_forward(C.byref(d), _ptr(x), _ptr(self.w_packed), _ptr(self.bias_packed),
+                                     _ptr(self.gamma_bf16), _ptr(self.beta_tiled), _ptr(out), _stream()), "ldic_conv_forward")
+        return out
+
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, sm_limit: int = 0,
                  residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         u8 = False
