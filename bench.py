@@ -430,7 +430,7 @@ def run_ours(args):
         "streams": (f"SM partition: hyperprior / syntax chain on a side stream on {net.side_sms} SMs next to g_s deconv 1-3"
                     if net.side_sms else "single stream"),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_first / conv_tc / conv_halo kernels (g_a, g_s, h_a, h_s, context convs + fused GDN/IGDN)",
+        "roofline": {"bound": "tensor", "kernel": "conv_first_kernel / conv_tc2_kernel (g_a, g_s, h_a, h_s, context convs + fused GDN/IGDN)",
                      "achieved": achieved_tf, "peak": tc_peak_sus, "unit": "TFLOP/s",
                      "frac": achieved_tf / tc_peak_sus if tc_peak_sus else None,
                      "traffic": conv_traffic, "traffic_note": "DRAM bytes of all conv launches of one step (ncu --set full, profiles/r02_traffic.json)",
