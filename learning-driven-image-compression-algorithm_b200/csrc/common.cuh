@@ -44,7 +44,7 @@ int num_sms();                    // multiprocessor count of the current device 
 
 // Tuning / diagnostic switches, read from the environment once at load time (see ldic_set_tuning in ldic.h)
 struct Tuning {
-  int debug_nostore, debug_timing, gdn_insert, stages_cap, tail_wide, lik_grid, first_epi, first_insert;
+  int debug_nostore, debug_timing, gdn_insert, stages_cap, tail_wide, lik_grid, first_epi, first_insert, first_tma_store;
   unsigned epoch;                 // bumped by ldic_set_tuning: cached launch plans of older epochs are not reused
 };
 const Tuning& tuning();

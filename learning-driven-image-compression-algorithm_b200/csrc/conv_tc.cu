@@ -77,6 +77,7 @@ struct ConvParams {
   int stages;
   int SA, SB;               // conv_wide_kernel: slots of the activation / weight rings
   int x_ovl;                // tiles overlap by x_ovl pixels in x (wide-N merged deconv: 2 = one halo pixel per side), else 0
+  int tma_store;            // first layer: the bf16 output tile leaves through shared memory and TMA stores
   int gdn_insert;           // streaming kernels: conv stages of tile it+1 issued before the GDN stages of tile it
   int super_per_job;        // CTA-pair kernel: (tiles_per_job + 1) / 2 pairs of adjacent tiles per job
   int ngroups, Cg;          // accumulator columns = ngroups x Cg
@@ -165,6 +166,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA store of a shared-memory box (same 128-byte swizzle as the operand tiles) to global memory; bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {     // true on exactly one lane of a converged warp
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -396,6 +406,10 @@ struct EpiRing {
   int t_first, t_stride, rank;
   uint32_t buf_free_cl, x2_ready_cl;
   int pair_store;           // lane-pair transposed bf16 stores (off for the first layer: measured 6 % slower there)
+  // first layer: the normalised bf16 tile is written over the tile's own x^2 operand slots (same rows, same swizzle) and
+  // leaves with one TMA store per 64-channel block instead of 32-byte-per-lane global stores
+  const CUtensorMap* tma_out;
+  int epi_threads;
 };
 
 // Fused tail on the CPT accumulator columns of one thread (CPT / CG output pixels of CG channels each); every index
@@ -579,6 +593,11 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         }
         if (edbg) { e_t1 = clock64(); e_slot += e_t1 - e_t0; }
         const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
+        if (R.tma_out && it > 0) {
+          // the slots still feed the TMA store of the previous tile's output: its issuer waits for the reads, then everyone
+          if (warp == 0 && lane == 0) tma_store_wait_read();
+          asm volatile("bar.sync 2, %0;" ::"r"(R.epi_threads) : "memory");
+        }
         if constexpr (TF) {
           // TF32 parity mode: the x^2 operand stays fp32 (rounded to tf32): 32 columns per 128-byte row, NP / 32 slots
 #pragma unroll
@@ -641,8 +660,26 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
             const float rs = rsqrt_approx(nrm);
             xr[c + k] *= igdn ? nrm * rs : rs;
           }
-          if (pair_store) store_cols_paired(c);
+          if (R.tma_out) {
+#pragma unroll
+            for (int j = 0; j < LDW / 8; ++j) {
+              const int col = col0 + c + j * 8;
+              const uint32_t a_addr = R.ring_base + ((gpos + (uint32_t)(col >> 6)) % R.nslots) * R.slot_bytes;
+              const float* x8 = &xr[c + j * 8];
+              st_shared_v4(a_addr + row_off + (((uint32_t)((col & 63) >> 3) ^ rx) << 4), pack_bf16x2(x8[0], x8[1]),
+                           pack_bf16x2(x8[2], x8[3]), pack_bf16x2(x8[4], x8[5]), pack_bf16x2(x8[6], x8[7]));
+            }
+          } else if (pair_store) store_cols_paired(c);
           else if (P.ngroups == 1 && valid) store_cols(c, LDW);
+        }
+        if (R.tma_out) {
+          fence_async_smem();                // generic-proxy writes -> visible to the TMA (async proxy)
+          asm volatile("bar.sync 2, %0;" ::"r"(R.epi_threads) : "memory");
+          if (warp == 0 && lane == 0 && !(P.dbg_nostore & 1)) {
+            for (int kb = 0; kb < gk; ++kb)
+              tma_store_4d(R.tma_out, R.ring_base + ((gpos + (uint32_t)kb) % R.nslots) * R.slot_bytes, kb * 64, tc.x0, tc.y0, tc.n0);
+            tma_store_commit();
+          }
         }
         stored = (P.ngroups == 1);
       } else if (P.act == LDIC_ACT_RELU) {
@@ -722,6 +759,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& P, const EpiRing
         }
       }
     }
+    if (R.tma_out && warp == 0 && lane == 0) tma_store_wait_all();      // the last tile's output has left shared memory
     if (edbg && lane == 0) {
       P.dbg[16] = (unsigned long long)(clock64() - e_begin); P.dbg[17] = (unsigned long long)e_acc;
       P.dbg[18] = (unsigned long long)e_norm; P.dbg[19] = (unsigned long long)e_slot; P.dbg[20] = (unsigned long long)ntiles_cta;
@@ -1109,6 +1147,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== epilogue warps (both CTAs, own tile) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
+    R.tma_out = nullptr; R.epi_threads = 0;
     R.pair_store = 1;
     R.ring_base = smem_base; R.slot_bytes = kStageBytes; R.nslots = (uint32_t)stages; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
@@ -1569,7 +1608,8 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
 template <int NP, bool U8 = false, int EW = kEpiWarps>
 __global__ void __launch_bounds__(EW * 32 + 128, 1)
 conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ ConvParams P) {
+                  const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmY,
+                  const __grid_constant__ ConvParams P) {
   constexpr int kBTileBytes = NP * kBlockK * 2;
   constexpr int GK = NP / 64;
   // roles: warps 0..EW-1 epilogue, EW TMA, EW+1 MMA, EW+2 / EW+3 patch builders
@@ -1621,6 +1661,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmW);
     if (gdn) prefetch_tmap(&tmG);
+    if (P.tma_store) prefetch_tmap(&tmY);
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
   for (int i = threadIdx.x; i < NP; i += kThreads) {
@@ -1798,10 +1839,12 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ===================== epilogue warps =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     EpiRing R;
+    R.tma_out = nullptr; R.epi_threads = 0;
     R.pair_store = 0;
     R.ring_base = ring_base; R.slot_bytes = kATileBytes; R.nslots = (uint32_t)S; R.empty_bar = empty_bar;
     R.acc_full = acc_full; R.buf_free = buf_free; R.x2_ready = x2_ready; R.norm_full = norm_full;
     R.s_bias = s_bias; R.s_beta = s_beta; R.insert_after = P.gdn_insert;
+    if (P.tma_store) { R.tma_out = &tmY; R.epi_threads = kEpiThreads; }
     epilogue_role<NP, false, EW>(P, R, tmem_base, gk, ntiles_cta, warp, lane);
   }
 
@@ -2117,7 +2160,7 @@ void choose_tile(int Wg, int Hg, int B, int* TW, int* TH, int* TN) {
 enum PlanKernel { PK_PAIR = 0, PK_W3 = 1, PK_WIDE = 2, PK_FIRST = 3, PK_FIRST_U8 = 4, PK_PAIR_RES = 5, PK_PAIR_TF = 6 };
 struct Plan {
   ConvParams P;
-  CUtensorMap a, w, g;
+  CUtensorMap a, w, g, y;   // y: output map of the first layer's TMA stores (P.tma_store)
   int kernel, np, grid;
   int epi_warps;           // first-layer kernel: 12 epilogue warps at 192 channels (three per TMEM lane quadrant), else 8
   size_t smem;
@@ -2270,7 +2313,7 @@ int launch_plan(const Plan& pl, cudaStream_t st) {
       const bool u8 = pl.kernel == PK_FIRST_U8;
       switch (pl.np) {
 #define LDIC_LAUNCH_FIRST(NPV, U8V, EWV) \
-  conv_first_kernel<NPV, U8V, EWV><<<pl.grid, EWV * 32 + 128, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.P)
+  conv_first_kernel<NPV, U8V, EWV><<<pl.grid, EWV * 32 + 128, pl.smem, st>>>(pl.a, pl.w, pl.g, pl.y, pl.P)
         case 64: if (u8) LDIC_LAUNCH_FIRST(64, true, 8); else LDIC_LAUNCH_FIRST(64, false, 8); break;
         case 128: if (u8) LDIC_LAUNCH_FIRST(128, true, 8); else LDIC_LAUNCH_FIRST(128, false, 8); break;
         case 192:
@@ -2396,6 +2439,15 @@ int build_plan_first(const LdicConvDesc* d, const Layer& L, const void* x, const
     if ((rc = encode_map(&pl->g, gamma_bf16, 2, dims, str, box))) return rc;
   } else {
     pl->g = pl->w;
+  }
+  pl->y = pl->w;
+  // TMA stores of the bf16 output tile through the tile's own x^2 slots (needs the GDN epilogue's slots: one per 64 channels)
+  P.tma_store = gdn && !d->out_f32 && y && tuning().first_tma_store && L.out_sX == L.Np && (((uintptr_t)y) & 127) == 0;
+  if (P.tma_store) {
+    cuuint64_t dims[4] = {(cuuint64_t)L.Np, (cuuint64_t)L.Wg, (cuuint64_t)L.Hg, (cuuint64_t)L.Bg};
+    cuuint64_t str[3] = {(cuuint64_t)L.out_sX * 2, (cuuint64_t)L.out_sY * 2, (cuuint64_t)L.out_sN * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)kFirstTW, (cuuint32_t)kFirstTH, 1};
+    if ((rc = encode_map(&pl->y, y, 4, dims, str, box))) return rc;
   }
   pl->kernel = u8 ? PK_FIRST_U8 : PK_FIRST;
   pl->np = L.Np;
@@ -2726,6 +2778,9 @@ int conv_forward_impl(const LdicConvDesc* d, const void* x, const void* w_packed
   if (pl && repl) {
     Plan p = *pl;                                   // per-call copy: this call's activation addresses
     if (repl(&p.a, const_cast<void*>(x)) != CUDA_SUCCESS) return fail(LDIC_ECUDA, "conv: cuTensorMapReplaceAddress failed");
+    if (p.P.tma_store) {
+      if ((((uintptr_t)y) & 127) || repl(&p.y, y) != CUDA_SUCCESS) return fail(LDIC_ECUDA, "conv: cuTensorMapReplaceAddress (output) failed");
+    }
     p.P.out = y;
     p.P.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     if (tail) { p.P.tail_x = tail->x_nchw; p.P.tail_w = tail->w; p.P.tail_xo = tail->x_tilde_nchw; p.P.tail_sq = tail->sq_err; }

@@ -43,6 +43,7 @@ static Tuning g_tuning = [] {
   // (2 = default; 0 = the contraction never waits for the patch builders: measured no faster, 0.380 vs 0.378 ms uint8,
   // 0.346 vs 0.335 ms fp32 -- the wait for the contraction is its own ~1.5 k cycles, not the issue order)
   t.first_insert = env("LDIC_FIRST_INSERT", 2);
+  t.first_tma_store = env("LDIC_FIRST_TMA_STORE", 1);   // first layer: output tile through shared memory + TMA stores
   t.epoch = 0;
   return t;
 }();
@@ -66,6 +67,7 @@ extern "C" int ldic_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "lik_grid")) f = &t.lik_grid;
   else if (!strcmp(key, "first_epi")) f = &t.first_epi;
   else if (!strcmp(key, "first_insert")) f = &t.first_insert;
+  else if (!strcmp(key, "first_tma_store")) f = &t.first_tma_store;
   if (!f) return fail(LDIC_EINVAL, "set_tuning: unknown key '%s'", key);
   std::lock_guard<std::mutex> lk(g_init_mu);
   const int old = *f;
