@@ -337,6 +337,8 @@ typedef struct {
   int quant, sigma_is_log;
   float scale_bound;   /* sigma = max(sigma, scale_bound) when > 0 (GaussianConditional: 0.11) */
   int streams;
+  int col_groups;      /* G > 1: the segment is coded group by group (all rows' columns [0, cols/G), then the next cols/G, ...),
+                          so the symbols of one row lie in G different streams; 0 / 1: row-major order */
 } LdicRansArgs;
 LDIC_API size_t ldic_rans_max_bytes(long long seg_elems, int streams);
 LDIC_API size_t ldic_rans_workspace_bytes(long long segments, long long seg_elems, int streams);

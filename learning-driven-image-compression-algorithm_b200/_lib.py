@@ -56,6 +56,7 @@ class RansArgs(C.Structure):
         ("sigma_period", C.c_int),
         ("rows", C.c_longlong), ("cols", C.c_longlong), ("rows_per_segment", C.c_longlong),
         ("quant", C.c_int), ("sigma_is_log", C.c_int), ("scale_bound", C.c_float), ("streams", C.c_int),
+        ("col_groups", C.c_int),
     ]
 
 

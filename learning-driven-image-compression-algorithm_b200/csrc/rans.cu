@@ -24,7 +24,7 @@
 // a time and, per symbol, each lane owns one sub-interval of the window (one integer for windows of up to 32, i.e.
 // sigma <= 2.2; wider windows continue with a 32-ary search inside the winning sub-interval, at most two more rounds).
 // Bitstream (little endian), per segment:
-//   u32 magic 'LRA1' | u32 n | u32 S | u32 E | u32 W | u32 quant | u32 0 | u32 0 | u32 state[S] | u16 words_of_stream[S] (+pad to 4)
+//   u32 magic 'LRA1' | u32 n | u32 S | u32 E | u32 W | u32 quant | u32 column groups (0: none) | u32 0 | u32 state[S] | u16 words_of_stream[S] (+pad to 4)
 //   | {u32 index, i32 value} escape[E] | u16 word[W]   (stream 0's words first, each in decoding order)
 #include "common.cuh"
 #include "rans_phi_table.h"
@@ -54,6 +54,9 @@ struct Addr {
   unsigned cols; long long rows_per_seg;
   int quant, sigma_is_log; float scale_bound;
   const int* prow;      // optional: per-element (mode 2) mu / sigma of row r are read from row prow[r] (incremental decoding)
+  // column groups: the segment is coded group by group -- all rows' columns [0, cg), then [cg, 2 cg), ... -- so that the
+  // symbols of one row lie in `groups` different streams and a wavefront decoder advances them in parallel
+  unsigned groups, cg, grp_elems;
 };
 
 struct Model { int m, R; float mu, inv; };     // inv = 1 / sigma, correctly rounded
@@ -92,8 +95,15 @@ __device__ __forceinline__ uint32_t cdf_at(const Model& M, int j) {
 // (mu, sigma) of element i of segment seg as the coder sees them; also the raw mean (for quant 2) and the address row / col
 __device__ __forceinline__ void load_params(const Addr& A, long long seg, unsigned i, long long& row, unsigned& col,
                                             float& mu_raw, float& sigma) {
-  const unsigned r = i / A.cols;
-  col = i - r * A.cols;
+  unsigned r;
+  if (A.groups > 1) {
+    const unsigned g = i / A.grp_elems, rem = i - g * A.grp_elems;
+    r = rem / A.cg;
+    col = g * A.cg + (rem - r * A.cg);
+  } else {
+    r = i / A.cols;
+    col = i - r * A.cols;
+  }
   row = seg * A.rows_per_seg + r;
   mu_raw = 0.f;
   const long long prow = A.prow ? (long long)__ldg(A.prow + row) : row;
@@ -322,7 +332,8 @@ __global__ void __launch_bounds__(kStreamThreads) k_rans_enc_streams(const uint2
 }
 
 // ---- encoder pass 5: scan the word counts, write header / states / counts (one CTA per segment) --------------------
-__global__ void __launch_bounds__(1024) k_rans_enc_scan(unsigned n, unsigned S, int quant, const uint32_t* __restrict__ states,
+__global__ void __launch_bounds__(1024) k_rans_enc_scan(unsigned n, unsigned S, int quant, unsigned groups,
+                                                        const uint32_t* __restrict__ states,
                                                         const uint32_t* __restrict__ wcount, uint32_t* __restrict__ woffs,
                                                         const uint32_t* __restrict__ esc_total, unsigned char* __restrict__ out,
                                                         long long out_stride, uint32_t* __restrict__ sizes,
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(1024) k_rans_enc_scan(unsigned n, unsigned S, 
     sizes[seg] = fits ? (uint32_t)total : 0u;
     if (out_stride >= kHeaderBytes) {
       uint32_t* h = reinterpret_cast<uint32_t*>(o);
-      h[0] = kMagic; h[1] = n; h[2] = S; h[3] = E; h[4] = W; h[5] = (uint32_t)quant; h[6] = 0; h[7] = 0;
+      h[0] = kMagic; h[1] = n; h[2] = S; h[3] = E; h[4] = W; h[5] = (uint32_t)quant; h[6] = groups > 1 ? groups : 0; h[7] = 0;
     }
   }
   if ((long long)L.esc_off > out_stride) return;
@@ -370,7 +381,8 @@ __global__ void __launch_bounds__(kOpsThreads) k_rans_pack(unsigned n, unsigned 
 }
 
 // ---- decoder pass 1: validate the header, scan the word counts (one CTA per segment) -------------------------------
-__global__ void __launch_bounds__(1024) k_rans_dec_scan(unsigned n, unsigned S, int quant, const unsigned char* __restrict__ in,
+__global__ void __launch_bounds__(1024) k_rans_dec_scan(unsigned n, unsigned S, int quant, unsigned groups,
+                                                        const unsigned char* __restrict__ in,
                                                         long long in_stride, const uint32_t* __restrict__ sizes,
                                                         uint32_t* __restrict__ wcount, uint32_t* __restrict__ woffs,
                                                         uint32_t* __restrict__ status) {
@@ -383,7 +395,8 @@ __global__ void __launch_bounds__(1024) k_rans_dec_scan(unsigned n, unsigned S, 
     int ok = size >= (uint32_t)kHeaderBytes && (long long)size <= in_stride;
     if (ok) {
       const uint32_t* h = reinterpret_cast<const uint32_t*>(src);
-      ok = h[0] == kMagic && h[1] == n && h[2] == S && h[5] == (uint32_t)quant && h[3] <= n && h[4] <= n &&
+      ok = h[0] == kMagic && h[1] == n && h[2] == S && h[5] == (uint32_t)quant && h[6] == (groups > 1 ? groups : 0u) &&
+           h[3] <= n && h[4] <= n &&
            (unsigned long long)L.esc_off + 8ull * h[3] + 2ull * h[4] == size;
     }
     s_ok = ok;
@@ -671,6 +684,10 @@ int make_addr(const LdicRansArgs* a, bool need_v, Addr* A, long long* segs, long
   A->cols = (unsigned)a->cols; A->rows_per_seg = a->rows_per_segment;
   A->quant = a->quant; A->sigma_is_log = a->sigma_is_log; A->scale_bound = a->scale_bound;
   A->prow = nullptr;
+  A->groups = a->col_groups > 1 ? (unsigned)a->col_groups : 1u;
+  if (a->col_groups < 0 || a->cols % A->groups) return fail(LDIC_EINVAL, "rans: cols must be a multiple of col_groups");
+  A->cg = (unsigned)(a->cols / A->groups);
+  A->grp_elems = (unsigned)(a->rows_per_segment * A->cg);
   *segs = a->rows / a->rows_per_segment;
   *n = ne;
   if (*segs > 65535) return fail(LDIC_EINVAL, "rans: at most 65535 segments per call");
@@ -724,7 +741,7 @@ LDIC_API int ldic_rans_encode(const LdicRansArgs* a, unsigned char* out, long lo
   k_rans_enc_streams<<<dim3((S + kStreamThreads - 1) / kStreamThreads, (unsigned)segs), kStreamThreads, 0, st>>>(
       w.ops, (unsigned)n, S, w.slab, w.states, w.wcount);
   if (int r = check_launch("k_rans_enc_streams")) return r;
-  k_rans_enc_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, w.states, w.wcount, w.woffs, w.esc_total, out, out_stride,
+  k_rans_enc_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, A.groups, w.states, w.wcount, w.woffs, w.esc_total, out, out_stride,
                                                    sizes, status);
   if (int r = check_launch("k_rans_enc_scan")) return r;
   if (n > 0) {
@@ -747,7 +764,7 @@ LDIC_API int ldic_rans_decode(const LdicRansArgs* a, const unsigned char* in, lo
   const unsigned S = (unsigned)a->streams;
   Ws w; carve(workspace, segs, n, S, &w);
   LDIC_CUDA(cudaMemsetAsync(status, 0, 4 * segs, st));
-  k_rans_dec_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, in, in_stride, sizes, w.wcount, w.woffs, status);
+  k_rans_dec_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, A.groups, in, in_stride, sizes, w.wcount, w.woffs, status);
   if (int r = check_launch("k_rans_dec_scan")) return r;
   if (n == 0) return LDIC_OK;
   DecOut O; O.v = v_hat; O.rs = v_hat_rs; O.off = v_hat_off; O.vb = nullptr; O.vb_rs = 0; O.vb_off = 0; O.vb_map = nullptr;
@@ -772,7 +789,7 @@ LDIC_API int ldic_rans_decode_begin(const LdicRansArgs* a, const unsigned char* 
   const unsigned S = (unsigned)a->streams;
   Ws w; carve(workspace, segs, n, S, &w);
   LDIC_CUDA(cudaMemsetAsync(status, 0, 4 * segs, st));
-  k_rans_dec_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, in, in_stride, sizes, w.wcount, w.woffs, status);
+  k_rans_dec_scan<<<(unsigned)segs, 1024, 0, st>>>((unsigned)n, S, a->quant, A.groups, in, in_stride, sizes, w.wcount, w.woffs, status);
   if (int r = check_launch("k_rans_dec_scan")) return r;
   k_rans_dec_init<<<dim3((S + 255) / 256, (unsigned)segs), 256, 0, st>>>(S, in, in_stride, w.wcount, w.woffs, (uint4*)state, status);
   return check_launch("k_rans_dec_init");

@@ -388,13 +388,20 @@ class Net(nn.Module):
 
     # ---- f4: actual bitstreams (the reference only estimates the rate, model/net.py:856-861) ----------------------------
     def y_streams(self, h: int, w: int, symbols_per_stream: int = 2048) -> int:
-        """Streams per image of the content latent: every row of the latent is cut into k equal runs (k the smallest
-        divisor of w that brings a run to about `symbols_per_stream` symbols), so no stream crosses a row -- the decoder
-        walks wavefronts (pixel (r, c) at step c + 2r, see `decompress`) and a stream must be consumed in order."""
-        Cc = self.N - self.M
-        limit = min(65535, max(Cc, symbols_per_stream + symbols_per_stream // 4))
-        k = next((d for d in range(1, w + 1) if w % d == 0 and (w // d) * Cc <= limit), w)
-        return h * k
+        """Streams per image of the content latent: for every column group (y_groups) every row of the latent is cut into
+        k equal runs (k the smallest divisor of w that brings a run to about `symbols_per_stream` symbols), so no stream
+        crosses a row -- the decoder walks wavefronts (pixel (r, c) at step c + 2r, see `decompress`) and a stream must
+        be consumed in order."""
+        G = self.y_groups()
+        cg = (self.N - self.M) // G
+        limit = min(65535, max(cg, symbols_per_stream + symbols_per_stream // 4))
+        k = next((d for d in range(1, w + 1) if w % d == 0 and (w // d) * cg <= limit), w)
+        return G * h * k
+
+    def y_groups(self) -> int:
+        """Column groups of the content streams (LdicRansArgs.col_groups): the channels of a pixel are spread over four
+        streams, which the wavefront decoder advances in parallel (176 = 4 x 44 symbols per pixel at N-M = 176)."""
+        return 4 if (self.N - self.M) % 4 == 0 else 1
 
     def entropy_encode(self, out: Dict[str, torch.Tensor], symbols_per_stream: int = 2048) -> Dict[str, "ops.RansStreams"]:
         """rANS-codes the three symbol streams of one rd_forward result with the very (mu, sigma) its likelihoods were
@@ -413,7 +420,7 @@ class Net(nn.Module):
                                         streams=ops.rans_streams_for(hz * wz * N, sps))
         enc["y"] = ops.rans_encode_rows(y, B * h * w, Cc, h * w, v_rs=N, v_off=M, mu=lat["ctx"], mu_mode=2, mu_rs=lat["ctx_rs"],
                                         sigma=lat["ctx"], sigma_mode=2, sigma_rs=lat["ctx_rs"], sigma_off=lat["ctx_sig_off"],
-                                        sigma_is_log=True, streams=self.y_streams(h, w, sps))
+                                        sigma_is_log=True, streams=self.y_streams(h, w, sps), col_groups=self.y_groups())
         enc["syntax"] = ops.rans_encode(lat["z3_syntax"].reshape(B, -1, 1, 1), lat["syn_first"].reshape(B, -1, 1, 1),
                                         lat["syn_second"].reshape(B, -1, 1, 1), streams=1)
         return enc
@@ -456,18 +463,21 @@ class Net(nn.Module):
             y_hat = torch.empty(batch, h, w, Cc, dtype=torch.float32, device=ctx.device)
             ops.rans_decode_rows(y_streams, batch * h * w, Cc, h * w, y_hat, v_hat_rs=Cc, mu=ctx, mu_mode=2, mu_rs=ctx_rs,
                                  sigma=ctx, sigma_mode=2, sigma_rs=ctx_rs, sigma_off=ctx_sig_off, sigma_is_log=True,
-                                 streams=self.y_streams(h, w, symbols_per_stream))
+                                 streams=self.y_streams(h, w, symbols_per_stream), col_groups=self.y_groups())
         return y_hat
 
     def _wavefront_table(self, h: int, w: int, dev) -> torch.Tensor:
-        """[T, h, 2] int32 (first symbol, count) of the pixel (r, t - 2r) each row r decodes at step t (count 0: none)."""
-        Cc = self.N - self.M
+        """[T, h, G, 2] int32 (first symbol, count) per column group of the pixel (r, t - 2r) each row r decodes at step t
+        (count 0: none)."""
+        G = self.y_groups()
+        cg = (self.N - self.M) // G
         T = w + 2 * (h - 1)
-        table = torch.zeros(T, h, 2, dtype=torch.int32)
+        table = torch.zeros(T, h, G, 2, dtype=torch.int32)
         for t in range(T):
             for r in range(max(0, (t - w + 2) // 2), min(h - 1, t // 2) + 1):
-                table[t, r, 0] = (r * w + (t - 2 * r)) * Cc
-                table[t, r, 1] = Cc
+                for g in range(G):                      # group g of the segment starts at symbol g * (h * w * cg)
+                    table[t, r, g, 0] = g * h * w * cg + (r * w + (t - 2 * r)) * cg
+                    table[t, r, g, 1] = cg
         return table.to(dev)
 
     def _decode_y_steps(self, data, h2, table, B, h, w, symbols_per_stream, schedule):
@@ -478,13 +488,15 @@ class Net(nn.Module):
         T = w + 2 * (h - 1)
         y_hat = torch.zeros(B, h, w, Cc, dtype=torch.float32, device=dev)
         y_hat_bf16 = torch.zeros(B, h, w, N, dtype=torch.bfloat16, device=dev)
-        dec = ops.RansDecoder(data, B * h * w, Cc, h * w, streams=self.y_streams(h, w, symbols_per_stream), device=dev)
+        G = self.y_groups()
+        dec = ops.RansDecoder(data, B * h * w, Cc, h * w, streams=self.y_streams(h, w, symbols_per_stream), device=dev,
+                              col_groups=G)
         if schedule == "full":
             for t in range(T):
                 r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
                 ctx = self.prediction_model.raw_tc(y_hat_bf16, h2, M)
                 rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
-                dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=y_hat_bf16, vb_rs=N, vb_off=M,
+                dec.decode(table[t, r0:r1 + 1], (r1 - r0 + 1) * G, y_hat, v_hat_rs=Cc, v_hat_bf16=y_hat_bf16, vb_rs=N, vb_off=M,
                            mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2, sigma_rs=rs, sigma_off=so, sigma_is_log=True)
         elif schedule == "band":
             # sheared image: pixel (r, c) lives in column c + 2r + 8 (8 = the reach of the taps to the left), so the
@@ -506,7 +518,7 @@ class Net(nn.Module):
                 o1 = L0s.column_of_band(x_s[:, :, t:t + BAND].contiguous(), LEFT)            # (B*h, 4, 4, N): the wavefront's pixels
                 ctx = L[3](L[2](L[1](o1)))                                                   # (B*h, 1, 2, Cp)
                 rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
-                dec.decode(table[t, r0:r1 + 1], r1 - r0 + 1, y_hat, v_hat_rs=Cc, v_hat_bf16=x_s, vb_rs=2 * N, vb_off=M,
+                dec.decode(table[t, r0:r1 + 1], (r1 - r0 + 1) * G, y_hat, v_hat_rs=Cc, v_hat_bf16=x_s, vb_rs=2 * N, vb_off=M,
                            param_row_map=prow, bf16_row_map=vb_map, mu=ctx, mu_mode=2, mu_rs=rs, sigma=ctx, sigma_mode=2,
                            sigma_rs=rs, sigma_off=so, sigma_is_log=True)
             y_hat_bf16[..., M:] = y_hat.to(torch.bfloat16)

@@ -334,8 +334,9 @@ def rans_tobytes(streams, copy_stream: Optional["torch.cuda.Stream"] = None) -> 
 
 
 def _rans_args(rows, cols, rows_per_segment, v, v_rs, v_off, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs, sigma_off,
-               sigma_period, quant, sigma_is_log, scale_bound, streams):
+               sigma_period, quant, sigma_is_log, scale_bound, streams, col_groups=1):
     a = RansArgs()
+    a.col_groups = int(col_groups)
     a.v, a.v_rs, a.v_off = _ptr(v), v_rs, v_off
     a.mu, a.mu_rs, a.mu_off, a.mu_mode = _ptr(mu), mu_rs, mu_off, mu_mode
     a.sigma, a.sigma_rs, a.sigma_off, a.sigma_mode, a.sigma_period = _ptr(sigma), sigma_rs, sigma_off, sigma_mode, sigma_period
@@ -352,7 +353,7 @@ def _rans_ws(device, segs, seg_elems, streams):
 def rans_encode_rows(v, rows, cols, rows_per_segment, *, v_rs, v_off=0, mu=None, mu_mode=0, mu_rs=0, mu_off=0,
                      sigma=None, sigma_mode=2, sigma_rs=0, sigma_off=0, sigma_period=1, quant=QUANT_ROUND,
                      sigma_is_log=False, scale_bound=0.0, streams: Optional[int] = None,
-                     capacity: Optional[int] = None) -> RansStreams:
+                     capacity: Optional[int] = None, col_groups: int = 1) -> RansStreams:
     """Raw strided form of ldic_rans_encode (same addressing as likelihood_rows): one bitstream per `rows_per_segment`
     rows.  Stream-ordered, no synchronisation; read the result with RansStreams.tobytes() / .nbytes()."""
     _req(v, torch.float32, "v")
@@ -369,7 +370,7 @@ def rans_encode_rows(v, rows, cols, rows_per_segment, *, v_rs, v_off=0, mu=None,
     if segs == 0:
         return RansStreams(buf[:0], sizes[:0], status[:0], S, seg_elems, quant)
     a = _rans_args(rows, cols, rows_per_segment, v, v_rs, v_off, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs,
-                   sigma_off, sigma_period, quant, sigma_is_log, scale_bound, S)
+                   sigma_off, sigma_period, quant, sigma_is_log, scale_bound, S, col_groups)
     ws = _rans_ws(v.device, segs, seg_elems, S)
     check(_L().ldic_rans_encode(C.byref(a), _ptr(buf), stride, _ptr(sizes), _ptr(status), _ptr(ws), _stream()), "ldic_rans_encode")
     return RansStreams(buf[:segs], sizes[:segs], status[:segs], S, seg_elems, quant)
@@ -377,7 +378,8 @@ def rans_encode_rows(v, rows, cols, rows_per_segment, *, v_rs, v_off=0, mu=None,
 
 def rans_decode_rows(data, rows, cols, rows_per_segment, v_hat, *, v_hat_rs, v_hat_off=0, mu=None, mu_mode=0, mu_rs=0, mu_off=0,
                      sigma=None, sigma_mode=2, sigma_rs=0, sigma_off=0, sigma_period=1, quant=QUANT_ROUND,
-                     sigma_is_log=False, scale_bound=0.0, streams: Optional[int] = None, check_status: bool = True) -> torch.Tensor:
+                     sigma_is_log=False, scale_bound=0.0, streams: Optional[int] = None, check_status: bool = True,
+                     col_groups: int = 1) -> torch.Tensor:
     """ldic_rans_decode: `data` is a RansStreams or a list of bytes objects (one per segment); the symbols land in
     v_hat[row * v_hat_rs + v_hat_off + col].  Returns the per-segment status tensor (raises on a bad stream unless
     check_status=False)."""
@@ -403,7 +405,7 @@ def rans_decode_rows(data, rows, cols, rows_per_segment, v_hat, *, v_hat_rs, v_h
     if segs == 0:
         return status[:0]
     a = _rans_args(rows, cols, rows_per_segment, None, 0, 0, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs, sigma_off,
-                   sigma_period, quant, sigma_is_log, scale_bound, S)
+                   sigma_period, quant, sigma_is_log, scale_bound, S, col_groups)
     ws = _rans_ws(v_hat.device, segs, seg_elems, S)
     check(_L().ldic_rans_decode(C.byref(a), _ptr(buf), buf.stride(0) if segs else 0, _ptr(sizes), _ptr(v_hat), v_hat_rs, v_hat_off,
                                 _ptr(status), _ptr(ws), _stream()), "ldic_rans_decode")
@@ -419,7 +421,8 @@ class RansDecoder:
     (first symbol, count) pairs (segment-relative); every range must continue the stream it lies in.  `dec.finish()`
     synchronises and raises on a corrupt or mis-ordered decode."""
 
-    def __init__(self, data, rows, cols, rows_per_segment, *, streams: int, quant: int = QUANT_ROUND, device=None):
+    def __init__(self, data, rows, cols, rows_per_segment, *, streams: int, quant: int = QUANT_ROUND, device=None,
+                 col_groups: int = 1):
         segs, seg_elems = rows // rows_per_segment, rows_per_segment * cols
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         if isinstance(data, RansStreams):
@@ -436,12 +439,13 @@ class RansDecoder:
                     host[i, :len(b)] = torch.frombuffer(bytearray(b), dtype=torch.uint8)
             buf = host.to(dev)
             sizes = torch.tensor([len(b) for b in data], dtype=torch.int32, device=dev)
-        self.buf, self.sizes, self.S, self.quant = buf, sizes, int(streams), quant
+        self.buf, self.sizes, self.S, self.quant, self.col_groups = buf, sizes, int(streams), quant, int(col_groups)
         self.rows, self.cols, self.rps, self.segs = rows, cols, rows_per_segment, segs
         self.status = torch.zeros(max(segs, 1), dtype=torch.int32, device=dev)
         self.state = torch.empty((max(segs, 1), self.S, 4), dtype=torch.int32, device=dev)
         ones = torch.ones(1, dtype=torch.float32, device=dev)             # begin only needs the geometry of the problem
-        a = _rans_args(rows, cols, rows_per_segment, None, 0, 0, None, 0, 0, 0, ones, 3, 0, 0, 1, quant, False, 0.0, self.S)
+        a = _rans_args(rows, cols, rows_per_segment, None, 0, 0, None, 0, 0, 0, ones, 3, 0, 0, 1, quant, False, 0.0, self.S,
+                       self.col_groups)
         ws = _rans_ws(dev, segs, seg_elems, self.S)
         if segs:
             check(_L().ldic_rans_decode_begin(C.byref(a), _ptr(buf), buf.stride(0), _ptr(sizes), _ptr(self.state),
@@ -456,7 +460,7 @@ class RansDecoder:
         if v_hat_bf16 is not None:
             _req(v_hat_bf16, torch.bfloat16, "v_hat_bf16")
         a = _rans_args(self.rows, self.cols, self.rps, None, 0, 0, mu, mu_mode, mu_rs, mu_off, sigma, sigma_mode, sigma_rs,
-                       sigma_off, sigma_period, self.quant, sigma_is_log, scale_bound, self.S)
+                       sigma_off, sigma_period, self.quant, sigma_is_log, scale_bound, self.S, self.col_groups)
         if self.segs and nranges:
             check(_L().ldic_rans_decode_ranges(C.byref(a), _ptr(self.buf), self.buf.stride(0), _ptr(self.state), _ptr(ranges),
                                                int(nranges), _ptr(v_hat), v_hat_rs, v_hat_off, _ptr(v_hat_bf16), vb_rs, vb_off,

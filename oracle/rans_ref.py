@@ -89,7 +89,15 @@ def stream_counts(n: int, S: int) -> np.ndarray:
     return np.clip(n - s * Ls, 0, Ls)
 
 
-def encode_segment(k, mu, sigma, S: int, quant: int = 1) -> bytes:
+def group_order(rows: int, cols: int, groups: int) -> np.ndarray:
+    """Coding order of a [rows, cols] segment with `groups` column groups: indices into the row-major flattening, all
+    rows' columns [0, cols/G) first, then the next cols/G, ... (csrc/rans.cu: LdicRansArgs.col_groups)."""
+    idx = np.arange(rows * cols, dtype=np.int64).reshape(rows, groups, cols // groups)
+    return idx.transpose(1, 0, 2).reshape(-1)
+
+
+def encode_segment(k, mu, sigma, S: int, quant: int = 1, groups: int = 0) -> bytes:
+    """k, mu, sigma in CODING order (see group_order); `groups` is only recorded in the header (0: row-major)."""
     k = np.asarray(k, dtype=np.int64).ravel()
     n = k.size
     mu, sigma, m, R = make_model(np.asarray(mu, dtype=f32).ravel(), np.asarray(sigma, dtype=f32).ravel())
@@ -121,7 +129,7 @@ def encode_segment(k, mu, sigma, S: int, quant: int = 1) -> bytes:
     E = int(esc.sum())
     W = int(nw.sum())
     out = bytearray(esc_off + 8 * E + 2 * W)
-    struct.pack_into("<8I", out, 0, MAGIC, n, S, E, W, quant, 0, 0)
+    struct.pack_into("<8I", out, 0, MAGIC, n, S, E, W, quant, groups if groups > 1 else 0, 0)
     out[states_off:states_off + 4 * S] = x.astype("<u4").tobytes()
     out[counts_off:counts_off + 2 * S] = nw.astype("<u2").tobytes()
     ei = np.nonzero(esc)[0]
@@ -134,9 +142,9 @@ def encode_segment(k, mu, sigma, S: int, quant: int = 1) -> bytes:
     return bytes(out)
 
 
-def decode_segment(buf: bytes, mu, sigma, S: int, quant: int = 1) -> np.ndarray:
-    magic, n, S_h, E, W, q_h, _, _ = struct.unpack_from("<8I", buf, 0)
-    if magic != MAGIC or S_h != S or q_h != quant:
+def decode_segment(buf: bytes, mu, sigma, S: int, quant: int = 1, groups: int = 0) -> np.ndarray:
+    magic, n, S_h, E, W, q_h, g_h, _ = struct.unpack_from("<8I", buf, 0)
+    if magic != MAGIC or S_h != S or q_h != quant or g_h != (groups if groups > 1 else 0):
         raise ValueError("bad header")
     mu, sigma, m, R = make_model(np.asarray(mu, dtype=f32).ravel(), np.asarray(sigma, dtype=f32).ravel())
     if mu.size != n:

@@ -71,6 +71,24 @@ def test_strided_nhwc_slices_and_broadcast_modes_vs_oracle(ldic):
     ops.rans_decode_rows(blobs, B * h * w, Cc, h * w, out, v_hat_rs=N, v_hat_off=M, mu=ctx, mu_mode=2, mu_rs=64, sigma=ctx,
                          sigma_mode=2, sigma_rs=64, sigma_off=32, streams=S)
     assert torch.equal(out[..., M:], torch.round(y[..., M:])) and out[..., :M].abs().sum().item() == 0
+    # column groups: the same symbols coded group by group (two groups of 10 channels), against the oracle on the reordered arrays
+    enc = ops.rans_encode_rows(y, B * h * w, Cc, h * w, v_rs=N, v_off=M, mu=ctx, mu_mode=2, mu_rs=64, sigma=ctx, sigma_mode=2,
+                               sigma_rs=64, sigma_off=32, streams=6, col_groups=2)
+    gblobs = enc.tobytes()
+    order = rr.group_order(h * w, Cc, 2)
+    for b in range(B):
+        k = torch.round(y[b, :, :, M:]).reshape(-1).cpu().numpy().astype(np.int64)
+        rows = slice(b * h * w, (b + 1) * h * w)
+        mu = ctx[rows, :Cc].reshape(-1).cpu().numpy()
+        sg = ctx[rows, 32:32 + Cc].reshape(-1).cpu().numpy()
+        assert gblobs[b] == rr.encode_segment(k[order], mu[order], sg[order], 6, groups=2), b
+    out = torch.zeros(B, h, w, N, device="cuda")
+    ops.rans_decode_rows(gblobs, B * h * w, Cc, h * w, out, v_hat_rs=N, v_hat_off=M, mu=ctx, mu_mode=2, mu_rs=64, sigma=ctx,
+                         sigma_mode=2, sigma_rs=64, sigma_off=32, streams=6, col_groups=2)
+    assert torch.equal(out[..., M:], torch.round(y[..., M:]))
+    with pytest.raises(ldic.LdicError, match="bad header"):                      # decoded with another grouping than coded with
+        ops.rans_decode_rows(gblobs, B * h * w, Cc, h * w, out, v_hat_rs=N, v_hat_off=M, mu=ctx, mu_mode=2, mu_rs=64, sigma=ctx,
+                             sigma_mode=2, sigma_rs=64, sigma_off=32, streams=6)
     # per-channel sigma, no mean (the z stream of model/net.py:676,:781)
     enc = ops.rans_encode_rows(y, B * h * w, Cc, h * w, v_rs=N, v_off=M, sigma=sig_c, sigma_mode=1, streams=S)
     blobs = enc.tobytes()
@@ -230,7 +248,7 @@ def test_net_compress_bitstreams_round_trip(ldic, B, H, W):
     bpp_ref = net.metrics(out, B, H, W)[0].item()
     assert abs(info["bpp_estimated"] / bpp_ref - 1) < 1e-5
     hz, wz, h, w = H // 64, W // 64, H // 16, W // 16
-    Sz, Sy = ops.rans_streams_for(hz * wz * net.N), ops.rans_streams_for(h * w * (net.N - net.M))
+    Sz, Sy = ops.rans_streams_for(hz * wz * net.N), net.y_streams(h, w)
     # untrained context models put many symbols deep in the tails, where the estimate charges up to -log2(1e-8) = 26.6
     # bits and the coder 16 (window) or 80 (escape): only the upper bound is tight here; the two-sided 1 % check is
     # test_round_trip_and_rate_at_the_bench_size, where the symbols follow their model

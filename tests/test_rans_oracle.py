@@ -135,35 +135,62 @@ def test_container_round_trip_and_rejection():
 def test_wavefront_schedule_and_row_aligned_streams():
     """Host logic of Net.decompress: every pixel is decoded exactly once, after the pixels its context reads
     (model/net.py:219-242: rows r-3..r-1 at columns c-2..c+1, and (r, c-2), (r, c-1)) and after its predecessor in its
-    stream; content streams never cross a row of the latent."""
+    streams; content streams never cross a row of the latent nor a column group."""
     import ldic_b200
-    net = ldic_b200.Net((1, 64, 64, 3), (1, 64, 64, 3), False, False)
-    Cc = net.N - net.M
-    for h, w in [(4, 4), (8, 12), (32, 48), (16, 16), (5, 7)]:
-        S = net.y_streams(h, w)
-        assert S % h == 0 and (h * w * Cc) % S == 0
-        run = h * w * Cc // S                                   # symbols per stream
-        assert (w * Cc) % run == 0 and run <= 65535             # a whole number of streams per row
-        table = net._wavefront_table(h, w, "cpu").numpy()
-        T = w + 2 * (h - 1)
-        assert table.shape == (T, h, 2)
-        when = {}
-        for t in range(T):
-            for r in range(h):
-                first, count = table[t, r]
-                if count == 0:
-                    continue
-                assert count == Cc and first % Cc == 0
-                p = first // Cc
-                assert p // w == r and (r, p % w) not in when
-                when[(r, p % w)] = t
-        assert len(when) == h * w
-        for (r, c), t in when.items():
-            deps = [(r + i - 3, c + j - 2) for i in range(4) for j in range(4) if not (i == 3 and j >= 2)]
-            for rr, cc in deps:
-                if 0 <= rr < h and 0 <= cc < w:
-                    assert when[(rr, cc)] < t, ((r, c), (rr, cc))
-            if c > 0:                                           # stream predecessor: the pixel to the left (same row)
-                assert when[(r, c - 1)] == t - 1
-    hi = ldic_b200.Net((1, 64, 64, 3), (1, 64, 64, 3), True, False)
-    assert hi.y_streams(32, 48) % 32 == 0 and (48 * (hi.N - hi.M)) % (32 * 48 * (hi.N - hi.M) // hi.y_streams(32, 48)) == 0
+    for high in (False, True):
+        net = ldic_b200.Net((1, 64, 64, 3), (1, 64, 64, 3), high, False)
+        Cc, G = net.N - net.M, net.y_groups()
+        cg = Cc // G
+        assert G == 4 and cg * G == Cc
+        for h, w in [(4, 4), (8, 12), (32, 48), (16, 16), (5, 7)]:
+            S = net.y_streams(h, w)
+            assert S % (h * G) == 0 and (h * w * Cc) % S == 0
+            run = h * w * Cc // S                               # symbols per stream
+            assert (w * cg) % run == 0 and run <= 65535         # a whole number of streams per (row, column group)
+            table = net._wavefront_table(h, w, "cpu").numpy()
+            T = w + 2 * (h - 1)
+            assert table.shape == (T, h, G, 2)
+            when = {}
+            for t in range(T):
+                for r in range(h):
+                    if table[t, r, 0, 1] == 0:
+                        assert not table[t, r, :, 1].any()
+                        continue
+                    pix = set()
+                    for g in range(G):
+                        first, count = table[t, r, g]
+                        assert count == cg and (first - g * h * w * cg) % cg == 0
+                        p = (first - g * h * w * cg) // cg
+                        assert 0 <= p < h * w and first // run == (first + count - 1) // run      # inside one stream
+                        pix.add(int(p))
+                    assert len(pix) == 1
+                    p = pix.pop()
+                    assert p // w == r and (r, p % w) not in when
+                    when[(r, p % w)] = t
+            assert len(when) == h * w
+            for (r, c), t in when.items():
+                deps = [(r + i - 3, c + j - 2) for i in range(4) for j in range(4) if not (i == 3 and j >= 2)]
+                for rr, cc in deps:
+                    if 0 <= rr < h and 0 <= cc < w:
+                        assert when[(rr, cc)] < t, ((r, c), (rr, cc))
+                if c > 0:                                       # stream predecessor: the pixel to the left (same row)
+                    assert when[(r, c - 1)] == t - 1
+
+
+def test_column_groups_reorder_only():
+    """col_groups changes the ORDER in which a segment is coded (and one header word), nothing else."""
+    rng = np.random.default_rng(5)
+    rows, cols, G, S = 6, 8, 4, 6
+    mu = (rng.standard_normal(rows * cols) * 2).astype(np.float32)
+    sigma = np.exp(rng.standard_normal(rows * cols) * 0.5).astype(np.float32)
+    k = np.rint(mu + sigma * rng.standard_normal(rows * cols)).astype(np.int64)
+    order = rr.group_order(rows, cols, G)
+    assert sorted(order.tolist()) == list(range(rows * cols)) and order[:3].tolist() == [0, 1, 8]
+    blob = rr.encode_segment(k[order], mu[order], sigma[order], S, groups=G)
+    back = np.empty_like(k)
+    back[order] = rr.decode_segment(blob, mu[order], sigma[order], S, groups=G)
+    assert np.array_equal(back, k)
+    plain = rr.encode_segment(k[order], mu[order], sigma[order], S)
+    assert blob[:24] == plain[:24] and blob[24:28] == (4).to_bytes(4, "little") and blob[28:] == plain[28:]
+    with pytest.raises(ValueError):
+        rr.decode_segment(blob, mu[order], sigma[order], S)
