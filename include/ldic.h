@@ -184,7 +184,8 @@ enum {
                           aux1 = M | s << 8 | x_org << 12 | w_in << 16.  s > 0: x is stored SHEARED by s columns per row --
                           patch cell (i,j) of the pixel at (y,x) is read from column x + j - 2 + s (i - 3); w_in > 0: x is
                           w_in columns wide and the W output columns start at its column x_org (the wavefront decoder
-                          computes one column of a 10-column band)                                                     */
+                          computes one column of a 10-column band); aux0 = N | pitch << 12 with pitch > 0: that band is a
+                          column slice of a wider image with `pitch` pixels per row                                    */
   LDIC_CTX_CONV2 = 9,  /* [P,4,4,N] -> [P,2,2,N]   Conv2d(N,N,3,2,1)  :297                                           */
   LDIC_CTX_CONV3 = 10, /* [P,2,2,N] -> [P,2,2,N]   Conv2d(N,N,3,1,1)  :299                                           */
   LDIC_CTX_FC = 11,    /* [P,2,2,N] -> [P,1,2,Cout_pad] fp32 (mu | log sigma), Linear(4N, 2*Cout) :302; Cout = N-M   */

@@ -1920,6 +1920,7 @@ struct Layer {          // everything derived from an LdicConvDesc
   int cin_map, map_N, map_M;   // 0: ci = k - cin_offset;  1: context conv1 (y | h2 channel segments)
   int Kw;                      // K extent (columns) of one packed weight block
   long long vC, vW, vH, vN;    // activation view behind the TMA map (mode 1 splits vW into parity x vW/2)
+  long long vPitch;            // pixels between consecutive rows of the view in memory (= vW unless the input is a column band)
   int Wg, Hg, Bg;              // pixel grid the M tiles walk over
   int oB, Ho, Wo, Cs;          // output tensor [oB, Ho, Wo, Cs]
   long long out_sN, out_sY, out_sX;
@@ -2049,10 +2050,18 @@ int build_layer(const LdicConvDesc* d, Layer* L) {
       // aux1 = M | shear << 8 | x_org << 12 | w_in << 16.  shear: the input image is stored sheared by `shear` columns per
       // row (column offset + shear * row offset); w_in > 0: the input image is w_in columns wide and the output grid (d->W
       // columns) starts at its column x_org -- the wavefront decoder computes ONE column of a 10-column band.
-      const int N = d->aux0, M = d->aux1 & 0xff, shear = (d->aux1 >> 8) & 0xf, x_org = (d->aux1 >> 12) & 0xf, w_in = d->aux1 >> 16;
+      // aux0 = N | pitch << 12: pitch > 0 = the band is a view into a wider image with `pitch` pixels per row.
+      const int N = d->aux0 & 0xfff, pitch = d->aux0 >> 12;
+      const int M = d->aux1 & 0xff, shear = (d->aux1 >> 8) & 0xf, x_org = (d->aux1 >> 12) & 0xf, w_in = d->aux1 >> 16;
       if (w_in) {
         if (w_in < x_org + d->W) return fail(LDIC_EINVAL, "ctx conv1: the output columns must lie inside the input band");
         L->vW = w_in;
+        if (pitch) {
+          if (pitch < w_in) return fail(LDIC_EINVAL, "ctx conv1: row pitch smaller than the band");
+          L->vPitch = pitch;
+        }
+      } else if (pitch) {
+        return fail(LDIC_EINVAL, "ctx conv1: a row pitch needs a band (w_in)");
       }
       if (N <= 0 || N % 64 || M < 0 || M >= N || d->Cin != 2 * N - M || d->Cin_pad != 2 * N || d->Cout != N || d->Cout_pad != N)
         return fail(LDIC_EINVAL, "ctx conv1: need aux0=N (multiple of 64), aux1=M, Cin=2N-M, Cin_pad=2N, Cout=Cout_pad=N");
@@ -2568,8 +2577,9 @@ int build_plan(const LdicConvDesc* d, const void* x, const void* w_packed, const
 
   const cuuint64_t C = (cuuint64_t)L.vC;
   {
+    const cuuint64_t pitch = (cuuint64_t)(L.vPitch ? L.vPitch : L.vW);
     cuuint64_t dims[4] = {C, (cuuint64_t)L.vW, (cuuint64_t)L.vH, (cuuint64_t)L.vN};
-    cuuint64_t str[3] = {C * 2, (cuuint64_t)L.vW * C * 2, (cuuint64_t)L.vH * L.vW * C * 2};
+    cuuint64_t str[3] = {C * 2, pitch * C * 2, (cuuint64_t)L.vH * pitch * C * 2};
     if (strided) {
       cuuint32_t box[4] = {64, (cuuint32_t)(2 * P.TW), (cuuint32_t)(2 * P.TH), (cuuint32_t)P.TN};
       cuuint32_t es[4] = {1, 2, 2, 1};

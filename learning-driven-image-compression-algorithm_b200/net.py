@@ -515,7 +515,7 @@ class Net(nn.Module):
             L0s = self.prediction_model.sheared_conv1(N, M, SH)
             for t in range(T):
                 r0, r1 = max(0, (t - w + 2) // 2), min(h - 1, t // 2)
-                o1 = L0s.column_of_band(x_s[:, :, t:t + BAND].contiguous(), LEFT)            # (B*h, 4, 4, N): the wavefront's pixels
+                o1 = L0s.column_of_band(x_s[:, :, t:t + BAND], LEFT)                         # (B*h, 4, 4, N): the wavefront's pixels
                 ctx = L[3](L[2](L[1](o1)))                                                   # (B*h, 1, 2, Cp)
                 rs, so = 2 * ctx.shape[-1], ctx.shape[-1]
                 dec.decode(table[t, r0:r1 + 1], (r1 - r0 + 1) * G, y_hat, v_hat_rs=Cc, v_hat_bf16=x_s, vb_rs=2 * N, vb_off=M,

@@ -809,13 +809,19 @@ class ConvTC:
         if self.kind != _lib.LDIC_CTX_CONV1:
             raise LdicError("column_of_band: context conv 1 only")
         _req(x, torch.bfloat16, "x")
-        if x.dim() != 4 or x.shape[-1] != self.cin_pad or not x.is_contiguous():
-            raise LdicError(f"conv input must be contiguous NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
-        B, H, w_in, _ = x.shape
-        if not (0 <= x_org < 16 and x_org < w_in < 32768 and self.aux[1] < (1 << 12)):
+        if x.dim() != 4 or x.shape[-1] != self.cin_pad:
+            raise LdicError(f"conv input must be NHWC bf16 with {self.cin_pad} channels, got {tuple(x.shape)}")
+        B, H, w_in, Cp = x.shape
+        # the band may be a column slice x_full[:, :, t:t+w_in] of a wider contiguous image: only the row pitch differs
+        pitch = x.stride(1) // Cp
+        if (x.stride(3) != 1 or x.stride(2) != Cp or x.stride(1) != pitch * Cp or x.stride(0) != H * pitch * Cp or pitch < w_in
+                or pitch >= (1 << 19)):
+            raise LdicError("column_of_band: x must be a contiguous NHWC image or a column slice of one")
+        if not (0 <= x_org < 16 and x_org < w_in < 32768 and self.aux[1] < (1 << 12) and self.aux[0] < (1 << 12)):
             raise LdicError("column_of_band: bad band geometry")
         out = torch.empty(self.out_dims(B, H, 1), dtype=torch.float32 if self.out_f32 else torch.bfloat16, device=x.device)
         d = self._desc(B, H, 1, 0)
+        d.aux0 = int(self.aux[0]) | ((int(pitch) << 12) if pitch != w_in else 0)
         d.aux1 = int(self.aux[1]) | (int(x_org) << 12) | (int(w_in) << 16)
         check(_L().ldic_conv_forward(C.byref(d), _ptr(x), _ptr(self.w_packed), _ptr(self.bias_packed),
                                      _ptr(self.gamma_bf16), _ptr(self.beta_tiled), _ptr(out), _stream()), "ldic_conv_forward")
