@@ -48,7 +48,8 @@ LDIC_API long long ldic_launch_count(void);
 /* 0 when device `dev` is compute capability 10.x, LDIC_ENOTSUP otherwise. */
 LDIC_API int ldic_check_device(int dev);
 /* Tuning / diagnostic switches.  They are read from the environment ONCE, when the library is loaded
- * (LDIC_DEBUG_NOSTORE, LDIC_DEBUG_TIMING, LDIC_GDN_INSERT, LDIC_STAGES, LDIC_TAIL_WIDE, LDIC_LIK_GRID); no
+ * (LDIC_DEBUG_NOSTORE, LDIC_DEBUG_TIMING, LDIC_GDN_INSERT, LDIC_STAGES, LDIC_TAIL_WIDE, LDIC_LIK_GRID, LDIC_FIRST_EPI,
+ * LDIC_FIRST_INSERT, LDIC_FIRST_TMA_STORE: first-layer epilogue warps / ring order of its x^2 slots / TMA stores); no
  * entry point calls getenv on its hot path.  ldic_set_tuning changes one at run time (tests, A/B runs): key is
  * the environment name without the LDIC_ prefix in lower case ("tail_wide", "stages", ...); returns the previous
  * value or LDIC_EINVAL.  Changing a switch invalidates the cached launch plans.                            */
