@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return obj
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    link = [_nvcc(), "--shared", "-Xcompiler", "-fPIC"] + objs + ["-o", LIB_PATH]
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC"] + objs + ["-o", LIB_PATH]
     if verbose:
         print(" ".join(link), file=sys.stderr)
     subprocess.run(link, check=True)
